@@ -1,0 +1,152 @@
+/* nsb200.h -- C ABI of libnsb200.so: B200-native (sm_100a) FV1 / FVCR defect + Jacobian assembly of the
+ * incompressible Navier-Stokes system, drop-in for the element-assembly path of UG4's NavierStokes plugin.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the UG4 plugin tree).
+ * The library collapses ugcore's element loop (gather LocalVector -> prep_elem -> add_*_elem ->
+ * AddLocalMatrixToGlobal/AddLocalVector) into device kernels; see DESIGN.md and INTEGRATION.md.
+ *
+ * All functions return 0 on success, a negative nsb_status otherwise; nsb_last_error(ctx) gives the text
+ * (the reference throws UG_THROW at the same conditions).  No CPU fallback exists: every compute entry
+ * point fails with NSB_ERR_CUDA when no device is usable.
+ */
+#ifndef NSB200_H
+#define NSB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsb_ctx nsb_ctx;
+
+typedef enum {
+    NSB_OK = 0,
+    NSB_ERR_INVALID = -1,      /* bad argument / call order                                             */
+    NSB_ERR_SETUP = -2,        /* prep_elem_loop validation failed (stabilisation / upwind / ... unset)  */
+    NSB_ERR_CUDA = -3,         /* CUDA runtime error or no device                                        */
+    NSB_ERR_GEOMETRY = -4,     /* element-level failure on device (ray search found no cut side, ...)    */
+    NSB_ERR_UNSUPPORTED = -5
+} nsb_status;
+
+enum { NSB_TRI = 0, NSB_QUAD = 1, NSB_TET = 2, NSB_HEX = 3 };
+enum { NSB_DISC_FV1 = 0, NSB_DISC_FVCR = 1 };
+/* upwind_interface.cpp:43-62 (CreateNavierStokesUpwind: "no","full","skewed","lps","pos") */
+enum { NSB_UPWIND_UNSET = 0, NSB_UPWIND_NO = 1, NSB_UPWIND_FULL = 2, NSB_UPWIND_SKEWED = 3,
+       NSB_UPWIND_LPS = 4, NSB_UPWIND_POSITIVE = 5 };
+/* fv1/stabilization.cpp:46-57 (CreateNavierStokesStabilization: "fields","flow") + WithoutStabilization */
+enum { NSB_STAB_UNSET = -1, NSB_STAB_FIELDS = 0, NSB_STAB_FLOW = 1, NSB_STAB_NONE = 2 };
+/* fv1/stabilization.cpp:86-100 (set_diffusion_length: "raw","fivepoint","cor") */
+enum { NSB_DIFF_RAW = 0, NSB_DIFF_FIVEPOINT = 1, NSB_DIFF_COR = 2 };
+
+/* which element contributions to assemble (bitmask): the IElemDisc slots registered at
+ * fv1/navier_stokes_fv1.cpp:1553-1572 / fvcr/navier_stokes_fvcr.cpp:825-843 */
+enum { NSB_JAC_A = 1, NSB_DEF_A = 2, NSB_JAC_M = 4, NSB_DEF_M = 8, NSB_RHS = 16 };
+
+/* how element contributions reach the global CSR matrix / defect vector */
+enum {
+    NSB_SCATTER_GATHER = 0,    /* owner-computes: one warp per matrix row block, written once, deterministic */
+    NSB_SCATTER_COLORED = 1,   /* element kernel, one launch per colour of a greedy element colouring, deterministic */
+    NSB_SCATTER_ATOMIC = 2     /* element kernel, red.global.add.f64 */
+};
+
+enum { NSB_HOST = 0, NSB_DEVICE = 1 };   /* where u / values / defect pointers live */
+
+/* State of NavierStokesFV1 / NavierStokesFVCR and their bases that the element routines read.
+ * Defaults (nsb_params_default) mirror navier_stokes_base.cpp:53-67,
+ * incompressible_navier_stokes_base.cpp:53-66, fv1/navier_stokes_fv1.cpp:62-87,
+ * fvcr/navier_stokes_fvcr.cpp:63-88, fv1/stabilization.h:321-325. */
+typedef struct {
+    int32_t disc;            /* NSB_DISC_*                                                            */
+    int32_t conv_upwind;     /* set_upwind(name)            fv1/navier_stokes_fv1.h:213-215            */
+    int32_t stab;            /* set_stabilization(name)     fv1/navier_stokes_fv1.h:190-199            */
+    int32_t stab_upwind;     /* stab->set_upwind(); 0 = "not set" (auto-wired from conv_upwind like the
+                                reference's set_upwind/set_stabilization string overloads)            */
+    int32_t diff_length;     /* set_diffusion_length(name)                                            */
+    int32_t stokes;          /* set_stokes      incompressible_navier_stokes_plugin.cpp:244-266        */
+    int32_t laplace;         /* set_laplace                                                            */
+    int32_t peclet_blend;    /* set_peclet_blend                                                       */
+    int32_t pac_upwind;      /* set_pac_upwind  fv1/navier_stokes_fv1.h:217-225                        */
+    int32_t defect_upwind;   /* FVCR set_defect_upwind      fvcr/navier_stokes_fvcr.cpp:82             */
+    int32_t has_source;      /* set_source given                                                       */
+    int32_t kin_visc_set, density_set;   /* prep_elem_loop throws when unset (:169-181)               */
+    int32_t reserved;
+    double  exact_jacobian;  /* set_exact_jacobian(bool|number) -> m_bFullNewtonFactor                 */
+    double  grad_div;        /* FVCR set_grad_div                                                      */
+    double  kin_visc;        /* set_kinematic_viscosity(number)                                        */
+    double  density;         /* set_density(number), default 1                                         */
+    double  source[3];       /* set_source(vector)                                                     */
+} nsb_params;
+
+/* Local time series handed to the element routines by ugcore's instationary assembling
+ * (IElemDisc::local_time_solutions(); read at fv1/navier_stokes_fv1.cpp:268-280, 617-629). */
+typedef struct {
+    const double *sol0;      /* solution(0): current time point, NULL when stationary                 */
+    const double *sol1;      /* solution(1): previous time point                                       */
+    double dt;               /* time(0) - time(1)                                                      */
+} nsb_time_series;
+
+int  nsb_create(int device, nsb_ctx **out);
+void nsb_destroy(nsb_ctx *ctx);
+const char *nsb_last_error(const nsb_ctx *ctx);       /* also valid with ctx == NULL (creation errors)  */
+/* use an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own stream */
+int  nsb_set_stream(nsb_ctx *ctx, void *cuda_stream);
+
+void nsb_params_default(nsb_params *p);
+int  nsb_set_params(nsb_ctx *ctx, const nsb_params *p);
+
+/* Upload grid connectivity once (replaces the per-element FillCornerCoordinates + dd->indices() of
+ * ugcore's element loop) and build on the host: node->element adjacency, the block-CSR pattern (full
+ * element coupling incl. explicit zeros, dof = node*(dim+1)+fct), the element->CSR scatter map and a greedy
+ * element colouring; then precompute the SCV-volume table on device.  conn: [n_elem][nsh] int32,
+ * coords: [n_node][dim] double (host pointers, borrowed for the call). */
+int  nsb_upload_mesh(nsb_ctx *ctx, int elem_type, int64_t n_elem, int64_t n_node,
+                     const int32_t *conn, const double *coords);
+/* FVCR variant: additionally elem_sides [n_elem][nside] (global side ids; side k of an element is its
+ * reference side k). dofs: side*dim+d, then n_side*dim + elem for the pressure. */
+int  nsb_upload_mesh_fvcr(nsb_ctx *ctx, int elem_type, int64_t n_elem, int64_t n_node, int64_t n_side,
+                          const int32_t *conn, const int32_t *elem_sides, const double *coords);
+
+int64_t nsb_num_dofs(const nsb_ctx *ctx);
+int64_t nsb_nnz(const nsb_ctx *ctx);
+int     nsb_num_colors(const nsb_ctx *ctx);
+/* scalar CSR pattern (rows sorted), so the host SparseMatrix can adopt the identical sparsity */
+int  nsb_get_csr(const nsb_ctx *ctx, int64_t *rowptr /*[ndof+1]*/, int32_t *colind /*[nnz]*/);
+
+/* prep_elem_loop (fv1/navier_stokes_fv1.cpp:136-199, fvcr/navier_stokes_fvcr.cpp:145-196): validates
+ * the set-up, returns NSB_ERR_SETUP with the reference's message when it would throw. */
+int  nsb_prep_elem_loop(nsb_ctx *ctx);
+
+/* The element loop.  values[nnz] / defect[ndof] := beta*old + scale_a*(A-part) + scale_m*(M-part),
+ * A-part = add_jac_A_elem / add_def_A_elem (- add_rhs_elem when NSB_RHS), M-part = add_jac_M_elem /
+ * add_def_M_elem, for all elements, scattered into the global CSR matrix / vector.
+ * u: evaluation point ([ndof]); ts: local time series or NULL (stationary).
+ * values / defect may be NULL when the corresponding bits are absent from `what`.
+ * location: NSB_HOST (buffers are copied in/out inside the call) or NSB_DEVICE (device pointers,
+ * asynchronous on the context's stream). */
+int  nsb_assemble(nsb_ctx *ctx, int what, int scatter_mode, const double *u, const nsb_time_series *ts,
+                  double scale_a, double scale_m, double beta, double *values, double *defect, int location);
+
+/* NSB_DEVICE calls are asynchronous: element-level failures (the reference's UG_THROW inside upwind /
+ * stabilisation code, upwind.cpp:354, stabilization.cpp:292,641) are latched on the device; this call
+ * synchronises and reports them (NSB_ERR_GEOMETRY). NSB_HOST calls do it implicitly. */
+int  nsb_check_errors(nsb_ctx *ctx);
+
+/* compat mode of the IElemDisc slots: local matrices/vectors of all elements, laid out
+ * like ugcore's LocalMatrix/LocalVector (index fct*nsh+sh): Jloc [n_elem][L][L], dloc [n_elem][L]. */
+int  nsb_local_contributions(nsb_ctx *ctx, int what, const double *u, const nsb_time_series *ts,
+                             double *Jloc, double *dloc, int location);
+
+/* interface exchange helpers for the multi-GPU path (replace pcl additive->unique sums on this path):
+ * out[i] = src[idx[i]]  /  dst[idx[i]] += in[i]   (device pointers, context stream) */
+int  nsb_pack(nsb_ctx *ctx, int64_t n, const int64_t *idx, const double *src, double *out);
+int  nsb_unpack_add(nsb_ctx *ctx, int64_t n, const int64_t *idx, const double *in, double *dst);
+
+/* instrumentation */
+int64_t nsb_launch_count(const nsb_ctx *ctx);          /* kernels launched by this context so far       */
+int  nsb_synchronize(nsb_ctx *ctx);
+const char *nsb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

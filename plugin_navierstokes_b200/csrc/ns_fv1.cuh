@@ -1,0 +1,703 @@
+// ns_fv1.cuh -- device-side building blocks of the FV1 (vertex-centred, Schneider-Raw stabilised)
+// incompressible Navier-Stokes element assembly for sm_100a.
+//
+// What is computed follows the UG4 NavierStokes plugin (file:line cited per function, relative to the
+// reference tree); how it is computed is organised for the GPU: every quantity that belongs to one
+// sub-control-volume face (SCVF, one integration point "ip") is produced by ONE lane in registers
+// (`ip_eval`), parked in shared memory as an `IpRec`, and consumed by lanes that each own one COLUMN
+// (corner k, function cf) of the local Jacobian (`jac_col`), so a flux derivative is evaluated once and
+// added to row `from` / subtracted from row `to` without cross-lane traffic.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "ref_tables.cuh"
+
+namespace nsb {
+
+enum { E_TRI = 0, E_QUAD = 1, E_TET = 2, E_HEX = 3 };
+enum { UPW_NONE = 0, UPW_NO = 1, UPW_FULL = 2, UPW_SKEWED = 3, UPW_LPS = 4, UPW_POSITIVE = 5 };
+enum { STAB_FIELDS = 0, STAB_FLOW = 1, STAB_NONE = 2 };
+enum { DIFF_RAW = 0, DIFF_FIVEPOINT = 1, DIFF_COR = 2 };
+enum { W_JAC_A = 1, W_DEF_A = 2, W_JAC_M = 4, W_DEF_M = 8, W_RHS = 16 };
+
+template <int E> struct ET;
+template <> struct ET<E_TRI>  { static constexpr int DIM = 2, NSH = 3, NIP = 3,  NSIDE = 3, NINC = 2; };
+template <> struct ET<E_QUAD> { static constexpr int DIM = 2, NSH = 4, NIP = 4,  NSIDE = 4, NINC = 2; };
+template <> struct ET<E_TET>  { static constexpr int DIM = 3, NSH = 4, NIP = 6,  NSIDE = 4, NINC = 3; };
+template <> struct ET<E_HEX>  { static constexpr int DIM = 3, NSH = 8, NIP = 12, NSIDE = 6, NINC = 3; };
+
+// Runtime-uniform state of the disc (NavierStokesFV1 members; fv1/navier_stokes_fv1.h:604-614).
+struct KParams {
+    int upw_stab, upw_conv, stab, diff_len;
+    int stokes, laplace, peclet, pac, time_dep, has_source;
+    int what, pad;
+    double exact_jac, visc, rho, dt, scale_a, scale_m;
+    double src[3];
+};
+
+#define NSB_DEV __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------------
+// P1 / Q1 Lagrange shapes (ugcore LagrangeP1) at a local point
+// ------------------------------------------------------------------------------------------------
+template <int E> NSB_DEV void lagrange(const double* xi, double* N)
+{
+    if constexpr (E == E_TRI) { N[0] = 1.0 - xi[0] - xi[1]; N[1] = xi[0]; N[2] = xi[1]; }
+    else if constexpr (E == E_TET) { N[0] = 1.0 - xi[0] - xi[1] - xi[2]; N[1] = xi[0]; N[2] = xi[1]; N[3] = xi[2]; }
+    else if constexpr (E == E_QUAD) {
+        const double x = xi[0], y = xi[1];
+        N[0] = (1 - x) * (1 - y); N[1] = x * (1 - y); N[2] = x * y; N[3] = (1 - x) * y;
+    } else {
+        const double x = xi[0], y = xi[1], z = xi[2];
+        const double a0 = (1 - x) * (1 - y), a1 = x * (1 - y), a2 = x * y, a3 = (1 - x) * y;
+        N[0] = a0 * (1 - z); N[1] = a1 * (1 - z); N[2] = a2 * (1 - z); N[3] = a3 * (1 - z);
+        N[4] = a0 * z;       N[5] = a1 * z;       N[6] = a2 * z;       N[7] = a3 * z;
+    }
+}
+
+template <int E> NSB_DEV void lagrange_grad(const double* xi, double (*dN)[ET<E>::DIM])
+{
+    if constexpr (E == E_TRI) { dN[0][0] = -1; dN[0][1] = -1; dN[1][0] = 1; dN[1][1] = 0; dN[2][0] = 0; dN[2][1] = 1; }
+    else if constexpr (E == E_TET) {
+        dN[0][0] = -1; dN[0][1] = -1; dN[0][2] = -1; dN[1][0] = 1; dN[1][1] = 0; dN[1][2] = 0;
+        dN[2][0] = 0; dN[2][1] = 1; dN[2][2] = 0; dN[3][0] = 0; dN[3][1] = 0; dN[3][2] = 1;
+    } else if constexpr (E == E_QUAD) {
+        const double x = xi[0], y = xi[1];
+        dN[0][0] = -(1 - y); dN[0][1] = -(1 - x); dN[1][0] = (1 - y); dN[1][1] = -x;
+        dN[2][0] = y;        dN[2][1] = x;        dN[3][0] = -y;      dN[3][1] = (1 - x);
+    } else {
+        const double x = xi[0], y = xi[1], z = xi[2];
+        const double fx[2] = {1 - x, x}, fy[2] = {1 - y, y}, fz[2] = {1 - z, z};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int bx = (k & 1) ^ ((k >> 1) & 1), by = (k >> 1) & 1, bz = (k >> 2) & 1;
+            dN[k][0] = (bx ? 1.0 : -1.0) * fy[by] * fz[bz];
+            dN[k][1] = fx[bx] * (by ? 1.0 : -1.0) * fz[bz];
+            dN[k][2] = fx[bx] * fy[by] * (bz ? 1.0 : -1.0);
+        }
+    }
+}
+
+template <int DIM> NSB_DEV double dotv(const double* a, const double* b)
+{
+    double s = a[0] * b[0];
+#pragma unroll
+    for (int d = 1; d < DIM; d++) s += a[d] * b[d];
+    return s;
+}
+template <int DIM> NSB_DEV double dist2(const double* a, const double* b)
+{
+    double s = 0;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) { const double t = a[d] - b[d]; s += t * t; }
+    return s;
+}
+NSB_DEV void cross3(double* o, const double* a, const double* b)
+{ o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; }
+
+// inverse of a DIM x DIM matrix; returns the determinant
+template <int DIM> NSB_DEV double inv_mat(const double (*a)[DIM], double (*inv)[DIM])
+{
+    if constexpr (DIM == 2) {
+        const double det = a[0][0] * a[1][1] - a[0][1] * a[1][0], r = 1.0 / det;
+        inv[0][0] = a[1][1] * r; inv[0][1] = -a[0][1] * r; inv[1][0] = -a[1][0] * r; inv[1][1] = a[0][0] * r;
+        return det;
+    } else {
+        const double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1];
+        const double c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+        const double c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+        const double det = a[0][0] * c00 + a[0][1] * c01 + a[0][2] * c02, r = 1.0 / det;
+        inv[0][0] = c00 * r; inv[1][0] = c01 * r; inv[2][0] = c02 * r;
+        inv[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * r;
+        inv[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * r;
+        inv[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * r;
+        inv[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * r;
+        inv[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * r;
+        inv[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * r;
+        return det;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FV1Geometry of one SCVF (ugcore FV1Geometry::update, called from prep_elem,
+// fv1/navier_stokes_fv1.cpp:208-248; conventions SURVEY.md App. B-2)
+// ------------------------------------------------------------------------------------------------
+template <int E> struct IpGeo {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    double n[DIM], xip[DIM], N[NSH], G[NSH][DIM], ds;
+    int from, to;
+};
+
+// x: element corner coordinates [NSH][DIM] (shared memory)
+template <int E> NSB_DEV void ip_geometry(const double* __restrict__ x, int ip, IpGeo<E>& g)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    const int f = tab::EDGE[E][ip][0], t = tab::EDGE[E][ip][1];
+    g.from = f; g.to = t;
+    double cen[DIM], c0[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) s += x[k * DIM + d];
+        cen[d] = s * (1.0 / NSH);
+        c0[d] = 0.5 * (x[f * DIM + d] + x[t * DIM + d]);
+    }
+    if constexpr (DIM == 2) {
+        // SCVF corners [edge midpoint, barycentre]; n = (dy, -dx) of c1 - c0
+        g.n[0] = cen[1] - c0[1]; g.n[1] = -(cen[0] - c0[0]);
+        g.xip[0] = 0.5 * (c0[0] + cen[0]); g.xip[1] = 0.5 * (c0[1] + cen[1]);
+        g.ds = 0.0;
+    } else {
+        // SCVF corners [edge midpoint, centre of face A, barycentre, centre of face B]
+        const int fa = tab::SCVF_FA[E][ip], fb = tab::SCVF_FB[E][ip];
+        constexpr int NFC = (E == E_TET) ? 3 : 4;
+        double c1[3] = {0, 0, 0}, c3[3] = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < NFC; q++) {
+            const int ka = tab::SIDE[E][fa][q], kb = tab::SIDE[E][fb][q];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { c1[d] += x[ka * 3 + d]; c3[d] += x[kb * 3 + d]; }
+        }
+        double a[3], b[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            c1[d] *= (1.0 / NFC); c3[d] *= (1.0 / NFC);
+            a[d] = cen[d] - c0[d]; b[d] = c3[d] - c1[d];
+            g.xip[d] = 0.25 * (c0[d] + c1[d] + cen[d] + c3[d]);
+        }
+        cross3(g.n, a, b);
+#pragma unroll
+        for (int d = 0; d < 3; d++) g.n[d] *= 0.5;
+        g.ds = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];      // |corner(0) - corner(2)|^2
+    }
+    // shapes and global gradients at the local ip
+    double xi[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) xi[d] = tab::LIP[E][ip][d];
+    lagrange<E>(xi, g.N);
+    double dN[NSH][DIM];
+    lagrange_grad<E>(xi, dN);
+    double JT[DIM][DIM], JI[DIM][DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; i++)
+#pragma unroll
+        for (int j = 0; j < DIM; j++) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < NSH; k++) s += dN[k][i] * x[k * DIM + j];
+            JT[i][j] = s;
+        }
+    inv_mat<DIM>(JT, JI);
+#pragma unroll
+    for (int k = 0; k < NSH; k++)
+#pragma unroll
+        for (int j = 0; j < DIM; j++) {
+            double s = 0;
+#pragma unroll
+            for (int i = 0; i < DIM; i++) s += JI[j][i] * dN[k][i];
+            g.G[k][j] = s;
+        }
+}
+
+// SCV volume of corner `co` (ugcore FV1Geometry SCV::volume; App. B-2). Simplices: |T|/(dim+1).
+template <int E> NSB_DEV double scv_volume(const double* __restrict__ x, int co)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    if constexpr (E == E_TRI) {
+        const double a = (x[2] - x[0]) * (x[5] - x[1]) - (x[4] - x[0]) * (x[3] - x[1]);
+        return fabs(a) * (0.5 / 3.0);
+    } else if constexpr (E == E_TET) {
+        double a[3], b[3], c[3], t[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { a[d] = x[3 + d] - x[d]; b[d] = x[6 + d] - x[d]; c[d] = x[9 + d] - x[d]; }
+        cross3(t, a, b);
+        return fabs(dotv<3>(t, c)) * (1.0 / 24.0);
+    } else if constexpr (E == E_QUAD) {
+        const int nx = (co + 1) & 3, pv = (co + 3) & 3;
+        double bc[2], m1[2], m2[2];
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            bc[d] = 0.25 * (x[d] + x[2 + d] + x[4 + d] + x[6 + d]);
+            m1[d] = 0.5 * (x[co * 2 + d] + x[nx * 2 + d]);
+            m2[d] = 0.5 * (x[pv * 2 + d] + x[co * 2 + d]);
+        }
+        const double ax = bc[0] - x[co * 2], ay = bc[1] - x[co * 2 + 1], bx = m2[0] - m1[0], by = m2[1] - m1[1];
+        return 0.5 * fabs(ax * by - ay * bx);
+    } else {
+        // trilinear image of the reference octant adjacent to corner `co`; exact volume by the
+        // long-diagonal formula
+        const int cx = (co & 1) ^ ((co >> 1) & 1), cy = (co >> 1) & 1, cz = (co >> 2) & 1;
+        const double lo[3] = {cx ? 0.5 : 0.0, cy ? 0.5 : 0.0, cz ? 0.5 : 0.0};
+        double p[8][3];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int qx = (q & 1) ^ ((q >> 1) & 1), qy = (q >> 1) & 1, qz = (q >> 2) & 1;
+            const double xi[3] = {lo[0] + 0.5 * qx, lo[1] + 0.5 * qy, lo[2] + 0.5 * qz};
+            double N[8];
+            lagrange<E_HEX>(xi, N);
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) s += N[k] * x[k * 3 + d];
+                p[q][d] = s;
+            }
+        }
+        double a[3], b[3], c[3], t[3], v = 0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) { a[d] = (p[6][d] - p[1][d]) + (p[7][d] - p[0][d]); b[d] = p[6][d] - p[3][d]; c[d] = p[2][d] - p[0][d]; }
+        cross3(t, b, c); v += dotv<3>(a, t);
+#pragma unroll
+        for (int d = 0; d < 3; d++) { a[d] = p[7][d] - p[0][d]; b[d] = (p[6][d] - p[3][d]) + (p[5][d] - p[0][d]); c[d] = p[6][d] - p[4][d]; }
+        cross3(t, b, c); v += dotv<3>(a, t);
+#pragma unroll
+        for (int d = 0; d < 3; d++) { a[d] = p[6][d] - p[1][d]; b[d] = p[5][d] - p[0][d]; c[d] = (p[6][d] - p[4][d]) + (p[2][d] - p[0][d]); }
+        cross3(t, b, c); v += dotv<3>(a, t);
+        return fabs(v) * (1.0 / 12.0);
+    }
+    (void)DIM; (void)NSH;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ElementSideRayIntersection (ugcore geometry_util.h): sides in reference order,
+// quadrilateral sides as triangles (p0,p1,p2),(p0,p2,p3); first hit with t<=0 (upwind search) wins.
+// Call sites: upwind.cpp:351,547.
+// ------------------------------------------------------------------------------------------------
+#define NSB_RAY_SMALL 1e-12
+template <int E> NSB_DEV bool side_ray_cut(const double* __restrict__ x, const double* from, const double* dir,
+                                           int& side_out, double* gcut, double* lcut)
+{
+    constexpr int DIM = ET<E>::DIM, NSIDE = ET<E>::NSIDE;
+    if constexpr (DIM == 2) {
+        const double dn = sqrt(dir[0] * dir[0] + dir[1] * dir[1]);
+        for (int s = 0; s < NSIDE; s++) {
+            const int p0 = tab::SIDE[E][s][0], p1 = tab::SIDE[E][s][1];
+            const double ex = x[p1 * 2] - x[p0 * 2], ey = x[p1 * 2 + 1] - x[p0 * 2 + 1];
+            const double det = dir[0] * (-ey) + dir[1] * ex;
+            if (!(fabs(det) > NSB_RAY_SMALL * dn * sqrt(ex * ex + ey * ey))) continue;
+            const double rx = x[p0 * 2] - from[0], ry = x[p0 * 2 + 1] - from[1];
+            const double t = (rx * (-ey) + ry * ex) / det;
+            const double bc = (dir[0] * ry - dir[1] * rx) / det;
+            if (!(bc >= -NSB_RAY_SMALL && bc <= 1.0 + NSB_RAY_SMALL)) continue;
+            if (!(t <= 0.0)) continue;
+#pragma unroll
+            for (int d = 0; d < 2; d++) {
+                gcut[d] = from[d] + t * dir[d];
+                lcut[d] = (1 - bc) * tab::CORNER[E][p0][d] + bc * tab::CORNER[E][p1][d];
+            }
+            side_out = s;
+            return true;
+        }
+        return false;
+    } else {
+        const double dn = sqrt(dotv<3>(dir, dir));
+        constexpr int NTRI = (E == E_HEX) ? 2 : 1;
+        for (int s = 0; s < NSIDE; s++) {
+            const int p0 = tab::SIDE[E][s][0];
+#pragma unroll
+            for (int k = 0; k < NTRI; k++) {
+                const int p1 = tab::SIDE[E][s][1 + k], p2 = tab::SIDE[E][s][2 + k];
+                double e1[3], e2[3], r[3], nrm[3], q[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) { e1[d] = x[p1 * 3 + d] - x[p0 * 3 + d]; e2[d] = x[p2 * 3 + d] - x[p0 * 3 + d]; r[d] = from[d] - x[p0 * 3 + d]; }
+                cross3(nrm, e1, e2);
+                const double det = -dotv<3>(dir, nrm);
+                if (!(fabs(det) > NSB_RAY_SMALL * dn * sqrt(dotv<3>(nrm, nrm)))) continue;
+                const double t = dotv<3>(r, nrm) / det;
+                cross3(q, r, dir);
+                const double b1 = dotv<3>(e2, q) / det, b2 = -dotv<3>(e1, q) / det;
+                if (!(b1 >= -NSB_RAY_SMALL && b2 >= -NSB_RAY_SMALL && b1 + b2 <= 1.0 + NSB_RAY_SMALL)) continue;
+                if (!(t <= 0.0)) continue;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    gcut[d] = from[d] + t * dir[d];
+                    lcut[d] = (1 - b1 - b2) * tab::CORNER[E][p0][d] + b1 * tab::CORNER[E][p1][d] + b2 * tab::CORNER[E][p2][d];
+                }
+                side_out = s;
+                return true;
+            }
+        }
+        return false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Upwind shapes of ONE ip for the upwinds without ip-shapes (upwind.cpp:52-80 No, :133-172 Full,
+// :337-430 Skewed, :505-575 LinearProfileSkewed). `type` folds away when it is a compile-time constant.
+// returns false if the ray search found no cut side (reference throws, upwind.cpp:354).
+// ------------------------------------------------------------------------------------------------
+template <int E> NSB_DEV bool upwind_ip(int type, const double* __restrict__ x, const IpGeo<E>& g,
+                                        const double* vel, double* up, double& len)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    if (type == UPW_NO) {
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = g.N[k];
+        len = 1.0;
+        return true;
+    }
+#pragma unroll
+    for (int k = 0; k < NSH; k++) up[k] = 0.0;
+    if (type == UPW_FULL) {
+        const double flux = dotv<DIM>(g.n, vel);
+        const int co = flux > 0.0 ? g.from : g.to;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = (k == co) ? 1.0 : 0.0;
+        len = sqrt(dist2<DIM>(g.xip, x + co * DIM));
+        return true;
+    }
+    // skewed / linear profile skewed
+    if (sqrt(dotv<DIM>(vel, vel)) < 1e-14) { len = 1.0; return true; }
+    int side = 0; double gc[DIM], lc[DIM];
+    if (!side_ray_cut<E>(x, g.xip, vel, side, gc, lc)) { len = 1.0; return false; }
+    constexpr int NSC = (DIM == 2) ? 2 : (E == E_TET ? 3 : 4);
+    if (type == UPW_SKEWED) {
+        double mn = 1.79769313486231570e308; int best = 0;
+#pragma unroll
+        for (int i = 0; i < NSC; i++) {
+            const int co = tab::SIDE[E][side][i];
+            const double dd = dist2<DIM>(gc, x + co * DIM);
+            if (dd < mn) { mn = dd; best = co; }
+        }
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = (k == best) ? 1.0 : 0.0;
+        len = sqrt(dist2<DIM>(g.xip, x + best * DIM));
+    } else {
+        double Nc[NSH];
+        lagrange<E>(lc, Nc);
+        int mask = 0;
+#pragma unroll
+        for (int i = 0; i < NSC; i++) mask |= 1 << tab::SIDE[E][side][i];
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = ((mask >> k) & 1) ? Nc[k] : 0.0;
+        len = sqrt(dist2<DIM>(g.xip, gc));
+    }
+    return true;
+}
+
+// Diffusion length (fv1/diffusion_length.h:47-198). cor_* are the element-wide min/avg needed by COR.
+template <int DIM> NSB_DEV double diff_len_sq_inv(int type, double nn, double volf, double volt, double ds,
+                                                  double cor_minN, double cor_avgN, double cor_minD)
+{
+    double A = 0.5 * (volf + volt); A *= A;
+    if (type == DIFF_RAW)       return DIM == 2 ? 1.0 / (0.5 * A / nn + 3.0 * nn / 8.0) : 1.0 / (0.5 * A / nn + 3.0 * ds / 8.0);
+    if (type == DIFF_FIVEPOINT) return DIM == 2 ? 2.0 * nn / A + 8.0 / nn : 2.0 * nn / A + 8.0 * ds / nn;
+    return DIM == 2 ? 2.0 * cor_minN / A + 8.0 / (3.0 * cor_avgN) : 2.0 * cor_minN / A + 8.0 * cor_minD / (3.0 * cor_avgN);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Record of one ip, parked in shared memory between the per-ip phase and the column phase.
+// ------------------------------------------------------------------------------------------------
+template <int E> struct IpRec {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1;
+    double n[DIM];
+    double std[DIM];        // StdVel[ip]
+    double U[DIM];          // transported velocity after Peclet blend (UpwindVel)
+    double prod;            // (StdVel . n) * rho
+    double w;               // Peclet weight (1 if off)
+    double invdiag;         // 1/diag of the stabilisation's ip system (diagonal branch)
+    double F[NF];           // defect fluxes (momentum d, continuity)
+    double N[NSH];
+    double G[NSH][DIM];
+    double up[NSH];         // convective upwind shapes up_sh(ip,k) (+ ip-shape part folded in cvx)
+    double cvx[NSH];        // sum_ip2 N_k(ip2) up_ip(ip,ip2)   (Positive upwind only, else 0)
+    double sb[NSH];         // a*N_k + b*up_k (+ c*(down_k-up_k) for FLOW): diagonal-block numerator
+};
+
+// Stabilisation shape accessors. Diagonal branch: recomputed from the record
+// (stabilization.cpp:213-236 FIELDS, :536-582 FLOW, :826-849 none).
+template <int E> struct StabDiag {
+    static constexpr int DIM = ET<E>::DIM;
+    const IpRec<E>& r; int stab; double rho;
+    NSB_DEV double sv(int d, int d2, int k) const
+    {
+        if (stab == STAB_NONE) return d == d2 ? r.N[k] : 0.0;
+        if (stab == STAB_FIELDS) return d == d2 ? r.sb[k] * r.invdiag : 0.0;
+        if (d == d2) {
+            double s = r.sb[k];
+#pragma unroll
+            for (int q = 0; q < DIM; q++) if (q != d) s -= r.std[q] * r.G[k][q];
+            return s * r.invdiag;
+        }
+        return r.std[d] * r.G[k][d2] * r.invdiag;
+    }
+    NSB_DEV double sp(int d, int k) const
+    {
+        if (stab == STAB_NONE) return 0.0;
+        return -1.0 * r.G[k][d] / rho * r.invdiag;
+    }
+};
+// Dense branch: shapes live in shared memory arrays sv[ip][d][d2][k], sp[ip][d][k]
+template <int E> struct StabDense {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    const double* svp; const double* spp;       // already offset to this ip
+    NSB_DEV double sv(int d, int d2, int k) const { return svp[(d * DIM + d2) * NSH + k]; }
+    NSB_DEV double sp(int d, int k) const { return spp[d * NSH + k]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// One COLUMN (corner k, function cf) of the flux derivative of one ip: val[rf] is added to row
+// (rf, from) and subtracted from row (rf, to).  add_jac_A_elem, fv1/navier_stokes_fv1.cpp:317-594.
+// ------------------------------------------------------------------------------------------------
+template <int E, class SV>
+NSB_DEV void jac_col(const KParams& p, const IpRec<E>& r, const SV& S, bool connected, int k, int cf, double* val)
+{
+    constexpr int DIM = ET<E>::DIM, P = DIM;
+    const double nurho = p.visc * p.rho;
+    const bool conv_up = !p.stokes && !p.pac, conv_st = !p.stokes && p.pac;
+    if (cf < DIM) {
+        const int d2 = cf;
+        // diffusion :336-356
+        const double flux_sh = -1.0 * nurho * dotv<DIM>(r.G[k], r.n);
+#pragma unroll
+        for (int d1 = 0; d1 < DIM; d1++) {
+            double v = (d1 == d2) ? flux_sh : 0.0;
+            if (!p.laplace) v += -1.0 * nurho * r.G[k][d1] * r.n[d2];
+            val[d1] = v;
+        }
+        if (conv_st) {                                           // :400-417
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++)
+                if (connected || d1 == d2) val[d1] += r.prod * r.w * S.sv(d1, d2, k);
+        }
+        if (conv_up) {                                           // :430-457
+            const double c = (r.up[k] + r.cvx[k]) * (r.prod * r.w);
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++) if (d1 == d2) val[d1] += c;
+        }
+        if (!p.stokes && p.peclet) {                             // :460-468
+            const double c = r.prod * (1.0 - r.w) * r.N[k];
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++) if (d1 == d2) val[d1] += c;
+        }
+        if (!p.stokes && p.exact_jac != 0.0) {                   // :475-550
+            if (conv_st) {
+#pragma unroll
+                for (int d1 = 0; d1 < DIM; d1++) {
+                    double pv = 0.0;
+                    if (connected) {
+#pragma unroll
+                        for (int q = 0; q < DIM; q++) pv += r.w * S.sv(q, d2, k) * r.n[q];
+                    } else pv = S.sv(d1, d1, k) * r.n[d1];        // quirk :494-496
+                    pv *= p.exact_jac * p.rho;
+                    val[d1] += pv * r.U[d1];
+                }
+            }
+            if (conv_up) {
+                const double pv = r.w * r.up[k] * r.n[d2] * p.rho;   // quirk :528-529 (no factor, no ip part)
+#pragma unroll
+                for (int d1 = 0; d1 < DIM; d1++) val[d1] += pv * r.U[d1];
+            }
+            if (p.peclet) {
+                const double c = (1.0 - r.w) * r.N[k] * r.n[d2] * p.rho;   // quirk :542-545
+#pragma unroll
+                for (int d1 = 0; d1 < DIM; d1++) val[d1] += r.U[d1] * c;
+            }
+        }
+        // continuity row :561-584
+        if (connected) {
+            double cv = 0.0;
+#pragma unroll
+            for (int q = 0; q < DIM; q++) cv += S.sv(q, d2, k) * r.n[q] * p.rho;
+            val[P] = cv;
+        } else val[P] = S.sv(d2, d2, k) * r.n[d2] * p.rho;
+    } else {
+        // pressure column :363-368, :419-426, :504-516, :586-592
+#pragma unroll
+        for (int d1 = 0; d1 < DIM; d1++) {
+            double v = r.N[k] * r.n[d1];
+            if (conv_st) v += r.prod * r.w * S.sp(d1, k);
+            val[d1] = v;
+        }
+        if (conv_st && p.exact_jac != 0.0) {
+            double pp = 0.0;
+#pragma unroll
+            for (int q = 0; q < DIM; q++) pp += S.sp(q, k) * r.n[q];
+            pp *= p.exact_jac * p.rho;
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++) val[d1] += pp * r.U[d1];
+        }
+        double cp = 0.0;
+#pragma unroll
+        for (int q = 0; q < DIM; q++) cp += S.sp(q, k) * r.n[q] * p.rho;
+        val[P] = cp;
+    }
+}
+
+// peclet_blend, fv1/navier_stokes_fv1.cpp:871-892
+template <int E> NSB_DEV double peclet_blend(double* U, const IpGeo<E>& g, const double* __restrict__ x,
+                                             const double* std, double visc)
+{
+    constexpr int DIM = ET<E>::DIM;
+    const double Pe = dotv<DIM>(std, g.n) / dotv<DIM>(g.n, g.n) * sqrt(dist2<DIM>(x + g.to * DIM, x + g.from * DIM)) / visc;
+    const double Pe2 = Pe * Pe, w = Pe2 / (5.0 + Pe2);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) U[d] = w * U[d] + (1.0 - w) * std[d];
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Everything of one ip for the DIAGONAL stabilisation branch (upwinds without ip shapes):
+// geometry -> StdVel -> upwind(s) -> diffusion length -> FIELDS/FLOW/none closure -> defect fluxes.
+// Restates the common prologue (fv1/navier_stokes_fv1.cpp:261-314), stabilization.cpp:142-241 /
+// :456-587 / :805-850 and add_def_A_elem (:667-777) for one SCVF.
+//   x  [NSH][DIM] corner coordinates, u [NSH][NF] the `u` argument, s0/s1 the local time series
+//   (pSol/pOldSol; s0==u and s1==nullptr when stationary), vol [NSH] SCV volumes.
+// returns false when a ray search failed.
+// ------------------------------------------------------------------------------------------------
+template <int E> NSB_DEV bool ip_eval(const KParams& p, const double* __restrict__ x, const double* __restrict__ u,
+                                      const double* __restrict__ s0, const double* __restrict__ s1,
+                                      const double* __restrict__ vol, int ip,
+                                      double cor_minN, double cor_avgN, double cor_minD, IpRec<E>& r)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, P = DIM;
+    IpGeo<E> g;
+    ip_geometry<E>(x, ip, g);
+    bool ok = true;
+    double std[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) s += u[k * NF + d] * g.N[k];
+        std[d] = s;
+    }
+    // ---- stabilisation's upwind (+ downwind for FLOW) ----
+    double up[NSH], dn[NSH], uplen = 1.0, dnlen = 1.0;
+    if (!p.stokes) {
+        ok &= upwind_ip<E>(p.upw_stab, x, g, std, up, uplen);
+        if (p.stab == STAB_FLOW) {
+            double neg[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) neg[d] = -1.0 * std[d];
+            ok &= upwind_ip<E>(p.upw_stab, x, g, neg, dn, dnlen);
+        }
+    }
+    // ---- Schneider-Raw closure, diagonal branch ----
+    double stabvel[DIM], invdiag = 0.0;
+    if (p.stab == STAB_NONE) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) stabvel[d] = std[d];
+#pragma unroll
+        for (int k = 0; k < NSH; k++) r.sb[k] = 0.0;
+    } else {
+        const double nn = dotv<DIM>(g.n, g.n);
+        const double a = p.visc * diff_len_sq_inv<DIM>(p.diff_len, nn, vol[g.from], vol[g.to], g.ds, cor_minN, cor_avgN, cor_minD);
+        double b = 0.0, c = 0.0;
+        if (!p.stokes) {
+            const double nrm = sqrt(dotv<DIM>(std, std));
+            b = nrm / uplen;
+            if (p.stab == STAB_FLOW) c = nrm / (dnlen + uplen);
+        }
+        double diag = a;
+        if (p.time_dep) diag += 1.0 / p.dt;
+        if (!p.stokes) diag += b;
+        invdiag = 1.0 / diag;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) {
+            double sv = a * g.N[k];
+            if (!p.stokes) {
+                sv += b * up[k];
+                if (p.stab == STAB_FLOW) sv += c * (dn[k] - up[k]);
+            }
+            r.sb[k] = sv;
+        }
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            double rhs = p.has_source ? p.src[d] : 0.0;
+            if (p.time_dep) {
+                double o = 0.0;
+#pragma unroll
+                for (int k = 0; k < NSH; k++) o += g.N[k] * s1[k * NF + d];
+                rhs += o / p.dt;
+            }
+#pragma unroll
+            for (int k = 0; k < NSH; k++) {
+                double sv = r.sb[k];
+                if (p.stab == STAB_FLOW) {
+#pragma unroll
+                    for (int q = 0; q < DIM; q++) if (q != d) sv -= std[q] * g.G[k][q];
+                }
+                rhs += sv * s0[k * NF + d];
+                if (p.stab == STAB_FLOW) {
+#pragma unroll
+                    for (int q = 0; q < DIM; q++) if (q != d) rhs += std[d] * g.G[k][q] * s0[k * NF + q];
+                }
+                rhs += (-1.0 * g.G[k][d] / p.rho) * s0[k * NF + P];
+            }
+            stabvel[d] = rhs / diag;
+        }
+    }
+    // ---- convective upwind ----
+    double cup[NSH];
+    double U[DIM], w = 1.0;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) U[d] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NSH; k++) cup[k] = 0.0;
+    if (!p.stokes) {
+        if (p.pac) {
+#pragma unroll
+            for (int d = 0; d < DIM; d++) U[d] = stabvel[d];
+        } else {
+            if (p.upw_conv == p.upw_stab) {
+#pragma unroll
+                for (int k = 0; k < NSH; k++) cup[k] = up[k];
+            } else {
+                double l2;
+                ok &= upwind_ip<E>(p.upw_conv, x, g, std, cup, l2);
+            }
+#pragma unroll
+            for (int k = 0; k < NSH; k++)
+#pragma unroll
+                for (int d = 0; d < DIM; d++) U[d] += cup[k] * u[k * NF + d];     // upwind_vel, upwind_interface.h:334-358
+        }
+        if (p.peclet) w = peclet_blend<E>(U, g, x, std, p.visc);
+    }
+    const double prod = dotv<DIM>(std, g.n) * p.rho;
+    // ---- defect fluxes :686-776 ----
+    if (p.what & W_DEF_A) {
+        double gv[DIM][DIM];
+#pragma unroll
+        for (int d1 = 0; d1 < DIM; d1++)
+#pragma unroll
+            for (int d2 = 0; d2 < DIM; d2++) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < NSH; k++) s += g.G[k][d2] * u[k * NF + d1];
+                gv[d1][d2] = s;
+            }
+        double pr = 0;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) pr += g.N[k] * u[k * NF + P];
+#pragma unroll
+        for (int d1 = 0; d1 < DIM; d1++) {
+            double df = 0;
+#pragma unroll
+            for (int d2 = 0; d2 < DIM; d2++) df += gv[d1][d2] * g.n[d2];
+            if (!p.laplace) {
+#pragma unroll
+                for (int d2 = 0; d2 < DIM; d2++) df += gv[d2][d1] * g.n[d2];
+            }
+            double f = df * (-1.0) * p.visc * p.rho;
+            if (!p.stokes) f += U[d1] * prod;
+            f += pr * g.n[d1];
+            r.F[d1] = f;
+        }
+        r.F[P] = dotv<DIM>(stabvel, g.n) * p.rho;
+    }
+    // ---- park the record ----
+#pragma unroll
+    for (int d = 0; d < DIM; d++) { r.n[d] = g.n[d]; r.std[d] = std[d]; r.U[d] = U[d]; }
+    r.prod = prod; r.w = w; r.invdiag = invdiag;
+#pragma unroll
+    for (int k = 0; k < NSH; k++) {
+        r.N[k] = g.N[k]; r.up[k] = cup[k]; r.cvx[k] = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) r.G[k][d] = g.G[k][d];
+    }
+    return ok;
+}
+
+}  // namespace nsb

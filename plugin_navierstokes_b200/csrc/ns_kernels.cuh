@@ -1,0 +1,383 @@
+// ns_kernels.cuh -- FV1 assembly kernels for sm_100a (diagonal stabilisation branch).
+//
+//  fv1_elem_kernel   : one element (hex) or 2-3 elements (tet/quad/tri) per warp. Per-ip phase: lane = ip.
+//                      Column phase: lane = (corner k, function cf) owns one COLUMN of the local Jacobian in
+//                      registers. Scatter: coloured read-modify-write, red.global.add.f64, or local output.
+//  fv1_gather_kernel : owner-computes. One warp per grid node (= NF matrix rows). Per-ip phase: lane =
+//                      (adjacent element, SCVF incident to the node). Column phase: lane = (k, cf), partial
+//                      rows accumulate in shared memory in a fixed order and are streamed out ONCE with
+//                      coalesced stores: no atomics, no colouring, no read-modify-write of HBM.
+#pragma once
+#include <utility>
+#include "ns_fv1.cuh"
+
+namespace nsb {
+
+// Device view of the uploaded grid + precomputed tables
+struct MeshDev {
+    int64_t n_elem, n_node;
+    const int32_t* conn;        // [n_elem][NSH]
+    const double*  coords;      // [n_node][DIM]
+    const double*  scvvol;      // [n_elem][NSH]  SCV volumes (precomputed FV1Geometry table)
+    const int64_t* brow;        // [n_node+1] prefix sum of block-row lengths
+    const uint8_t* emap;        // [n_elem][NSH][NSH] slot of node conn[e][k] in the block row of conn[e][a]
+    const int64_t* adj_ptr;     // [n_node+1] node -> adjacent (element, local corner)
+    const int32_t* adj;         // elem*NSH + local corner
+    int32_t max_cnt;            // longest block row
+};
+
+enum { SC_COLORED = 1, SC_ATOMIC = 2, SC_LOCAL = 3 };
+
+template <int N, class F, int... I> NSB_DEV void static_for_impl(F&& f, std::integer_sequence<int, I...>)
+{ (f(std::integral_constant<int, I>{}), ...); }
+template <int N, class F> NSB_DEV void static_for(F&& f) { static_for_impl<N>(f, std::make_integer_sequence<int, N>{}); }
+
+// compile-time edge tables (from/to corner of SCVF ip) so that accumulator indices fold to registers
+template <int E> __host__ __device__ constexpr int edge_corner(int ip, int j)
+{
+    if (E == E_TRI)  { constexpr int T[3][2]  = {{0,1},{1,2},{2,0}}; return T[ip][j]; }
+    if (E == E_QUAD) { constexpr int T[4][2]  = {{0,1},{1,2},{2,3},{3,0}}; return T[ip][j]; }
+    if (E == E_TET)  { constexpr int T[6][2]  = {{0,1},{1,2},{2,0},{0,3},{1,3},{2,3}}; return T[ip][j]; }
+    constexpr int T[12][2] = {{0,1},{1,2},{2,3},{3,0},{0,4},{1,5},{2,6},{3,7},{4,5},{5,6},{6,7},{7,4}};
+    return T[ip][j];
+}
+
+// per-(sub-)element workspace in shared memory
+template <int E> struct ElemWS {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1;
+    double x[NSH * DIM];
+    double u[NSH * NF];
+    double s0[NSH * NF];
+    double s1[NSH * NF];
+    double vol[NSH];
+    double nn[NIP], ds[NIP];            // COR diffusion length scratch
+    int64_t rowbase[NSH];               // first value index of row (node a, fct 0)
+    int32_t cnt[NSH];                   // block-row length of node a
+    int32_t node[NSH];
+    IpRec<E> rec[NIP];
+};
+
+template <int E> NSB_DEV void cor_stats(const double* nn, const double* ds, double& mnN, double& avN, double& mnD)
+{
+    constexpr int NIP = ET<E>::NIP;
+    mnN = 1.79769313486231570e308; mnD = 1.79769313486231570e308; avN = 0.0;
+    for (int i = 0; i < NIP; i++) { if (nn[i] < mnN) mnN = nn[i]; avN += nn[i]; if (ET<E>::DIM == 3 && ds[i] < mnD) mnD = ds[i]; }
+    avN /= NIP;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int E, int SC>
+__global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, const int32_t* __restrict__ elem_list,
+                                                       int64_t n_list, const double* __restrict__ u,
+                                                       const double* __restrict__ s0, const double* __restrict__ s1,
+                                                       double* __restrict__ val, double* __restrict__ def,
+                                                       double* __restrict__ Jloc, double* __restrict__ dloc,
+                                                       int* __restrict__ errflag)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, L = NSH * NF;
+    constexpr int EPW = 32 / L;                         // elements per warp
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ElemWS<E>* wsall = reinterpret_cast<ElemWS<E>*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / L, col = lane - sub * L;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t li = gw * EPW + sub;
+    const bool active = sub < EPW && li < n_list;
+    ElemWS<E>& ws = wsall[warp * EPW + (sub < EPW ? sub : 0)];
+    const int64_t e = active ? (elem_list ? (int64_t)elem_list[li] : li) : 0;
+    const int k = col / NF, cf = col - k * NF;
+
+    // ---- stage element data ----
+    if (active) {
+        if (col < NSH) {
+            const int nd = m.conn[e * NSH + col];
+            ws.node[col] = nd;
+            ws.vol[col] = m.scvvol[e * NSH + col];
+            const int64_t b0 = m.brow[nd], b1 = m.brow[nd + 1];
+            ws.rowbase[col] = b0 * (NF * NF); ws.cnt[col] = (int32_t)(b1 - b0);
+        }
+    }
+    __syncwarp();
+    if (active) {
+        for (int i = col; i < NSH * NF; i += L) {
+            const int kk = i / NF, ff = i - kk * NF;
+            const int64_t gi = (int64_t)ws.node[kk] * NF + ff;
+            ws.u[i] = u[gi];
+            if (p.time_dep) { ws.s0[i] = s0[gi]; ws.s1[i] = s1[gi]; }
+        }
+        for (int i = col; i < NSH * DIM; i += L) {
+            const int kk = i / DIM, dd = i - kk * DIM;
+            ws.x[i] = m.coords[(int64_t)ws.node[kk] * DIM + dd];
+        }
+    }
+    __syncwarp();
+    // ---- per-ip phase: lane = ip ----
+    double cmn = 0, cav = 0, cmd = 0;
+    if (p.diff_len == DIFF_COR && p.stab != STAB_NONE) {
+        if (active && col < NIP) {
+            IpGeo<E> g; ip_geometry<E>(ws.x, col, g);
+            ws.nn[col] = dotv<DIM>(g.n, g.n); ws.ds[col] = g.ds;
+        }
+        __syncwarp();
+        if (active) cor_stats<E>(ws.nn, ws.ds, cmn, cav, cmd);
+    }
+    if (active && col < NIP) {
+        const double* ps0 = p.time_dep ? ws.s0 : ws.u;
+        const bool ok = ip_eval<E>(p, ws.x, ws.u, ps0, ws.s1, ws.vol, col, cmn, cav, cmd, ws.rec[col]);
+        if (!ok) atomicExch(errflag, 1);
+    }
+    __syncwarp();
+    if (!active) return;
+
+    // ---- column phase: lane = (k, cf) ----
+    if (p.what & (W_JAC_A | W_JAC_M)) {
+        double acc[L];
+#pragma unroll
+        for (int i = 0; i < L; i++) acc[i] = 0.0;
+        if (p.what & W_JAC_A) {
+            const bool connected = (p.stab == STAB_FLOW);
+            static_for<NIP>([&](auto ipc) {
+                constexpr int ip = decltype(ipc)::value;
+                constexpr int f = edge_corner<E>(ip, 0), t = edge_corner<E>(ip, 1);
+                const IpRec<E>& r = ws.rec[ip];
+                StabDiag<E> S{r, p.stab, p.rho};
+                double v[NF];
+                jac_col<E>(p, r, S, connected, k, cf, v);
+#pragma unroll
+                for (int rf = 0; rf < NF; rf++) { acc[f * NF + rf] += v[rf]; acc[t * NF + rf] -= v[rf]; }
+            });
+#pragma unroll
+            for (int i = 0; i < L; i++) acc[i] *= p.scale_a;
+        }
+        if ((p.what & W_JAC_M) && cf < DIM) {           // add_jac_M_elem :781-808
+            const double mv = p.scale_m * ws.vol[k] * p.rho;
+#pragma unroll
+            for (int a = 0; a < NSH; a++)
+#pragma unroll
+                for (int rf = 0; rf < DIM; rf++) if (a == k && rf == cf) acc[a * NF + rf] += mv;
+        }
+        if (SC == SC_LOCAL) {
+            // LocalMatrix layout: row index rf*NSH + a, column index cf*NSH + k
+            double* J = Jloc + e * (int64_t)(L * L);
+#pragma unroll
+            for (int a = 0; a < NSH; a++)
+#pragma unroll
+                for (int rf = 0; rf < NF; rf++) J[(rf * NSH + a) * L + (cf * NSH + k)] = acc[a * NF + rf];
+        } else {
+            const uint8_t* em = m.emap + e * (int64_t)(NSH * NSH);
+#pragma unroll
+            for (int a = 0; a < NSH; a++) {
+                const int slot = em[a * NSH + k];
+                const int64_t base = ws.rowbase[a] + (int64_t)slot * NF + cf;
+                const int64_t rstride = (int64_t)ws.cnt[a] * NF;
+#pragma unroll
+                for (int rf = 0; rf < NF; rf++) {
+                    double* q = val + base + rf * rstride;
+                    if (SC == SC_ATOMIC) atomicAdd(q, acc[a * NF + rf]);
+                    else *q += acc[a * NF + rf];
+                }
+            }
+        }
+    }
+    // ---- defect: lane = row (a = k, rf = cf) ----
+    if (p.what & (W_DEF_A | W_DEF_M | W_RHS)) {
+        double d = 0.0;
+        if (p.what & W_DEF_A) {
+#pragma unroll
+            for (int t = 0; t < ET<E>::NINC; t++) {
+                const int ip = tab::INC[E][k][t];
+                d += (double)tab::INC_SIGN[E][k][t] * ws.rec[ip].F[cf];
+            }
+        }
+        if ((p.what & W_RHS) && p.has_source && cf < DIM) d -= p.src[cf] * ws.vol[k] * p.rho;   // add_rhs_elem :841-869
+        d *= p.scale_a;
+        if ((p.what & W_DEF_M) && cf < DIM) d += p.scale_m * ws.u[k * NF + cf] * ws.vol[k] * p.rho;   // :811-838
+        if (SC == SC_LOCAL) dloc[e * (int64_t)L + cf * NSH + k] = d;
+        else {
+            double* q = def + (int64_t)ws.node[k] * NF + cf;
+            if (SC == SC_ATOMIC) atomicAdd(q, d); else *q += d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// owner-computes gather kernel
+// ------------------------------------------------------------------------------------------------
+template <int E> struct GatherCfg {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, NINC = ET<E>::NINC;
+    static constexpr int CH = (DIM == 3) ? 8 : 16;           // adjacent elements handled per round
+    static constexpr int NREC = CH * NINC;                    // <= 32
+};
+template <int E> struct GatherWS {
+    using C = GatherCfg<E>;
+    double x[C::CH][C::NSH * C::DIM];
+    double u[C::CH][C::NSH * C::NF];
+    double s0[C::CH][C::NSH * C::NF];
+    double s1[C::CH][C::NSH * C::NF];
+    double vol[C::CH][C::NSH];
+    int32_t elem[C::CH];
+    int32_t la[C::CH];
+    IpRec<E> rec[C::NREC];
+};
+
+template <int E>
+__global__ void __launch_bounds__(128) fv1_gather_kernel(KParams p, MeshDev m, const double* __restrict__ u,
+                                                         const double* __restrict__ s0, const double* __restrict__ s1,
+                                                         double beta, double* __restrict__ val, double* __restrict__ def,
+                                                         int* __restrict__ errflag)
+{
+    using C = GatherCfg<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, L = NSH * NF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    // per-warp layout: [GatherWS][rowacc NF*NF*max_cnt doubles]
+    const size_t per_warp = (sizeof(GatherWS<E>) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
+    GatherWS<E>& ws = *reinterpret_cast<GatherWS<E>*>(smem_raw + warp * per_warp);
+    double* rowacc = reinterpret_cast<double*>(smem_raw + warp * per_warp + sizeof(GatherWS<E>));
+    const bool want_jac = p.what & (W_JAC_A | W_JAC_M), want_def = p.what & (W_DEF_A | W_DEF_M | W_RHS);
+    const int k = lane / NF, cf = lane - k * NF;               // column owned in the column phase
+    const bool connected = (p.stab == STAB_FLOW);
+
+    for (int64_t a = (int64_t)blockIdx.x * nwarp + warp; a < m.n_node; a += (int64_t)gridDim.x * nwarp) {
+        const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1];
+        const int64_t b0 = m.brow[a];
+        const int cnt = (int)(m.brow[a + 1] - b0);
+        const int rowlen = cnt * NF;                            // scalars per matrix row
+        if (want_jac) for (int i = lane; i < NF * rowlen; i += 32) rowacc[i] = 0.0;
+        double dsum = 0.0;                                      // lanes < NF: defect entry (a, lane)
+        double volsum = 0.0;                                    // sum of the node's SCV volumes
+        int self_slot = 0;
+        for (int64_t qb = q0; qb < q1; qb += CH) {
+            const int nj = (int)((q1 - qb) < CH ? (q1 - qb) : CH);
+            __syncwarp();
+            // ---- stage up to CH adjacent elements ----
+            if (lane < nj) {
+                const int32_t ad = m.adj[qb + lane];
+                ws.elem[lane] = ad / NSH; ws.la[lane] = ad - (ad / NSH) * NSH;
+            }
+            __syncwarp();
+            for (int i = lane; i < nj * NSH; i += 32) {
+                const int j = i / NSH, kk = i - j * NSH;
+                const int64_t e = ws.elem[j];
+                const int64_t nd = m.conn[e * NSH + kk];
+                ws.vol[j][kk] = m.scvvol[e * NSH + kk];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) ws.x[j][kk * DIM + d] = m.coords[nd * DIM + d];
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    ws.u[j][kk * NF + f] = u[nd * NF + f];
+                    if (p.time_dep) { ws.s0[j][kk * NF + f] = s0[nd * NF + f]; ws.s1[j][kk * NF + f] = s1[nd * NF + f]; }
+                }
+            }
+            __syncwarp();
+            // ---- per-ip phase: lane = (adjacent element j, incident SCVF t) ----
+            if (p.what & (W_JAC_A | W_DEF_A)) {
+                const int j = lane / NINC, t = lane - j * NINC;
+                if (j < nj) {
+                    const int ip = tab::INC[E][ws.la[j]][t];
+                    double cmn = 0, cav = 0, cmd = 0;
+                    if (p.diff_len == DIFF_COR && p.stab != STAB_NONE) {
+                        double nn[ET<E>::NIP], ds[ET<E>::NIP];
+                        for (int i = 0; i < ET<E>::NIP; i++) { IpGeo<E> g; ip_geometry<E>(ws.x[j], i, g); nn[i] = dotv<DIM>(g.n, g.n); ds[i] = g.ds; }
+                        cor_stats<E>(nn, ds, cmn, cav, cmd);
+                    }
+                    const double* ps0 = p.time_dep ? ws.s0[j] : ws.u[j];
+                    const bool ok = ip_eval<E>(p, ws.x[j], ws.u[j], ps0, ws.s1[j], ws.vol[j], ip, cmn, cav, cmd, ws.rec[lane]);
+                    if (!ok) atomicExch(errflag, 1);
+                }
+            }
+            __syncwarp();
+            // ---- column phase: lane = (k, cf); fixed summation order j = 0..nj-1, t = 0..NINC-1 ----
+            if (want_jac && lane < L) {
+                for (int j = 0; j < nj; j++) {
+                    const int la = ws.la[j];
+                    double acc[NF];
+#pragma unroll
+                    for (int rf = 0; rf < NF; rf++) acc[rf] = 0.0;
+                    if (p.what & W_JAC_A) {
+#pragma unroll
+                        for (int t = 0; t < NINC; t++) {
+                            const IpRec<E>& r = ws.rec[j * NINC + t];
+                            const double sg = (double)tab::INC_SIGN[E][la][t];
+                            StabDiag<E> S{r, p.stab, p.rho};
+                            double v[NF];
+                            jac_col<E>(p, r, S, connected, k, cf, v);
+#pragma unroll
+                            for (int rf = 0; rf < NF; rf++) acc[rf] += sg * v[rf];
+                        }
+#pragma unroll
+                        for (int rf = 0; rf < NF; rf++) acc[rf] *= p.scale_a;
+                    }
+                    const int slot = m.emap[(int64_t)ws.elem[j] * (NSH * NSH) + la * NSH + k];
+#pragma unroll
+                    for (int rf = 0; rf < NF; rf++) rowacc[rf * rowlen + slot * NF + cf] += acc[rf];
+                }
+            }
+            // ---- defect + lumped mass: lanes < NF own (a, rf = lane) ----
+            if (lane < NF) {
+                for (int j = 0; j < nj; j++) {
+                    const int la = ws.la[j];
+                    if (p.what & W_DEF_A) {
+#pragma unroll
+                        for (int t = 0; t < NINC; t++)
+                            dsum += (double)tab::INC_SIGN[E][la][t] * ws.rec[j * NINC + t].F[lane];
+                    }
+                    volsum += ws.vol[j][la];
+                }
+                if (qb == q0) self_slot = m.emap[(int64_t)ws.elem[0] * (NSH * NSH) + ws.la[0] * NSH + ws.la[0]];
+            }
+        }
+        __syncwarp();
+        // ---- stream the finished rows out once ----
+        if (want_jac) {
+            if ((p.what & W_JAC_M) && lane < DIM)                // lumped mass on the diagonal (:781-808)
+                rowacc[lane * rowlen + self_slot * NF + lane] += p.scale_m * volsum * p.rho;
+            __syncwarp();
+            double* out = val + b0 * (NF * NF);
+            if (beta == 0.0) for (int i = lane; i < NF * rowlen; i += 32) out[i] = rowacc[i];
+            else for (int i = lane; i < NF * rowlen; i += 32) out[i] = beta * out[i] + rowacc[i];
+        }
+        if (want_def && lane < NF) {
+            double d = (p.what & W_DEF_A) ? dsum : 0.0;
+            if ((p.what & W_RHS) && p.has_source && lane < DIM) d -= p.src[lane] * volsum * p.rho;
+            d *= p.scale_a;
+            if ((p.what & W_DEF_M) && lane < DIM) d += p.scale_m * u[a * NF + lane] * volsum * p.rho;
+            double* q = def + a * NF + lane;
+            *q = (beta == 0.0) ? d : beta * (*q) + d;
+        }
+    }
+}
+
+// SCV-volume table (precomputed FV1Geometry data, uploaded mesh only)
+template <int E>
+__global__ void scv_volume_kernel(int64_t n_elem, const int32_t* __restrict__ conn, const double* __restrict__ coords,
+                                  double* __restrict__ scvvol)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_elem * NSH) return;
+    const int64_t e = i / NSH; const int co = (int)(i - e * NSH);
+    double x[NSH * DIM];
+#pragma unroll
+    for (int k = 0; k < NSH; k++) {
+        const int64_t nd = conn[e * NSH + k];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) x[k * DIM + d] = coords[nd * DIM + d];
+    }
+    scvvol[i] = scv_volume<E>(x, co);
+}
+
+__global__ void scale_kernel(int64_t n, double beta, double* __restrict__ a)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] *= beta;
+}
+__global__ void pack_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ src, double* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = src[idx[i]];
+}
+__global__ void unpack_add_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ in, double* __restrict__ dst)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[idx[i]] += in[i];
+}
+
+}  // namespace nsb

@@ -1,0 +1,689 @@
+// nsb200.cu -- host side of libnsb200.so: context, grid preprocessing (adjacency, block-CSR pattern,
+// element->CSR scatter map, colouring), kernel dispatch, and the extern "C" entry points of include/nsb200.h.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/nsb200.h"
+#include "ns_kernels.cuh"
+#include "ns_dense.cuh"
+#include "ns_fvcr.cuh"
+
+using namespace nsb;
+
+static std::string g_create_error;
+
+struct nsb_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    nsb_params prm;
+    bool mesh_ready = false;
+    int elem = -1, disc = NSB_DISC_FV1;
+    int64_t n_elem = 0, n_node = 0, n_side = 0, n_dof = 0, nnz = 0;
+    int n_colors = 0, max_cnt = 0;
+    // host copies needed after upload
+    std::vector<int64_t> h_brow;          // block-row prefix (FV1) / scalar rowptr (FVCR)
+    std::vector<int32_t> h_bcol;          // block columns (FV1) / scalar colind (FVCR)
+    std::vector<int64_t> h_color_ptr;
+    // device
+    int32_t *d_conn = nullptr, *d_adj = nullptr, *d_color_order = nullptr, *d_esides = nullptr;
+    double *d_coords = nullptr, *d_scvvol = nullptr;
+    int64_t *d_brow = nullptr, *d_adj_ptr = nullptr;
+    uint8_t *d_emap = nullptr;
+    FvcrDev fvcr{};
+    int *d_err = nullptr;
+    // staging for NSB_HOST calls
+    double *d_u = nullptr, *d_s0 = nullptr, *d_s1 = nullptr, *d_val = nullptr, *d_def = nullptr;
+    double *d_jloc = nullptr, *d_dloc = nullptr;
+    int64_t launches = 0;
+    int sm_count = 148;
+};
+
+static int set_err(nsb_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CUDA_TRY(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+    return set_err(c, NSB_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); } while (0)
+
+template <class F> static void parallel_for(int64_t n, F fn)
+{
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (n < 4096) nt = 1;
+    std::vector<std::thread> th;
+    const int64_t chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) {
+        const int64_t lo = t * chunk, hi = std::min(n, lo + chunk);
+        if (lo >= hi) break;
+        th.emplace_back([=]() { fn(lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+
+static const int kNSH[4] = {3, 4, 4, 8}, kDIM[4] = {2, 2, 3, 3}, kNSIDE[4] = {3, 4, 4, 6};
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* nsb_version(void) { return "nsb200 0.1 (sm_100a)"; }
+
+extern "C" const char* nsb_last_error(const nsb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void nsb_params_default(nsb_params* p)
+{
+    memset(p, 0, sizeof *p);
+    p->disc = NSB_DISC_FV1;
+    p->conv_upwind = NSB_UPWIND_UNSET;      // no default upwind / stabilisation
+    p->stab = NSB_STAB_UNSET;
+    p->stab_upwind = NSB_UPWIND_UNSET;
+    p->diff_length = NSB_DIFF_RAW;          // stabilization.h:324
+    p->defect_upwind = 1;                   // fvcr/navier_stokes_fvcr.cpp:82
+    p->density = 1.0; p->density_set = 1;   // fv1/navier_stokes_fv1.cpp:82
+    p->exact_jacobian = 0.0;                // navier_stokes_base.cpp:57
+}
+
+extern "C" int nsb_create(int device, nsb_ctx** out)
+{
+    if (!out) return set_err(nullptr, NSB_ERR_INVALID, "nsb_create: out == NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(nullptr, NSB_ERR_CUDA, "nsb_create: no CUDA device available (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return set_err(nullptr, NSB_ERR_INVALID, "nsb_create: device %d out of range", device);
+    nsb_ctx* c = new nsb_ctx();
+    c->device = device;
+    nsb_params_default(&c->prm);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess) {
+        set_err(nullptr, NSB_ERR_CUDA, "nsb_create: cannot initialise device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        delete c; return NSB_ERR_CUDA;
+    }
+    cudaMemset(c->d_err, 0, sizeof(int));
+    c->stream = c->own_stream;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return NSB_OK;
+}
+
+static void free_mesh(nsb_ctx* c)
+{
+    cudaFree(c->d_conn); cudaFree(c->d_adj); cudaFree(c->d_color_order); cudaFree(c->d_esides); cudaFree(c->d_coords);
+    cudaFree(c->d_scvvol); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
+    cudaFree(c->d_u); cudaFree(c->d_s0); cudaFree(c->d_s1); cudaFree(c->d_val); cudaFree(c->d_def);
+    cudaFree(c->d_jloc); cudaFree(c->d_dloc);
+    fvcr_free(c->fvcr);
+    c->d_conn = c->d_adj = c->d_color_order = c->d_esides = nullptr; c->d_coords = c->d_scvvol = nullptr;
+    c->d_brow = c->d_adj_ptr = nullptr; c->d_emap = nullptr;
+    c->d_u = c->d_s0 = c->d_s1 = c->d_val = c->d_def = c->d_jloc = c->d_dloc = nullptr;
+    c->mesh_ready = false;
+}
+
+extern "C" void nsb_destroy(nsb_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_mesh(c);
+    cudaFree(c->d_err);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int nsb_set_stream(nsb_ctx* c, void* s)
+{
+    if (!c) return NSB_ERR_INVALID;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return NSB_OK;
+}
+
+extern "C" int nsb_set_params(nsb_ctx* c, const nsb_params* p)
+{
+    if (!c || !p) return NSB_ERR_INVALID;
+    c->prm = *p;
+    return NSB_OK;
+}
+
+extern "C" int64_t nsb_num_dofs(const nsb_ctx* c) { return c ? c->n_dof : 0; }
+extern "C" int64_t nsb_nnz(const nsb_ctx* c) { return c ? c->nnz : 0; }
+extern "C" int nsb_num_colors(const nsb_ctx* c) { return c ? c->n_colors : 0; }
+extern "C" int64_t nsb_launch_count(const nsb_ctx* c) { return c ? c->launches : 0; }
+extern "C" int nsb_synchronize(nsb_ctx* c)
+{
+    if (!c) return NSB_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid preprocessing (host). "entities" are nodes (FV1) or sides (FVCR velocity dofs).
+// ------------------------------------------------------------------------------------------------
+struct EntityGraph {
+    std::vector<int64_t> adj_ptr;   // entity -> incident (element, local index)
+    std::vector<int32_t> adj;       // elem*per + local
+    std::vector<int64_t> brow;      // entity -> neighbouring entities (sorted, incl. itself)
+    std::vector<int32_t> bcol;
+    int max_cnt = 0;
+};
+
+static int build_entity_graph(nsb_ctx* c, int64_t n_elem, int64_t n_ent, int per, const int32_t* conn, EntityGraph& g)
+{
+    if ((double)n_elem * per >= 2147483647.0) return set_err(c, NSB_ERR_UNSUPPORTED, "grid too large for 32-bit adjacency ids");
+    g.adj_ptr.assign(n_ent + 1, 0);
+    for (int64_t e = 0; e < n_elem; e++) for (int k = 0; k < per; k++) {
+        const int32_t nd = conn[e * per + k];
+        if (nd < 0 || nd >= n_ent) return set_err(c, NSB_ERR_INVALID, "connectivity entry out of range (element %lld)", (long long)e);
+        g.adj_ptr[nd + 1]++;
+    }
+    for (int64_t i = 0; i < n_ent; i++) g.adj_ptr[i + 1] += g.adj_ptr[i];
+    g.adj.resize(g.adj_ptr[n_ent]);
+    { std::vector<int64_t> pos(g.adj_ptr.begin(), g.adj_ptr.end() - 1);
+      for (int64_t e = 0; e < n_elem; e++) for (int k = 0; k < per; k++) g.adj[pos[conn[e * per + k]]++] = (int32_t)(e * per + k); }
+    // neighbour lists: count, prefix, fill
+    std::vector<int32_t> cnt(n_ent);
+    auto gather = [&](int64_t i, std::vector<int32_t>& tmp) {
+        tmp.clear();
+        for (int64_t q = g.adj_ptr[i]; q < g.adj_ptr[i + 1]; q++) { const int64_t e = g.adj[q] / per; for (int k = 0; k < per; k++) tmp.push_back(conn[e * per + k]); }
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+    };
+    parallel_for(n_ent, [&](int64_t lo, int64_t hi) { std::vector<int32_t> tmp; for (int64_t i = lo; i < hi; i++) { gather(i, tmp); cnt[i] = (int32_t)tmp.size(); } });
+    g.brow.assign(n_ent + 1, 0);
+    g.max_cnt = 0;
+    for (int64_t i = 0; i < n_ent; i++) { g.brow[i + 1] = g.brow[i] + cnt[i]; g.max_cnt = std::max(g.max_cnt, (int)cnt[i]); }
+    g.bcol.resize(g.brow[n_ent]);
+    parallel_for(n_ent, [&](int64_t lo, int64_t hi) { std::vector<int32_t> tmp; for (int64_t i = lo; i < hi; i++) { gather(i, tmp); std::copy(tmp.begin(), tmp.end(), g.bcol.begin() + g.brow[i]); } });
+    return NSB_OK;
+}
+
+// slot of entity conn[e][k] in the neighbour list of entity conn[e][a]
+static void build_emap(int64_t n_elem, int per, const int32_t* conn, const EntityGraph& g, std::vector<uint8_t>& emap)
+{
+    emap.resize((size_t)n_elem * per * per);
+    parallel_for(n_elem, [&](int64_t lo, int64_t hi) {
+        for (int64_t e = lo; e < hi; e++) for (int a = 0; a < per; a++) {
+            const int32_t na = conn[e * per + a];
+            const int32_t* b = g.bcol.data() + g.brow[na]; const int32_t* en = g.bcol.data() + g.brow[na + 1];
+            for (int k = 0; k < per; k++) emap[(e * per + a) * per + k] = (uint8_t)(std::lower_bound(b, en, conn[e * per + k]) - b);
+        }
+    });
+}
+
+// greedy colouring: no two elements of a colour share an entity; order = colour-major, element-minor
+static int color_elements(int64_t n_elem, int64_t n_ent, int per, const int32_t* conn, std::vector<int32_t>& order, std::vector<int64_t>& cptr)
+{
+    std::vector<uint64_t> mask(n_ent, 0);
+    std::vector<uint8_t> col(n_elem);
+    int ncol = 0;
+    for (int64_t e = 0; e < n_elem; e++) {
+        uint64_t used = 0;
+        for (int k = 0; k < per; k++) used |= mask[conn[e * per + k]];
+        int cc = 0; while (cc < 63 && ((used >> cc) & 1)) cc++;
+        col[e] = (uint8_t)cc; ncol = std::max(ncol, cc + 1);
+        for (int k = 0; k < per; k++) mask[conn[e * per + k]] |= (uint64_t)1 << cc;
+    }
+    cptr.assign(ncol + 1, 0);
+    for (int64_t e = 0; e < n_elem; e++) cptr[col[e] + 1]++;
+    for (int i = 0; i < ncol; i++) cptr[i + 1] += cptr[i];
+    order.resize(n_elem);
+    std::vector<int64_t> pos(cptr.begin(), cptr.end() - 1);
+    for (int64_t e = 0; e < n_elem; e++) order[pos[col[e]]++] = (int32_t)e;
+    return ncol;
+}
+
+template <class T> static cudaError_t upload(T** dptr, const T* h, size_t n)
+{
+    cudaError_t e = cudaMalloc((void**)dptr, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+template <int E> static void launch_scvvol(nsb_ctx* c)
+{
+    const int64_t n = c->n_elem * ET<E>::NSH;
+    scv_volume_kernel<E><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol);
+    c->launches++;
+}
+
+extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coords)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (elem < 0 || elem > 3 || n_elem <= 0 || n_node <= 0 || !conn || !coords) return set_err(c, NSB_ERR_INVALID, "nsb_upload_mesh: bad arguments");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    free_mesh(c);
+    const int nsh = kNSH[elem], dim = kDIM[elem], nf = dim + 1;
+    c->elem = elem; c->disc = NSB_DISC_FV1; c->n_elem = n_elem; c->n_node = n_node; c->n_side = 0;
+    EntityGraph g;
+    int rc = build_entity_graph(c, n_elem, n_node, nsh, conn, g);
+    if (rc) return rc;
+    if (g.max_cnt > 255) return set_err(c, NSB_ERR_UNSUPPORTED, "a node has %d neighbours (> 255)", g.max_cnt);
+    std::vector<uint8_t> emap; build_emap(n_elem, nsh, conn, g, emap);
+    std::vector<int32_t> order;
+    c->n_colors = color_elements(n_elem, n_node, nsh, conn, order, c->h_color_ptr);
+    c->max_cnt = g.max_cnt;
+    c->n_dof = n_node * nf; c->nnz = g.brow[n_node] * nf * nf;
+    CUDA_TRY(c, upload(&c->d_conn, conn, (size_t)n_elem * nsh));
+    CUDA_TRY(c, upload(&c->d_coords, coords, (size_t)n_node * dim));
+    CUDA_TRY(c, upload(&c->d_brow, g.brow.data(), g.brow.size()));
+    CUDA_TRY(c, upload(&c->d_adj_ptr, g.adj_ptr.data(), g.adj_ptr.size()));
+    CUDA_TRY(c, upload(&c->d_adj, g.adj.data(), g.adj.size()));
+    CUDA_TRY(c, upload(&c->d_emap, emap.data(), emap.size()));
+    CUDA_TRY(c, upload(&c->d_color_order, order.data(), order.size()));
+    CUDA_TRY(c, cudaMalloc(&c->d_scvvol, (size_t)n_elem * nsh * sizeof(double)));
+    switch (elem) { case 0: launch_scvvol<E_TRI>(c); break; case 1: launch_scvvol<E_QUAD>(c); break;
+                    case 2: launch_scvvol<E_TET>(c); break; default: launch_scvvol<E_HEX>(c); }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->h_brow.swap(g.brow); c->h_bcol.swap(g.bcol);
+    c->mesh_ready = true;
+    return NSB_OK;
+}
+
+extern "C" int nsb_get_csr(const nsb_ctx* c, int64_t* rowptr, int32_t* colind)
+{
+    if (!c || !c->mesh_ready || !rowptr || !colind) return NSB_ERR_INVALID;
+    if (c->disc == NSB_DISC_FVCR) {
+        std::copy(c->h_brow.begin(), c->h_brow.end(), rowptr);
+        std::copy(c->h_bcol.begin(), c->h_bcol.end(), colind);
+        return NSB_OK;
+    }
+    const int nf = kDIM[c->elem] + 1;
+    const int64_t n = c->n_node;
+    parallel_for(n, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; i++) {
+            const int64_t b0 = c->h_brow[i], cnt = c->h_brow[i + 1] - b0;
+            for (int rf = 0; rf < nf; rf++) {
+                int64_t pos = b0 * nf * nf + rf * cnt * nf;
+                rowptr[i * nf + rf] = pos;
+                for (int64_t q = 0; q < cnt; q++) for (int cf = 0; cf < nf; cf++) colind[pos++] = c->h_bcol[b0 + q] * nf + cf;
+            }
+        }
+    });
+    rowptr[n * nf] = c->nnz;
+    return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep_elem_loop validation + parameter resolution
+// ------------------------------------------------------------------------------------------------
+static int resolve_params(nsb_ctx* c, KParams& k, int what, const nsb_time_series* ts, double sa, double sm)
+{
+    const nsb_params& p = c->prm;
+    memset(&k, 0, sizeof k);
+    if (c->disc == NSB_DISC_FV1) {
+        // fv1/navier_stokes_fv1.cpp:136-181
+        if (p.stab == NSB_STAB_UNSET) return set_err(c, NSB_ERR_SETUP, "Stabilization has not been set.");
+        if (p.stab < 0 || p.stab > 2) return set_err(c, NSB_ERR_INVALID, "unknown stabilization id %d", p.stab);
+        int upw_stab = p.stab_upwind;
+        if (p.pac_upwind) {                      // fv1/navier_stokes_fv1.h:217-225
+            if (p.conv_upwind == NSB_UPWIND_UNSET) return set_err(c, NSB_ERR_SETUP, "Upwind must be specified previously.");
+            upw_stab = p.conv_upwind;
+        } else if (upw_stab == NSB_UPWIND_UNSET) upw_stab = p.conv_upwind;   // string overloads auto-wire (:190-215)
+        if (!p.stokes) {
+            if (!p.pac_upwind && p.conv_upwind == NSB_UPWIND_UNSET)
+                return set_err(c, NSB_ERR_SETUP, "Upwinding for convective Term in Momentum eq. not set.");
+            if (upw_stab == NSB_UPWIND_UNSET) return set_err(c, NSB_ERR_SETUP, "No upwind object set in the stabilization.");
+        }
+        k.upw_stab = upw_stab; k.upw_conv = p.conv_upwind; k.stab = p.stab; k.diff_len = p.diff_length;
+        k.pac = p.pac_upwind ? 1 : 0;
+    } else {
+        // fvcr/navier_stokes_fvcr.cpp:145-181
+        if (!p.stokes && p.conv_upwind == NSB_UPWIND_UNSET)
+            return set_err(c, NSB_ERR_SETUP, "Upwinding for convective Term in Momentum eq. not set.");
+        if (!p.stokes && p.conv_upwind == NSB_UPWIND_POSITIVE)
+            return set_err(c, NSB_ERR_SETUP, "No update function registered for Geometry (upwind has no Crouzeix-Raviart overload)");
+        k.upw_conv = p.conv_upwind; k.upw_stab = p.conv_upwind;
+        k.pac = p.defect_upwind ? 1 : 0;          // FVCR reuses the slot for m_bDefectUpwind
+    }
+    if (!p.kin_visc_set) return set_err(c, NSB_ERR_SETUP, "NavierStokes::prep_elem_loop: Kinematic Viscosity has not been set, but is required.");
+    if (!p.density_set) return set_err(c, NSB_ERR_SETUP, "NavierStokes::prep_elem_loop: Density has not been set, but is required.");
+    k.stokes = p.stokes ? 1 : 0; k.laplace = p.laplace ? 1 : 0; k.peclet = p.peclet_blend ? 1 : 0;
+    k.has_source = p.has_source ? 1 : 0;
+    k.what = what;
+    k.exact_jac = p.exact_jacobian; k.visc = p.kin_visc; k.rho = p.density;
+    k.scale_a = sa; k.scale_m = sm;
+    for (int d = 0; d < 3; d++) k.src[d] = p.source[d];
+    k.time_dep = (ts && ts->sol0) ? 1 : 0;
+    if (k.time_dep) {
+        if (!ts->sol1) return set_err(c, NSB_ERR_SETUP, "NavierStokes::add_jac_A_elem:  Stabilization needs exactly two time points.");
+        k.dt = ts->dt;
+    }
+    // exact_jac is "grad_div" for FVCR in a second slot
+    if (c->disc == NSB_DISC_FVCR) k.dt = p.grad_div;
+    return NSB_OK;
+}
+
+extern "C" int nsb_prep_elem_loop(nsb_ctx* c)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_prep_elem_loop: no grid uploaded");
+    KParams k;
+    return resolve_params(c, k, 0, nullptr, 1.0, 1.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+static MeshDev mesh_view(const nsb_ctx* c)
+{
+    MeshDev m;
+    m.n_elem = c->n_elem; m.n_node = c->n_node; m.conn = c->d_conn; m.coords = c->d_coords; m.scvvol = c->d_scvvol;
+    m.brow = c->d_brow; m.emap = c->d_emap; m.adj_ptr = c->d_adj_ptr; m.adj = c->d_adj; m.max_cnt = c->max_cnt;
+    return m;
+}
+
+static bool needs_dense(const KParams& k)
+{
+    return !k.stokes && (k.upw_stab == UPW_POSITIVE || (!k.pac && k.upw_conv == UPW_POSITIVE));
+}
+
+template <int E, int SC>
+static int launch_elem(nsb_ctx* c, const KParams& k, const int32_t* list, int64_t n_list, const double* u, const double* s0,
+                       const double* s1, double* val, double* def, double* jl, double* dl)
+{
+    if (n_list <= 0) return NSB_OK;
+    constexpr int L = ET<E>::NSH * (ET<E>::DIM + 1), EPW = 32 / L, WPB = 4;
+    const MeshDev m = mesh_view(c);
+    if (needs_dense(k)) {
+        const size_t smem = sizeof(DenseWS<E>) * WPB;
+        auto kern = fv1_dense_kernel<E, SC>;
+        CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t nblk = (n_list + WPB - 1) / WPB;
+        kern<<<(unsigned)nblk, WPB * 32, smem, c->stream>>>(k, m, list, n_list, u, s0, s1, val, def, jl, dl, c->d_err);
+    } else {
+        const size_t smem = sizeof(ElemWS<E>) * EPW * WPB;
+        auto kern = fv1_elem_kernel<E, SC>;
+        CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t ngrp = (n_list + EPW - 1) / EPW, nblk = (ngrp + WPB - 1) / WPB;
+        kern<<<(unsigned)nblk, WPB * 32, smem, c->stream>>>(k, m, list, n_list, u, s0, s1, val, def, jl, dl, c->d_err);
+    }
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return NSB_OK;
+}
+
+template <int E>
+static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const double* s0, const double* s1, double beta,
+                         double* val, double* def)
+{
+    constexpr int NF = ET<E>::DIM + 1, WPB = 4;
+    const MeshDev m = mesh_view(c);
+    const size_t per_warp = (sizeof(GatherWS<E>) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
+    const size_t smem = per_warp * WPB;
+    auto kern = fv1_gather_kernel<E>;
+    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, smem));
+    if (occ < 1) return set_err(c, NSB_ERR_CUDA, "gather kernel does not fit on an SM (smem %zu)", smem);
+    int64_t nblk = std::min<int64_t>((c->n_node + WPB - 1) / WPB, (int64_t)c->sm_count * occ);
+    kern<<<(unsigned)nblk, WPB * 32, smem, c->stream>>>(k, m, u, s0, s1, beta, val, def, c->d_err);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return NSB_OK;
+}
+
+template <int E>
+static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u, const double* s0, const double* s1,
+                        double beta, double* val, double* def)
+{
+    const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
+    if (mode == NSB_SCATTER_GATHER && needs_dense(k)) mode = NSB_SCATTER_COLORED;   // dense ip systems need whole elements
+    if (mode == NSB_SCATTER_GATHER) return launch_gather<E>(c, k, u, s0, s1, beta, val, def);
+    // element kernels accumulate into beta*old
+    if (jac) {
+        if (beta == 0.0) CUDA_TRY(c, cudaMemsetAsync(val, 0, sizeof(double) * c->nnz, c->stream));
+        else if (beta != 1.0) { scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->nnz, beta, val); c->launches++; }
+    }
+    if (dfc) {
+        if (beta == 0.0) CUDA_TRY(c, cudaMemsetAsync(def, 0, sizeof(double) * c->n_dof, c->stream));
+        else if (beta != 1.0) { scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->n_dof, beta, def); c->launches++; }
+    }
+    if (mode == NSB_SCATTER_ATOMIC) return launch_elem<E, SC_ATOMIC>(c, k, nullptr, c->n_elem, u, s0, s1, val, def, nullptr, nullptr);
+    if (mode == NSB_SCATTER_COLORED) {
+        for (int col = 0; col < c->n_colors; col++) {
+            const int64_t lo = c->h_color_ptr[col], hi = c->h_color_ptr[col + 1];
+            int rc = launch_elem<E, SC_COLORED>(c, k, c->d_color_order + lo, hi - lo, u, s0, s1, val, def, nullptr, nullptr);
+            if (rc) return rc;
+        }
+        return NSB_OK;
+    }
+    return set_err(c, NSB_ERR_INVALID, "unknown scatter mode %d", mode);
+}
+
+static int check_device_error(nsb_ctx* c)
+{
+    int flag = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&flag, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (flag) {
+        cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream);
+        return set_err(c, NSB_ERR_GEOMETRY, flag == 2 ? "Could not compute inverse." : "GetNodeNextToCut: Cannot find cut side.");
+    }
+    return NSB_OK;
+}
+
+static int ensure(nsb_ctx* c, double** p, size_t n)
+{
+    if (*p) return NSB_OK;
+    CUDA_TRY(c, cudaMalloc(p, std::max<size_t>(n, 1) * sizeof(double)));
+    return NSB_OK;
+}
+
+extern "C" int nsb_assemble(nsb_ctx* c, int what, int mode, const double* u, const nsb_time_series* ts, double sa, double sm,
+                            double beta, double* values, double* defect, int location)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: no grid uploaded");
+    if (!u) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: u == NULL");
+    const bool jac = what & (NSB_JAC_A | NSB_JAC_M), dfc = what & (NSB_DEF_A | NSB_DEF_M | NSB_RHS);
+    if ((jac && !values) || (dfc && !defect)) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: output pointer missing for requested part");
+    if (!jac && !dfc) return NSB_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    KParams k;
+    int rc = resolve_params(c, k, what, ts, sa, sm);
+    if (rc) return rc;
+    const double *du = u, *ds0 = ts ? ts->sol0 : nullptr, *ds1 = ts ? ts->sol1 : nullptr;
+    double *dv = values, *dd = defect;
+    if (location == NSB_HOST) {
+        const size_t nb = sizeof(double) * c->n_dof;
+        if ((rc = ensure(c, &c->d_u, c->n_dof))) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, nb, cudaMemcpyHostToDevice, c->stream)); du = c->d_u;
+        if (k.time_dep || (c->disc == NSB_DISC_FVCR && ds0)) {
+            if ((rc = ensure(c, &c->d_s0, c->n_dof)) || (rc = ensure(c, &c->d_s1, c->n_dof))) return rc;
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_s0, ts->sol0, nb, cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_s1, ts->sol1, nb, cudaMemcpyHostToDevice, c->stream));
+            ds0 = c->d_s0; ds1 = c->d_s1;
+        }
+        if (jac) { if ((rc = ensure(c, &c->d_val, c->nnz))) return rc; dv = c->d_val;
+                   if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(dv, values, sizeof(double) * c->nnz, cudaMemcpyHostToDevice, c->stream)); }
+        if (dfc) { if ((rc = ensure(c, &c->d_def, c->n_dof))) return rc; dd = c->d_def;
+                   if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(dd, defect, nb, cudaMemcpyHostToDevice, c->stream)); }
+    }
+    if (c->disc == NSB_DISC_FVCR) rc = fvcr_assemble(c->fvcr, k, c->elem, mode, du, beta, dv, dd, c->stream, c->sm_count, c->d_err, &c->launches);
+    else switch (c->elem) {
+        case NSB_TRI:  rc = assemble_fv1<E_TRI>(c, k, mode, du, ds0, ds1, beta, dv, dd); break;
+        case NSB_QUAD: rc = assemble_fv1<E_QUAD>(c, k, mode, du, ds0, ds1, beta, dv, dd); break;
+        case NSB_TET:  rc = assemble_fv1<E_TET>(c, k, mode, du, ds0, ds1, beta, dv, dd); break;
+        default:       rc = assemble_fv1<E_HEX>(c, k, mode, du, ds0, ds1, beta, dv, dd); break;
+    }
+    if (rc > 0) return set_err(c, NSB_ERR_CUDA, "CUDA launch failure in FVCR path: %s", cudaGetErrorString((cudaError_t)rc));
+    if (rc) return rc;
+    if (location == NSB_HOST) {
+        if (jac) CUDA_TRY(c, cudaMemcpyAsync(values, dv, sizeof(double) * c->nnz, cudaMemcpyDeviceToHost, c->stream));
+        if (dfc) CUDA_TRY(c, cudaMemcpyAsync(defect, dd, sizeof(double) * c->n_dof, cudaMemcpyDeviceToHost, c->stream));
+        return check_device_error(c);          // synchronises
+    }
+    return NSB_OK;
+}
+
+extern "C" int nsb_check_errors(nsb_ctx* c)      /* device-pointer mode: poll the element-level error flag */
+{
+    if (!c) return NSB_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return check_device_error(c);
+}
+
+extern "C" int nsb_local_contributions(nsb_ctx* c, int what, const double* u, const nsb_time_series* ts, double* Jloc,
+                                       double* dloc, int location)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_local_contributions: no grid uploaded");
+    if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "local contributions: FV1 only");
+    if (!u || !Jloc || !dloc) return set_err(c, NSB_ERR_INVALID, "nsb_local_contributions: NULL pointer");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    KParams k;
+    int rc = resolve_params(c, k, what, ts, 1.0, 1.0);
+    if (rc) return rc;
+    const int L = kNSH[c->elem] * (kDIM[c->elem] + 1);
+    const size_t nJ = (size_t)c->n_elem * L * L, nd = (size_t)c->n_elem * L;
+    const double *du = u, *ds0 = ts ? ts->sol0 : nullptr, *ds1 = ts ? ts->sol1 : nullptr;
+    double *dj = Jloc, *ddl = dloc;
+    if (location == NSB_HOST) {
+        const size_t nb = sizeof(double) * c->n_dof;
+        if ((rc = ensure(c, &c->d_u, c->n_dof))) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, nb, cudaMemcpyHostToDevice, c->stream)); du = c->d_u;
+        if (k.time_dep) {
+            if ((rc = ensure(c, &c->d_s0, c->n_dof)) || (rc = ensure(c, &c->d_s1, c->n_dof))) return rc;
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_s0, ts->sol0, nb, cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_s1, ts->sol1, nb, cudaMemcpyHostToDevice, c->stream));
+            ds0 = c->d_s0; ds1 = c->d_s1;
+        }
+        if ((rc = ensure(c, &c->d_jloc, nJ)) || (rc = ensure(c, &c->d_dloc, nd))) return rc;
+        dj = c->d_jloc; ddl = c->d_dloc;
+    }
+    CUDA_TRY(c, cudaMemsetAsync(dj, 0, sizeof(double) * nJ, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(ddl, 0, sizeof(double) * nd, c->stream));
+    switch (c->elem) {
+        case NSB_TRI:  rc = launch_elem<E_TRI, SC_LOCAL>(c, k, nullptr, c->n_elem, du, ds0, ds1, nullptr, nullptr, dj, ddl); break;
+        case NSB_QUAD: rc = launch_elem<E_QUAD, SC_LOCAL>(c, k, nullptr, c->n_elem, du, ds0, ds1, nullptr, nullptr, dj, ddl); break;
+        case NSB_TET:  rc = launch_elem<E_TET, SC_LOCAL>(c, k, nullptr, c->n_elem, du, ds0, ds1, nullptr, nullptr, dj, ddl); break;
+        default:       rc = launch_elem<E_HEX, SC_LOCAL>(c, k, nullptr, c->n_elem, du, ds0, ds1, nullptr, nullptr, dj, ddl); break;
+    }
+    if (rc) return rc;
+    if (location == NSB_HOST) {
+        CUDA_TRY(c, cudaMemcpyAsync(Jloc, dj, sizeof(double) * nJ, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(dloc, ddl, sizeof(double) * nd, cudaMemcpyDeviceToHost, c->stream));
+        return check_device_error(c);
+    }
+    return NSB_OK;
+}
+
+extern "C" int nsb_pack(nsb_ctx* c, int64_t n, const int64_t* idx, const double* src, double* out)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (n <= 0) return NSB_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    pack_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, c->sm_count * 8), 256, 0, c->stream>>>(n, idx, src, out);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return NSB_OK;
+}
+
+extern "C" int nsb_unpack_add(nsb_ctx* c, int64_t n, const int64_t* idx, const double* in, double* dst)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (n <= 0) return NSB_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    unpack_add_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, c->sm_count * 8), 256, 0, c->stream>>>(n, idx, in, dst);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FVCR upload (side-based velocity dofs + element pressure); kernels in ns_fvcr.cuh
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_upload_mesh_fvcr(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_node, int64_t n_side, const int32_t* conn,
+                                    const int32_t* esides, const double* coords)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if ((elem != NSB_TRI && elem != NSB_TET)) return set_err(c, NSB_ERR_UNSUPPORTED, "FVCR: simplices (tri, tet) only; hanging-node / quad / hex CR geometries are out of scope");
+    if (n_elem <= 0 || n_node <= 0 || n_side <= 0 || !conn || !esides || !coords) return set_err(c, NSB_ERR_INVALID, "nsb_upload_mesh_fvcr: bad arguments");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    free_mesh(c);
+    const int nco = kNSH[elem], dim = kDIM[elem], ns = kNSIDE[elem];
+    c->elem = elem; c->disc = NSB_DISC_FVCR; c->n_elem = n_elem; c->n_node = n_node; c->n_side = n_side;
+    for (int64_t i = 0; i < n_elem * nco; i++) if (conn[i] < 0 || conn[i] >= n_node) return set_err(c, NSB_ERR_INVALID, "connectivity entry out of range");
+    EntityGraph g;
+    int rc = build_entity_graph(c, n_elem, n_side, ns, esides, g);
+    if (rc) return rc;
+    // scalar CSR: velocity rows (side s, d): neighbour sides x dim, then pressures of adjacent elements;
+    // pressure row e: its sides x dim (sorted), then itself.
+    const int64_t pbase = n_side * dim;
+    c->n_dof = pbase + n_elem;
+    std::vector<int64_t>& rp = c->h_brow; std::vector<int32_t>& ci = c->h_bcol;
+    rp.assign(c->n_dof + 1, 0);
+    for (int64_t s = 0; s < n_side; s++) {
+        const int64_t len = (g.brow[s + 1] - g.brow[s]) * dim + (g.adj_ptr[s + 1] - g.adj_ptr[s]);
+        for (int d = 0; d < dim; d++) rp[s * dim + d + 1] = len;
+    }
+    for (int64_t e = 0; e < n_elem; e++) rp[pbase + e + 1] = ns * dim + 1;
+    for (int64_t i = 0; i < c->n_dof; i++) rp[i + 1] += rp[i];
+    c->nnz = rp[c->n_dof];
+    if ((double)c->nnz >= 2147483647.0 * 4) return set_err(c, NSB_ERR_UNSUPPORTED, "FVCR grid too large");
+    ci.resize(c->nnz);
+    parallel_for(n_side, [&](int64_t lo, int64_t hi) {
+        for (int64_t s = lo; s < hi; s++) for (int d = 0; d < dim; d++) {
+            int64_t q = rp[s * dim + d];
+            for (int64_t kk = g.brow[s]; kk < g.brow[s + 1]; kk++) for (int d2 = 0; d2 < dim; d2++) ci[q++] = g.bcol[kk] * dim + d2;
+            for (int64_t kk = g.adj_ptr[s]; kk < g.adj_ptr[s + 1]; kk++) ci[q++] = (int32_t)(pbase + g.adj[kk] / ns);
+        }
+    });
+    std::vector<int32_t> psort((size_t)n_elem * ns);        // rank of local side k among the element's sorted sides
+    parallel_for(n_elem, [&](int64_t lo, int64_t hi) {
+        for (int64_t e = lo; e < hi; e++) {
+            int32_t tmp[6]; for (int kk = 0; kk < ns; kk++) tmp[kk] = esides[e * ns + kk];
+            std::sort(tmp, tmp + ns);
+            int64_t q = rp[pbase + e];
+            for (int kk = 0; kk < ns; kk++) for (int d2 = 0; d2 < dim; d2++) ci[q++] = tmp[kk] * dim + d2;
+            ci[q++] = (int32_t)(pbase + e);
+            for (int kk = 0; kk < ns; kk++) psort[e * ns + kk] = (int32_t)(std::lower_bound(tmp, tmp + ns, esides[e * ns + kk]) - tmp);
+        }
+    });
+    // scatter maps: slot of side k in the row of side a; slot of element e among the elements of side a
+    std::vector<uint8_t> emap; build_emap(n_elem, ns, esides, g, emap);
+    std::vector<uint8_t> pslot((size_t)n_elem * ns);
+    parallel_for(n_elem, [&](int64_t lo, int64_t hi) {
+        for (int64_t e = lo; e < hi; e++) for (int a = 0; a < ns; a++) {
+            const int32_t s = esides[e * ns + a];
+            int r = 0;
+            for (int64_t kk = g.adj_ptr[s]; kk < g.adj_ptr[s + 1]; kk++) if (g.adj[kk] / ns == e) r = (int)(kk - g.adj_ptr[s]);
+            pslot[e * ns + a] = (uint8_t)r;
+        }
+    });
+    std::vector<int32_t> order;
+    c->n_colors = color_elements(n_elem, n_side, ns, esides, order, c->h_color_ptr);
+    c->max_cnt = g.max_cnt;
+    // rowptr of velocity rows only needs (first value index, row length) per side
+    std::vector<int64_t> srow(n_side + 1);
+    for (int64_t s = 0; s <= n_side; s++) srow[s] = s < n_side ? rp[s * dim] : rp[pbase];
+    std::vector<int32_t> scnt(n_side);
+    for (int64_t s = 0; s < n_side; s++) scnt[s] = (int32_t)(g.brow[s + 1] - g.brow[s]);
+    CUDA_TRY(c, upload(&c->d_conn, conn, (size_t)n_elem * nco));
+    CUDA_TRY(c, upload(&c->d_coords, coords, (size_t)n_node * dim));
+    CUDA_TRY(c, upload(&c->d_esides, esides, (size_t)n_elem * ns));
+    CUDA_TRY(c, upload(&c->d_color_order, order.data(), order.size()));
+    FvcrDev& f = c->fvcr;
+    f.n_elem = n_elem; f.n_node = n_node; f.n_side = n_side; f.nnz = c->nnz; f.n_dof = c->n_dof;
+    f.conn = c->d_conn; f.coords = c->d_coords; f.esides = c->d_esides; f.color_order = c->d_color_order;
+    f.n_colors = c->n_colors; f.color_ptr = c->h_color_ptr.data();
+    CUDA_TRY(c, upload(&f.srow, srow.data(), srow.size()));
+    CUDA_TRY(c, upload(&f.scnt, scnt.data(), scnt.size()));
+    CUDA_TRY(c, upload(&f.emap, emap.data(), emap.size()));
+    CUDA_TRY(c, upload(&f.pslot, pslot.data(), pslot.size()));
+    CUDA_TRY(c, upload(&f.psort, psort.data(), psort.size()));
+    CUDA_TRY(c, upload(&f.sadj_ptr, g.adj_ptr.data(), g.adj_ptr.size()));
+    f.prow0 = rp[pbase];
+    c->mesh_ready = true;
+    return NSB_OK;
+}

@@ -1,0 +1,498 @@
+"""Host-side mirror of the reference's element-disc classes for the assembly path.
+
+Same names, setters, defaults and error behaviour as the UG4 plugin's Lua-visible classes (SURVEY.md
+App. D): NavierStokesFV1 / NavierStokesFVCR (+ the `NavierStokes(fcts, subsets, discType)` factory of
+lua/lua-include.lua:36-47), upwind names of upwind_interface.cpp:43-62, stabilisation names of
+fv1/stabilization.cpp:46-57,86-100.  Everything numerical happens in libnsb200.so (CUDA); this module
+only keeps the disc state and passes pointers.  ugcore's Domain / ApproximationSpace are replaced by
+`set_grid(elem, conn, coords)`; `assemble_jacobian` / `assemble_defect` play the role of ugcore's
+DomainDiscretization::assemble_* restricted to this disc.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+
+_UPWIND_NAMES = {  # upwind_interface.cpp:46-61 (trimmed, case-insensitive)
+    "no": 1, "full": 2, "skewed": 3, "linearprofileskewed": 4, "lps": 4, "positive": 5, "pos": 5,
+}
+_STAB_NAMES = {"fields": 0, "flow": 1}                      # stabilization.cpp:52-53
+_DIFF_NAMES = {"raw": 0, "fivepoint": 1, "cor": 2}          # stabilization.cpp:94-96
+_ELEMS = {"tri": capi.TRI, "quad": capi.QUAD, "tet": capi.TET, "hex": capi.HEX,
+          "triangle": capi.TRI, "quadrilateral": capi.QUAD, "tetrahedron": capi.TET, "hexahedron": capi.HEX}
+_NSH = {capi.TRI: 3, capi.QUAD: 4, capi.TET: 4, capi.HEX: 8}
+_DIM = {capi.TRI: 2, capi.QUAD: 2, capi.TET: 3, capi.HEX: 3}
+_NSIDE = {capi.TRI: 3, capi.QUAD: 4, capi.TET: 4, capi.HEX: 6}
+
+
+class UGError(RuntimeError):
+    """the counterpart of UG_THROW on this path"""
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class INavierStokesUpwind:
+    """marker objects mirroring the registered upwind classes (register_navier_stokes.cpp:156-228)"""
+    _id = 0
+
+    def __eq__(self, other):
+        return isinstance(other, INavierStokesUpwind) and other._id == self._id
+
+
+class NavierStokesNoUpwind(INavierStokesUpwind):
+    _id = 1
+
+
+class NavierStokesFullUpwind(INavierStokesUpwind):
+    _id = 2
+
+
+class NavierStokesSkewedUpwind(INavierStokesUpwind):
+    _id = 3
+
+
+class NavierStokesLinearProfileSkewedUpwind(INavierStokesUpwind):
+    _id = 4
+
+
+class NavierStokesPositiveUpwind(INavierStokesUpwind):
+    _id = 5
+
+
+class NavierStokesRegularUpwind(INavierStokesUpwind):
+    """2-D only in the reference (upwind.cpp:806); not provided on the device path."""
+    _id = 6
+
+
+def CreateNavierStokesUpwind(name):
+    n = name.strip().lower()
+    if n not in _UPWIND_NAMES and n not in ("regular", "reg"):
+        raise UGError("NavierStokes: upwind type '%s' not found. Options are: no, full, skewed, "
+                      "linearprofileskewed (lps), positive (pos), regular (reg)" % name)
+    if n in ("regular", "reg"):
+        return NavierStokesRegularUpwind()
+    cls = {1: NavierStokesNoUpwind, 2: NavierStokesFullUpwind, 3: NavierStokesSkewedUpwind,
+           4: NavierStokesLinearProfileSkewedUpwind, 5: NavierStokesPositiveUpwind}[_UPWIND_NAMES[n]]
+    return cls()
+
+
+class INavierStokesFV1Stabilization:
+    _id = -1
+
+    def __init__(self):
+        self._upwind = None
+        self._diff = 0          # RAW, stabilization.h:324
+
+    def set_upwind(self, upwind):
+        self._upwind = upwind
+
+    def upwind(self):
+        return self._upwind
+
+
+class INavierStokesSRFV1Stabilization(INavierStokesFV1Stabilization):
+    def set_diffusion_length(self, name):
+        n = name.strip().lower()
+        if n not in _DIFF_NAMES:
+            raise UGError("Diffusion Length calculation method not found. Use one of [Raw, Fivepoint, Cor].")
+        self._diff = _DIFF_NAMES[n]
+
+
+class NavierStokesFIELDSStabilization(INavierStokesSRFV1Stabilization):
+    _id = 0
+
+
+class NavierStokesFLOWStabilization(INavierStokesSRFV1Stabilization):
+    _id = 1
+
+
+class NavierStokesFV1WithoutStabilization(INavierStokesFV1Stabilization):
+    _id = 2
+
+
+def CreateNavierStokesStabilization(name):
+    n = name.strip().lower()
+    if n == "fields":
+        return NavierStokesFIELDSStabilization()
+    if n == "flow":
+        return NavierStokesFLOWStabilization()
+    raise UGError("NavierStokes: stabilization type '%s' not a valid name of a Schneider-Raw stabilization."
+                  " Options are: fields, flow" % name)
+
+
+class _DeviceDisc:
+    """shared machinery: context ownership, grid upload, the element loop on the device"""
+    _disc = capi.DISC_FV1
+
+    def __init__(self, fcts, subsets="", device=0):
+        if isinstance(fcts, str):
+            fcts = [f.strip() for f in fcts.split(",") if f.strip()]
+        self._fcts = list(fcts)
+        self._subsets = subsets
+        self._device = device
+        self._ctx = None
+        self._elem = None
+        self._time_dependent = False
+        # navier_stokes_base.cpp:53-67, incompressible_navier_stokes_base.cpp:53-66
+        self._exact_jac = 0.0
+        self._stokes = self._laplace = self._peclet = False
+        self._visc = None
+        self._density = 1.0
+        self._source = None
+        self._grad_div = 0.0
+        self._conv_upwind = None
+        self.scatter_mode = capi.SCATTER_GATHER
+
+    # ---- NavierStokesBase (register_navier_stokes.cpp:105-126) ----
+    def set_kinematic_viscosity(self, v):
+        if callable(v) or isinstance(v, str):
+            raise UGError("device path: kinematic viscosity must be a number (Lua/UserData callbacks cannot run on device)")
+        self._visc = float(v)
+
+    def set_source(self, v):
+        if callable(v) or isinstance(v, str):
+            raise UGError("device path: source must be a constant vector")
+        self._source = [float(x) for x in v]
+
+    def set_exact_jacobian(self, v):
+        # bool overload -> 1.0/0.0, number overload -> factor (navier_stokes_base.h)
+        self._exact_jac = float(v)
+
+    # ---- IncompressibleNavierStokesBase (incompressible_navier_stokes_plugin.cpp:244-266) ----
+    def set_density(self, v):
+        if callable(v) or isinstance(v, str):
+            raise UGError("device path: density must be a number")
+        self._density = float(v)
+
+    def set_peclet_blend(self, b):
+        self._peclet = bool(b)
+
+    def set_grad_div(self, f):
+        self._grad_div = float(f)
+
+    def set_laplace(self, b):
+        self._laplace = bool(b)
+
+    def set_stokes(self, b):
+        self._stokes = bool(b)
+
+    def requests_local_time_series(self):
+        return True                                   # navier_stokes_base.h:200
+
+    # ---- grid / context ----
+    def _context(self):
+        if self._ctx is None:
+            L = capi.lib()
+            ctx = C.c_void_p()
+            rc = L.nsb_create(self._device, C.byref(ctx))
+            if rc != 0:
+                raise UGError(L.nsb_last_error(None).decode())
+            self._ctx = ctx
+        return self._ctx
+
+    def _check(self, rc):
+        if rc != 0:
+            raise UGError(capi.lib().nsb_last_error(self._ctx).decode())
+
+    def __del__(self):
+        try:
+            if self._ctx is not None:
+                capi.lib().nsb_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    close = __del__
+
+    def _num_fct_check(self, dim):
+        if len(self._fcts) != dim + 1:           # fv1/navier_stokes_fv1.cpp:66, fvcr/navier_stokes_fvcr.cpp:67-68
+            raise UGError("Wrong number of functions: The ElemDisc 'NavierStokes' needs exactly %d symbolic function." % (dim + 1))
+
+    @property
+    def num_dofs(self):
+        return capi.lib().nsb_num_dofs(self._ctx)
+
+    @property
+    def nnz(self):
+        return capi.lib().nsb_nnz(self._ctx)
+
+    @property
+    def num_colors(self):
+        return capi.lib().nsb_num_colors(self._ctx)
+
+    @property
+    def launch_count(self):
+        return capi.lib().nsb_launch_count(self._ctx)
+
+    def csr(self):
+        """(rowptr int64 [ndof+1], colind int32 [nnz]) of the global Jacobian (sorted rows)"""
+        rowptr = np.empty(self.num_dofs + 1, dtype=np.int64)
+        colind = np.empty(self.nnz, dtype=np.int32)
+        self._check(capi.lib().nsb_get_csr(self._ctx, rowptr.ctypes.data, colind.ctypes.data))
+        return rowptr, colind
+
+    def use_stream(self, cuda_stream):
+        self._check(capi.lib().nsb_set_stream(self._context(), C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(capi.lib().nsb_synchronize(self._ctx))
+
+    def check_errors(self):
+        self._check(capi.lib().nsb_check_errors(self._ctx))
+
+    def _params(self):
+        raise NotImplementedError
+
+    def prep_elem_loop(self):
+        """validation of prep_elem_loop (throws like the reference)"""
+        p = self._params()
+        self._check(capi.lib().nsb_set_params(self._context(), C.byref(p)))
+        self._check(capi.lib().nsb_prep_elem_loop(self._ctx))
+
+    # ---- the element loop ----
+    @staticmethod
+    def _ptr(a):
+        if a is None:
+            return None
+        if _is_torch(a):
+            return C.c_void_p(a.data_ptr())
+        return C.c_void_p(a.ctypes.data)
+
+    def assemble(self, what, u, values=None, defect=None, time_series=None, scale_a=1.0, scale_m=1.0, beta=0.0,
+                 scatter_mode=None):
+        """values/defect := beta*old + scale_a*A-part + scale_m*M-part (see nsb_assemble).
+        u (and the optional (sol0, sol1, dt) time series) are numpy arrays (host path, copies inside the
+        call) or torch CUDA tensors (device path, asynchronous). Returns (values, defect)."""
+        L = capi.lib()
+        p = self._params()
+        self._check(L.nsb_set_params(self._context(), C.byref(p)))
+        on_dev = _is_torch(u)
+        jac = bool(what & (capi.JAC_A | capi.JAC_M))
+        dfc = bool(what & (capi.DEF_A | capi.DEF_M | capi.RHS))
+        if on_dev:
+            import torch
+            assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous()
+            if jac and values is None:
+                values = torch.empty(self.nnz, dtype=torch.float64, device=u.device)
+                beta = 0.0
+            if dfc and defect is None:
+                defect = torch.empty(self.num_dofs, dtype=torch.float64, device=u.device)
+                beta = 0.0
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+            if jac and values is None:
+                values = np.zeros(self.nnz)
+            if dfc and defect is None:
+                defect = np.zeros(self.num_dofs)
+        ts = None
+        keep = []
+        if time_series is not None:
+            s0, s1, dt = time_series
+            if not on_dev:
+                s0 = np.ascontiguousarray(s0, dtype=np.float64).reshape(-1)
+                s1 = np.ascontiguousarray(s1, dtype=np.float64).reshape(-1)
+            keep = [s0, s1]
+            ts = capi.TimeSeries(self._ptr(s0), self._ptr(s1), float(dt))
+        mode = self.scatter_mode if scatter_mode is None else scatter_mode
+        rc = L.nsb_assemble(self._ctx, what, mode, self._ptr(u), C.byref(ts) if ts is not None else None,
+                            float(scale_a), float(scale_m), float(beta), self._ptr(values) if jac else None,
+                            self._ptr(defect) if dfc else None, capi.DEVICE if on_dev else capi.HOST)
+        del keep
+        self._check(rc)
+        return values, defect
+
+    def assemble_jacobian(self, u, **kw):
+        return self.assemble(capi.JAC_A, u, **kw)[0]
+
+    def assemble_defect(self, u, **kw):
+        return self.assemble(capi.DEF_A | capi.RHS, u, **kw)[1]
+
+    def assemble_jacobian_defect(self, u, **kw):
+        return self.assemble(capi.JAC_A | capi.DEF_A | capi.RHS, u, **kw)
+
+
+class NavierStokesFV1(_DeviceDisc):
+    """fv1/navier_stokes_fv1.h -- registered at fv1/register_fv1.cpp:166-184"""
+    _disc = capi.DISC_FV1
+
+    def __init__(self, fcts, subsets="", device=0):
+        super().__init__(fcts, subsets, device)
+        self._stab = None
+        self._conv_stab = None
+
+    def disc_type(self):
+        return "fv1"
+
+    def use_hanging(self):
+        return False
+
+    # fv1/navier_stokes_fv1.h:185-225
+    def set_stabilization(self, stab, diff_length=None):
+        if isinstance(stab, str):
+            s = CreateNavierStokesStabilization(stab)
+            if diff_length is not None:
+                s.set_diffusion_length(diff_length)
+            self._stab = s
+            if self._conv_upwind is not None:
+                self._stab.set_upwind(self._conv_upwind)
+        else:
+            self._stab = stab
+
+    def stabilization(self):
+        return self._stab
+
+    def set_upwind(self, up):
+        if isinstance(up, str):
+            self._conv_stab = None
+            self._conv_upwind = CreateNavierStokesUpwind(up)
+            if self._stab is not None and self._stab.upwind() is None:
+                self._stab.set_upwind(self._conv_upwind)
+        elif isinstance(up, INavierStokesFV1Stabilization):
+            self._conv_stab = up
+            self._conv_upwind = None
+        else:
+            self._conv_stab = None
+            self._conv_upwind = up
+
+    def set_pac_upwind(self, b):
+        if b:
+            if self._conv_upwind is None:
+                raise UGError("Upwind must be specified previously.\n")
+            if self._stab is None:
+                raise UGError("Stabilization must be specified previously.\n")
+            self._stab.set_upwind(self._conv_upwind)
+            self.set_upwind(self._stab)
+
+    def set_grid(self, elem, conn, coords):
+        """upload grid connectivity + coordinates (replaces the Domain / DoFDistribution of ugcore)"""
+        e = _ELEMS[elem] if isinstance(elem, str) else int(elem)
+        self._num_fct_check(_DIM[e])
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        assert conn.shape[1] == _NSH[e] and coords.shape[1] == _DIM[e]
+        self._elem = e
+        self._check(capi.lib().nsb_upload_mesh(self._context(), e, conn.shape[0], coords.shape[0],
+                                               conn.ctypes.data, coords.ctypes.data))
+        self._n_elem = conn.shape[0]
+
+    def _params(self):
+        p = capi.Params()
+        capi.lib().nsb_params_default(C.byref(p))
+        p.disc = capi.DISC_FV1
+        pac = self._conv_stab is not None
+        if pac and self._conv_stab is not self._stab:
+            raise UGError("device path: a convective stabilisation different from the continuity stabilisation is not supported")
+        cu = self._stab.upwind() if (pac and self._stab is not None) else self._conv_upwind
+        if cu is not None and cu._id == 6:
+            raise UGError("device path: RegularUpwind is not provided")
+        p.conv_upwind = cu._id if cu is not None else 0
+        p.pac_upwind = int(pac)
+        if self._stab is not None:
+            p.stab = self._stab._id
+            su = self._stab.upwind()
+            p.stab_upwind = su._id if su is not None else 0
+            p.diff_length = self._stab._diff
+        p.stokes, p.laplace, p.peclet_blend = int(self._stokes), int(self._laplace), int(self._peclet)
+        p.exact_jacobian = self._exact_jac
+        p.kin_visc_set = int(self._visc is not None)
+        p.kin_visc = self._visc if self._visc is not None else 0.0
+        p.density_set = int(self._density is not None)
+        p.density = self._density if self._density is not None else 0.0
+        if self._source is not None:
+            p.has_source = 1
+            for d, v in enumerate(self._source[:3]):
+                p.source[d] = v
+        return p
+
+    def local_contributions(self, what, u, time_series=None):
+        """compat mode: per-element LocalMatrix / LocalVector blocks [n_elem, L, L], [n_elem, L]"""
+        L = capi.lib()
+        p = self._params()
+        self._check(L.nsb_set_params(self._context(), C.byref(p)))
+        nsh, nf = _NSH[self._elem], _DIM[self._elem] + 1
+        Ls = nsh * nf
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+        J = np.zeros((self._n_elem, Ls, Ls))
+        d = np.zeros((self._n_elem, Ls))
+        ts = None
+        if time_series is not None:
+            s0 = np.ascontiguousarray(time_series[0], dtype=np.float64).reshape(-1)
+            s1 = np.ascontiguousarray(time_series[1], dtype=np.float64).reshape(-1)
+            ts = capi.TimeSeries(self._ptr(s0), self._ptr(s1), float(time_series[2]))
+        self._check(L.nsb_local_contributions(self._ctx, what, self._ptr(u), C.byref(ts) if ts is not None else None,
+                                              self._ptr(J), self._ptr(d), capi.HOST))
+        return J, d
+
+
+class NavierStokesFVCR(_DeviceDisc):
+    """fvcr/navier_stokes_fvcr.h -- registered at fvcr/register_fvcr.cpp:289-303"""
+    _disc = capi.DISC_FVCR
+
+    def __init__(self, fcts, subsets="", device=0):
+        super().__init__(fcts, subsets, device)
+        self._defect_upwind = True                     # fvcr/navier_stokes_fvcr.cpp:82
+        self.scatter_mode = capi.SCATTER_COLORED
+
+    def disc_type(self):
+        return "fvcr"
+
+    def use_hanging(self):
+        return True                                    # fvcr/navier_stokes_fvcr.cpp:111-116
+
+    def set_upwind(self, up):
+        self._conv_upwind = CreateNavierStokesUpwind(up) if isinstance(up, str) else up
+
+    def set_defect_upwind(self, b):
+        self._defect_upwind = bool(b)
+
+    def set_grid(self, elem, conn, coords, elem_sides=None, n_side=None):
+        from . import meshgen
+        e = _ELEMS[elem] if isinstance(elem, str) else int(elem)
+        self._num_fct_check(_DIM[e])
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        if elem_sides is None:
+            name = {capi.TRI: "tri", capi.QUAD: "quad", capi.TET: "tet", capi.HEX: "hex"}[e]
+            elem_sides, n_side = meshgen.element_sides(name, conn)
+        es = np.ascontiguousarray(elem_sides, dtype=np.int32)
+        self._elem = e
+        self._check(capi.lib().nsb_upload_mesh_fvcr(self._context(), e, conn.shape[0], coords.shape[0], int(n_side),
+                                                    conn.ctypes.data, es.ctypes.data, coords.ctypes.data))
+        self._n_elem = conn.shape[0]
+        self.elem_sides, self.n_side = es, int(n_side)
+
+    def _params(self):
+        p = capi.Params()
+        capi.lib().nsb_params_default(C.byref(p))
+        p.disc = capi.DISC_FVCR
+        cu = self._conv_upwind
+        if cu is not None and cu._id == 6:
+            raise UGError("device path: RegularUpwind is not provided")
+        p.conv_upwind = cu._id if cu is not None else 0
+        p.defect_upwind = int(self._defect_upwind)
+        p.stokes, p.laplace, p.peclet_blend = int(self._stokes), int(self._laplace), int(self._peclet)
+        p.exact_jacobian = self._exact_jac
+        p.grad_div = self._grad_div
+        p.kin_visc_set = int(self._visc is not None)
+        p.kin_visc = self._visc if self._visc is not None else 0.0
+        p.density_set = 1
+        p.density = self._density
+        if self._source is not None:
+            p.has_source = 1
+            for d, v in enumerate(self._source[:3]):
+                p.source[d] = v
+        return p
+
+
+def NavierStokes(fcts, subsets, disc_type=None, device=0):
+    """lua/lua-include.lua:36-47"""
+    if disc_type is None or disc_type == "fv1":
+        return NavierStokesFV1(fcts, subsets, device)
+    if disc_type == "fvcr":
+        return NavierStokesFVCR(fcts, subsets, device)
+    if disc_type in ("fv", "fe", "fecr"):
+        raise UGError("NavierStokes: disc type '%s' is outside the device assembly path (fv1, fvcr)" % disc_type)
+    raise UGError("NavierStokes: no disc type '%s' available. Use 'fv1', 'fv', 'fvcr', 'fe' or 'fecr'." % disc_type)

@@ -1,0 +1,154 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerance: 1e-12 relative per defect entry / Jacobian nonzero (north_star); identical CSR sparsity."""
+import numpy as np
+import pytest
+
+import plugin_navierstokes_b200 as pkg
+from plugin_navierstokes_b200 import capi
+from tests import parity
+from tests.parity import TOL
+
+pytestmark = pytest.mark.gpu
+
+SIZES = {"tri": 9, "quad": 8, "tet": 4, "hex": 4}
+FCTS = {2: "u,v,p", 3: "u,v,w,p"}
+MODES = {"gather": capi.SCATTER_GATHER, "colored": capi.SCATTER_COLORED, "atomic": capi.SCATTER_ATOMIC}
+
+
+def _run_case(ora, elem, mode, upwind="full", stab="fields", diff="raw", what=None, time_dep=False, seed=0, **flags):
+    coords, conn, u = parity.make_case(elem, SIZES[elem], seed=seed)
+    dim = coords.shape[1]
+    E = ora.ELEM[elem]
+    disc = pkg.NavierStokesFV1(FCTS[dim], "Inner")
+    parity.configure(disc, upwind=upwind, stab=stab, diff=diff, **flags)
+    disc.set_grid(elem, conn, coords)
+    disc.prep_elem_loop()
+    rp, ci = disc.csr()
+    rowptr, colind = ora.fv1_csr(E, conn, coords.shape[0])
+    assert np.array_equal(rp, rowptr) and np.array_equal(ci, colind)
+    what = what if what is not None else (capi.JAC_A | capi.DEF_A)
+    ts, s0, s1, dt = None, None, None, 0.0
+    if time_dep:
+        dt = 0.05
+        s0 = u * 1.01 + 0.003
+        s1 = u * 0.97 - 0.002
+        ts = (s0, s1, dt)
+    p = ora.make_params(elem=elem, upwind=upwind, stab=stab, diff_len=diff, kin_visc=flags.get("visc", 1e-2),
+                        density=flags.get("density", 1.0), stokes=flags.get("stokes", False),
+                        laplace=flags.get("laplace", False), peclet_blend=flags.get("peclet", False),
+                        pac=flags.get("pac", False), exact_jac=flags.get("exact", 0.0),
+                        source=flags.get("source"), dt=dt, time_dependent=time_dep,
+                        stab_upwind=flags.get("stab_upwind") or "same")
+    sa, sm = (0.7, 1.3) if (what & (capi.JAC_M | capi.DEF_M)) else (1.0, 1.0)
+    ov, od = ora.assemble(p, conn, coords, u, rowptr, colind, what, sol0=s0, sol1=s1, scale_a=sa, scale_m=sm)
+    gv, gd = disc.assemble(what, u, time_series=ts, scale_a=sa, scale_m=sm, scatter_mode=MODES[mode])
+    if what & (capi.JAC_A | capi.JAC_M):
+        eg, ee = parity.entry_errors(gv, ov, rowptr)
+        assert eg < TOL and ee < TOL, ("jacobian", elem, mode, upwind, stab, eg, ee)
+    if what & (capi.DEF_A | capi.DEF_M | capi.RHS):
+        eg, ee = parity.entry_errors(gd, od)
+        assert eg < TOL and ee < TOL, ("defect", elem, mode, upwind, stab, eg, ee)
+    disc.close()
+
+
+@pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
+@pytest.mark.parametrize("mode", ["gather", "colored", "atomic"])
+@pytest.mark.parametrize("upwind", ["no", "full", "skewed", "lps"])
+@pytest.mark.parametrize("stab", ["fields", "flow", "none"])
+def test_stationary_jac_def(ora, elem, mode, upwind, stab):
+    _run_case(ora, elem, mode, upwind=upwind, stab=stab)
+
+
+@pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
+@pytest.mark.parametrize("mode", ["gather", "colored"])
+@pytest.mark.parametrize("flags", [
+    dict(exact=1.0), dict(peclet=True), dict(peclet=True, exact=0.5), dict(laplace=True), dict(stokes=True, upwind=None),
+    dict(pac=True), dict(pac=True, exact=1.0, peclet=True), dict(pac=True, stab="flow", exact=1.0),
+    dict(diff="fivepoint"), dict(diff="cor"), dict(stab="flow", diff="cor", upwind="lps"),
+    dict(density=1.3, visc=3e-3, source=[0.3, -0.2, 0.1]), dict(upwind="lps", stab_upwind="full"),
+], ids=lambda f: "-".join("%s=%s" % kv for kv in f.items()))
+def test_flags(ora, elem, mode, flags):
+    flags = dict(flags)
+    if "source" in flags and elem in ("tri", "quad"):
+        flags["source"] = flags["source"][:2]
+    _run_case(ora, elem, mode, **flags)
+
+
+@pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
+@pytest.mark.parametrize("mode", ["gather", "colored", "atomic"])
+@pytest.mark.parametrize("stab", ["fields", "flow"])
+def test_instationary_parts(ora, elem, mode, stab):
+    """two time points: 1/dt in the ip system, u_old/dt in its rhs, lumped mass + rhs parts, scales"""
+    src = [0.3, -0.2, 0.1][: (2 if elem in ("tri", "quad") else 3)]
+    what = capi.JAC_A | capi.DEF_A | capi.JAC_M | capi.DEF_M | capi.RHS
+    _run_case(ora, elem, mode, upwind="lps", stab=stab, what=what, time_dep=True, source=src, density=1.2)
+    _run_case(ora, elem, mode, upwind="full", stab=stab, what=capi.DEF_M | capi.JAC_M)
+
+
+@pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
+def test_local_contributions_match_oracle(ora, elem):
+    """compat mode of the IElemDisc slots: per-element LocalMatrix / LocalVector blocks"""
+    coords, conn, u = parity.make_case(elem, 3, seed=5)
+    dim = coords.shape[1]
+    disc = pkg.NavierStokesFV1(FCTS[dim], "Inner")
+    parity.configure(disc, upwind="lps", stab="flow", exact=1.0)
+    disc.set_grid(elem, conn, coords)
+    J, d = disc.local_contributions(capi.JAC_A | capi.DEF_A, u)
+    p = ora.make_params(elem=elem, upwind="lps", stab="flow", exact_jac=1.0)
+    for e in range(conn.shape[0]):
+        Jo, do = ora.fv1_elem(p, coords[conn[e]], u[conn[e]].T, ora.JAC_A | ora.DEF_A)
+        assert np.abs(J[e] - Jo).max() <= TOL * np.abs(Jo).max(), e
+        assert np.abs(d[e] - do).max() <= TOL * np.abs(do).max(), e
+
+
+def test_prep_elem_loop_errors_mirror_the_reference():
+    coords, conn, u = parity.make_case("quad", 3)
+    d = pkg.NavierStokesFV1("u,v,p", "Inner")
+    d.set_grid("quad", conn, coords)
+    d.set_kinematic_viscosity(0.01)
+    with pytest.raises(pkg.UGError, match="Stabilization has not been set"):
+        d.prep_elem_loop()
+    d.set_stabilization("fields")
+    with pytest.raises(pkg.UGError, match="Upwinding for convective Term"):
+        d.prep_elem_loop()
+    d.set_stokes(True)
+    d.prep_elem_loop()
+    d2 = pkg.NavierStokesFV1("u,v,p", "Inner")
+    d2.set_grid("quad", conn, coords)
+    d2.set_upwind("full")
+    d2.set_stabilization("fields")
+    with pytest.raises(pkg.UGError, match="Kinematic Viscosity has not been set"):
+        d2.prep_elem_loop()
+    with pytest.raises(pkg.UGError, match="Wrong number of functions"):
+        pkg.NavierStokesFV1("u,v,w,p", "Inner").set_grid("quad", conn, coords)
+
+
+def test_deterministic_modes_are_bitwise_reproducible():
+    coords, conn, u = parity.make_case("hex", 6, seed=9)
+    disc = pkg.NavierStokesFV1("u,v,w,p", "Inner")
+    parity.configure(disc, upwind="lps", stab="flow")
+    disc.set_grid("hex", conn, coords)
+    for mode in (capi.SCATTER_GATHER, capi.SCATTER_COLORED):
+        a = disc.assemble(capi.JAC_A | capi.DEF_A, u, scatter_mode=mode)
+        b = disc.assemble(capi.JAC_A | capi.DEF_A, u, scatter_mode=mode)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_device_pointer_path_and_beta():
+    import torch
+    coords, conn, u = parity.make_case("hex", 5, seed=3)
+    disc = pkg.NavierStokesFV1("u,v,w,p", "Inner")
+    parity.configure(disc, upwind="full", stab="fields")
+    disc.set_grid("hex", conn, coords)
+    hv, hd = disc.assemble(capi.JAC_A | capi.DEF_A, u)
+    ud = torch.from_numpy(u.reshape(-1)).cuda()
+    disc.use_stream(torch.cuda.current_stream().cuda_stream)
+    for mode in (capi.SCATTER_GATHER, capi.SCATTER_COLORED, capi.SCATTER_ATOMIC):
+        dv, dd = disc.assemble(capi.JAC_A | capi.DEF_A, ud, scatter_mode=mode)
+        disc.check_errors()
+        assert np.allclose(dv.cpu().numpy(), hv, rtol=1e-13, atol=1e-13 * np.abs(hv).max())
+        # accumulate a second time with beta = 1 -> exactly twice for the deterministic modes
+        dv2, dd2 = disc.assemble(capi.JAC_A | capi.DEF_A, ud, values=dv.clone(), defect=dd.clone(), beta=1.0, scatter_mode=mode)
+        disc.check_errors()
+        assert np.allclose(dv2.cpu().numpy(), 2 * hv, rtol=1e-12, atol=1e-12 * np.abs(hv).max())
+        assert np.allclose(dd2.cpu().numpy(), 2 * hd, rtol=1e-12, atol=1e-12 * np.abs(hd).max())
