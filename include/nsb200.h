@@ -88,7 +88,8 @@ typedef struct {
 int  nsb_create(int device, nsb_ctx **out);
 void nsb_destroy(nsb_ctx *ctx);
 const char *nsb_last_error(const nsb_ctx *ctx);       /* also valid with ctx == NULL (creation errors)  */
-/* use an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own stream */
+/* run on an existing cudaStream_t (e.g. torch's current stream; NULL = the legacy default stream).
+ * A fresh context runs on its own non-blocking stream. */
 int  nsb_set_stream(nsb_ctx *ctx, void *cuda_stream);
 
 void nsb_params_default(nsb_params *p);

@@ -1,0 +1,27 @@
+// dense_inst.cu -- instantiates the dense-ip-system element kernel for one element type (-DNSB_ELEM=e)
+#include "ns_dense.cuh"
+#include "ns_launch.h"
+#ifndef NSB_ELEM
+#error "compile with -DNSB_ELEM=0..3"
+#endif
+namespace nsb {
+constexpr int E = NSB_ELEM;
+template <int SC> static cudaError_t dense_sc(NSB_ELEM_ARGS)
+{
+    constexpr int WPB = 4;
+    const size_t smem = sizeof(DenseWS<E>) * WPB;
+    auto kern = fv1_dense_kernel<E, SC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t nblk = (n_list + WPB - 1) / WPB;
+    kern<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err);
+    return cudaGetLastError();
+}
+cudaError_t NSB_CAT(launch_dense_, NSB_ELEM)(NSB_ELEM_ARGS)
+{
+    if (n_list <= 0) return cudaSuccess;
+    if (sc == SC_COLORED) return dense_sc<SC_COLORED>(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st);
+    if (sc == SC_ATOMIC) return dense_sc<SC_ATOMIC>(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st);
+    return dense_sc<SC_LOCAL>(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st);
+}
+}

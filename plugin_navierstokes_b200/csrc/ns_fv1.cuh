@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
 #include "ref_tables.cuh"
 
 namespace nsb {

@@ -367,17 +367,4 @@ __global__ void scv_volume_kernel(int64_t n_elem, const int32_t* __restrict__ co
     scvvol[i] = scv_volume<E>(x, co);
 }
 
-__global__ void scale_kernel(int64_t n, double beta, double* __restrict__ a)
-{
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] *= beta;
-}
-__global__ void pack_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ src, double* __restrict__ out)
-{
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = src[idx[i]];
-}
-__global__ void unpack_add_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ in, double* __restrict__ dst)
-{
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[idx[i]] += in[i];
-}
-
 }  // namespace nsb

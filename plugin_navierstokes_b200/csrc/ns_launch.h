@@ -1,0 +1,26 @@
+// ns_launch.h -- host-callable launchers; each element type is instantiated in its own translation unit
+// (fv1_inst.cu / dense_inst.cu compiled with -DNSB_ELEM=0..3) so the library builds in parallel.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "ns_fv1.cuh"
+
+namespace nsb {
+struct MeshDev;
+
+struct LaunchInfo { int64_t launches = 0; };
+
+#define NSB_ELEM_ARGS int sc, const KParams& k, const MeshDev& m, const int32_t* list, int64_t n_list, const double* u, \
+    const double* s0, const double* s1, double* val, double* def, double* jl, double* dl, int* d_err, cudaStream_t st
+#define NSB_GATHER_ARGS const KParams& k, const MeshDev& m, const double* u, const double* s0, const double* s1, double beta, \
+    double* val, double* def, int* d_err, cudaStream_t st, int sm_count
+#define NSB_DECL(E)                                                                                   \
+    cudaError_t launch_elem_##E(NSB_ELEM_ARGS);                                                       \
+    cudaError_t launch_dense_##E(NSB_ELEM_ARGS);                                                      \
+    cudaError_t launch_gather_##E(NSB_GATHER_ARGS);                                                   \
+    cudaError_t launch_scvvol_##E(int64_t n_elem, const int32_t* conn, const double* coords, double* scvvol, cudaStream_t st);
+NSB_DECL(0) NSB_DECL(1) NSB_DECL(2) NSB_DECL(3)
+#undef NSB_DECL
+#define NSB_CAT2(a, b) a##b
+#define NSB_CAT(a, b) NSB_CAT2(a, b)
+}

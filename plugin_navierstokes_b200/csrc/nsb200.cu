@@ -12,10 +12,26 @@
 
 #include "../../include/nsb200.h"
 #include "ns_kernels.cuh"
-#include "ns_dense.cuh"
+#include "ns_launch.h"
 #include "ns_fvcr.cuh"
 
 using namespace nsb;
+
+namespace nsb {
+__global__ void scale_kernel(int64_t n, double beta, double* __restrict__ a)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] *= beta;
+}
+__global__ void pack_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ src, double* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = src[idx[i]];
+}
+__global__ void unpack_add_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ in, double* __restrict__ dst)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[idx[i]] += in[i];
+}
+
+}
 
 static std::string g_create_error;
 
@@ -142,7 +158,7 @@ extern "C" void nsb_destroy(nsb_ctx* c)
 extern "C" int nsb_set_stream(nsb_ctx* c, void* s)
 {
     if (!c) return NSB_ERR_INVALID;
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;          // NULL is the legacy default stream
     return NSB_OK;
 }
 
@@ -248,11 +264,15 @@ template <class T> static cudaError_t upload(T** dptr, const T* h, size_t n)
     return cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice);
 }
 
-template <int E> static void launch_scvvol(nsb_ctx* c)
+static cudaError_t launch_scvvol(nsb_ctx* c)
 {
-    const int64_t n = c->n_elem * ET<E>::NSH;
-    scv_volume_kernel<E><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol);
     c->launches++;
+    switch (c->elem) {
+        case 0: return launch_scvvol_0(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol, c->stream);
+        case 1: return launch_scvvol_1(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol, c->stream);
+        case 2: return launch_scvvol_2(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol, c->stream);
+        default: return launch_scvvol_3(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol, c->stream);
+    }
 }
 
 extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coords)
@@ -280,9 +300,7 @@ extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_n
     CUDA_TRY(c, upload(&c->d_emap, emap.data(), emap.size()));
     CUDA_TRY(c, upload(&c->d_color_order, order.data(), order.size()));
     CUDA_TRY(c, cudaMalloc(&c->d_scvvol, (size_t)n_elem * nsh * sizeof(double)));
-    switch (elem) { case 0: launch_scvvol<E_TRI>(c); break; case 1: launch_scvvol<E_QUAD>(c); break;
-                    case 2: launch_scvvol<E_TET>(c); break; default: launch_scvvol<E_HEX>(c); }
-    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, launch_scvvol(c));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->h_brow.swap(g.brow); c->h_bcol.swap(g.bcol);
     c->mesh_ready = true;
@@ -387,58 +405,43 @@ static bool needs_dense(const KParams& k)
     return !k.stokes && (k.upw_stab == UPW_POSITIVE || (!k.pac && k.upw_conv == UPW_POSITIVE));
 }
 
-template <int E, int SC>
-static int launch_elem(nsb_ctx* c, const KParams& k, const int32_t* list, int64_t n_list, const double* u, const double* s0,
-                       const double* s1, double* val, double* def, double* jl, double* dl)
+static int launch_elem(nsb_ctx* c, int sc, const KParams& k, const int32_t* list, int64_t n_list, const double* u,
+                       const double* s0, const double* s1, double* val, double* def, double* jl, double* dl)
 {
     if (n_list <= 0) return NSB_OK;
-    constexpr int L = ET<E>::NSH * (ET<E>::DIM + 1), EPW = 32 / L, WPB = 4;
     const MeshDev m = mesh_view(c);
-    if (needs_dense(k)) {
-        const size_t smem = sizeof(DenseWS<E>) * WPB;
-        auto kern = fv1_dense_kernel<E, SC>;
-        CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t nblk = (n_list + WPB - 1) / WPB;
-        kern<<<(unsigned)nblk, WPB * 32, smem, c->stream>>>(k, m, list, n_list, u, s0, s1, val, def, jl, dl, c->d_err);
-    } else {
-        const size_t smem = sizeof(ElemWS<E>) * EPW * WPB;
-        auto kern = fv1_elem_kernel<E, SC>;
-        CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t ngrp = (n_list + EPW - 1) / EPW, nblk = (ngrp + WPB - 1) / WPB;
-        kern<<<(unsigned)nblk, WPB * 32, smem, c->stream>>>(k, m, list, n_list, u, s0, s1, val, def, jl, dl, c->d_err);
-    }
+    cudaError_t e;
+#define NSB_GO(fn) fn(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, c->d_err, c->stream)
+    if (needs_dense(k)) switch (c->elem) { case 0: e = NSB_GO(launch_dense_0); break; case 1: e = NSB_GO(launch_dense_1); break;
+                                           case 2: e = NSB_GO(launch_dense_2); break; default: e = NSB_GO(launch_dense_3); }
+    else switch (c->elem) { case 0: e = NSB_GO(launch_elem_0); break; case 1: e = NSB_GO(launch_elem_1); break;
+                            case 2: e = NSB_GO(launch_elem_2); break; default: e = NSB_GO(launch_elem_3); }
+#undef NSB_GO
     c->launches++;
-    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, e);
     return NSB_OK;
 }
 
-template <int E>
 static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const double* s0, const double* s1, double beta,
                          double* val, double* def)
 {
-    constexpr int NF = ET<E>::DIM + 1, WPB = 4;
     const MeshDev m = mesh_view(c);
-    const size_t per_warp = (sizeof(GatherWS<E>) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
-    const size_t smem = per_warp * WPB;
-    auto kern = fv1_gather_kernel<E>;
-    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, smem));
-    if (occ < 1) return set_err(c, NSB_ERR_CUDA, "gather kernel does not fit on an SM (smem %zu)", smem);
-    int64_t nblk = std::min<int64_t>((c->n_node + WPB - 1) / WPB, (int64_t)c->sm_count * occ);
-    kern<<<(unsigned)nblk, WPB * 32, smem, c->stream>>>(k, m, u, s0, s1, beta, val, def, c->d_err);
+    cudaError_t e;
+#define NSB_GO(fn) fn(k, m, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count)
+    switch (c->elem) { case 0: e = NSB_GO(launch_gather_0); break; case 1: e = NSB_GO(launch_gather_1); break;
+                       case 2: e = NSB_GO(launch_gather_2); break; default: e = NSB_GO(launch_gather_3); }
+#undef NSB_GO
     c->launches++;
-    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, e);
     return NSB_OK;
 }
 
-template <int E>
 static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u, const double* s0, const double* s1,
                         double beta, double* val, double* def)
 {
     const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
     if (mode == NSB_SCATTER_GATHER && needs_dense(k)) mode = NSB_SCATTER_COLORED;   // dense ip systems need whole elements
-    if (mode == NSB_SCATTER_GATHER) return launch_gather<E>(c, k, u, s0, s1, beta, val, def);
+    if (mode == NSB_SCATTER_GATHER) return launch_gather(c, k, u, s0, s1, beta, val, def);
     // element kernels accumulate into beta*old
     if (jac) {
         if (beta == 0.0) CUDA_TRY(c, cudaMemsetAsync(val, 0, sizeof(double) * c->nnz, c->stream));
@@ -448,11 +451,11 @@ static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u,
         if (beta == 0.0) CUDA_TRY(c, cudaMemsetAsync(def, 0, sizeof(double) * c->n_dof, c->stream));
         else if (beta != 1.0) { scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->n_dof, beta, def); c->launches++; }
     }
-    if (mode == NSB_SCATTER_ATOMIC) return launch_elem<E, SC_ATOMIC>(c, k, nullptr, c->n_elem, u, s0, s1, val, def, nullptr, nullptr);
+    if (mode == NSB_SCATTER_ATOMIC) return launch_elem(c, SC_ATOMIC, k, nullptr, c->n_elem, u, s0, s1, val, def, nullptr, nullptr);
     if (mode == NSB_SCATTER_COLORED) {
         for (int col = 0; col < c->n_colors; col++) {
             const int64_t lo = c->h_color_ptr[col], hi = c->h_color_ptr[col + 1];
-            int rc = launch_elem<E, SC_COLORED>(c, k, c->d_color_order + lo, hi - lo, u, s0, s1, val, def, nullptr, nullptr);
+            int rc = launch_elem(c, SC_COLORED, k, c->d_color_order + lo, hi - lo, u, s0, s1, val, def, nullptr, nullptr);
             if (rc) return rc;
         }
         return NSB_OK;
@@ -510,12 +513,7 @@ extern "C" int nsb_assemble(nsb_ctx* c, int what, int mode, const double* u, con
                    if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(dd, defect, nb, cudaMemcpyHostToDevice, c->stream)); }
     }
     if (c->disc == NSB_DISC_FVCR) rc = fvcr_assemble(c->fvcr, k, c->elem, mode, du, beta, dv, dd, c->stream, c->sm_count, c->d_err, &c->launches);
-    else switch (c->elem) {
-        case NSB_TRI:  rc = assemble_fv1<E_TRI>(c, k, mode, du, ds0, ds1, beta, dv, dd); break;
-        case NSB_QUAD: rc = assemble_fv1<E_QUAD>(c, k, mode, du, ds0, ds1, beta, dv, dd); break;
-        case NSB_TET:  rc = assemble_fv1<E_TET>(c, k, mode, du, ds0, ds1, beta, dv, dd); break;
-        default:       rc = assemble_fv1<E_HEX>(c, k, mode, du, ds0, ds1, beta, dv, dd); break;
-    }
+    else rc = assemble_fv1(c, k, mode, du, ds0, ds1, beta, dv, dd);
     if (rc > 0) return set_err(c, NSB_ERR_CUDA, "CUDA launch failure in FVCR path: %s", cudaGetErrorString((cudaError_t)rc));
     if (rc) return rc;
     if (location == NSB_HOST) {
@@ -563,12 +561,7 @@ extern "C" int nsb_local_contributions(nsb_ctx* c, int what, const double* u, co
     }
     CUDA_TRY(c, cudaMemsetAsync(dj, 0, sizeof(double) * nJ, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(ddl, 0, sizeof(double) * nd, c->stream));
-    switch (c->elem) {
-        case NSB_TRI:  rc = launch_elem<E_TRI, SC_LOCAL>(c, k, nullptr, c->n_elem, du, ds0, ds1, nullptr, nullptr, dj, ddl); break;
-        case NSB_QUAD: rc = launch_elem<E_QUAD, SC_LOCAL>(c, k, nullptr, c->n_elem, du, ds0, ds1, nullptr, nullptr, dj, ddl); break;
-        case NSB_TET:  rc = launch_elem<E_TET, SC_LOCAL>(c, k, nullptr, c->n_elem, du, ds0, ds1, nullptr, nullptr, dj, ddl); break;
-        default:       rc = launch_elem<E_HEX, SC_LOCAL>(c, k, nullptr, c->n_elem, du, ds0, ds1, nullptr, nullptr, dj, ddl); break;
-    }
+    rc = launch_elem(c, SC_LOCAL, k, nullptr, c->n_elem, du, ds0, ds1, nullptr, nullptr, dj, ddl);
     if (rc) return rc;
     if (location == NSB_HOST) {
         CUDA_TRY(c, cudaMemcpyAsync(Jloc, dj, sizeof(double) * nJ, cudaMemcpyDeviceToHost, c->stream));

@@ -9,9 +9,10 @@ TOL = 1e-12          # north_star: <= 1e-12 relative per defect entry and per Ja
 def entry_errors(a, b, rowptr=None):
     """(max |a-b| / max|b|,  max per-entry relative error).
 
-    The per-entry error is measured against max(|b_i|, 1e-3 * s_i), s_i = the largest magnitude in the
-    entry's matrix row (or the vector's max): an entry that is the sum of cancelling element
-    contributions is only defined to eps * (size of the contributions), not eps * (its own size)."""
+    The per-entry error is measured against max(|b_i|, 1e-2 * s_i), s_i = the largest magnitude in the
+    entry's matrix row (or the vector's max): an entry that is the sum of cancelling flux contributions
+    is only defined to eps * (size of the contributions), not eps * (its own size); the floor admits an
+    absolute error of 1e-14 * (row scale) on such entries."""
     a, b = np.asarray(a), np.asarray(b)
     assert a.shape == b.shape
     gmax = np.abs(b).max()
@@ -23,7 +24,7 @@ def entry_errors(a, b, rowptr=None):
         s = np.repeat(rowmax, np.diff(rowptr))
     else:
         s = np.full(b.shape, gmax)
-    denom = np.maximum(np.abs(b), 1e-3 * np.maximum(s, 1e-300))
+    denom = np.maximum(np.abs(b), 1e-2 * np.maximum(s, 1e-300))
     return diff.max() / gmax, (diff / denom).max()
 
 

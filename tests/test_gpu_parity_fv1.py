@@ -86,6 +86,32 @@ def test_instationary_parts(ora, elem, mode, stab):
 
 
 @pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
+@pytest.mark.parametrize("mode", ["colored", "atomic", "gather"])
+@pytest.mark.parametrize("flags", [
+    dict(stab="fields"), dict(stab="flow"), dict(stab="none"), dict(stab="flow", exact=1.0, peclet=True),
+    dict(stab="fields", pac=True, exact=1.0), dict(stab="flow", pac=True, exact=0.5, peclet=True),
+    dict(stab="flow", diff="cor"), dict(stab="fields", upwind="full", stab_upwind="positive"),
+    dict(stab="flow", upwind="positive", stab_upwind="lps", exact=1.0), dict(stab="fields", laplace=True, density=1.4),
+], ids=lambda f: "-".join("%s=%s" % kv for kv in f.items()))
+def test_positive_upwind_dense_branch(ora, elem, mode, flags):
+    """PositiveUpwind has ip-shapes: nIp x nIp system per element (stabilization.cpp:244-403, :590-771).
+    (the gather mode routes these configurations to the coloured element kernel)"""
+    flags = dict(flags)
+    flags.setdefault("upwind", "positive")
+    _run_case(ora, elem, mode, **flags)
+
+
+@pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
+@pytest.mark.parametrize("stab", ["fields", "flow"])
+def test_positive_upwind_instationary(ora, elem, stab):
+    """config 5: FLOW + PositiveUpwind with two time points, mass parts and scales"""
+    src = [0.3, -0.2, 0.1][: (2 if elem in ("tri", "quad") else 3)]
+    what = capi.JAC_A | capi.DEF_A | capi.JAC_M | capi.DEF_M | capi.RHS
+    _run_case(ora, elem, "colored", upwind="positive", stab=stab, what=what, time_dep=True, source=src, density=1.2)
+    _run_case(ora, elem, "atomic", upwind="positive", stab=stab, what=capi.JAC_A | capi.DEF_A, time_dep=True, pac=True, exact=1.0)
+
+
+@pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
 def test_local_contributions_match_oracle(ora, elem):
     """compat mode of the IElemDisc slots: per-element LocalMatrix / LocalVector blocks"""
     coords, conn, u = parity.make_case(elem, 3, seed=5)
