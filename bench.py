@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- the round contract benchmark.
+
+Metric (BASELINE.json): elements assembled per second for the FV1 Jacobian + defect of the incompressible
+Navier-Stokes system, workload = config 3 (3-D cavity, hexahedra, LinearProfileSkewedUpwind + FIELDS/RAW,
+nu = 1e-2) at the single-GPU share of the 368^3 mesh: 184^3 = 6.23 M elements per GPU (weak scaling:
+N GPUs assemble N such blocks of one (2x2x2-blocked) global mesh and sum interface rows over NCCL).
+
+A "step" = one pass of the hot path over the mesh: Jacobian AND defect of the stiffness part for every
+element, scattered into the global CSR matrix / defect vector.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 184] [--mode gather|colored|atomic]
+  python bench.py --impl reference ...     # the reference arm: CPU oracle on the host cores
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fv1_jacobian_defect_elements_assembled_per_s"
+UNIT = "elements/s"
+VISC = 1e-2
+UPWIND, STAB = "lps", "fields"
+
+
+def algorithmic_bytes(n_elem, n_node, nsh, dim, n_dof, nnz, n_timepoints=1):
+    """connectivity + coordinates + state + every Jacobian nonzero written once + defect"""
+    return 4 * nsh * n_elem + 8 * dim * n_node + 8 * n_dof * n_timepoints + 8 * nnz + 8 * n_dof
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_problem(n, rank=0, world=1):
+    """the rank's block of the global hex mesh + state (config 3). Returns dict."""
+    from plugin_navierstokes_b200 import meshgen
+    if world == 1:
+        coords, conn = meshgen.hex_grid(n, n, n)
+        u = meshgen.state_vortex3d(coords, seed=3)
+        return dict(coords=coords, conn=conn, u=u, iface=None)
+    from plugin_navierstokes_b200 import partition
+    return partition.block_problem(n, rank, world)
+
+
+def cpu_baseline(n_sample, threads, sweeps=1):
+    """the CPU oracle ("port" of the reference's element routines, UG4-like loop: separate Jacobian and
+    defect sweeps, each rebuilding geometry + stabilisation) on a bounded sample of the same workload"""
+    from oracle import oracle as ora
+    from plugin_navierstokes_b200 import meshgen
+    coords, conn = meshgen.hex_grid(n_sample, n_sample, n_sample)
+    u = meshgen.state_vortex3d(coords, seed=3)
+    p = ora.make_params(elem="hex", upwind=UPWIND, stab=STAB, kin_visc=VISC)
+    rowptr, colind = ora.fv1_csr(ora.HEX, conn, coords.shape[0])
+    vals, dfc = np.zeros(colind.size), np.zeros(rowptr.size - 1)
+    best = None
+    for _ in range(sweeps):
+        vals[:] = 0
+        dfc[:] = 0
+        t0 = time.perf_counter()
+        ora.assemble(p, conn, coords, u, rowptr, colind, ora.JAC_A, nthreads=threads, values=vals, defect=dfc)
+        ora.assemble(p, conn, coords, u, rowptr, colind, ora.DEF_A, nthreads=threads, values=vals, defect=dfc)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return conn.shape[0] / best, conn.shape[0], best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path. The UG4 plugin cannot be compiled here (ugcore absent),
+    so this is the oracle port, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = args.ref_n
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, ne, dt = cpu_baseline(n_sample, threads)
+        if i >= args.warmup:
+            rates.append((r, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([dt for _, dt in rates])) * 1e3
+    sample = "hex %d^3 (%d elements) of config 3, Jacobian sweep + defect sweep, %d OpenMP threads" % (n_sample, n_sample ** 3, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config3: FV1 hex %d^3 per GPU, LPS upwind + FIELDS/RAW, nu=1e-2, Jacobian+defect (A part)" % args.n,
+                   "reference_kind": "oracle port of the UG4 element routines (UG4 itself not buildable: ugcore absent)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--n", type=int, default=184, help="hex cells per direction per GPU (config 3: 184)")
+    ap.add_argument("--mode", default="gather", choices=["gather", "colored", "atomic"])
+    ap.add_argument("--ref-n", type=int, default=64, help="cells per direction of the CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import plugin_navierstokes_b200 as pkg
+    from plugin_navierstokes_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    prob = build_problem(args.n, rank, world)
+    coords, conn, u = prob["coords"], prob["conn"], prob["u"]
+    disc = pkg.NavierStokes("u,v,w,p", "Inner", "fv1", device=local)
+    disc.set_kinematic_viscosity(VISC)
+    disc.set_upwind(UPWIND)
+    disc.set_stabilization(STAB)
+    disc.set_grid("hex", conn, coords)
+    disc.prep_elem_loop()
+    mode = {"gather": capi.SCATTER_GATHER, "colored": capi.SCATTER_COLORED, "atomic": capi.SCATTER_ATOMIC}[args.mode]
+    what = capi.JAC_A | capi.DEF_A
+    n_elem, n_node = conn.shape[0], coords.shape[0]
+    nnz, n_dof = disc.nnz, disc.num_dofs
+    abytes = algorithmic_bytes(n_elem, n_node, 8, 3, n_dof, nnz)
+
+    disc.use_stream(torch.cuda.current_stream().cuda_stream)
+    ud = torch.from_numpy(np.ascontiguousarray(u.reshape(-1))).to(dev)
+    vals = torch.empty(nnz, dtype=torch.float64, device=dev)
+    dfc = torch.empty(n_dof, dtype=torch.float64, device=dev)
+    exch = None
+    if world > 1:
+        from plugin_navierstokes_b200 import partition
+        exch = partition.InterfaceExchange(disc, prob["iface"], dev)
+
+    def step():
+        disc.assemble(what, ud, values=vals, defect=dfc, scatter_mode=mode)
+        if exch is not None:
+            exch.sum_to_owner(vals, dfc)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    disc.check_errors()
+    l0 = disc.launch_count + (exch.launches if exch else 0)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    kernel_ms = []
+    ev[0].record()
+    for i in range(args.steps):
+        ev[2 * i + 1].record()
+        disc.assemble(what, ud, values=vals, defect=dfc, scatter_mode=mode)
+        ev[2 * i + 2].record()
+        if exch is not None:
+            exch.sum_to_owner(vals, dfc)
+    ev[-1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    disc.check_errors()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]
+    launches = disc.launch_count + (exch.launches if exch else 0) - l0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    ne = torch.tensor([float(n_elem)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ne, op=dist.ReduceOp.SUM)
+    total_ms = float(t.item())
+    total_elems = float(ne.item())
+    ms_per_step = total_ms / args.steps
+    value = total_elems / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            hu = torch.from_numpy(np.ascontiguousarray(u.reshape(-1))).pin_memory()
+            hv = torch.empty(nnz, dtype=torch.float64).pin_memory()
+            hd = torch.empty(n_dof, dtype=torch.float64).pin_memory()
+            del vals
+            torch.cuda.empty_cache()
+            disc.assemble(what, hu.numpy(), values=hv.numpy(), defect=hd.numpy(), scatter_mode=mode)   # warm-up, allocates staging
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                disc.assemble(what, hu.numpy(), values=hv.numpy(), defect=hd.numpy(), scatter_mode=mode)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / args.e2e_steps
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e = {"value": total_elems / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(8 * n_dof),
+                   "d2h_bytes_per_step": int(8 * (nnz + n_dof)),
+                   "note": "nsb_assemble(NSB_HOST): u from pinned host memory, CSR values + defect returned to pinned host memory"}
+        except Exception as ex:       # noqa: BLE001
+            e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        kms = float(np.mean(kernel_ms))
+        achieved = abytes / (kms * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu:
+            threads = os.cpu_count() or 1
+            r, ne_s, dt = cpu_baseline(args.ref_n, threads)
+            cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "hex %d^3 (%d elements) of the same workload, Jacobian sweep + defect sweep, %.1f s" % (args.ref_n, ne_s, dt)}
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.mode)
+            except Exception:
+                traffic = None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "config3: FV1 hex %d^3 per GPU (%d elements/GPU), LPS upwind + FIELDS/RAW, nu=1e-2, "
+                                   "Jacobian+defect (A part) into global CSR" % (args.n, n_elem),
+                       "scatter": args.mode, "l2": "inputs+outputs (%.1f GB) exceed L2, no flush needed" % (abytes / 1e9),
+                       "algorithmic_bytes_per_element": abytes / n_elem, "nnz": int(nnz), "colors": disc.num_colors},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kms,
+                         "kernel": "fv1 %s (all launches of one assembly pass)" % args.mode},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -6,22 +6,28 @@
 #endif
 namespace nsb {
 constexpr int E = NSB_ELEM;
-template <int SC> static cudaError_t dense_sc(NSB_ELEM_ARGS)
+template <int SC, bool PAC> static cudaError_t dense_sc(NSB_ELEM_ARGS)
 {
     constexpr int WPB = 4;
-    const size_t smem = sizeof(DenseWS<E>) * WPB;
-    auto kern = fv1_dense_kernel<E, SC>;
+    const size_t smem = sizeof(DenseWS<E, PAC>) * WPB;
+    auto kern = fv1_dense_kernel<E, SC, PAC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t nblk = (n_list + WPB - 1) / WPB;
     kern<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err);
     return cudaGetLastError();
 }
+#define NSB_FWD sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st
 cudaError_t NSB_CAT(launch_dense_, NSB_ELEM)(NSB_ELEM_ARGS)
 {
     if (n_list <= 0) return cudaSuccess;
-    if (sc == SC_COLORED) return dense_sc<SC_COLORED>(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st);
-    if (sc == SC_ATOMIC) return dense_sc<SC_ATOMIC>(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st);
-    return dense_sc<SC_LOCAL>(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st);
+    if (k.pac) {
+        if (sc == SC_COLORED) return dense_sc<SC_COLORED, true>(NSB_FWD);
+        if (sc == SC_ATOMIC) return dense_sc<SC_ATOMIC, true>(NSB_FWD);
+        return dense_sc<SC_LOCAL, true>(NSB_FWD);
+    }
+    if (sc == SC_COLORED) return dense_sc<SC_COLORED, false>(NSB_FWD);
+    if (sc == SC_ATOMIC) return dense_sc<SC_ATOMIC, false>(NSB_FWD);
+    return dense_sc<SC_LOCAL, false>(NSB_FWD);
 }
 }

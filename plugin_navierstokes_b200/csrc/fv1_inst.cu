@@ -8,32 +8,37 @@
 namespace nsb {
 constexpr int E = NSB_ELEM;
 
-template <int SC> static cudaError_t elem_sc(NSB_ELEM_ARGS)
+template <int SC, bool PAC> static cudaError_t elem_sc(NSB_ELEM_ARGS)
 {
     constexpr int L = ET<E>::NSH * (ET<E>::DIM + 1), EPW = 32 / L, WPB = 4;
-    const size_t smem = sizeof(ElemWS<E>) * EPW * WPB;
-    auto kern = fv1_elem_kernel<E, SC>;
+    const size_t smem = sizeof(ElemWS<E, PAC>) * EPW * WPB;
+    auto kern = fv1_elem_kernel<E, SC, PAC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t ngrp = (n_list + EPW - 1) / EPW, nblk = (ngrp + WPB - 1) / WPB;
     kern<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err);
     return cudaGetLastError();
 }
-
+#define NSB_FWD sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st
 cudaError_t NSB_CAT(launch_elem_, NSB_ELEM)(NSB_ELEM_ARGS)
 {
     if (n_list <= 0) return cudaSuccess;
-    if (sc == SC_COLORED) return elem_sc<SC_COLORED>(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st);
-    if (sc == SC_ATOMIC) return elem_sc<SC_ATOMIC>(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st);
-    return elem_sc<SC_LOCAL>(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, d_err, st);
+    if (k.pac) {
+        if (sc == SC_COLORED) return elem_sc<SC_COLORED, true>(NSB_FWD);
+        if (sc == SC_ATOMIC) return elem_sc<SC_ATOMIC, true>(NSB_FWD);
+        return elem_sc<SC_LOCAL, true>(NSB_FWD);
+    }
+    if (sc == SC_COLORED) return elem_sc<SC_COLORED, false>(NSB_FWD);
+    if (sc == SC_ATOMIC) return elem_sc<SC_ATOMIC, false>(NSB_FWD);
+    return elem_sc<SC_LOCAL, false>(NSB_FWD);
 }
 
-cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
+template <bool PAC> static cudaError_t gather_t(NSB_GATHER_ARGS)
 {
     constexpr int NF = ET<E>::DIM + 1, WPB = 4;
-    const size_t per_warp = (sizeof(GatherWS<E>) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
+    const size_t per_warp = (sizeof(GatherWS<E, PAC>) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
     const size_t smem = per_warp * WPB;
-    auto kern = fv1_gather_kernel<E>;
+    auto kern = fv1_gather_kernel<E, PAC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
@@ -43,6 +48,11 @@ cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
     const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
     kern<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, u, s0, s1, beta, val, def, d_err);
     return cudaGetLastError();
+}
+cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
+{
+    if (k.pac) return gather_t<true>(k, m, u, s0, s1, beta, val, def, d_err, st, sm_count);
+    return gather_t<false>(k, m, u, s0, s1, beta, val, def, d_err, st, sm_count);
 }
 
 cudaError_t NSB_CAT(launch_scvvol_, NSB_ELEM)(int64_t n_elem, const int32_t* conn, const double* coords, double* scvvol, cudaStream_t st)

@@ -14,7 +14,7 @@
 
 namespace nsb {
 
-template <int E> struct DenseWS {
+template <int E, bool PAC> struct DenseWS {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1;
     double x[NSH * DIM], u[NSH * NF], s0[NSH * NF], s1[NSH * NF], vol[NSH];
     int64_t rowbase[NSH];
@@ -31,11 +31,11 @@ template <int E> struct DenseWS {
     double M[NIP][NIP];
     int32_t perm[NIP];
     double sv[NIP][DIM][DIM][NSH], sp[NIP][DIM][NSH], svel[NIP][DIM];
-    IpRec<E> rec[NIP];
+    IpRec<E, PAC> rec[NIP];
 };
 
 // NavierStokesPositiveUpwind::compute (upwind.cpp:643-786) for the ip velocities sgn*std; all 32 lanes call.
-template <int E> NSB_DEV void positive_upwind(DenseWS<E>& ws, int lane, double sgn, int slot)
+template <int E, class WS> NSB_DEV void positive_upwind(WS& ws, int lane, double sgn, int slot)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NINC = ET<E>::NINC;
     const double eps = 2.220446049250313e-16 * 10;
@@ -97,7 +97,7 @@ template <int E> NSB_DEV void positive_upwind(DenseWS<E>& ws, int lane, double s
 }
 
 // per-ip upwinds (No/Full/Skewed/LPS) into the same shared layout; ip shapes are zero
-template <int E> NSB_DEV bool simple_upwind(DenseWS<E>& ws, int lane, int type, double sgn, int slot)
+template <int E, class WS> NSB_DEV bool simple_upwind(WS& ws, int lane, int type, double sgn, int slot)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP;
     bool ok = true;
@@ -122,7 +122,7 @@ template <int E> NSB_DEV bool simple_upwind(DenseWS<E>& ws, int lane, int type, 
     return ok;
 }
 
-template <int E, int SC>
+template <int E, int SC, bool PAC>
 __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, const int32_t* __restrict__ elem_list,
                                                         int64_t n_list, const double* __restrict__ u,
                                                         const double* __restrict__ s0, const double* __restrict__ s1,
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, L = NSH * NF, P = DIM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    DenseWS<E>& ws = reinterpret_cast<DenseWS<E>*>(smem_raw)[warp];
+    DenseWS<E, PAC>& ws = reinterpret_cast<DenseWS<E, PAC>*>(smem_raw)[warp];
     const int64_t li = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (li >= n_list) return;                               // whole warp leaves together
     const int64_t e = elem_list ? (int64_t)elem_list[li] : li;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                             if (flow) { const double s2 = ws.std[ip][d] * ws.G[ip][k][d2]; rhs += s2 * ws.s0[k * NF + d2]; ws.sv[ip][d][d2][k] = s2 / diag; }
                             else ws.sv[ip][d][d2][k] = 0.0;
                         }
-                        const double sumP = -1.0 * ws.G[ip][k][d] / p.rho;
+                        const double sumP = -1.0 * ws.G[ip][k][d] * p.inv_rho;
                         rhs += sumP * ws.s0[k * NF + P];
                         ws.sp[ip][d][k] = sumP / diag;
                     }
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                                 for (int q = 0; q < DIM; q++) if (q != d) v -= ws.std[ip][q] * ws.G[ip][k][q];
                             }
                         } else v = ws.std[ip][d] * ws.G[ip][k][d2];
-                    } else if (kind == 1) v = -1.0 * ws.G[ip][k][d] / p.rho;
+                    } else if (kind == 1) v = -1.0 * ws.G[ip][k][d] * p.inv_rho;
                     else {
                         v = p.has_source ? p.src[d] : 0.0;
                         if (p.time_dep) { double o = 0.0; for (int q = 0; q < NSH; q++) o += ws.N[ip][q] * ws.s1[q * NF + d]; v += o / p.dt; }
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                                 }
                             }
                             v += ws.s0[q * NF + d] * cv;
-                            v += ws.s0[q * NF + P] * (-1.0 * ws.G[ip][q][d] / p.rho);
+                            v += ws.s0[q * NF + P] * (-1.0 * ws.G[ip][q][d] * p.inv_rho);
                         }
                     }
                     bvec[i] = v;
@@ -343,29 +343,32 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
         }
     }
     __syncwarp();
-    // ---- R: transported velocity, blend, defect fluxes -> records ----
+    // ---- R: transported velocity, blend, defect fluxes, factored flux derivative -> records ----
     if (lane < NIP) {
         const int ip = lane;
-        IpRec<E>& r = ws.rec[ip];
+        IpRec<E, PAC>& r = ws.rec[ip];
         IpGeo<E> g;
         g.from = tab::EDGE[E][ip][0]; g.to = tab::EDGE[E][ip][1];
-        double std[DIM], U[DIM], w = 1.0;
+        double std[DIM], U[DIM], w = 1.0, up[NSH], cvx[NSH];
 #pragma unroll
         for (int d = 0; d < DIM; d++) { g.n[d] = ws.n[ip][d]; std[d] = ws.std[ip][d]; U[d] = 0.0; }
-        for (int k = 0; k < NSH; k++) { r.up[k] = 0.0; r.cvx[k] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < NSH; k++) { up[k] = 0.0; cvx[k] = 0.0; g.N[k] = ws.N[ip][k]; for (int d = 0; d < DIM; d++) g.G[k][d] = ws.G[ip][k][d]; }
         if (!p.stokes) {
-            if (p.pac) { for (int d = 0; d < DIM; d++) U[d] = ws.svel[ip][d]; }
+            if constexpr (PAC) { for (int d = 0; d < DIM; d++) U[d] = ws.svel[ip][d]; }
             else {
+#pragma unroll
                 for (int k = 0; k < NSH; k++) {
                     const double s = ws.ush[cslot][ip][k];
-                    r.up[k] = s;
+                    up[k] = s;
                     for (int d = 0; d < DIM; d++) U[d] += s * ws.u[k * NF + d];
                 }
                 if (conv_pos) {                              // upwind_vel with ip shapes, upwind_interface.h:351-356
                     for (int j = 0; j < NIP; j++) {
                         const double s = ws.uip[cslot][ip][j];
                         for (int d = 0; d < DIM; d++) U[d] += s * ws.std[j][d];
-                        for (int k = 0; k < NSH; k++) r.cvx[k] += ws.N[j][k] * s;      // fv1/navier_stokes_fv1.cpp:441-448
+#pragma unroll
+                        for (int k = 0; k < NSH; k++) cvx[k] += ws.N[j][k] * s;      // fv1/navier_stokes_fv1.cpp:441-448
                     }
                 }
             }
@@ -375,10 +378,10 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
         if (p.what & W_DEF_A) {
             double gv[DIM][DIM];
             for (int d1 = 0; d1 < DIM; d1++) for (int d2 = 0; d2 < DIM; d2++) {
-                double s = 0; for (int k = 0; k < NSH; k++) s += ws.G[ip][k][d2] * ws.u[k * NF + d1];
+                double s = 0; for (int k = 0; k < NSH; k++) s += g.G[k][d2] * ws.u[k * NF + d1];
                 gv[d1][d2] = s;
             }
-            double pr = 0; for (int k = 0; k < NSH; k++) pr += ws.N[ip][k] * ws.u[k * NF + P];
+            double pr = 0; for (int k = 0; k < NSH; k++) pr += g.N[k] * ws.u[k * NF + P];
             for (int d1 = 0; d1 < DIM; d1++) {
                 double df = 0;
                 for (int d2 = 0; d2 < DIM; d2++) df += gv[d1][d2] * g.n[d2];
@@ -390,10 +393,10 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
             }
             r.F[P] = dotv<DIM>(ws.svel[ip], g.n) * p.rho;
         }
-#pragma unroll
-        for (int d = 0; d < DIM; d++) { r.n[d] = g.n[d]; r.std[d] = std[d]; r.U[d] = U[d]; }
-        r.prod = prod; r.w = w; r.invdiag = 0.0;
-        for (int k = 0; k < NSH; k++) { r.N[k] = ws.N[ip][k]; r.sb[k] = 0.0; for (int d = 0; d < DIM; d++) r.G[k][d] = ws.G[ip][k][d]; }
+        if (p.what & W_JAC_A) {
+            StabDense<E> S{&ws.sv[ip][0][0][0], &ws.sp[ip][0][0]};
+            ip_coeffs<E, PAC>(p, g.n, g.N, g.G, up, cvx, U, w, prod, S, p.stab == STAB_FLOW, r);
+        }
     }
     __syncwarp();
     // ---- C: column phase ----
@@ -404,13 +407,11 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
 #pragma unroll
         for (int i = 0; i < L; i++) acc[i] = 0.0;
         if (p.what & W_JAC_A) {
-            const bool connected = (p.stab == STAB_FLOW);
             static_for<NIP>([&](auto ipc) {
                 constexpr int ip = decltype(ipc)::value;
                 constexpr int f = edge_corner<E>(ip, 0), t = edge_corner<E>(ip, 1);
-                StabDense<E> S{&ws.sv[ip][0][0][0], &ws.sp[ip][0][0]};
                 double v[NF];
-                jac_col<E>(p, ws.rec[ip], S, connected, k, cf, v);
+                jac_col<E, PAC>(ws.rec[ip], k, cf, v);
 #pragma unroll
                 for (int rf = 0; rf < NF; rf++) { acc[f * NF + rf] += v[rf]; acc[t * NF + rf] -= v[rf]; }
             });

@@ -32,7 +32,7 @@ struct KParams {
     int upw_stab, upw_conv, stab, diff_len;
     int stokes, laplace, peclet, pac, time_dep, has_source;
     int what, pad;
-    double exact_jac, visc, rho, dt, scale_a, scale_m;
+    double exact_jac, visc, rho, inv_rho, dt, scale_a, scale_m;
     double src[3];
 };
 
@@ -389,44 +389,50 @@ template <int DIM> NSB_DEV double diff_len_sq_inv(int type, double nn, double vo
 
 // ------------------------------------------------------------------------------------------------
 // Record of one ip, parked in shared memory between the per-ip phase and the column phase.
+// It holds the flux derivative B(rf, cf; k) of add_jac_A_elem (fv1/navier_stokes_fv1.cpp:317-594) in a
+// column-ready factored form, so the column phase is (almost) pure accumulation:
+//     B(d1,d2;k) = A[k][d1]*n[d2] + delta(d1,d2)*D[k]  (+ Q[k][d1][d2] when the stabilisation is the upwind, PAC)
+//     B(d1,P ;k) = N[k]*n[d1]                          (+ Pm[k][d1] for PAC)
+//     B(P ,d2;k) = C[k][d2]            B(P,P;k) = CP[k]
 // ------------------------------------------------------------------------------------------------
-template <int E> struct IpRec {
+template <int E, bool PAC> struct IpRecPacPart {};
+template <int E> struct IpRecPacPart<E, true> {
+    double Q[ET<E>::NSH][ET<E>::DIM][ET<E>::DIM];
+    double Pm[ET<E>::NSH][ET<E>::DIM];
+};
+template <int E, bool PAC> struct IpRec : IpRecPacPart<E, PAC> {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1;
     double n[DIM];
-    double std[DIM];        // StdVel[ip]
-    double U[DIM];          // transported velocity after Peclet blend (UpwindVel)
-    double prod;            // (StdVel . n) * rho
-    double w;               // Peclet weight (1 if off)
-    double invdiag;         // 1/diag of the stabilisation's ip system (diagonal branch)
-    double F[NF];           // defect fluxes (momentum d, continuity)
+    double F[NF];           // defect fluxes (momentum d, continuity), add_def_A_elem :686-776
+    double A[NSH][DIM];
+    double D[NSH];
     double N[NSH];
-    double G[NSH][DIM];
-    double up[NSH];         // convective upwind shapes up_sh(ip,k) (+ ip-shape part folded in cvx)
-    double cvx[NSH];        // sum_ip2 N_k(ip2) up_ip(ip,ip2)   (Positive upwind only, else 0)
-    double sb[NSH];         // a*N_k + b*up_k (+ c*(down_k-up_k) for FLOW): diagonal-block numerator
+    double C[NSH][DIM];
+    double CP[NSH];
 };
 
-// Stabilisation shape accessors. Diagonal branch: recomputed from the record
-// (stabilization.cpp:213-236 FIELDS, :536-582 FLOW, :826-849 none).
+// Stabilisation shape accessors used while building the record. Diagonal branch: closed forms
+// (stabilization.cpp:213-236 FIELDS, :536-582 FLOW, :826-849 none) from per-ip data in registers.
 template <int E> struct StabDiag {
     static constexpr int DIM = ET<E>::DIM;
-    const IpRec<E>& r; int stab; double rho;
+    const double* N; const double (*G)[DIM]; const double* sb; const double* std;
+    double invdiag, inv_rho; int stab;
     NSB_DEV double sv(int d, int d2, int k) const
     {
-        if (stab == STAB_NONE) return d == d2 ? r.N[k] : 0.0;
-        if (stab == STAB_FIELDS) return d == d2 ? r.sb[k] * r.invdiag : 0.0;
+        if (stab == STAB_NONE) return d == d2 ? N[k] : 0.0;
+        if (stab == STAB_FIELDS) return d == d2 ? sb[k] * invdiag : 0.0;
         if (d == d2) {
-            double s = r.sb[k];
+            double s = sb[k];
 #pragma unroll
-            for (int q = 0; q < DIM; q++) if (q != d) s -= r.std[q] * r.G[k][q];
-            return s * r.invdiag;
+            for (int q = 0; q < DIM; q++) if (q != d) s -= std[q] * G[k][q];
+            return s * invdiag;
         }
-        return r.std[d] * r.G[k][d2] * r.invdiag;
+        return std[d] * G[k][d2] * invdiag;
     }
     NSB_DEV double sp(int d, int k) const
     {
         if (stab == STAB_NONE) return 0.0;
-        return -1.0 * r.G[k][d] / rho * r.invdiag;
+        return -1.0 * G[k][d] * inv_rho * invdiag;
     }
 };
 // Dense branch: shapes live in shared memory arrays sv[ip][d][d2][k], sp[ip][d][k]
@@ -437,92 +443,112 @@ template <int E> struct StabDense {
     NSB_DEV double sp(int d, int k) const { return spp[d * NSH + k]; }
 };
 
-// ------------------------------------------------------------------------------------------------
-// One COLUMN (corner k, function cf) of the flux derivative of one ip: val[rf] is added to row
-// (rf, from) and subtracted from row (rf, to).  add_jac_A_elem, fv1/navier_stokes_fv1.cpp:317-594.
-// ------------------------------------------------------------------------------------------------
-template <int E, class SV>
-NSB_DEV void jac_col(const KParams& p, const IpRec<E>& r, const SV& S, bool connected, int k, int cf, double* val)
+// Builds the factored flux derivative of one ip (see IpRec). Terms and quirks of
+// add_jac_A_elem, fv1/navier_stokes_fv1.cpp:336-592:
+//   diffusion :336-356, pressure :363-368, convection by upwind :430-457 / by stabilisation (PAC) :400-427,
+//   Peclet part :460-468, exact-Newton extras :475-550 (factor NOT applied to the upwind and Peclet
+//   parts, :528-529,:542-545; un-connected PAC term :494-496), continuity :561-592.
+// up/cvx: convective upwind shapes and sum_ip2 N_k(ip2)*up_ip(ip,ip2); U: transported velocity (blended).
+template <int E, bool PAC, class SV>
+NSB_DEV void ip_coeffs(const KParams& p, const double* n, const double* N, const double (*G)[ET<E>::DIM],
+                       const double* up, const double* cvx, const double* U, double w, double prod,
+                       const SV& S, bool connected, IpRec<E, PAC>& r)
 {
-    constexpr int DIM = ET<E>::DIM, P = DIM;
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
     const double nurho = p.visc * p.rho;
-    const bool conv_up = !p.stokes && !p.pac, conv_st = !p.stokes && p.pac;
-    if (cf < DIM) {
-        const int d2 = cf;
-        // diffusion :336-356
-        const double flux_sh = -1.0 * nurho * dotv<DIM>(r.G[k], r.n);
 #pragma unroll
-        for (int d1 = 0; d1 < DIM; d1++) {
-            double v = (d1 == d2) ? flux_sh : 0.0;
-            if (!p.laplace) v += -1.0 * nurho * r.G[k][d1] * r.n[d2];
-            val[d1] = v;
-        }
-        if (conv_st) {                                           // :400-417
+    for (int d = 0; d < DIM; d++) r.n[d] = n[d];
 #pragma unroll
-            for (int d1 = 0; d1 < DIM; d1++)
-                if (connected || d1 == d2) val[d1] += r.prod * r.w * S.sv(d1, d2, k);
-        }
-        if (conv_up) {                                           // :430-457
-            const double c = (r.up[k] + r.cvx[k]) * (r.prod * r.w);
+    for (int k = 0; k < NSH; k++) {
+        double D = -1.0 * nurho * dotv<DIM>(G[k], n);
+        double A[DIM];
 #pragma unroll
-            for (int d1 = 0; d1 < DIM; d1++) if (d1 == d2) val[d1] += c;
-        }
-        if (!p.stokes && p.peclet) {                             // :460-468
-            const double c = r.prod * (1.0 - r.w) * r.N[k];
+        for (int d1 = 0; d1 < DIM; d1++) A[d1] = p.laplace ? 0.0 : -1.0 * nurho * G[k][d1];
+        if (!p.stokes) {
+            if (!PAC) D += (up[k] + cvx[k]) * (prod * w);
+            if (p.peclet) D += prod * (1.0 - w) * N[k];
+            if (p.exact_jac != 0.0) {
+                double e = 0.0;
+                if (!PAC) e += w * up[k] * p.rho;
+                if (p.peclet) e += (1.0 - w) * N[k] * p.rho;
 #pragma unroll
-            for (int d1 = 0; d1 < DIM; d1++) if (d1 == d2) val[d1] += c;
-        }
-        if (!p.stokes && p.exact_jac != 0.0) {                   // :475-550
-            if (conv_st) {
-#pragma unroll
-                for (int d1 = 0; d1 < DIM; d1++) {
-                    double pv = 0.0;
-                    if (connected) {
-#pragma unroll
-                        for (int q = 0; q < DIM; q++) pv += r.w * S.sv(q, d2, k) * r.n[q];
-                    } else pv = S.sv(d1, d1, k) * r.n[d1];        // quirk :494-496
-                    pv *= p.exact_jac * p.rho;
-                    val[d1] += pv * r.U[d1];
-                }
-            }
-            if (conv_up) {
-                const double pv = r.w * r.up[k] * r.n[d2] * p.rho;   // quirk :528-529 (no factor, no ip part)
-#pragma unroll
-                for (int d1 = 0; d1 < DIM; d1++) val[d1] += pv * r.U[d1];
-            }
-            if (p.peclet) {
-                const double c = (1.0 - r.w) * r.N[k] * r.n[d2] * p.rho;   // quirk :542-545
-#pragma unroll
-                for (int d1 = 0; d1 < DIM; d1++) val[d1] += r.U[d1] * c;
+                for (int d1 = 0; d1 < DIM; d1++) A[d1] += e * U[d1];
             }
         }
-        // continuity row :561-584
-        if (connected) {
-            double cv = 0.0;
+        r.D[k] = D; r.N[k] = N[k];
 #pragma unroll
-            for (int q = 0; q < DIM; q++) cv += S.sv(q, d2, k) * r.n[q] * p.rho;
-            val[P] = cv;
-        } else val[P] = S.sv(d2, d2, k) * r.n[d2] * p.rho;
-    } else {
-        // pressure column :363-368, :419-426, :504-516, :586-592
-#pragma unroll
-        for (int d1 = 0; d1 < DIM; d1++) {
-            double v = r.N[k] * r.n[d1];
-            if (conv_st) v += r.prod * r.w * S.sp(d1, k);
-            val[d1] = v;
-        }
-        if (conv_st && p.exact_jac != 0.0) {
-            double pp = 0.0;
-#pragma unroll
-            for (int q = 0; q < DIM; q++) pp += S.sp(q, k) * r.n[q];
-            pp *= p.exact_jac * p.rho;
-#pragma unroll
-            for (int d1 = 0; d1 < DIM; d1++) val[d1] += pp * r.U[d1];
-        }
+        for (int d1 = 0; d1 < DIM; d1++) r.A[k][d1] = A[d1];
+        // continuity row
         double cp = 0.0;
 #pragma unroll
-        for (int q = 0; q < DIM; q++) cp += S.sp(q, k) * r.n[q] * p.rho;
-        val[P] = cp;
+        for (int q = 0; q < DIM; q++) cp += S.sp(q, k) * n[q] * p.rho;
+        r.CP[k] = cp;
+#pragma unroll
+        for (int d2 = 0; d2 < DIM; d2++) {
+            double cv = 0.0;
+            if (connected) {
+#pragma unroll
+                for (int q = 0; q < DIM; q++) cv += S.sv(q, d2, k) * n[q] * p.rho;
+            } else cv = S.sv(d2, d2, k) * n[d2] * p.rho;
+            r.C[k][d2] = cv;
+        }
+        if constexpr (PAC) {
+            double pp = 0.0;
+            if (!p.stokes && p.exact_jac != 0.0) {
+#pragma unroll
+                for (int q = 0; q < DIM; q++) pp += S.sp(q, k) * n[q];
+                pp *= p.exact_jac * p.rho;
+            }
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++) {
+                r.Pm[k][d1] = p.stokes ? 0.0 : prod * w * S.sp(d1, k) + pp * U[d1];
+#pragma unroll
+                for (int d2 = 0; d2 < DIM; d2++) {
+                    double q = 0.0;
+                    if (!p.stokes) {
+                        if (connected || d1 == d2) q = prod * w * S.sv(d1, d2, k);
+                        if (p.exact_jac != 0.0) {
+                            double pv = 0.0;
+                            if (connected) {
+#pragma unroll
+                                for (int z = 0; z < DIM; z++) pv += w * S.sv(z, d2, k) * n[z];
+                            } else pv = S.sv(d1, d1, k) * n[d1];
+                            pv *= p.exact_jac * p.rho;
+                            q += pv * U[d1];
+                        }
+                    }
+                    r.Q[k][d1][d2] = q;
+                }
+            }
+        }
+    }
+}
+
+// One COLUMN (corner k, function cf) of the flux derivative of one ip: val[rf] is added to row
+// (rf, from) and subtracted from row (rf, to).
+template <int E, bool PAC>
+NSB_DEV void jac_col(const IpRec<E, PAC>& r, int k, int cf, double* val)
+{
+    constexpr int DIM = ET<E>::DIM, P = DIM;
+    if (cf < DIM) {
+        const double ncf = r.n[cf];
+#pragma unroll
+        for (int d1 = 0; d1 < DIM; d1++) {
+            double v = r.A[k][d1] * ncf;
+            if (d1 == cf) v += r.D[k];
+            if constexpr (PAC) v += r.Q[k][d1][cf];
+            val[d1] = v;
+        }
+        val[P] = r.C[k][cf];
+    } else {
+        const double Nk = r.N[k];
+#pragma unroll
+        for (int d1 = 0; d1 < DIM; d1++) {
+            double v = Nk * r.n[d1];
+            if constexpr (PAC) v += r.Pm[k][d1];
+            val[d1] = v;
+        }
+        val[P] = r.CP[k];
     }
 }
 
@@ -547,10 +573,11 @@ template <int E> NSB_DEV double peclet_blend(double* U, const IpGeo<E>& g, const
 //   (pSol/pOldSol; s0==u and s1==nullptr when stationary), vol [NSH] SCV volumes.
 // returns false when a ray search failed.
 // ------------------------------------------------------------------------------------------------
-template <int E> NSB_DEV bool ip_eval(const KParams& p, const double* __restrict__ x, const double* __restrict__ u,
-                                      const double* __restrict__ s0, const double* __restrict__ s1,
-                                      const double* __restrict__ vol, int ip,
-                                      double cor_minN, double cor_avgN, double cor_minD, IpRec<E>& r)
+template <int E, bool PAC>
+NSB_DEV bool ip_eval(const KParams& p, const double* __restrict__ x, const double* __restrict__ u,
+                     const double* __restrict__ s0, const double* __restrict__ s1,
+                     const double* __restrict__ vol, int ip,
+                     double cor_minN, double cor_avgN, double cor_minD, IpRec<E, PAC>& r)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, P = DIM;
     IpGeo<E> g;
@@ -576,12 +603,12 @@ template <int E> NSB_DEV bool ip_eval(const KParams& p, const double* __restrict
         }
     }
     // ---- Schneider-Raw closure, diagonal branch ----
-    double stabvel[DIM], invdiag = 0.0;
+    double stabvel[DIM], invdiag = 0.0, sb[NSH];
     if (p.stab == STAB_NONE) {
 #pragma unroll
         for (int d = 0; d < DIM; d++) stabvel[d] = std[d];
 #pragma unroll
-        for (int k = 0; k < NSH; k++) r.sb[k] = 0.0;
+        for (int k = 0; k < NSH; k++) sb[k] = 0.0;
     } else {
         const double nn = dotv<DIM>(g.n, g.n);
         const double a = p.visc * diff_len_sq_inv<DIM>(p.diff_len, nn, vol[g.from], vol[g.to], g.ds, cor_minN, cor_avgN, cor_minD);
@@ -602,7 +629,7 @@ template <int E> NSB_DEV bool ip_eval(const KParams& p, const double* __restrict
                 sv += b * up[k];
                 if (p.stab == STAB_FLOW) sv += c * (dn[k] - up[k]);
             }
-            r.sb[k] = sv;
+            sb[k] = sv;
         }
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
@@ -615,7 +642,7 @@ template <int E> NSB_DEV bool ip_eval(const KParams& p, const double* __restrict
             }
 #pragma unroll
             for (int k = 0; k < NSH; k++) {
-                double sv = r.sb[k];
+                double sv = sb[k];
                 if (p.stab == STAB_FLOW) {
 #pragma unroll
                     for (int q = 0; q < DIM; q++) if (q != d) sv -= std[q] * g.G[k][q];
@@ -625,9 +652,9 @@ template <int E> NSB_DEV bool ip_eval(const KParams& p, const double* __restrict
 #pragma unroll
                     for (int q = 0; q < DIM; q++) if (q != d) rhs += std[d] * g.G[k][q] * s0[k * NF + q];
                 }
-                rhs += (-1.0 * g.G[k][d] / p.rho) * s0[k * NF + P];
+                rhs += (-1.0 * g.G[k][d] * p.inv_rho) * s0[k * NF + P];
             }
-            stabvel[d] = rhs / diag;
+            stabvel[d] = rhs * invdiag;
         }
     }
     // ---- convective upwind ----
@@ -638,7 +665,7 @@ template <int E> NSB_DEV bool ip_eval(const KParams& p, const double* __restrict
 #pragma unroll
     for (int k = 0; k < NSH; k++) cup[k] = 0.0;
     if (!p.stokes) {
-        if (p.pac) {
+        if constexpr (PAC) {
 #pragma unroll
             for (int d = 0; d < DIM; d++) U[d] = stabvel[d];
         } else {
@@ -688,15 +715,13 @@ template <int E> NSB_DEV bool ip_eval(const KParams& p, const double* __restrict
         }
         r.F[P] = dotv<DIM>(stabvel, g.n) * p.rho;
     }
-    // ---- park the record ----
+    // ---- park the record: factored flux derivative ----
+    if (p.what & W_JAC_A) {
+        double zero[NSH];
 #pragma unroll
-    for (int d = 0; d < DIM; d++) { r.n[d] = g.n[d]; r.std[d] = std[d]; r.U[d] = U[d]; }
-    r.prod = prod; r.w = w; r.invdiag = invdiag;
-#pragma unroll
-    for (int k = 0; k < NSH; k++) {
-        r.N[k] = g.N[k]; r.up[k] = cup[k]; r.cvx[k] = 0.0;
-#pragma unroll
-        for (int d = 0; d < DIM; d++) r.G[k][d] = g.G[k][d];
+        for (int k = 0; k < NSH; k++) zero[k] = 0.0;
+        StabDiag<E> S{g.N, g.G, sb, std, invdiag, p.inv_rho, p.stab};
+        ip_coeffs<E, PAC>(p, g.n, g.N, g.G, cup, zero, U, w, prod, S, p.stab == STAB_FLOW, r);
     }
     return ok;
 }

@@ -43,7 +43,7 @@ template <int E> __host__ __device__ constexpr int edge_corner(int ip, int j)
 }
 
 // per-(sub-)element workspace in shared memory
-template <int E> struct ElemWS {
+template <int E, bool PAC> struct ElemWS {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1;
     double x[NSH * DIM];
     double u[NSH * NF];
@@ -54,7 +54,7 @@ template <int E> struct ElemWS {
     int64_t rowbase[NSH];               // first value index of row (node a, fct 0)
     int32_t cnt[NSH];                   // block-row length of node a
     int32_t node[NSH];
-    IpRec<E> rec[NIP];
+    IpRec<E, PAC> rec[NIP];
 };
 
 template <int E> NSB_DEV void cor_stats(const double* nn, const double* ds, double& mnN, double& avN, double& mnD)
@@ -66,7 +66,7 @@ template <int E> NSB_DEV void cor_stats(const double* nn, const double* ds, doub
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int E, int SC>
+template <int E, int SC, bool PAC>
 __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, const int32_t* __restrict__ elem_list,
                                                        int64_t n_list, const double* __restrict__ u,
                                                        const double* __restrict__ s0, const double* __restrict__ s1,
@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, L = NSH * NF;
     constexpr int EPW = 32 / L;                         // elements per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ElemWS<E>* wsall = reinterpret_cast<ElemWS<E>*>(smem_raw);
+    ElemWS<E, PAC>* wsall = reinterpret_cast<ElemWS<E, PAC>*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / L, col = lane - sub * L;
     const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const int64_t li = gw * EPW + sub;
     const bool active = sub < EPW && li < n_list;
-    ElemWS<E>& ws = wsall[warp * EPW + (sub < EPW ? sub : 0)];
+    ElemWS<E, PAC>& ws = wsall[warp * EPW + (sub < EPW ? sub : 0)];
     const int64_t e = active ? (elem_list ? (int64_t)elem_list[li] : li) : 0;
     const int k = col / NF, cf = col - k * NF;
 
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
     }
     if (active && col < NIP) {
         const double* ps0 = p.time_dep ? ws.s0 : ws.u;
-        const bool ok = ip_eval<E>(p, ws.x, ws.u, ps0, ws.s1, ws.vol, col, cmn, cav, cmd, ws.rec[col]);
+        const bool ok = ip_eval<E, PAC>(p, ws.x, ws.u, ps0, ws.s1, ws.vol, col, cmn, cav, cmd, ws.rec[col]);
         if (!ok) atomicExch(errflag, 1);
     }
     __syncwarp();
@@ -135,14 +135,11 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
 #pragma unroll
         for (int i = 0; i < L; i++) acc[i] = 0.0;
         if (p.what & W_JAC_A) {
-            const bool connected = (p.stab == STAB_FLOW);
             static_for<NIP>([&](auto ipc) {
                 constexpr int ip = decltype(ipc)::value;
                 constexpr int f = edge_corner<E>(ip, 0), t = edge_corner<E>(ip, 1);
-                const IpRec<E>& r = ws.rec[ip];
-                StabDiag<E> S{r, p.stab, p.rho};
                 double v[NF];
-                jac_col<E>(p, r, S, connected, k, cf, v);
+                jac_col<E, PAC>(ws.rec[ip], k, cf, v);
 #pragma unroll
                 for (int rf = 0; rf < NF; rf++) { acc[f * NF + rf] += v[rf]; acc[t * NF + rf] -= v[rf]; }
             });
@@ -208,7 +205,7 @@ template <int E> struct GatherCfg {
     static constexpr int CH = (DIM == 3) ? 8 : 16;           // adjacent elements handled per round
     static constexpr int NREC = CH * NINC;                    // <= 32
 };
-template <int E> struct GatherWS {
+template <int E, bool PAC> struct GatherWS {
     using C = GatherCfg<E>;
     double x[C::CH][C::NSH * C::DIM];
     double u[C::CH][C::NSH * C::NF];
@@ -217,10 +214,10 @@ template <int E> struct GatherWS {
     double vol[C::CH][C::NSH];
     int32_t elem[C::CH];
     int32_t la[C::CH];
-    IpRec<E> rec[C::NREC];
+    IpRec<E, PAC> rec[C::NREC];
 };
 
-template <int E>
+template <int E, bool PAC>
 __global__ void __launch_bounds__(128) fv1_gather_kernel(KParams p, MeshDev m, const double* __restrict__ u,
                                                          const double* __restrict__ s0, const double* __restrict__ s1,
                                                          double beta, double* __restrict__ val, double* __restrict__ def,
@@ -231,12 +228,11 @@ __global__ void __launch_bounds__(128) fv1_gather_kernel(KParams p, MeshDev m, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     // per-warp layout: [GatherWS][rowacc NF*NF*max_cnt doubles]
-    const size_t per_warp = (sizeof(GatherWS<E>) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
-    GatherWS<E>& ws = *reinterpret_cast<GatherWS<E>*>(smem_raw + warp * per_warp);
-    double* rowacc = reinterpret_cast<double*>(smem_raw + warp * per_warp + sizeof(GatherWS<E>));
+    const size_t per_warp = (sizeof(GatherWS<E, PAC>) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
+    GatherWS<E, PAC>& ws = *reinterpret_cast<GatherWS<E, PAC>*>(smem_raw + warp * per_warp);
+    double* rowacc = reinterpret_cast<double*>(smem_raw + warp * per_warp + sizeof(GatherWS<E, PAC>));
     const bool want_jac = p.what & (W_JAC_A | W_JAC_M), want_def = p.what & (W_DEF_A | W_DEF_M | W_RHS);
     const int k = lane / NF, cf = lane - k * NF;               // column owned in the column phase
-    const bool connected = (p.stab == STAB_FLOW);
 
     for (int64_t a = (int64_t)blockIdx.x * nwarp + warp; a < m.n_node; a += (int64_t)gridDim.x * nwarp) {
         const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1];
@@ -282,7 +278,7 @@ __global__ void __launch_bounds__(128) fv1_gather_kernel(KParams p, MeshDev m, c
                         cor_stats<E>(nn, ds, cmn, cav, cmd);
                     }
                     const double* ps0 = p.time_dep ? ws.s0[j] : ws.u[j];
-                    const bool ok = ip_eval<E>(p, ws.x[j], ws.u[j], ps0, ws.s1[j], ws.vol[j], ip, cmn, cav, cmd, ws.rec[lane]);
+                    const bool ok = ip_eval<E, PAC>(p, ws.x[j], ws.u[j], ps0, ws.s1[j], ws.vol[j], ip, cmn, cav, cmd, ws.rec[lane]);
                     if (!ok) atomicExch(errflag, 1);
                 }
             }
@@ -297,11 +293,9 @@ __global__ void __launch_bounds__(128) fv1_gather_kernel(KParams p, MeshDev m, c
                     if (p.what & W_JAC_A) {
 #pragma unroll
                         for (int t = 0; t < NINC; t++) {
-                            const IpRec<E>& r = ws.rec[j * NINC + t];
                             const double sg = (double)tab::INC_SIGN[E][la][t];
-                            StabDiag<E> S{r, p.stab, p.rho};
                             double v[NF];
-                            jac_col<E>(p, r, S, connected, k, cf, v);
+                            jac_col<E, PAC>(ws.rec[j * NINC + t], k, cf, v);
 #pragma unroll
                             for (int rf = 0; rf < NF; rf++) acc[rf] += sg * v[rf];
                         }

@@ -368,7 +368,7 @@ static int resolve_params(nsb_ctx* c, KParams& k, int what, const nsb_time_serie
     k.stokes = p.stokes ? 1 : 0; k.laplace = p.laplace ? 1 : 0; k.peclet = p.peclet_blend ? 1 : 0;
     k.has_source = p.has_source ? 1 : 0;
     k.what = what;
-    k.exact_jac = p.exact_jacobian; k.visc = p.kin_visc; k.rho = p.density;
+    k.exact_jac = p.exact_jacobian; k.visc = p.kin_visc; k.rho = p.density; k.inv_rho = 1.0 / p.density;
     k.scale_a = sa; k.scale_m = sm;
     for (int d = 0; d < 3; d++) k.src[d] = p.source[d];
     k.time_dep = (ts && ts->sol0) ? 1 : 0;
