@@ -1,6 +1,7 @@
 // fv1_inst.cu -- instantiates the FV1 element / gather / SCV-volume kernels for one element type (-DNSB_ELEM=e)
 #include <algorithm>
-#include "ns_kernels.cuh"
+#include <type_traits>
+#include "ns_gather.cuh"
 #include "ns_launch.h"
 #ifndef NSB_ELEM
 #error "compile with -DNSB_ELEM=0..3"
@@ -33,12 +34,15 @@ cudaError_t NSB_CAT(launch_elem_, NSB_ELEM)(NSB_ELEM_ARGS)
     return elem_sc<SC_LOCAL, false>(NSB_FWD);
 }
 
-template <bool PAC> static cudaError_t gather_t(NSB_GATHER_ARGS)
+template <int STAB, bool TD> static cudaError_t gather_t(NSB_GATHER_ARGS)
 {
-    constexpr int NF = ET<E>::DIM + 1, WPB = 4;
-    const size_t per_warp = (sizeof(GatherWS<E, PAC>) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
-    const size_t smem = per_warp * WPB;
-    auto kern = fv1_gather_kernel<E, PAC>;
+    constexpr int NF = ET<E>::DIM + 1, WPB = 4, NIP = ET<E>::NIP, NSH = ET<E>::NSH;
+    constexpr bool FULLC = (STAB == STAB_FLOW);
+    using WS = typename std::conditional<TD, GWS<E, FULLC>, GWS_stat<E, FULLC>>::type;
+    const size_t tab_bytes = (sizeof(double) * NIP * NSH + 15) & ~(size_t)15;
+    const size_t per_warp = (sizeof(WS) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
+    const size_t smem = tab_bytes + per_warp * WPB;
+    auto kern = fv1_gather2_kernel<E, STAB, TD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
@@ -46,14 +50,31 @@ template <bool PAC> static cudaError_t gather_t(NSB_GATHER_ARGS)
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
-    kern<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, u, s0, s1, beta, val, def, d_err);
+    kern<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, geo, u, s0, s1, beta, val, def, d_err);
     return cudaGetLastError();
 }
+#define NSB_GFWD k, m, geo, u, s0, s1, beta, val, def, d_err, st, sm_count
 cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
 {
-    if (k.pac) return gather_t<true>(k, m, u, s0, s1, beta, val, def, d_err, st, sm_count);
-    return gather_t<false>(k, m, u, s0, s1, beta, val, def, d_err, st, sm_count);
+    if (k.time_dep) switch (k.stab) {
+        case STAB_FIELDS: return gather_t<STAB_FIELDS, true>(NSB_GFWD);
+        case STAB_FLOW: return gather_t<STAB_FLOW, true>(NSB_GFWD);
+        default: return gather_t<STAB_NONE, true>(NSB_GFWD);
+    }
+    switch (k.stab) {
+        case STAB_FIELDS: return gather_t<STAB_FIELDS, false>(NSB_GFWD);
+        case STAB_FLOW: return gather_t<STAB_FLOW, false>(NSB_GFWD);
+        default: return gather_t<STAB_NONE, false>(NSB_GFWD);
+    }
 }
+
+cudaError_t NSB_CAT(launch_geom_, NSB_ELEM)(int64_t n_elem, const int32_t* conn, const double* coords, double* geo, cudaStream_t st)
+{
+    const int64_t n = n_elem * ET<E>::NIP;
+    geom_kernel<E><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n_elem, conn, coords, geo);
+    return cudaGetLastError();
+}
+size_t NSB_CAT(geom_record_doubles_, NSB_ELEM)() { return GeoRec<E>::SZ; }
 
 cudaError_t NSB_CAT(launch_scvvol_, NSB_ELEM)(int64_t n_elem, const int32_t* conn, const double* coords, double* scvvol, cudaStream_t st)
 {

@@ -3,10 +3,7 @@
 //  fv1_elem_kernel   : one element (hex) or 2-3 elements (tet/quad/tri) per warp. Per-ip phase: lane = ip.
 //                      Column phase: lane = (corner k, function cf) owns one COLUMN of the local Jacobian in
 //                      registers. Scatter: coloured read-modify-write, red.global.add.f64, or local output.
-//  fv1_gather_kernel : owner-computes. One warp per grid node (= NF matrix rows). Per-ip phase: lane =
-//                      (adjacent element, SCVF incident to the node). Column phase: lane = (k, cf), partial
-//                      rows accumulate in shared memory in a fixed order and are streamed out ONCE with
-//                      coalesced stores: no atomics, no colouring, no read-modify-write of HBM.
+//  (the owner-computes "gather" kernel lives in ns_gather.cuh)
 #pragma once
 #include <utility>
 #include "ns_fv1.cuh"
@@ -193,151 +190,6 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
         else {
             double* q = def + (int64_t)ws.node[k] * NF + cf;
             if (SC == SC_ATOMIC) atomicAdd(q, d); else *q += d;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// owner-computes gather kernel
-// ------------------------------------------------------------------------------------------------
-template <int E> struct GatherCfg {
-    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, NINC = ET<E>::NINC;
-    static constexpr int CH = (DIM == 3) ? 8 : 16;           // adjacent elements handled per round
-    static constexpr int NREC = CH * NINC;                    // <= 32
-};
-template <int E, bool PAC> struct GatherWS {
-    using C = GatherCfg<E>;
-    double x[C::CH][C::NSH * C::DIM];
-    double u[C::CH][C::NSH * C::NF];
-    double s0[C::CH][C::NSH * C::NF];
-    double s1[C::CH][C::NSH * C::NF];
-    double vol[C::CH][C::NSH];
-    int32_t elem[C::CH];
-    int32_t la[C::CH];
-    IpRec<E, PAC> rec[C::NREC];
-};
-
-template <int E, bool PAC>
-__global__ void __launch_bounds__(128) fv1_gather_kernel(KParams p, MeshDev m, const double* __restrict__ u,
-                                                         const double* __restrict__ s0, const double* __restrict__ s1,
-                                                         double beta, double* __restrict__ val, double* __restrict__ def,
-                                                         int* __restrict__ errflag)
-{
-    using C = GatherCfg<E>;
-    constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, L = NSH * NF;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    // per-warp layout: [GatherWS][rowacc NF*NF*max_cnt doubles]
-    const size_t per_warp = (sizeof(GatherWS<E, PAC>) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
-    GatherWS<E, PAC>& ws = *reinterpret_cast<GatherWS<E, PAC>*>(smem_raw + warp * per_warp);
-    double* rowacc = reinterpret_cast<double*>(smem_raw + warp * per_warp + sizeof(GatherWS<E, PAC>));
-    const bool want_jac = p.what & (W_JAC_A | W_JAC_M), want_def = p.what & (W_DEF_A | W_DEF_M | W_RHS);
-    const int k = lane / NF, cf = lane - k * NF;               // column owned in the column phase
-
-    for (int64_t a = (int64_t)blockIdx.x * nwarp + warp; a < m.n_node; a += (int64_t)gridDim.x * nwarp) {
-        const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1];
-        const int64_t b0 = m.brow[a];
-        const int cnt = (int)(m.brow[a + 1] - b0);
-        const int rowlen = cnt * NF;                            // scalars per matrix row
-        if (want_jac) for (int i = lane; i < NF * rowlen; i += 32) rowacc[i] = 0.0;
-        double dsum = 0.0;                                      // lanes < NF: defect entry (a, lane)
-        double volsum = 0.0;                                    // sum of the node's SCV volumes
-        int self_slot = 0;
-        for (int64_t qb = q0; qb < q1; qb += CH) {
-            const int nj = (int)((q1 - qb) < CH ? (q1 - qb) : CH);
-            __syncwarp();
-            // ---- stage up to CH adjacent elements ----
-            if (lane < nj) {
-                const int32_t ad = m.adj[qb + lane];
-                ws.elem[lane] = ad / NSH; ws.la[lane] = ad - (ad / NSH) * NSH;
-            }
-            __syncwarp();
-            for (int i = lane; i < nj * NSH; i += 32) {
-                const int j = i / NSH, kk = i - j * NSH;
-                const int64_t e = ws.elem[j];
-                const int64_t nd = m.conn[e * NSH + kk];
-                ws.vol[j][kk] = m.scvvol[e * NSH + kk];
-#pragma unroll
-                for (int d = 0; d < DIM; d++) ws.x[j][kk * DIM + d] = m.coords[nd * DIM + d];
-#pragma unroll
-                for (int f = 0; f < NF; f++) {
-                    ws.u[j][kk * NF + f] = u[nd * NF + f];
-                    if (p.time_dep) { ws.s0[j][kk * NF + f] = s0[nd * NF + f]; ws.s1[j][kk * NF + f] = s1[nd * NF + f]; }
-                }
-            }
-            __syncwarp();
-            // ---- per-ip phase: lane = (adjacent element j, incident SCVF t) ----
-            if (p.what & (W_JAC_A | W_DEF_A)) {
-                const int j = lane / NINC, t = lane - j * NINC;
-                if (j < nj) {
-                    const int ip = tab::INC[E][ws.la[j]][t];
-                    double cmn = 0, cav = 0, cmd = 0;
-                    if (p.diff_len == DIFF_COR && p.stab != STAB_NONE) {
-                        double nn[ET<E>::NIP], ds[ET<E>::NIP];
-                        for (int i = 0; i < ET<E>::NIP; i++) { IpGeo<E> g; ip_geometry<E>(ws.x[j], i, g); nn[i] = dotv<DIM>(g.n, g.n); ds[i] = g.ds; }
-                        cor_stats<E>(nn, ds, cmn, cav, cmd);
-                    }
-                    const double* ps0 = p.time_dep ? ws.s0[j] : ws.u[j];
-                    const bool ok = ip_eval<E, PAC>(p, ws.x[j], ws.u[j], ps0, ws.s1[j], ws.vol[j], ip, cmn, cav, cmd, ws.rec[lane]);
-                    if (!ok) atomicExch(errflag, 1);
-                }
-            }
-            __syncwarp();
-            // ---- column phase: lane = (k, cf); fixed summation order j = 0..nj-1, t = 0..NINC-1 ----
-            if (want_jac && lane < L) {
-                for (int j = 0; j < nj; j++) {
-                    const int la = ws.la[j];
-                    double acc[NF];
-#pragma unroll
-                    for (int rf = 0; rf < NF; rf++) acc[rf] = 0.0;
-                    if (p.what & W_JAC_A) {
-#pragma unroll
-                        for (int t = 0; t < NINC; t++) {
-                            const double sg = (double)tab::INC_SIGN[E][la][t];
-                            double v[NF];
-                            jac_col<E, PAC>(ws.rec[j * NINC + t], k, cf, v);
-#pragma unroll
-                            for (int rf = 0; rf < NF; rf++) acc[rf] += sg * v[rf];
-                        }
-#pragma unroll
-                        for (int rf = 0; rf < NF; rf++) acc[rf] *= p.scale_a;
-                    }
-                    const int slot = m.emap[(int64_t)ws.elem[j] * (NSH * NSH) + la * NSH + k];
-#pragma unroll
-                    for (int rf = 0; rf < NF; rf++) rowacc[rf * rowlen + slot * NF + cf] += acc[rf];
-                }
-            }
-            // ---- defect + lumped mass: lanes < NF own (a, rf = lane) ----
-            if (lane < NF) {
-                for (int j = 0; j < nj; j++) {
-                    const int la = ws.la[j];
-                    if (p.what & W_DEF_A) {
-#pragma unroll
-                        for (int t = 0; t < NINC; t++)
-                            dsum += (double)tab::INC_SIGN[E][la][t] * ws.rec[j * NINC + t].F[lane];
-                    }
-                    volsum += ws.vol[j][la];
-                }
-                if (qb == q0) self_slot = m.emap[(int64_t)ws.elem[0] * (NSH * NSH) + ws.la[0] * NSH + ws.la[0]];
-            }
-        }
-        __syncwarp();
-        // ---- stream the finished rows out once ----
-        if (want_jac) {
-            if ((p.what & W_JAC_M) && lane < DIM)                // lumped mass on the diagonal (:781-808)
-                rowacc[lane * rowlen + self_slot * NF + lane] += p.scale_m * volsum * p.rho;
-            __syncwarp();
-            double* out = val + b0 * (NF * NF);
-            if (beta == 0.0) for (int i = lane; i < NF * rowlen; i += 32) out[i] = rowacc[i];
-            else for (int i = lane; i < NF * rowlen; i += 32) out[i] = beta * out[i] + rowacc[i];
-        }
-        if (want_def && lane < NF) {
-            double d = (p.what & W_DEF_A) ? dsum : 0.0;
-            if ((p.what & W_RHS) && p.has_source && lane < DIM) d -= p.src[lane] * volsum * p.rho;
-            d *= p.scale_a;
-            if ((p.what & W_DEF_M) && lane < DIM) d += p.scale_m * u[a * NF + lane] * volsum * p.rho;
-            double* q = def + a * NF + lane;
-            *q = (beta == 0.0) ? d : beta * (*q) + d;
         }
     }
 }

@@ -50,7 +50,7 @@ struct nsb_ctx {
     std::vector<int64_t> h_color_ptr;
     // device
     int32_t *d_conn = nullptr, *d_adj = nullptr, *d_color_order = nullptr, *d_esides = nullptr;
-    double *d_coords = nullptr, *d_scvvol = nullptr;
+    double *d_coords = nullptr, *d_scvvol = nullptr, *d_geo = nullptr;
     int64_t *d_brow = nullptr, *d_adj_ptr = nullptr;
     uint8_t *d_emap = nullptr;
     FvcrDev fvcr{};
@@ -134,11 +134,11 @@ extern "C" int nsb_create(int device, nsb_ctx** out)
 static void free_mesh(nsb_ctx* c)
 {
     cudaFree(c->d_conn); cudaFree(c->d_adj); cudaFree(c->d_color_order); cudaFree(c->d_esides); cudaFree(c->d_coords);
-    cudaFree(c->d_scvvol); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
+    cudaFree(c->d_scvvol); cudaFree(c->d_geo); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
     cudaFree(c->d_u); cudaFree(c->d_s0); cudaFree(c->d_s1); cudaFree(c->d_val); cudaFree(c->d_def);
     cudaFree(c->d_jloc); cudaFree(c->d_dloc);
     fvcr_free(c->fvcr);
-    c->d_conn = c->d_adj = c->d_color_order = c->d_esides = nullptr; c->d_coords = c->d_scvvol = nullptr;
+    c->d_conn = c->d_adj = c->d_color_order = c->d_esides = nullptr; c->d_coords = c->d_scvvol = c->d_geo = nullptr;
     c->d_brow = c->d_adj_ptr = nullptr; c->d_emap = nullptr;
     c->d_u = c->d_s0 = c->d_s1 = c->d_val = c->d_def = c->d_jloc = c->d_dloc = nullptr;
     c->mesh_ready = false;
@@ -301,6 +301,20 @@ extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_n
     CUDA_TRY(c, upload(&c->d_color_order, order.data(), order.size()));
     CUDA_TRY(c, cudaMalloc(&c->d_scvvol, (size_t)n_elem * nsh * sizeof(double)));
     CUDA_TRY(c, launch_scvvol(c));
+    {   // precomputed SCVF geometry table (normals, ips, global shape gradients) for the owner-computes kernel
+        size_t rec = 0;
+        switch (elem) { case 0: rec = geom_record_doubles_0(); break; case 1: rec = geom_record_doubles_1(); break;
+                        case 2: rec = geom_record_doubles_2(); break; default: rec = geom_record_doubles_3(); }
+        static const int kNIP[4] = {3, 4, 6, 12};
+        CUDA_TRY(c, cudaMalloc(&c->d_geo, (size_t)n_elem * kNIP[elem] * rec * sizeof(double)));
+        cudaError_t ge;
+        switch (elem) { case 0: ge = launch_geom_0(n_elem, c->d_conn, c->d_coords, c->d_geo, c->stream); break;
+                        case 1: ge = launch_geom_1(n_elem, c->d_conn, c->d_coords, c->d_geo, c->stream); break;
+                        case 2: ge = launch_geom_2(n_elem, c->d_conn, c->d_coords, c->d_geo, c->stream); break;
+                        default: ge = launch_geom_3(n_elem, c->d_conn, c->d_coords, c->d_geo, c->stream); }
+        c->launches++;
+        CUDA_TRY(c, ge);
+    }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->h_brow.swap(g.brow); c->h_bcol.swap(g.bcol);
     c->mesh_ready = true;
@@ -427,7 +441,7 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
 {
     const MeshDev m = mesh_view(c);
     cudaError_t e;
-#define NSB_GO(fn) fn(k, m, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count)
+#define NSB_GO(fn) fn(k, m, c->d_geo, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count)
     switch (c->elem) { case 0: e = NSB_GO(launch_gather_0); break; case 1: e = NSB_GO(launch_gather_1); break;
                        case 2: e = NSB_GO(launch_gather_2); break; default: e = NSB_GO(launch_gather_3); }
 #undef NSB_GO
@@ -440,7 +454,7 @@ static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u,
                         double beta, double* val, double* def)
 {
     const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
-    if (mode == NSB_SCATTER_GATHER && needs_dense(k)) mode = NSB_SCATTER_COLORED;   // dense ip systems need whole elements
+    if (mode == NSB_SCATTER_GATHER && (needs_dense(k) || k.pac)) mode = NSB_SCATTER_COLORED;   // dense ip systems / PAC need whole elements
     if (mode == NSB_SCATTER_GATHER) return launch_gather(c, k, u, s0, s1, beta, val, def);
     // element kernels accumulate into beta*old
     if (jac) {
