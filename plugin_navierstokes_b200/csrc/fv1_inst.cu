@@ -1,5 +1,6 @@
 // fv1_inst.cu -- instantiates the FV1 element / gather / SCV-volume kernels for one element type (-DNSB_ELEM=e)
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include "ns_gather.cuh"
 #include "ns_launch.h"
@@ -36,7 +37,8 @@ cudaError_t NSB_CAT(launch_elem_, NSB_ELEM)(NSB_ELEM_ARGS)
 
 template <int STAB, bool TD> static cudaError_t gather_t(NSB_GATHER_ARGS)
 {
-    constexpr int NF = ET<E>::DIM + 1, WPB = 4, NIP = ET<E>::NIP, NSH = ET<E>::NSH;
+    constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH;
+    static const int WPB = [] { const char* e = getenv("NSB_GATHER_WPB"); const int v = e ? atoi(e) : 4; return (v >= 1 && v <= 4) ? v : 4; }();
     constexpr bool FULLC = (STAB == STAB_FLOW);
     using WS = typename std::conditional<TD, GWS<E, FULLC>, GWS_stat<E, FULLC>>::type;
     const size_t tab_bytes = (sizeof(double) * NIP * NSH + 15) & ~(size_t)15;

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <utility>
 #include "ref_tables.cuh"
 
 namespace nsb {
@@ -266,60 +267,102 @@ template <int E> NSB_DEV double scv_volume(const double* __restrict__ x, int co)
 // Call sites: upwind.cpp:351,547.
 // ------------------------------------------------------------------------------------------------
 #define NSB_RAY_SMALL 1e-12
+
+template <int N, class F, int... I> NSB_DEV void static_for_impl(F&& f, std::integer_sequence<int, I...>)
+{ (f(std::integral_constant<int, I>{}), ...); }
+template <int N, class F> NSB_DEV void static_for(F&& f) { static_for_impl<N>(f, std::make_integer_sequence<int, N>{}); }
+
+// compile-time reference-element tables (fold into immediates once loops are unrolled)
+template <int E> __host__ __device__ constexpr int edge_corner(int ip, int j)
+{
+    if (E == E_TRI)  { constexpr int T[3][2]  = {{0,1},{1,2},{2,0}}; return T[ip][j]; }
+    if (E == E_QUAD) { constexpr int T[4][2]  = {{0,1},{1,2},{2,3},{3,0}}; return T[ip][j]; }
+    if (E == E_TET)  { constexpr int T[6][2]  = {{0,1},{1,2},{2,0},{0,3},{1,3},{2,3}}; return T[ip][j]; }
+    constexpr int T[12][2] = {{0,1},{1,2},{2,3},{3,0},{0,4},{1,5},{2,6},{3,7},{4,5},{5,6},{6,7},{7,4}};
+    return T[ip][j];
+}
+template <int E> __host__ __device__ constexpr int side_corner(int s, int i)
+{
+    if (E == E_TRI)  { constexpr int T[3][2] = {{0,1},{1,2},{2,0}}; return T[s][i]; }
+    if (E == E_QUAD) { constexpr int T[4][2] = {{0,1},{1,2},{2,3},{3,0}}; return T[s][i]; }
+    if (E == E_TET)  { constexpr int T[4][3] = {{0,2,1},{1,2,3},{0,3,2},{0,1,3}}; return T[s][i]; }
+    constexpr int T[6][4] = {{0,3,2,1},{0,1,5,4},{1,2,6,5},{2,3,7,6},{3,0,4,7},{4,5,6,7}};
+    return T[s][i];
+}
+
+// All candidate segments / triangles are tested in reference order with compile-time corner indices; the
+// inside / upstream tests are done on the un-divided Cramer numerators (sign-corrected by det), so the
+// only divisions are the three of the winning triangle.
 template <int E> NSB_DEV bool side_ray_cut(const double* __restrict__ x, const double* from, const double* dir,
                                            int& side_out, double* gcut, double* lcut)
 {
     constexpr int DIM = ET<E>::DIM, NSIDE = ET<E>::NSIDE;
+    constexpr double S = NSB_RAY_SMALL;
+    bool found = false;
+    int best = 0;
+    double tn = 0.0, n1 = 0.0, n2 = 0.0, bdet = 1.0;
     if constexpr (DIM == 2) {
-        const double dn = sqrt(dir[0] * dir[0] + dir[1] * dir[1]);
-        for (int s = 0; s < NSIDE; s++) {
-            const int p0 = tab::SIDE[E][s][0], p1 = tab::SIDE[E][s][1];
-            const double ex = x[p1 * 2] - x[p0 * 2], ey = x[p1 * 2 + 1] - x[p0 * 2 + 1];
-            const double det = dir[0] * (-ey) + dir[1] * ex;
-            if (!(fabs(det) > NSB_RAY_SMALL * dn * sqrt(ex * ex + ey * ey))) continue;
-            const double rx = x[p0 * 2] - from[0], ry = x[p0 * 2 + 1] - from[1];
-            const double t = (rx * (-ey) + ry * ex) / det;
-            const double bc = (dir[0] * ry - dir[1] * rx) / det;
-            if (!(bc >= -NSB_RAY_SMALL && bc <= 1.0 + NSB_RAY_SMALL)) continue;
-            if (!(t <= 0.0)) continue;
-#pragma unroll
-            for (int d = 0; d < 2; d++) {
-                gcut[d] = from[d] + t * dir[d];
-                lcut[d] = (1 - bc) * tab::CORNER[E][p0][d] + bc * tab::CORNER[E][p1][d];
+        const double dn2 = dir[0] * dir[0] + dir[1] * dir[1];
+        static_for<NSIDE>([&](auto sc) {
+            constexpr int s = decltype(sc)::value;
+            constexpr int p0 = side_corner<E>(s, 0), p1 = side_corner<E>(s, 1);
+            if (!found) {
+                const double ex = x[p1 * 2] - x[p0 * 2], ey = x[p1 * 2 + 1] - x[p0 * 2 + 1];
+                const double det = dir[0] * (-ey) + dir[1] * ex;
+                if (det * det > (S * S) * dn2 * (ex * ex + ey * ey)) {
+                    const double rx = x[p0 * 2] - from[0], ry = x[p0 * 2 + 1] - from[1];
+                    const double t_n = rx * (-ey) + ry * ex, b_n = dir[0] * ry - dir[1] * rx;
+                    const double sg = det > 0.0 ? 1.0 : -1.0, ad = fabs(det);
+                    if (b_n * sg >= -S * ad && b_n * sg <= (1.0 + S) * ad && t_n * sg <= 0.0) {
+                        found = true; best = s; tn = t_n; n1 = b_n; bdet = det;
+                    }
+                }
             }
-            side_out = s;
-            return true;
-        }
-        return false;
-    } else {
-        const double dn = sqrt(dotv<3>(dir, dir));
-        constexpr int NTRI = (E == E_HEX) ? 2 : 1;
-        for (int s = 0; s < NSIDE; s++) {
-            const int p0 = tab::SIDE[E][s][0];
+        });
+        if (!found) return false;
+        const double t = tn / bdet, bc = n1 / bdet;
+        const int p0 = tab::SIDE[E][best][0], p1 = tab::SIDE[E][best][1];
 #pragma unroll
-            for (int k = 0; k < NTRI; k++) {
-                const int p1 = tab::SIDE[E][s][1 + k], p2 = tab::SIDE[E][s][2 + k];
+        for (int d = 0; d < 2; d++) {
+            gcut[d] = from[d] + t * dir[d];
+            lcut[d] = (1 - bc) * tab::CORNER[E][p0][d] + bc * tab::CORNER[E][p1][d];
+        }
+        side_out = best;
+        return true;
+    } else {
+        const double dn2 = dotv<3>(dir, dir);
+        constexpr int TPS = (E == E_HEX) ? 2 : 1;            // triangles per side
+        static_for<NSIDE * TPS>([&](auto ic) {
+            constexpr int i = decltype(ic)::value, s = i / TPS, kk = i % TPS;
+            constexpr int p0 = side_corner<E>(s, 0), p1 = side_corner<E>(s, 1 + kk), p2 = side_corner<E>(s, 2 + kk);
+            if (!found) {
                 double e1[3], e2[3], r[3], nrm[3], q[3];
 #pragma unroll
                 for (int d = 0; d < 3; d++) { e1[d] = x[p1 * 3 + d] - x[p0 * 3 + d]; e2[d] = x[p2 * 3 + d] - x[p0 * 3 + d]; r[d] = from[d] - x[p0 * 3 + d]; }
                 cross3(nrm, e1, e2);
                 const double det = -dotv<3>(dir, nrm);
-                if (!(fabs(det) > NSB_RAY_SMALL * dn * sqrt(dotv<3>(nrm, nrm)))) continue;
-                const double t = dotv<3>(r, nrm) / det;
-                cross3(q, r, dir);
-                const double b1 = dotv<3>(e2, q) / det, b2 = -dotv<3>(e1, q) / det;
-                if (!(b1 >= -NSB_RAY_SMALL && b2 >= -NSB_RAY_SMALL && b1 + b2 <= 1.0 + NSB_RAY_SMALL)) continue;
-                if (!(t <= 0.0)) continue;
-#pragma unroll
-                for (int d = 0; d < 3; d++) {
-                    gcut[d] = from[d] + t * dir[d];
-                    lcut[d] = (1 - b1 - b2) * tab::CORNER[E][p0][d] + b1 * tab::CORNER[E][p1][d] + b2 * tab::CORNER[E][p2][d];
+                if (det * det > (S * S) * dn2 * dotv<3>(nrm, nrm)) {
+                    const double t_n = dotv<3>(r, nrm);
+                    cross3(q, r, dir);
+                    const double b1n = dotv<3>(e2, q), b2n = -dotv<3>(e1, q);
+                    const double sg = det > 0.0 ? 1.0 : -1.0, ad = fabs(det);
+                    if (b1n * sg >= -S * ad && b2n * sg >= -S * ad && (b1n + b2n) * sg <= (1.0 + S) * ad && t_n * sg <= 0.0) {
+                        found = true; best = i; tn = t_n; n1 = b1n; n2 = b2n; bdet = det;
+                    }
                 }
-                side_out = s;
-                return true;
             }
+        });
+        if (!found) return false;
+        const double t = tn / bdet, b1 = n1 / bdet, b2 = n2 / bdet;
+        const int s = best / TPS, kk = best - s * TPS;
+        const int p0 = tab::SIDE[E][s][0], p1 = tab::SIDE[E][s][1 + kk], p2 = tab::SIDE[E][s][2 + kk];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            gcut[d] = from[d] + t * dir[d];
+            lcut[d] = (1 - b1 - b2) * tab::CORNER[E][p0][d] + b1 * tab::CORNER[E][p1][d] + b2 * tab::CORNER[E][p2][d];
         }
-        return false;
+        side_out = s;
+        return true;
     }
 }
 

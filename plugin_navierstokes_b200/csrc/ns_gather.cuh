@@ -57,14 +57,17 @@ __global__ void geom_kernel(int64_t n_elem, const int32_t* __restrict__ conn, co
 
 // ---- shared-memory record of one ip (factored flux derivative, see IpRec in ns_fv1.cuh) --------------
 // FULLC (FLOW): continuity-row coefficients C[k][d2] are full; otherwise C[k][d2] = c[k]*n[d2].
+// The sign of the SCVF w.r.t. the owning node (+1: node is `from`, -1: `to`) is folded into A, D, C, CP, F, sn.
 template <int E, bool FULLC> struct FRec {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1;
     static constexpr int NC = FULLC ? NSH * DIM : NSH;
-    static constexpr int O_N = 0, O_F = DIM, O_IP = O_F + NF, O_A = O_IP + 1, O_D = O_A + NSH * DIM, O_C = O_D + NSH,
-                         O_CP = O_C + NC, RAW = O_CP + NSH;
+    static constexpr int O_N = 0, O_SN = DIM, O_F = O_SN + DIM, O_IP = O_F + NF, O_A = O_IP + 1, O_D = O_A + NSH * DIM,
+                         O_C = O_D + NSH, O_CP = O_C + NC, RAW = O_CP + NSH;
     static constexpr int SZ = RAW | 1;          // odd number of doubles -> conflict-free lane-strided access
     double v[SZ];
     NSB_DEV double& n(int d) { return v[O_N + d]; }
+    NSB_DEV double& sn(int d) { return v[O_SN + d]; }
+    NSB_DEV double sn(int d) const { return v[O_SN + d]; }
     NSB_DEV double& F(int f) { return v[O_F + f]; }
     NSB_DEV double& ipd() { return v[O_IP]; }
     NSB_DEV double& A(int k, int d) { return v[O_A + k * DIM + d]; }
@@ -122,7 +125,7 @@ template <int E, int STAB, bool TD>
 NSB_DEV bool ip_fast(const KParams& p, const double* __restrict__ us, const double* __restrict__ ss0,
                      const double* __restrict__ ss1, const double* __restrict__ xs, const double* __restrict__ vs,
                      const double* __restrict__ g, const double* __restrict__ gelem, const double* __restrict__ Nt, int ip,
-                     FRec<E, STAB == STAB_FLOW>& r)
+                     double sg, FRec<E, STAB == STAB_FLOW>& r)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, P = DIM;
     using R = GeoRec<E>;
@@ -247,7 +250,7 @@ NSB_DEV bool ip_fast(const KParams& p, const double* __restrict__ us, const doub
         for (int k = 0; k < NSH; k++) {
             gn[k] += Gd[k] * n[d];
             if (FLOW) sG[k] += Gd[k] * std[d];
-            if (want_jac) r.A(k, d) = (p.laplace ? 0.0 : -1.0 * nurho * Gd[k]) + ex[k] * U[d];
+            if (want_jac) r.A(k, d) = sg * ((p.laplace ? 0.0 : -1.0 * nurho * Gd[k]) + ex[k] * U[d]);
             if (want_def) {
                 sp += Gd[k] * us[k * NF + P];
 #pragma unroll
@@ -266,21 +269,21 @@ NSB_DEV bool ip_fast(const KParams& p, const double* __restrict__ us, const doub
     // ---- Jacobian coefficients ----
     if (want_jac) {
 #pragma unroll
-        for (int d = 0; d < DIM; d++) r.n(d) = n[d];
+        for (int d = 0; d < DIM; d++) { r.n(d) = n[d]; r.sn(d) = sg * n[d]; }
         r.ipd() = (double)ip;
         const double cw = prod * w, cpe = prod * (1.0 - w);
 #pragma unroll
         for (int k = 0; k < NSH; k++) {
             double D = -1.0 * nurho * gn[k];
             if (!p.stokes) { D += up[k] * cw; if (p.peclet) D += cpe * N[k]; }
-            r.D(k) = D;
-            if constexpr (STAB == STAB_NONE) { r.C(k) = N[k] * p.rho; r.CP(k) = 0.0; }
+            r.D(k) = sg * D;
+            if constexpr (STAB == STAB_NONE) { r.C(k) = sg * N[k] * p.rho; r.CP(k) = 0.0; }
             else {
-                r.CP(k) = -1.0 * gn[k] * invdiag;                       // sum_q sp(q,k) n_q rho, rho cancels
-                if constexpr (!FLOW) r.C(k) = sb[k] * invdiag * p.rho;
+                r.CP(k) = -sg * gn[k] * invdiag;                       // sum_q sp(q,k) n_q rho, rho cancels
+                if constexpr (!FLOW) r.C(k) = sg * sb[k] * invdiag * p.rho;
                 else {
                     // sum_q sv(q,d2,k) n_q rho = ((sb_k - std.G_k) n_d2 + G_k[d2] (std.n)) invdiag rho
-                    const double c0 = (sb[k] - sG[k]) * invdiag * p.rho, c1 = sn * invdiag * p.rho;
+                    const double c0 = sg * (sb[k] - sG[k]) * invdiag * p.rho, c1 = sg * sn * invdiag * p.rho;
 #pragma unroll
                     for (int d2 = 0; d2 < DIM; d2++) {
                         const double Gkd = __ldg(g + R::HEAD + d2 * R::NSHP + k);
@@ -307,7 +310,7 @@ NSB_DEV bool ip_fast(const KParams& p, const double* __restrict__ us, const doub
             double f = df * (-1.0) * nurho;
             if (!p.stokes) f += U[d1] * prod;
             f += pr * n[d1];
-            r.F(d1) = f;
+            r.F(d1) = sg * f;
         }
         // continuity: stab_vel . n * rho
         double cont;
@@ -345,7 +348,7 @@ NSB_DEV bool ip_fast(const KParams& p, const double* __restrict__ us, const doub
             }
             cont = acc * invdiag * p.rho;
         }
-        r.F(P) = cont;
+        r.F(P) = sg * cont;
     }
     return ok;
 }
@@ -433,16 +436,16 @@ __global__ void __launch_bounds__(128, 3) fv1_gather2_kernel(KParams p, MeshDev 
                     const double* gp = ge + ip * R::SZ;
                     const double* ps0 = nullptr; const double* ps1 = nullptr;
                     if constexpr (TD) { ps0 = ws.s0 + j * C::US; ps1 = ws.s1 + j * C::US; }
+                    const double sg = (double)tab::INC_SIGN[E][ws.la[j]][t];
                     const bool ok = ip_fast<E, STAB, TD>(p, ws.u + j * C::US, ps0, ps1, ws.x + j * C::XS, ws.vol + j * C::VS,
-                                                         gp, ge, Ntab + ip * NSH, ip, ws.rec[lane]);
+                                                         gp, ge, Ntab + ip * NSH, ip, sg, ws.rec[lane]);
                     if (!ok) atomicExch(errflag, 1);
                 }
             }
             __syncwarp();
-            // ---- phase 2: lane = (k, cf); fixed order j, t ----
+            // ---- phase 2: lane = (k, cf); fixed order j, t (signs are already folded into the records) ----
             if (want_jac && lane < L) {
                 for (int j = 0; j < nj; j++) {
-                    const int la = ws.la[j];
                     double acc[NF];
 #pragma unroll
                     for (int rf = 0; rf < NF; rf++) acc[rf] = 0.0;
@@ -450,22 +453,19 @@ __global__ void __launch_bounds__(128, 3) fv1_gather2_kernel(KParams p, MeshDev 
 #pragma unroll
                         for (int t = 0; t < NINC; t++) {
                             const FRec<E, FULLC>& r = ws.rec[j * NINC + t];
-                            const double sg = (double)tab::INC_SIGN[E][la][t];
                             if (cf < DIM) {
                                 const double ncf = r.n(cf);
 #pragma unroll
-                                for (int d1 = 0; d1 < DIM; d1++) {
-                                    double v = r.A(k, d1) * ncf;
-                                    if (d1 == cf) v += r.D(k);
-                                    acc[d1] += sg * v;
-                                }
-                                if constexpr (FULLC) acc[DIM] += sg * r.C(k * DIM + cf);
-                                else acc[DIM] += sg * (r.C(k) * ncf);
+                                for (int d1 = 0; d1 < DIM; d1++) acc[d1] += r.A(k, d1) * ncf;
+#pragma unroll
+                                for (int d1 = 0; d1 < DIM; d1++) if (d1 == cf) acc[d1] += r.D(k);
+                                if constexpr (FULLC) acc[DIM] += r.C(k * DIM + cf);
+                                else acc[DIM] += r.C(k) * ncf;
                             } else {
                                 const double Nk = Ntab[(int)r.ipd() * NSH + k];
 #pragma unroll
-                                for (int d1 = 0; d1 < DIM; d1++) acc[d1] += sg * (Nk * r.n(d1));
-                                acc[DIM] += sg * r.CP(k);
+                                for (int d1 = 0; d1 < DIM; d1++) acc[d1] += Nk * r.sn(d1);
+                                acc[DIM] += r.CP(k);
                             }
                         }
 #pragma unroll
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(128, 3) fv1_gather2_kernel(KParams p, MeshDev 
                     const int la = ws.la[j];
                     if (p.what & W_DEF_A) {
 #pragma unroll
-                        for (int t = 0; t < NINC; t++) dsum += (double)tab::INC_SIGN[E][la][t] * ws.rec[j * NINC + t].F(lane);
+                        for (int t = 0; t < NINC; t++) dsum += ws.rec[j * NINC + t].F(lane);
                     }
                     volsum += ws.vol[j * C::VS + la];
                 }

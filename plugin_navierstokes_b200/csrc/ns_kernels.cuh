@@ -25,20 +25,6 @@ struct MeshDev {
 
 enum { SC_COLORED = 1, SC_ATOMIC = 2, SC_LOCAL = 3 };
 
-template <int N, class F, int... I> NSB_DEV void static_for_impl(F&& f, std::integer_sequence<int, I...>)
-{ (f(std::integral_constant<int, I>{}), ...); }
-template <int N, class F> NSB_DEV void static_for(F&& f) { static_for_impl<N>(f, std::make_integer_sequence<int, N>{}); }
-
-// compile-time edge tables (from/to corner of SCVF ip) so that accumulator indices fold to registers
-template <int E> __host__ __device__ constexpr int edge_corner(int ip, int j)
-{
-    if (E == E_TRI)  { constexpr int T[3][2]  = {{0,1},{1,2},{2,0}}; return T[ip][j]; }
-    if (E == E_QUAD) { constexpr int T[4][2]  = {{0,1},{1,2},{2,3},{3,0}}; return T[ip][j]; }
-    if (E == E_TET)  { constexpr int T[6][2]  = {{0,1},{1,2},{2,0},{0,3},{1,3},{2,3}}; return T[ip][j]; }
-    constexpr int T[12][2] = {{0,1},{1,2},{2,3},{3,0},{0,4},{1,5},{2,6},{3,7},{4,5},{5,6},{6,7},{7,4}};
-    return T[ip][j];
-}
-
 // per-(sub-)element workspace in shared memory
 template <int E, bool PAC> struct ElemWS {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1;
