@@ -2,7 +2,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
-#include "ns_gather.cuh"
+#include "ns_owner.cuh"
 #include "ns_launch.h"
 #ifndef NSB_ELEM
 #error "compile with -DNSB_ELEM=0..3"
@@ -35,30 +35,41 @@ cudaError_t NSB_CAT(launch_elem_, NSB_ELEM)(NSB_ELEM_ARGS)
     return elem_sc<SC_LOCAL, false>(NSB_FWD);
 }
 
-template <int STAB, bool TD> static cudaError_t gather_t(NSB_GATHER_ARGS)
+// owner-computes path: (A) flux kernel, thread per element  ->  (B) rows kernel, warp per node
+template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
 {
-    constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH;
-    static const int WPB = [] { const char* e = getenv("NSB_GATHER_WPB"); const int v = e ? atoi(e) : 4; return (v >= 1 && v <= 4) ? v : 4; }();
-    constexpr bool FULLC = (STAB == STAB_FLOW);
-    using WS = typename std::conditional<TD, GWS<E, FULLC>, GWS_stat<E, FULLC>>::type;
+    constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
+    cudaError_t e;
+    if (k.what & (W_JAC_A | W_DEF_A)) {
+        const size_t smem_a = sizeof(double) * (NSH * DIM + NSH) * BS;
+        auto ka = fv1_flux_kernel<E, STAB, EXACT, BS>;
+        e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+        if (e != cudaSuccess) return e;
+        ka<<<(unsigned)((m.n_elem + BS - 1) / BS), BS, smem_a, st>>>(k, m, geo, u, s0, s1, flux, d_err);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    static const int WPB = [] { const char* ev = getenv("NSB_ROWS_WPB"); const int v = ev ? atoi(ev) : 4; return (v >= 1 && v <= 4) ? v : 4; }();
+    using WS = RowWS<E, EXACT>;
     const size_t tab_bytes = (sizeof(double) * NIP * NSH + 15) & ~(size_t)15;
     const size_t per_warp = (sizeof(WS) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
     const size_t smem = tab_bytes + per_warp * WPB;
-    auto kern = fv1_gather2_kernel<E, STAB, TD>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kb = fv1_rows_kernel<E, STAB, EXACT>;
+    e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WPB * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, WPB * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
-    kern<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, geo, u, s0, s1, beta, val, def, d_err);
+    kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, geo, flux, u, beta, val, def);
     return cudaGetLastError();
 }
-#define NSB_GFWD k, m, geo, u, s0, s1, beta, val, def, d_err, st, sm_count
+#define NSB_GFWD k, m, geo, flux, u, s0, s1, beta, val, def, d_err, st, sm_count
 cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
 {
-    if (k.time_dep) switch (k.stab) {
+    const bool exact = !k.stokes && k.exact_jac != 0.0;
+    if (exact) switch (k.stab) {
         case STAB_FIELDS: return gather_t<STAB_FIELDS, true>(NSB_GFWD);
         case STAB_FLOW: return gather_t<STAB_FLOW, true>(NSB_GFWD);
         default: return gather_t<STAB_NONE, true>(NSB_GFWD);
@@ -69,6 +80,7 @@ cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
         default: return gather_t<STAB_NONE, false>(NSB_GFWD);
     }
 }
+size_t NSB_CAT(flux_record_doubles_, NSB_ELEM)() { return FluxRec<E, true>::SZ; }
 
 cudaError_t NSB_CAT(launch_geom_, NSB_ELEM)(int64_t n_elem, const int32_t* conn, const double* coords, double* geo, cudaStream_t st)
 {

@@ -1,0 +1,677 @@
+// ns_owner.cuh -- owner-computes FV1 assembly for sm_100a (diagonal stabilisation branch), two kernels:
+//
+//  (A) fv1_flux_kernel : one THREAD per element, warp-uniform control flow. For each SCVF (ip) of the element,
+//      in reference order: StdVel -> upwind (No/Full/Skewed/LPS, ray search over constant-memory side tables)
+//      -> diffusion length -> FIELDS/FLOW/none closure -> defect fluxes. Every SCVF is evaluated ONCE.
+//      Nodal unknowns live in registers, corner coordinates / SCV volumes in thread-private shared columns
+//      (conflict-free). The SCVF geometry (normal, ip, global gradients) comes from the table precomputed at
+//      upload. Output: one compact FluxRec per (element, ip) = the state-dependent coefficients only.
+//  (B) fv1_rows_kernel : one WARP per grid node (= NF consecutive CSR rows). Stages the FluxRecs and the
+//      geometry of the <= CH*NINC SCVFs incident to the node with coalesced 128-bit loads, then lane =
+//      (corner k, function cf) accumulates its column of every incident SCVF (fixed order -> bitwise
+//      deterministic) into the node's rows in shared memory, and the finished rows are streamed to HBM exactly
+//      once (st.global.cs): no atomics, no colouring, no read-modify-write, no zero-fill of the matrix.
+//
+// Arithmetic restated from fv1/navier_stokes_fv1.cpp:250-778, fv1/stabilization.cpp:122-241,436-587,805-850,
+// upwind.cpp:52-80,133-172,381-430,505-575, fv1/diffusion_length.h:47-198.
+#pragma once
+#include <type_traits>
+#include "ns_kernels.cuh"
+
+namespace nsb {
+
+// ---- precomputed SCVF geometry table -------------------------------------------------------------
+// record of one (element, ip): [ n[DIM], xip[DIM], ds, pad... | G[d][k] d-major, k padded to even ]
+template <int E> struct GeoRec {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    static constexpr int HEAD = (DIM == 3) ? 8 : 4;
+    static constexpr int NSHP = (NSH + 1) & ~1;
+    static constexpr int SZ = HEAD + DIM * NSHP;          // doubles, even -> 16-byte aligned records
+};
+
+template <int E>
+__global__ void geom_kernel(int64_t n_elem, const int32_t* __restrict__ conn, const double* __restrict__ coords,
+                            double* __restrict__ geo)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP;
+    using R = GeoRec<E>;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_elem * NIP) return;
+    const int64_t e = i / NIP; const int ip = (int)(i - e * NIP);
+    double x[NSH * DIM];
+#pragma unroll
+    for (int k = 0; k < NSH; k++) {
+        const int64_t nd = conn[e * NSH + k];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) x[k * DIM + d] = coords[nd * DIM + d];
+    }
+    IpGeo<E> g;
+    ip_geometry<E>(x, ip, g);
+    double* r = geo + i * R::SZ;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) { r[d] = g.n[d]; r[DIM + d] = g.xip[d]; }
+    if (DIM == 3) { r[6] = g.ds; r[7] = 0.0; }
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+#pragma unroll
+        for (int k = 0; k < R::NSHP; k++) r[R::HEAD + d * R::NSHP + k] = (k < NSH) ? g.G[k < NSH ? k : 0][d] : 0.0;
+}
+
+// ---- compact per-(element, ip) record written by (A), read by (B) ------------------------------------
+//   F[NF]   defect fluxes (momentum d, continuity)                       add_def_A_elem :686-776
+//   inv     1/diag of the ip system (0 for no stabilisation)
+//   sn      StdVel . n ; std[DIM] StdVel                                 (FLOW continuity coefficients)
+//   cK[k]   (a N_k + b up_k + c (down_k - up_k)) * inv * rho  |  N_k rho (no stabilisation)
+//   dK[k]   up_k * prod * w + prod (1-w) N_k                             convective diagonal, :430-468
+//   EXACT:  eK[k] = rho (w up_k + (1-w) N_k [peclet]) , U[DIM]           exact-Newton extras, :521-549
+template <int E, bool EXACT> struct FluxRec {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1;
+    static constexpr int O_F = 0, O_INV = NF, O_SN = NF + 1, O_STD = NF + 2;
+    static constexpr int O_CK = (O_STD + DIM + 1) & ~1, O_DK = O_CK + NSH, O_EK = O_DK + NSH, O_U = O_EK + NSH;
+    static constexpr int RAW = EXACT ? O_U + DIM : O_EK;
+    static constexpr int SZ = (RAW + 1) & ~1;
+};
+
+NSB_DEV double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+// thread-private column in shared memory: element i of the calling thread
+#define NSB_COL(base, i) (base)[(i) * BS + tid]
+
+// ray / side intersection with warp-uniform side tables (constant memory); corner coordinates in the
+// thread's shared column xs. Same tests as side_ray_cut (ns_fv1.cuh), first hit in reference order wins.
+template <int E, int BS>
+NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const double* from, const double* dir,
+                             int& side_out, double* gcut, double* lcut)
+{
+    constexpr int DIM = ET<E>::DIM, NSIDE = ET<E>::NSIDE;
+    constexpr double S = NSB_RAY_SMALL;
+    bool found = false;
+    int best = 0;
+    double tn = 0.0, n1 = 0.0, n2 = 0.0, bdet = 1.0;
+    if constexpr (DIM == 2) {
+        const double dn2 = dir[0] * dir[0] + dir[1] * dir[1];
+        for (int s = 0; s < NSIDE; s++) {
+            const int p0 = tab::C_SIDE[E][s][0], p1 = tab::C_SIDE[E][s][1];
+            const double x0 = NSB_COL(xs, p0 * 2), y0 = NSB_COL(xs, p0 * 2 + 1);
+            const double ex = NSB_COL(xs, p1 * 2) - x0, ey = NSB_COL(xs, p1 * 2 + 1) - y0;
+            const double det = dir[0] * (-ey) + dir[1] * ex;
+            const double rx = x0 - from[0], ry = y0 - from[1];
+            const double t_n = rx * (-ey) + ry * ex, b_n = dir[0] * ry - dir[1] * rx;
+            const double sg = det > 0.0 ? 1.0 : -1.0, ad = fabs(det);
+            const bool hit = !found && det * det > (S * S) * dn2 * (ex * ex + ey * ey) &&
+                             b_n * sg >= -S * ad && b_n * sg <= (1.0 + S) * ad && t_n * sg <= 0.0;
+            if (hit) { found = true; best = s; tn = t_n; n1 = b_n; bdet = det; }
+        }
+        if (!found) return false;
+        const double t = tn / bdet, bc = n1 / bdet;
+        const int p0 = tab::SIDE[E][best][0], p1 = tab::SIDE[E][best][1];
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            gcut[d] = from[d] + t * dir[d];
+            lcut[d] = (1 - bc) * tab::CORNER[E][p0][d] + bc * tab::CORNER[E][p1][d];
+        }
+        side_out = best;
+        return true;
+    } else {
+        const double dn2 = dotv<3>(dir, dir);
+        constexpr int TPS = (E == E_HEX) ? 2 : 1;
+        for (int i = 0; i < NSIDE * TPS; i++) {
+            const int s = i / TPS, kk = i - s * TPS;
+            const int p0 = tab::C_SIDE[E][s][0], p1 = tab::C_SIDE[E][s][1 + kk], p2 = tab::C_SIDE[E][s][2 + kk];
+            double e1[3], e2[3], r[3], nrm[3], q[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double x0 = NSB_COL(xs, p0 * 3 + d);
+                e1[d] = NSB_COL(xs, p1 * 3 + d) - x0; e2[d] = NSB_COL(xs, p2 * 3 + d) - x0; r[d] = from[d] - x0;
+            }
+            cross3(nrm, e1, e2);
+            const double det = -dotv<3>(dir, nrm);
+            const double t_n = dotv<3>(r, nrm);
+            cross3(q, r, dir);
+            const double b1n = dotv<3>(e2, q), b2n = -dotv<3>(e1, q);
+            const double sg = det > 0.0 ? 1.0 : -1.0, ad = fabs(det);
+            const bool hit = !found && det * det > (S * S) * dn2 * dotv<3>(nrm, nrm) &&
+                             b1n * sg >= -S * ad && b2n * sg >= -S * ad && (b1n + b2n) * sg <= (1.0 + S) * ad && t_n * sg <= 0.0;
+            if (hit) { found = true; best = i; tn = t_n; n1 = b1n; n2 = b2n; bdet = det; }
+        }
+        if (!found) return false;
+        const double t = tn / bdet, b1 = n1 / bdet, b2 = n2 / bdet;
+        const int s = best / TPS, kk = best - s * TPS;
+        const int p0 = tab::SIDE[E][s][0], p1 = tab::SIDE[E][s][1 + kk], p2 = tab::SIDE[E][s][2 + kk];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            gcut[d] = from[d] + t * dir[d];
+            lcut[d] = (1 - b1 - b2) * tab::CORNER[E][p0][d] + b1 * tab::CORNER[E][p1][d] + b2 * tab::CORNER[E][p2][d];
+        }
+        side_out = s;
+        return true;
+    }
+}
+
+// upwind shapes of the current ip (warp-uniform `type`, `from`, `to`); see upwind_ip in ns_fv1.cuh
+template <int E, int BS>
+NSB_DEV bool upwind_uniform(int type, const double* __restrict__ xs, int tid, const double* n, const double* xip,
+                            const double* N, int from, int to, const double* vel, double* up, double& len)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    if (type == UPW_NO) {
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = N[k];
+        len = 1.0;
+        return true;
+    }
+    if (type == UPW_FULL) {                                      // upwind.cpp:150-171
+        const double flux = dotv<DIM>(n, vel);
+        const int co = flux > 0.0 ? from : to;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = (k == co) ? 1.0 : 0.0;
+        double s = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) { const double t = xip[d] - NSB_COL(xs, co * DIM + d); s += t * t; }
+        len = sqrt(s);
+        return true;
+    }
+#pragma unroll
+    for (int k = 0; k < NSH; k++) up[k] = 0.0;
+    if (sqrt(dotv<DIM>(vel, vel)) < 1e-14) { len = 1.0; return true; }      // upwind.cpp:407-413, 531-537
+    int side = 0; double gc[DIM], lc[DIM];
+    if (!ray_cut_uniform<E, BS>(xs, tid, xip, vel, side, gc, lc)) { len = 1.0; return false; }
+    constexpr int NSC = (DIM == 2) ? 2 : (E == E_TET ? 3 : 4);
+    if (type == UPW_SKEWED) {                                    // GetNodeNextToCut, upwind.cpp:337-379
+        double mn = 1.79769313486231570e308; int bestc = 0;
+#pragma unroll
+        for (int i = 0; i < NSC; i++) {
+            const int co = tab::SIDE[E][side][i];
+            double dd = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { const double t = gc[d] - NSB_COL(xs, co * DIM + d); dd += t * t; }
+            if (dd < mn) { mn = dd; bestc = co; }
+        }
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = (k == bestc) ? 1.0 : 0.0;
+        double s = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) { const double t = xip[d] - NSB_COL(xs, bestc * DIM + d); s += t * t; }
+        len = sqrt(s);
+    } else {                                                     // LPS, upwind.cpp:562-573
+        double Nc[NSH];
+        lagrange<E>(lc, Nc);
+        int mask = 0;
+#pragma unroll
+        for (int i = 0; i < NSC; i++) mask |= 1 << tab::SIDE[E][side][i];
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = ((mask >> k) & 1) ? Nc[k] : 0.0;
+        len = sqrt(dist2<DIM>(xip, gc));
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (A) flux kernel
+// ------------------------------------------------------------------------------------------------
+template <int E, int STAB, bool EXACT, int BS>
+__global__ void __launch_bounds__(BS) fv1_flux_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
+                                                      const double* __restrict__ u, const double* __restrict__ s0,
+                                                      const double* __restrict__ s1, double* __restrict__ flux,
+                                                      int* __restrict__ errflag)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, P = DIM;
+    constexpr bool FLOW = (STAB == STAB_FLOW);
+    using R = GeoRec<E>;
+    using FR = FluxRec<E, EXACT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* xs = reinterpret_cast<double*>(smem_raw);            // [NSH*DIM][BS]
+    double* vs = xs + NSH * DIM * BS;                            // [NSH][BS]
+    const int tid = threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * BS + tid;
+    if (e >= m.n_elem) return;                                   // no block-wide barriers below
+    const bool td = p.time_dep;
+    // ---- element data: unknowns in registers, coordinates / volumes in the thread's shared column ----
+    int nd[NSH];
+    double ur[NSH][NF];
+#pragma unroll
+    for (int k = 0; k < NSH; k++) nd[k] = m.conn[e * NSH + k];
+#pragma unroll
+    for (int k = 0; k < NSH; k++) {
+        if (NF == 4) {
+            const double2 a = ldg2(u + (int64_t)nd[k] * 4), b = ldg2(u + (int64_t)nd[k] * 4 + 2);
+            ur[k][0] = a.x; ur[k][1] = a.y; ur[k][2] = b.x; ur[k][NF - 1] = b.y;
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; f++) ur[k][f] = u[(int64_t)nd[k] * NF + f];
+        }
+#pragma unroll
+        for (int d = 0; d < DIM; d++) NSB_COL(xs, k * DIM + d) = m.coords[(int64_t)nd[k] * DIM + d];
+        NSB_COL(vs, k) = m.scvvol[e * NSH + k];
+    }
+    const double nurho = p.visc * p.rho;
+    const bool want_def = p.what & W_DEF_A, want_jac = p.what & W_JAC_A;
+    bool ok = true;
+    // COR diffusion length: element-wide statistics of the SCVF normals (diffusion_length.h:139-172)
+    double cmn = 0.0, cav = 0.0, cmd = 0.0;
+    if (STAB != STAB_NONE && p.diff_len == DIFF_COR) {
+        cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
+        for (int i = 0; i < NIP; i++) {
+            const double* h = geo + (e * NIP + i) * R::SZ;
+            double q = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { const double t = __ldg(h + d); q += t * t; }
+            if (q < cmn) cmn = q;
+            cav += q;
+            if (DIM == 3) { const double t = __ldg(h + R::HEAD - 2); if (t < cmd) cmd = t; }
+        }
+        cav /= NIP;
+    }
+
+    for (int ip = 0; ip < NIP; ip++) {
+        const double* g = geo + (e * NIP + ip) * R::SZ;
+        double* fr = flux + (e * NIP + ip) * FR::SZ;
+        const int from = tab::C_EDGE[E][ip][0], to = tab::C_EDGE[E][ip][1];
+        double n[DIM], xip[DIM], ds = 0.0;
+        {
+            double h[R::HEAD];
+#pragma unroll
+            for (int i = 0; i < R::HEAD; i += 2) { const double2 v = ldg2(g + i); h[i] = v.x; h[i + 1] = v.y; }
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { n[d] = h[d]; xip[d] = h[DIM + d]; }
+            if (DIM == 3) ds = h[R::HEAD - 2];
+        }
+        double N[NSH];
+#pragma unroll
+        for (int k = 0; k < NSH; k++) N[k] = tab::NIPSH[E][ip][k];
+        // ---- StdVel from the `u` argument (:282-293) ----
+        double std[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < NSH; k++) s += ur[k][d] * N[k];
+            std[d] = s;
+        }
+        const double sn = dotv<DIM>(std, n);
+        const double prod = sn * p.rho;
+        // ---- upwinds ----
+        double up[NSH], dnm[NSH], uplen = 1.0, dnlen = 1.0;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) { up[k] = 0.0; dnm[k] = 0.0; }
+        if (!p.stokes) {
+            ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, std, up, uplen);
+            if (FLOW) {                                          // update_downwind, upwind_interface.h:157-165
+                double neg[DIM], dn[NSH];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) neg[d] = -1.0 * std[d];
+                ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, neg, dn, dnlen);
+#pragma unroll
+                for (int k = 0; k < NSH; k++) dnm[k] = dn[k] - up[k];
+            }
+        }
+        // ---- diagonal of the ip system and numerators sb_k (stabilization.cpp:166-236 / :489-582) ----
+        double inv = 0.0, sb[NSH];
+        if (STAB != STAB_NONE) {
+            const double nn = dotv<DIM>(n, n);
+            const double a = p.visc * diff_len_sq_inv<DIM>(p.diff_len, nn, NSB_COL(vs, from), NSB_COL(vs, to), ds, cmn, cav, cmd);
+            double b = 0.0, c = 0.0;
+            if (!p.stokes) {
+                const double nrm = sqrt(dotv<DIM>(std, std));
+                b = nrm / uplen;
+                if (FLOW) c = nrm / (dnlen + uplen);
+            }
+            double diag = a;
+            if (td) diag += 1.0 / p.dt;
+            if (!p.stokes) diag += b;
+            inv = 1.0 / diag;
+#pragma unroll
+            for (int k = 0; k < NSH; k++) {
+                double s = a * N[k];
+                if (!p.stokes) { s += b * up[k]; if (FLOW) s += c * dnm[k]; }
+                sb[k] = s;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NSH; k++) sb[k] = 0.0;
+        }
+        // ---- convective upwind, transported velocity, Peclet blend ----
+        double U[DIM], w = 1.0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) U[d] = 0.0;
+        if (!p.stokes) {
+            if (p.upw_conv != p.upw_stab) { double l2; ok &= upwind_uniform<E, BS>(p.upw_conv, xs, tid, n, xip, N, from, to, std, up, l2); }
+#pragma unroll
+            for (int k = 0; k < NSH; k++)
+#pragma unroll
+                for (int d = 0; d < DIM; d++) U[d] += up[k] * ur[k][d];          // upwind_vel, upwind_interface.h:334-358
+            if (p.peclet) {                                       // peclet_blend :871-892
+                double dd = 0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) { const double t = NSB_COL(xs, to * DIM + d) - NSB_COL(xs, from * DIM + d); dd += t * t; }
+                const double Pe = sn / dotv<DIM>(n, n) * sqrt(dd) / p.visc;
+                const double Pe2 = Pe * Pe;
+                w = Pe2 / (5.0 + Pe2);
+#pragma unroll
+                for (int d = 0; d < DIM; d++) U[d] = w * U[d] + (1.0 - w) * std[d];
+            }
+        }
+        // ---- Jacobian coefficients ----
+        if (want_jac) {
+            const double cw = prod * w, cpe = prod * (1.0 - w);
+            double ck[NSH], dk[NSH];
+#pragma unroll
+            for (int k = 0; k < NSH; k++) {
+                ck[k] = (STAB == STAB_NONE) ? N[k] * p.rho : sb[k] * inv * p.rho;
+                double D = 0.0;
+                if (!p.stokes) { D = up[k] * cw; if (p.peclet) D += cpe * N[k]; }
+                dk[k] = D;
+            }
+            if constexpr (NSH % 2 == 0) {
+#pragma unroll
+                for (int k = 0; k < NSH; k += 2) {
+                    *reinterpret_cast<double2*>(fr + FR::O_CK + k) = make_double2(ck[k], ck[k + 1]);
+                    *reinterpret_cast<double2*>(fr + FR::O_DK + k) = make_double2(dk[k], dk[k + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NSH; k++) { fr[FR::O_CK + k] = ck[k]; fr[FR::O_DK + k] = dk[k]; }
+            }
+            if constexpr (EXACT) {
+                const bool exact = !p.stokes && p.exact_jac != 0.0;
+#pragma unroll
+                for (int k = 0; k < NSH; k++) {
+                    double ev = 0.0;
+                    if (exact) { ev = w * up[k] * p.rho; if (p.peclet) ev += (1.0 - w) * N[k] * p.rho; }   // quirks :528-529,:542-545
+                    fr[FR::O_EK + k] = ev;
+                }
+#pragma unroll
+                for (int d = 0; d < DIM; d++) fr[FR::O_U + d] = U[d];
+            }
+        }
+        fr[FR::O_INV] = inv; fr[FR::O_SN] = sn;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) fr[FR::O_STD + d] = std[d];
+        // ---- defect fluxes (:686-776): stream the global gradients (d-major) ----
+        if (want_def) {
+            double gv[DIM][DIM], gp[DIM], gv0[DIM][DIM], gp0[DIM], sG[NSH];
+#pragma unroll
+            for (int k = 0; k < NSH; k++) sG[k] = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                double Gd[R::NSHP];
+#pragma unroll
+                for (int k = 0; k < R::NSHP; k += 2) { const double2 v = ldg2(g + R::HEAD + d * R::NSHP + k); Gd[k] = v.x; Gd[k + 1] = v.y; }
+                double sp = 0.0, sv[DIM];
+#pragma unroll
+                for (int q = 0; q < DIM; q++) sv[q] = 0.0;
+#pragma unroll
+                for (int k = 0; k < NSH; k++) {
+                    if (FLOW) sG[k] += Gd[k] * std[d];
+                    sp += Gd[k] * ur[k][P];
+#pragma unroll
+                    for (int q = 0; q < DIM; q++) sv[q] += Gd[k] * ur[k][q];
+                }
+                gp[d] = sp;
+#pragma unroll
+                for (int q = 0; q < DIM; q++) gv[q][d] = sv[q];
+                if (td) {                                        // the closure uses solution(0) (:296, :646)
+                    double sp0 = 0.0, sv0[DIM];
+#pragma unroll
+                    for (int q = 0; q < DIM; q++) sv0[q] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NSH; k++) {
+                        sp0 += Gd[k] * s0[(int64_t)nd[k] * NF + P];
+#pragma unroll
+                        for (int q = 0; q < DIM; q++) sv0[q] += Gd[k] * s0[(int64_t)nd[k] * NF + q];
+                    }
+                    gp0[d] = sp0;
+#pragma unroll
+                    for (int q = 0; q < DIM; q++) gv0[q][d] = sv0[q];
+                }
+            }
+            double pr = 0.0;
+#pragma unroll
+            for (int k = 0; k < NSH; k++) pr += N[k] * ur[k][P];
+            double F[NF];
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++) {
+                double df = 0.0;
+#pragma unroll
+                for (int d2 = 0; d2 < DIM; d2++) df += gv[d1][d2] * n[d2];
+                if (!p.laplace) {
+#pragma unroll
+                    for (int d2 = 0; d2 < DIM; d2++) df += gv[d2][d1] * n[d2];
+                }
+                double f = df * (-1.0) * nurho;
+                if (!p.stokes) f += U[d1] * prod;
+                f += pr * n[d1];
+                F[d1] = f;
+            }
+            double cont;
+            if (STAB == STAB_NONE) cont = sn * p.rho;
+            else {
+                // (stab_vel . n) rho with rhs_d = src_d + old_d/dt + sum_k [sv(d,d,k) s_dk + sum_{q!=d} sv(d,q,k) s_qk] - G_kd/rho p_k
+                //  = n.src + n.old/dt + sum_k (sb_k [- std.G_k]) (s_k.n) [+ (std.n) div s] - (grad p . n)/rho
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < NSH; k++) {
+                    double sk = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) sk += (td ? s0[(int64_t)nd[k] * NF + d] : ur[k][d]) * n[d];
+                    acc += (FLOW ? sb[k] - sG[k] : sb[k]) * sk;
+                }
+                double gpn = 0.0, div = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) { gpn += (td ? gp0[d] : gp[d]) * n[d]; div += td ? gv0[d][d] : gv[d][d]; }
+                acc -= gpn * p.inv_rho;
+                if (FLOW) acc += sn * div;
+                if (p.has_source) {
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) acc += p.src[d] * n[d];
+                }
+                if (td) {
+                    double o = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NSH; k++) {
+                        double sk = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DIM; d++) sk += s1[(int64_t)nd[k] * NF + d] * n[d];
+                        o += N[k] * sk;
+                    }
+                    acc += o / p.dt;
+                }
+                cont = acc * inv * p.rho;
+            }
+            F[P] = cont;
+#pragma unroll
+            for (int f = 0; f < NF; f++) fr[FR::O_F + f] = F[f];
+        }
+    }
+    if (!ok) atomicExch(errflag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (B) rows kernel
+// ------------------------------------------------------------------------------------------------
+template <int E> struct RowCfg {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, NINC = ET<E>::NINC, NIP = ET<E>::NIP;
+    static constexpr int CH = (DIM == 3) ? 8 : 16;          // adjacent elements per round
+    static constexpr int NREC = CH * NINC;
+};
+template <int E, bool EXACT> struct RowWS {
+    using C = RowCfg<E>;
+    double geo[C::NREC][GeoRec<E>::SZ];
+    double flx[C::NREC][FluxRec<E, EXACT>::SZ];
+    double vol[C::CH];
+    int32_t elem[C::CH];
+    int32_t la[C::CH];
+    int32_t ipx[C::NREC];           // ip | (sign bit 8)
+    uint8_t slot[C::CH][C::NSH];
+};
+
+template <int E, int STAB, bool EXACT>
+__global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
+                                                          const double* __restrict__ flux, const double* __restrict__ u,
+                                                          double beta, double* __restrict__ val, double* __restrict__ def)
+{
+    using C = RowCfg<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, L = NSH * NF, NIP = C::NIP;
+    constexpr bool FLOW = (STAB == STAB_FLOW);
+    using R = GeoRec<E>;
+    using FR = FluxRec<E, EXACT>;
+    using WS = RowWS<E, EXACT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double* Ntab = reinterpret_cast<double*>(smem_raw);
+    const size_t tab_bytes = (sizeof(double) * NIP * NSH + 15) & ~(size_t)15;
+    const size_t per_warp = (sizeof(WS) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
+    WS& ws = *reinterpret_cast<WS*>(smem_raw + tab_bytes + warp * per_warp);
+    double* rowacc = reinterpret_cast<double*>(smem_raw + tab_bytes + warp * per_warp + sizeof(WS));
+    for (int i = threadIdx.x; i < NIP * NSH; i += blockDim.x) Ntab[i] = tab::NIPSH[E][i / NSH][i % NSH];
+    __syncthreads();
+    const bool want_jac = p.what & (W_JAC_A | W_JAC_M), want_def = p.what & (W_DEF_A | W_DEF_M | W_RHS);
+    const bool jac_a = p.what & W_JAC_A, def_a = p.what & W_DEF_A;
+    const int k = lane / NF, cf = lane - k * NF;
+    const double nurho = p.laplace ? 0.0 : p.visc * p.rho;      // A-part -nu rho G_kd1 n_d2 vanishes for laplace (:346-356)
+    const double nurho_d = p.visc * p.rho;
+
+    for (int64_t a = (int64_t)blockIdx.x * nwarp + warp; a < m.n_node; a += (int64_t)gridDim.x * nwarp) {
+        const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1];
+        const int64_t b0 = m.brow[a];
+        const int cnt = (int)(m.brow[a + 1] - b0);
+        const int rowlen = cnt * NF;
+        if (want_jac) for (int i = lane; i < NF * rowlen; i += 32) rowacc[i] = 0.0;
+        double dsum = 0.0, volsum = 0.0;
+        int self_slot = 0;
+        for (int64_t qb = q0; qb < q1; qb += CH) {
+            const int nj = (int)((q1 - qb) < CH ? (q1 - qb) : CH);
+            const int nrec = nj * NINC;
+            __syncwarp();
+            // ---- stage: adjacency, slots, signs ----
+            if (lane < nj) {
+                const int32_t ad = m.adj[qb + lane];
+                const int e = ad / NSH, la = ad - e * NSH;
+                ws.elem[lane] = e; ws.la[lane] = la;
+                ws.vol[lane] = m.scvvol[(int64_t)e * NSH + la];
+#pragma unroll
+                for (int kk = 0; kk < NSH; kk++) ws.slot[lane][kk] = m.emap[(int64_t)e * (NSH * NSH) + la * NSH + kk];
+#pragma unroll
+                for (int t = 0; t < NINC; t++)
+                    ws.ipx[lane * NINC + t] = tab::INC[E][la][t] | (tab::INC_SIGN[E][la][t] < 0 ? 256 : 0);
+            }
+            __syncwarp();
+            // ---- stage: geometry + flux records of the incident SCVFs, coalesced 128-bit loads ----
+            if (jac_a) {
+                constexpr int GV = R::SZ / 2;
+                for (int i = lane; i < nrec * GV; i += 32) {
+                    const int r = i / GV, o = i - r * GV;
+                    const int j = r / NINC;
+                    const int64_t gi = (int64_t)ws.elem[j] * NIP + (ws.ipx[r] & 255);
+                    const double2 v = ldg2(geo + gi * R::SZ + 2 * o);
+                    *reinterpret_cast<double2*>(&ws.geo[r][2 * o]) = v;
+                }
+            }
+            if (jac_a || def_a) {
+                constexpr int FV = FR::SZ / 2;
+                for (int i = lane; i < nrec * FV; i += 32) {
+                    const int r = i / FV, o = i - r * FV;
+                    const int j = r / NINC;
+                    const int64_t gi = (int64_t)ws.elem[j] * NIP + (ws.ipx[r] & 255);
+                    const double2 v = ldg2(flux + gi * FR::SZ + 2 * o);
+                    *reinterpret_cast<double2*>(&ws.flx[r][2 * o]) = v;
+                }
+            }
+            __syncwarp();
+            // ---- accumulate: lane = (k, cf); fixed order j, t  (add_jac_A_elem :317-594) ----
+            if (want_jac && lane < L) {
+                for (int j = 0; j < nj; j++) {
+                    double acc[NF];
+#pragma unroll
+                    for (int rf = 0; rf < NF; rf++) acc[rf] = 0.0;
+                    if (jac_a) {
+#pragma unroll
+                        for (int t = 0; t < NINC; t++) {
+                            const int r = j * NINC + t;
+                            const double* gr = ws.geo[r];
+                            const double* fl = ws.flx[r];
+                            const int ipx = ws.ipx[r];
+                            const double sg = (ipx & 256) ? -1.0 : 1.0;
+                            double n[DIM], Gk[DIM];
+#pragma unroll
+                            for (int d = 0; d < DIM; d++) { n[d] = gr[d]; Gk[d] = gr[R::HEAD + d * R::NSHP + k]; }
+                            const double gn = dotv<DIM>(Gk, n);
+                            const double inv = fl[FR::O_INV];
+                            double v[NF];
+                            if (cf < DIM) {
+                                const double ncf = n[cf];
+#pragma unroll
+                                for (int d1 = 0; d1 < DIM; d1++) {
+                                    double av = -1.0 * nurho * Gk[d1];
+                                    if constexpr (EXACT) av += fl[FR::O_EK + k] * fl[FR::O_U + d1];
+                                    v[d1] = av * ncf;
+                                }
+                                const double D = -1.0 * nurho_d * gn + fl[FR::O_DK + k];
+#pragma unroll
+                                for (int d1 = 0; d1 < DIM; d1++) if (d1 == cf) v[d1] += D;
+                                // continuity row (:561-584)
+                                double cv = fl[FR::O_CK + k] * ncf;
+                                if constexpr (FLOW) {
+                                    // sum_q sv(q,d2,k) n_q rho = ((sb_k - std.G_k) n_d2 + G_k[d2] (std.n)) inv rho
+                                    double sG = 0.0;
+#pragma unroll
+                                    for (int d = 0; d < DIM; d++) sG += fl[FR::O_STD + d] * Gk[d];
+                                    cv += (Gk[cf] * fl[FR::O_SN] - sG * ncf) * inv * p.rho;
+                                }
+                                v[DIM] = cv;
+                            } else {
+                                const double Nk = Ntab[(ipx & 255) * NSH + k];
+#pragma unroll
+                                for (int d1 = 0; d1 < DIM; d1++) v[d1] = Nk * n[d1];            // :363-368
+                                v[DIM] = (STAB == STAB_NONE) ? 0.0 : -1.0 * gn * inv;           // :586-592, rho cancels
+                            }
+#pragma unroll
+                            for (int rf = 0; rf < NF; rf++) acc[rf] += sg * v[rf];
+                        }
+#pragma unroll
+                        for (int rf = 0; rf < NF; rf++) acc[rf] *= p.scale_a;
+                    }
+                    const int slot = ws.slot[j][k];
+#pragma unroll
+                    for (int rf = 0; rf < NF; rf++) rowacc[rf * rowlen + slot * NF + cf] += acc[rf];
+                }
+            }
+            // ---- defect + lumped mass: lanes < NF own (a, rf = lane) ----
+            if (lane < NF) {
+                for (int j = 0; j < nj; j++) {
+                    if (def_a) {
+#pragma unroll
+                        for (int t = 0; t < NINC; t++) {
+                            const int r = j * NINC + t;
+                            dsum += ((ws.ipx[r] & 256) ? -1.0 : 1.0) * ws.flx[r][FR::O_F + lane];
+                        }
+                    }
+                    volsum += ws.vol[j];
+                }
+                if (qb == q0) self_slot = ws.slot[0][ws.la[0]];
+            }
+        }
+        __syncwarp();
+        if (want_jac) {
+            if ((p.what & W_JAC_M) && lane < DIM) rowacc[lane * rowlen + self_slot * NF + lane] += p.scale_m * volsum * p.rho;
+            __syncwarp();
+            double* out = val + b0 * (NF * NF);
+            const int tot = NF * rowlen;
+            if (beta == 0.0) {
+                if ((NF * NF) % 2 == 0) {
+                    for (int i = 2 * lane; i < tot; i += 64) __stcs(reinterpret_cast<double2*>(out + i), make_double2(rowacc[i], rowacc[i + 1]));
+                } else for (int i = lane; i < tot; i += 32) __stcs(out + i, rowacc[i]);
+            } else for (int i = lane; i < tot; i += 32) out[i] = beta * out[i] + rowacc[i];
+        }
+        if (want_def && lane < NF) {
+            double d = def_a ? dsum : 0.0;
+            if ((p.what & W_RHS) && p.has_source && lane < DIM) d -= p.src[lane] * volsum * p.rho;
+            d *= p.scale_a;
+            if ((p.what & W_DEF_M) && lane < DIM) d += p.scale_m * u[a * NF + lane] * volsum * p.rho;
+            double* q = def + a * NF + lane;
+            *q = (beta == 0.0) ? d : beta * (*q) + d;
+        }
+    }
+}
+
+}  // namespace nsb

@@ -50,7 +50,7 @@ struct nsb_ctx {
     std::vector<int64_t> h_color_ptr;
     // device
     int32_t *d_conn = nullptr, *d_adj = nullptr, *d_color_order = nullptr, *d_esides = nullptr;
-    double *d_coords = nullptr, *d_scvvol = nullptr, *d_geo = nullptr;
+    double *d_coords = nullptr, *d_scvvol = nullptr, *d_geo = nullptr, *d_flux = nullptr;
     int64_t *d_brow = nullptr, *d_adj_ptr = nullptr;
     uint8_t *d_emap = nullptr;
     FvcrDev fvcr{};
@@ -134,11 +134,11 @@ extern "C" int nsb_create(int device, nsb_ctx** out)
 static void free_mesh(nsb_ctx* c)
 {
     cudaFree(c->d_conn); cudaFree(c->d_adj); cudaFree(c->d_color_order); cudaFree(c->d_esides); cudaFree(c->d_coords);
-    cudaFree(c->d_scvvol); cudaFree(c->d_geo); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
+    cudaFree(c->d_scvvol); cudaFree(c->d_geo); cudaFree(c->d_flux); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
     cudaFree(c->d_u); cudaFree(c->d_s0); cudaFree(c->d_s1); cudaFree(c->d_val); cudaFree(c->d_def);
     cudaFree(c->d_jloc); cudaFree(c->d_dloc);
     fvcr_free(c->fvcr);
-    c->d_conn = c->d_adj = c->d_color_order = c->d_esides = nullptr; c->d_coords = c->d_scvvol = c->d_geo = nullptr;
+    c->d_conn = c->d_adj = c->d_color_order = c->d_esides = nullptr; c->d_coords = c->d_scvvol = c->d_geo = c->d_flux = nullptr;
     c->d_brow = c->d_adj_ptr = nullptr; c->d_emap = nullptr;
     c->d_u = c->d_s0 = c->d_s1 = c->d_val = c->d_def = c->d_jloc = c->d_dloc = nullptr;
     c->mesh_ready = false;
@@ -441,11 +441,18 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
 {
     const MeshDev m = mesh_view(c);
     cudaError_t e;
-#define NSB_GO(fn) fn(k, m, c->d_geo, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count)
+    if (!c->d_flux) {       // per-(element, ip) flux records exchanged between the flux and the rows kernel
+        size_t rec = 0;
+        switch (c->elem) { case 0: rec = flux_record_doubles_0(); break; case 1: rec = flux_record_doubles_1(); break;
+                           case 2: rec = flux_record_doubles_2(); break; default: rec = flux_record_doubles_3(); }
+        static const int kNIP[4] = {3, 4, 6, 12};
+        CUDA_TRY(c, cudaMalloc(&c->d_flux, (size_t)c->n_elem * kNIP[c->elem] * rec * sizeof(double)));
+    }
+#define NSB_GO(fn) fn(k, m, c->d_geo, c->d_flux, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count)
     switch (c->elem) { case 0: e = NSB_GO(launch_gather_0); break; case 1: e = NSB_GO(launch_gather_1); break;
                        case 2: e = NSB_GO(launch_gather_2); break; default: e = NSB_GO(launch_gather_3); }
 #undef NSB_GO
-    c->launches++;
+    c->launches += (k.what & (W_JAC_A | W_DEF_A)) ? 2 : 1;
     CUDA_TRY(c, e);
     return NSB_OK;
 }
