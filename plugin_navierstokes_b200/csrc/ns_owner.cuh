@@ -499,11 +499,16 @@ template <int E, bool EXACT> struct RowWS {
     double geo[C::NREC][GeoRec<E>::SZ];
     double flx[C::NREC][FluxRec<E, EXACT>::SZ];
     double vol[C::CH];
-    int32_t elem[C::CH];
-    int32_t la[C::CH];
-    int32_t ipx[C::NREC];           // ip | (sign bit 8)
-    uint8_t slot[C::CH][C::NSH];
+    int32_t ipx[C::NREC];           // ip | (256 if the node is the `to` corner of the SCVF)
+    uint8_t slot[C::CH][8];
 };
+
+NSB_DEV void cp_async16(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+NSB_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int E, int STAB, bool EXACT>
 __global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
@@ -516,20 +521,34 @@ __global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, 
     using R = GeoRec<E>;
     using FR = FluxRec<E, EXACT>;
     using WS = RowWS<E, EXACT>;
+    constexpr int GV = R::SZ / 2, FV = FR::SZ / 2;               // 16-byte chunks per record
+    static_assert(GV <= 32 && FV <= 32, "record wider than a warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    // block layout: [Ntab NIP*NSH doubles][inc table NSH*NINC ints][per warp: WS | rowacc NF*NF*max_cnt doubles]
     double* Ntab = reinterpret_cast<double*>(smem_raw);
-    const size_t tab_bytes = (sizeof(double) * NIP * NSH + 15) & ~(size_t)15;
+    int32_t* inctab = reinterpret_cast<int32_t*>(smem_raw + sizeof(double) * NIP * NSH);
+    const size_t tab_bytes = (sizeof(double) * NIP * NSH + sizeof(int32_t) * NSH * NINC + 15) & ~(size_t)15;
     const size_t per_warp = (sizeof(WS) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
     WS& ws = *reinterpret_cast<WS*>(smem_raw + tab_bytes + warp * per_warp);
     double* rowacc = reinterpret_cast<double*>(smem_raw + tab_bytes + warp * per_warp + sizeof(WS));
     for (int i = threadIdx.x; i < NIP * NSH; i += blockDim.x) Ntab[i] = tab::NIPSH[E][i / NSH][i % NSH];
+    for (int i = threadIdx.x; i < NSH * NINC; i += blockDim.x)
+        inctab[i] = tab::INC[E][i / NINC][i % NINC] | (tab::INC_SIGN[E][i / NINC][i % NINC] < 0 ? 256 : 0);
     __syncthreads();
     const bool want_jac = p.what & (W_JAC_A | W_JAC_M), want_def = p.what & (W_DEF_A | W_DEF_M | W_RHS);
     const bool jac_a = p.what & W_JAC_A, def_a = p.what & W_DEF_A;
-    const int k = lane / NF, cf = lane - k * NF;
-    const double nurho = p.laplace ? 0.0 : p.visc * p.rho;      // A-part -nu rho G_kd1 n_d2 vanishes for laplace (:346-356)
-    const double nurho_d = p.visc * p.rho;
+    // lane = (corner k, function cf) of the element block; per-lane selectors make the accumulate branch-free
+    const int k = (lane < L) ? lane / NF : 0, cf = (lane < L) ? lane - (lane / NF) * NF : 0;
+    const bool isv = cf < DIM;                                   // velocity column / pressure column
+    const int cfv = isv ? cf : 0;
+    const double wv = isv ? 1.0 : 0.0, wp = isv ? 0.0 : 1.0;
+    double msk[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) msk[d] = (isv && d == cf) ? 1.0 : 0.0;
+    const double nurho_a = p.laplace ? 0.0 : -1.0 * p.visc * p.rho;   // -nu rho G_kd1 n_d2 vanishes for laplace (:346-356)
+    const double nurho_d = -1.0 * p.visc * p.rho;
+    const double rho_f = FLOW ? p.rho : 0.0;
 
     for (int64_t a = (int64_t)blockIdx.x * nwarp + warp; a < m.n_node; a += (int64_t)gridDim.x * nwarp) {
         const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1];
@@ -543,41 +562,34 @@ __global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, 
             const int nj = (int)((q1 - qb) < CH ? (q1 - qb) : CH);
             const int nrec = nj * NINC;
             __syncwarp();
-            // ---- stage: adjacency, slots, signs ----
+            // ---- adjacency of this round: lane j < nj holds (element, local corner) ----
+            const int32_t ad = (lane < nj) ? m.adj[qb + lane] : 0;
+            const int e_l = ad / NSH, la_l = ad - e_l * NSH;
+            // record handled by this lane (r = lane < nrec): SCVF t of adjacent element j
+            const int rj = lane / NINC, rt = lane - rj * NINC;
+            const int e_r = __shfl_sync(0xffffffffu, e_l, rj < CH ? rj : 0);
+            const int la_r = __shfl_sync(0xffffffffu, la_l, rj < CH ? rj : 0);
+            const int ipx_r = inctab[la_r * NINC + rt];
+            const int64_t gi_r = (int64_t)e_r * NIP + (ipx_r & 255);
+            if (lane < nrec) ws.ipx[lane] = ipx_r;
+            // ---- asynchronous staging: every 16-byte chunk of every incident record in flight at once ----
+            for (int r = 0; r < nrec; r++) {
+                const int64_t gi = __shfl_sync(0xffffffffu, gi_r, r);
+                if (jac_a && lane < GV) cp_async16(&ws.geo[r][2 * lane], geo + gi * R::SZ + 2 * lane);
+                if (lane < FV) cp_async16(&ws.flx[r][2 * lane], flux + gi * FR::SZ + 2 * lane);
+            }
+            // scatter slots + the node's SCV volume in the adjacent elements (plain loads, overlapped with the copies)
             if (lane < nj) {
-                const int32_t ad = m.adj[qb + lane];
-                const int e = ad / NSH, la = ad - e * NSH;
-                ws.elem[lane] = e; ws.la[lane] = la;
-                ws.vol[lane] = m.scvvol[(int64_t)e * NSH + la];
-#pragma unroll
-                for (int kk = 0; kk < NSH; kk++) ws.slot[lane][kk] = m.emap[(int64_t)e * (NSH * NSH) + la * NSH + kk];
-#pragma unroll
-                for (int t = 0; t < NINC; t++)
-                    ws.ipx[lane * NINC + t] = tab::INC[E][la][t] | (tab::INC_SIGN[E][la][t] < 0 ? 256 : 0);
+                const uint8_t* em = m.emap + (int64_t)ad * NSH;
+                if (NSH == 8) *reinterpret_cast<uint2*>(ws.slot[lane]) = __ldg(reinterpret_cast<const uint2*>(em));
+                else if (NSH == 4) *reinterpret_cast<uint32_t*>(ws.slot[lane]) = __ldg(reinterpret_cast<const uint32_t*>(em));
+                else { for (int q = 0; q < NSH; q++) ws.slot[lane][q] = em[q]; }
+                ws.vol[lane] = m.scvvol[ad];
             }
+            const int sslot = __shfl_sync(0xffffffffu, la_l, 0);
+            cp_async_wait_all();
             __syncwarp();
-            // ---- stage: geometry + flux records of the incident SCVFs, coalesced 128-bit loads ----
-            if (jac_a) {
-                constexpr int GV = R::SZ / 2;
-                for (int i = lane; i < nrec * GV; i += 32) {
-                    const int r = i / GV, o = i - r * GV;
-                    const int j = r / NINC;
-                    const int64_t gi = (int64_t)ws.elem[j] * NIP + (ws.ipx[r] & 255);
-                    const double2 v = ldg2(geo + gi * R::SZ + 2 * o);
-                    *reinterpret_cast<double2*>(&ws.geo[r][2 * o]) = v;
-                }
-            }
-            if (jac_a || def_a) {
-                constexpr int FV = FR::SZ / 2;
-                for (int i = lane; i < nrec * FV; i += 32) {
-                    const int r = i / FV, o = i - r * FV;
-                    const int j = r / NINC;
-                    const int64_t gi = (int64_t)ws.elem[j] * NIP + (ws.ipx[r] & 255);
-                    const double2 v = ldg2(flux + gi * FR::SZ + 2 * o);
-                    *reinterpret_cast<double2*>(&ws.flx[r][2 * o]) = v;
-                }
-            }
-            __syncwarp();
+            if (qb == q0) self_slot = ws.slot[0][sslot];
             // ---- accumulate: lane = (k, cf); fixed order j, t  (add_jac_A_elem :317-594) ----
             if (want_jac && lane < L) {
                 for (int j = 0; j < nj; j++) {
@@ -597,36 +609,30 @@ __global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, 
                             for (int d = 0; d < DIM; d++) { n[d] = gr[d]; Gk[d] = gr[R::HEAD + d * R::NSHP + k]; }
                             const double gn = dotv<DIM>(Gk, n);
                             const double inv = fl[FR::O_INV];
-                            double v[NF];
-                            if (cf < DIM) {
-                                const double ncf = n[cf];
+                            const double ncf = gr[cfv];
+                            const double Nk = Ntab[(ipx & 255) * NSH + k];
+                            // velocity column: X = -nu rho G_k (+ e_k U), Y = n_cf ; pressure column: X = n, Y = N_k (:363-368)
+                            const double Y = wv * ncf + wp * Nk;
+                            const double D = nurho_d * gn + fl[FR::O_DK + k];
+                            double ek = 0.0;
+                            if constexpr (EXACT) ek = fl[FR::O_EK + k];
 #pragma unroll
-                                for (int d1 = 0; d1 < DIM; d1++) {
-                                    double av = -1.0 * nurho * Gk[d1];
-                                    if constexpr (EXACT) av += fl[FR::O_EK + k] * fl[FR::O_U + d1];
-                                    v[d1] = av * ncf;
-                                }
-                                const double D = -1.0 * nurho_d * gn + fl[FR::O_DK + k];
-#pragma unroll
-                                for (int d1 = 0; d1 < DIM; d1++) if (d1 == cf) v[d1] += D;
-                                // continuity row (:561-584)
-                                double cv = fl[FR::O_CK + k] * ncf;
-                                if constexpr (FLOW) {
-                                    // sum_q sv(q,d2,k) n_q rho = ((sb_k - std.G_k) n_d2 + G_k[d2] (std.n)) inv rho
-                                    double sG = 0.0;
-#pragma unroll
-                                    for (int d = 0; d < DIM; d++) sG += fl[FR::O_STD + d] * Gk[d];
-                                    cv += (Gk[cf] * fl[FR::O_SN] - sG * ncf) * inv * p.rho;
-                                }
-                                v[DIM] = cv;
-                            } else {
-                                const double Nk = Ntab[(ipx & 255) * NSH + k];
-#pragma unroll
-                                for (int d1 = 0; d1 < DIM; d1++) v[d1] = Nk * n[d1];            // :363-368
-                                v[DIM] = (STAB == STAB_NONE) ? 0.0 : -1.0 * gn * inv;           // :586-592, rho cancels
+                            for (int d1 = 0; d1 < DIM; d1++) {
+                                double X = wv * (nurho_a * Gk[d1]) + wp * n[d1];
+                                if constexpr (EXACT) X += wv * ek * fl[FR::O_U + d1];
+                                acc[d1] += sg * (X * Y + msk[d1] * D);
                             }
+                            // continuity row: velocity column (:561-584), pressure column (:586-592, rho cancels)
+                            double cv = fl[FR::O_CK + k] * ncf;
+                            if constexpr (FLOW) {
+                                // sum_q sv(q,d2,k) n_q rho = ((sb_k - std.G_k) n_d2 + G_k[d2] (std.n)) inv rho
+                                double sG = 0.0;
 #pragma unroll
-                            for (int rf = 0; rf < NF; rf++) acc[rf] += sg * v[rf];
+                                for (int d = 0; d < DIM; d++) sG += fl[FR::O_STD + d] * Gk[d];
+                                cv += (gr[R::HEAD + cfv * R::NSHP + k] * fl[FR::O_SN] - sG * ncf) * inv * rho_f;
+                            }
+                            const double cpv = (STAB == STAB_NONE) ? 0.0 : -1.0 * gn * inv;
+                            acc[DIM] += sg * (wv * cv + wp * cpv);
                         }
 #pragma unroll
                         for (int rf = 0; rf < NF; rf++) acc[rf] *= p.scale_a;
@@ -636,20 +642,19 @@ __global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, 
                     for (int rf = 0; rf < NF; rf++) rowacc[rf * rowlen + slot * NF + cf] += acc[rf];
                 }
             }
-            // ---- defect + lumped mass: lanes < NF own (a, rf = lane) ----
-            if (lane < NF) {
-                for (int j = 0; j < nj; j++) {
-                    if (def_a) {
+            // ---- defect: lane r < nrec contributes its signed fluxes; deterministic butterfly reduction ----
+            if (def_a) {
+                double f[NF];
 #pragma unroll
-                        for (int t = 0; t < NINC; t++) {
-                            const int r = j * NINC + t;
-                            dsum += ((ws.ipx[r] & 256) ? -1.0 : 1.0) * ws.flx[r][FR::O_F + lane];
-                        }
-                    }
-                    volsum += ws.vol[j];
-                }
-                if (qb == q0) self_slot = ws.slot[0][ws.la[0]];
+                for (int q = 0; q < NF; q++) f[q] = (lane < nrec) ? ((ipx_r & 256) ? -1.0 : 1.0) * ws.flx[lane][FR::O_F + q] : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int q = 0; q < NF; q++) f[q] += __shfl_xor_sync(0xffffffffu, f[q], o);
+#pragma unroll
+                for (int q = 0; q < NF; q++) if (lane == q) dsum += f[q];
             }
+            if (lane < NF) for (int j = 0; j < nj; j++) volsum += ws.vol[j];
         }
         __syncwarp();
         if (want_jac) {
