@@ -49,7 +49,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    static const int WPB = [] { const char* ev = getenv("NSB_ROWS_WPB"); const int v = ev ? atoi(ev) : 4; return (v >= 1 && v <= 4) ? v : 4; }();
+    static const int WPB = [] { const char* ev = getenv("NSB_ROWS_WPB"); const int v = ev ? atoi(ev) : 3; return (v >= 1 && v <= 3) ? v : 3; }();
     using WS = RowWS<E, EXACT>;
     const size_t tab_bytes = (sizeof(double) * NIP * NSH + sizeof(int32_t) * NSH * ET<E>::NINC + 15) & ~(size_t)15;
     const size_t per_warp = (sizeof(WS) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;

@@ -209,8 +209,72 @@ NSB_DEV bool upwind_uniform(int type, const double* __restrict__ xs, int tid, co
 // ------------------------------------------------------------------------------------------------
 // (A) flux kernel
 // ------------------------------------------------------------------------------------------------
+// FV1Geometry of SCVF `ip` (warp-uniform) from the thread's shared corner column; see ip_geometry (ns_fv1.cuh).
+// cen = element barycentre (hoisted). G is only computed when wantG.
+template <int E, int BS>
+NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, const double* cen, double* n, double* xip,
+                             double& ds, bool wantG, double (*G)[ET<E>::DIM])
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    const int f = tab::C_EDGE[E][ip][0], t = tab::C_EDGE[E][ip][1];
+    double c0[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) c0[d] = 0.5 * (NSB_COL(xs, f * DIM + d) + NSB_COL(xs, t * DIM + d));
+    if constexpr (DIM == 2) {
+        n[0] = cen[1] - c0[1]; n[1] = -(cen[0] - c0[0]);
+        xip[0] = 0.5 * (c0[0] + cen[0]); xip[1] = 0.5 * (c0[1] + cen[1]);
+        ds = 0.0;
+    } else {
+        const int fa = tab::C_FA[E][ip], fb = tab::C_FB[E][ip];
+        constexpr int NFC = (E == E_TET) ? 3 : 4;
+        double c1[3] = {0, 0, 0}, c3[3] = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < NFC; q++) {
+            const int ka = tab::C_SIDE[E][fa][q], kb = tab::C_SIDE[E][fb][q];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { c1[d] += NSB_COL(xs, ka * 3 + d); c3[d] += NSB_COL(xs, kb * 3 + d); }
+        }
+        double a[3], b[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            c1[d] *= (1.0 / NFC); c3[d] *= (1.0 / NFC);
+            a[d] = cen[d] - c0[d]; b[d] = c3[d] - c1[d];
+            xip[d] = 0.25 * (c0[d] + c1[d] + cen[d] + c3[d]);
+        }
+        cross3(n, a, b);
+#pragma unroll
+        for (int d = 0; d < 3; d++) n[d] *= 0.5;
+        ds = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    }
+    if (wantG) {
+        double JT[DIM][DIM], JI[DIM][DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; i++)
+#pragma unroll
+            for (int j = 0; j < DIM; j++) JT[i][j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NSH; k++)
+#pragma unroll
+            for (int j = 0; j < DIM; j++) {
+                const double xkj = NSB_COL(xs, k * DIM + j);
+#pragma unroll
+                for (int i = 0; i < DIM; i++) JT[i][j] += tab::C_DNIP[E][ip][k][i] * xkj;
+            }
+        inv_mat<DIM>(JT, JI);
+#pragma unroll
+        for (int k = 0; k < NSH; k++)
+#pragma unroll
+            for (int j = 0; j < DIM; j++) {
+                double s = 0;
+#pragma unroll
+                for (int i = 0; i < DIM; i++) s += JI[j][i] * tab::C_DNIP[E][ip][k][i];
+                G[k][j] = s;
+            }
+    }
+}
+
 template <int E, int STAB, bool EXACT, int BS>
-__global__ void __launch_bounds__(BS) fv1_flux_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
+__global__ void __launch_bounds__(BS, 3) fv1_flux_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
                                                       const double* __restrict__ u, const double* __restrict__ s0,
                                                       const double* __restrict__ s1, double* __restrict__ flux,
                                                       int* __restrict__ errflag)
@@ -247,35 +311,34 @@ __global__ void __launch_bounds__(BS) fv1_flux_kernel(KParams p, MeshDev m, cons
     const double nurho = p.visc * p.rho;
     const bool want_def = p.what & W_DEF_A, want_jac = p.what & W_JAC_A;
     bool ok = true;
+    double cen[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) s += NSB_COL(xs, k * DIM + d);
+        cen[d] = s * (1.0 / NSH);
+    }
     // COR diffusion length: element-wide statistics of the SCVF normals (diffusion_length.h:139-172)
     double cmn = 0.0, cav = 0.0, cmd = 0.0;
     if (STAB != STAB_NONE && p.diff_len == DIFF_COR) {
         cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
         for (int i = 0; i < NIP; i++) {
-            const double* h = geo + (e * NIP + i) * R::SZ;
-            double q = 0.0;
-#pragma unroll
-            for (int d = 0; d < DIM; d++) { const double t = __ldg(h + d); q += t * t; }
+            double nn_[DIM], xx_[DIM], dsi;
+            ip_geometry_col<E, BS>(xs, tid, i, cen, nn_, xx_, dsi, false, nullptr);
+            const double q = dotv<DIM>(nn_, nn_);
             if (q < cmn) cmn = q;
             cav += q;
-            if (DIM == 3) { const double t = __ldg(h + R::HEAD - 2); if (t < cmd) cmd = t; }
+            if (DIM == 3 && dsi < cmd) cmd = dsi;
         }
         cav /= NIP;
     }
 
     for (int ip = 0; ip < NIP; ip++) {
-        const double* g = geo + (e * NIP + ip) * R::SZ;
         double* fr = flux + (e * NIP + ip) * FR::SZ;
         const int from = tab::C_EDGE[E][ip][0], to = tab::C_EDGE[E][ip][1];
-        double n[DIM], xip[DIM], ds = 0.0;
-        {
-            double h[R::HEAD];
-#pragma unroll
-            for (int i = 0; i < R::HEAD; i += 2) { const double2 v = ldg2(g + i); h[i] = v.x; h[i + 1] = v.y; }
-#pragma unroll
-            for (int d = 0; d < DIM; d++) { n[d] = h[d]; xip[d] = h[DIM + d]; }
-            if (DIM == 3) ds = h[R::HEAD - 2];
-        }
+        double n[DIM], xip[DIM], ds = 0.0, G[NSH][DIM];
+        ip_geometry_col<E, BS>(xs, tid, ip, cen, n, xip, ds, want_def, G);
         double N[NSH];
 #pragma unroll
         for (int k = 0; k < NSH; k++) N[k] = tab::NIPSH[E][ip][k];
@@ -394,9 +457,9 @@ __global__ void __launch_bounds__(BS) fv1_flux_kernel(KParams p, MeshDev m, cons
             for (int k = 0; k < NSH; k++) sG[k] = 0.0;
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
-                double Gd[R::NSHP];
+                double Gd[NSH];
 #pragma unroll
-                for (int k = 0; k < R::NSHP; k += 2) { const double2 v = ldg2(g + R::HEAD + d * R::NSHP + k); Gd[k] = v.x; Gd[k + 1] = v.y; }
+                for (int k = 0; k < NSH; k++) Gd[k] = G[k][d];
                 double sp = 0.0, sv[DIM];
 #pragma unroll
                 for (int q = 0; q < DIM; q++) sv[q] = 0.0;
@@ -496,7 +559,9 @@ template <int E> struct RowCfg {
 };
 template <int E, bool EXACT> struct RowWS {
     using C = RowCfg<E>;
-    double geo[C::NREC][GeoRec<E>::SZ];
+    // staged geometry = [n, (pad)] (NH doubles, the first NH of the record) + G[d][k]
+    static constexpr int NH = (C::DIM + 1) & ~1, GS = NH + C::DIM * GeoRec<E>::NSHP;
+    double geo[C::NREC][GS];
     double flx[C::NREC][FluxRec<E, EXACT>::SZ];
     double vol[C::CH];
     int32_t ipx[C::NREC];           // ip | (256 if the node is the `to` corner of the SCVF)
@@ -511,7 +576,7 @@ NSB_DEV void cp_async16(void* smem_dst, const void* gsrc)
 NSB_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int E, int STAB, bool EXACT>
-__global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
+__global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
                                                           const double* __restrict__ flux, const double* __restrict__ u,
                                                           double beta, double* __restrict__ val, double* __restrict__ def)
 {
@@ -521,7 +586,8 @@ __global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, 
     using R = GeoRec<E>;
     using FR = FluxRec<E, EXACT>;
     using WS = RowWS<E, EXACT>;
-    constexpr int GV = R::SZ / 2, FV = FR::SZ / 2;               // 16-byte chunks per record
+    constexpr int NH = WS::NH, GS = WS::GS;
+    constexpr int GV = GS / 2, FV = FR::SZ / 2, HV = NH / 2;     // 16-byte chunks per staged record
     static_assert(GV <= 32 && FV <= 32, "record wider than a warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -575,7 +641,8 @@ __global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, 
             // ---- asynchronous staging: every 16-byte chunk of every incident record in flight at once ----
             for (int r = 0; r < nrec; r++) {
                 const int64_t gi = __shfl_sync(0xffffffffu, gi_r, r);
-                if (jac_a && lane < GV) cp_async16(&ws.geo[r][2 * lane], geo + gi * R::SZ + 2 * lane);
+                if (jac_a && lane < GV)       // chunks [0, HV) = normal, then the gradients (skipping xip / ds)
+                    cp_async16(&ws.geo[r][2 * lane], geo + gi * R::SZ + (lane < HV ? 2 * lane : R::HEAD - NH + 2 * lane));
                 if (lane < FV) cp_async16(&ws.flx[r][2 * lane], flux + gi * FR::SZ + 2 * lane);
             }
             // scatter slots + the node's SCV volume in the adjacent elements (plain loads, overlapped with the copies)
@@ -606,7 +673,7 @@ __global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, 
                             const double sg = (ipx & 256) ? -1.0 : 1.0;
                             double n[DIM], Gk[DIM];
 #pragma unroll
-                            for (int d = 0; d < DIM; d++) { n[d] = gr[d]; Gk[d] = gr[R::HEAD + d * R::NSHP + k]; }
+                            for (int d = 0; d < DIM; d++) { n[d] = gr[d]; Gk[d] = gr[NH + d * R::NSHP + k]; }
                             const double gn = dotv<DIM>(Gk, n);
                             const double inv = fl[FR::O_INV];
                             const double ncf = gr[cfv];
@@ -629,7 +696,7 @@ __global__ void __launch_bounds__(128, 4) fv1_rows_kernel(KParams p, MeshDev m, 
                                 double sG = 0.0;
 #pragma unroll
                                 for (int d = 0; d < DIM; d++) sG += fl[FR::O_STD + d] * Gk[d];
-                                cv += (gr[R::HEAD + cfv * R::NSHP + k] * fl[FR::O_SN] - sG * ncf) * inv * rho_f;
+                                cv += (gr[NH + cfv * R::NSHP + k] * fl[FR::O_SN] - sG * ncf) * inv * rho_f;
                             }
                             const double cpv = (STAB == STAB_NONE) ? 0.0 : -1.0 * gn * inv;
                             acc[DIM] += sg * (wv * cv + wp * cpv);
