@@ -32,8 +32,8 @@ template <> struct ET<E_HEX>  { static constexpr int DIM = 3, NSH = 8, NIP = 12,
 struct KParams {
     int upw_stab, upw_conv, stab, diff_len;
     int stokes, laplace, peclet, pac, time_dep, has_source;
-    int what, pad;
-    double exact_jac, visc, rho, inv_rho, dt, scale_a, scale_m;
+    int what, defect_upwind;
+    double exact_jac, visc, rho, inv_rho, dt, scale_a, scale_m, grad_div;
     double src[3];
 };
 

@@ -1,24 +1,376 @@
-// ns_fvcr.cuh -- FVCR (Crouzeix-Raviart) element assembly kernels.
+// ns_fvcr.cuh -- FVCR (Crouzeix-Raviart velocity on element sides, element-constant pressure) element
+// assembly for sm_100a: NavierStokesFVCR::add_jac_A_elem / add_def_A_elem / add_jac_M_elem / add_def_M_elem /
+// add_rhs_elem, fvcr/navier_stokes_fvcr.cpp:244-759, on simplices (regular grids; the hanging-node HCR
+// branches :492-503, :657-668 are out of scope).  CRFVGeometry conventions: SURVEY.md App. B-3.
+//
+// Mapping: 2 (tet, L = 13) or 4 (tri, L = 7) elements per warp. Per-ip phase: lane = SCVF. Column phase: lane =
+// one column (side s, component d2 | pressure) of the local Jacobian, accumulated in registers with
+// compile-time from/to rows; scatter by coloured read-modify-write or red.global.add.f64.
 #pragma once
-#include "ns_fv1.cuh"
+#include "ns_kernels.cuh"
+
 namespace nsb {
+
 struct FvcrDev {
     int64_t n_elem = 0, n_node = 0, n_side = 0, nnz = 0, n_dof = 0, prow0 = 0;
     const int32_t *conn = nullptr, *esides = nullptr, *color_order = nullptr;
     const double* coords = nullptr;
-    int64_t *srow = nullptr, *sadj_ptr = nullptr;
-    int32_t *scnt = nullptr, *psort = nullptr;
-    uint8_t *emap = nullptr, *pslot = nullptr;
+    int64_t *srow = nullptr, *sadj_ptr = nullptr;   // first value index of row (side,0); side -> adjacent elements
+    int32_t *scnt = nullptr, *psort = nullptr;      // neighbour sides per side; rank of local side among sorted sides
+    uint8_t *emap = nullptr, *pslot = nullptr;      // slot of side k in the row of side a; slot of elem among a's elements
     int n_colors = 0; const int64_t* color_ptr = nullptr;
 };
-inline void fvcr_free(FvcrDev& f)
+
+template <int E> struct CRT;
+template <> struct CRT<E_TRI> { static constexpr int DIM = 2, NCO = 3, NS = 3, NIP = 3; };
+template <> struct CRT<E_TET> { static constexpr int DIM = 3, NCO = 4, NS = 4, NIP = 6; };
+
+// SCVF -> (from side, to side): the two sides sharing the (dim-2)-object, lower index = from
+template <int E> __host__ __device__ constexpr int cr_ft(int ip, int j)
 {
-    cudaFree(f.srow); cudaFree(f.sadj_ptr); cudaFree(f.scnt); cudaFree(f.psort); cudaFree(f.emap); cudaFree(f.pslot);
-    f = FvcrDev{};
+    if (E == E_TRI) { constexpr int T[3][2] = {{0, 2}, {0, 1}, {1, 2}}; return T[ip][j]; }
+    constexpr int T[6][2] = {{0, 3}, {0, 1}, {0, 2}, {2, 3}, {1, 3}, {1, 2}};
+    return T[ip][j];
 }
-inline int fvcr_assemble(const FvcrDev& f, const KParams& k, int elem, int mode, const double* u, double beta, double* val,
-                         double* def, cudaStream_t st, int sm_count, int* d_err, int64_t* launches)
+
+template <int E> struct CRRec {
+    static constexpr int DIM = CRT<E>::DIM, NS = CRT<E>::NS;
+    double n[DIM];
+    double F[DIM];              // momentum defect fluxes of this ip
+    double A[NS][DIM];          // B(d1,d2;s) = A[s][d1] n[d2] + delta D[s] - gd[s][d2] n[d1]
+    double D[NS];
+    double gd[NS][DIM];
+};
+
+template <int E> struct CRWS {
+    static constexpr int DIM = CRT<E>::DIM, NCO = CRT<E>::NCO, NS = CRT<E>::NS, NIP = CRT<E>::NIP, L = NS * DIM + 1;
+    double x[NCO * DIM];
+    double u[L];
+    double G[NS][DIM];          // global CR shape gradients (constant on a simplex)
+    double scvn[NS][DIM], scvx[NS][DIM], vol;
+    double bary[DIM];
+    int64_t rowbase[NS];
+    int32_t rowlen[NS], scnt[NS], side[NS];
+    CRRec<E> rec[NIP];
+};
+
+// Crouzeix-Raviart shapes 1 - dim * lambda_opposite(side) at a local point
+template <int E> NSB_DEV void cr_shapes(const double* xi, double* N)
 {
-    return -5;
+    constexpr int DIM = CRT<E>::DIM, NS = CRT<E>::NS;
+    double lam[CRT<E>::NCO];
+    lagrange<E>(xi, lam);
+#pragma unroll
+    for (int s = 0; s < NS; s++) N[s] = 1.0 - DIM * lam[tab::CR_OPP[E][s]];
 }
+
+// CR upwind shapes of one ip: upwind.cpp:82-104 (No), :174-213 (Full), :432-499 (Skewed), :577-636 (LPS)
+template <int E> NSB_DEV bool cr_upwind_ip(int type, const CRWS<E>& ws, const double* n, const double* xip, const double* N,
+                                           int from, int to, const double* vel, double* up)
+{
+    constexpr int DIM = CRT<E>::DIM, NS = CRT<E>::NS;
+    if (type == UPW_NO) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) up[s] = N[s];
+        return true;
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) up[s] = 0.0;
+    if (type == UPW_FULL) {
+        const double flux = dotv<DIM>(n, vel);
+        const int sd = flux > 0.0 ? from : to;
+#pragma unroll
+        for (int s = 0; s < NS; s++) up[s] = (s == sd) ? 1.0 : 0.0;
+        return true;
+    }
+    const double nrm = sqrt(dotv<DIM>(vel, vel));
+    if (type == UPW_SKEWED ? (nrm < 1e-14) : (nrm == 0.0)) return true;
+    int side = 0; double gc[DIM], lc[DIM], Nc[NS];
+    if (!side_ray_cut<E>(ws.x, xip, vel, side, gc, lc)) return false;
+    cr_shapes<E>(lc, Nc);
+    if (type == UPW_SKEWED) {
+        double mx = -1000.0; int best = 0;
+#pragma unroll
+        for (int s = 0; s < NS; s++) if (Nc[s] > mx) { mx = Nc[s]; best = s; }
+#pragma unroll
+        for (int s = 0; s < NS; s++) up[s] = (s == best) ? 1.0 : 0.0;
+    } else {
+#pragma unroll
+        for (int s = 0; s < NS; s++) up[s] = Nc[s];
+    }
+    return true;
 }
+
+template <int E, int SC>
+__global__ void __launch_bounds__(128) fvcr_elem_kernel(KParams p, FvcrDev m, const int32_t* __restrict__ elem_list,
+                                                        int64_t n_list, const double* __restrict__ u,
+                                                        double* __restrict__ val, double* __restrict__ def,
+                                                        int* __restrict__ errflag)
+{
+    constexpr int DIM = CRT<E>::DIM, NCO = CRT<E>::NCO, NS = CRT<E>::NS, NIP = CRT<E>::NIP, L = NS * DIM + 1, PI = NS * DIM;
+    constexpr int EPW = 32 / L;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CRWS<E>* wsall = reinterpret_cast<CRWS<E>*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / L, col = lane - sub * L;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t li = gw * EPW + sub;
+    const bool active = sub < EPW && li < n_list;
+    CRWS<E>& ws = wsall[warp * EPW + (sub < EPW ? sub : 0)];
+    const int64_t e = active ? (elem_list ? (int64_t)elem_list[li] : li) : 0;
+    const int64_t pbase = m.n_side * DIM;
+    const double nurho = p.visc * p.rho;
+
+    // ---- stage ----
+    if (active) {
+        if (col < NS) {
+            const int sd = m.esides[e * NS + col];
+            ws.side[col] = sd;
+            const int nadj = (int)(m.sadj_ptr[sd + 1] - m.sadj_ptr[sd]);
+            ws.rowbase[col] = m.srow[sd]; ws.scnt[col] = m.scnt[sd]; ws.rowlen[col] = m.scnt[sd] * DIM + nadj;
+        }
+        for (int i = col; i < NCO * DIM; i += L) {
+            const int kk = i / DIM, dd = i - kk * DIM;
+            ws.x[i] = m.coords[(int64_t)m.conn[e * NCO + kk] * DIM + dd];
+        }
+    }
+    __syncwarp();
+    if (active) {
+        // local dofs: (side s, comp d) at s*DIM+d, pressure last
+        if (col < PI) { const int s = col / DIM, d = col - s * DIM; ws.u[col] = u[(int64_t)ws.side[s] * DIM + d]; }
+        else ws.u[PI] = u[pbase + e];
+        // ---- CRFVGeometry (App. B-3): lane 0 of the element does the (small) element-level part ----
+        if (col == 0) {
+            double JT[DIM][DIM], JI[DIM][DIM], dl[NCO][DIM], xi0[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) xi0[d] = 0.0;
+            lagrange_grad<E>(xi0, dl);
+#pragma unroll
+            for (int i = 0; i < DIM; i++)
+#pragma unroll
+                for (int j = 0; j < DIM; j++) { double s = 0; for (int k = 0; k < NCO; k++) s += dl[k][i] * ws.x[k * DIM + j]; JT[i][j] = s; }
+            const double det = inv_mat<DIM>(JT, JI);
+            const double elemvol = fabs(det) / (DIM == 2 ? 2.0 : 6.0);
+            ws.vol = elemvol / NS;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { double s = 0; for (int k = 0; k < NCO; k++) s += ws.x[k * DIM + d]; ws.bary[d] = s / NCO; }
+            for (int s = 0; s < NS; s++) {
+                const int o = tab::CR_OPP[E][s];
+#pragma unroll
+                for (int j = 0; j < DIM; j++) { double g = 0; for (int i = 0; i < DIM; i++) g += JI[j][i] * dl[o][i]; ws.G[s][j] = -1.0 * DIM * g; }
+                double xb[DIM], nn[DIM];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) xb[d] = 0.0;
+                for (int q = 0; q < DIM; q++) for (int d = 0; d < DIM; d++) xb[d] += ws.x[tab::SIDE[E][s][q] * DIM + d];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) xb[d] /= DIM;
+                if constexpr (DIM == 2) {
+                    const double* a = ws.x + tab::SIDE[E][s][0] * 2; const double* b = ws.x + tab::SIDE[E][s][1] * 2;
+                    nn[0] = b[1] - a[1]; nn[1] = -(b[0] - a[0]);
+                } else {
+                    double e1[3], e2[3], c[3];
+                    for (int d = 0; d < 3; d++) { e1[d] = ws.x[tab::SIDE[E][s][1] * 3 + d] - ws.x[tab::SIDE[E][s][0] * 3 + d];
+                                                  e2[d] = ws.x[tab::SIDE[E][s][2] * 3 + d] - ws.x[tab::SIDE[E][s][0] * 3 + d]; }
+                    cross3(c, e1, e2);
+                    for (int d = 0; d < 3; d++) nn[d] = 0.5 * c[d];
+                }
+                double outw = 0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) outw += nn[d] * (xb[d] - ws.bary[d]);
+                const double sg = outw < 0 ? -1.0 : 1.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) { ws.scvn[s][d] = sg * nn[d]; ws.scvx[s][d] = xb[d]; }
+            }
+        }
+    }
+    __syncwarp();
+    // ---- per-ip phase: lane = SCVF ----
+    if (active && col < NIP && (p.what & (W_JAC_A | W_DEF_A))) {
+        const int ip = col;
+        const int from = tab::CR_FROM[E][ip], to = tab::CR_TO[E][ip];
+        CRRec<E>& r = ws.rec[ip];
+        // SCVF spanned by the (dim-2)-object and the barycentre; normal oriented from -> to
+        double n[DIM], xip[DIM], lip[DIM], N[NS];
+        {
+            double lb[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { double s = 0; for (int k = 0; k < NCO; k++) s += tab::CORNER[E][k][d]; lb[d] = s / NCO; }
+            if constexpr (DIM == 2) {
+                const double* a = ws.x + ip * 2;
+                n[0] = ws.bary[1] - a[1]; n[1] = -(ws.bary[0] - a[0]);
+                for (int d = 0; d < 2; d++) { xip[d] = 0.5 * (a[d] + ws.bary[d]); lip[d] = 0.5 * (tab::CORNER[E][ip][d] + lb[d]); }
+            } else {
+                const int c0 = tab::EDGE[E][ip][0], c1 = tab::EDGE[E][ip][1];
+                double e1[3], e2[3], c[3];
+                for (int d = 0; d < 3; d++) { e1[d] = ws.x[c1 * 3 + d] - ws.x[c0 * 3 + d]; e2[d] = ws.bary[d] - ws.x[c0 * 3 + d]; }
+                cross3(c, e1, e2);
+                for (int d = 0; d < 3; d++) {
+                    n[d] = 0.5 * c[d];
+                    xip[d] = (ws.x[c0 * 3 + d] + ws.x[c1 * 3 + d] + ws.bary[d]) / 3.0;
+                    lip[d] = (tab::CORNER[E][c0][d] + tab::CORNER[E][c1][d] + lb[d]) / 3.0;
+                }
+            }
+            double ft = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) ft += n[d] * (ws.scvx[to][d] - ws.scvx[from][d]);
+            if (ft < 0) {
+#pragma unroll
+                for (int d = 0; d < DIM; d++) n[d] = -n[d];
+            }
+            cr_shapes<E>(lip, N);
+        }
+        double std[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) { double s = 0; for (int k = 0; k < NS; k++) s += ws.u[k * DIM + d] * N[k]; std[d] = s; }
+        const double prod = dotv<DIM>(std, n) * p.rho;
+        // Peclet weight (fvcr/navier_stokes_fvcr.cpp:244-265)
+        double w = 1.0;
+        if (!p.stokes && p.peclet) {
+            double dd = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { const double t = ws.scvx[to][d] - ws.scvx[from][d]; dd += t * t; }
+            const double Pe = dotv<DIM>(std, n) / dotv<DIM>(n, n) * sqrt(dd) / p.visc;
+            const double Pe2 = Pe * Pe;
+            w = Pe2 / (5.0 + Pe2);
+        }
+        double up[NS], U[DIM];
+        bool ok = true;
+        if (!p.stokes) {
+            ok = cr_upwind_ip<E>(p.upw_conv, ws, n, xip, N, from, to, std, up);
+            if (!ok) atomicExch(errflag, 1);
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { double s = 0; for (int k = 0; k < NS; k++) s += up[k] * ws.u[k * DIM + d]; U[d] = s; }
+            if (p.peclet) {
+#pragma unroll
+                for (int d = 0; d < DIM; d++) U[d] = w * U[d] + (1.0 - w) * std[d];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NS; k++) up[k] = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) U[d] = 0.0;
+        }
+        if (p.what & W_JAC_A) {                                   // :299-476
+#pragma unroll
+            for (int d = 0; d < DIM; d++) r.n[d] = n[d];
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+                double D = -1.0 * nurho * dotv<DIM>(ws.G[k], n);
+                if (!p.stokes) { D += up[k] * prod * w; if (p.peclet) D += prod * (1.0 - w) * N[k]; }
+                r.D[k] = D;
+#pragma unroll
+                for (int d1 = 0; d1 < DIM; d1++) {
+                    double A = p.laplace ? 0.0 : -1.0 * nurho * ws.G[k][d1];
+                    if (!p.stokes && p.exact_jac != 0.0) {
+                        A += p.exact_jac * p.rho * std[d1] * N[k];                          // :425-426 (StdVel, not the upwind velocity)
+                        if (p.peclet) A += U[d1] * (1.0 - w) * N[k] * p.rho * p.exact_jac;  // :451-454
+                    }
+                    r.A[k][d1] = A;
+                    r.gd[k][d1] = p.grad_div > 0 ? p.grad_div * ws.G[k][d1] : 0.0;          // :341-348
+                }
+            }
+        }
+        if (p.what & W_DEF_A) {                                   // :538-641
+            double gv[DIM][DIM];
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++)
+#pragma unroll
+                for (int d2 = 0; d2 < DIM; d2++) { double s = 0; for (int k = 0; k < NS; k++) s += ws.G[k][d2] * ws.u[k * DIM + d1]; gv[d1][d2] = s; }
+            double divu = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) divu += gv[d][d];
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++) {
+                double df = 0;
+#pragma unroll
+                for (int d2 = 0; d2 < DIM; d2++) df += gv[d1][d2] * n[d2];
+                if (!p.laplace) {
+#pragma unroll
+                    for (int d2 = 0; d2 < DIM; d2++) df += gv[d2][d1] * n[d2];
+                }
+                double f = df * (-1.0) * nurho;
+                if (p.grad_div > 0) f -= p.grad_div * divu * n[d1];                          // :588-596
+                if (!p.stokes) f += (p.defect_upwind ? U[d1] : std[d1]) * prod;              // :602-630
+                f += ws.u[PI] * n[d1];
+                r.F[d1] = f;
+            }
+        }
+    }
+    __syncwarp();
+    if (!active) return;
+    // ---- column phase ----
+    if (p.what & (W_JAC_A | W_JAC_M)) {
+        double acc[L];
+#pragma unroll
+        for (int i = 0; i < L; i++) acc[i] = 0.0;
+        const int s = col < PI ? col / DIM : 0, d2 = col < PI ? col - s * DIM : 0;
+        if (p.what & W_JAC_A) {
+            static_for<NIP>([&](auto ipc) {
+                constexpr int ip = decltype(ipc)::value;
+                constexpr int f = cr_ft<E>(ip, 0), t = cr_ft<E>(ip, 1);
+                const CRRec<E>& r = ws.rec[ip];
+#pragma unroll
+                for (int d1 = 0; d1 < DIM; d1++) {
+                    double v;
+                    if (col < PI) { v = r.A[s][d1] * r.n[d2] - r.gd[s][d2] * r.n[d1]; if (d1 == d2) v += r.D[s]; }
+                    else v = r.n[d1];                                                  // :470-475
+                    acc[f * DIM + d1] += v; acc[t * DIM + d1] -= v;
+                }
+            });
+            if (col < PI) acc[PI] = ws.scvn[s][d2];                                     // :483-489
+#pragma unroll
+            for (int i = 0; i < L; i++) acc[i] *= p.scale_a;
+        }
+        if ((p.what & W_JAC_M) && col < PI) {                                           // :672-699
+#pragma unroll
+            for (int i = 0; i < PI; i++) if (i == col) acc[i] += p.scale_m * ws.vol * p.rho;
+        }
+        // scatter: velocity rows (side a, d1), then the pressure row of the element
+        const int nsl = col < PI ? s : 0;
+#pragma unroll
+        for (int a = 0; a < NS; a++) {
+            int64_t off;
+            if (col < PI) off = (int64_t)m.emap[e * (NS * NS) + a * NS + nsl] * DIM + d2;
+            else off = (int64_t)ws.scnt[a] * DIM + m.pslot[e * NS + a];
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++) {
+                double* q = val + ws.rowbase[a] + (int64_t)d1 * ws.rowlen[a] + off;
+                if (SC == SC_ATOMIC) atomicAdd(q, acc[a * DIM + d1]); else *q += acc[a * DIM + d1];
+            }
+        }
+        {
+            const int64_t off = col < PI ? (int64_t)m.psort[e * NS + nsl] * DIM + d2 : (int64_t)NS * DIM;
+            double* q = val + m.prow0 + e * (int64_t)L + off;
+            if (SC == SC_ATOMIC) atomicAdd(q, acc[PI]); else *q += acc[PI];
+        }
+    }
+    if (p.what & (W_DEF_A | W_DEF_M | W_RHS)) {
+        double d = 0.0;
+        if (col < PI) {
+            const int s = col / DIM, d1 = col - s * DIM;
+            if (p.what & W_DEF_A) {
+#pragma unroll
+                for (int ip = 0; ip < NIP; ip++) {
+                    if (tab::CR_FROM[E][ip] == s) d += ws.rec[ip].F[d1];
+                    if (tab::CR_TO[E][ip] == s) d -= ws.rec[ip].F[d1];
+                }
+            }
+            if ((p.what & W_RHS) && p.has_source) d -= p.src[d1] * ws.vol;               // no density factor, :757
+            d *= p.scale_a;
+            if (p.what & W_DEF_M) d += p.scale_m * ws.u[col] * ws.vol * p.rho;           // :702-729
+            double* q = def + (int64_t)ws.side[s] * DIM + d1;
+            if (SC == SC_ATOMIC) atomicAdd(q, d); else *q += d;
+        } else {
+            if (p.what & W_DEF_A) {                                                      // :648-654
+                for (int sd = 0; sd < NS; sd++)
+#pragma unroll
+                    for (int d1 = 0; d1 < DIM; d1++) d += ws.scvn[sd][d1] * ws.u[sd * DIM + d1];
+            }
+            d *= p.scale_a;
+            double* q = def + pbase + e;
+            if (SC == SC_ATOMIC) atomicAdd(q, d); else *q += d;
+        }
+    }
+}
+
+}  // namespace nsb

@@ -21,6 +21,7 @@ struct MeshDev {
     const int64_t* adj_ptr;     // [n_node+1] node -> adjacent (element, local corner)
     const int32_t* adj;         // elem*NSH + local corner
     int32_t max_cnt;            // longest block row
+    const int32_t* node_order;  // Z-curve traversal order of the nodes (rows kernel), may be null
 };
 
 enum { SC_COLORED = 1, SC_ATOMIC = 2, SC_LOCAL = 3 };

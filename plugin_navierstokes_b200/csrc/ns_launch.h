@@ -24,6 +24,11 @@ struct LaunchInfo { int64_t launches = 0; };
     size_t flux_record_doubles_##E();
 NSB_DECL(0) NSB_DECL(1) NSB_DECL(2) NSB_DECL(3)
 #undef NSB_DECL
+struct FvcrDev;
+cudaError_t launch_fvcr_0(int sc, const KParams& k, const FvcrDev& m, const int32_t* list, int64_t n_list, const double* u,
+                          double* val, double* def, int* d_err, cudaStream_t st);
+cudaError_t launch_fvcr_2(int sc, const KParams& k, const FvcrDev& m, const int32_t* list, int64_t n_list, const double* u,
+                          double* val, double* def, int* d_err, cudaStream_t st);
 #define NSB_CAT2(a, b) a##b
 #define NSB_CAT(a, b) NSB_CAT2(a, b)
 }

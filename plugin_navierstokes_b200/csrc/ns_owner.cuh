@@ -616,7 +616,8 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
     const double nurho_d = -1.0 * p.visc * p.rho;
     const double rho_f = FLOW ? p.rho : 0.0;
 
-    for (int64_t a = (int64_t)blockIdx.x * nwarp + warp; a < m.n_node; a += (int64_t)gridDim.x * nwarp) {
+    for (int64_t ai = (int64_t)blockIdx.x * nwarp + warp; ai < m.n_node; ai += (int64_t)gridDim.x * nwarp) {
+        const int64_t a = m.node_order ? (int64_t)m.node_order[ai] : ai;
         const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1];
         const int64_t b0 = m.brow[a];
         const int cnt = (int)(m.brow[a + 1] - b0);

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <functional>
 #include <string>
 #include <thread>
@@ -49,7 +50,7 @@ struct nsb_ctx {
     std::vector<int32_t> h_bcol;          // block columns (FV1) / scalar colind (FVCR)
     std::vector<int64_t> h_color_ptr;
     // device
-    int32_t *d_conn = nullptr, *d_adj = nullptr, *d_color_order = nullptr, *d_esides = nullptr;
+    int32_t *d_conn = nullptr, *d_adj = nullptr, *d_color_order = nullptr, *d_esides = nullptr, *d_node_order = nullptr;
     double *d_coords = nullptr, *d_scvvol = nullptr, *d_geo = nullptr, *d_flux = nullptr;
     int64_t *d_brow = nullptr, *d_adj_ptr = nullptr;
     uint8_t *d_emap = nullptr;
@@ -131,14 +132,20 @@ extern "C" int nsb_create(int device, nsb_ctx** out)
     return NSB_OK;
 }
 
+static void fvcr_free(FvcrDev& f)
+{
+    cudaFree(f.srow); cudaFree(f.sadj_ptr); cudaFree(f.scnt); cudaFree(f.psort); cudaFree(f.emap); cudaFree(f.pslot);
+    f = FvcrDev{};
+}
+
 static void free_mesh(nsb_ctx* c)
 {
-    cudaFree(c->d_conn); cudaFree(c->d_adj); cudaFree(c->d_color_order); cudaFree(c->d_esides); cudaFree(c->d_coords);
+    cudaFree(c->d_conn); cudaFree(c->d_adj); cudaFree(c->d_color_order); cudaFree(c->d_esides); cudaFree(c->d_node_order); cudaFree(c->d_coords);
     cudaFree(c->d_scvvol); cudaFree(c->d_geo); cudaFree(c->d_flux); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
     cudaFree(c->d_u); cudaFree(c->d_s0); cudaFree(c->d_s1); cudaFree(c->d_val); cudaFree(c->d_def);
     cudaFree(c->d_jloc); cudaFree(c->d_dloc);
     fvcr_free(c->fvcr);
-    c->d_conn = c->d_adj = c->d_color_order = c->d_esides = nullptr; c->d_coords = c->d_scvvol = c->d_geo = c->d_flux = nullptr;
+    c->d_conn = c->d_adj = c->d_color_order = c->d_esides = c->d_node_order = nullptr; c->d_coords = c->d_scvvol = c->d_geo = c->d_flux = nullptr;
     c->d_brow = c->d_adj_ptr = nullptr; c->d_emap = nullptr;
     c->d_u = c->d_s0 = c->d_s1 = c->d_val = c->d_def = c->d_jloc = c->d_dloc = nullptr;
     c->mesh_ready = false;
@@ -257,6 +264,32 @@ static int color_elements(int64_t n_elem, int64_t n_ent, int per, const int32_t*
     return ncol;
 }
 
+// Z-curve (Morton) order of the grid nodes: the rows kernel walks the nodes in this order so that the SCVF records
+// shared by neighbouring nodes (in every coordinate direction) are re-read from L2 instead of HBM.
+static void morton_order(int64_t n, int dim, const double* coords, std::vector<int32_t>& order)
+{
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = 0; i < n; i++) for (int d = 0; d < dim; d++) { lo[d] = std::min(lo[d], coords[i * dim + d]); hi[d] = std::max(hi[d], coords[i * dim + d]); }
+    const int bits = dim == 3 ? 20 : 30;
+    double sc[3];
+    for (int d = 0; d < dim; d++) sc[d] = hi[d] > lo[d] ? ((double)((1u << bits) - 1)) / (hi[d] - lo[d]) : 0.0;
+    // one common scale keeps the curve isotropic on anisotropic boxes
+    double smin = 1e300; for (int d = 0; d < dim; d++) if (sc[d] > 0) smin = std::min(smin, sc[d]);
+    std::vector<std::pair<uint64_t, int32_t>> key(n);
+    parallel_for(n, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            uint64_t code = 0;
+            uint32_t q[3] = {0, 0, 0};
+            for (int d = 0; d < dim; d++) q[d] = (uint32_t)((coords[i * dim + d] - lo[d]) * smin);
+            for (int bit = 0; bit < bits; bit++) for (int d = 0; d < dim; d++) code |= (uint64_t)((q[d] >> bit) & 1u) << (bit * dim + d);
+            key[i] = {code, (int32_t)i};
+        }
+    });
+    std::sort(key.begin(), key.end());
+    order.resize(n);
+    for (int64_t i = 0; i < n; i++) order[i] = key[i].second;
+}
+
 template <class T> static cudaError_t upload(T** dptr, const T* h, size_t n)
 {
     cudaError_t e = cudaMalloc((void**)dptr, std::max<size_t>(n, 1) * sizeof(T));
@@ -299,6 +332,7 @@ extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_n
     CUDA_TRY(c, upload(&c->d_adj, g.adj.data(), g.adj.size()));
     CUDA_TRY(c, upload(&c->d_emap, emap.data(), emap.size()));
     CUDA_TRY(c, upload(&c->d_color_order, order.data(), order.size()));
+    { std::vector<int32_t> zo; morton_order(n_node, dim, coords, zo); CUDA_TRY(c, upload(&c->d_node_order, zo.data(), zo.size())); }
     CUDA_TRY(c, cudaMalloc(&c->d_scvvol, (size_t)n_elem * nsh * sizeof(double)));
     CUDA_TRY(c, launch_scvvol(c));
     {   // precomputed SCVF geometry table (normals, ips, global shape gradients) for the owner-computes kernel
@@ -375,7 +409,8 @@ static int resolve_params(nsb_ctx* c, KParams& k, int what, const nsb_time_serie
         if (!p.stokes && p.conv_upwind == NSB_UPWIND_POSITIVE)
             return set_err(c, NSB_ERR_SETUP, "No update function registered for Geometry (upwind has no Crouzeix-Raviart overload)");
         k.upw_conv = p.conv_upwind; k.upw_stab = p.conv_upwind;
-        k.pac = p.defect_upwind ? 1 : 0;          // FVCR reuses the slot for m_bDefectUpwind
+        k.defect_upwind = p.defect_upwind ? 1 : 0;
+        k.grad_div = p.grad_div;
     }
     if (!p.kin_visc_set) return set_err(c, NSB_ERR_SETUP, "NavierStokes::prep_elem_loop: Kinematic Viscosity has not been set, but is required.");
     if (!p.density_set) return set_err(c, NSB_ERR_SETUP, "NavierStokes::prep_elem_loop: Density has not been set, but is required.");
@@ -390,8 +425,6 @@ static int resolve_params(nsb_ctx* c, KParams& k, int what, const nsb_time_serie
         if (!ts->sol1) return set_err(c, NSB_ERR_SETUP, "NavierStokes::add_jac_A_elem:  Stabilization needs exactly two time points.");
         k.dt = ts->dt;
     }
-    // exact_jac is "grad_div" for FVCR in a second slot
-    if (c->disc == NSB_DISC_FVCR) k.dt = p.grad_div;
     return NSB_OK;
 }
 
@@ -411,6 +444,7 @@ static MeshDev mesh_view(const nsb_ctx* c)
     MeshDev m;
     m.n_elem = c->n_elem; m.n_node = c->n_node; m.conn = c->d_conn; m.coords = c->d_coords; m.scvvol = c->d_scvvol;
     m.brow = c->d_brow; m.emap = c->d_emap; m.adj_ptr = c->d_adj_ptr; m.adj = c->d_adj; m.max_cnt = c->max_cnt;
+    m.node_order = getenv("NSB_NO_ZORDER") ? nullptr : c->d_node_order;
     return m;
 }
 
@@ -484,6 +518,32 @@ static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u,
     return set_err(c, NSB_ERR_INVALID, "unknown scatter mode %d", mode);
 }
 
+// FVCR: element kernel with coloured (deterministic) or atomic scatter; the owner-computes path is FV1-only
+static int assemble_fvcr(nsb_ctx* c, const KParams& k, int mode, const double* u, double beta, double* val, double* def)
+{
+    const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
+    if (mode == NSB_SCATTER_GATHER) mode = NSB_SCATTER_COLORED;
+    if (jac) {
+        if (beta == 0.0) CUDA_TRY(c, cudaMemsetAsync(val, 0, sizeof(double) * c->nnz, c->stream));
+        else if (beta != 1.0) { scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->nnz, beta, val); c->launches++; }
+    }
+    if (dfc) {
+        if (beta == 0.0) CUDA_TRY(c, cudaMemsetAsync(def, 0, sizeof(double) * c->n_dof, c->stream));
+        else if (beta != 1.0) { scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->n_dof, beta, def); c->launches++; }
+    }
+    auto go = [&](int sc, const int32_t* list, int64_t n) -> cudaError_t {
+        c->launches++;
+        return c->elem == NSB_TRI ? launch_fvcr_0(sc, k, c->fvcr, list, n, u, val, def, c->d_err, c->stream)
+                                  : launch_fvcr_2(sc, k, c->fvcr, list, n, u, val, def, c->d_err, c->stream);
+    };
+    if (mode == NSB_SCATTER_ATOMIC) { CUDA_TRY(c, go(SC_ATOMIC, nullptr, c->n_elem)); return NSB_OK; }
+    for (int col = 0; col < c->n_colors; col++) {
+        const int64_t lo = c->h_color_ptr[col], hi = c->h_color_ptr[col + 1];
+        if (hi > lo) CUDA_TRY(c, go(SC_COLORED, c->d_color_order + lo, hi - lo));
+    }
+    return NSB_OK;
+}
+
 static int check_device_error(nsb_ctx* c)
 {
     int flag = 0;
@@ -533,9 +593,8 @@ extern "C" int nsb_assemble(nsb_ctx* c, int what, int mode, const double* u, con
         if (dfc) { if ((rc = ensure(c, &c->d_def, c->n_dof))) return rc; dd = c->d_def;
                    if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(dd, defect, nb, cudaMemcpyHostToDevice, c->stream)); }
     }
-    if (c->disc == NSB_DISC_FVCR) rc = fvcr_assemble(c->fvcr, k, c->elem, mode, du, beta, dv, dd, c->stream, c->sm_count, c->d_err, &c->launches);
+    if (c->disc == NSB_DISC_FVCR) rc = assemble_fvcr(c, k, mode, du, beta, dv, dd);
     else rc = assemble_fv1(c, k, mode, du, ds0, ds1, beta, dv, dd);
-    if (rc > 0) return set_err(c, NSB_ERR_CUDA, "CUDA launch failure in FVCR path: %s", cudaGetErrorString((cudaError_t)rc));
     if (rc) return rc;
     if (location == NSB_HOST) {
         if (jac) CUDA_TRY(c, cudaMemcpyAsync(values, dv, sizeof(double) * c->nnz, cudaMemcpyDeviceToHost, c->stream));
@@ -690,7 +749,7 @@ extern "C" int nsb_upload_mesh_fvcr(nsb_ctx* c, int elem, int64_t n_elem, int64_
     FvcrDev& f = c->fvcr;
     f.n_elem = n_elem; f.n_node = n_node; f.n_side = n_side; f.nnz = c->nnz; f.n_dof = c->n_dof;
     f.conn = c->d_conn; f.coords = c->d_coords; f.esides = c->d_esides; f.color_order = c->d_color_order;
-    f.n_colors = c->n_colors; f.color_ptr = c->h_color_ptr.data();
+    f.n_colors = c->n_colors; f.color_ptr = nullptr;
     CUDA_TRY(c, upload(&f.srow, srow.data(), srow.size()));
     CUDA_TRY(c, upload(&f.scnt, scnt.data(), scnt.size()));
     CUDA_TRY(c, upload(&f.emap, emap.data(), emap.size()));
