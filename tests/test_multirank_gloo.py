@@ -1,0 +1,138 @@
+"""world_size-2 (and 4) CPU tests of the multi-GPU host logic over gloo: partition, interface lists, and the
+additive -> owner summation of defect entries and matrix rows. The per-rank assembly uses the CPU oracle here
+(no GPU in this container); the exchange code is the same one bench.py drives over NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from plugin_navierstokes_b200 import meshgen, partition
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, elem, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as ora
+        E = ora.ELEM[elem]
+        coords, conn = meshgen.make_mesh(elem, n, jitter=0.2, seed=1)
+        dim = coords.shape[1]
+        nf = dim + 1
+        u = meshgen.random_state(coords.shape[0], nf, seed=2)
+        part = partition.rcb_partition(coords[conn].mean(axis=1), world)
+        lconn, lcoords, l2g = partition.local_mesh(conn, coords, part, rank)
+        p = ora.make_params(elem=elem, upwind="lps", stab="flow", kin_visc=0.05, exact_jac=1.0)
+        rowptr, colind = ora.fv1_csr(E, lconn, lcoords.shape[0])
+        vals, dfc = ora.assemble(p, lconn, lcoords, u[l2g], rowptr, colind, ora.JAC_A | ora.DEF_A)
+        add_vals, add_dfc = vals.copy(), dfc.copy()
+        ex = partition.InterfaceExchange(None, dict(l2g=l2g, boundary=None), device=None, nf=nf, csr=(rowptr, colind))
+        tv, td = torch.from_numpy(vals), torch.from_numpy(dfc)
+        ex.sum_to_owner(tv, td)
+        q.put((rank, l2g, rowptr, colind, add_vals, add_dfc, tv.numpy().copy(), td.numpy().copy(), ex.owner.copy(),
+               {k: v[1] for k, v in ex.shared.items()}, ex.bytes_per_exchange()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _global_matrix(l2g, rowptr, colind, vals, nf, ndof):
+    rows = np.repeat(np.arange(rowptr.size - 1), np.diff(rowptr))
+    gr = l2g[rows // nf] * nf + rows % nf
+    gc = l2g[colind // nf] * nf + colind % nf
+    return sp.csr_matrix((vals, (gr, gc)), shape=(ndof, ndof))
+
+
+@pytest.mark.parametrize("elem,n,world", [("quad", 8, 2), ("hex", 4, 2), ("tri", 6, 4)])
+def test_interface_summation_over_gloo(ora, elem, n, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, elem, n, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    # single-domain reference
+    E = ora.ELEM[elem]
+    coords, conn = meshgen.make_mesh(elem, n, jitter=0.2, seed=1)
+    nf = coords.shape[1] + 1
+    u = meshgen.random_state(coords.shape[0], nf, seed=2)
+    p = ora.make_params(elem=elem, upwind="lps", stab="flow", kin_visc=0.05, exact_jac=1.0)
+    rowptr, colind = ora.fv1_csr(E, conn, coords.shape[0])
+    gv, gd = ora.assemble(p, conn, coords, u, rowptr, colind, ora.JAC_A | ora.DEF_A)
+    ndof = coords.shape[0] * nf
+    G = sp.csr_matrix((gv, colind, rowptr), shape=(ndof, ndof))
+    # (1) the additive local matrices / defects sum to the single-domain result, with identical sparsity
+    A = sum(_global_matrix(r[1], r[2], r[3], r[4], nf, ndof) for r in res)
+    dsum = np.zeros(ndof)
+    for r in res:
+        np.add.at(dsum, (r[1][:, None] * nf + np.arange(nf)).ravel(), r[5])
+    assert abs(A - G).max() < 1e-12 * abs(G).max()
+    pat = sum(_global_matrix(r[1], r[2], r[3], np.ones_like(r[4]), nf, ndof) for r in res)
+    assert np.array_equal(pat.indptr, G.indptr) and np.array_equal(pat.indices, colind)
+    assert np.abs(dsum - gd).max() < 1e-12 * np.abs(gd).max()
+    # (2) after sum_to_owner every node's defect on its owner is the single-domain defect
+    owner_g = np.full(coords.shape[0], world, dtype=int)
+    for r in res:
+        owner_g[r[1]] = np.minimum(owner_g[r[1]], r[0])
+    for r in res:
+        rank, l2g, own = r[0], r[1], r[8]
+        assert np.array_equal(own, owner_g[l2g])
+        mine = own == rank
+        d_local = r[7].reshape(-1, nf)
+        assert np.abs(d_local[mine] - gd.reshape(-1, nf)[l2g[mine]]).max() < 1e-12 * np.abs(gd).max()
+    # (3) matrix: on the owner, a block (a, b) whose two nodes are shared with the same set of ranks carries the full sum
+    holders = [set() for _ in range(coords.shape[0])]
+    for r in res:
+        for g in r[1]:
+            holders[g].add(r[0])
+    total_checked = 0
+    for r in res:
+        rank, l2g = r[0], r[1]
+        M = _global_matrix(l2g, r[2], r[3], r[6], nf, ndof).tocsr()
+        shared_g = np.unique(np.concatenate([v for v in r[9].values()])) if r[9] else np.zeros(0, int)
+        checked = 0
+        for a in shared_g:
+            if owner_g[a] != rank:
+                continue
+            for b in shared_g:
+                if not holders[a] <= holders[b]:       # every rank touching row a also holds column b
+                    continue
+                blk_g = G[a * nf:(a + 1) * nf, b * nf:(b + 1) * nf].toarray()
+                blk_l = M[a * nf:(a + 1) * nf, b * nf:(b + 1) * nf].toarray()
+                if np.abs(blk_g).max() == 0 and np.abs(blk_l).max() == 0:
+                    continue
+                assert np.abs(blk_l - blk_g).max() < 1e-12 * abs(G).max(), (rank, a, b)
+                checked += 1
+        total_checked += checked
+    assert total_checked > 0
+    assert any(r[10] > 0 for r in res)
+
+
+def test_rcb_and_block_partition():
+    c = np.random.default_rng(0).uniform(size=(1000, 3))
+    part = partition.rcb_partition(c, 8)
+    assert sorted(np.bincount(part)) == [125] * 8
+    assert partition.block_dims(8) == [2, 2, 2] and partition.block_dims(2) == [2, 1, 1] and partition.block_dims(4) == [2, 2, 1]
+    # block problems of neighbouring ranks agree on shared nodes (coordinates and state)
+    a, b = partition.block_problem(4, 0, 2), partition.block_problem(4, 1, 2)
+    ga, gb = a["iface"]["l2g"], b["iface"]["l2g"]
+    common, ia, ib = np.intersect1d(ga, gb, return_indices=True)
+    assert common.size == 25
+    assert np.allclose(a["coords"][ia], b["coords"][ib]) and np.array_equal(a["u"][ia], b["u"][ib])
+    assert set(ia) <= set(a["iface"]["boundary"])
