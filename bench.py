@@ -9,7 +9,7 @@ N GPUs assemble N such blocks of one (2x2x2-blocked) global mesh and sum interfa
 A "step" = one pass of the hot path over the mesh: Jacobian AND defect of the stiffness part for every
 element, scattered into the global CSR matrix / defect vector.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 184] [--mode gather|colored|atomic]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--cells 184] [--mode gather|colored|atomic]
   python bench.py --impl reference ...     # the reference arm: CPU oracle on the host cores
 
 One JSON line on stdout (rank 0).
@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--n", type=int, default=184, help="hex cells per direction per GPU (config 3: 184)")
+    ap.add_argument("--cells", dest="n", type=int, default=184, help="hex cells per direction per GPU (config 3: 184)")
     ap.add_argument("--mode", default="gather", choices=["gather", "colored", "atomic"])
     ap.add_argument("--ref-n", type=int, default=64, help="cells per direction of the CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -293,7 +293,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(args.mode)
+                bpe = json.load(open(tp))["bytes_per_element"].get(args.mode)
+                traffic = bpe * n_elem if bpe else None          # per launch (= pass), scaled from the ncu capture
             except Exception:
                 traffic = None
         out = {
