@@ -50,7 +50,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
         if (e != cudaSuccess) return e;
     }
     static const int WPB = [] { const char* ev = getenv("NSB_ROWS_WPB"); const int v = ev ? atoi(ev) : 3; return (v >= 1 && v <= 3) ? v : 3; }();
-    using WS = RowWS<E, EXACT>;
+    using WS = RowWS<E, STAB == STAB_FLOW, EXACT>;
     const size_t tab_bytes = (sizeof(double) * NIP * NSH + sizeof(int32_t) * NSH * ET<E>::NINC + 15) & ~(size_t)15;
     const size_t per_warp = (sizeof(WS) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
     const size_t smem = tab_bytes + per_warp * WPB;
@@ -80,7 +80,7 @@ cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
         default: return gather_t<STAB_NONE, false>(NSB_GFWD);
     }
 }
-size_t NSB_CAT(flux_record_doubles_, NSB_ELEM)() { return FluxRec<E, true>::SZ; }
+size_t NSB_CAT(flux_record_doubles_, NSB_ELEM)() { return FluxRec<E, true, true>::SZ; }
 
 cudaError_t NSB_CAT(launch_geom_, NSB_ELEM)(int64_t n_elem, const int32_t* conn, const double* coords, double* geo, cudaStream_t st)
 {

@@ -60,16 +60,17 @@ __global__ void geom_kernel(int64_t n_elem, const int32_t* __restrict__ conn, co
 // ---- compact per-(element, ip) record written by (A), read by (B) ------------------------------------
 //   F[NF]   defect fluxes (momentum d, continuity)                       add_def_A_elem :686-776
 //   inv     1/diag of the ip system (0 for no stabilisation)
-//   sn      StdVel . n ; std[DIM] StdVel                                 (FLOW continuity coefficients)
+//   sn      StdVel . n ; std[DIM] StdVel                                 (FLOW continuity coefficients; FLOW records only)
 //   cK[k]   (a N_k + b up_k + c (down_k - up_k)) * inv * rho  |  N_k rho (no stabilisation)
 //   dK[k]   up_k * prod * w + prod (1-w) N_k                             convective diagonal, :430-468
 //   EXACT:  eK[k] = rho (w up_k + (1-w) N_k [peclet]) , U[DIM]           exact-Newton extras, :521-549
-template <int E, bool EXACT> struct FluxRec {
+template <int E, bool FLOWREC, bool EXACT> struct FluxRec {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1;
-    static constexpr int O_F = 0, O_INV = NF, O_SN = NF + 1, O_STD = NF + 2;
-    static constexpr int O_CK = (O_STD + DIM + 1) & ~1, O_DK = O_CK + NSH, O_EK = O_DK + NSH, O_U = O_EK + NSH;
+    static constexpr int O_F = 0, O_INV = NF, O_SN = NF + 1, O_STD = NF + 2;           // sn / std only when FLOWREC
+    static constexpr int HEADRAW = NF + 1 + (FLOWREC ? 1 + DIM : 0);
+    static constexpr int O_CK = (HEADRAW + 1) & ~1, O_DK = O_CK + NSH, O_EK = O_DK + NSH, O_U = O_EK + NSH;
     static constexpr int RAW = EXACT ? O_U + DIM : O_EK;
-    static constexpr int SZ = (RAW + 1) & ~1;
+    static constexpr int SZ = (RAW + 3) & ~3;              // multiple of 32 bytes: sector-aligned records (hex FIELDS: 192 B)
 };
 
 NSB_DEV double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(BS, 3) fv1_flux_kernel(KParams p, MeshDev m, c
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, P = DIM;
     constexpr bool FLOW = (STAB == STAB_FLOW);
     using R = GeoRec<E>;
-    using FR = FluxRec<E, EXACT>;
+    using FR = FluxRec<E, FLOW, EXACT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* xs = reinterpret_cast<double*>(smem_raw);            // [NSH*DIM][BS]
     double* vs = xs + NSH * DIM * BS;                            // [NSH][BS]
@@ -447,9 +448,12 @@ __global__ void __launch_bounds__(BS, 3) fv1_flux_kernel(KParams p, MeshDev m, c
                 for (int d = 0; d < DIM; d++) fr[FR::O_U + d] = U[d];
             }
         }
-        fr[FR::O_INV] = inv; fr[FR::O_SN] = sn;
+        fr[FR::O_INV] = inv;
+        if constexpr (FLOW) {
+            fr[FR::O_SN] = sn;
 #pragma unroll
-        for (int d = 0; d < DIM; d++) fr[FR::O_STD + d] = std[d];
+            for (int d = 0; d < DIM; d++) fr[FR::O_STD + d] = std[d];
+        }
         // ---- defect fluxes (:686-776): stream the global gradients (d-major) ----
         if (want_def) {
             double gv[DIM][DIM], gp[DIM], gv0[DIM][DIM], gp0[DIM], sG[NSH];
@@ -557,12 +561,12 @@ template <int E> struct RowCfg {
     static constexpr int CH = (DIM == 3) ? 8 : 16;          // adjacent elements per round
     static constexpr int NREC = CH * NINC;
 };
-template <int E, bool EXACT> struct RowWS {
+template <int E, bool FLOWREC, bool EXACT> struct RowWS {
     using C = RowCfg<E>;
     // staged geometry = [n, (pad)] (NH doubles, the first NH of the record) + G[d][k]
     static constexpr int NH = (C::DIM + 1) & ~1, GS = NH + C::DIM * GeoRec<E>::NSHP;
     double geo[C::NREC][GS];
-    double flx[C::NREC][FluxRec<E, EXACT>::SZ];
+    double flx[C::NREC][FluxRec<E, FLOWREC, EXACT>::SZ];
     double vol[C::CH];
     int32_t ipx[C::NREC];           // ip | (256 if the node is the `to` corner of the SCVF)
     uint8_t slot[C::CH][8];
@@ -584,8 +588,8 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
     constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, L = NSH * NF, NIP = C::NIP;
     constexpr bool FLOW = (STAB == STAB_FLOW);
     using R = GeoRec<E>;
-    using FR = FluxRec<E, EXACT>;
-    using WS = RowWS<E, EXACT>;
+    using FR = FluxRec<E, FLOW, EXACT>;
+    using WS = RowWS<E, FLOW, EXACT>;
     constexpr int NH = WS::NH, GS = WS::GS;
     constexpr int GV = GS / 2, FV = FR::SZ / 2, HV = NH / 2;     // 16-byte chunks per staged record
     static_assert(GV <= 32 && FV <= 32, "record wider than a warp");
@@ -608,11 +612,14 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
     const int k = (lane < L) ? lane / NF : 0, cf = (lane < L) ? lane - (lane / NF) * NF : 0;
     const bool isv = cf < DIM;                                   // velocity column / pressure column
     const int cfv = isv ? cf : 0;
-    const double wv = isv ? 1.0 : 0.0, wp = isv ? 0.0 : 1.0;
     double msk[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; d++) msk[d] = (isv && d == cf) ? 1.0 : 0.0;
-    const double nurho_a = p.laplace ? 0.0 : -1.0 * p.visc * p.rho;   // -nu rho G_kd1 n_d2 vanishes for laplace (:346-356)
+    // branch-free blend coefficients: velocity column uses (-nu rho G_k [+ e_k U]) * n_cf, pressure column N_k * n
+    const double cA = isv ? (p.laplace ? 0.0 : -1.0 * p.visc * p.rho) : 0.0;   // -nu rho G_kd1 n_d2 vanishes for laplace (:346-356)
+    const double cPn = isv ? 0.0 : 1.0;
+    const double cV1 = isv ? 1.0 : 0.0;
+    const double cPc = (isv || STAB == STAB_NONE) ? 0.0 : -1.0;                // continuity row of the pressure column (:586-592)
     const double nurho_d = -1.0 * p.visc * p.rho;
     const double rho_f = FLOW ? p.rho : 0.0;
 
@@ -657,11 +664,20 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
             const int sslot = __shfl_sync(0xffffffffu, la_l, 0);
             cp_async_wait_all();
             __syncwarp();
+            // fold the sign of the SCVF w.r.t. this node (+: node is `from`, -: `to`) into the staged record
+            if (jac_a && lane < nrec && (ipx_r & 256)) {
+#pragma unroll
+                for (int d = 0; d < DIM; d++) ws.geo[lane][d] = -ws.geo[lane][d];
+#pragma unroll
+                for (int q = 0; q < NSH; q++) ws.flx[lane][FR::O_DK + q] = -ws.flx[lane][FR::O_DK + q];
+                if constexpr (FLOW) ws.flx[lane][FR::O_SN] = -ws.flx[lane][FR::O_SN];
+            }
+            __syncwarp();
             if (qb == q0) self_slot = ws.slot[0][sslot];
             // ---- accumulate: lane = (k, cf); fixed order j, t  (add_jac_A_elem :317-594) ----
             if (want_jac && lane < L) {
                 for (int j = 0; j < nj; j++) {
-                    double acc[NF];
+                    double acc[NF], accD = 0.0;
 #pragma unroll
                     for (int rf = 0; rf < NF; rf++) acc[rf] = 0.0;
                     if (jac_a) {
@@ -670,38 +686,37 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
                             const int r = j * NINC + t;
                             const double* gr = ws.geo[r];
                             const double* fl = ws.flx[r];
-                            const int ipx = ws.ipx[r];
-                            const double sg = (ipx & 256) ? -1.0 : 1.0;
-                            double n[DIM], Gk[DIM];
+                            double sn[DIM], Gk[DIM];                  // sn = signed normal
 #pragma unroll
-                            for (int d = 0; d < DIM; d++) { n[d] = gr[d]; Gk[d] = gr[NH + d * R::NSHP + k]; }
-                            const double gn = dotv<DIM>(Gk, n);
+                            for (int d = 0; d < DIM; d++) { sn[d] = gr[d]; Gk[d] = gr[NH + d * R::NSHP + k]; }
+                            const double gns = dotv<DIM>(Gk, sn);
                             const double inv = fl[FR::O_INV];
-                            const double ncf = gr[cfv];
-                            const double Nk = Ntab[(ipx & 255) * NSH + k];
-                            // velocity column: X = -nu rho G_k (+ e_k U), Y = n_cf ; pressure column: X = n, Y = N_k (:363-368)
-                            const double Y = wv * ncf + wp * Nk;
-                            const double D = nurho_d * gn + fl[FR::O_DK + k];
-                            double ek = 0.0;
-                            if constexpr (EXACT) ek = fl[FR::O_EK + k];
+                            const double sncf = gr[cfv];
+                            const double Nk = Ntab[(ws.ipx[r] & 255) * NSH + k];
+                            // momentum rows: velocity column (:336-356, :430-468, :521-549), pressure column (:363-368)
+                            double yv = cA * sncf;
+                            const double yp = cPn * Nk;
 #pragma unroll
-                            for (int d1 = 0; d1 < DIM; d1++) {
-                                double X = wv * (nurho_a * Gk[d1]) + wp * n[d1];
-                                if constexpr (EXACT) X += wv * ek * fl[FR::O_U + d1];
-                                acc[d1] += sg * (X * Y + msk[d1] * D);
+                            for (int d1 = 0; d1 < DIM; d1++) acc[d1] += yv * Gk[d1] + yp * sn[d1];
+                            if constexpr (EXACT) {
+                                const double ye = cV1 * fl[FR::O_EK + k] * sncf;
+#pragma unroll
+                                for (int d1 = 0; d1 < DIM; d1++) acc[d1] += ye * fl[FR::O_U + d1];
                             }
+                            accD += nurho_d * gns + fl[FR::O_DK + k];          // diagonal d1 == d2 (velocity columns only)
                             // continuity row: velocity column (:561-584), pressure column (:586-592, rho cancels)
-                            double cv = fl[FR::O_CK + k] * ncf;
+                            double cv = fl[FR::O_CK + k] * sncf;
                             if constexpr (FLOW) {
                                 // sum_q sv(q,d2,k) n_q rho = ((sb_k - std.G_k) n_d2 + G_k[d2] (std.n)) inv rho
                                 double sG = 0.0;
 #pragma unroll
                                 for (int d = 0; d < DIM; d++) sG += fl[FR::O_STD + d] * Gk[d];
-                                cv += (gr[NH + cfv * R::NSHP + k] * fl[FR::O_SN] - sG * ncf) * inv * rho_f;
+                                cv += (gr[NH + cfv * R::NSHP + k] * fl[FR::O_SN] - sG * sncf) * inv * rho_f;
                             }
-                            const double cpv = (STAB == STAB_NONE) ? 0.0 : -1.0 * gn * inv;
-                            acc[DIM] += sg * (wv * cv + wp * cpv);
+                            acc[DIM] += cV1 * cv + cPc * (gns * inv);
                         }
+#pragma unroll
+                        for (int d1 = 0; d1 < DIM; d1++) acc[d1] += msk[d1] * accD;
 #pragma unroll
                         for (int rf = 0; rf < NF; rf++) acc[rf] *= p.scale_a;
                     }
