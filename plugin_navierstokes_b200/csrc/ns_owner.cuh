@@ -578,13 +578,33 @@ NSB_DEV void cp_async16(void* smem_dst, const void* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 NSB_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+NSB_DEV void cp_async16_ca(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+NSB_DEV void cp_async16_hint(void* smem_dst, const void* gsrc, uint64_t pol)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
+}
+// staging flavour (experiment knob, warp-uniform): 0 cp.async.cg, 1 cp.async.ca, 2 ld.global.nc + st.shared, 3 cp.async.cg + L2 evict_last
+NSB_DEV void stage16(int mode, void* smem_dst, const double* gsrc, uint64_t pol)
+{
+    if (mode == 0) cp_async16(smem_dst, gsrc);
+    else if (mode == 1) cp_async16_ca(smem_dst, gsrc);
+    else if (mode == 2) *reinterpret_cast<double2*>(smem_dst) = __ldg(reinterpret_cast<const double2*>(gsrc));
+    else cp_async16_hint(smem_dst, gsrc, pol);
+}
 
 template <int E, int STAB, bool EXACT>
 __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
                                                           const double* __restrict__ flux, const double* __restrict__ u,
-                                                          double beta, double* __restrict__ val, double* __restrict__ def)
+                                                          double beta, double* __restrict__ val, double* __restrict__ def, int stage_mode)
 {
     using C = RowCfg<E>;
+    uint64_t l2pol = 0;
+    if (stage_mode == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(l2pol));
     constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, L = NSH * NF, NIP = C::NIP;
     constexpr bool FLOW = (STAB == STAB_FLOW);
     using R = GeoRec<E>;
@@ -650,8 +670,8 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
             for (int r = 0; r < nrec; r++) {
                 const int64_t gi = __shfl_sync(0xffffffffu, gi_r, r);
                 if (jac_a && lane < GV)       // chunks [0, HV) = normal, then the gradients (skipping xip / ds)
-                    cp_async16(&ws.geo[r][2 * lane], geo + gi * R::SZ + (lane < HV ? 2 * lane : R::HEAD - NH + 2 * lane));
-                if (lane < FV) cp_async16(&ws.flx[r][2 * lane], flux + gi * FR::SZ + 2 * lane);
+                    stage16(stage_mode, &ws.geo[r][2 * lane], geo + gi * R::SZ + (lane < HV ? 2 * lane : R::HEAD - NH + 2 * lane), l2pol);
+                if (lane < FV) stage16(stage_mode, &ws.flx[r][2 * lane], flux + gi * FR::SZ + 2 * lane, l2pol);
             }
             // scatter slots + the node's SCV volume in the adjacent elements (plain loads, overlapped with the copies)
             if (lane < nj) {
