@@ -62,8 +62,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
-    static const int stage_mode = [] { const char* ev = getenv("NSB_STAGE"); return ev ? atoi(ev) : 0; }();
-    kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, geo, flux, u, beta, val, def, stage_mode);
+    kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, geo, flux, u, beta, val, def);
     return cudaGetLastError();
 }
 #define NSB_GFWD k, m, geo, flux, u, s0, s1, beta, val, def, d_err, st, sm_count

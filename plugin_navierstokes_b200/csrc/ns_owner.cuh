@@ -60,7 +60,7 @@ __global__ void geom_kernel(int64_t n_elem, const int32_t* __restrict__ conn, co
 // ---- compact per-(element, ip) record written by (A), read by (B) ------------------------------------
 //   F[NF]   defect fluxes (momentum d, continuity)                       add_def_A_elem :686-776
 //   inv     1/diag of the ip system (0 for no stabilisation)
-//   sn      StdVel . n ; std[DIM] StdVel                                 (FLOW continuity coefficients; FLOW records only)
+//   sn      StdVel . n ; std[DIM] StdVel                                 (FLOW continuity coefficients)
 //   cK[k]   (a N_k + b up_k + c (down_k - up_k)) * inv * rho  |  N_k rho (no stabilisation)
 //   dK[k]   up_k * prod * w + prod (1-w) N_k                             convective diagonal, :430-468
 //   EXACT:  eK[k] = rho (w up_k + (1-w) N_k [peclet]) , U[DIM]           exact-Newton extras, :521-549
@@ -578,33 +578,13 @@ NSB_DEV void cp_async16(void* smem_dst, const void* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 NSB_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
-NSB_DEV void cp_async16_ca(void* smem_dst, const void* gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-NSB_DEV void cp_async16_hint(void* smem_dst, const void* gsrc, uint64_t pol)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
-}
-// staging flavour (experiment knob, warp-uniform): 0 cp.async.cg, 1 cp.async.ca, 2 ld.global.nc + st.shared, 3 cp.async.cg + L2 evict_last
-NSB_DEV void stage16(int mode, void* smem_dst, const double* gsrc, uint64_t pol)
-{
-    if (mode == 0) cp_async16(smem_dst, gsrc);
-    else if (mode == 1) cp_async16_ca(smem_dst, gsrc);
-    else if (mode == 2) *reinterpret_cast<double2*>(smem_dst) = __ldg(reinterpret_cast<const double2*>(gsrc));
-    else cp_async16_hint(smem_dst, gsrc, pol);
-}
 
 template <int E, int STAB, bool EXACT>
 __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
                                                           const double* __restrict__ flux, const double* __restrict__ u,
-                                                          double beta, double* __restrict__ val, double* __restrict__ def, int stage_mode)
+                                                          double beta, double* __restrict__ val, double* __restrict__ def)
 {
     using C = RowCfg<E>;
-    uint64_t l2pol = 0;
-    if (stage_mode == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(l2pol));
     constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, L = NSH * NF, NIP = C::NIP;
     constexpr bool FLOW = (STAB == STAB_FLOW);
     using R = GeoRec<E>;
@@ -632,14 +612,11 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
     const int k = (lane < L) ? lane / NF : 0, cf = (lane < L) ? lane - (lane / NF) * NF : 0;
     const bool isv = cf < DIM;                                   // velocity column / pressure column
     const int cfv = isv ? cf : 0;
+    const double wv = isv ? 1.0 : 0.0, wp = isv ? 0.0 : 1.0;
     double msk[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; d++) msk[d] = (isv && d == cf) ? 1.0 : 0.0;
-    // branch-free blend coefficients: velocity column uses (-nu rho G_k [+ e_k U]) * n_cf, pressure column N_k * n
-    const double cA = isv ? (p.laplace ? 0.0 : -1.0 * p.visc * p.rho) : 0.0;   // -nu rho G_kd1 n_d2 vanishes for laplace (:346-356)
-    const double cPn = isv ? 0.0 : 1.0;
-    const double cV1 = isv ? 1.0 : 0.0;
-    const double cPc = (isv || STAB == STAB_NONE) ? 0.0 : -1.0;                // continuity row of the pressure column (:586-592)
+    const double nurho_a = p.laplace ? 0.0 : -1.0 * p.visc * p.rho;   // -nu rho G_kd1 n_d2 vanishes for laplace (:346-356)
     const double nurho_d = -1.0 * p.visc * p.rho;
     const double rho_f = FLOW ? p.rho : 0.0;
 
@@ -670,8 +647,8 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
             for (int r = 0; r < nrec; r++) {
                 const int64_t gi = __shfl_sync(0xffffffffu, gi_r, r);
                 if (jac_a && lane < GV)       // chunks [0, HV) = normal, then the gradients (skipping xip / ds)
-                    stage16(stage_mode, &ws.geo[r][2 * lane], geo + gi * R::SZ + (lane < HV ? 2 * lane : R::HEAD - NH + 2 * lane), l2pol);
-                if (lane < FV) stage16(stage_mode, &ws.flx[r][2 * lane], flux + gi * FR::SZ + 2 * lane, l2pol);
+                    cp_async16(&ws.geo[r][2 * lane], geo + gi * R::SZ + (lane < HV ? 2 * lane : R::HEAD - NH + 2 * lane));
+                if (lane < FV) cp_async16(&ws.flx[r][2 * lane], flux + gi * FR::SZ + 2 * lane);
             }
             // scatter slots + the node's SCV volume in the adjacent elements (plain loads, overlapped with the copies)
             if (lane < nj) {
@@ -684,20 +661,11 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
             const int sslot = __shfl_sync(0xffffffffu, la_l, 0);
             cp_async_wait_all();
             __syncwarp();
-            // fold the sign of the SCVF w.r.t. this node (+: node is `from`, -: `to`) into the staged record
-            if (jac_a && lane < nrec && (ipx_r & 256)) {
-#pragma unroll
-                for (int d = 0; d < DIM; d++) ws.geo[lane][d] = -ws.geo[lane][d];
-#pragma unroll
-                for (int q = 0; q < NSH; q++) ws.flx[lane][FR::O_DK + q] = -ws.flx[lane][FR::O_DK + q];
-                if constexpr (FLOW) ws.flx[lane][FR::O_SN] = -ws.flx[lane][FR::O_SN];
-            }
-            __syncwarp();
             if (qb == q0) self_slot = ws.slot[0][sslot];
             // ---- accumulate: lane = (k, cf); fixed order j, t  (add_jac_A_elem :317-594) ----
             if (want_jac && lane < L) {
                 for (int j = 0; j < nj; j++) {
-                    double acc[NF], accD = 0.0;
+                    double acc[NF];
 #pragma unroll
                     for (int rf = 0; rf < NF; rf++) acc[rf] = 0.0;
                     if (jac_a) {
@@ -706,37 +674,38 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
                             const int r = j * NINC + t;
                             const double* gr = ws.geo[r];
                             const double* fl = ws.flx[r];
-                            double sn[DIM], Gk[DIM];                  // sn = signed normal
+                            const int ipx = ws.ipx[r];
+                            const double sg = (ipx & 256) ? -1.0 : 1.0;
+                            double n[DIM], Gk[DIM];
 #pragma unroll
-                            for (int d = 0; d < DIM; d++) { sn[d] = gr[d]; Gk[d] = gr[NH + d * R::NSHP + k]; }
-                            const double gns = dotv<DIM>(Gk, sn);
+                            for (int d = 0; d < DIM; d++) { n[d] = gr[d]; Gk[d] = gr[NH + d * R::NSHP + k]; }
+                            const double gn = dotv<DIM>(Gk, n);
                             const double inv = fl[FR::O_INV];
-                            const double sncf = gr[cfv];
-                            const double Nk = Ntab[(ws.ipx[r] & 255) * NSH + k];
-                            // momentum rows: velocity column (:336-356, :430-468, :521-549), pressure column (:363-368)
-                            double yv = cA * sncf;
-                            const double yp = cPn * Nk;
+                            const double ncf = gr[cfv];
+                            const double Nk = Ntab[(ipx & 255) * NSH + k];
+                            // velocity column: X = -nu rho G_k (+ e_k U), Y = n_cf ; pressure column: X = n, Y = N_k (:363-368)
+                            const double Y = wv * ncf + wp * Nk;
+                            const double D = nurho_d * gn + fl[FR::O_DK + k];
+                            double ek = 0.0;
+                            if constexpr (EXACT) ek = fl[FR::O_EK + k];
 #pragma unroll
-                            for (int d1 = 0; d1 < DIM; d1++) acc[d1] += yv * Gk[d1] + yp * sn[d1];
-                            if constexpr (EXACT) {
-                                const double ye = cV1 * fl[FR::O_EK + k] * sncf;
-#pragma unroll
-                                for (int d1 = 0; d1 < DIM; d1++) acc[d1] += ye * fl[FR::O_U + d1];
+                            for (int d1 = 0; d1 < DIM; d1++) {
+                                double X = wv * (nurho_a * Gk[d1]) + wp * n[d1];
+                                if constexpr (EXACT) X += wv * ek * fl[FR::O_U + d1];
+                                acc[d1] += sg * (X * Y + msk[d1] * D);
                             }
-                            accD += nurho_d * gns + fl[FR::O_DK + k];          // diagonal d1 == d2 (velocity columns only)
                             // continuity row: velocity column (:561-584), pressure column (:586-592, rho cancels)
-                            double cv = fl[FR::O_CK + k] * sncf;
+                            double cv = fl[FR::O_CK + k] * ncf;
                             if constexpr (FLOW) {
                                 // sum_q sv(q,d2,k) n_q rho = ((sb_k - std.G_k) n_d2 + G_k[d2] (std.n)) inv rho
                                 double sG = 0.0;
 #pragma unroll
                                 for (int d = 0; d < DIM; d++) sG += fl[FR::O_STD + d] * Gk[d];
-                                cv += (gr[NH + cfv * R::NSHP + k] * fl[FR::O_SN] - sG * sncf) * inv * rho_f;
+                                cv += (gr[NH + cfv * R::NSHP + k] * fl[FR::O_SN] - sG * ncf) * inv * rho_f;
                             }
-                            acc[DIM] += cV1 * cv + cPc * (gns * inv);
+                            const double cpv = (STAB == STAB_NONE) ? 0.0 : -1.0 * gn * inv;
+                            acc[DIM] += sg * (wv * cv + wp * cpv);
                         }
-#pragma unroll
-                        for (int d1 = 0; d1 < DIM; d1++) acc[d1] += msk[d1] * accD;
 #pragma unroll
                         for (int rf = 0; rf < NF; rf++) acc[rf] *= p.scale_a;
                     }
