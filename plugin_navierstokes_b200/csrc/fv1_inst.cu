@@ -41,8 +41,9 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
     if (k.what & (W_JAC_A | W_DEF_A)) {
-        const size_t smem_a = sizeof(double) * (NSH * DIM + NSH) * BS;
-        auto ka = fv1_flux_kernel<E, STAB, EXACT, BS>;
+        const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH) * BS + NIP * NSH * DIM + NIP * NSH);
+        static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 3; }();
+        auto ka = minb == 2 ? fv1_flux_kernel<E, STAB, EXACT, BS, 2> : minb == 4 ? fv1_flux_kernel<E, STAB, EXACT, BS, 4> : fv1_flux_kernel<E, STAB, EXACT, BS, 3>;
         e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
         if (e != cudaSuccess) return e;
         ka<<<(unsigned)((m.n_elem + BS - 1) / BS), BS, smem_a, st>>>(k, m, geo, u, s0, s1, flux, d_err);

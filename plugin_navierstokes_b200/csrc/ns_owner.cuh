@@ -211,10 +211,11 @@ NSB_DEV bool upwind_uniform(int type, const double* __restrict__ xs, int tid, co
 // (A) flux kernel
 // ------------------------------------------------------------------------------------------------
 // FV1Geometry of SCVF `ip` (warp-uniform) from the thread's shared corner column; see ip_geometry (ns_fv1.cuh).
-// cen = element barycentre (hoisted). G is only computed when wantG.
+// cen = element barycentre (hoisted). dnt = local shape gradients at the ips [NIP][NSH][DIM] (shared memory).
+// JI (inverse transposed Jacobian at the ip) is only computed when wantJ: global_grad(k) = JI * dnt[ip][k].
 template <int E, int BS>
-NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, const double* cen, double* n, double* xip,
-                             double& ds, bool wantG, double (*G)[ET<E>::DIM])
+NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, const double* cen, const double* __restrict__ dnt,
+                             double* n, double* xip, double& ds, bool wantJ, double (*JI)[ET<E>::DIM])
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
     const int f = tab::C_EDGE[E][ip][0], t = tab::C_EDGE[E][ip][1];
@@ -247,35 +248,31 @@ NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, con
         for (int d = 0; d < 3; d++) n[d] *= 0.5;
         ds = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
     }
-    if (wantG) {
-        double JT[DIM][DIM], JI[DIM][DIM];
+    if (wantJ) {
+        double JT[DIM][DIM];
 #pragma unroll
         for (int i = 0; i < DIM; i++)
 #pragma unroll
             for (int j = 0; j < DIM; j++) JT[i][j] = 0.0;
+        const double* dn = dnt + ip * (NSH * DIM);
 #pragma unroll
-        for (int k = 0; k < NSH; k++)
+        for (int k = 0; k < NSH; k++) {
+            double dk[DIM];
+#pragma unroll
+            for (int i = 0; i < DIM; i++) dk[i] = dn[k * DIM + i];
 #pragma unroll
             for (int j = 0; j < DIM; j++) {
                 const double xkj = NSB_COL(xs, k * DIM + j);
 #pragma unroll
-                for (int i = 0; i < DIM; i++) JT[i][j] += tab::C_DNIP[E][ip][k][i] * xkj;
+                for (int i = 0; i < DIM; i++) JT[i][j] += dk[i] * xkj;
             }
+        }
         inv_mat<DIM>(JT, JI);
-#pragma unroll
-        for (int k = 0; k < NSH; k++)
-#pragma unroll
-            for (int j = 0; j < DIM; j++) {
-                double s = 0;
-#pragma unroll
-                for (int i = 0; i < DIM; i++) s += JI[j][i] * tab::C_DNIP[E][ip][k][i];
-                G[k][j] = s;
-            }
     }
 }
 
-template <int E, int STAB, bool EXACT, int BS>
-__global__ void __launch_bounds__(BS, 3) fv1_flux_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
+template <int E, int STAB, bool EXACT, int BS, int MINB = 3>
+__global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
                                                       const double* __restrict__ u, const double* __restrict__ s0,
                                                       const double* __restrict__ s1, double* __restrict__ flux,
                                                       int* __restrict__ errflag)
@@ -287,7 +284,12 @@ __global__ void __launch_bounds__(BS, 3) fv1_flux_kernel(KParams p, MeshDev m, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* xs = reinterpret_cast<double*>(smem_raw);            // [NSH*DIM][BS]
     double* vs = xs + NSH * DIM * BS;                            // [NSH][BS]
+    double* dnt = vs + NSH * BS;                                 // [NIP][NSH][DIM] local shape gradients at the ips
+    double* Nt = dnt + NIP * NSH * DIM;                          // [NIP][NSH]      shape values at the ips
     const int tid = threadIdx.x;
+    for (int i = tid; i < NIP * NSH * DIM; i += BS) dnt[i] = tab::C_DNIP[E][i / (NSH * DIM)][(i / DIM) % NSH][i % DIM];
+    for (int i = tid; i < NIP * NSH; i += BS) Nt[i] = tab::NIPSH[E][i / NSH][i % NSH];
+    __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * BS + tid;
     if (e >= m.n_elem) return;                                   // no block-wide barriers below
     const bool td = p.time_dep;
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(BS, 3) fv1_flux_kernel(KParams p, MeshDev m, c
         cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
         for (int i = 0; i < NIP; i++) {
             double nn_[DIM], xx_[DIM], dsi;
-            ip_geometry_col<E, BS>(xs, tid, i, cen, nn_, xx_, dsi, false, nullptr);
+            ip_geometry_col<E, BS>(xs, tid, i, cen, dnt, nn_, xx_, dsi, false, nullptr);
             const double q = dotv<DIM>(nn_, nn_);
             if (q < cmn) cmn = q;
             cav += q;
@@ -338,11 +340,11 @@ __global__ void __launch_bounds__(BS, 3) fv1_flux_kernel(KParams p, MeshDev m, c
     for (int ip = 0; ip < NIP; ip++) {
         double* fr = flux + (e * NIP + ip) * FR::SZ;
         const int from = tab::C_EDGE[E][ip][0], to = tab::C_EDGE[E][ip][1];
-        double n[DIM], xip[DIM], ds = 0.0, G[NSH][DIM];
-        ip_geometry_col<E, BS>(xs, tid, ip, cen, n, xip, ds, want_def, G);
+        double n[DIM], xip[DIM], ds = 0.0, JI[DIM][DIM];
+        ip_geometry_col<E, BS>(xs, tid, ip, cen, dnt, n, xip, ds, want_def, JI);
         double N[NSH];
 #pragma unroll
-        for (int k = 0; k < NSH; k++) N[k] = tab::NIPSH[E][ip][k];
+        for (int k = 0; k < NSH; k++) N[k] = Nt[ip * NSH + k];
         // ---- StdVel from the `u` argument (:282-293) ----
         double std[DIM];
 #pragma unroll
@@ -461,9 +463,14 @@ __global__ void __launch_bounds__(BS, 3) fv1_flux_kernel(KParams p, MeshDev m, c
             for (int k = 0; k < NSH; k++) sG[k] = 0.0;
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
-                double Gd[NSH];
+                double Gd[NSH];                                  // global_grad(k)[d] = sum_i JI[d][i] * local_grad(k)[i]
 #pragma unroll
-                for (int k = 0; k < NSH; k++) Gd[k] = G[k][d];
+                for (int k = 0; k < NSH; k++) {
+                    double g = 0.0;
+#pragma unroll
+                    for (int i = 0; i < DIM; i++) g += JI[d][i] * dnt[(ip * NSH + k) * DIM + i];
+                    Gd[k] = g;
+                }
                 double sp = 0.0, sv[DIM];
 #pragma unroll
                 for (int q = 0; q < DIM; q++) sv[q] = 0.0;
