@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* xs = reinterpret_cast<double*>(smem_raw);            // [NSH*DIM][BS]
     double* vs = xs + NSH * DIM * BS;                            // [NSH][BS]
-    double* dnt = vs + NSH * BS;                                 // [NIP][NSH][DIM] local shape gradients at the ips
+    double* us = vs + NSH * BS;                                  // [NSH*NF][BS] nodal unknowns (the `u` argument)
+    double* dnt = us + NSH * NF * BS;                            // [NIP][NSH][DIM] local shape gradients at the ips
     double* Nt = dnt + NIP * NSH * DIM;                          // [NIP][NSH]      shape values at the ips
     const int tid = threadIdx.x;
     for (int i = tid; i < NIP * NSH * DIM; i += BS) dnt[i] = tab::C_DNIP[E][i / (NSH * DIM)][(i / DIM) % NSH][i % DIM];
@@ -295,17 +296,16 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
     const bool td = p.time_dep;
     // ---- element data: unknowns in registers, coordinates / volumes in the thread's shared column ----
     int nd[NSH];
-    double ur[NSH][NF];
 #pragma unroll
     for (int k = 0; k < NSH; k++) nd[k] = m.conn[e * NSH + k];
 #pragma unroll
     for (int k = 0; k < NSH; k++) {
         if (NF == 4) {
             const double2 a = ldg2(u + (int64_t)nd[k] * 4), b = ldg2(u + (int64_t)nd[k] * 4 + 2);
-            ur[k][0] = a.x; ur[k][1] = a.y; ur[k][2] = b.x; ur[k][NF - 1] = b.y;
+            NSB_COL(us, k * NF + 0) = a.x; NSB_COL(us, k * NF + 1) = a.y; NSB_COL(us, k * NF + 2) = b.x; NSB_COL(us, k * NF + NF - 1) = b.y;
         } else {
 #pragma unroll
-            for (int f = 0; f < NF; f++) ur[k][f] = u[(int64_t)nd[k] * NF + f];
+            for (int f = 0; f < NF; f++) NSB_COL(us, k * NF + f) = u[(int64_t)nd[k] * NF + f];
         }
 #pragma unroll
         for (int d = 0; d < DIM; d++) NSB_COL(xs, k * DIM + d) = m.coords[(int64_t)nd[k] * DIM + d];
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
         for (int d = 0; d < DIM; d++) {
             double s = 0;
 #pragma unroll
-            for (int k = 0; k < NSH; k++) s += ur[k][d] * N[k];
+            for (int k = 0; k < NSH; k++) s += NSB_COL(us, k * NF + d) * N[k];
             std[d] = s;
         }
         const double sn = dotv<DIM>(std, n);
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
 #pragma unroll
             for (int k = 0; k < NSH; k++)
 #pragma unroll
-                for (int d = 0; d < DIM; d++) U[d] += up[k] * ur[k][d];          // upwind_vel, upwind_interface.h:334-358
+                for (int d = 0; d < DIM; d++) U[d] += up[k] * NSB_COL(us, k * NF + d);          // upwind_vel, upwind_interface.h:334-358
             if (p.peclet) {                                       // peclet_blend :871-892
                 double dd = 0;
 #pragma unroll
@@ -477,9 +477,9 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
 #pragma unroll
                 for (int k = 0; k < NSH; k++) {
                     if (FLOW) sG[k] += Gd[k] * std[d];
-                    sp += Gd[k] * ur[k][P];
+                    sp += Gd[k] * NSB_COL(us, k * NF + P);
 #pragma unroll
-                    for (int q = 0; q < DIM; q++) sv[q] += Gd[k] * ur[k][q];
+                    for (int q = 0; q < DIM; q++) sv[q] += Gd[k] * NSB_COL(us, k * NF + q);
                 }
                 gp[d] = sp;
 #pragma unroll
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
             }
             double pr = 0.0;
 #pragma unroll
-            for (int k = 0; k < NSH; k++) pr += N[k] * ur[k][P];
+            for (int k = 0; k < NSH; k++) pr += N[k] * NSB_COL(us, k * NF + P);
             double F[NF];
 #pragma unroll
             for (int d1 = 0; d1 < DIM; d1++) {
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
                 for (int k = 0; k < NSH; k++) {
                     double sk = 0.0;
 #pragma unroll
-                    for (int d = 0; d < DIM; d++) sk += (td ? s0[(int64_t)nd[k] * NF + d] : ur[k][d]) * n[d];
+                    for (int d = 0; d < DIM; d++) sk += (td ? s0[(int64_t)nd[k] * NF + d] : NSB_COL(us, k * NF + d)) * n[d];
                     acc += (FLOW ? sb[k] - sG[k] : sb[k]) * sk;
                 }
                 double gpn = 0.0, div = 0.0;
