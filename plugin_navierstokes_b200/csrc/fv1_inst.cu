@@ -42,7 +42,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     cudaError_t e;
     if (k.what & (W_JAC_A | W_DEF_A)) {
         const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * BS + NIP * NSH * DIM + NIP * NSH);
-        static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 3; }();
+        static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 2; }();
         auto ka = minb == 2 ? fv1_flux_kernel<E, STAB, EXACT, BS, 2> : minb == 4 ? fv1_flux_kernel<E, STAB, EXACT, BS, 4> : fv1_flux_kernel<E, STAB, EXACT, BS, 3>;
         e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
         if (e != cudaSuccess) return e;
@@ -63,10 +63,12 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
-    kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, geo, flux, u, beta, val, def);
+    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, geo, flux, u, beta, val, def, work_counter);
     return cudaGetLastError();
 }
-#define NSB_GFWD k, m, geo, flux, u, s0, s1, beta, val, def, d_err, st, sm_count
+#define NSB_GFWD k, m, geo, flux, u, s0, s1, beta, val, def, d_err, st, sm_count, work_counter
 cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
 {
     const bool exact = !k.stokes && k.exact_jac != 0.0;

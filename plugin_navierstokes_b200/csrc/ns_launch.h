@@ -13,7 +13,7 @@ struct LaunchInfo { int64_t launches = 0; };
 #define NSB_ELEM_ARGS int sc, const KParams& k, const MeshDev& m, const int32_t* list, int64_t n_list, const double* u, \
     const double* s0, const double* s1, double* val, double* def, double* jl, double* dl, int* d_err, cudaStream_t st
 #define NSB_GATHER_ARGS const KParams& k, const MeshDev& m, const double* geo, double* flux, const double* u, const double* s0, const double* s1, double beta, \
-    double* val, double* def, int* d_err, cudaStream_t st, int sm_count
+    double* val, double* def, int* d_err, cudaStream_t st, int sm_count, unsigned long long* work_counter
 #define NSB_DECL(E)                                                                                   \
     cudaError_t launch_elem_##E(NSB_ELEM_ARGS);                                                       \
     cudaError_t launch_dense_##E(NSB_ELEM_ARGS);                                                      \

@@ -589,7 +589,8 @@ NSB_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.asyn
 template <int E, int STAB, bool EXACT>
 __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
                                                           const double* __restrict__ flux, const double* __restrict__ u,
-                                                          double beta, double* __restrict__ val, double* __restrict__ def)
+                                                          double beta, double* __restrict__ val, double* __restrict__ def,
+                                                          unsigned long long* __restrict__ work_counter)
 {
     using C = RowCfg<E>;
     constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, L = NSH * NF, NIP = C::NIP;
@@ -627,7 +628,15 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
     const double nurho_d = -1.0 * p.visc * p.rho;
     const double rho_f = FLOW ? p.rho : 0.0;
 
-    for (int64_t ai = (int64_t)blockIdx.x * nwarp + warp; ai < m.n_node; ai += (int64_t)gridDim.x * nwarp) {
+    // dynamic work distribution: every warp atomically takes the next node of the traversal order. A static
+    // grid-stride assignment lets the persistent warps drift apart, which destroys the L2 reuse of the SCVF
+    // records shared by neighbouring nodes (measured: 1.75x table re-reads at 128^3 with the static loop).
+    (void)nwarp;
+    for (;;) {
+        unsigned long long ai_u = 0;
+        if (lane == 0) ai_u = atomicAdd(work_counter, 1ULL);
+        const int64_t ai = (int64_t)__shfl_sync(0xffffffffu, ai_u, 0);
+        if (ai >= m.n_node) break;
         const int64_t a = m.node_order ? (int64_t)m.node_order[ai] : ai;
         const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1];
         const int64_t b0 = m.brow[a];

@@ -56,6 +56,7 @@ struct nsb_ctx {
     uint8_t *d_emap = nullptr;
     FvcrDev fvcr{};
     int *d_err = nullptr;
+    unsigned long long* d_counter = nullptr;
     // staging for NSB_HOST calls
     double *d_u = nullptr, *d_s0 = nullptr, *d_s1 = nullptr, *d_val = nullptr, *d_def = nullptr;
     double *d_jloc = nullptr, *d_dloc = nullptr;
@@ -121,7 +122,7 @@ extern "C" int nsb_create(int device, nsb_ctx** out)
     c->device = device;
     nsb_params_default(&c->prm);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess) {
+        cudaMalloc(&c->d_err, sizeof(int)) != cudaSuccess || cudaMalloc(&c->d_counter, sizeof(unsigned long long)) != cudaSuccess) {
         set_err(nullptr, NSB_ERR_CUDA, "nsb_create: cannot initialise device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
         delete c; return NSB_ERR_CUDA;
     }
@@ -157,7 +158,7 @@ extern "C" void nsb_destroy(nsb_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_mesh(c);
-    cudaFree(c->d_err);
+    cudaFree(c->d_err); cudaFree(c->d_counter);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -482,7 +483,7 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
         static const int kNIP[4] = {3, 4, 6, 12};
         CUDA_TRY(c, cudaMalloc(&c->d_flux, (size_t)c->n_elem * kNIP[c->elem] * rec * sizeof(double)));
     }
-#define NSB_GO(fn) fn(k, m, c->d_geo, c->d_flux, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count)
+#define NSB_GO(fn) fn(k, m, c->d_geo, c->d_flux, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter)
     switch (c->elem) { case 0: e = NSB_GO(launch_gather_0); break; case 1: e = NSB_GO(launch_gather_1); break;
                        case 2: e = NSB_GO(launch_gather_2); break; default: e = NSB_GO(launch_gather_3); }
 #undef NSB_GO
