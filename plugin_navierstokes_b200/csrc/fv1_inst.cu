@@ -36,6 +36,29 @@ cudaError_t NSB_CAT(launch_elem_, NSB_ELEM)(NSB_ELEM_ARGS)
 }
 
 // owner-computes path: (A) flux kernel, thread per element  ->  (B) rows kernel, warp per node
+template <int STAB, bool EXACT, int CHP, int MINB>
+static cudaError_t rows_t(const KParams& k, const MeshDev& m, const double* rec, const double* u, double beta, double* val,
+                          double* def, cudaStream_t st, int sm_count, unsigned long long* work_counter, int WPB)
+{
+    constexpr int NF = ET<E>::DIM + 1;
+    using WS = RowWS<E, STAB == STAB_FLOW, EXACT, CHP>;
+    const size_t tab_bytes = rows_tab_bytes<E>(m.max_cnt);
+    const size_t per_warp = (sizeof(WS) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
+    const size_t smem = tab_bytes + per_warp * WPB;
+    auto kb = fv1_rows_kernel<E, STAB, EXACT, CHP, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, WPB * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
+    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, rec, u, beta, val, def, work_counter);
+    return cudaGetLastError();
+}
+
 template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
 {
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
@@ -46,29 +69,26 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
         auto ka = minb == 2 ? fv1_flux_kernel<E, STAB, EXACT, BS, 2> : minb == 4 ? fv1_flux_kernel<E, STAB, EXACT, BS, 4> : fv1_flux_kernel<E, STAB, EXACT, BS, 3>;
         e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
         if (e != cudaSuccess) return e;
-        ka<<<(unsigned)((m.n_elem + BS - 1) / BS), BS, smem_a, st>>>(k, m, geo, u, s0, s1, flux, d_err);
+        ka<<<(unsigned)((m.n_elem + BS - 1) / BS), BS, smem_a, st>>>(k, m, u, s0, s1, rec, d_err);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    static const int WPB = [] { const char* ev = getenv("NSB_ROWS_WPB"); const int v = ev ? atoi(ev) : 3; return (v >= 1 && v <= 3) ? v : 3; }();
-    using WS = RowWS<E, STAB == STAB_FLOW, EXACT>;
-    const size_t tab_bytes = (sizeof(double) * NIP * NSH + sizeof(int32_t) * NSH * ET<E>::NINC + 15) & ~(size_t)15;
-    const size_t per_warp = (sizeof(WS) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
-    const size_t smem = tab_bytes + per_warp * WPB;
-    auto kb = fv1_rows_kernel<E, STAB, EXACT>;
-    e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int occ = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, WPB * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
-    const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
-    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return e;
-    kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, geo, flux, u, beta, val, def, work_counter);
-    return cudaGetLastError();
+    // experiment knobs (hex only): NSB_ROWS_CH = adjacent elements staged per round, NSB_ROWS_MINB = blocks/SM the
+    // register allocation is bounded for
+    // measured best on B200 for hex (profiles/r1_history.md): 4 elements per round, 96 registers, 2 warps per block
+    static const int WPB = [] { const char* ev = getenv("NSB_ROWS_WPB"); const int v = ev ? atoi(ev) : (E == 3 ? 2 : 3); return (v >= 1 && v <= 3) ? v : 3; }();
+    static const int CHV = [] { const char* ev = getenv("NSB_ROWS_CH"); return ev ? atoi(ev) : 4; }();
+    static const int MINBV = [] { const char* ev = getenv("NSB_ROWS_MINB"); return ev ? atoi(ev) : 6; }();
+    if constexpr (E == 3) {
+        if (CHV == 4 && MINBV == 8) return rows_t<STAB, EXACT, 4, 8>(k, m, rec, u, beta, val, def, st, sm_count, work_counter, WPB);
+        if (CHV == 4 && MINBV == 6) return rows_t<STAB, EXACT, 4, 6>(k, m, rec, u, beta, val, def, st, sm_count, work_counter, WPB);
+        if (CHV == 4) return rows_t<STAB, EXACT, 4, 5>(k, m, rec, u, beta, val, def, st, sm_count, work_counter, WPB);
+        if (MINBV == 6) return rows_t<STAB, EXACT, 8, 6>(k, m, rec, u, beta, val, def, st, sm_count, work_counter, WPB);
+        return rows_t<STAB, EXACT, 8, 5>(k, m, rec, u, beta, val, def, st, sm_count, work_counter, WPB);
+    }
+    return rows_t<STAB, EXACT, 0, 5>(k, m, rec, u, beta, val, def, st, sm_count, work_counter, WPB);
 }
-#define NSB_GFWD k, m, geo, flux, u, s0, s1, beta, val, def, d_err, st, sm_count, work_counter
+#define NSB_GFWD k, m, rec, u, s0, s1, beta, val, def, d_err, st, sm_count, work_counter
 cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
 {
     const bool exact = !k.stokes && k.exact_jac != 0.0;
@@ -83,15 +103,20 @@ cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
         default: return gather_t<STAB_NONE, false>(NSB_GFWD);
     }
 }
-size_t NSB_CAT(flux_record_doubles_, NSB_ELEM)() { return FluxRec<E, true, true>::SZ; }
+// doubles per combined SCVF record [geometry | flux] for the given stabilisation / Jacobian flavour
+int NSB_CAT(scvf_record_doubles_, NSB_ELEM)(bool flow, bool exact)
+{
+    const int g = GeoRec<E>::SZ;
+    if (flow) return g + (exact ? FluxRec<E, true, true>::SZ : FluxRec<E, true, false>::SZ);
+    return g + (exact ? FluxRec<E, false, true>::SZ : FluxRec<E, false, false>::SZ);
+}
 
-cudaError_t NSB_CAT(launch_geom_, NSB_ELEM)(int64_t n_elem, const int32_t* conn, const double* coords, double* geo, cudaStream_t st)
+cudaError_t NSB_CAT(launch_geom_, NSB_ELEM)(int64_t n_elem, const int32_t* conn, const double* coords, double* rec, int stride, cudaStream_t st)
 {
     const int64_t n = n_elem * ET<E>::NIP;
-    geom_kernel<E><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n_elem, conn, coords, geo);
+    geom_kernel<E><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n_elem, conn, coords, rec, stride);
     return cudaGetLastError();
 }
-size_t NSB_CAT(geom_record_doubles_, NSB_ELEM)() { return GeoRec<E>::SZ; }
 
 cudaError_t NSB_CAT(launch_scvvol_, NSB_ELEM)(int64_t n_elem, const int32_t* conn, const double* coords, double* scvvol, cudaStream_t st)
 {

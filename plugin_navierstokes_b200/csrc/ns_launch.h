@@ -12,16 +12,15 @@ struct LaunchInfo { int64_t launches = 0; };
 
 #define NSB_ELEM_ARGS int sc, const KParams& k, const MeshDev& m, const int32_t* list, int64_t n_list, const double* u, \
     const double* s0, const double* s1, double* val, double* def, double* jl, double* dl, int* d_err, cudaStream_t st
-#define NSB_GATHER_ARGS const KParams& k, const MeshDev& m, const double* geo, double* flux, const double* u, const double* s0, const double* s1, double beta, \
+#define NSB_GATHER_ARGS const KParams& k, const MeshDev& m, double* rec, const double* u, const double* s0, const double* s1, double beta, \
     double* val, double* def, int* d_err, cudaStream_t st, int sm_count, unsigned long long* work_counter
 #define NSB_DECL(E)                                                                                   \
     cudaError_t launch_elem_##E(NSB_ELEM_ARGS);                                                       \
     cudaError_t launch_dense_##E(NSB_ELEM_ARGS);                                                      \
     cudaError_t launch_gather_##E(NSB_GATHER_ARGS);                                                   \
     cudaError_t launch_scvvol_##E(int64_t n_elem, const int32_t* conn, const double* coords, double* scvvol, cudaStream_t st); \
-    cudaError_t launch_geom_##E(int64_t n_elem, const int32_t* conn, const double* coords, double* geo, cudaStream_t st); \
-    size_t geom_record_doubles_##E(); \
-    size_t flux_record_doubles_##E();
+    cudaError_t launch_geom_##E(int64_t n_elem, const int32_t* conn, const double* coords, double* rec, int stride, cudaStream_t st); \
+    int scvf_record_doubles_##E(bool flow, bool exact);
 NSB_DECL(0) NSB_DECL(1) NSB_DECL(2) NSB_DECL(3)
 #undef NSB_DECL
 struct FvcrDev;

@@ -3,14 +3,16 @@
 //  (A) fv1_flux_kernel : one THREAD per element, warp-uniform control flow. For each SCVF (ip) of the element,
 //      in reference order: StdVel -> upwind (No/Full/Skewed/LPS, ray search over constant-memory side tables)
 //      -> diffusion length -> FIELDS/FLOW/none closure -> defect fluxes. Every SCVF is evaluated ONCE.
-//      Nodal unknowns live in registers, corner coordinates / SCV volumes in thread-private shared columns
-//      (conflict-free). The SCVF geometry (normal, ip, global gradients) comes from the table precomputed at
-//      upload. Output: one compact FluxRec per (element, ip) = the state-dependent coefficients only.
-//  (B) fv1_rows_kernel : one WARP per grid node (= NF consecutive CSR rows). Stages the FluxRecs and the
-//      geometry of the <= CH*NINC SCVFs incident to the node with coalesced 128-bit loads, then lane =
-//      (corner k, function cf) accumulates its column of every incident SCVF (fixed order -> bitwise
-//      deterministic) into the node's rows in shared memory, and the finished rows are streamed to HBM exactly
-//      once (st.global.cs): no atomics, no colouring, no read-modify-write, no zero-fill of the matrix.
+//      Nodal unknowns, corner coordinates and SCV volumes live in thread-private shared columns (conflict-free).
+//      Output: the flux half of one combined SCVF record per (element, ip) = the state-dependent coefficients
+//      only; the static half (normal, G_k.n, global gradients) is written once per mesh by geom_kernel.
+//  (B) fv1_rows_kernel : one WARP per grid node (= NF consecutive CSR rows), nodes handed out by an atomic
+//      counter. Every incident SCVF record is fetched with ONE TMA bulk copy (cp.async.bulk -> UBLKCP)
+//      completing on a warp-private mbarrier. lane = (element jj of JP in parallel, corner k) builds the NF x NF
+//      block d r(node) / d u(corner k) of its element in registers (fixed SCVF order -> bitwise deterministic);
+//      the blocks are parked in the consumed record area and added by all 32 lanes, one element at a time, into
+//      a bank-rotated block-major row accumulator in shared memory. Finished rows are streamed to HBM exactly
+//      once (st.global.cs): no atomics, no colouring, no global read-modify-write, no zero-fill of the matrix.
 //
 // Arithmetic restated from fv1/navier_stokes_fv1.cpp:250-778, fv1/stabilization.cpp:122-241,436-587,805-850,
 // upwind.cpp:52-80,133-172,381-430,505-575, fv1/diffusion_length.h:47-198.
@@ -21,17 +23,19 @@
 namespace nsb {
 
 // ---- precomputed SCVF geometry table -------------------------------------------------------------
-// record of one (element, ip): [ n[DIM], xip[DIM], ds, pad... | G[d][k] d-major, k padded to even ]
+// record of one (element, ip): [ n[DIM], 0.. (HEAD doubles; slot HEAD-1 is always 0) | gn[k] = G_k . n | G[d][k] d-major ],
+// k padded to even so that every part is 16-byte aligned. Static per mesh: built once in nsb_upload_mesh.
 template <int E> struct GeoRec {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
-    static constexpr int HEAD = (DIM == 3) ? 8 : 4;
+    static constexpr int HEAD = 4, O_ZERO = 3;
     static constexpr int NSHP = (NSH + 1) & ~1;
-    static constexpr int SZ = HEAD + DIM * NSHP;          // doubles, even -> 16-byte aligned records
+    static constexpr int O_GN = HEAD, O_G = HEAD + NSHP;
+    static constexpr int SZ = O_G + DIM * NSHP;           // hex 36, tet 20, quad / tri 16 doubles
 };
 
 template <int E>
 __global__ void geom_kernel(int64_t n_elem, const int32_t* __restrict__ conn, const double* __restrict__ coords,
-                            double* __restrict__ geo)
+                            double* __restrict__ rec, int stride)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP;
     using R = GeoRec<E>;
@@ -47,14 +51,15 @@ __global__ void geom_kernel(int64_t n_elem, const int32_t* __restrict__ conn, co
     }
     IpGeo<E> g;
     ip_geometry<E>(x, ip, g);
-    double* r = geo + i * R::SZ;
+    double* r = rec + i * stride;                          // geometry part of the combined SCVF record
 #pragma unroll
-    for (int d = 0; d < DIM; d++) { r[d] = g.n[d]; r[DIM + d] = g.xip[d]; }
-    if (DIM == 3) { r[6] = g.ds; r[7] = 0.0; }
+    for (int d = 0; d < R::HEAD; d++) r[d] = (d < DIM) ? g.n[d < DIM ? d : 0] : 0.0;
+#pragma unroll
+    for (int k = 0; k < R::NSHP; k++) r[R::O_GN + k] = (k < NSH) ? dotv<DIM>(g.G[k < NSH ? k : 0], g.n) : 0.0;
 #pragma unroll
     for (int d = 0; d < DIM; d++)
 #pragma unroll
-        for (int k = 0; k < R::NSHP; k++) r[R::HEAD + d * R::NSHP + k] = (k < NSH) ? g.G[k < NSH ? k : 0][d] : 0.0;
+        for (int k = 0; k < R::NSHP; k++) r[R::O_G + d * R::NSHP + k] = (k < NSH) ? g.G[k < NSH ? k : 0][d] : 0.0;
 }
 
 // ---- compact per-(element, ip) record written by (A), read by (B) ------------------------------------
@@ -272,9 +277,9 @@ NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, con
 }
 
 template <int E, int STAB, bool EXACT, int BS, int MINB = 3>
-__global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
+__global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m,
                                                       const double* __restrict__ u, const double* __restrict__ s0,
-                                                      const double* __restrict__ s1, double* __restrict__ flux,
+                                                      const double* __restrict__ s1, double* __restrict__ rec,
                                                       int* __restrict__ errflag)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, P = DIM;
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
     }
 
     for (int ip = 0; ip < NIP; ip++) {
-        double* fr = flux + (e * NIP + ip) * FR::SZ;
+        double* fr = rec + (e * NIP + ip) * (R::SZ + FR::SZ) + R::SZ;      // flux part of the combined SCVF record
         const int from = tab::C_EDGE[E][ip][0], to = tab::C_EDGE[E][ip][1];
         double n[DIM], xip[DIM], ds = 0.0, JI[DIM][DIM];
         ip_geometry_col<E, BS>(xs, tid, ip, cen, dnt, n, xip, ds, want_def, JI);
@@ -563,70 +568,112 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
 // ------------------------------------------------------------------------------------------------
 // (B) rows kernel
 // ------------------------------------------------------------------------------------------------
-template <int E> struct RowCfg {
+template <int E, int CHP = 0> struct RowCfg {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, NINC = ET<E>::NINC, NIP = ET<E>::NIP;
-    static constexpr int CH = (DIM == 3) ? 8 : 16;          // adjacent elements per round
+    static constexpr int CH = CHP ? CHP : ((DIM == 3) ? 8 : 16);   // adjacent elements per round
     static constexpr int NREC = CH * NINC;
 };
-template <int E, bool FLOWREC, bool EXACT> struct RowWS {
-    using C = RowCfg<E>;
-    // staged geometry = [n, (pad)] (NH doubles, the first NH of the record) + G[d][k]
-    static constexpr int NH = (C::DIM + 1) & ~1, GS = NH + C::DIM * GeoRec<E>::NSHP;
-    double geo[C::NREC][GS];
-    double flx[C::NREC][FluxRec<E, FLOWREC, EXACT>::SZ];
-    double vol[C::CH];
+// shared-memory stride of a staged record: the lanes of a half-warp read the same field of JP different elements'
+// records (NINC records apart); the stride is padded so that those reads fall into disjoint banks.
+template <int E> constexpr int rows_smem_stride(int rs)
+{
+    constexpr int NSH = ET<E>::NSH, NINC = ET<E>::NINC;
+    if (NSH == 3) return rs;
+    for (int s = rs; s < rs + 32; s += 2) {
+        const int off = (NINC * s * 8) % 128;             // byte offset (mod one bank sweep) between consecutive elements
+        if (NSH == 8 && off == 64) return s;              // 2 elements x 8 corners x 8 B per half-warp
+        if (NSH == 4 && (off == 32 || off == 96)) return s;   // 4 elements x 4 corners x 8 B per half-warp
+    }
+    return rs;
+}
+template <int E, bool FLOWREC, bool EXACT, int CHP = 0> struct RowWS {
+    using C = RowCfg<E, CHP>;
+    // staged SCVF record = [geometry record (GS doubles) | flux record], RS doubles in HBM, SS apart in shared memory
+    static constexpr int GS = GeoRec<E>::SZ, RS = GS + FluxRec<E, FLOWREC, EXACT>::SZ, SS = rows_smem_stride<E>(RS);
+    alignas(16) double rec[C::NREC][SS];
+    unsigned long long bar;         // mbarrier the bulk copies of one round complete on
     int32_t ipx[C::NREC];           // ip | (256 if the node is the `to` corner of the SCVF)
     uint8_t slot[C::CH][8];
 };
-
-NSB_DEV void cp_async16(void* smem_dst, const void* gsrc)
+// block-level tables in front of the per-warp work spaces: shape values at the ips, incidence table, slot rotation
+template <int E> __host__ __device__ constexpr size_t rows_tab_bytes(int max_cnt)
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+    return (sizeof(double) * ET<E>::NIP * ET<E>::NSH + sizeof(int32_t) * ET<E>::NSH * ET<E>::NINC + (size_t)max_cnt + 15) & ~(size_t)15;
 }
-NSB_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
-template <int E, int STAB, bool EXACT>
-__global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, const double* __restrict__ geo,
-                                                          const double* __restrict__ flux, const double* __restrict__ u,
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on a warp-private mbarrier ----
+NSB_DEV unsigned smem_u32(const void* q) { return (unsigned)__cvta_generic_to_shared(q); }
+NSB_DEV void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+NSB_DEV void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+NSB_DEV void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+NSB_DEV void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int E, int STAB, bool EXACT, int CHP = 0, int MINB = 5>
+__global__ void __launch_bounds__(96, MINB) fv1_rows_kernel(KParams p, MeshDev m,
+                                                          const double* __restrict__ rec, const double* __restrict__ u,
                                                           double beta, double* __restrict__ val, double* __restrict__ def,
                                                           unsigned long long* __restrict__ work_counter)
 {
-    using C = RowCfg<E>;
+    using C = RowCfg<E, CHP>;
     constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, L = NSH * NF, NIP = C::NIP;
     constexpr bool FLOW = (STAB == STAB_FLOW);
     using R = GeoRec<E>;
     using FR = FluxRec<E, FLOW, EXACT>;
-    using WS = RowWS<E, FLOW, EXACT>;
-    constexpr int NH = WS::NH, GS = WS::GS;
-    constexpr int GV = GS / 2, FV = FR::SZ / 2, HV = NH / 2;     // 16-byte chunks per staged record
-    static_assert(GV <= 32 && FV <= 32, "record wider than a warp");
+    using WS = RowWS<E, FLOW, EXACT, CHP>;
+    constexpr int GS = WS::GS, RS = WS::RS;
+    constexpr bool BLK = (NF == 4);                              // block-major rotated row accumulator (3-D)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    // block layout: [Ntab NIP*NSH doubles][inc table NSH*NINC ints][per warp: WS | rowacc NF*NF*max_cnt doubles]
+    // block layout: [Ntab NIP*NSH doubles][inc table NSH*NINC ints][rottab max_cnt bytes][per warp: WS | rowacc NF*NF*max_cnt doubles]
     double* Ntab = reinterpret_cast<double*>(smem_raw);
     int32_t* inctab = reinterpret_cast<int32_t*>(smem_raw + sizeof(double) * NIP * NSH);
-    const size_t tab_bytes = (sizeof(double) * NIP * NSH + sizeof(int32_t) * NSH * NINC + 15) & ~(size_t)15;
+    uint8_t* rottab = reinterpret_cast<uint8_t*>(inctab + NSH * NINC);
+    const size_t tab_bytes = rows_tab_bytes<E>(m.max_cnt);
     const size_t per_warp = (sizeof(WS) + sizeof(double) * NF * NF * m.max_cnt + 15) & ~(size_t)15;
     WS& ws = *reinterpret_cast<WS*>(smem_raw + tab_bytes + warp * per_warp);
     double* rowacc = reinterpret_cast<double*>(smem_raw + tab_bytes + warp * per_warp + sizeof(WS));
     for (int i = threadIdx.x; i < NIP * NSH; i += blockDim.x) Ntab[i] = tab::NIPSH[E][i / NSH][i % NSH];
     for (int i = threadIdx.x; i < NSH * NINC; i += blockDim.x)
         inctab[i] = tab::INC[E][i / NINC][i % NINC] | (tab::INC_SIGN[E][i / NINC][i % NINC] < 0 ? 256 : 0);
+    // 3-D row accumulator: one 128-byte block (NF x NF doubles) per column slot, its eight 16-byte chunks rotated by
+    // rot(slot) so that the corners of one element (slots s0 + {0,1,3,4,9,10,12,13} on a structured hex mesh) hit
+    // eight different bank groups in the read-modify-write below; any mesh is handled, only the conflict rate varies.
+    for (int i = threadIdx.x; i < m.max_cnt; i += blockDim.x) rottab[i] = (uint8_t)((i % 3 + 2 * ((i / 3) % 3) + 4 * (i / 9)) & 7);
+    if (lane == 0) mbar_init(&ws.bar, 1);
     __syncthreads();
+    unsigned phase = 0;
     const bool want_jac = p.what & (W_JAC_A | W_JAC_M), want_def = p.what & (W_DEF_A | W_DEF_M | W_RHS);
     const bool jac_a = p.what & W_JAC_A, def_a = p.what & W_DEF_A;
-    // lane = (corner k, function cf) of the element block; per-lane selectors make the accumulate branch-free
-    const int k = (lane < L) ? lane / NF : 0, cf = (lane < L) ? lane - (lane / NF) * NF : 0;
-    const bool isv = cf < DIM;                                   // velocity column / pressure column
-    const int cfv = isv ? cf : 0;
-    const double wv = isv ? 1.0 : 0.0, wp = isv ? 0.0 : 1.0;
-    double msk[DIM];
-#pragma unroll
-    for (int d = 0; d < DIM; d++) msk[d] = (isv && d == cf) ? 1.0 : 0.0;
-    const double nurho_a = p.laplace ? 0.0 : -1.0 * p.visc * p.rho;   // -nu rho G_kd1 n_d2 vanishes for laplace (:346-356)
+    // a defect-only pass needs the flux part of the records only
+    const int cp_off = jac_a ? 0 : GS;
+    const unsigned cp_bytes = (unsigned)sizeof(double) * (jac_a ? RS : RS - GS);
+    // Jacobian accumulate: lane = (jj, k) = corner k of the jj-th of JP adjacent elements processed in parallel; the lane
+    // builds the whole NF x NF block d r(node) / d u(corner k) of its element in registers. Every staged operand is
+    // read by exactly one lane per use (no 4-fold broadcast of the k-indexed coefficients over the column index): the
+    // shared-memory data pipe was the limiter of the lane = (k, cf) mapping (ncu: 91 % of peak wavefronts).
+    constexpr int JP = 32 / NSH;
+    const int jj = lane / NSH, k = lane - jj * NSH;
+    const double xscale = p.laplace ? 0.0 : -1.0 * p.visc * p.rho;    // -nu rho G_kd1 n_d2 vanishes for laplace (:346-356)
     const double nurho_d = -1.0 * p.visc * p.rho;
     const double rho_f = FLOW ? p.rho : 0.0;
+    (void)L; (void)rho_f;
 
     // dynamic work distribution: every warp atomically takes the next node of the traversal order. A static
     // grid-stride assignment lets the persistent warps drift apart, which destroys the L2 reuse of the SCVF
@@ -643,7 +690,9 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
         const int cnt = (int)(m.brow[a + 1] - b0);
         const int rowlen = cnt * NF;
         if (want_jac) for (int i = lane; i < NF * rowlen; i += 32) rowacc[i] = 0.0;
-        double dsum = 0.0, volsum = 0.0;
+        double fsum[NF], vsum = 0.0;                             // per-lane partial defect fluxes / SCV volumes
+#pragma unroll
+        for (int q = 0; q < NF; q++) fsum[q] = 0.0;
         int self_slot = 0;
         for (int64_t qb = q0; qb < q1; qb += CH) {
             const int nj = (int)((q1 - qb) < CH ? (q1 - qb) : CH);
@@ -659,102 +708,173 @@ __global__ void __launch_bounds__(96, 5) fv1_rows_kernel(KParams p, MeshDev m, c
             const int ipx_r = inctab[la_r * NINC + rt];
             const int64_t gi_r = (int64_t)e_r * NIP + (ipx_r & 255);
             if (lane < nrec) ws.ipx[lane] = ipx_r;
-            // ---- asynchronous staging: every 16-byte chunk of every incident record in flight at once ----
-            for (int r = 0; r < nrec; r++) {
-                const int64_t gi = __shfl_sync(0xffffffffu, gi_r, r);
-                if (jac_a && lane < GV)       // chunks [0, HV) = normal, then the gradients (skipping xip / ds)
-                    cp_async16(&ws.geo[r][2 * lane], geo + gi * R::SZ + (lane < HV ? 2 * lane : R::HEAD - NH + 2 * lane));
-                if (lane < FV) cp_async16(&ws.flx[r][2 * lane], flux + gi * FR::SZ + 2 * lane);
-            }
+            // ---- asynchronous staging: one TMA bulk copy per incident SCVF record, all in flight at once ----
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the record area doubles as block staging (generic writes)
+            if (lane == 0) mbar_arrive_expect_tx(&ws.bar, cp_bytes * (unsigned)nrec);
+            __syncwarp();
+            if (lane < nrec) bulk_g2s(&ws.rec[lane][cp_off], rec + gi_r * RS + cp_off, cp_bytes, &ws.bar);
             // scatter slots + the node's SCV volume in the adjacent elements (plain loads, overlapped with the copies)
             if (lane < nj) {
                 const uint8_t* em = m.emap + (int64_t)ad * NSH;
                 if (NSH == 8) *reinterpret_cast<uint2*>(ws.slot[lane]) = __ldg(reinterpret_cast<const uint2*>(em));
                 else if (NSH == 4) *reinterpret_cast<uint32_t*>(ws.slot[lane]) = __ldg(reinterpret_cast<const uint32_t*>(em));
                 else { for (int q = 0; q < NSH; q++) ws.slot[lane][q] = em[q]; }
-                ws.vol[lane] = m.scvvol[ad];
+                vsum += m.scvvol[ad];
             }
             const int sslot = __shfl_sync(0xffffffffu, la_l, 0);
-            cp_async_wait_all();
             __syncwarp();
+            mbar_wait(&ws.bar, phase);
+            phase ^= 1u;
             if (qb == q0) self_slot = ws.slot[0][sslot];
-            // ---- accumulate: lane = (k, cf); fixed order j, t  (add_jac_A_elem :317-594) ----
-            if (want_jac && lane < L) {
-                for (int j = 0; j < nj; j++) {
-                    double acc[NF];
+            // ---- defect: lane r < nrec adds the signed fluxes of its record (reduced over the warp once per node) ----
+            if (def_a && lane < nrec) {
+                const double sgr = (ipx_r & 256) ? -1.0 : 1.0;
 #pragma unroll
-                    for (int rf = 0; rf < NF; rf++) acc[rf] = 0.0;
-                    if (jac_a) {
+                for (int q = 0; q < NF; q++) fsum[q] += sgr * ws.rec[lane][GS + FR::O_F + q];
+            }
+            // ---- accumulate (add_jac_A_elem :317-594): block of (element j, corner k) in registers, fixed order t ----
+            if (want_jac && jac_a) {
+                for (int jb = 0; jb < nj; jb += JP) {
+                    const int j = jb + jj;
+                    const bool act = (jj < JP) && (j < nj);
+                    double B[NF][NF];
+#pragma unroll
+                    for (int rf = 0; rf < NF; rf++)
+#pragma unroll
+                        for (int cf = 0; cf < NF; cf++) B[rf][cf] = 0.0;
+                    if (act) {
+                        double accD = 0.0;
 #pragma unroll
                         for (int t = 0; t < NINC; t++) {
                             const int r = j * NINC + t;
-                            const double* gr = ws.geo[r];
-                            const double* fl = ws.flx[r];
+                            const double* rc = ws.rec[r];
                             const int ipx = ws.ipx[r];
-                            const double sg = (ipx & 256) ? -1.0 : 1.0;
-                            double n[DIM], Gk[DIM];
+                            const double sg = (ipx & 256) ? -p.scale_a : p.scale_a;      // orientation x scaling of the A part
+                            double Yn[DIM], G[DIM], A[DIM];
 #pragma unroll
-                            for (int d = 0; d < DIM; d++) { n[d] = gr[d]; Gk[d] = gr[NH + d * R::NSHP + k]; }
-                            const double gn = dotv<DIM>(Gk, n);
-                            const double inv = fl[FR::O_INV];
-                            const double ncf = gr[cfv];
+                            for (int d = 0; d < DIM; d++) { Yn[d] = sg * rc[d]; G[d] = rc[R::O_G + d * R::NSHP + k]; A[d] = xscale * G[d]; }
+                            if constexpr (EXACT) {               // + e_k U[d1] n[d2]  (:521-549)
+                                const double ek = rc[GS + FR::O_EK + k];
+#pragma unroll
+                                for (int d = 0; d < DIM; d++) A[d] += ek * rc[GS + FR::O_U + d];
+                            }
+                            const double gn = rc[R::O_GN + k];
+                            const double inv = rc[GS + FR::O_INV];           // 0 without stabilisation
+                            const double cK = rc[GS + FR::O_CK + k];
                             const double Nk = Ntab[(ipx & 255) * NSH + k];
-                            // velocity column: X = -nu rho G_k (+ e_k U), Y = n_cf ; pressure column: X = n, Y = N_k (:363-368)
-                            const double Y = wv * ncf + wp * Nk;
-                            const double D = nurho_d * gn + fl[FR::O_DK + k];
-                            double ek = 0.0;
-                            if constexpr (EXACT) ek = fl[FR::O_EK + k];
+                            accD += sg * (nurho_d * gn + rc[GS + FR::O_DK + k]);
 #pragma unroll
                             for (int d1 = 0; d1 < DIM; d1++) {
-                                double X = wv * (nurho_a * Gk[d1]) + wp * n[d1];
-                                if constexpr (EXACT) X += wv * ek * fl[FR::O_U + d1];
-                                acc[d1] += sg * (X * Y + msk[d1] * D);
+#pragma unroll
+                                for (int d2 = 0; d2 < DIM; d2++) B[d1][d2] += A[d1] * Yn[d2];
+                                B[d1][DIM] += Nk * Yn[d1];                   // pressure column (:363-368)
                             }
-                            // continuity row: velocity column (:561-584), pressure column (:586-592, rho cancels)
-                            double cv = fl[FR::O_CK + k] * ncf;
-                            if constexpr (FLOW) {
+                            // continuity row: velocity columns (:561-584), pressure column (:586-592, rho cancels)
+                            if constexpr (!FLOW) {
+#pragma unroll
+                                for (int d2 = 0; d2 < DIM; d2++) B[DIM][d2] += cK * Yn[d2];
+                            } else {
                                 // sum_q sv(q,d2,k) n_q rho = ((sb_k - std.G_k) n_d2 + G_k[d2] (std.n)) inv rho
                                 double sG = 0.0;
 #pragma unroll
-                                for (int d = 0; d < DIM; d++) sG += fl[FR::O_STD + d] * Gk[d];
-                                cv += (gr[NH + cfv * R::NSHP + k] * fl[FR::O_SN] - sG * ncf) * inv * rho_f;
+                                for (int d = 0; d < DIM; d++) sG += rc[GS + FR::O_STD + d] * G[d];
+                                const double ir = inv * rho_f;
+                                const double c0 = cK - sG * ir, c1 = sg * (rc[GS + FR::O_SN] * ir);
+#pragma unroll
+                                for (int d2 = 0; d2 < DIM; d2++) B[DIM][d2] += c0 * Yn[d2] + c1 * G[d2];
                             }
-                            const double cpv = (STAB == STAB_NONE) ? 0.0 : -1.0 * gn * inv;
-                            acc[DIM] += sg * (wv * cv + wp * cpv);
+                            B[DIM][DIM] += gn * (-1.0 * (inv * sg));
                         }
 #pragma unroll
-                        for (int rf = 0; rf < NF; rf++) acc[rf] *= p.scale_a;
+                        for (int d = 0; d < DIM; d++) B[d][d] += accD;
                     }
-                    const int slot = ws.slot[j][k];
+                    // scatter into the row accumulator. The same neighbour may be a corner of several of the JP elements, so
+                    // they take turns; the corners of one element are distinct nodes.
+                    const int ns = (nj - jb) < JP ? (nj - jb) : JP;
+                    if constexpr (BLK) {
+                        // 3-D: every lane parks its block in the (consumed) record area of this group, chunk c of lane l at
+                        // position (c + l) & 7 of a 128-byte line; then all 32 lanes add one element's NSH blocks at a time
+                        constexpr int LPB = 32 / NSH, CPL = 8 / LPB;         // lanes per block, 16-byte chunks per lane
+                        double* stage = ws.rec[jb * NINC];
+                        __syncwarp();
+                        if (act) {
 #pragma unroll
-                    for (int rf = 0; rf < NF; rf++) rowacc[rf * rowlen + slot * NF + cf] += acc[rf];
+                            for (int c = 0; c < 8; c++)
+                                *reinterpret_cast<double2*>(stage + lane * 16 + (((c + lane) & 7) << 1)) =
+                                    make_double2(B[c >> 1][(c & 1) * 2], B[c >> 1][(c & 1) * 2 + 1]);
+                        }
+                        __syncwarp();
+                        const int b = lane / LPB, c0 = (lane - b * LPB) * CPL;
+                        for (int s = 0; s < ns; s++) {
+                            const int slot = ws.slot[jb + s][b];
+                            const int ls = s * NSH + b;                      // lane that produced block b of element s
+                            const double* src = stage + ls * 16;
+                            double* dst = rowacc + slot * 16;
+                            const int rot = rottab[slot];
+#pragma unroll
+                            for (int cc = 0; cc < CPL; cc++) {
+                                const double2 v = *reinterpret_cast<const double2*>(src + (((c0 + cc + ls) & 7) << 1));
+                                double2* q = reinterpret_cast<double2*>(dst + (((c0 + cc + rot) & 7) << 1));
+                                double2 w = *q;
+                                w.x += v.x; w.y += v.y;
+                                *q = w;
+                            }
+                            __syncwarp();
+                        }
+                    } else {
+                        for (int s = 0; s < ns; s++) {
+                            if (act && jj == s) {
+                                double* ra = rowacc + ws.slot[j][k] * NF;
+#pragma unroll
+                                for (int rf = 0; rf < NF; rf++)
+#pragma unroll
+                                    for (int cf = 0; cf < NF; cf++) ra[rf * rowlen + cf] += B[rf][cf];
+                            }
+                            __syncwarp();
+                        }
+                    }
                 }
             }
-            // ---- defect: lane r < nrec contributes its signed fluxes; deterministic butterfly reduction ----
-            if (def_a) {
-                double f[NF];
-#pragma unroll
-                for (int q = 0; q < NF; q++) f[q] = (lane < nrec) ? ((ipx_r & 256) ? -1.0 : 1.0) * ws.flx[lane][FR::O_F + q] : 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int q = 0; q < NF; q++) f[q] += __shfl_xor_sync(0xffffffffu, f[q], o);
-#pragma unroll
-                for (int q = 0; q < NF; q++) if (lane == q) dsum += f[q];
-            }
-            if (lane < NF) for (int j = 0; j < nj; j++) volsum += ws.vol[j];
         }
         __syncwarp();
+        // deterministic butterfly reductions: SCV volume of the node, defect fluxes
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+        const double volsum = vsum;
+        double dsum = 0.0;
+        if (def_a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int q = 0; q < NF; q++) fsum[q] += __shfl_xor_sync(0xffffffffu, fsum[q], o);
+#pragma unroll
+            for (int q = 0; q < NF; q++) if (lane == q) dsum = fsum[q];
+        }
         if (want_jac) {
-            if ((p.what & W_JAC_M) && lane < DIM) rowacc[lane * rowlen + self_slot * NF + lane] += p.scale_m * volsum * p.rho;
+            if ((p.what & W_JAC_M) && lane < DIM) {
+                const int pos = BLK ? self_slot * (NF * NF) + ((((lane * 2 + (lane >> 1)) + rottab[self_slot]) & 7) << 1) + (lane & 1)
+                                    : lane * rowlen + self_slot * NF + lane;
+                rowacc[pos] += p.scale_m * volsum * p.rho;
+            }
             __syncwarp();
             double* out = val + b0 * (NF * NF);
-            const int tot = NF * rowlen;
-            if (beta == 0.0) {
-                if ((NF * NF) % 2 == 0) {
-                    for (int i = 2 * lane; i < tot; i += 64) __stcs(reinterpret_cast<double2*>(out + i), make_double2(rowacc[i], rowacc[i + 1]));
-                } else for (int i = lane; i < tot; i += 32) __stcs(out + i, rowacc[i]);
-            } else for (int i = lane; i < tot; i += 32) out[i] = beta * out[i] + rowacc[i];
+            if constexpr (BLK) {
+                // un-rotate: CSR row rf of the node = [slot][cf]; a lane moves the 16-byte chunk (slot, rf, column pair cp)
+#pragma unroll
+                for (int rf = 0; rf < NF; rf++) {
+                    double2* orow = reinterpret_cast<double2*>(out + rf * rowlen);
+                    for (int i = lane; i < 2 * cnt; i += 32) {
+                        const int slot = i >> 1, cp = i & 1;
+                        const double2 v = *reinterpret_cast<const double2*>(rowacc + slot * (NF * NF) + (((rf * 2 + cp + rottab[slot]) & 7) << 1));
+                        if (beta == 0.0) __stcs(orow + i, v);
+                        else { double2 o = orow[i]; o.x = beta * o.x + v.x; o.y = beta * o.y + v.y; orow[i] = o; }
+                    }
+                }
+            } else {
+                const int tot = NF * rowlen;
+                if (beta == 0.0) for (int i = lane; i < tot; i += 32) __stcs(out + i, rowacc[i]);
+                else for (int i = lane; i < tot; i += 32) out[i] = beta * out[i] + rowacc[i];
+            }
         }
         if (want_def && lane < NF) {
             double d = def_a ? dsum : 0.0;

@@ -51,7 +51,8 @@ struct nsb_ctx {
     std::vector<int64_t> h_color_ptr;
     // device
     int32_t *d_conn = nullptr, *d_adj = nullptr, *d_color_order = nullptr, *d_esides = nullptr, *d_node_order = nullptr;
-    double *d_coords = nullptr, *d_scvvol = nullptr, *d_geo = nullptr, *d_flux = nullptr;
+    double *d_coords = nullptr, *d_scvvol = nullptr, *d_rec = nullptr;
+    size_t rec_bytes = 0; int rec_stride = 0;     // combined SCVF record table [geometry | flux] of the owner-computes path
     int64_t *d_brow = nullptr, *d_adj_ptr = nullptr;
     uint8_t *d_emap = nullptr;
     FvcrDev fvcr{};
@@ -142,11 +143,11 @@ static void fvcr_free(FvcrDev& f)
 static void free_mesh(nsb_ctx* c)
 {
     cudaFree(c->d_conn); cudaFree(c->d_adj); cudaFree(c->d_color_order); cudaFree(c->d_esides); cudaFree(c->d_node_order); cudaFree(c->d_coords);
-    cudaFree(c->d_scvvol); cudaFree(c->d_geo); cudaFree(c->d_flux); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
+    cudaFree(c->d_scvvol); cudaFree(c->d_rec); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
     cudaFree(c->d_u); cudaFree(c->d_s0); cudaFree(c->d_s1); cudaFree(c->d_val); cudaFree(c->d_def);
     cudaFree(c->d_jloc); cudaFree(c->d_dloc);
     fvcr_free(c->fvcr);
-    c->d_conn = c->d_adj = c->d_color_order = c->d_esides = c->d_node_order = nullptr; c->d_coords = c->d_scvvol = c->d_geo = c->d_flux = nullptr;
+    c->d_conn = c->d_adj = c->d_color_order = c->d_esides = c->d_node_order = nullptr; c->d_coords = c->d_scvvol = c->d_rec = nullptr; c->rec_bytes = 0; c->rec_stride = 0;
     c->d_brow = c->d_adj_ptr = nullptr; c->d_emap = nullptr;
     c->d_u = c->d_s0 = c->d_s1 = c->d_val = c->d_def = c->d_jloc = c->d_dloc = nullptr;
     c->mesh_ready = false;
@@ -336,20 +337,6 @@ extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_n
     { std::vector<int32_t> zo; morton_order(n_node, dim, coords, zo); CUDA_TRY(c, upload(&c->d_node_order, zo.data(), zo.size())); }
     CUDA_TRY(c, cudaMalloc(&c->d_scvvol, (size_t)n_elem * nsh * sizeof(double)));
     CUDA_TRY(c, launch_scvvol(c));
-    {   // precomputed SCVF geometry table (normals, ips, global shape gradients) for the owner-computes kernel
-        size_t rec = 0;
-        switch (elem) { case 0: rec = geom_record_doubles_0(); break; case 1: rec = geom_record_doubles_1(); break;
-                        case 2: rec = geom_record_doubles_2(); break; default: rec = geom_record_doubles_3(); }
-        static const int kNIP[4] = {3, 4, 6, 12};
-        CUDA_TRY(c, cudaMalloc(&c->d_geo, (size_t)n_elem * kNIP[elem] * rec * sizeof(double)));
-        cudaError_t ge;
-        switch (elem) { case 0: ge = launch_geom_0(n_elem, c->d_conn, c->d_coords, c->d_geo, c->stream); break;
-                        case 1: ge = launch_geom_1(n_elem, c->d_conn, c->d_coords, c->d_geo, c->stream); break;
-                        case 2: ge = launch_geom_2(n_elem, c->d_conn, c->d_coords, c->d_geo, c->stream); break;
-                        default: ge = launch_geom_3(n_elem, c->d_conn, c->d_coords, c->d_geo, c->stream); }
-        c->launches++;
-        CUDA_TRY(c, ge);
-    }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->h_brow.swap(g.brow); c->h_bcol.swap(g.bcol);
     c->mesh_ready = true;
@@ -476,14 +463,31 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
 {
     const MeshDev m = mesh_view(c);
     cudaError_t e;
-    if (!c->d_flux) {       // per-(element, ip) flux records exchanged between the flux and the rows kernel
-        size_t rec = 0;
-        switch (c->elem) { case 0: rec = flux_record_doubles_0(); break; case 1: rec = flux_record_doubles_1(); break;
-                           case 2: rec = flux_record_doubles_2(); break; default: rec = flux_record_doubles_3(); }
-        static const int kNIP[4] = {3, 4, 6, 12};
-        CUDA_TRY(c, cudaMalloc(&c->d_flux, (size_t)c->n_elem * kNIP[c->elem] * rec * sizeof(double)));
+    {   // combined per-(element, ip) record table: static SCVF geometry | flux record written by the flux kernel.
+        // The stride depends on the stabilisation (FLOW) and Jacobian flavour (exact Newton): (re)built on change.
+        const bool flow = k.stab == STAB_FLOW, exact = !k.stokes && k.exact_jac != 0.0;
+        int stride = 0;
+        switch (c->elem) { case 0: stride = scvf_record_doubles_0(flow, exact); break; case 1: stride = scvf_record_doubles_1(flow, exact); break;
+                           case 2: stride = scvf_record_doubles_2(flow, exact); break; default: stride = scvf_record_doubles_3(flow, exact); }
+        if (stride != c->rec_stride) {
+            static const int kNIP[4] = {3, 4, 6, 12};
+            const size_t need = (size_t)c->n_elem * kNIP[c->elem] * stride * sizeof(double);
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            if (need > c->rec_bytes) {
+                cudaFree(c->d_rec); c->d_rec = nullptr; c->rec_bytes = 0; c->rec_stride = 0;
+                CUDA_TRY(c, cudaMalloc(&c->d_rec, need));
+                c->rec_bytes = need;
+            }
+            switch (c->elem) { case 0: e = launch_geom_0(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); break;
+                               case 1: e = launch_geom_1(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); break;
+                               case 2: e = launch_geom_2(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); break;
+                               default: e = launch_geom_3(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); }
+            c->launches++;
+            CUDA_TRY(c, e);
+            c->rec_stride = stride;
+        }
     }
-#define NSB_GO(fn) fn(k, m, c->d_geo, c->d_flux, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter)
+#define NSB_GO(fn) fn(k, m, c->d_rec, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter)
     switch (c->elem) { case 0: e = NSB_GO(launch_gather_0); break; case 1: e = NSB_GO(launch_gather_1); break;
                        case 2: e = NSB_GO(launch_gather_2); break; default: e = NSB_GO(launch_gather_3); }
 #undef NSB_GO
