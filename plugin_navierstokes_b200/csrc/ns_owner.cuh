@@ -121,24 +121,37 @@ NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const doubl
     } else {
         const double dn2 = dotv<3>(dir, dir);
         constexpr int TPS = (E == E_HEX) ? 2 : 1;
-        for (int i = 0; i < NSIDE * TPS; i++) {
-            const int s = i / TPS, kk = i - s * TPS;
-            const int p0 = tab::C_SIDE[E][s][0], p1 = tab::C_SIDE[E][s][1 + kk], p2 = tab::C_SIDE[E][s][2 + kk];
-            double e1[3], e2[3], r[3], nrm[3], q[3];
+        const unsigned amask = __activemask();
+        for (int s = 0; s < NSIDE; s++) {
+            // a quadrilateral side is cut as the triangles (p0,p1,p2), (p0,p2,p3): both share r = from - x(p0), q = r x dir
+            // and the diagonal edge; evaluating them together halves the dependent chains (same operations per value)
+            const int p0 = tab::C_SIDE[E][s][0];
+            double ed[TPS + 1][3], r[3], q[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 const double x0 = NSB_COL(xs, p0 * 3 + d);
-                e1[d] = NSB_COL(xs, p1 * 3 + d) - x0; e2[d] = NSB_COL(xs, p2 * 3 + d) - x0; r[d] = from[d] - x0;
+                r[d] = from[d] - x0;
+#pragma unroll
+                for (int j = 0; j <= TPS; j++) ed[j][d] = NSB_COL(xs, tab::C_SIDE[E][s][1 + j] * 3 + d) - x0;
             }
-            cross3(nrm, e1, e2);
-            const double det = -dotv<3>(dir, nrm);
-            const double t_n = dotv<3>(r, nrm);
             cross3(q, r, dir);
-            const double b1n = dotv<3>(e2, q), b2n = -dotv<3>(e1, q);
-            const double sg = det > 0.0 ? 1.0 : -1.0, ad = fabs(det);
-            const bool hit = !found && det * det > (S * S) * dn2 * dotv<3>(nrm, nrm) &&
-                             b1n * sg >= -S * ad && b2n * sg >= -S * ad && (b1n + b2n) * sg <= (1.0 + S) * ad && t_n * sg <= 0.0;
-            if (hit) { found = true; best = i; tn = t_n; n1 = b1n; n2 = b2n; bdet = det; }
+            double eq[TPS + 1];
+#pragma unroll
+            for (int j = 0; j <= TPS; j++) eq[j] = dotv<3>(ed[j], q);
+#pragma unroll
+            for (int kk = 0; kk < TPS; kk++) {
+                double nrm[3];
+                cross3(nrm, ed[kk], ed[kk + 1]);
+                const double det = -dotv<3>(dir, nrm);
+                const double t_n = dotv<3>(r, nrm);
+                const double b1n = eq[kk + 1], b2n = -eq[kk];
+                const double sg = det > 0.0 ? 1.0 : -1.0, ad = fabs(det);
+                const bool hit = !found && det * det > (S * S) * dn2 * dotv<3>(nrm, nrm) &&
+                                 b1n * sg >= -S * ad && b2n * sg >= -S * ad && (b1n + b2n) * sg <= (1.0 + S) * ad && t_n * sg <= 0.0;
+                if (hit) { found = true; best = s * TPS + kk; tn = t_n; n1 = b1n; n2 = b2n; bdet = det; }
+            }
+            // the first hit wins (sides in reference order): stop as soon as every element of the warp has one
+            if (__all_sync(amask, found)) break;
         }
         if (!found) return false;
         const double t = tn / bdet, b1 = n1 / bdet, b2 = n2 / bdet;

@@ -20,8 +20,12 @@ def entry_errors(a, b, rowptr=None):
         return np.abs(a).max(), np.abs(a).max()
     diff = np.abs(a - b)
     if rowptr is not None:
-        rowmax = np.maximum.reduceat(np.abs(b), rowptr[:-1])
-        s = np.repeat(rowmax, np.diff(rowptr))
+        rowptr = np.asarray(rowptr)
+        lens = np.diff(rowptr)
+        rowmax = np.zeros(lens.shape[0])
+        ne = lens > 0                                            # reduceat cannot handle empty rows (unreferenced nodes)
+        rowmax[ne] = np.maximum.reduceat(np.abs(b), rowptr[:-1][ne])
+        s = np.repeat(rowmax, lens)
     else:
         s = np.full(b.shape, gmax)
     denom = np.maximum(np.abs(b), 1e-2 * np.maximum(s, 1e-300))

@@ -178,3 +178,41 @@ def test_device_pointer_path_and_beta():
         disc.check_errors()
         assert np.allclose(dv2.cpu().numpy(), 2 * hv, rtol=1e-12, atol=1e-12 * np.abs(hv).max())
         assert np.allclose(dd2.cpu().numpy(), 2 * hd, rtol=1e-12, atol=1e-12 * np.abs(hd).max())
+
+
+@pytest.mark.parametrize("elem", ["hex", "tri"])
+@pytest.mark.parametrize("mode", ["gather", "colored", "atomic"])
+def test_unreferenced_nodes_and_ragged_valence(ora, elem, mode):
+    """Nodes no element touches (empty CSR rows, zero defect) in the middle and at the end of the numbering, and a mesh
+    with a removed element block (ragged node valence): the owner-computes scheduler must neither skip nor stall."""
+    coords, conn, u = parity.make_case(elem, SIZES[elem], seed=5)
+    dim = coords.shape[1]
+    nf = dim + 1
+    keep = np.ones(conn.shape[0], bool)
+    keep[3:9] = False                                           # punch a hole
+    conn = conn[keep]
+    # insert unreferenced nodes: one in the middle of the numbering, two at the end
+    mid = coords.shape[0] // 2
+    coords2 = np.concatenate([coords[:mid], [[9.0] * dim], coords[mid:], [[8.0] * dim, [7.0] * dim]])
+    conn2 = np.where(conn >= mid, conn + 1, conn).astype(np.int32)
+    u = u.reshape(-1, nf)
+    u2 = np.concatenate([u[:mid], np.full((1, nf), 0.5), u[mid:], np.full((2, nf), -0.25)])
+    used = np.zeros(coords2.shape[0], bool)
+    used[conn2.ravel()] = True
+    assert (~used).sum() >= 3
+    disc = pkg.NavierStokesFV1(FCTS[dim], "Inner")
+    parity.configure(disc, upwind="lps", stab="fields", diff="raw")
+    disc.set_grid(elem, conn2, coords2)
+    rp, ci = disc.csr()
+    rowptr, colind = ora.fv1_csr(ora.ELEM[elem], conn2, coords2.shape[0])
+    assert np.array_equal(rp, rowptr) and np.array_equal(ci, colind)
+    p = ora.make_params(elem=elem, upwind="lps", stab="fields", diff_len="raw", kin_visc=1e-2, density=1.0)
+    what = capi.JAC_A | capi.DEF_A | capi.JAC_M | capi.DEF_M
+    ov, od = ora.assemble(p, conn2, coords2, u2.reshape(-1), rowptr, colind, what, scale_a=0.7, scale_m=1.3)
+    gv, gd = disc.assemble(what, u2.reshape(-1), scale_a=0.7, scale_m=1.3, scatter_mode=MODES[mode])
+    eg, ee = parity.entry_errors(gv, ov, rowptr)
+    assert eg < TOL and ee < TOL
+    eg, ee = parity.entry_errors(gd, od)
+    assert eg < TOL and ee < TOL
+    assert np.all(gd.reshape(-1, nf)[~used] == 0.0)
+    disc.close()
