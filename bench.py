@@ -49,15 +49,47 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    """samples SM clocks / throttle reasons while the timed region runs: an NVML polling thread (5 ms period, starts
+    instantly, so even a 100 ms timed region gets samples); falls back to `nvidia-smi -lms` when NVML is unavailable"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index=0):
         self.index, self.samples, self.proc = index, [], None
+        self.nvml, self.handle, self.run, self.thread, self.sm, self.mx, self.reasons = None, None, False, None, [], None, set()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for bit, name in self.BITS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -71,6 +103,11 @@ class ClockSampler:
             self.samples.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.run = False
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -89,7 +126,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def build_problem(n, rank=0, world=1):
