@@ -279,5 +279,27 @@ class InterfaceExchange:
                 if dfc is not None:
                     dfc[p["didx_t"]] = 0.0
 
+    def copy_from_owner(self, vec):
+        """owner -> copies over the same dof lists in the reverse direction (additive/unique -> consistent): after the
+        call every rank's copies of a shared node hold the owner's `nf` values. Used to make the input state `u`
+        consistent before an assembly and to turn the summed defect into a consistent vector."""
+        dist = self.dist
+        ops, nbuf = [], []
+        for p in self.plans:
+            nm, nd = p["midx"].size, p["didx"].size
+            buf = p["buf"][nm:nm + nd]
+            if p["role"] == "recv":                                       # the lower rank owns the rows of this pair
+                self._pack(p["didx_t"], vec, buf)
+                ops.append(dist.P2POp(dist.isend, buf, p["peer"]))
+            else:
+                ops.append(dist.P2POp(dist.irecv, buf, p["peer"]))
+            nbuf.append(buf)
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for p, buf in zip(self.plans, nbuf):
+            if p["role"] == "send" and p["didx"].size:
+                vec[p["didx_t"]] = buf
+
     def bytes_per_exchange(self):
         return int(sum(8 * (p["midx"].size + p["didx"].size) for p in self.plans if p["role"] == "send"))

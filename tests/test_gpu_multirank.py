@@ -41,9 +41,11 @@ def _worker(rank, world, port, q):
         vals, dfc = disc.assemble(capi.JAC_A | capi.DEF_A, ud)
         ex = partition.InterfaceExchange(disc, dict(l2g=l2g, boundary=None), torch.device("cuda", rank))
         ex.sum_to_owner(vals, dfc)
+        cons = dfc.clone()
+        ex.copy_from_owner(cons)                                 # unique -> consistent over NCCL
         torch.cuda.synchronize()
         disc.check_errors()
-        q.put((rank, l2g, dfc.cpu().numpy(), ex.owner.copy(), ex.launches))
+        q.put((rank, l2g, dfc.cpu().numpy(), ex.owner.copy(), ex.launches, cons.cpu().numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -69,7 +71,8 @@ def test_two_gpu_defect_matches_single_domain(ora):
     rowptr, colind = ora.fv1_csr(ora.HEX, conn, coords.shape[0])
     _, gd = ora.assemble(prm, conn, coords, u, rowptr, colind, ora.DEF_A)
     gd = gd.reshape(-1, 4)
-    for rank, l2g, d, own, launches in res:
+    for rank, l2g, d, own, launches, cons in res:
         mine = own == rank
         assert np.abs(d.reshape(-1, 4)[mine] - gd[l2g[mine]]).max() < 1e-12 * np.abs(gd).max()
+        assert np.abs(cons.reshape(-1, 4) - gd[l2g]).max() < 1e-12 * np.abs(gd).max()     # every copy, after copy_from_owner
     assert sum(r[4] for r in res) > 0

@@ -42,8 +42,10 @@ def _worker(rank, world, port, elem, n, q):
         ex = partition.InterfaceExchange(None, dict(l2g=l2g, boundary=None), device=None, nf=nf, csr=(rowptr, colind))
         tv, td = torch.from_numpy(vals), torch.from_numpy(dfc)
         ex.sum_to_owner(tv, td)
+        tc = td.clone()
+        ex.copy_from_owner(tc)                                   # unique -> consistent
         q.put((rank, l2g, rowptr, colind, add_vals, add_dfc, tv.numpy().copy(), td.numpy().copy(), ex.owner.copy(),
-               {k: v[1] for k, v in ex.shared.items()}, ex.bytes_per_exchange()))
+               {k: v[1] for k, v in ex.shared.items()}, ex.bytes_per_exchange(), tc.numpy().copy()))
     finally:
         dist.destroy_process_group()
 
@@ -96,6 +98,9 @@ def test_interface_summation_over_gloo(ora, elem, n, world):
         mine = own == rank
         d_local = r[7].reshape(-1, nf)
         assert np.abs(d_local[mine] - gd.reshape(-1, nf)[l2g[mine]]).max() < 1e-12 * np.abs(gd).max()
+    # (2b) after copy_from_owner every copy of every node holds the single-domain defect (consistent storage)
+    for r in res:
+        assert np.abs(r[11].reshape(-1, nf) - gd.reshape(-1, nf)[r[1]]).max() < 1e-12 * np.abs(gd).max()
     # (3) matrix: on the owner, a block (a, b) whose two nodes are shared with the same set of ranks carries the full sum
     holders = [set() for _ in range(coords.shape[0])]
     for r in res:
