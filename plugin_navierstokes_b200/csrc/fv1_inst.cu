@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include "ns_owner.cuh"
+#include "ns_split.cuh"
 #include "ns_launch.h"
 #ifndef NSB_ELEM
 #error "compile with -DNSB_ELEM=0..3"
@@ -103,6 +104,57 @@ cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
         default: return gather_t<STAB_NONE, false>(NSB_GFWD);
     }
 }
+// ---- split path (ns_split.cuh): lean flux records + static table J0 ----
+template <int STAB, int CHP, int MINB>
+static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
+{
+    constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
+    cudaError_t e;
+    if (k.what & (W_JAC_A | W_DEF_A)) {
+        const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * BS + NIP * NSH * DIM + NIP * NSH);
+        auto ka = fv1_flux_kernel<E, STAB, false, BS, 2, true>;
+        e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+        if (e != cudaSuccess) return e;
+        ka<<<(unsigned)((m.n_elem + BS - 1) / BS), BS, smem_a, st>>>(k, m, u, s0, s1, rec, d_err);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    static const int WPB = [] { const char* ev = getenv("NSB_SPLIT_WPB"); const int v = ev ? atoi(ev) : 2; return (v >= 1 && v <= 2) ? v : 2; }();
+    constexpr size_t tab_bytes = (sizeof(int32_t) * NSH * ET<E>::NINC + 15) & ~(size_t)15;
+    const size_t smem = tab_bytes + split_warp_bytes<E, CHP>(m.max_cnt) * WPB;
+    auto kb = fv1_rows_split_kernel<E, CHP, MINB>;
+    e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, WPB * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
+    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, rec, j0, u, beta, val, def, work_counter);
+    return cudaGetLastError();
+}
+cudaError_t NSB_CAT(launch_split_, NSB_ELEM)(NSB_GATHER_ARGS, const double* j0)
+{
+    static const int CHV = [] { const char* ev = getenv("NSB_SPLIT_CH"); return ev ? atoi(ev) : 4; }();
+    static const int MINBV = [] { const char* ev = getenv("NSB_SPLIT_MINB"); return ev ? atoi(ev) : 12; }();
+#define NSB_SPLIT_GO(CH, MB) (k.stab == STAB_FIELDS ? split_t<STAB_FIELDS, CH, MB>(NSB_GFWD, j0) : split_t<STAB_NONE, CH, MB>(NSB_GFWD, j0))
+    if constexpr (E == 3) {
+        if (CHV == 4) return MINBV == 12 ? NSB_SPLIT_GO(4, 12) : NSB_SPLIT_GO(4, 8);
+        if (MINBV == 12) return NSB_SPLIT_GO(0, 12);
+    }
+    return MINBV == 12 ? NSB_SPLIT_GO(0, 12) : NSB_SPLIT_GO(0, 8);
+#undef NSB_SPLIT_GO
+}
+cudaError_t NSB_CAT(launch_j0_, NSB_ELEM)(const MeshDev& m, int laplace, double* j0, cudaStream_t st, int sm_count)
+{
+    const int64_t nblk = std::min<int64_t>((m.n_node + 3) / 4, (int64_t)sm_count * 16);
+    fv1_j0_kernel<E><<<(unsigned)nblk, 128, 0, st>>>(m, laplace, j0);
+    return cudaGetLastError();
+}
+int NSB_CAT(lean_record_doubles_, NSB_ELEM)() { return LeanRec<E>::SZ; }
+
 // doubles per combined SCVF record [geometry | flux] for the given stabilisation / Jacobian flavour
 int NSB_CAT(scvf_record_doubles_, NSB_ELEM)(bool flow, bool exact)
 {

@@ -289,7 +289,10 @@ NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, con
     }
 }
 
-template <int E, int STAB, bool EXACT, int BS, int MINB = 3>
+// lean SCVF record of the split path (ns_split.cuh): [F | n | cK | dK | pK = -G_k.n / diag]
+template <int E> struct LeanRec;
+
+template <int E, int STAB, bool EXACT, int BS, int MINB = 3, bool LEAN = false>
 __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m,
                                                       const double* __restrict__ u, const double* __restrict__ s0,
                                                       const double* __restrict__ s1, double* __restrict__ rec,
@@ -299,6 +302,10 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
     constexpr bool FLOW = (STAB == STAB_FLOW);
     using R = GeoRec<E>;
     using FR = FluxRec<E, FLOW, EXACT>;
+    static_assert(!LEAN || (!FLOW && !EXACT), "the split path covers FIELDS / no stabilisation with the fixed-point Jacobian");
+    constexpr int NSHP = (NSH + 1) & ~1;
+    constexpr int L_N = NF, L_CK = (NF + DIM + 1) & ~1, L_DK = L_CK + NSHP, L_PK = L_DK + NSHP;   // = LeanRec<E> offsets
+    constexpr int LRSZ = (L_PK + NSHP + 3) & ~3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* xs = reinterpret_cast<double*>(smem_raw);            // [NSH*DIM][BS]
     double* vs = xs + NSH * DIM * BS;                            // [NSH][BS]
@@ -356,10 +363,11 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
     }
 
     for (int ip = 0; ip < NIP; ip++) {
-        double* fr = rec + (e * NIP + ip) * (R::SZ + FR::SZ) + R::SZ;      // flux part of the combined SCVF record
+        double* fr = LEAN ? rec + (e * NIP + ip) * LRSZ                     // lean record of the split path
+                          : rec + (e * NIP + ip) * (R::SZ + FR::SZ) + R::SZ;      // flux part of the combined SCVF record
         const int from = tab::C_EDGE[E][ip][0], to = tab::C_EDGE[E][ip][1];
         double n[DIM], xip[DIM], ds = 0.0, JI[DIM][DIM];
-        ip_geometry_col<E, BS>(xs, tid, ip, cen, dnt, n, xip, ds, want_def, JI);
+        ip_geometry_col<E, BS>(xs, tid, ip, cen, dnt, n, xip, ds, want_def || (LEAN && want_jac), JI);
         double N[NSH];
 #pragma unroll
         for (int k = 0; k < NSH; k++) N[k] = Nt[ip * NSH + k];
@@ -446,15 +454,43 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
                 if (!p.stokes) { D = up[k] * cw; if (p.peclet) D += cpe * N[k]; }
                 dk[k] = D;
             }
+            constexpr int W_CK = LEAN ? L_CK : FR::O_CK, W_DK = LEAN ? L_DK : FR::O_DK;
             if constexpr (NSH % 2 == 0) {
 #pragma unroll
                 for (int k = 0; k < NSH; k += 2) {
-                    *reinterpret_cast<double2*>(fr + FR::O_CK + k) = make_double2(ck[k], ck[k + 1]);
-                    *reinterpret_cast<double2*>(fr + FR::O_DK + k) = make_double2(dk[k], dk[k + 1]);
+                    *reinterpret_cast<double2*>(fr + W_CK + k) = make_double2(ck[k], ck[k + 1]);
+                    *reinterpret_cast<double2*>(fr + W_DK + k) = make_double2(dk[k], dk[k + 1]);
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < NSH; k++) { fr[FR::O_CK + k] = ck[k]; fr[FR::O_DK + k] = dk[k]; }
+                for (int k = 0; k < NSH; k++) { fr[W_CK + k] = ck[k]; fr[W_DK + k] = dk[k]; }
+            }
+            if constexpr (LEAN) {
+                // pressure column of the continuity row (:586-592): -G_k.n / diag, with G_k.n = dnt_k . (JI^T n)
+                double mv[DIM], pk[NSH];
+#pragma unroll
+                for (int i = 0; i < DIM; i++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) s += JI[d][i] * n[d];
+                    mv[i] = s * (-1.0 * inv);
+                }
+#pragma unroll
+                for (int k = 0; k < NSH; k++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < DIM; i++) s += dnt[(ip * NSH + k) * DIM + i] * mv[i];
+                    pk[k] = s;
+                }
+                if constexpr (NSH % 2 == 0) {
+#pragma unroll
+                    for (int k = 0; k < NSH; k += 2) *reinterpret_cast<double2*>(fr + L_PK + k) = make_double2(pk[k], pk[k + 1]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NSH; k++) fr[L_PK + k] = pk[k];
+                }
+#pragma unroll
+                for (int d = 0; d < DIM; d++) fr[L_N + d] = n[d];
             }
             if constexpr (EXACT) {
                 const bool exact = !p.stokes && p.exact_jac != 0.0;
@@ -468,7 +504,7 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
                 for (int d = 0; d < DIM; d++) fr[FR::O_U + d] = U[d];
             }
         }
-        fr[FR::O_INV] = inv;
+        if constexpr (!LEAN) fr[FR::O_INV] = inv;
         if constexpr (FLOW) {
             fr[FR::O_SN] = sn;
 #pragma unroll

@@ -1,0 +1,313 @@
+// ns_split.cuh -- owner-computes FV1 assembly with the Jacobian split into a STATIC and a STATE part
+// (FIELDS / no stabilisation, fixed-point Jacobian; FLOW and exact-Newton keep the general rows kernel of ns_owner.cuh).
+//
+// For constant viscosity / density the local Jacobian of add_jac_A_elem (fv1/navier_stokes_fv1.cpp:317-594) is
+//     J = nu rho * S  +  P  +  state part,
+//   S : diffusion  -(G_k,d1 n_d2 [unless laplace] + delta_d1d2 G_k.n)      (:336-356)   geometry only
+//   P : pressure gradient  N_k n_d1 in the pressure column                  (:363-368)   geometry only
+//   state part : convective diagonal dK_k (:430-468), continuity row cK_k n_d2 (:561-584) and -G_k.n / diag (:586-592).
+// S and P are assembled ONCE per mesh into the table J0 (momentum rows only, same slot order as the CSR rows).
+// Every pass then moves, per SCVF, a lean 256-byte record (hex) instead of the 480-byte geometry + flux record, and
+// accumulates 5 instead of 16 values per (node, element, corner):
+//
+//   fv1_j0_kernel          once per mesh: warp per node, deterministic (adjacency order), J0[node][rf < DIM][slot][cf]
+//   fv1_flux_kernel<LEAN>  (ns_owner.cuh) writes [F | n | cK | dK | pK = -G_k.n / diag] per SCVF
+//   fv1_rows_split_kernel  warp per node: TMA bulk copies of the node's J0 rows and of the incident lean records,
+//                          lane = (element, corner) sums its NINC SCVFs in registers, per-slot accumulators in shared
+//                          memory, rows written once:  out = {nu rho, 1} * scale_a * J0 + state part (+ lumped mass).
+#pragma once
+#include "ns_owner.cuh"
+
+namespace nsb {
+
+template <int E> struct LeanRec {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1;
+    static constexpr int NSHP = (NSH + 1) & ~1;
+    static constexpr int O_F = 0, O_N = NF, HEAD = (NF + DIM + 1) & ~1;
+    static constexpr int O_CK = HEAD, O_DK = O_CK + NSHP, O_PK = O_DK + NSHP, RAW = O_PK + NSHP;
+    static constexpr int SZ = (RAW + 3) & ~3;              // hex 32 doubles = 256 B; tet / quad / tri 20 doubles = 160 B
+};
+
+// ---- static part, once per mesh ---------------------------------------------------------------------
+// J0 block row of node a: [rf < DIM][slot < cnt][cf < NF] at offset DIM*NF*brow[a]:
+//   cf < DIM : sum over incident SCVFs of  -sign * (G_k[rf] n[cf] (unless laplace) + delta_rf,cf G_k.n)   (to be scaled by nu rho)
+//   cf = DIM : sum of  sign * N_k n[rf]
+template <int E>
+__global__ void __launch_bounds__(128) fv1_j0_kernel(MeshDev m, int laplace, double* __restrict__ j0)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, NINC = ET<E>::NINC;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t a = warp0; a < m.n_node; a += nwarp) {
+        const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1], b0 = m.brow[a];
+        const int rowlen = (int)(m.brow[a + 1] - b0) * NF;
+        double* out = j0 + b0 * (DIM * NF);
+        for (int64_t q = q0; q < q1; q++) {                     // adjacency order (ascending element index): deterministic
+            const int32_t ad = m.adj[q];
+            const int e = ad / NSH, la = ad - e * NSH;
+            double x[NSH * DIM];
+#pragma unroll
+            for (int k = 0; k < NSH; k++) {
+                const int64_t nd = m.conn[(int64_t)e * NSH + k];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) x[k * DIM + d] = m.coords[nd * DIM + d];
+            }
+            double S[DIM][NF];
+#pragma unroll
+            for (int rf = 0; rf < DIM; rf++)
+#pragma unroll
+                for (int cf = 0; cf < NF; cf++) S[rf][cf] = 0.0;
+            for (int t = 0; t < NINC; t++) {
+                const int ip = tab::INC[E][la][t];
+                const double sg = (double)tab::INC_SIGN[E][la][t];
+                IpGeo<E> g;
+                ip_geometry<E>(x, ip, g);
+                double Gk[DIM], Nk = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) Gk[d] = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < NSH; kk++)
+                    if (kk == lane) {
+                        Nk = g.N[kk];
+#pragma unroll
+                        for (int d = 0; d < DIM; d++) Gk[d] = g.G[kk][d];
+                    }
+                const double gn = dotv<DIM>(Gk, g.n);
+#pragma unroll
+                for (int rf = 0; rf < DIM; rf++) {
+                    if (!laplace) {
+#pragma unroll
+                        for (int cf = 0; cf < DIM; cf++) S[rf][cf] -= Gk[rf] * (sg * g.n[cf]);
+                    }
+                    S[rf][rf] -= sg * gn;
+                    S[rf][DIM] += Nk * (sg * g.n[rf]);
+                }
+            }
+            if (lane < NSH) {
+                const int slot = m.emap[(int64_t)ad * NSH + lane];
+#pragma unroll
+                for (int rf = 0; rf < DIM; rf++)
+#pragma unroll
+                    for (int cf = 0; cf < NF; cf++) out[rf * rowlen + slot * NF + cf] += S[rf][cf];
+            }
+            __syncwarp();                                        // orders the read-modify-writes of successive elements
+        }
+    }
+}
+
+// ---- rows kernel of the split path --------------------------------------------------------------------
+template <int E, int CHP = 0> struct SplitCfg {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, NINC = ET<E>::NINC, NIP = ET<E>::NIP;
+    static constexpr int CH = CHP ? CHP : ((DIM == 3) ? 8 : 16);   // adjacent elements staged per round (CH * NINC <= 32)
+    static constexpr int NREC = CH * NINC;
+    static constexpr int NV = DIM + 2;                             // accumulated values per slot: D, C[DIM], PP
+    static_assert(NREC <= 32, "one lane issues one record copy");
+};
+template <int E, int CHP = 0> struct SplitWS {
+    using C = SplitCfg<E, CHP>;
+    static constexpr int RS = LeanRec<E>::SZ, SS = rows_smem_stride<E>(RS);
+    alignas(16) double rec[C::NREC][SS];
+    unsigned long long bar;
+    int32_t ipx[C::NREC];
+    uint8_t slot[C::CH][8];
+};
+__host__ __device__ constexpr int split_cnt_pad(int max_cnt) { return (max_cnt + 1) & ~1; }
+template <int E, int CHP> __host__ __device__ constexpr size_t split_warp_bytes(int max_cnt)
+{
+    using C = SplitCfg<E, CHP>;
+    return (sizeof(SplitWS<E, CHP>) + sizeof(double) * ((size_t)C::DIM * C::NF * max_cnt + (size_t)C::NV * split_cnt_pad(max_cnt)) + 15) & ~(size_t)15;
+}
+
+template <int E, int CHP = 0, int MINB = 8>
+__global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, MeshDev m, const double* __restrict__ rec,
+                                                                const double* __restrict__ j0, const double* __restrict__ u,
+                                                                double beta, double* __restrict__ val, double* __restrict__ def,
+                                                                unsigned long long* __restrict__ work_counter)
+{
+    using C = SplitCfg<E, CHP>;
+    using LR = LeanRec<E>;
+    using WS = SplitWS<E, CHP>;
+    constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, NIP = C::NIP, NV = C::NV, RS = WS::RS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // block layout: [inc table NSH*NINC ints, padded to 16 B][per warp: WS | j0 rows DIM*NF*max_cnt | acc NV*cntp]
+    int32_t* inctab = reinterpret_cast<int32_t*>(smem_raw);
+    constexpr size_t tab_bytes = (sizeof(int32_t) * NSH * NINC + 15) & ~(size_t)15;
+    const int cntp = split_cnt_pad(m.max_cnt);
+    const size_t per_warp = split_warp_bytes<E, CHP>(m.max_cnt);
+    WS& ws = *reinterpret_cast<WS*>(smem_raw + tab_bytes + warp * per_warp);
+    double* j0s = reinterpret_cast<double*>(smem_raw + tab_bytes + warp * per_warp + sizeof(WS));
+    double* acc = j0s + (size_t)DIM * NF * m.max_cnt;
+    for (int i = threadIdx.x; i < NSH * NINC; i += blockDim.x)
+        inctab[i] = tab::INC[E][i / NINC][i % NINC] | (tab::INC_SIGN[E][i / NINC][i % NINC] < 0 ? 256 : 0);
+    if (lane == 0) mbar_init(&ws.bar, 1);
+    __syncthreads();
+    unsigned phase = 0;
+    const bool want_jac = p.what & (W_JAC_A | W_JAC_M), want_def = p.what & (W_DEF_A | W_DEF_M | W_RHS);
+    const bool jac_a = p.what & W_JAC_A, def_a = p.what & W_DEF_A;
+    // a defect-only pass needs the fluxes only (head of the record)
+    const unsigned cp_bytes = (unsigned)sizeof(double) * (jac_a ? RS : LR::HEAD);
+    constexpr int JP = 32 / NSH;
+    const int jj = lane / NSH, k = lane - jj * NSH;
+    const double s_visc = p.visc * p.rho * p.scale_a, s_pres = p.scale_a;
+    (void)NIP;
+
+    for (;;) {
+        unsigned long long ai_u = 0;
+        if (lane == 0) ai_u = atomicAdd(work_counter, 1ULL);
+        const int64_t ai = (int64_t)__shfl_sync(0xffffffffu, ai_u, 0);
+        if (ai >= m.n_node) break;
+        const int64_t a = m.node_order ? (int64_t)m.node_order[ai] : ai;
+        const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1];
+        const int64_t b0 = m.brow[a];
+        const int cnt = (int)(m.brow[a + 1] - b0);
+        const int rowlen = cnt * NF;
+        const unsigned j0_bytes = jac_a ? (unsigned)(sizeof(double) * DIM * NF) * (unsigned)cnt : 0u;
+        __syncwarp();                                            // the previous node's output stage has read j0s / acc
+        if (want_jac) for (int i = lane; i < NV * cntp; i += 32) acc[i] = 0.0;
+        double fsum[NF], vsum = 0.0;
+#pragma unroll
+        for (int q = 0; q < NF; q++) fsum[q] = 0.0;
+        int self_slot = 0;
+        for (int64_t qb = q0; qb < q1; qb += CH) {
+            const int nj = (int)((q1 - qb) < CH ? (q1 - qb) : CH);
+            const int nrec = nj * NINC;
+            __syncwarp();
+            const int32_t ad = (lane < nj) ? m.adj[qb + lane] : 0;
+            const int e_l = ad / NSH, la_l = ad - e_l * NSH;
+            const int rj = lane / NINC, rt = lane - rj * NINC;
+            const int e_r = __shfl_sync(0xffffffffu, e_l, rj < CH ? rj : 0);
+            const int la_r = __shfl_sync(0xffffffffu, la_l, rj < CH ? rj : 0);
+            const int ipx_r = inctab[la_r * NINC + rt];
+            const int64_t gi_r = (int64_t)e_r * NIP + (ipx_r & 255);
+            if (lane < nrec) ws.ipx[lane] = ipx_r;
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            const bool first = (qb == q0);
+            if (lane == 0) mbar_arrive_expect_tx(&ws.bar, cp_bytes * (unsigned)nrec + (first ? j0_bytes : 0u));
+            __syncwarp();
+            if (lane < nrec) bulk_g2s(&ws.rec[lane][0], rec + gi_r * RS, cp_bytes, &ws.bar);
+            if (first && j0_bytes && lane == 31) bulk_g2s(j0s, j0 + b0 * (DIM * NF), j0_bytes, &ws.bar);
+            if (lane < nj) {
+                const uint8_t* em = m.emap + (int64_t)ad * NSH;
+                if (NSH == 8) *reinterpret_cast<uint2*>(ws.slot[lane]) = __ldg(reinterpret_cast<const uint2*>(em));
+                else if (NSH == 4) *reinterpret_cast<uint32_t*>(ws.slot[lane]) = __ldg(reinterpret_cast<const uint32_t*>(em));
+                else { for (int q = 0; q < NSH; q++) ws.slot[lane][q] = em[q]; }
+                vsum += m.scvvol[ad];
+            }
+            const int sslot = __shfl_sync(0xffffffffu, la_l, 0);
+            __syncwarp();
+            mbar_wait(&ws.bar, phase);
+            phase ^= 1u;
+            if (first) self_slot = ws.slot[0][sslot];
+            if (def_a && lane < nrec) {
+                const double sgr = (ipx_r & 256) ? -1.0 : 1.0;
+#pragma unroll
+                for (int q = 0; q < NF; q++) fsum[q] += sgr * ws.rec[lane][LR::O_F + q];
+            }
+            if (jac_a) {
+                for (int jb = 0; jb < nj; jb += JP) {
+                    const int j = jb + jj;
+                    const bool act = (jj < JP) && (j < nj);
+                    double D = 0.0, PP = 0.0, Cn[DIM];
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) Cn[d] = 0.0;
+                    if (act) {
+#pragma unroll
+                        for (int t = 0; t < NINC; t++) {
+                            const int r = j * NINC + t;
+                            const double* rc = ws.rec[r];
+                            const double sg = (ws.ipx[r] & 256) ? -p.scale_a : p.scale_a;
+                            D += sg * rc[LR::O_DK + k];
+                            PP += sg * rc[LR::O_PK + k];
+                            const double w = sg * rc[LR::O_CK + k];
+#pragma unroll
+                            for (int d = 0; d < DIM; d++) Cn[d] += w * rc[LR::O_N + d];
+                        }
+                    }
+                    // the same neighbour may be a corner of several of the JP elements: they take turns (fixed order ->
+                    // bitwise deterministic); the corners of one element are distinct nodes
+                    const int ns = (nj - jb) < JP ? (nj - jb) : JP;
+                    const int slot = act ? ws.slot[j][k] : 0;
+                    for (int s = 0; s < ns; s++) {
+                        if (act && jj == s) {
+                            acc[slot] += D;
+#pragma unroll
+                            for (int d = 0; d < DIM; d++) acc[(1 + d) * cntp + slot] += Cn[d];
+                            acc[(1 + DIM) * cntp + slot] += PP;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+        const double volsum = vsum;
+        double dsum = 0.0;
+        if (def_a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int q = 0; q < NF; q++) fsum[q] += __shfl_xor_sync(0xffffffffu, fsum[q], o);
+#pragma unroll
+            for (int q = 0; q < NF; q++) if (lane == q) dsum = fsum[q];
+        }
+        if (want_jac) {
+            if ((p.what & W_JAC_M) && lane == 0) acc[self_slot] += p.scale_m * volsum * p.rho;     // add_jac_M_elem :781-808
+            __syncwarp();
+            double* out = val + b0 * (NF * NF);
+            if constexpr (NF == 4) {
+                for (int rf = 0; rf < DIM; rf++) {
+                    double2* orow = reinterpret_cast<double2*>(out + rf * rowlen);
+                    const double2* jrow = reinterpret_cast<const double2*>(j0s + rf * rowlen);
+                    for (int i = lane; i < 2 * cnt; i += 32) {
+                        const int slot = i >> 1, cp = i & 1;
+                        double2 v = make_double2(0.0, 0.0);
+                        if (jac_a) { const double2 j = jrow[i]; v.x = j.x * s_visc; v.y = j.y * (cp ? s_pres : s_visc); }
+                        const double D = acc[slot];
+                        if (rf == 2 * cp) v.x += D;
+                        if (rf == 2 * cp + 1) v.y += D;
+                        if (beta == 0.0) __stcs(orow + i, v);
+                        else { double2 o = orow[i]; o.x = beta * o.x + v.x; o.y = beta * o.y + v.y; orow[i] = o; }
+                    }
+                }
+                double2* orow = reinterpret_cast<double2*>(out + DIM * rowlen);
+                for (int i = lane; i < 2 * cnt; i += 32) {
+                    const int slot = i >> 1, cp = i & 1;
+                    const double2 v = make_double2(acc[(1 + 2 * cp) * cntp + slot], acc[(2 + 2 * cp) * cntp + slot]);
+                    if (beta == 0.0) __stcs(orow + i, v);
+                    else { double2 o = orow[i]; o.x = beta * o.x + v.x; o.y = beta * o.y + v.y; orow[i] = o; }
+                }
+            } else {
+                for (int rf = 0; rf < DIM; rf++) {
+                    double* orow = out + rf * rowlen;
+                    for (int i = lane; i < rowlen; i += 32) {
+                        const int slot = i / NF, cf = i - slot * NF;
+                        double v = jac_a ? j0s[rf * rowlen + i] * (cf < DIM ? s_visc : s_pres) : 0.0;
+                        if (cf == rf) v += acc[slot];
+                        if (beta == 0.0) __stcs(orow + i, v);
+                        else orow[i] = beta * orow[i] + v;
+                    }
+                }
+                double* orow = out + DIM * rowlen;
+                for (int i = lane; i < rowlen; i += 32) {
+                    const int slot = i / NF, cf = i - slot * NF;
+                    const double v = acc[(1 + cf) * cntp + slot];
+                    if (beta == 0.0) __stcs(orow + i, v);
+                    else orow[i] = beta * orow[i] + v;
+                }
+            }
+        }
+        if (want_def && lane < NF) {
+            double d = def_a ? dsum : 0.0;
+            if ((p.what & W_RHS) && p.has_source && lane < DIM) d -= p.src[lane] * volsum * p.rho;
+            d *= p.scale_a;
+            if ((p.what & W_DEF_M) && lane < DIM) d += p.scale_m * u[a * NF + lane] * volsum * p.rho;
+            double* q = def + a * NF + lane;
+            *q = (beta == 0.0) ? d : beta * (*q) + d;
+        }
+    }
+}
+
+}  // namespace nsb

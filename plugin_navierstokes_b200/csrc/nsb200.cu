@@ -53,6 +53,8 @@ struct nsb_ctx {
     int32_t *d_conn = nullptr, *d_adj = nullptr, *d_color_order = nullptr, *d_esides = nullptr, *d_node_order = nullptr;
     double *d_coords = nullptr, *d_scvvol = nullptr, *d_rec = nullptr;
     size_t rec_bytes = 0; int rec_stride = 0;     // combined SCVF record table [geometry | flux] of the owner-computes path
+    bool rec_lean = false;                        // ... or lean flux records of the split path (no geometry half)
+    double* d_j0 = nullptr; int j0_laplace = -1;  // static Jacobian part of the split path (ns_split.cuh), built once per mesh
     int64_t *d_brow = nullptr, *d_adj_ptr = nullptr;
     uint8_t *d_emap = nullptr;
     FvcrDev fvcr{};
@@ -145,7 +147,8 @@ static void free_mesh(nsb_ctx* c)
     cudaFree(c->d_conn); cudaFree(c->d_adj); cudaFree(c->d_color_order); cudaFree(c->d_esides); cudaFree(c->d_node_order); cudaFree(c->d_coords);
     cudaFree(c->d_scvvol); cudaFree(c->d_rec); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
     cudaFree(c->d_u); cudaFree(c->d_s0); cudaFree(c->d_s1); cudaFree(c->d_val); cudaFree(c->d_def);
-    cudaFree(c->d_jloc); cudaFree(c->d_dloc);
+    cudaFree(c->d_jloc); cudaFree(c->d_dloc); cudaFree(c->d_j0);
+    c->d_j0 = nullptr; c->j0_laplace = -1; c->rec_lean = false;
     fvcr_free(c->fvcr);
     c->d_conn = c->d_adj = c->d_color_order = c->d_esides = c->d_node_order = nullptr; c->d_coords = c->d_scvvol = c->d_rec = nullptr; c->rec_bytes = 0; c->rec_stride = 0;
     c->d_brow = c->d_adj_ptr = nullptr; c->d_emap = nullptr;
@@ -463,14 +466,20 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
 {
     const MeshDev m = mesh_view(c);
     cudaError_t e;
-    {   // combined per-(element, ip) record table: static SCVF geometry | flux record written by the flux kernel.
+    static const int kNIP[4] = {3, 4, 6, 12};
+    const bool flow = k.stab == STAB_FLOW, exact = !k.stokes && k.exact_jac != 0.0;
+    // split path (ns_split.cuh): static Jacobian part J0 cached per mesh + lean flux records. FLOW couples the
+    // velocity components in the continuity row and exact Newton adds full blocks: those keep the general rows kernel.
+    static const bool no_split = getenv("NSB_NOSPLIT") != nullptr;
+    const bool lean = !flow && !exact && !no_split;
+    {   // per-(element, ip) record table: [static SCVF geometry | flux record] or the lean record of the split path.
         // The stride depends on the stabilisation (FLOW) and Jacobian flavour (exact Newton): (re)built on change.
-        const bool flow = k.stab == STAB_FLOW, exact = !k.stokes && k.exact_jac != 0.0;
         int stride = 0;
-        switch (c->elem) { case 0: stride = scvf_record_doubles_0(flow, exact); break; case 1: stride = scvf_record_doubles_1(flow, exact); break;
-                           case 2: stride = scvf_record_doubles_2(flow, exact); break; default: stride = scvf_record_doubles_3(flow, exact); }
-        if (stride != c->rec_stride) {
-            static const int kNIP[4] = {3, 4, 6, 12};
+        if (lean) switch (c->elem) { case 0: stride = lean_record_doubles_0(); break; case 1: stride = lean_record_doubles_1(); break;
+                                     case 2: stride = lean_record_doubles_2(); break; default: stride = lean_record_doubles_3(); }
+        else switch (c->elem) { case 0: stride = scvf_record_doubles_0(flow, exact); break; case 1: stride = scvf_record_doubles_1(flow, exact); break;
+                                case 2: stride = scvf_record_doubles_2(flow, exact); break; default: stride = scvf_record_doubles_3(flow, exact); }
+        if (stride != c->rec_stride || lean != c->rec_lean) {
             const size_t need = (size_t)c->n_elem * kNIP[c->elem] * stride * sizeof(double);
             CUDA_TRY(c, cudaStreamSynchronize(c->stream));
             if (need > c->rec_bytes) {
@@ -478,14 +487,38 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
                 CUDA_TRY(c, cudaMalloc(&c->d_rec, need));
                 c->rec_bytes = need;
             }
-            switch (c->elem) { case 0: e = launch_geom_0(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); break;
-                               case 1: e = launch_geom_1(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); break;
-                               case 2: e = launch_geom_2(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); break;
-                               default: e = launch_geom_3(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); }
+            if (!lean) {
+                switch (c->elem) { case 0: e = launch_geom_0(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); break;
+                                   case 1: e = launch_geom_1(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); break;
+                                   case 2: e = launch_geom_2(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); break;
+                                   default: e = launch_geom_3(c->n_elem, c->d_conn, c->d_coords, c->d_rec, stride, c->stream); }
+                c->launches++;
+                CUDA_TRY(c, e);
+            }
+            c->rec_stride = stride; c->rec_lean = lean;
+        }
+    }
+    if (lean) {
+        const int dim = kDIM[c->elem], nf = dim + 1;
+        if ((k.what & W_JAC_A) && c->j0_laplace != k.laplace) {
+            const size_t nj0 = (size_t)c->h_brow[c->n_node] * dim * nf;
+            if (!c->d_j0) CUDA_TRY(c, cudaMalloc(&c->d_j0, std::max<size_t>(nj0, 1) * sizeof(double)));
+            CUDA_TRY(c, cudaMemsetAsync(c->d_j0, 0, nj0 * sizeof(double), c->stream));
+            switch (c->elem) { case 0: e = launch_j0_0(m, k.laplace, c->d_j0, c->stream, c->sm_count); break;
+                               case 1: e = launch_j0_1(m, k.laplace, c->d_j0, c->stream, c->sm_count); break;
+                               case 2: e = launch_j0_2(m, k.laplace, c->d_j0, c->stream, c->sm_count); break;
+                               default: e = launch_j0_3(m, k.laplace, c->d_j0, c->stream, c->sm_count); }
             c->launches++;
             CUDA_TRY(c, e);
-            c->rec_stride = stride;
+            c->j0_laplace = k.laplace;
         }
+#define NSB_GO(fn) fn(k, m, c->d_rec, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter, c->d_j0)
+        switch (c->elem) { case 0: e = NSB_GO(launch_split_0); break; case 1: e = NSB_GO(launch_split_1); break;
+                           case 2: e = NSB_GO(launch_split_2); break; default: e = NSB_GO(launch_split_3); }
+#undef NSB_GO
+        c->launches += (k.what & (W_JAC_A | W_DEF_A)) ? 2 : 1;
+        CUDA_TRY(c, e);
+        return NSB_OK;
     }
 #define NSB_GO(fn) fn(k, m, c->d_rec, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter)
     switch (c->elem) { case 0: e = NSB_GO(launch_gather_0); break; case 1: e = NSB_GO(launch_gather_1); break;
