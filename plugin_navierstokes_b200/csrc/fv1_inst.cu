@@ -65,7 +65,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
     if (k.what & (W_JAC_A | W_DEF_A)) {
-        const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * BS + NIP * NSH * DIM + NIP * NSH);
+        const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * BS + NIP * NSH * DIM + NIP * NSH) + sizeof(int) * NIP * 12;
         static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 2; }();
         auto ka = minb == 2 ? fv1_flux_kernel<E, STAB, EXACT, BS, 2> : minb == 4 ? fv1_flux_kernel<E, STAB, EXACT, BS, 4> : fv1_flux_kernel<E, STAB, EXACT, BS, 3>;
         e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
@@ -111,12 +111,22 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
     if (k.what & (W_JAC_A | W_DEF_A)) {
-        const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * BS + NIP * NSH * DIM + NIP * NSH);
-        auto ka = fv1_flux_kernel<E, STAB, false, BS, 2, true>;
-        e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-        if (e != cudaSuccess) return e;
-        ka<<<(unsigned)((m.n_elem + BS - 1) / BS), BS, smem_a, st>>>(k, m, u, s0, s1, rec, d_err);
-        e = cudaGetLastError();
+        // NSB_FLUX_LPE = lanes per element (hex: 1 or 4), NSB_FLUX_MINB = blocks/SM the registers are bounded for
+        static const int LPEV = [] { const char* ev = getenv("NSB_FLUX_LPE"); return ev ? atoi(ev) : 1; }();
+        static const int FMB = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 0; }();
+        auto go = [&](auto ka, int lpe) -> cudaError_t {
+            const int epb = BS / lpe;
+            const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * epb + NIP * (NSH * DIM + 1) + NIP * (NSH + 1)) + sizeof(int) * NIP * 12;
+            cudaError_t e2 = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+            if (e2 != cudaSuccess) return e2;
+            ka<<<(unsigned)((m.n_elem + epb - 1) / epb), BS, smem_a, st>>>(k, m, u, s0, s1, rec, d_err);
+            return cudaGetLastError();
+        };
+        if constexpr (E == 3) {
+            if (LPEV == 4) e = FMB == 2 ? go(fv1_flux_kernel<E, STAB, false, BS, 2, true, 4>, 4) : FMB == 3 ? go(fv1_flux_kernel<E, STAB, false, BS, 3, true, 4>, 4)
+                             : FMB == 5 ? go(fv1_flux_kernel<E, STAB, false, BS, 5, true, 4>, 4) : go(fv1_flux_kernel<E, STAB, false, BS, 4, true, 4>, 4);
+            else e = FMB == 3 ? go(fv1_flux_kernel<E, STAB, false, BS, 3, true, 1>, 1) : go(fv1_flux_kernel<E, STAB, false, BS, 2, true, 1>, 1);
+        } else e = go(fv1_flux_kernel<E, STAB, false, BS, 2, true, 1>, 1);
         if (e != cudaSuccess) return e;
     }
     static const int WPB = [] { const char* ev = getenv("NSB_SPLIT_WPB"); const int v = ev ? atoi(ev) : 2; return (v >= 1 && v <= 2) ? v : 2; }();

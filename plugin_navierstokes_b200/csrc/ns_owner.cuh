@@ -231,12 +231,15 @@ NSB_DEV bool upwind_uniform(int type, const double* __restrict__ xs, int tid, co
 // FV1Geometry of SCVF `ip` (warp-uniform) from the thread's shared corner column; see ip_geometry (ns_fv1.cuh).
 // cen = element barycentre (hoisted). dnt = local shape gradients at the ips [NIP][NSH][DIM] (shared memory).
 // JI (inverse transposed Jacobian at the ip) is only computed when wantJ: global_grad(k) = JI * dnt[ip][k].
-template <int E, int BS>
+// iptab (shared memory, [NIP][12] ints: from, to, corners of face A, corners of face B) replaces the constant-memory
+// tables when the lanes of a warp work on different ips (LPE > 1): constant loads with diverging addresses serialise.
+template <int E, int BS, int DSTR = ET<E>::NSH * ET<E>::DIM, bool SMTAB = false>
 NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, const double* cen, const double* __restrict__ dnt,
-                             double* n, double* xip, double& ds, bool wantJ, double (*JI)[ET<E>::DIM])
+                             double* n, double* xip, double& ds, bool wantJ, double (*JI)[ET<E>::DIM],
+                             const int* __restrict__ iptab = nullptr)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
-    const int f = tab::C_EDGE[E][ip][0], t = tab::C_EDGE[E][ip][1];
+    const int f = SMTAB ? iptab[ip * 12] : tab::C_EDGE[E][ip][0], t = SMTAB ? iptab[ip * 12 + 1] : tab::C_EDGE[E][ip][1];
     double c0[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; d++) c0[d] = 0.5 * (NSB_COL(xs, f * DIM + d) + NSB_COL(xs, t * DIM + d));
@@ -245,12 +248,12 @@ NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, con
         xip[0] = 0.5 * (c0[0] + cen[0]); xip[1] = 0.5 * (c0[1] + cen[1]);
         ds = 0.0;
     } else {
-        const int fa = tab::C_FA[E][ip], fb = tab::C_FB[E][ip];
+        const int fa = SMTAB ? 0 : tab::C_FA[E][ip], fb = SMTAB ? 0 : tab::C_FB[E][ip];
         constexpr int NFC = (E == E_TET) ? 3 : 4;
         double c1[3] = {0, 0, 0}, c3[3] = {0, 0, 0};
 #pragma unroll
         for (int q = 0; q < NFC; q++) {
-            const int ka = tab::C_SIDE[E][fa][q], kb = tab::C_SIDE[E][fb][q];
+            const int ka = SMTAB ? iptab[ip * 12 + 2 + q] : tab::C_SIDE[E][fa][q], kb = SMTAB ? iptab[ip * 12 + 6 + q] : tab::C_SIDE[E][fb][q];
 #pragma unroll
             for (int d = 0; d < 3; d++) { c1[d] += NSB_COL(xs, ka * 3 + d); c3[d] += NSB_COL(xs, kb * 3 + d); }
         }
@@ -272,7 +275,7 @@ NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, con
         for (int i = 0; i < DIM; i++)
 #pragma unroll
             for (int j = 0; j < DIM; j++) JT[i][j] = 0.0;
-        const double* dn = dnt + ip * (NSH * DIM);
+        const double* dn = dnt + ip * DSTR;
 #pragma unroll
         for (int k = 0; k < NSH; k++) {
             double dk[DIM];
@@ -292,14 +295,20 @@ NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, con
 // lean SCVF record of the split path (ns_split.cuh): [F | n | cK | dK | pK = -G_k.n / diag]
 template <int E> struct LeanRec;
 
-template <int E, int STAB, bool EXACT, int BS, int MINB = 3, bool LEAN = false>
-__global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m,
+// LPE = lanes per element: the SCVFs of an element are dealt to LPE adjacent lanes (ip = ii * LPE + sub), the element's
+// unknowns / coordinates live once in a shared column used by all of them. LPE = 1 is the thread-per-element layout.
+template <int E, int STAB, bool EXACT, int NT, int MINB = 3, bool LEAN = false, int LPE = 1>
+__global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m,
                                                       const double* __restrict__ u, const double* __restrict__ s0,
                                                       const double* __restrict__ s1, double* __restrict__ rec,
                                                       int* __restrict__ errflag)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, P = DIM;
     constexpr bool FLOW = (STAB == STAB_FLOW);
+    constexpr int BS = NT / LPE;                                 // elements (shared columns) per block
+    constexpr bool SMT = LPE > 1;
+    constexpr int DSTR = NSH * DIM + (SMT ? 1 : 0), NSTR = NSH + (SMT ? 1 : 0);   // odd strides: the LPE ips of a warp hit disjoint banks
+    static_assert(NT % LPE == 0 && 32 % LPE == 0 && NIP % LPE == 0 && NSH % LPE == 0, "bad LPE");
     using R = GeoRec<E>;
     using FR = FluxRec<E, FLOW, EXACT>;
     static_assert(!LEAN || (!FLOW && !EXACT), "the split path covers FIELDS / no stabilisation with the fixed-point Jacobian");
@@ -310,32 +319,44 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
     double* xs = reinterpret_cast<double*>(smem_raw);            // [NSH*DIM][BS]
     double* vs = xs + NSH * DIM * BS;                            // [NSH][BS]
     double* us = vs + NSH * BS;                                  // [NSH*NF][BS] nodal unknowns (the `u` argument)
-    double* dnt = us + NSH * NF * BS;                            // [NIP][NSH][DIM] local shape gradients at the ips
-    double* Nt = dnt + NIP * NSH * DIM;                          // [NIP][NSH]      shape values at the ips
-    const int tid = threadIdx.x;
-    for (int i = tid; i < NIP * NSH * DIM; i += BS) dnt[i] = tab::C_DNIP[E][i / (NSH * DIM)][(i / DIM) % NSH][i % DIM];
-    for (int i = tid; i < NIP * NSH; i += BS) Nt[i] = tab::NIPSH[E][i / NSH][i % NSH];
+    double* dnt = us + NSH * NF * BS;                            // [NIP][DSTR] local shape gradients at the ips
+    double* Nt = dnt + NIP * DSTR;                               // [NIP][NSTR] shape values at the ips
+    int* iptab = reinterpret_cast<int*>(Nt + NIP * NSTR);        // [NIP][12]   from, to, face corners (LPE > 1)
+    for (int i = threadIdx.x; i < NIP * NSH * DIM; i += NT) dnt[(i / (NSH * DIM)) * DSTR + i % (NSH * DIM)] = tab::C_DNIP[E][i / (NSH * DIM)][(i / DIM) % NSH][i % DIM];
+    for (int i = threadIdx.x; i < NIP * NSH; i += NT) Nt[(i / NSH) * NSTR + i % NSH] = tab::NIPSH[E][i / NSH][i % NSH];
+    if constexpr (SMT) {
+        for (int i = threadIdx.x; i < NIP * 12; i += NT) {
+            const int ip = i / 12, j = i - ip * 12;
+            int v = 0;
+            if (j < 2) v = tab::EDGE[E][ip][j];
+            else if (DIM == 3) v = (j < 6) ? tab::SIDE[E][tab::SCVF_FA[E][ip]][j - 2] : tab::SIDE[E][tab::SCVF_FB[E][ip]][j - 6];
+            iptab[i] = v < 0 ? 0 : v;
+        }
+    }
     __syncthreads();
-    const int64_t e = (int64_t)blockIdx.x * BS + tid;
-    if (e >= m.n_elem) return;                                   // no block-wide barriers below
+    const int tid = threadIdx.x / LPE, sub = threadIdx.x - tid * LPE;   // element column of this lane, its ip group
+    int64_t e = (int64_t)blockIdx.x * BS + tid;
+    if constexpr (LPE == 1) { if (e >= m.n_elem) return; }       // no block-wide barriers below
+    else if (e >= m.n_elem) e = m.n_elem - 1;                    // surplus lanes redo the last element (identical values)
     const bool td = p.time_dep;
-    // ---- element data: unknowns in registers, coordinates / volumes in the thread's shared column ----
-    int nd[NSH];
+    // ---- element data: unknowns, coordinates and volumes in the element's shared column ----
+    const int32_t* nd = m.conn + e * NSH;                        // re-read where needed (time-dependent closure only)
 #pragma unroll
-    for (int k = 0; k < NSH; k++) nd[k] = m.conn[e * NSH + k];
-#pragma unroll
-    for (int k = 0; k < NSH; k++) {
+    for (int kq = 0; kq < NSH / LPE; kq++) {
+        const int k = kq * LPE + sub;
+        const int64_t ndk = nd[k];
         if (NF == 4) {
-            const double2 a = ldg2(u + (int64_t)nd[k] * 4), b = ldg2(u + (int64_t)nd[k] * 4 + 2);
+            const double2 a = ldg2(u + ndk * 4), b = ldg2(u + ndk * 4 + 2);
             NSB_COL(us, k * NF + 0) = a.x; NSB_COL(us, k * NF + 1) = a.y; NSB_COL(us, k * NF + 2) = b.x; NSB_COL(us, k * NF + NF - 1) = b.y;
         } else {
 #pragma unroll
-            for (int f = 0; f < NF; f++) NSB_COL(us, k * NF + f) = u[(int64_t)nd[k] * NF + f];
+            for (int f = 0; f < NF; f++) NSB_COL(us, k * NF + f) = u[ndk * NF + f];
         }
 #pragma unroll
-        for (int d = 0; d < DIM; d++) NSB_COL(xs, k * DIM + d) = m.coords[(int64_t)nd[k] * DIM + d];
+        for (int d = 0; d < DIM; d++) NSB_COL(xs, k * DIM + d) = m.coords[ndk * DIM + d];
         NSB_COL(vs, k) = m.scvvol[e * NSH + k];
     }
+    if constexpr (SMT) __syncwarp();
     const double nurho = p.visc * p.rho;
     const bool want_def = p.what & W_DEF_A, want_jac = p.what & W_JAC_A;
     bool ok = true;
@@ -353,7 +374,7 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
         cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
         for (int i = 0; i < NIP; i++) {
             double nn_[DIM], xx_[DIM], dsi;
-            ip_geometry_col<E, BS>(xs, tid, i, cen, dnt, nn_, xx_, dsi, false, nullptr);
+            ip_geometry_col<E, BS, DSTR, SMT>(xs, tid, i, cen, dnt, nn_, xx_, dsi, false, nullptr, iptab);
             const double q = dotv<DIM>(nn_, nn_);
             if (q < cmn) cmn = q;
             cav += q;
@@ -362,15 +383,14 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
         cav /= NIP;
     }
 
-    for (int ip = 0; ip < NIP; ip++) {
+    for (int ii = 0; ii < NIP / LPE; ii++) {
+        const int ip = ii * LPE + sub;
         double* fr = LEAN ? rec + (e * NIP + ip) * LRSZ                     // lean record of the split path
                           : rec + (e * NIP + ip) * (R::SZ + FR::SZ) + R::SZ;      // flux part of the combined SCVF record
-        const int from = tab::C_EDGE[E][ip][0], to = tab::C_EDGE[E][ip][1];
+        const int from = SMT ? iptab[ip * 12] : tab::C_EDGE[E][ip][0], to = SMT ? iptab[ip * 12 + 1] : tab::C_EDGE[E][ip][1];
         double n[DIM], xip[DIM], ds = 0.0, JI[DIM][DIM];
-        ip_geometry_col<E, BS>(xs, tid, ip, cen, dnt, n, xip, ds, want_def || (LEAN && want_jac), JI);
-        double N[NSH];
-#pragma unroll
-        for (int k = 0; k < NSH; k++) N[k] = Nt[ip * NSH + k];
+        ip_geometry_col<E, BS, DSTR, SMT>(xs, tid, ip, cen, dnt, n, xip, ds, want_def || (LEAN && want_jac), JI, iptab);
+        const double* N = Nt + ip * NSTR;                        // shape values at the ip, re-read from shared memory at each use
         // ---- StdVel from the `u` argument (:282-293) ----
         double std[DIM];
 #pragma unroll
@@ -398,29 +418,50 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
             }
         }
         // ---- diagonal of the ip system and numerators sb_k (stabilization.cpp:166-236 / :489-582) ----
-        double inv = 0.0, sb[NSH];
+        double inv = 0.0, qa = 0.0, qb = 0.0, qc = 0.0;          // sb_k = qa N_k + qb up_k + qc (down_k - up_k), formed where it is used
         if (STAB != STAB_NONE) {
             const double nn = dotv<DIM>(n, n);
-            const double a = p.visc * diff_len_sq_inv<DIM>(p.diff_len, nn, NSB_COL(vs, from), NSB_COL(vs, to), ds, cmn, cav, cmd);
-            double b = 0.0, c = 0.0;
+            qa = p.visc * diff_len_sq_inv<DIM>(p.diff_len, nn, NSB_COL(vs, from), NSB_COL(vs, to), ds, cmn, cav, cmd);
             if (!p.stokes) {
                 const double nrm = sqrt(dotv<DIM>(std, std));
-                b = nrm / uplen;
-                if (FLOW) c = nrm / (dnlen + uplen);
+                qb = nrm / uplen;
+                if (FLOW) qc = nrm / (dnlen + uplen);
             }
-            double diag = a;
+            double diag = qa;
             if (td) diag += 1.0 / p.dt;
-            if (!p.stokes) diag += b;
+            if (!p.stokes) diag += qb;
             inv = 1.0 / diag;
+        }
+        auto sbk = [&](int k) -> double {
+            if (STAB == STAB_NONE) return 0.0;
+            double s = qa * N[k];
+            if (!p.stokes) { s += qb * up[k]; if (FLOW) s += qc * dnm[k]; }
+            return s;
+        };
+        // everything that uses the STABILISATION's upwind shapes happens here: the convective upwind below may overwrite `up`
+        constexpr int W_CK = LEAN ? L_CK : FR::O_CK, W_DK = LEAN ? L_DK : FR::O_DK;
+        if (want_jac) {                                          // continuity-row coefficients (:561-584)
+            if constexpr (NSH % 2 == 0) {
+#pragma unroll
+                for (int k = 0; k < NSH; k += 2) {
+                    const double c0 = (STAB == STAB_NONE) ? N[k] * p.rho : sbk(k) * inv * p.rho;
+                    const double c1 = (STAB == STAB_NONE) ? N[k + 1] * p.rho : sbk(k + 1) * inv * p.rho;
+                    *reinterpret_cast<double2*>(fr + W_CK + k) = make_double2(c0, c1);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NSH; k++) fr[W_CK + k] = (STAB == STAB_NONE) ? N[k] * p.rho : sbk(k) * inv * p.rho;
+            }
+        }
+        double acc = 0.0;                                        // closure sum  sum_k sb_k (s_k . n)
+        if (STAB != STAB_NONE && want_def) {
 #pragma unroll
             for (int k = 0; k < NSH; k++) {
-                double s = a * N[k];
-                if (!p.stokes) { s += b * up[k]; if (FLOW) s += c * dnm[k]; }
-                sb[k] = s;
-            }
-        } else {
+                double sk = 0.0;
 #pragma unroll
-            for (int k = 0; k < NSH; k++) sb[k] = 0.0;
+                for (int d = 0; d < DIM; d++) sk += (td ? s0[(int64_t)nd[k] * NF + d] : NSB_COL(us, k * NF + d)) * n[d];
+                acc += sbk(k) * sk;
+            }
         }
         // ---- convective upwind, transported velocity, Peclet blend ----
         double U[DIM], w = 1.0;
@@ -446,24 +487,20 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
         // ---- Jacobian coefficients ----
         if (want_jac) {
             const double cw = prod * w, cpe = prod * (1.0 - w);
-            double ck[NSH], dk[NSH];
-#pragma unroll
-            for (int k = 0; k < NSH; k++) {
-                ck[k] = (STAB == STAB_NONE) ? N[k] * p.rho : sb[k] * inv * p.rho;
-                double D = 0.0;
-                if (!p.stokes) { D = up[k] * cw; if (p.peclet) D += cpe * N[k]; }
-                dk[k] = D;
-            }
-            constexpr int W_CK = LEAN ? L_CK : FR::O_CK, W_DK = LEAN ? L_DK : FR::O_DK;
             if constexpr (NSH % 2 == 0) {
 #pragma unroll
                 for (int k = 0; k < NSH; k += 2) {
-                    *reinterpret_cast<double2*>(fr + W_CK + k) = make_double2(ck[k], ck[k + 1]);
-                    *reinterpret_cast<double2*>(fr + W_DK + k) = make_double2(dk[k], dk[k + 1]);
+                    double D0 = 0.0, D1 = 0.0;
+                    if (!p.stokes) { D0 = up[k] * cw; D1 = up[k + 1] * cw; if (p.peclet) { D0 += cpe * N[k]; D1 += cpe * N[k + 1]; } }
+                    *reinterpret_cast<double2*>(fr + W_DK + k) = make_double2(D0, D1);
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < NSH; k++) { fr[W_CK + k] = ck[k]; fr[W_DK + k] = dk[k]; }
+                for (int k = 0; k < NSH; k++) {
+                    double D = 0.0;
+                    if (!p.stokes) { D = up[k] * cw; if (p.peclet) D += cpe * N[k]; }
+                    fr[W_DK + k] = D;
+                }
             }
             if constexpr (LEAN) {
                 // pressure column of the continuity row (:586-592): -G_k.n / diag, with G_k.n = dnt_k . (JI^T n)
@@ -479,7 +516,7 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
                 for (int k = 0; k < NSH; k++) {
                     double s = 0.0;
 #pragma unroll
-                    for (int i = 0; i < DIM; i++) s += dnt[(ip * NSH + k) * DIM + i] * mv[i];
+                    for (int i = 0; i < DIM; i++) s += dnt[ip * DSTR + k * DIM + i] * mv[i];
                     pk[k] = s;
                 }
                 if constexpr (NSH % 2 == 0) {
@@ -510,52 +547,60 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
 #pragma unroll
             for (int d = 0; d < DIM; d++) fr[FR::O_STD + d] = std[d];
         }
-        // ---- defect fluxes (:686-776): stream the global gradients (d-major) ----
+        // ---- defect fluxes (:686-776), corner-major: global_grad(k) = JI * local_grad(k) is formed once per corner and
+        // consumed at once (velocity / pressure gradients, closure sum), so no per-corner array stays live ----
         if (want_def) {
-            double gv[DIM][DIM], gp[DIM], gv0[DIM][DIM], gp0[DIM], sG[NSH];
-#pragma unroll
-            for (int k = 0; k < NSH; k++) sG[k] = 0.0;
+            double gv[DIM][DIM], gp[DIM], gv0[DIM][DIM], gp0[DIM];
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
-                double Gd[NSH];                                  // global_grad(k)[d] = sum_i JI[d][i] * local_grad(k)[i]
+                gp[d] = 0.0; gp0[d] = 0.0;
 #pragma unroll
-                for (int k = 0; k < NSH; k++) {
+                for (int q = 0; q < DIM; q++) { gv[q][d] = 0.0; gv0[q][d] = 0.0; }
+            }
+            double pr = 0.0, oacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < NSH; k++) {
+                double Gk[DIM], uk[NF];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) {
                     double g = 0.0;
 #pragma unroll
-                    for (int i = 0; i < DIM; i++) g += JI[d][i] * dnt[(ip * NSH + k) * DIM + i];
-                    Gd[k] = g;
+                    for (int i = 0; i < DIM; i++) g += JI[d][i] * dnt[ip * DSTR + k * DIM + i];
+                    Gk[d] = g;
                 }
-                double sp = 0.0, sv[DIM];
 #pragma unroll
-                for (int q = 0; q < DIM; q++) sv[q] = 0.0;
+                for (int q = 0; q < NF; q++) uk[q] = NSB_COL(us, k * NF + q);
 #pragma unroll
-                for (int k = 0; k < NSH; k++) {
-                    if (FLOW) sG[k] += Gd[k] * std[d];
-                    sp += Gd[k] * NSB_COL(us, k * NF + P);
+                for (int d = 0; d < DIM; d++) {
+                    gp[d] += Gk[d] * uk[P];
 #pragma unroll
-                    for (int q = 0; q < DIM; q++) sv[q] += Gd[k] * NSB_COL(us, k * NF + q);
+                    for (int q = 0; q < DIM; q++) gv[q][d] += Gk[d] * uk[q];
                 }
-                gp[d] = sp;
+                pr += N[k] * uk[P];
+                if (STAB != STAB_NONE) {
+                    // (stab_vel . n) rho with rhs_d = src_d + old_d/dt + sum_k [sv(d,d,k) s_dk + sum_{q!=d} sv(d,q,k) s_qk] - G_kd/rho p_k
+                    //  = n.src + n.old/dt + sum_k (sb_k [- std.G_k]) (s_k.n) [+ (std.n) div s] - (grad p . n)/rho
+                    double sk = 0.0;
+                    if (td) {                                    // the closure uses solution(0) (:296, :646)
+                        double s0k[NF], o = 0.0;
 #pragma unroll
-                for (int q = 0; q < DIM; q++) gv[q][d] = sv[q];
-                if (td) {                                        // the closure uses solution(0) (:296, :646)
-                    double sp0 = 0.0, sv0[DIM];
+                        for (int q = 0; q < NF; q++) s0k[q] = s0[(int64_t)nd[k] * NF + q];
 #pragma unroll
-                    for (int q = 0; q < DIM; q++) sv0[q] = 0.0;
+                        for (int d = 0; d < DIM; d++) {
+                            gp0[d] += Gk[d] * s0k[P];
 #pragma unroll
-                    for (int k = 0; k < NSH; k++) {
-                        sp0 += Gd[k] * s0[(int64_t)nd[k] * NF + P];
+                            for (int q = 0; q < DIM; q++) gv0[q][d] += Gk[d] * s0k[q];
+                            sk += s0k[d] * n[d];
+                            o += s1[(int64_t)nd[k] * NF + d] * n[d];
+                        }
+                        oacc += N[k] * o;
+                    } else {
 #pragma unroll
-                        for (int q = 0; q < DIM; q++) sv0[q] += Gd[k] * s0[(int64_t)nd[k] * NF + q];
+                        for (int d = 0; d < DIM; d++) sk += uk[d] * n[d];
                     }
-                    gp0[d] = sp0;
-#pragma unroll
-                    for (int q = 0; q < DIM; q++) gv0[q][d] = sv0[q];
+                    if (FLOW) acc -= dotv<DIM>(Gk, std) * sk;
                 }
             }
-            double pr = 0.0;
-#pragma unroll
-            for (int k = 0; k < NSH; k++) pr += N[k] * NSB_COL(us, k * NF + P);
             double F[NF];
 #pragma unroll
             for (int d1 = 0; d1 < DIM; d1++) {
@@ -574,16 +619,6 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
             double cont;
             if (STAB == STAB_NONE) cont = sn * p.rho;
             else {
-                // (stab_vel . n) rho with rhs_d = src_d + old_d/dt + sum_k [sv(d,d,k) s_dk + sum_{q!=d} sv(d,q,k) s_qk] - G_kd/rho p_k
-                //  = n.src + n.old/dt + sum_k (sb_k [- std.G_k]) (s_k.n) [+ (std.n) div s] - (grad p . n)/rho
-                double acc = 0.0;
-#pragma unroll
-                for (int k = 0; k < NSH; k++) {
-                    double sk = 0.0;
-#pragma unroll
-                    for (int d = 0; d < DIM; d++) sk += (td ? s0[(int64_t)nd[k] * NF + d] : NSB_COL(us, k * NF + d)) * n[d];
-                    acc += (FLOW ? sb[k] - sG[k] : sb[k]) * sk;
-                }
                 double gpn = 0.0, div = 0.0;
 #pragma unroll
                 for (int d = 0; d < DIM; d++) { gpn += (td ? gp0[d] : gp[d]) * n[d]; div += td ? gv0[d][d] : gv[d][d]; }
@@ -593,17 +628,7 @@ __global__ void __launch_bounds__(BS, MINB) fv1_flux_kernel(KParams p, MeshDev m
 #pragma unroll
                     for (int d = 0; d < DIM; d++) acc += p.src[d] * n[d];
                 }
-                if (td) {
-                    double o = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NSH; k++) {
-                        double sk = 0.0;
-#pragma unroll
-                        for (int d = 0; d < DIM; d++) sk += s1[(int64_t)nd[k] * NF + d] * n[d];
-                        o += N[k] * sk;
-                    }
-                    acc += o / p.dt;
-                }
+                if (td) acc += oacc / p.dt;
                 cont = acc * inv * p.rho;
             }
             F[P] = cont;
