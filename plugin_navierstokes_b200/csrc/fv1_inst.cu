@@ -65,7 +65,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
     if (k.what & (W_JAC_A | W_DEF_A)) {
-        const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * BS + NIP * NSH * DIM + NIP * NSH) + sizeof(int) * NIP * 12;
+        const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * BS + NIP * NSH * DIM + NIP * NSH + 24) + sizeof(int) * (NIP * 12 + 24);
         static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 2; }();
         auto ka = minb == 2 ? fv1_flux_kernel<E, STAB, EXACT, BS, 2> : minb == 4 ? fv1_flux_kernel<E, STAB, EXACT, BS, 4> : fv1_flux_kernel<E, STAB, EXACT, BS, 3>;
         e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
@@ -105,30 +105,33 @@ cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
     }
 }
 // ---- split path (ns_split.cuh): lean flux records + static table J0 ----
+// stages: 1 = flux kernel, 2 = rows kernel, 3 = both (one stream); rows_bps > 0 caps the rows blocks per SM (pipelined mode)
 template <int STAB, int CHP, int MINB>
-static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
+static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0, int stages, int rows_bps)
 {
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
-    if (k.what & (W_JAC_A | W_DEF_A)) {
+    if ((stages & 1) && (k.what & (W_JAC_A | W_DEF_A))) {
         // NSB_FLUX_LPE = lanes per element (hex: 1 or 4), NSB_FLUX_MINB = blocks/SM the registers are bounded for
-        static const int LPEV = [] { const char* ev = getenv("NSB_FLUX_LPE"); return ev ? atoi(ev) : 1; }();
+        static const int LPEV = [] { const char* ev = getenv("NSB_FLUX_LPE"); return ev ? atoi(ev) : 4; }();
         static const int FMB = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 0; }();
         auto go = [&](auto ka, int lpe) -> cudaError_t {
             const int epb = BS / lpe;
-            const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * epb + NIP * (NSH * DIM + 1) + NIP * (NSH + 1)) + sizeof(int) * NIP * 12;
+            const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * epb + NIP * (NSH * DIM + 1) + NIP * (NSH + 1) + 24) + sizeof(int) * (NIP * 12 + 24);
             cudaError_t e2 = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
             if (e2 != cudaSuccess) return e2;
             ka<<<(unsigned)((m.n_elem + epb - 1) / epb), BS, smem_a, st>>>(k, m, u, s0, s1, rec, d_err);
             return cudaGetLastError();
         };
+#define NSB_FLUX_GO(MB, LP) (k.time_dep ? go(fv1_flux_kernel<E, STAB, false, BS, MB, true, LP, true>, LP) : go(fv1_flux_kernel<E, STAB, false, BS, MB, true, LP, false>, LP))
         if constexpr (E == 3) {
-            if (LPEV == 4) e = FMB == 2 ? go(fv1_flux_kernel<E, STAB, false, BS, 2, true, 4>, 4) : FMB == 3 ? go(fv1_flux_kernel<E, STAB, false, BS, 3, true, 4>, 4)
-                             : FMB == 5 ? go(fv1_flux_kernel<E, STAB, false, BS, 5, true, 4>, 4) : go(fv1_flux_kernel<E, STAB, false, BS, 4, true, 4>, 4);
-            else e = FMB == 3 ? go(fv1_flux_kernel<E, STAB, false, BS, 3, true, 1>, 1) : go(fv1_flux_kernel<E, STAB, false, BS, 2, true, 1>, 1);
-        } else e = go(fv1_flux_kernel<E, STAB, false, BS, 2, true, 1>, 1);
+            if (LPEV == 4) e = FMB == 3 ? NSB_FLUX_GO(3, 4) : NSB_FLUX_GO(4, 4);
+            else e = FMB == 3 ? NSB_FLUX_GO(3, 1) : NSB_FLUX_GO(2, 1);
+        } else e = NSB_FLUX_GO(2, 1);
+#undef NSB_FLUX_GO
         if (e != cudaSuccess) return e;
     }
+    if (!(stages & 2)) return cudaSuccess;
     static const int WPB = [] { const char* ev = getenv("NSB_SPLIT_WPB"); const int v = ev ? atoi(ev) : 2; return (v >= 1 && v <= 2) ? v : 2; }();
     constexpr size_t tab_bytes = (sizeof(int32_t) * NSH * ET<E>::NINC + 15) & ~(size_t)15;
     const size_t smem = tab_bytes + split_warp_bytes<E, CHP>(m.max_cnt) * WPB;
@@ -139,22 +142,24 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, WPB * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (rows_bps > 0 && occ > rows_bps) occ = rows_bps;
     const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
+    if (nblk <= 0) return cudaSuccess;
     e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, rec, j0, u, beta, val, def, work_counter);
     return cudaGetLastError();
 }
-cudaError_t NSB_CAT(launch_split_, NSB_ELEM)(NSB_GATHER_ARGS, const double* j0)
+cudaError_t NSB_CAT(launch_split_, NSB_ELEM)(NSB_GATHER_ARGS, const double* j0, int stages, int rows_bps)
 {
     static const int CHV = [] { const char* ev = getenv("NSB_SPLIT_CH"); return ev ? atoi(ev) : 4; }();
     static const int MINBV = [] { const char* ev = getenv("NSB_SPLIT_MINB"); return ev ? atoi(ev) : 12; }();
-#define NSB_SPLIT_GO(CH, MB) (k.stab == STAB_FIELDS ? split_t<STAB_FIELDS, CH, MB>(NSB_GFWD, j0) : split_t<STAB_NONE, CH, MB>(NSB_GFWD, j0))
+#define NSB_SPLIT_GO(CH, MB) (k.stab == STAB_FIELDS ? split_t<STAB_FIELDS, CH, MB>(NSB_GFWD, j0, stages, rows_bps) : split_t<STAB_NONE, CH, MB>(NSB_GFWD, j0, stages, rows_bps))
     if constexpr (E == 3) {
-        if (CHV == 4) return MINBV == 12 ? NSB_SPLIT_GO(4, 12) : NSB_SPLIT_GO(4, 8);
-        if (MINBV == 12) return NSB_SPLIT_GO(0, 12);
+        if (CHV == 4) return MINBV == 16 ? NSB_SPLIT_GO(4, 16) : NSB_SPLIT_GO(4, 12);
+        return MINBV == 16 ? NSB_SPLIT_GO(0, 16) : NSB_SPLIT_GO(0, 12);
     }
-    return MINBV == 12 ? NSB_SPLIT_GO(0, 12) : NSB_SPLIT_GO(0, 8);
+    return NSB_SPLIT_GO(0, 12);
 #undef NSB_SPLIT_GO
 }
 cudaError_t NSB_CAT(launch_j0_, NSB_ELEM)(const MeshDev& m, int laplace, double* j0, cudaStream_t st, int sm_count)

@@ -87,7 +87,7 @@ NSB_DEV double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const doub
 // thread's shared column xs. Same tests as side_ray_cut (ns_fv1.cuh), first hit in reference order wins.
 template <int E, int BS>
 NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const double* from, const double* dir,
-                             int& side_out, double* gcut, double* lcut)
+                             int& side_out, double* gcut, double* lcut, const int* __restrict__ sidetab, const double* __restrict__ cortab)
 {
     constexpr int DIM = ET<E>::DIM, NSIDE = ET<E>::NSIDE;
     constexpr double S = NSB_RAY_SMALL;
@@ -110,11 +110,11 @@ NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const doubl
         }
         if (!found) return false;
         const double t = tn / bdet, bc = n1 / bdet;
-        const int p0 = tab::SIDE[E][best][0], p1 = tab::SIDE[E][best][1];
+        const int p0 = sidetab[best * 4], p1 = sidetab[best * 4 + 1];
 #pragma unroll
         for (int d = 0; d < 2; d++) {
             gcut[d] = from[d] + t * dir[d];
-            lcut[d] = (1 - bc) * tab::CORNER[E][p0][d] + bc * tab::CORNER[E][p1][d];
+            lcut[d] = (1 - bc) * cortab[p0 * 3 + d] + bc * cortab[p1 * 3 + d];
         }
         side_out = best;
         return true;
@@ -156,11 +156,11 @@ NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const doubl
         if (!found) return false;
         const double t = tn / bdet, b1 = n1 / bdet, b2 = n2 / bdet;
         const int s = best / TPS, kk = best - s * TPS;
-        const int p0 = tab::SIDE[E][s][0], p1 = tab::SIDE[E][s][1 + kk], p2 = tab::SIDE[E][s][2 + kk];
+        const int p0 = sidetab[s * 4], p1 = sidetab[s * 4 + 1 + kk], p2 = sidetab[s * 4 + 2 + kk];
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             gcut[d] = from[d] + t * dir[d];
-            lcut[d] = (1 - b1 - b2) * tab::CORNER[E][p0][d] + b1 * tab::CORNER[E][p1][d] + b2 * tab::CORNER[E][p2][d];
+            lcut[d] = (1 - b1 - b2) * cortab[p0 * 3 + d] + b1 * cortab[p1 * 3 + d] + b2 * cortab[p2 * 3 + d];
         }
         side_out = s;
         return true;
@@ -170,7 +170,8 @@ NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const doubl
 // upwind shapes of the current ip (warp-uniform `type`, `from`, `to`); see upwind_ip in ns_fv1.cuh
 template <int E, int BS>
 NSB_DEV bool upwind_uniform(int type, const double* __restrict__ xs, int tid, const double* n, const double* xip,
-                            const double* N, int from, int to, const double* vel, double* up, double& len)
+                            const double* N, int from, int to, const double* vel, double* up, double& len,
+                            const int* __restrict__ sidetab, const double* __restrict__ cortab)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
     if (type == UPW_NO) {
@@ -194,13 +195,13 @@ NSB_DEV bool upwind_uniform(int type, const double* __restrict__ xs, int tid, co
     for (int k = 0; k < NSH; k++) up[k] = 0.0;
     if (sqrt(dotv<DIM>(vel, vel)) < 1e-14) { len = 1.0; return true; }      // upwind.cpp:407-413, 531-537
     int side = 0; double gc[DIM], lc[DIM];
-    if (!ray_cut_uniform<E, BS>(xs, tid, xip, vel, side, gc, lc)) { len = 1.0; return false; }
+    if (!ray_cut_uniform<E, BS>(xs, tid, xip, vel, side, gc, lc, sidetab, cortab)) { len = 1.0; return false; }
     constexpr int NSC = (DIM == 2) ? 2 : (E == E_TET ? 3 : 4);
     if (type == UPW_SKEWED) {                                    // GetNodeNextToCut, upwind.cpp:337-379
         double mn = 1.79769313486231570e308; int bestc = 0;
 #pragma unroll
         for (int i = 0; i < NSC; i++) {
-            const int co = tab::SIDE[E][side][i];
+            const int co = sidetab[side * 4 + i];
             double dd = 0;
 #pragma unroll
             for (int d = 0; d < DIM; d++) { const double t = gc[d] - NSB_COL(xs, co * DIM + d); dd += t * t; }
@@ -217,7 +218,7 @@ NSB_DEV bool upwind_uniform(int type, const double* __restrict__ xs, int tid, co
         lagrange<E>(lc, Nc);
         int mask = 0;
 #pragma unroll
-        for (int i = 0; i < NSC; i++) mask |= 1 << tab::SIDE[E][side][i];
+        for (int i = 0; i < NSC; i++) mask |= 1 << sidetab[side * 4 + i];
 #pragma unroll
         for (int k = 0; k < NSH; k++) up[k] = ((mask >> k) & 1) ? Nc[k] : 0.0;
         len = sqrt(dist2<DIM>(xip, gc));
@@ -297,7 +298,7 @@ template <int E> struct LeanRec;
 
 // LPE = lanes per element: the SCVFs of an element are dealt to LPE adjacent lanes (ip = ii * LPE + sub), the element's
 // unknowns / coordinates live once in a shared column used by all of them. LPE = 1 is the thread-per-element layout.
-template <int E, int STAB, bool EXACT, int NT, int MINB = 3, bool LEAN = false, int LPE = 1>
+template <int E, int STAB, bool EXACT, int NT, int MINB = 3, bool LEAN = false, int LPE = 1, bool TD = true>
 __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m,
                                                       const double* __restrict__ u, const double* __restrict__ s0,
                                                       const double* __restrict__ s1, double* __restrict__ rec,
@@ -321,7 +322,14 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
     double* us = vs + NSH * BS;                                  // [NSH*NF][BS] nodal unknowns (the `u` argument)
     double* dnt = us + NSH * NF * BS;                            // [NIP][DSTR] local shape gradients at the ips
     double* Nt = dnt + NIP * DSTR;                               // [NIP][NSTR] shape values at the ips
-    int* iptab = reinterpret_cast<int*>(Nt + NIP * NSTR);        // [NIP][12]   from, to, face corners (LPE > 1)
+    double* cortab = Nt + NIP * NSTR;                            // [8][3]      reference corners (tab::CORNER)
+    int* sidetab = reinterpret_cast<int*>(cortab + 24);          // [6][4]      corners of the sides (tab::SIDE)
+    int* iptab = sidetab + 24;                                   // [NIP][12]   from, to, face corners (LPE > 1)
+    for (int i = threadIdx.x; i < 24; i += NT) {
+        cortab[i] = tab::CORNER[E][i / 3][i % 3];
+        const int v = tab::SIDE[E][i / 4][i % 4];
+        sidetab[i] = v < 0 ? 0 : v;
+    }
     for (int i = threadIdx.x; i < NIP * NSH * DIM; i += NT) dnt[(i / (NSH * DIM)) * DSTR + i % (NSH * DIM)] = tab::C_DNIP[E][i / (NSH * DIM)][(i / DIM) % NSH][i % DIM];
     for (int i = threadIdx.x; i < NIP * NSH; i += NT) Nt[(i / NSH) * NSTR + i % NSH] = tab::NIPSH[E][i / NSH][i % NSH];
     if constexpr (SMT) {
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
     int64_t e = (int64_t)blockIdx.x * BS + tid;
     if constexpr (LPE == 1) { if (e >= m.n_elem) return; }       // no block-wide barriers below
     else if (e >= m.n_elem) e = m.n_elem - 1;                    // surplus lanes redo the last element (identical values)
-    const bool td = p.time_dep;
+    const bool td = TD && p.time_dep;                            // TD = false: the time-dependent closure is compiled out
     // ---- element data: unknowns, coordinates and volumes in the element's shared column ----
     const int32_t* nd = m.conn + e * NSH;                        // re-read where needed (time-dependent closure only)
 #pragma unroll
@@ -407,12 +415,12 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
 #pragma unroll
         for (int k = 0; k < NSH; k++) { up[k] = 0.0; dnm[k] = 0.0; }
         if (!p.stokes) {
-            ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, std, up, uplen);
+            ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, std, up, uplen, sidetab, cortab);
             if (FLOW) {                                          // update_downwind, upwind_interface.h:157-165
                 double neg[DIM], dn[NSH];
 #pragma unroll
                 for (int d = 0; d < DIM; d++) neg[d] = -1.0 * std[d];
-                ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, neg, dn, dnlen);
+                ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, neg, dn, dnlen, sidetab, cortab);
 #pragma unroll
                 for (int k = 0; k < NSH; k++) dnm[k] = dn[k] - up[k];
             }
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
 #pragma unroll
         for (int d = 0; d < DIM; d++) U[d] = 0.0;
         if (!p.stokes) {
-            if (p.upw_conv != p.upw_stab) { double l2; ok &= upwind_uniform<E, BS>(p.upw_conv, xs, tid, n, xip, N, from, to, std, up, l2); }
+            if (p.upw_conv != p.upw_stab) { double l2; ok &= upwind_uniform<E, BS>(p.upw_conv, xs, tid, n, xip, N, from, to, std, up, l2, sidetab, cortab); }
 #pragma unroll
             for (int k = 0; k < NSH; k++)
 #pragma unroll

@@ -12,9 +12,10 @@
 //
 //   fv1_j0_kernel          once per mesh: warp per node, deterministic (adjacency order), J0[node][rf < DIM][slot][cf]
 //   fv1_flux_kernel<LEAN>  (ns_owner.cuh) writes [F | n | cK | dK | pK = -G_k.n / diag] per SCVF
-//   fv1_rows_split_kernel  warp per node: TMA bulk copies of the node's J0 rows and of the incident lean records,
-//                          lane = (element, corner) sums its NINC SCVFs in registers, per-slot accumulators in shared
-//                          memory, rows written once:  out = {nu rho, 1} * scale_a * J0 + state part (+ lumped mass).
+//   fv1_rows_split_kernel  warp per node: lane = (element, corner) loads its coefficients of the NINC incident lean records
+//                          directly and sums them in registers; per-slot accumulators in shared memory; the node's J0
+//                          rows arrive by one TMA bulk copy; rows written once:
+//                          out = {nu rho, 1} * scale_a * J0 + state part (+ lumped mass).
 #pragma once
 #include "ns_owner.cuh"
 
@@ -96,8 +97,15 @@ __global__ void __launch_bounds__(128) fv1_j0_kernel(MeshDev m, int laplace, dou
 }
 
 // ---- rows kernel of the split path --------------------------------------------------------------------
+// warp per node (atomic tickets). Per round of CH adjacent elements: one TMA bulk copy per incident lean record, all in
+// flight at once on a warp-private mbarrier (plus, in the first round, the node's J0 rows). lane = (jj, k) = corner k of
+// the jj-th of JP = 32 / NSH elements handled in parallel sums its NINC SCVFs in registers and adds the 5 values into
+// the per-slot accumulators of ITS copy jj (the same neighbour may be a corner of several adjacent elements; the
+// corners of one element are distinct nodes -> no conflicts inside a copy). The copies are merged in fixed order ->
+// bitwise deterministic. Rows are written once: out = {nu rho, 1} * scale_a * J0 + state part (+ lumped mass).
 template <int E, int CHP = 0> struct SplitCfg {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1, NINC = ET<E>::NINC, NIP = ET<E>::NIP;
+    static constexpr int JP = 32 / NSH;                            // adjacent elements handled in parallel
     static constexpr int CH = CHP ? CHP : ((DIM == 3) ? 8 : 16);   // adjacent elements staged per round (CH * NINC <= 32)
     static constexpr int NREC = CH * NINC;
     static constexpr int NV = DIM + 2;                             // accumulated values per slot: D, C[DIM], PP
@@ -115,10 +123,10 @@ __host__ __device__ constexpr int split_cnt_pad(int max_cnt) { return (max_cnt +
 template <int E, int CHP> __host__ __device__ constexpr size_t split_warp_bytes(int max_cnt)
 {
     using C = SplitCfg<E, CHP>;
-    return (sizeof(SplitWS<E, CHP>) + sizeof(double) * ((size_t)C::DIM * C::NF * max_cnt + (size_t)C::NV * split_cnt_pad(max_cnt)) + 15) & ~(size_t)15;
+    return (sizeof(SplitWS<E, CHP>) + sizeof(double) * ((size_t)C::DIM * C::NF * max_cnt + (size_t)C::JP * C::NV * split_cnt_pad(max_cnt)) + 15) & ~(size_t)15;
 }
 
-template <int E, int CHP = 0, int MINB = 8>
+template <int E, int CHP = 0, int MINB = 12>
 __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, MeshDev m, const double* __restrict__ rec,
                                                                 const double* __restrict__ j0, const double* __restrict__ u,
                                                                 double beta, double* __restrict__ val, double* __restrict__ def,
@@ -127,13 +135,14 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
     using C = SplitCfg<E, CHP>;
     using LR = LeanRec<E>;
     using WS = SplitWS<E, CHP>;
-    constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, NIP = C::NIP, NV = C::NV, RS = WS::RS;
+    constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, CH = C::CH, NIP = C::NIP, NV = C::NV, JP = C::JP, RS = WS::RS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // block layout: [inc table NSH*NINC ints, padded to 16 B][per warp: WS | j0 rows DIM*NF*max_cnt | acc NV*cntp]
+    // block layout: [inc table NSH*NINC ints, padded to 16 B][per warp: WS | j0 rows DIM*NF*max_cnt | acc JP*NV*cntp]
     int32_t* inctab = reinterpret_cast<int32_t*>(smem_raw);
     constexpr size_t tab_bytes = (sizeof(int32_t) * NSH * NINC + 15) & ~(size_t)15;
     const int cntp = split_cnt_pad(m.max_cnt);
+    const int accn = NV * cntp;                                  // doubles per accumulator copy
     const size_t per_warp = split_warp_bytes<E, CHP>(m.max_cnt);
     WS& ws = *reinterpret_cast<WS*>(smem_raw + tab_bytes + warp * per_warp);
     double* j0s = reinterpret_cast<double*>(smem_raw + tab_bytes + warp * per_warp + sizeof(WS));
@@ -147,8 +156,9 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
     const bool jac_a = p.what & W_JAC_A, def_a = p.what & W_DEF_A;
     // a defect-only pass needs the fluxes only (head of the record)
     const unsigned cp_bytes = (unsigned)sizeof(double) * (jac_a ? RS : LR::HEAD);
-    constexpr int JP = 32 / NSH;
     const int jj = lane / NSH, k = lane - jj * NSH;
+    const bool lane_on = jj < JP;
+    double* accj = acc + (lane_on ? jj : 0) * accn;
     const double s_visc = p.visc * p.rho * p.scale_a, s_pres = p.scale_a;
     (void)NIP;
 
@@ -164,10 +174,12 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
         const int rowlen = cnt * NF;
         const unsigned j0_bytes = jac_a ? (unsigned)(sizeof(double) * DIM * NF) * (unsigned)cnt : 0u;
         __syncwarp();                                            // the previous node's output stage has read j0s / acc
-        if (want_jac) for (int i = lane; i < NV * cntp; i += 32) acc[i] = 0.0;
-        double fsum[NF], vsum = 0.0;
-#pragma unroll
-        for (int q = 0; q < NF; q++) fsum[q] = 0.0;
+        if (want_jac) {
+            double2* z = reinterpret_cast<double2*>(acc);
+            const int nz = (JP * accn) >> 1;
+            for (int i = lane; i < nz; i += 32) z[i] = make_double2(0.0, 0.0);
+        }
+        double fs = 0.0, vsum = 0.0;                             // lane (jj, k < NF): signed flux component k; SCV volumes
         int self_slot = 0;
         for (int64_t qb = q0; qb < q1; qb += CH) {
             const int nj = (int)((q1 - qb) < CH ? (q1 - qb) : CH);
@@ -199,24 +211,20 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             mbar_wait(&ws.bar, phase);
             phase ^= 1u;
             if (first) self_slot = ws.slot[0][sslot];
-            if (def_a && lane < nrec) {
-                const double sgr = (ipx_r & 256) ? -1.0 : 1.0;
-#pragma unroll
-                for (int q = 0; q < NF; q++) fsum[q] += sgr * ws.rec[lane][LR::O_F + q];
-            }
-            if (jac_a) {
-                for (int jb = 0; jb < nj; jb += JP) {
-                    const int j = jb + jj;
-                    const bool act = (jj < JP) && (j < nj);
+            for (int jb = 0; jb < nj; jb += JP) {
+                const int j = jb + jj;
+                if (lane_on && j < nj) {
                     double D = 0.0, PP = 0.0, Cn[DIM];
 #pragma unroll
                     for (int d = 0; d < DIM; d++) Cn[d] = 0.0;
-                    if (act) {
 #pragma unroll
-                        for (int t = 0; t < NINC; t++) {
-                            const int r = j * NINC + t;
-                            const double* rc = ws.rec[r];
-                            const double sg = (ws.ipx[r] & 256) ? -p.scale_a : p.scale_a;
+                    for (int t = 0; t < NINC; t++) {
+                        const int r = j * NINC + t;
+                        const double* rc = ws.rec[r];
+                        const bool neg = ws.ipx[r] & 256;
+                        if (def_a && k < NF) { const double f = rc[LR::O_F + k]; fs += neg ? -f : f; }
+                        if (jac_a) {
+                            const double sg = neg ? -p.scale_a : p.scale_a;
                             D += sg * rc[LR::O_DK + k];
                             PP += sg * rc[LR::O_PK + k];
                             const double w = sg * rc[LR::O_CK + k];
@@ -224,37 +232,35 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
                             for (int d = 0; d < DIM; d++) Cn[d] += w * rc[LR::O_N + d];
                         }
                     }
-                    // the same neighbour may be a corner of several of the JP elements: they take turns (fixed order ->
-                    // bitwise deterministic); the corners of one element are distinct nodes
-                    const int ns = (nj - jb) < JP ? (nj - jb) : JP;
-                    const int slot = act ? ws.slot[j][k] : 0;
-                    for (int s = 0; s < ns; s++) {
-                        if (act && jj == s) {
-                            acc[slot] += D;
+                    if (jac_a) {
+                        const int slot = ws.slot[j][k];
+                        accj[slot] += D;
 #pragma unroll
-                            for (int d = 0; d < DIM; d++) acc[(1 + d) * cntp + slot] += Cn[d];
-                            acc[(1 + DIM) * cntp + slot] += PP;
-                        }
-                        __syncwarp();
+                        for (int d = 0; d < DIM; d++) accj[(1 + d) * cntp + slot] += Cn[d];
+                        accj[(1 + DIM) * cntp + slot] += PP;
                     }
                 }
             }
         }
         __syncwarp();
+        // deterministic reductions: SCV volume of the node (butterfly), defect fluxes (lane q < NF sums its component over jj)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
         const double volsum = vsum;
         double dsum = 0.0;
         if (def_a) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int q = 0; q < NF; q++) fsum[q] += __shfl_xor_sync(0xffffffffu, fsum[q], o);
-#pragma unroll
-            for (int q = 0; q < NF; q++) if (lane == q) dsum = fsum[q];
+            for (int j2 = 0; j2 < JP; j2++) dsum += __shfl_sync(0xffffffffu, fs, j2 * NSH + (lane < NF ? lane : 0));
         }
         if (want_jac) {
-            if ((p.what & W_JAC_M) && lane == 0) acc[self_slot] += p.scale_m * volsum * p.rho;     // add_jac_M_elem :781-808
+            // merge the JP accumulator copies (fixed order) into copy 0, add the lumped mass (add_jac_M_elem :781-808)
+            for (int i = lane; i < accn; i += 32) {
+                double sacc = acc[i];
+#pragma unroll
+                for (int c = 1; c < JP; c++) sacc += acc[c * accn + i];
+                if ((p.what & W_JAC_M) && i == self_slot) sacc += p.scale_m * volsum * p.rho;
+                acc[i] = sacc;
+            }
             __syncwarp();
             double* out = val + b0 * (NF * NF);
             if constexpr (NF == 4) {
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
                     for (int i = lane; i < 2 * cnt; i += 32) {
                         const int slot = i >> 1, cp = i & 1;
                         double2 v = make_double2(0.0, 0.0);
-                        if (jac_a) { const double2 j = jrow[i]; v.x = j.x * s_visc; v.y = j.y * (cp ? s_pres : s_visc); }
+                        if (jac_a) { const double2 jv = jrow[i]; v.x = jv.x * s_visc; v.y = jv.y * (cp ? s_pres : s_visc); }
                         const double D = acc[slot];
                         if (rf == 2 * cp) v.x += D;
                         if (rf == 2 * cp + 1) v.y += D;
