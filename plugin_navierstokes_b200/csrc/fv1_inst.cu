@@ -105,13 +105,12 @@ cudaError_t NSB_CAT(launch_gather_, NSB_ELEM)(NSB_GATHER_ARGS)
     }
 }
 // ---- split path (ns_split.cuh): lean flux records + static table J0 ----
-// stages: 1 = flux kernel, 2 = rows kernel, 3 = both (one stream); rows_bps > 0 caps the rows blocks per SM (pipelined mode)
-template <int STAB, int CHP, int MINB>
-static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0, int stages, int rows_bps)
+template <int STAB, int CHP, int MINB, bool J0D = false>
+static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
 {
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
-    if ((stages & 1) && (k.what & (W_JAC_A | W_DEF_A))) {
+    if (k.what & (W_JAC_A | W_DEF_A)) {
         // NSB_FLUX_LPE = lanes per element (hex: 1 or 4), NSB_FLUX_MINB = blocks/SM the registers are bounded for
         static const int LPEV = [] { const char* ev = getenv("NSB_FLUX_LPE"); return ev ? atoi(ev) : 4; }();
         static const int FMB = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 0; }();
@@ -131,18 +130,17 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0, int stages, int ro
 #undef NSB_FLUX_GO
         if (e != cudaSuccess) return e;
     }
-    if (!(stages & 2)) return cudaSuccess;
     static const int WPB = [] { const char* ev = getenv("NSB_SPLIT_WPB"); const int v = ev ? atoi(ev) : 2; return (v >= 1 && v <= 2) ? v : 2; }();
     constexpr size_t tab_bytes = (sizeof(int32_t) * NSH * ET<E>::NINC + 15) & ~(size_t)15;
-    const size_t smem = tab_bytes + split_warp_bytes<E, CHP>(m.max_cnt) * WPB;
-    auto kb = fv1_rows_split_kernel<E, CHP, MINB>;
+    const size_t smem = tab_bytes + split_warp_bytes<E, CHP, J0D>(m.max_cnt) * WPB;
+    const bool fast = k.what == (W_JAC_A | W_DEF_A) && beta == 0.0;
+    auto kb = fast ? fv1_rows_split_kernel<E, CHP, MINB, J0D, true> : fv1_rows_split_kernel<E, CHP, MINB, J0D, false>;
     e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, WPB * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    if (rows_bps > 0 && occ > rows_bps) occ = rows_bps;
     const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
     if (nblk <= 0) return cudaSuccess;
     e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
@@ -150,12 +148,15 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0, int stages, int ro
     kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, rec, j0, u, beta, val, def, work_counter);
     return cudaGetLastError();
 }
-cudaError_t NSB_CAT(launch_split_, NSB_ELEM)(NSB_GATHER_ARGS, const double* j0, int stages, int rows_bps)
+cudaError_t NSB_CAT(launch_split_, NSB_ELEM)(NSB_GATHER_ARGS, const double* j0)
 {
     static const int CHV = [] { const char* ev = getenv("NSB_SPLIT_CH"); return ev ? atoi(ev) : 4; }();
     static const int MINBV = [] { const char* ev = getenv("NSB_SPLIT_MINB"); return ev ? atoi(ev) : 12; }();
-#define NSB_SPLIT_GO(CH, MB) (k.stab == STAB_FIELDS ? split_t<STAB_FIELDS, CH, MB>(NSB_GFWD, j0, stages, rows_bps) : split_t<STAB_NONE, CH, MB>(NSB_GFWD, j0, stages, rows_bps))
+#define NSB_SPLIT_GO(CH, MB) (k.stab == STAB_FIELDS ? split_t<STAB_FIELDS, CH, MB>(NSB_GFWD, j0) : split_t<STAB_NONE, CH, MB>(NSB_GFWD, j0))
+    static const int J0DV = [] { const char* ev = getenv("NSB_SPLIT_J0D"); return ev ? atoi(ev) : 0; }();
     if constexpr (E == 3) {
+        if (J0DV) return MINBV == 16 ? (k.stab == STAB_FIELDS ? split_t<STAB_FIELDS, 4, 16, true>(NSB_GFWD, j0) : split_t<STAB_NONE, 4, 16, true>(NSB_GFWD, j0))
+                                     : (k.stab == STAB_FIELDS ? split_t<STAB_FIELDS, 4, 12, true>(NSB_GFWD, j0) : split_t<STAB_NONE, 4, 12, true>(NSB_GFWD, j0));
         if (CHV == 4) return MINBV == 16 ? NSB_SPLIT_GO(4, 16) : NSB_SPLIT_GO(4, 12);
         return MINBV == 16 ? NSB_SPLIT_GO(0, 16) : NSB_SPLIT_GO(0, 12);
     }

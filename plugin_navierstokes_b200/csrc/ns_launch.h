@@ -21,7 +21,7 @@ struct LaunchInfo { int64_t launches = 0; };
     cudaError_t launch_scvvol_##E(int64_t n_elem, const int32_t* conn, const double* coords, double* scvvol, cudaStream_t st); \
     cudaError_t launch_geom_##E(int64_t n_elem, const int32_t* conn, const double* coords, double* rec, int stride, cudaStream_t st); \
     int scvf_record_doubles_##E(bool flow, bool exact);                                               \
-    cudaError_t launch_split_##E(NSB_GATHER_ARGS, const double* j0, int stages, int rows_bps);                                  \
+    cudaError_t launch_split_##E(NSB_GATHER_ARGS, const double* j0);                                  \
     cudaError_t launch_j0_##E(const MeshDev& m, int laplace, double* j0, cudaStream_t st, int sm_count); \
     int lean_record_doubles_##E();
 NSB_DECL(0) NSB_DECL(1) NSB_DECL(2) NSB_DECL(3)

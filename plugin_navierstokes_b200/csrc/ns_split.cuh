@@ -120,13 +120,16 @@ template <int E, int CHP = 0> struct SplitWS {
     uint8_t slot[C::CH][8];
 };
 __host__ __device__ constexpr int split_cnt_pad(int max_cnt) { return (max_cnt + 1) & ~1; }
-template <int E, int CHP> __host__ __device__ constexpr size_t split_warp_bytes(int max_cnt)
+// J0D: the node's J0 rows are read straight from global memory in the output stage (prefetched into L2 at the top of
+// the node) instead of being staged in shared memory by a bulk copy: smaller footprint per warp -> more warps per SM.
+template <int E, int CHP, bool J0D = false> __host__ __device__ constexpr size_t split_warp_bytes(int max_cnt)
 {
     using C = SplitCfg<E, CHP>;
-    return (sizeof(SplitWS<E, CHP>) + sizeof(double) * ((size_t)C::DIM * C::NF * max_cnt + (size_t)C::JP * C::NV * split_cnt_pad(max_cnt)) + 15) & ~(size_t)15;
+    return (sizeof(SplitWS<E, CHP>) + sizeof(double) * ((J0D ? 0 : (size_t)C::DIM * C::NF * max_cnt) + (size_t)C::JP * C::NV * split_cnt_pad(max_cnt)) + 15) & ~(size_t)15;
 }
 
-template <int E, int CHP = 0, int MINB = 12>
+// FAST: the standard pass (what = JAC_A | DEF_A, beta = 0) with the flags folded at compile time.
+template <int E, int CHP = 0, int MINB = 12, bool J0D = false, bool FAST = false>
 __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, MeshDev m, const double* __restrict__ rec,
                                                                 const double* __restrict__ j0, const double* __restrict__ u,
                                                                 double beta, double* __restrict__ val, double* __restrict__ def,
@@ -143,17 +146,19 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
     constexpr size_t tab_bytes = (sizeof(int32_t) * NSH * NINC + 15) & ~(size_t)15;
     const int cntp = split_cnt_pad(m.max_cnt);
     const int accn = NV * cntp;                                  // doubles per accumulator copy
-    const size_t per_warp = split_warp_bytes<E, CHP>(m.max_cnt);
+    const size_t per_warp = split_warp_bytes<E, CHP, J0D>(m.max_cnt);
     WS& ws = *reinterpret_cast<WS*>(smem_raw + tab_bytes + warp * per_warp);
     double* j0s = reinterpret_cast<double*>(smem_raw + tab_bytes + warp * per_warp + sizeof(WS));
-    double* acc = j0s + (size_t)DIM * NF * m.max_cnt;
+    double* acc = j0s + (J0D ? 0 : (size_t)DIM * NF * m.max_cnt);
     for (int i = threadIdx.x; i < NSH * NINC; i += blockDim.x)
         inctab[i] = tab::INC[E][i / NINC][i % NINC] | (tab::INC_SIGN[E][i / NINC][i % NINC] < 0 ? 256 : 0);
     if (lane == 0) mbar_init(&ws.bar, 1);
     __syncthreads();
     unsigned phase = 0;
-    const bool want_jac = p.what & (W_JAC_A | W_JAC_M), want_def = p.what & (W_DEF_A | W_DEF_M | W_RHS);
-    const bool jac_a = p.what & W_JAC_A, def_a = p.what & W_DEF_A;
+    const int what = FAST ? (W_JAC_A | W_DEF_A) : p.what;
+    if (FAST) beta = 0.0;
+    const bool want_jac = what & (W_JAC_A | W_JAC_M), want_def = what & (W_DEF_A | W_DEF_M | W_RHS);
+    const bool jac_a = what & W_JAC_A, def_a = what & W_DEF_A;
     // a defect-only pass needs the fluxes only (head of the record)
     const unsigned cp_bytes = (unsigned)sizeof(double) * (jac_a ? RS : LR::HEAD);
     const int jj = lane / NSH, k = lane - jj * NSH;
@@ -162,22 +167,43 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
     const double s_visc = p.visc * p.rho * p.scale_a, s_pres = p.scale_a;
     (void)NIP;
 
+    // The header of a node is a chain of dependent global loads (ticket -> adjacency range / block row -> adjacency
+    // entries). It is fetched one node ahead: the ticket is taken at the top of the previous node, the ranges are
+    // loaded while that node's records are in flight, the first adjacency entries while its rows are written.
+    auto take = [&]() -> unsigned long long { unsigned long long t = 0; if (lane == 0) t = atomicAdd(work_counter, 1ULL); return t; };
+    int64_t nx_ai = (int64_t)__shfl_sync(0xffffffffu, take(), 0);
+    int64_t nx_a = 0, nx_q0 = 0, nx_q1 = 0, nx_b0 = 0, nx_b1 = 0;
+    int32_t nx_ad = 0;
+    if (nx_ai < m.n_node) {
+        nx_a = m.node_order ? (int64_t)m.node_order[nx_ai] : nx_ai;
+        nx_q0 = m.adj_ptr[nx_a]; nx_q1 = m.adj_ptr[nx_a + 1]; nx_b0 = m.brow[nx_a]; nx_b1 = m.brow[nx_a + 1];
+        nx_ad = (nx_q0 + lane < nx_q1 && lane < CH) ? m.adj[nx_q0 + lane] : 0;
+    }
     for (;;) {
-        unsigned long long ai_u = 0;
-        if (lane == 0) ai_u = atomicAdd(work_counter, 1ULL);
-        const int64_t ai = (int64_t)__shfl_sync(0xffffffffu, ai_u, 0);
-        if (ai >= m.n_node) break;
-        const int64_t a = m.node_order ? (int64_t)m.node_order[ai] : ai;
-        const int64_t q0 = m.adj_ptr[a], q1 = m.adj_ptr[a + 1];
-        const int64_t b0 = m.brow[a];
-        const int cnt = (int)(m.brow[a + 1] - b0);
+        if (nx_ai >= m.n_node) break;
+        const int64_t a = nx_a, q0 = nx_q0, q1 = nx_q1, b0 = nx_b0;
+        const int cnt = (int)(nx_b1 - nx_b0);
+        const int32_t ad_first = nx_ad;
+        const unsigned long long tk = take();                    // ticket of the next node; consumed below
         const int rowlen = cnt * NF;
-        const unsigned j0_bytes = jac_a ? (unsigned)(sizeof(double) * DIM * NF) * (unsigned)cnt : 0u;
+        const unsigned j0_bytes = (jac_a && !J0D) ? (unsigned)(sizeof(double) * DIM * NF) * (unsigned)cnt : 0u;
+        const double* j0g = j0 + b0 * (DIM * NF);
+        if (J0D && jac_a) {
+            const int nline = (cnt * DIM * NF * (int)sizeof(double) + 127) >> 7;
+            for (int i = lane; i < nline; i += 32) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(j0g + i * 16));
+        }
         __syncwarp();                                            // the previous node's output stage has read j0s / acc
         if (want_jac) {
             double2* z = reinterpret_cast<double2*>(acc);
             const int nz = (JP * accn) >> 1;
             for (int i = lane; i < nz; i += 32) z[i] = make_double2(0.0, 0.0);
+        }
+        if (q0 >= q1) {                                          // unreferenced node: no records will be waited for
+            nx_ai = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+            if (nx_ai < m.n_node) {
+                nx_a = m.node_order ? (int64_t)m.node_order[nx_ai] : nx_ai;
+                nx_q0 = m.adj_ptr[nx_a]; nx_q1 = m.adj_ptr[nx_a + 1]; nx_b0 = m.brow[nx_a]; nx_b1 = m.brow[nx_a + 1];
+            }
         }
         double fs = 0.0, vsum = 0.0;                             // lane (jj, k < NF): signed flux component k; SCV volumes
         int self_slot = 0;
@@ -185,7 +211,8 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             const int nj = (int)((q1 - qb) < CH ? (q1 - qb) : CH);
             const int nrec = nj * NINC;
             __syncwarp();
-            const int32_t ad = (lane < nj) ? m.adj[qb + lane] : 0;
+            const bool first = (qb == q0);
+            const int32_t ad = first ? ad_first : ((lane < nj) ? m.adj[qb + lane] : 0);
             const int e_l = ad / NSH, la_l = ad - e_l * NSH;
             const int rj = lane / NINC, rt = lane - rj * NINC;
             const int e_r = __shfl_sync(0xffffffffu, e_l, rj < CH ? rj : 0);
@@ -193,12 +220,12 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             const int ipx_r = inctab[la_r * NINC + rt];
             const int64_t gi_r = (int64_t)e_r * NIP + (ipx_r & 255);
             if (lane < nrec) ws.ipx[lane] = ipx_r;
+            // asynchronous staging: one TMA bulk copy per incident SCVF record (and the node's J0 rows), all in flight at once
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            const bool first = (qb == q0);
             if (lane == 0) mbar_arrive_expect_tx(&ws.bar, cp_bytes * (unsigned)nrec + (first ? j0_bytes : 0u));
             __syncwarp();
             if (lane < nrec) bulk_g2s(&ws.rec[lane][0], rec + gi_r * RS, cp_bytes, &ws.bar);
-            if (first && j0_bytes && lane == 31) bulk_g2s(j0s, j0 + b0 * (DIM * NF), j0_bytes, &ws.bar);
+            if (first && j0_bytes && lane == 31) bulk_g2s(j0s, j0g, j0_bytes, &ws.bar);
             if (lane < nj) {
                 const uint8_t* em = m.emap + (int64_t)ad * NSH;
                 if (NSH == 8) *reinterpret_cast<uint2*>(ws.slot[lane]) = __ldg(reinterpret_cast<const uint2*>(em));
@@ -207,6 +234,13 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
                 vsum += m.scvvol[ad];
             }
             const int sslot = __shfl_sync(0xffffffffu, la_l, 0);
+            if (first) {                                         // next node: ticket arrived -> load its ranges while the records fly
+                nx_ai = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+                if (nx_ai < m.n_node) {
+                    nx_a = m.node_order ? (int64_t)m.node_order[nx_ai] : nx_ai;
+                    nx_q0 = m.adj_ptr[nx_a]; nx_q1 = m.adj_ptr[nx_a + 1]; nx_b0 = m.brow[nx_a]; nx_b1 = m.brow[nx_a + 1];
+                }
+            }
             __syncwarp();
             mbar_wait(&ws.bar, phase);
             phase ^= 1u;
@@ -243,6 +277,7 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             }
         }
         __syncwarp();
+        nx_ad = (nx_ai < m.n_node && nx_q0 + lane < nx_q1 && lane < CH) ? m.adj[nx_q0 + lane] : 0;   // used at the top of the next node
         // deterministic reductions: SCV volume of the node (butterfly), defect fluxes (lane q < NF sums its component over jj)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
@@ -258,7 +293,7 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
                 double sacc = acc[i];
 #pragma unroll
                 for (int c = 1; c < JP; c++) sacc += acc[c * accn + i];
-                if ((p.what & W_JAC_M) && i == self_slot) sacc += p.scale_m * volsum * p.rho;
+                if ((what & W_JAC_M) && i == self_slot) sacc += p.scale_m * volsum * p.rho;
                 acc[i] = sacc;
             }
             __syncwarp();
@@ -266,11 +301,11 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             if constexpr (NF == 4) {
                 for (int rf = 0; rf < DIM; rf++) {
                     double2* orow = reinterpret_cast<double2*>(out + rf * rowlen);
-                    const double2* jrow = reinterpret_cast<const double2*>(j0s + rf * rowlen);
+                    const double2* jrow = reinterpret_cast<const double2*>((J0D ? j0g : j0s) + rf * rowlen);
                     for (int i = lane; i < 2 * cnt; i += 32) {
                         const int slot = i >> 1, cp = i & 1;
                         double2 v = make_double2(0.0, 0.0);
-                        if (jac_a) { const double2 jv = jrow[i]; v.x = jv.x * s_visc; v.y = jv.y * (cp ? s_pres : s_visc); }
+                        if (jac_a) { const double2 jv = J0D ? __ldcs(jrow + i) : jrow[i]; v.x = jv.x * s_visc; v.y = jv.y * (cp ? s_pres : s_visc); }
                         const double D = acc[slot];
                         if (rf == 2 * cp) v.x += D;
                         if (rf == 2 * cp + 1) v.y += D;
@@ -290,7 +325,7 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
                     double* orow = out + rf * rowlen;
                     for (int i = lane; i < rowlen; i += 32) {
                         const int slot = i / NF, cf = i - slot * NF;
-                        double v = jac_a ? j0s[rf * rowlen + i] * (cf < DIM ? s_visc : s_pres) : 0.0;
+                        double v = jac_a ? (J0D ? __ldcs(j0g + rf * rowlen + i) : j0s[rf * rowlen + i]) * (cf < DIM ? s_visc : s_pres) : 0.0;
                         if (cf == rf) v += acc[slot];
                         if (beta == 0.0) __stcs(orow + i, v);
                         else orow[i] = beta * orow[i] + v;
@@ -307,9 +342,9 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
         }
         if (want_def && lane < NF) {
             double d = def_a ? dsum : 0.0;
-            if ((p.what & W_RHS) && p.has_source && lane < DIM) d -= p.src[lane] * volsum * p.rho;
+            if ((what & W_RHS) && p.has_source && lane < DIM) d -= p.src[lane] * volsum * p.rho;
             d *= p.scale_a;
-            if ((p.what & W_DEF_M) && lane < DIM) d += p.scale_m * u[a * NF + lane] * volsum * p.rho;
+            if ((what & W_DEF_M) && lane < DIM) d += p.scale_m * u[a * NF + lane] * volsum * p.rho;
             double* q = def + a * NF + lane;
             *q = (beta == 0.0) ? d : beta * (*q) + d;
         }

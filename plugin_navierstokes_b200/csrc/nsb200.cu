@@ -55,15 +55,6 @@ struct nsb_ctx {
     size_t rec_bytes = 0; int rec_stride = 0;     // combined SCVF record table [geometry | flux] of the owner-computes path
     bool rec_lean = false;                        // ... or lean flux records of the split path (no geometry half)
     double* d_j0 = nullptr; int j0_laplace = -1;  // static Jacobian part of the split path (ns_split.cuh), built once per mesh
-    // pipelined split path: the elements are cut into pipe_k contiguous chunks; the rows of a node are assembled as soon as
-    // the chunk of its last adjacent element has its flux records. Flux kernels run on the caller's stream, rows kernels
-    // on a high-priority side stream, so that the FP64-bound flux work and the HBM-bound row output overlap.
-    int pipe_k = 0;
-    std::vector<int64_t> pipe_eptr, pipe_nptr;    // element / node (in pipe order) offsets per chunk
-    int32_t* d_pipe_order = nullptr;
-    unsigned long long* d_pipe_counters = nullptr;
-    cudaStream_t pipe_stream = nullptr;
-    std::vector<cudaEvent_t> pipe_ev;             // [pipe_k] flux(c) done, [pipe_k] = fork, [pipe_k + 1] = join
     int64_t *d_brow = nullptr, *d_adj_ptr = nullptr;
     uint8_t *d_emap = nullptr;
     FvcrDev fvcr{};
@@ -158,9 +149,7 @@ static void free_mesh(nsb_ctx* c)
     cudaFree(c->d_u); cudaFree(c->d_s0); cudaFree(c->d_s1); cudaFree(c->d_val); cudaFree(c->d_def);
     cudaFree(c->d_jloc); cudaFree(c->d_dloc); cudaFree(c->d_j0);
     c->d_j0 = nullptr; c->j0_laplace = -1; c->rec_lean = false;
-    cudaFree(c->d_pipe_order); cudaFree(c->d_pipe_counters); c->d_pipe_order = nullptr; c->d_pipe_counters = nullptr;
-    for (auto ev : c->pipe_ev) cudaEventDestroy(ev);
-    c->pipe_ev.clear(); c->pipe_k = 0;
+
     fvcr_free(c->fvcr);
     c->d_conn = c->d_adj = c->d_color_order = c->d_esides = c->d_node_order = nullptr; c->d_coords = c->d_scvvol = c->d_rec = nullptr; c->rec_bytes = 0; c->rec_stride = 0;
     c->d_brow = c->d_adj_ptr = nullptr; c->d_emap = nullptr;
@@ -175,7 +164,6 @@ extern "C" void nsb_destroy(nsb_ctx* c)
     cudaStreamSynchronize(c->stream);
     free_mesh(c);
     cudaFree(c->d_err); cudaFree(c->d_counter);
-    if (c->pipe_stream) cudaStreamDestroy(c->pipe_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -474,45 +462,6 @@ static int launch_elem(nsb_ctx* c, int sc, const KParams& k, const int32_t* list
     return NSB_OK;
 }
 
-// chunked element ranges + node order by "ready chunk" (= chunk of the node's last adjacent element) for the pipelined path
-static int ensure_pipeline(nsb_ctx* c, int K)
-{
-    if (c->pipe_k == K) return NSB_OK;
-    const int nsh = kNSH[c->elem];
-    const int64_t ne = c->n_elem, nn = c->n_node;
-    const int64_t per = (ne + K - 1) / K;
-    c->pipe_eptr.assign(K + 1, 0);
-    for (int i = 0; i <= K; i++) c->pipe_eptr[i] = std::min<int64_t>(ne, per * i);
-    // the adjacency lists are sorted by element index: the last entry is the node's last adjacent element
-    std::vector<int64_t> adj_ptr(nn + 1);
-    std::vector<int32_t> last(nn, 0);
-    CUDA_TRY(c, cudaMemcpy(adj_ptr.data(), c->d_adj_ptr, sizeof(int64_t) * (nn + 1), cudaMemcpyDeviceToHost));
-    {
-        std::vector<int32_t> adj(adj_ptr[nn]);
-        CUDA_TRY(c, cudaMemcpy(adj.data(), c->d_adj, sizeof(int32_t) * adj.size(), cudaMemcpyDeviceToHost));
-        for (int64_t a = 0; a < nn; a++) last[a] = adj_ptr[a + 1] > adj_ptr[a] ? (int32_t)((adj[adj_ptr[a + 1] - 1] / nsh) / per) : 0;
-    }
-    c->pipe_nptr.assign(K + 1, 0);
-    for (int64_t a = 0; a < nn; a++) c->pipe_nptr[last[a] + 1]++;
-    for (int i = 0; i < K; i++) c->pipe_nptr[i + 1] += c->pipe_nptr[i];
-    std::vector<int32_t> order(nn);
-    { std::vector<int64_t> pos(c->pipe_nptr.begin(), c->pipe_nptr.end() - 1);
-      for (int64_t a = 0; a < nn; a++) order[pos[last[a]]++] = (int32_t)a; }
-    cudaFree(c->d_pipe_order); cudaFree(c->d_pipe_counters); c->d_pipe_order = nullptr; c->d_pipe_counters = nullptr;
-    CUDA_TRY(c, upload(&c->d_pipe_order, order.data(), order.size()));
-    CUDA_TRY(c, cudaMalloc(&c->d_pipe_counters, sizeof(unsigned long long) * K));
-    if (!c->pipe_stream) {
-        int lo = 0, hi = 0;
-        CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CUDA_TRY(c, cudaStreamCreateWithPriority(&c->pipe_stream, cudaStreamNonBlocking, hi));
-    }
-    for (auto ev : c->pipe_ev) cudaEventDestroy(ev);
-    c->pipe_ev.assign(K + 2, nullptr);
-    for (auto& ev : c->pipe_ev) CUDA_TRY(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    c->pipe_k = K;
-    return NSB_OK;
-}
-
 static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const double* s0, const double* s1, double beta,
                          double* val, double* def)
 {
@@ -564,40 +513,11 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
             CUDA_TRY(c, e);
             c->j0_laplace = k.laplace;
         }
-        auto split_go = [&](const MeshDev& mm, double* recp, cudaStream_t st, unsigned long long* counter, int stages, int bps) -> cudaError_t {
-#define NSB_GO(fn) fn(k, mm, recp, u, s0, s1, beta, val, def, c->d_err, st, c->sm_count, counter, c->d_j0, stages, bps)
-            switch (c->elem) { case 0: return NSB_GO(launch_split_0); case 1: return NSB_GO(launch_split_1);
-                               case 2: return NSB_GO(launch_split_2); default: return NSB_GO(launch_split_3); }
+#define NSB_GO(fn) fn(k, m, c->d_rec, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter, c->d_j0)
+        switch (c->elem) { case 0: e = NSB_GO(launch_split_0); break; case 1: e = NSB_GO(launch_split_1); break;
+                           case 2: e = NSB_GO(launch_split_2); break; default: e = NSB_GO(launch_split_3); }
 #undef NSB_GO
-        };
-        static const int pipe_req = [] { const char* ev = getenv("NSB_PIPE"); return ev ? atoi(ev) : 0; }();
-        static const int pipe_bps = [] { const char* ev = getenv("NSB_PIPE_ROWS_BPS"); return ev ? atoi(ev) : 6; }();
         const bool flux_needed = k.what & (W_JAC_A | W_DEF_A);
-        if (pipe_req > 1 && flux_needed && c->n_elem >= (int64_t)pipe_req * 4096) {
-            int rc = ensure_pipeline(c, pipe_req);
-            if (rc) return rc;
-            const int K = c->pipe_k;
-            const int nsh = kNSH[c->elem];
-            CUDA_TRY(c, cudaEventRecord(c->pipe_ev[K], c->stream));                 // fork: the side stream sees u and earlier work
-            CUDA_TRY(c, cudaStreamWaitEvent(c->pipe_stream, c->pipe_ev[K], 0));
-            for (int ch = 0; ch < K; ch++) {
-                const int64_t e0 = c->pipe_eptr[ch], e1 = c->pipe_eptr[ch + 1];
-                MeshDev mf = m;
-                mf.n_elem = e1 - e0; mf.conn = m.conn + e0 * nsh; mf.scvvol = m.scvvol + e0 * nsh;
-                CUDA_TRY(c, split_go(mf, c->d_rec + (size_t)e0 * kNIP[c->elem] * c->rec_stride, c->stream, nullptr, 1, 0));
-                CUDA_TRY(c, cudaEventRecord(c->pipe_ev[ch], c->stream));
-                CUDA_TRY(c, cudaStreamWaitEvent(c->pipe_stream, c->pipe_ev[ch], 0));
-                MeshDev mr = m;
-                mr.node_order = c->d_pipe_order + c->pipe_nptr[ch];
-                mr.n_node = c->pipe_nptr[ch + 1] - c->pipe_nptr[ch];
-                CUDA_TRY(c, split_go(mr, c->d_rec, c->pipe_stream, c->d_pipe_counters + ch, 2, ch + 1 < K ? pipe_bps : 0));
-                c->launches += 2;
-            }
-            CUDA_TRY(c, cudaEventRecord(c->pipe_ev[K + 1], c->pipe_stream));        // join
-            CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->pipe_ev[K + 1], 0));
-            return NSB_OK;
-        }
-        e = split_go(m, c->d_rec, c->stream, c->d_counter, 3, 0);
         c->launches += flux_needed ? 2 : 1;
         CUDA_TRY(c, e);
         return NSB_OK;

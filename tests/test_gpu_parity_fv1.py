@@ -216,3 +216,38 @@ def test_unreferenced_nodes_and_ragged_valence(ora, elem, mode):
     assert eg < TOL and ee < TOL
     assert np.all(gd.reshape(-1, nf)[~used] == 0.0)
     disc.close()
+
+
+@pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
+def test_split_path_reuse_across_parameter_changes(ora, elem):
+    """one context, many passes: the split path caches the static Jacobian part J0 per mesh. It must follow a
+    change of the laplace flag (J0 rebuilt), of viscosity / density (run-time scale of J0), and a detour through the
+    general rows kernel (exact Newton, FLOW) and back (record table re-laid out)."""
+    coords, conn, u = parity.make_case(elem, SIZES[elem], seed=3)
+    dim = coords.shape[1]
+    E = ora.ELEM[elem]
+    disc = pkg.NavierStokesFV1(FCTS[dim], "Inner")
+    parity.configure(disc, upwind="lps", stab="fields")
+    disc.set_grid(elem, conn, coords)
+    rowptr, colind = ora.fv1_csr(E, conn, coords.shape[0])
+    what = capi.JAC_A | capi.DEF_A
+    steps = [dict(), dict(laplace=True), dict(laplace=True, visc=3e-3, density=1.7), dict(exact=1.0), dict(),
+             dict(stab="flow"), dict(visc=5e-2), dict(laplace=True)]
+    for st in steps:
+        visc, dens = st.get("visc", 1e-2), st.get("density", 1.0)
+        disc.set_kinematic_viscosity(visc)
+        disc.set_density(dens)
+        disc.set_laplace(bool(st.get("laplace", False)))
+        disc.set_exact_jacobian(st.get("exact", 0.0))
+        disc.set_stabilization(st.get("stab", "fields"), "raw")
+        disc.set_upwind("lps")
+        disc.prep_elem_loop()
+        p = ora.make_params(elem=elem, upwind="lps", stab=st.get("stab", "fields"), diff_len="raw", kin_visc=visc, density=dens,
+                            laplace=st.get("laplace", False), exact_jac=st.get("exact", 0.0))
+        ov, od = ora.assemble(p, conn, coords, u, rowptr, colind, what)
+        gv, gd = disc.assemble(what, u, scatter_mode=capi.SCATTER_GATHER)
+        eg, ee = parity.entry_errors(gv, ov, rowptr)
+        assert eg < TOL and ee < TOL, ("jacobian", elem, st, eg, ee)
+        eg, ee = parity.entry_errors(gd, od)
+        assert eg < TOL and ee < TOL, ("defect", elem, st, eg, ee)
+    disc.close()
