@@ -170,8 +170,12 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
     // The header of a node is a chain of dependent global loads (ticket -> adjacency range / block row -> adjacency
     // entries). It is fetched one node ahead: the ticket is taken at the top of the previous node, the ranges are
     // loaded while that node's records are in flight, the first adjacency entries while its rows are written.
-    auto take = [&]() -> unsigned long long { unsigned long long t = 0; if (lane == 0) t = atomicAdd(work_counter, 1ULL); return t; };
-    int64_t nx_ai = (int64_t)__shfl_sync(0xffffffffu, take(), 0);
+    // Tickets are taken TG nodes at a time (one atomic per TG nodes; neighbouring warps still work on a tight window).
+    constexpr int TG = 8;
+    auto take = [&]() -> unsigned long long { unsigned long long t = 0; if (lane == 0) t = atomicAdd(work_counter, (unsigned long long)TG); return t; };
+    int64_t tk_base = (int64_t)__shfl_sync(0xffffffffu, take(), 0);
+    int tk_off = 0;
+    int64_t nx_ai = tk_base;
     int64_t nx_a = 0, nx_q0 = 0, nx_q1 = 0, nx_b0 = 0, nx_b1 = 0;
     int32_t nx_ad = 0;
     if (nx_ai < m.n_node) {
@@ -184,7 +188,8 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
         const int64_t a = nx_a, q0 = nx_q0, q1 = nx_q1, b0 = nx_b0;
         const int cnt = (int)(nx_b1 - nx_b0);
         const int32_t ad_first = nx_ad;
-        const unsigned long long tk = take();                    // ticket of the next node; consumed below
+        const bool need_tk = (++tk_off == TG);                   // next node: a new ticket batch, taken now and consumed below
+        const unsigned long long tk = need_tk ? take() : 0ULL;
         const int rowlen = cnt * NF;
         const unsigned j0_bytes = (jac_a && !J0D) ? (unsigned)(sizeof(double) * DIM * NF) * (unsigned)cnt : 0u;
         const double* j0g = j0 + b0 * (DIM * NF);
@@ -199,7 +204,8 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             for (int i = lane; i < nz; i += 32) z[i] = make_double2(0.0, 0.0);
         }
         if (q0 >= q1) {                                          // unreferenced node: no records will be waited for
-            nx_ai = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+            if (need_tk) { tk_base = (int64_t)__shfl_sync(0xffffffffu, tk, 0); tk_off = 0; }
+                nx_ai = tk_base + tk_off;
             if (nx_ai < m.n_node) {
                 nx_a = m.node_order ? (int64_t)m.node_order[nx_ai] : nx_ai;
                 nx_q0 = m.adj_ptr[nx_a]; nx_q1 = m.adj_ptr[nx_a + 1]; nx_b0 = m.brow[nx_a]; nx_b1 = m.brow[nx_a + 1];
@@ -226,16 +232,20 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             __syncwarp();
             if (lane < nrec) bulk_g2s(&ws.rec[lane][0], rec + gi_r * RS, cp_bytes, &ws.bar);
             if (first && j0_bytes && lane == 31) bulk_g2s(j0s, j0g, j0_bytes, &ws.bar);
+            // scatter slots + the node's SCV volume in the adjacent elements: loaded now, used after the records have landed
+            uint2 emv = make_uint2(0u, 0u);
+            double vv = 0.0;
             if (lane < nj) {
                 const uint8_t* em = m.emap + (int64_t)ad * NSH;
-                if (NSH == 8) *reinterpret_cast<uint2*>(ws.slot[lane]) = __ldg(reinterpret_cast<const uint2*>(em));
-                else if (NSH == 4) *reinterpret_cast<uint32_t*>(ws.slot[lane]) = __ldg(reinterpret_cast<const uint32_t*>(em));
-                else { for (int q = 0; q < NSH; q++) ws.slot[lane][q] = em[q]; }
-                vsum += m.scvvol[ad];
+                if (NSH == 8) emv = __ldg(reinterpret_cast<const uint2*>(em));
+                else if (NSH == 4) emv.x = __ldg(reinterpret_cast<const uint32_t*>(em));
+                else { for (int q = 0; q < NSH; q++) emv.x |= (uint32_t)em[q] << (8 * q); }
+                vv = m.scvvol[ad];
             }
             const int sslot = __shfl_sync(0xffffffffu, la_l, 0);
             if (first) {                                         // next node: ticket arrived -> load its ranges while the records fly
-                nx_ai = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+                if (need_tk) { tk_base = (int64_t)__shfl_sync(0xffffffffu, tk, 0); tk_off = 0; }
+                nx_ai = tk_base + tk_off;
                 if (nx_ai < m.n_node) {
                     nx_a = m.node_order ? (int64_t)m.node_order[nx_ai] : nx_ai;
                     nx_q0 = m.adj_ptr[nx_a]; nx_q1 = m.adj_ptr[nx_a + 1]; nx_b0 = m.brow[nx_a]; nx_b1 = m.brow[nx_a + 1];
@@ -244,6 +254,12 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             __syncwarp();
             mbar_wait(&ws.bar, phase);
             phase ^= 1u;
+            if (lane < nj) {
+                if (NSH == 8) *reinterpret_cast<uint2*>(ws.slot[lane]) = emv;
+                else *reinterpret_cast<uint32_t*>(ws.slot[lane]) = emv.x;
+            }
+            vsum += vv;
+            __syncwarp();
             if (first) self_slot = ws.slot[0][sslot];
             for (int jb = 0; jb < nj; jb += JP) {
                 const int j = jb + jj;
@@ -277,7 +293,6 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             }
         }
         __syncwarp();
-        nx_ad = (nx_ai < m.n_node && nx_q0 + lane < nx_q1 && lane < CH) ? m.adj[nx_q0 + lane] : 0;   // used at the top of the next node
         // deterministic reductions: SCV volume of the node (butterfly), defect fluxes (lane q < NF sums its component over jj)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
@@ -287,6 +302,7 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
 #pragma unroll
             for (int j2 = 0; j2 < JP; j2++) dsum += __shfl_sync(0xffffffffu, fs, j2 * NSH + (lane < NF ? lane : 0));
         }
+        nx_ad = (nx_ai < m.n_node && nx_q0 + lane < nx_q1 && lane < CH) ? m.adj[nx_q0 + lane] : 0;   // used at the top of the next node
         if (want_jac) {
             // merge the JP accumulator copies (fixed order) into copy 0, add the lumped mass (add_jac_M_elem :781-808)
             for (int i = lane; i < accn; i += 32) {
@@ -299,26 +315,26 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             __syncwarp();
             double* out = val + b0 * (NF * NF);
             if constexpr (NF == 4) {
-                for (int rf = 0; rf < DIM; rf++) {
-                    double2* orow = reinterpret_cast<double2*>(out + rf * rowlen);
-                    const double2* jrow = reinterpret_cast<const double2*>((J0D ? j0g : j0s) + rf * rowlen);
-                    for (int i = lane; i < 2 * cnt; i += 32) {
-                        const int slot = i >> 1, cp = i & 1;
-                        double2 v = make_double2(0.0, 0.0);
-                        if (jac_a) { const double2 jv = J0D ? __ldcs(jrow + i) : jrow[i]; v.x = jv.x * s_visc; v.y = jv.y * (cp ? s_pres : s_visc); }
+                // the NF rows of the node are contiguous (in the CSR values and in the staged J0 rows): one loop over all
+                // 16-byte chunks; chunk i = row rf, slot, column pair cp
+                const int n2 = 2 * cnt;
+                double2* o2 = reinterpret_cast<double2*>(out);
+                const double2* j2 = reinterpret_cast<const double2*>(J0D ? j0g : j0s);
+                for (int i = lane; i < NF * n2; i += 32) {
+                    const int rf = (i >= n2) + (i >= 2 * n2) + (i >= 3 * n2);
+                    const int ii = i - rf * n2, slot = ii >> 1, cp = ii & 1;
+                    double2 v;
+                    if (rf < DIM) {
+                        v = make_double2(0.0, 0.0);
+                        if (jac_a) { const double2 jv = J0D ? __ldcs(j2 + i) : j2[i]; v.x = jv.x * s_visc; v.y = jv.y * (cp ? s_pres : s_visc); }
                         const double D = acc[slot];
                         if (rf == 2 * cp) v.x += D;
                         if (rf == 2 * cp + 1) v.y += D;
-                        if (beta == 0.0) __stcs(orow + i, v);
-                        else { double2 o = orow[i]; o.x = beta * o.x + v.x; o.y = beta * o.y + v.y; orow[i] = o; }
+                    } else {
+                        v = make_double2(acc[(1 + 2 * cp) * cntp + slot], acc[(2 + 2 * cp) * cntp + slot]);
                     }
-                }
-                double2* orow = reinterpret_cast<double2*>(out + DIM * rowlen);
-                for (int i = lane; i < 2 * cnt; i += 32) {
-                    const int slot = i >> 1, cp = i & 1;
-                    const double2 v = make_double2(acc[(1 + 2 * cp) * cntp + slot], acc[(2 + 2 * cp) * cntp + slot]);
-                    if (beta == 0.0) __stcs(orow + i, v);
-                    else { double2 o = orow[i]; o.x = beta * o.x + v.x; o.y = beta * o.y + v.y; orow[i] = o; }
+                    if (beta == 0.0) __stcs(o2 + i, v);
+                    else { double2 o = o2[i]; o.x = beta * o.x + v.x; o.y = beta * o.y + v.y; o2[i] = o; }
                 }
             } else {
                 for (int rf = 0; rf < DIM; rf++) {
