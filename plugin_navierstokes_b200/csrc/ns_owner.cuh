@@ -461,26 +461,47 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
                 for (int k = 0; k < NSH; k++) fr[W_CK + k] = (STAB == STAB_NONE) ? N[k] * p.rho : sbk(k) * inv * p.rho;
             }
         }
+        // transported velocity of the stabilisation's upwind: Us = sum_k up_k u_k (upwind_vel, upwind_interface.h:334-358)
+        double Us[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) Us[d] = 0.0;
+        if (!p.stokes) {
+#pragma unroll
+            for (int k = 0; k < NSH; k++)
+#pragma unroll
+                for (int d = 0; d < DIM; d++) Us[d] += up[k] * NSB_COL(us, k * NF + d);
+        }
         double acc = 0.0;                                        // closure sum  sum_k sb_k (s_k . n)
         if (STAB != STAB_NONE && want_def) {
+            if (!FLOW && !td) {
+                // stationary FIELDS: sum_k (qa N_k + qb up_k) (u_k . n) = (qa StdVel + qb Us) . n
 #pragma unroll
-            for (int k = 0; k < NSH; k++) {
-                double sk = 0.0;
+                for (int d = 0; d < DIM; d++) acc += (qa * std[d] + qb * Us[d]) * n[d];
+            } else {
 #pragma unroll
-                for (int d = 0; d < DIM; d++) sk += (td ? s0[(int64_t)nd[k] * NF + d] : NSB_COL(us, k * NF + d)) * n[d];
-                acc += sbk(k) * sk;
+                for (int k = 0; k < NSH; k++) {
+                    double sk = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) sk += (td ? s0[(int64_t)nd[k] * NF + d] : NSB_COL(us, k * NF + d)) * n[d];
+                    acc += sbk(k) * sk;
+                }
             }
         }
         // ---- convective upwind, transported velocity, Peclet blend ----
         double U[DIM], w = 1.0;
 #pragma unroll
-        for (int d = 0; d < DIM; d++) U[d] = 0.0;
+        for (int d = 0; d < DIM; d++) U[d] = Us[d];
         if (!p.stokes) {
-            if (p.upw_conv != p.upw_stab) { double l2; ok &= upwind_uniform<E, BS>(p.upw_conv, xs, tid, n, xip, N, from, to, std, up, l2, sidetab, cortab); }
+            if (p.upw_conv != p.upw_stab) {
+                double l2;
+                ok &= upwind_uniform<E, BS>(p.upw_conv, xs, tid, n, xip, N, from, to, std, up, l2, sidetab, cortab);
 #pragma unroll
-            for (int k = 0; k < NSH; k++)
+                for (int d = 0; d < DIM; d++) U[d] = 0.0;
 #pragma unroll
-                for (int d = 0; d < DIM; d++) U[d] += up[k] * NSB_COL(us, k * NF + d);          // upwind_vel, upwind_interface.h:334-358
+                for (int k = 0; k < NSH; k++)
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) U[d] += up[k] * NSB_COL(us, k * NF + d);
+            }
             if (p.peclet) {                                       // peclet_blend :871-892
                 double dd = 0;
 #pragma unroll
