@@ -1,4 +1,5 @@
 // dense_inst.cu -- instantiates the dense-ip-system element kernel for one element type (-DNSB_ELEM=e)
+#include <cstdlib>
 #include "ns_dense.cuh"
 #include "ns_launch.h"
 #ifndef NSB_ELEM
@@ -8,7 +9,9 @@ namespace nsb {
 constexpr int E = NSB_ELEM;
 template <int SC, bool PAC> static cudaError_t dense_sc(NSB_ELEM_ARGS)
 {
-    constexpr int WPB = 4;
+    // one warp = one element with a ~30 KB (hex) workspace in shared memory: small blocks pack more warps per SM
+    // (1 warp/block: 7 blocks/SM; 4 warps/block: 1 block/SM)
+    static const int WPB = [] { const char* ev = getenv("NSB_DENSE_WPB"); const int v = ev ? atoi(ev) : 1; return (v >= 1 && v <= 4) ? v : 1; }();
     const size_t smem = sizeof(DenseWS<E, PAC>) * WPB;
     auto kern = fv1_dense_kernel<E, SC, PAC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

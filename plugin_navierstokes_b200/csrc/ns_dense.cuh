@@ -22,16 +22,23 @@ template <int E, bool PAC> struct DenseWS {
     // geometry
     double n[NIP][DIM], xip[NIP][DIM], N[NIP][NSH], G[NIP][NSH][DIM], ds[NIP], nn[NIP];
     double std[NIP][DIM];
-    // upwinds: [0] = upwind of the stabilisation, [1] = its downwind (FLOW), [2] = convective upwind
-    double ush[3][NIP][NSH], uip[3][NIP][NIP], ulen[3][NIP];
-    double flux[NIP];
-    int32_t has[NIP];
-    // ip system
-    double a[NIP], b[NIP], c[NIP];
-    double M[NIP][NIP];
-    int32_t perm[NIP];
     double sv[NIP][DIM][DIM][NSH], sp[NIP][DIM][NSH], svel[NIP][DIM];
-    IpRec<E, PAC> rec[NIP];
+    // The upwind shapes and the ip system are dead once phase R has read its upwind rows: the per-ip records of
+    // phases R / C live in the same storage (7.6 KB of the 30 KB workspace for hex -> 10 instead of 7 warps per SM).
+    struct Closure {
+        // upwinds: [0] = upwind of the stabilisation, [1] = its downwind (FLOW), [2] = convective upwind
+        double ush[3][NIP][NSH], uip[3][NIP][NIP], ulen[3][NIP];
+        double flux[NIP];
+        // ip system
+        double a[NIP], b[NIP], c[NIP];
+        double M[NIP][NIP];
+        int32_t has[NIP];
+        int32_t perm[NIP];
+    };
+    union {
+        Closure cl;
+        IpRec<E, PAC> rec[NIP];
+    };
 };
 
 // NavierStokesPositiveUpwind::compute (upwind.cpp:643-786) for the ip velocities sgn*std; all 32 lanes call.
@@ -41,8 +48,8 @@ template <int E, class WS> NSB_DEV void positive_upwind(WS& ws, int lane, double
     const double eps = 2.220446049250313e-16 * 10;
     if (lane < NIP) {
         const int ip = lane;
-        for (int k = 0; k < NSH; k++) ws.ush[slot][ip][k] = 0.0;
-        for (int j = 0; j < NIP; j++) ws.uip[slot][ip][j] = 0.0;
+        for (int k = 0; k < NSH; k++) ws.cl.ush[slot][ip][k] = 0.0;
+        for (int j = 0; j < NIP; j++) ws.cl.uip[slot][ip][j] = 0.0;
         double v[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; d++) v[d] = sgn * ws.std[ip][d];
@@ -55,11 +62,11 @@ template <int E, class WS> NSB_DEV void positive_upwind(WS& ws, int lane, double
             const double vel = sqrt(normsq), len = sqrt(ws.nn[ip]);
             if (fabs(fl / sqrt(vel * len)) <= eps) has = 0;
         }
-        if (!has) { ws.ush[slot][ip][f] = 0.5; ws.ush[slot][ip][t] = 0.5; }
-        ws.flux[ip] = fl; ws.has[ip] = has;
+        if (!has) { ws.cl.ush[slot][ip][f] = 0.5; ws.cl.ush[slot][ip][t] = 0.5; }
+        ws.cl.flux[ip] = fl; ws.cl.has[ip] = has;
     }
     __syncwarp();
-    const unsigned any = __ballot_sync(0xffffffffu, lane < NIP && ws.has[lane < NIP ? lane : 0]);
+    const unsigned any = __ballot_sync(0xffffffffu, lane < NIP && ws.cl.has[lane < NIP ? lane : 0]);
     if (any != 0u && lane < NSH) {
         const int sh = lane;
         int ips[NINC]; double fl[NINC]; int cnt = 0;
@@ -67,16 +74,16 @@ template <int E, class WS> NSB_DEV void positive_upwind(WS& ws, int lane, double
 #pragma unroll
         for (int q = 0; q < NINC; q++) {
             const int ip = tab::INC[E][sh][q];
-            if (!ws.has[ip]) continue;
-            const double f = (double)tab::INC_SIGN[E][sh][q] * ws.flux[ip];
+            if (!ws.cl.has[ip]) continue;
+            const double f = (double)tab::INC_SIGN[E][sh][q] * ws.cl.flux[ip];
             ips[cnt] = ip; fl[cnt] = f; cnt++;
             m_in += -1.0 * fmin(f, 0.0); m_out += fmax(f, 0.0);
         }
         const double F = fmax(m_in, m_out);
         for (int i = 0; i < cnt; i++) if (fl[i] > 0) {
             double sum = 0.0;
-            for (int j = 0; j < cnt; j++) if (fl[j] < 0) { const double s = -1.0 * fl[j] / F; ws.uip[slot][ips[i]][ips[j]] = s; sum += s; }
-            ws.ush[slot][ips[i]][sh] = 1.0 - sum;
+            for (int j = 0; j < cnt; j++) if (fl[j] < 0) { const double s = -1.0 * fl[j] / F; ws.cl.uip[slot][ips[i]][ips[j]] = s; sum += s; }
+            ws.cl.ush[slot][ips[i]][sh] = 1.0 - sum;
         }
     }
     __syncwarp();
@@ -87,11 +94,11 @@ template <int E, class WS> NSB_DEV void positive_upwind(WS& ws, int lane, double
         for (int d = 0; d < DIM; d++) up[d] = 0.0;
         for (int k = 0; k < NSH; k++)
 #pragma unroll
-            for (int d = 0; d < DIM; d++) up[d] += ws.ush[slot][ip][k] * ws.x[k * DIM + d];
+            for (int d = 0; d < DIM; d++) up[d] += ws.cl.ush[slot][ip][k] * ws.x[k * DIM + d];
         for (int j = 0; j < NIP; j++)
 #pragma unroll
-            for (int d = 0; d < DIM; d++) up[d] += ws.uip[slot][ip][j] * ws.xip[j][d];
-        ws.ulen[slot][ip] = sqrt(dist2<DIM>(ws.xip[ip], up));
+            for (int d = 0; d < DIM; d++) up[d] += ws.cl.uip[slot][ip][j] * ws.xip[j][d];
+        ws.cl.ulen[slot][ip] = sqrt(dist2<DIM>(ws.xip[ip], up));
     }
     __syncwarp();
 }
@@ -114,9 +121,9 @@ template <int E, class WS> NSB_DEV bool simple_upwind(WS& ws, int lane, int type
         for (int d = 0; d < DIM; d++) v[d] = sgn * ws.std[ip][d];
         ok = upwind_ip<E>(type, ws.x, g, v, up, len);
 #pragma unroll
-        for (int k = 0; k < NSH; k++) ws.ush[slot][ip][k] = up[k];
-        for (int j = 0; j < NIP; j++) ws.uip[slot][ip][j] = 0.0;
-        ws.ulen[slot][ip] = len;
+        for (int k = 0; k < NSH; k++) ws.cl.ush[slot][ip][k] = up[k];
+        for (int j = 0; j < NIP; j++) ws.cl.uip[slot][ip][j] = 0.0;
+        ws.cl.ulen[slot][ip] = len;
     }
     __syncwarp();
     return ok;
@@ -208,14 +215,14 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
         if (lane < NIP) {
             const int ip = lane;
             const int f = tab::EDGE[E][ip][0], t = tab::EDGE[E][ip][1];
-            ws.a[ip] = p.visc * diff_len_sq_inv<DIM>(p.diff_len, ws.nn[ip], ws.vol[f], ws.vol[t], ws.ds[ip], cmn, cav, cmd);
+            ws.cl.a[ip] = p.visc * diff_len_sq_inv<DIM>(p.diff_len, ws.nn[ip], ws.vol[f], ws.vol[t], ws.ds[ip], cmn, cav, cmd);
             double b = 0.0, c = 0.0;
             if (!p.stokes) {
                 const double nrm = sqrt(dotv<DIM>(ws.std[ip], ws.std[ip]));
-                b = nrm / ws.ulen[0][ip];
-                if (p.stab == STAB_FLOW) c = nrm / (ws.ulen[1][ip] + ws.ulen[0][ip]);
+                b = nrm / ws.cl.ulen[0][ip];
+                if (p.stab == STAB_FLOW) c = nrm / (ws.cl.ulen[1][ip] + ws.cl.ulen[0][ip]);
             }
-            ws.b[ip] = b; ws.c[ip] = c;
+            ws.cl.b[ip] = b; ws.cl.c[ip] = c;
         }
         __syncwarp();
         const bool dense = !p.stokes && stab_pos;
@@ -224,17 +231,17 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
             // diagonal branch written into the dense layout (stabilization.cpp:166-241 / :489-587)
             if (lane < NIP) {
                 const int ip = lane;
-                double diag = ws.a[ip];
+                double diag = ws.cl.a[ip];
                 if (p.time_dep) diag += 1.0 / p.dt;
-                if (!p.stokes) diag += ws.b[ip];
+                if (!p.stokes) diag += ws.cl.b[ip];
                 for (int d = 0; d < DIM; d++) {
                     double rhs = p.has_source ? p.src[d] : 0.0;
                     if (p.time_dep) { double o = 0.0; for (int k = 0; k < NSH; k++) o += ws.N[ip][k] * ws.s1[k * NF + d]; rhs += o / p.dt; }
                     for (int k = 0; k < NSH; k++) {
-                        double sumVel = ws.a[ip] * ws.N[ip][k];
+                        double sumVel = ws.cl.a[ip] * ws.N[ip][k];
                         if (!p.stokes) {
-                            sumVel += ws.b[ip] * ws.ush[0][ip][k];
-                            if (flow) sumVel += ws.c[ip] * (ws.ush[1][ip][k] - ws.ush[0][ip][k]);
+                            sumVel += ws.cl.b[ip] * ws.cl.ush[0][ip][k];
+                            if (flow) sumVel += ws.cl.c[ip] * (ws.cl.ush[1][ip][k] - ws.cl.ush[0][ip][k]);
                         }
                         if (flow) for (int d2 = 0; d2 < DIM; d2++) if (d2 != d) sumVel -= ws.std[ip][d2] * ws.G[ip][k][d2];
                         rhs += sumVel * ws.s0[k * NF + d];
@@ -256,29 +263,29 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                 const int ip = lane;
                 for (int j = 0; j < NIP; j++) {
                     double v = 0.0;
-                    if (j == ip) { if (p.time_dep) v += 1.0 / p.dt; v += ws.a[ip]; v += ws.b[ip]; }
-                    v -= ws.uip[0][ip][j] * ws.b[ip];
-                    if (flow) v += ws.c[ip] * (ws.uip[0][ip][j] - ws.uip[1][ip][j]);
-                    ws.M[ip][j] = v;
+                    if (j == ip) { if (p.time_dep) v += 1.0 / p.dt; v += ws.cl.a[ip]; v += ws.cl.b[ip]; }
+                    v -= ws.cl.uip[0][ip][j] * ws.cl.b[ip];
+                    if (flow) v += ws.cl.c[ip] * (ws.cl.uip[0][ip][j] - ws.cl.uip[1][ip][j]);
+                    ws.cl.M[ip][j] = v;
                 }
-                ws.perm[ip] = ip;
+                ws.cl.perm[ip] = ip;
             }
             __syncwarp();
             // LU with partial pivoting (GetInverse; App. B-5). Every lane takes the same decisions.
             for (int kk = 0; kk < NIP; kk++) {
-                int pv = kk; double best = fabs(ws.M[kk][kk]);
-                for (int i = kk + 1; i < NIP; i++) { const double v = fabs(ws.M[i][kk]); if (v > best) { best = v; pv = i; } }
+                int pv = kk; double best = fabs(ws.cl.M[kk][kk]);
+                for (int i = kk + 1; i < NIP; i++) { const double v = fabs(ws.cl.M[i][kk]); if (v > best) { best = v; pv = i; } }
                 if (!(best > 0.0)) { if (lane == 0) atomicExch(errflag, 2); break; }
                 __syncwarp();
                 if (pv != kk) {
-                    if (lane < NIP) { const double t = ws.M[kk][lane]; ws.M[kk][lane] = ws.M[pv][lane]; ws.M[pv][lane] = t; }
-                    if (lane == NIP) { const int t = ws.perm[kk]; ws.perm[kk] = ws.perm[pv]; ws.perm[pv] = t; }
+                    if (lane < NIP) { const double t = ws.cl.M[kk][lane]; ws.cl.M[kk][lane] = ws.cl.M[pv][lane]; ws.cl.M[pv][lane] = t; }
+                    if (lane == NIP) { const int t = ws.cl.perm[kk]; ws.cl.perm[kk] = ws.cl.perm[pv]; ws.cl.perm[pv] = t; }
                 }
                 __syncwarp();
                 if (lane > kk && lane < NIP) {
-                    const double l = ws.M[lane][kk] / ws.M[kk][kk];
-                    ws.M[lane][kk] = l;
-                    for (int j = kk + 1; j < NIP; j++) ws.M[lane][j] -= l * ws.M[kk][j];
+                    const double l = ws.cl.M[lane][kk] / ws.cl.M[kk][kk];
+                    ws.cl.M[lane][kk] = l;
+                    for (int j = kk + 1; j < NIP; j++) ws.cl.M[lane][j] -= l * ws.cl.M[kk][j];
                 }
                 __syncwarp();
             }
@@ -292,13 +299,13 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                 double bvec[NIP];
 #pragma unroll
                 for (int i = 0; i < NIP; i++) {
-                    const int ip = ws.perm[i];
+                    const int ip = ws.cl.perm[i];
                     double v;
                     if (kind == 0) {
                         if (!flow || d2 == d) {
-                            v = ws.a[ip] * ws.N[ip][k] + ws.b[ip] * ws.ush[0][ip][k];
+                            v = ws.cl.a[ip] * ws.N[ip][k] + ws.cl.b[ip] * ws.cl.ush[0][ip][k];
                             if (flow) {
-                                v += ws.c[ip] * (ws.ush[1][ip][k] - ws.ush[0][ip][k]);
+                                v += ws.cl.c[ip] * (ws.cl.ush[1][ip][k] - ws.cl.ush[0][ip][k]);
                                 for (int q = 0; q < DIM; q++) if (q != d) v -= ws.std[ip][q] * ws.G[ip][k][q];
                             }
                         } else v = ws.std[ip][d] * ws.G[ip][k][d2];
@@ -307,9 +314,9 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                         v = p.has_source ? p.src[d] : 0.0;
                         if (p.time_dep) { double o = 0.0; for (int q = 0; q < NSH; q++) o += ws.N[ip][q] * ws.s1[q * NF + d]; v += o / p.dt; }
                         for (int q = 0; q < NSH; q++) {
-                            double cv = ws.a[ip] * ws.N[ip][q] + ws.b[ip] * ws.ush[0][ip][q];
+                            double cv = ws.cl.a[ip] * ws.N[ip][q] + ws.cl.b[ip] * ws.cl.ush[0][ip][q];
                             if (flow) {
-                                cv += ws.c[ip] * (ws.ush[1][ip][q] - ws.ush[0][ip][q]);
+                                cv += ws.cl.c[ip] * (ws.cl.ush[1][ip][q] - ws.cl.ush[0][ip][q]);
                                 for (int d3 = 0; d3 < DIM; d3++) if (d3 != d) {
                                     cv -= ws.std[ip][d3] * ws.G[ip][q][d3];
                                     v += ws.s0[q * NF + d3] * (ws.std[ip][d] * ws.G[ip][q][d3]);
@@ -324,12 +331,12 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
 #pragma unroll
                 for (int i = 0; i < NIP; i++)
 #pragma unroll
-                    for (int j = 0; j < i; j++) bvec[i] -= ws.M[i][j] * bvec[j];
+                    for (int j = 0; j < i; j++) bvec[i] -= ws.cl.M[i][j] * bvec[j];
 #pragma unroll
                 for (int i = NIP - 1; i >= 0; i--) {
 #pragma unroll
-                    for (int j = i + 1; j < NIP; j++) bvec[i] -= ws.M[i][j] * bvec[j];
-                    bvec[i] /= ws.M[i][i];
+                    for (int j = i + 1; j < NIP; j++) bvec[i] -= ws.cl.M[i][j] * bvec[j];
+                    bvec[i] /= ws.cl.M[i][i];
                 }
 #pragma unroll
                 for (int i = 0; i < NIP; i++) {
@@ -344,12 +351,12 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
     }
     __syncwarp();
     // ---- R: transported velocity, blend, defect fluxes, factored flux derivative -> records ----
+    // (the records alias the closure storage: every lane reads its upwind rows first, then the warp synchronises)
+    IpGeo<E> g;
+    double std[DIM], U[DIM], w = 1.0, up[NSH], cvx[NSH];
     if (lane < NIP) {
         const int ip = lane;
-        IpRec<E, PAC>& r = ws.rec[ip];
-        IpGeo<E> g;
         g.from = tab::EDGE[E][ip][0]; g.to = tab::EDGE[E][ip][1];
-        double std[DIM], U[DIM], w = 1.0, up[NSH], cvx[NSH];
 #pragma unroll
         for (int d = 0; d < DIM; d++) { g.n[d] = ws.n[ip][d]; std[d] = ws.std[ip][d]; U[d] = 0.0; }
 #pragma unroll
@@ -359,13 +366,13 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
             else {
 #pragma unroll
                 for (int k = 0; k < NSH; k++) {
-                    const double s = ws.ush[cslot][ip][k];
+                    const double s = ws.cl.ush[cslot][ip][k];
                     up[k] = s;
                     for (int d = 0; d < DIM; d++) U[d] += s * ws.u[k * NF + d];
                 }
                 if (conv_pos) {                              // upwind_vel with ip shapes, upwind_interface.h:351-356
                     for (int j = 0; j < NIP; j++) {
-                        const double s = ws.uip[cslot][ip][j];
+                        const double s = ws.cl.uip[cslot][ip][j];
                         for (int d = 0; d < DIM; d++) U[d] += s * ws.std[j][d];
 #pragma unroll
                         for (int k = 0; k < NSH; k++) cvx[k] += ws.N[j][k] * s;      // fv1/navier_stokes_fv1.cpp:441-448
@@ -374,6 +381,11 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
             }
             if (p.peclet) w = peclet_blend<E>(U, g, ws.x, std, p.visc);
         }
+    }
+    __syncwarp();
+    if (lane < NIP) {
+        const int ip = lane;
+        IpRec<E, PAC>& r = ws.rec[ip];
         const double prod = dotv<DIM>(std, g.n) * p.rho;
         if (p.what & W_DEF_A) {
             double gv[DIM][DIM];

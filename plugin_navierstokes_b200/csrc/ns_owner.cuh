@@ -728,6 +728,25 @@ NSB_DEV void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// bulk copy with an L2 eviction-priority hint (createpolicy): evict_last for data with a second reader, evict_first for streams
+NSB_DEV unsigned long long l2_policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+NSB_DEV unsigned long long l2_policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+NSB_DEV void bulk_g2s_hint(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar, unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 template <int E, int STAB, bool EXACT, int CHP = 0, int MINB = 5>
 __global__ void __launch_bounds__(96, MINB) fv1_rows_kernel(KParams p, MeshDev m,
                                                           const double* __restrict__ rec, const double* __restrict__ u,

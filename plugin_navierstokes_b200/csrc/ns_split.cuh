@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
     if (lane == 0) mbar_init(&ws.bar, 1);
     __syncthreads();
     unsigned phase = 0;
+    // L2 priorities: a lean record has a second reader (the other node of its edge) -> evict_last; the J0 rows are a stream
+    const unsigned long long pol_rec = l2_policy_evict_last(), pol_j0 = l2_policy_evict_first();
+    const bool l2hint = m.l2_hints != 0;
     const int what = FAST ? (W_JAC_A | W_DEF_A) : p.what;
     if (FAST) beta = 0.0;
     const bool want_jac = what & (W_JAC_A | W_JAC_M), want_def = what & (W_DEF_A | W_DEF_M | W_RHS);
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
     // entries). It is fetched one node ahead: the ticket is taken at the top of the previous node, the ranges are
     // loaded while that node's records are in flight, the first adjacency entries while its rows are written.
     // Tickets are taken TG nodes at a time (one atomic per TG nodes; neighbouring warps still work on a tight window).
-    constexpr int TG = 8;
+    const int TG = m.ticket_group;
     auto take = [&]() -> unsigned long long { unsigned long long t = 0; if (lane == 0) t = atomicAdd(work_counter, (unsigned long long)TG); return t; };
     int64_t tk_base = (int64_t)__shfl_sync(0xffffffffu, take(), 0);
     int tk_off = 0;
@@ -230,8 +233,13 @@ __global__ void __launch_bounds__(64, MINB) fv1_rows_split_kernel(KParams p, Mes
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             if (lane == 0) mbar_arrive_expect_tx(&ws.bar, cp_bytes * (unsigned)nrec + (first ? j0_bytes : 0u));
             __syncwarp();
-            if (lane < nrec) bulk_g2s(&ws.rec[lane][0], rec + gi_r * RS, cp_bytes, &ws.bar);
-            if (first && j0_bytes && lane == 31) bulk_g2s(j0s, j0g, j0_bytes, &ws.bar);
+            if (l2hint) {
+                if (lane < nrec) bulk_g2s_hint(&ws.rec[lane][0], rec + gi_r * RS, cp_bytes, &ws.bar, pol_rec);
+                if (first && j0_bytes && lane == 31) bulk_g2s_hint(j0s, j0g, j0_bytes, &ws.bar, pol_j0);
+            } else {
+                if (lane < nrec) bulk_g2s(&ws.rec[lane][0], rec + gi_r * RS, cp_bytes, &ws.bar);
+                if (first && j0_bytes && lane == 31) bulk_g2s(j0s, j0g, j0_bytes, &ws.bar);
+            }
             // scatter slots + the node's SCV volume in the adjacent elements: loaded now, used after the records have landed
             uint2 emv = make_uint2(0u, 0u);
             double vv = 0.0;
