@@ -109,7 +109,8 @@ NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const doubl
             if (hit) { found = true; best = s; tn = t_n; n1 = b_n; bdet = det; }
         }
         if (!found) return false;
-        const double t = tn / bdet, bc = n1 / bdet;
+        const double ibd = 1.0 / bdet;
+        const double t = tn * ibd, bc = n1 * ibd;
         const int p0 = sidetab[best * 4], p1 = sidetab[best * 4 + 1];
 #pragma unroll
         for (int d = 0; d < 2; d++) {
@@ -154,7 +155,8 @@ NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const doubl
             if (__all_sync(amask, found)) break;
         }
         if (!found) return false;
-        const double t = tn / bdet, b1 = n1 / bdet, b2 = n2 / bdet;
+        const double ibd = 1.0 / bdet;                            // one reciprocal instead of three dependent divisions
+        const double t = tn * ibd, b1 = n1 * ibd, b2 = n2 * ibd;
         const int s = best / TPS, kk = best - s * TPS;
         const int p0 = sidetab[s * 4], p1 = sidetab[s * 4 + 1 + kk], p2 = sidetab[s * 4 + 2 + kk];
 #pragma unroll
@@ -576,35 +578,31 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
 #pragma unroll
             for (int d = 0; d < DIM; d++) fr[FR::O_STD + d] = std[d];
         }
-        // ---- defect fluxes (:686-776), corner-major: global_grad(k) = JI * local_grad(k) is formed once per corner and
-        // consumed at once (velocity / pressure gradients, closure sum), so no per-corner array stays live ----
+        // ---- defect fluxes (:686-776): the local gradient tensor Lg[i][q] = sum_k dN_k/dxi_i u_k,q is summed first and
+        // mapped to global gradients once (grad = J^-T Lg) instead of forming global_grad(k) per corner ----
         if (want_def) {
-            double gv[DIM][DIM], gp[DIM], gv0[DIM][DIM], gp0[DIM];
+            double Lg[DIM][NF], L0[DIM][NF], ms[DIM];
 #pragma unroll
-            for (int d = 0; d < DIM; d++) {
-                gp[d] = 0.0; gp0[d] = 0.0;
+            for (int i = 0; i < DIM; i++) {
 #pragma unroll
-                for (int q = 0; q < DIM; q++) { gv[q][d] = 0.0; gv0[q][d] = 0.0; }
+                for (int q = 0; q < NF; q++) { Lg[i][q] = 0.0; L0[i][q] = 0.0; }
+                double s = 0.0;                                  // FLOW: std . G_k = dN_k . (J^-1 std)
+#pragma unroll
+                for (int d = 0; d < DIM; d++) s += JI[d][i] * std[d];
+                ms[i] = s;
             }
             double pr = 0.0, oacc = 0.0;
 #pragma unroll
             for (int k = 0; k < NSH; k++) {
-                double Gk[DIM], uk[NF];
+                double dl[DIM], uk[NF];
 #pragma unroll
-                for (int d = 0; d < DIM; d++) {
-                    double g = 0.0;
-#pragma unroll
-                    for (int i = 0; i < DIM; i++) g += JI[d][i] * dnt[ip * DSTR + k * DIM + i];
-                    Gk[d] = g;
-                }
+                for (int i = 0; i < DIM; i++) dl[i] = dnt[ip * DSTR + k * DIM + i];
 #pragma unroll
                 for (int q = 0; q < NF; q++) uk[q] = NSB_COL(us, k * NF + q);
 #pragma unroll
-                for (int d = 0; d < DIM; d++) {
-                    gp[d] += Gk[d] * uk[P];
+                for (int i = 0; i < DIM; i++)
 #pragma unroll
-                    for (int q = 0; q < DIM; q++) gv[q][d] += Gk[d] * uk[q];
-                }
+                    for (int q = 0; q < NF; q++) Lg[i][q] += dl[i] * uk[q];
                 pr += N[k] * uk[P];
                 if (STAB != STAB_NONE) {
                     // (stab_vel . n) rho with rhs_d = src_d + old_d/dt + sum_k [sv(d,d,k) s_dk + sum_{q!=d} sv(d,q,k) s_qk] - G_kd/rho p_k
@@ -615,19 +613,32 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
 #pragma unroll
                         for (int q = 0; q < NF; q++) s0k[q] = s0[(int64_t)nd[k] * NF + q];
 #pragma unroll
-                        for (int d = 0; d < DIM; d++) {
-                            gp0[d] += Gk[d] * s0k[P];
+                        for (int i = 0; i < DIM; i++)
 #pragma unroll
-                            for (int q = 0; q < DIM; q++) gv0[q][d] += Gk[d] * s0k[q];
-                            sk += s0k[d] * n[d];
-                            o += s1[(int64_t)nd[k] * NF + d] * n[d];
-                        }
+                            for (int q = 0; q < NF; q++) L0[i][q] += dl[i] * s0k[q];
+#pragma unroll
+                        for (int d = 0; d < DIM; d++) { sk += s0k[d] * n[d]; o += s1[(int64_t)nd[k] * NF + d] * n[d]; }
                         oacc += N[k] * o;
-                    } else {
+                    } else if (FLOW) {
 #pragma unroll
                         for (int d = 0; d < DIM; d++) sk += uk[d] * n[d];
                     }
-                    if (FLOW) acc -= dotv<DIM>(Gk, std) * sk;
+                    if (FLOW) acc -= dotv<DIM>(dl, ms) * sk;
+                }
+            }
+            double gv[DIM][DIM], gp[DIM], gv0[DIM][DIM], gp0[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                double sp_ = 0.0, sp0_ = 0.0;
+#pragma unroll
+                for (int i = 0; i < DIM; i++) { sp_ += JI[d][i] * Lg[i][P]; sp0_ += JI[d][i] * L0[i][P]; }
+                gp[d] = sp_; gp0[d] = sp0_;
+#pragma unroll
+                for (int q = 0; q < DIM; q++) {
+                    double sv_ = 0.0, sv0_ = 0.0;
+#pragma unroll
+                    for (int i = 0; i < DIM; i++) { sv_ += JI[d][i] * Lg[i][q]; sv0_ += JI[d][i] * L0[i][q]; }
+                    gv[q][d] = sv_; gv0[q][d] = sv0_;
                 }
             }
             double F[NF];
