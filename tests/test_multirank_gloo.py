@@ -57,7 +57,7 @@ def _global_matrix(l2g, rowptr, colind, vals, nf, ndof):
     return sp.csr_matrix((vals, (gr, gc)), shape=(ndof, ndof))
 
 
-@pytest.mark.parametrize("elem,n,world", [("quad", 8, 2), ("hex", 4, 2), ("tri", 6, 4)])
+@pytest.mark.parametrize("elem,n,world", [("quad", 8, 2), ("hex", 4, 2), ("tri", 6, 4), ("hex", 4, 8)])
 def test_interface_summation_over_gloo(ora, elem, n, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
