@@ -124,7 +124,7 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
         };
 #define NSB_FLUX_GO(MB, LP) (k.time_dep ? go(fv1_flux_kernel<E, STAB, false, BS, MB, true, LP, true>, LP) : go(fv1_flux_kernel<E, STAB, false, BS, MB, true, LP, false>, LP))
         if constexpr (E == 3) {
-            if (LPEV == 4) e = FMB == 3 ? NSB_FLUX_GO(3, 4) : NSB_FLUX_GO(4, 4);
+            if (LPEV == 4) e = FMB == 3 ? NSB_FLUX_GO(3, 4) : FMB == 5 ? NSB_FLUX_GO(5, 4) : NSB_FLUX_GO(4, 4);
             else e = FMB == 3 ? NSB_FLUX_GO(3, 1) : NSB_FLUX_GO(2, 1);
         } else e = NSB_FLUX_GO(2, 1);
 #undef NSB_FLUX_GO

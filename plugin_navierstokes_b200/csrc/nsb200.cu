@@ -474,7 +474,8 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
     // split path (ns_split.cuh): static Jacobian part J0 cached per mesh + lean flux records. FLOW couples the
     // velocity components in the continuity row and exact Newton adds full blocks: those keep the general rows kernel.
     static const bool no_split = getenv("NSB_NOSPLIT") != nullptr;
-    const bool lean = !flow && !exact && !no_split;
+    // (the split rows kernel keeps JP accumulator copies + the J0 rows per warp in shared memory: bounded row length only)
+    const bool lean = !flow && !exact && !no_split && c->max_cnt <= 64;
     {   // per-(element, ip) record table: [static SCVF geometry | flux record] or the lean record of the split path.
         // The stride depends on the stabilisation (FLOW) and Jacobian flavour (exact Newton): (re)built on change.
         int stride = 0;
