@@ -326,12 +326,14 @@ def main():
             r, ne_s, dt = cpu_baseline(args.ref_n, threads, sweeps=5)
             cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "hex %d^3 (%d elements) of the same workload, Jacobian sweep + defect sweep, best of 5 (%.1f s each)" % (args.ref_n, ne_s, dt)}
-        traffic = None
+        traffic, share = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                bpe = json.load(open(tp))["bytes_per_element"].get(args.mode)
+                tj = json.load(open(tp))
+                bpe = tj["bytes_per_element"].get(args.mode)
                 traffic = bpe * n_elem if bpe else None          # per launch (= pass), scaled from the ncu capture
+                share = tj.get("kernel_share_ncu") if args.mode == "gather" else None
             except Exception:
                 traffic = None
         out = {
@@ -344,7 +346,8 @@ def main():
                        "algorithmic_bytes_per_element": abytes / n_elem, "nnz": int(nnz), "colors": disc.num_colors},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kms,
-                         "kernel": "fv1 %s (all launches of one assembly pass)" % args.mode},
+                         "kernel": "fv1 %s (all launches of one assembly pass: flux kernel + rows kernel)" % args.mode,
+                         "kernel_share_ncu": share},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out))
