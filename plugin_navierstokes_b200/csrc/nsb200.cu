@@ -438,7 +438,7 @@ static MeshDev mesh_view(const nsb_ctx* c)
     m.brow = c->d_brow; m.emap = c->d_emap; m.adj_ptr = c->d_adj_ptr; m.adj = c->d_adj; m.max_cnt = c->max_cnt;
     m.node_order = getenv("NSB_ZORDER") ? c->d_node_order : nullptr;   // opt-in: measured neutral on B200 (profiles/)
     { const char* ev = getenv("NSB_L2HINT"); m.l2_hints = ev ? atoi(ev) : 0; }
-    { const char* ev = getenv("NSB_TICKET_GROUP"); const int v = ev ? atoi(ev) : 8; m.ticket_group = v >= 1 ? v : 8; }
+    { const char* ev = getenv("NSB_TICKET_GROUP"); const int v = ev ? atoi(ev) : 4; m.ticket_group = v >= 1 ? v : 4; }
     return m;
 }
 
