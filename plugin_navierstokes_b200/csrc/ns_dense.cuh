@@ -311,20 +311,10 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                         } else v = ws.std[ip][d] * ws.G[ip][k][d2];
                     } else if (kind == 1) v = -1.0 * ws.G[ip][k][d] * p.inv_rho;
                     else {
+                        // stab_vel: the solve is linear, so only the state-independent part r0 = src + old / dt goes through the
+                        // system here; the shape part  sum_k sv(d,d2,k) s_k,d2 + sp(d,k) p_k  is added from the solved shapes below
                         v = p.has_source ? p.src[d] : 0.0;
                         if (p.time_dep) { double o = 0.0; for (int q = 0; q < NSH; q++) o += ws.N[ip][q] * ws.s1[q * NF + d]; v += o / p.dt; }
-                        for (int q = 0; q < NSH; q++) {
-                            double cv = ws.cl.a[ip] * ws.N[ip][q] + ws.cl.b[ip] * ws.cl.ush[0][ip][q];
-                            if (flow) {
-                                cv += ws.cl.c[ip] * (ws.cl.ush[1][ip][q] - ws.cl.ush[0][ip][q]);
-                                for (int d3 = 0; d3 < DIM; d3++) if (d3 != d) {
-                                    cv -= ws.std[ip][d3] * ws.G[ip][q][d3];
-                                    v += ws.s0[q * NF + d3] * (ws.std[ip][d] * ws.G[ip][q][d3]);
-                                }
-                            }
-                            v += ws.s0[q * NF + d] * cv;
-                            v += ws.s0[q * NF + P] * (-1.0 * ws.G[ip][q][d] * p.inv_rho);
-                        }
                     }
                     bvec[i] = v;
                 }
@@ -346,6 +336,18 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                     } else if (kind == 1) ws.sp[i][d][k] = bvec[i];
                     else ws.svel[i][d] = bvec[i];
                 }
+            }
+            __syncwarp();
+            // stab_vel(ip, d) = M^-1 r0 + sum_k [ sum_d2 sv(ip,d,d2,k) s0_k,d2 + sp(ip,d,k) s0_k,P ]   (stabilization.cpp:288-292, 637-641)
+            for (int t = lane; t < NIP * DIM; t += 32) {
+                const int i = t / DIM, d = t - i * DIM;
+                double v = ws.svel[i][d];
+                for (int q = 0; q < NSH; q++) {
+#pragma unroll
+                    for (int d2 = 0; d2 < DIM; d2++) v += ws.sv[i][d][d2][q] * ws.s0[q * NF + d2];
+                    v += ws.sp[i][d][q] * ws.s0[q * NF + P];
+                }
+                ws.svel[i][d] = v;
             }
         }
     }
