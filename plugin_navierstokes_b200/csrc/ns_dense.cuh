@@ -32,6 +32,7 @@ template <int E, bool PAC> struct DenseWS {
         // ip system
         double a[NIP], b[NIP], c[NIP];
         double M[NIP][NIP];
+        double dinv[NIP];          // reciprocals of the LU diagonal (one division per row instead of one per row and right-hand side)
         int32_t has[NIP];
         int32_t perm[NIP];
     };
@@ -289,6 +290,8 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                 }
                 __syncwarp();
             }
+            if (lane < NIP) ws.cl.dinv[lane] = 1.0 / ws.cl.M[lane][lane];
+            __syncwarp();
             // right-hand sides: ids [0, NV) velocity shapes, [NV, NV+NPR) pressure shapes, then DIM stab_vel rhs
             const int NV = flow ? DIM * DIM * NSH : NSH, NPR = DIM * NSH, NR = NV + NPR + DIM;
             for (int r = lane; r < NR; r += 32) {
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
                 for (int i = NIP - 1; i >= 0; i--) {
 #pragma unroll
                     for (int j = i + 1; j < NIP; j++) bvec[i] -= ws.cl.M[i][j] * bvec[j];
-                    bvec[i] /= ws.cl.M[i][i];
+                    bvec[i] *= ws.cl.dinv[i];
                 }
 #pragma unroll
                 for (int i = 0; i < NIP; i++) {
