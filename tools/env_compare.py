@@ -1,5 +1,6 @@
-"""saves J / d of hex n^3 LPS+FIELDS (J+d, owner-computes) for bitwise comparison between env settings:
-   python tools/pipe_check.py 48 out.npz ; NSB_PIPE=8 python tools/pipe_check.py 48 out2.npz ; python tools/pipe_check.py cmp out.npz out2.npz"""
+"""saves J / d of hex n^3 LPS+FIELDS (J+d, owner-computes) to compare two settings of the experiment knobs (README) bit by bit:
+   python tools/env_compare.py 48 a.npz ; NSB_NOSPLIT=1 python tools/env_compare.py 48 b.npz ; python tools/env_compare.py cmp a.npz b.npz
+(split vs general rows kernel: 6e-19 absolute on a 1e-3 matrix scale; ticket group / Z-curve / hints: bitwise equal)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
