@@ -212,9 +212,10 @@ template <int dim> class NavierStokesFV1 : public NavierStokesDeviceDisc {
     NavierStokesFV1(const char* fcts, const char* subsets, int device = 0) : NavierStokesDeviceDisc(fcts, subsets, NSB_DISC_FV1, dim, device) {}
     std::string disc_type() const override { return "fv1"; }
     // :190-199
-    void set_stabilization(const std::string& name) { m_prm.stab = stab_id(name); m_prm.diff_length = NSB_DIFF_RAW; if (m_conv) m_stab_upwind = m_conv; }
+    // a fresh stabilisation object: its upwind is the convective one if that is valid, EMPTY otherwise (never a stale one)
+    void set_stabilization(const std::string& name) { m_prm.stab = stab_id(name); m_prm.diff_length = NSB_DIFF_RAW; m_stab_upwind = m_conv; }
     void set_stabilization(const std::string& name, const std::string& diff) { set_stabilization(name); m_prm.diff_length = diff_length_id(diff); }
-    void set_no_stabilization() { m_prm.stab = NSB_STAB_NONE; }     // NavierStokesFV1WithoutStabilization
+    void set_no_stabilization() { m_prm.stab = NSB_STAB_NONE; m_stab_upwind = m_conv; }     // NavierStokesFV1WithoutStabilization
     void set_stabilization_upwind(const std::string& name) { m_stab_upwind = upwind_id(name); }   // stab->set_upwind(...)
     // :213-215
     void set_upwind(const std::string& name) { m_pac = false; m_conv = upwind_id(name); if (m_prm.stab != NSB_STAB_UNSET && !m_stab_upwind) m_stab_upwind = m_conv; }

@@ -143,6 +143,15 @@ int  nsb_pack(nsb_ctx *ctx, int64_t n, const int64_t *idx, const double *src, do
 int  nsb_unpack_add(nsb_ctx *ctx, int64_t n, const int64_t *idx, const double *in, double *dst);
 
 /* instrumentation */
+enum {
+    NSB_Q_DEVICE_BYTES = 0,     /* device memory held by the context (grid tables, caches, staging buffers)        */
+    NSB_Q_SETUP_SECONDS = 1,    /* host preprocessing + upload time of the last nsb_upload_mesh*                    */
+    NSB_Q_FUSED = 2,            /* 1 when the fused patch kernel serves NSB_SCATTER_GATHER on this grid             */
+    NSB_Q_PATCHES = 3,          /* number of node patches                                                           */
+    NSB_Q_SCVF_EVALS = 4,       /* SCVF evaluations per pass of the fused kernel (>= n_elem * nip: patch overlap)   */
+    NSB_Q_PATCH_TABLE_BYTES = 5 /* bytes of the per-patch tables read by every pass                                 */
+};
+int  nsb_query(const nsb_ctx *ctx, int what, double *out);
 int64_t nsb_launch_count(const nsb_ctx *ctx);          /* kernels launched by this context so far       */
 int  nsb_synchronize(nsb_ctx *ctx);
 const char *nsb_version(void);

@@ -14,13 +14,14 @@ DISC_FV1, DISC_FVCR = 0, 1
 JAC_A, DEF_A, JAC_M, DEF_M, RHS = 1, 2, 4, 8, 16
 SCATTER_GATHER, SCATTER_COLORED, SCATTER_ATOMIC = 0, 1, 2
 HOST, DEVICE = 0, 1
+Q_DEVICE_BYTES, Q_SETUP_SECONDS, Q_FUSED, Q_PATCHES, Q_SCVF_EVALS, Q_PATCH_TABLE_BYTES = range(6)
 OK, ERR_INVALID, ERR_SETUP, ERR_CUDA, ERR_GEOMETRY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 SYMBOLS = [
     "nsb_create", "nsb_destroy", "nsb_last_error", "nsb_set_stream", "nsb_params_default", "nsb_set_params",
     "nsb_upload_mesh", "nsb_upload_mesh_fvcr", "nsb_num_dofs", "nsb_nnz", "nsb_num_colors", "nsb_get_csr",
     "nsb_prep_elem_loop", "nsb_assemble", "nsb_local_contributions", "nsb_pack", "nsb_unpack_add",
-    "nsb_launch_count", "nsb_synchronize", "nsb_version", "nsb_check_errors",
+    "nsb_launch_count", "nsb_synchronize", "nsb_version", "nsb_check_errors", "nsb_query",
 ]
 
 
@@ -82,5 +83,6 @@ def lib():
     L.nsb_synchronize.argtypes = [vp]
     L.nsb_check_errors.argtypes = [vp]
     L.nsb_version.restype = C.c_char_p
+    L.nsb_query.argtypes = [vp, i32, C.POINTER(C.c_double)]
     _lib = L
     return L

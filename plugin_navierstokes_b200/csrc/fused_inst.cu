@@ -1,0 +1,43 @@
+// fused_inst.cu -- instantiates the fused patch kernel (ns_fused.cuh) for one element type (-DNSB_ELEM=e)
+#include <algorithm>
+#include <cstdlib>
+#include "ns_fused.cuh"
+#include "ns_launch.h"
+#ifndef NSB_ELEM
+#error "compile with -DNSB_ELEM=0..3"
+#endif
+namespace nsb {
+constexpr int E = NSB_ELEM;
+
+PatchCaps NSB_CAT(fused_caps_, NSB_ELEM)() { return FusedCfg<E>::caps(); }
+size_t NSB_CAT(fused_smem_bytes_, NSB_ELEM)(int max_cnt) { return FusedLayout<E>(max_cnt).total; }
+
+template <int STAB, bool TD>
+static cudaError_t fused_t(const FusedArgs& A, int max_cnt, cudaStream_t st, int sm_count, unsigned long long* work_counter)
+{
+    const size_t smem = FusedLayout<E>(max_cnt).total;
+    auto kern = fv1_fused_kernel<E, STAB, TD>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    const int nblk = std::min<int64_t>(A.n_patch, sm_count);
+    if (nblk <= 0) return cudaSuccess;
+    kern<<<nblk, FusedCfg<E>::NT, smem, st>>>(A, max_cnt, work_counter);
+    return cudaGetLastError();
+}
+
+cudaError_t NSB_CAT(launch_fused_, NSB_ELEM)(const FusedArgs& A, int max_cnt, cudaStream_t st, int sm_count, unsigned long long* work_counter)
+{
+    if (A.p.stab == STAB_FIELDS) return A.p.time_dep ? fused_t<STAB_FIELDS, true>(A, max_cnt, st, sm_count, work_counter)
+                                                     : fused_t<STAB_FIELDS, false>(A, max_cnt, st, sm_count, work_counter);
+    return A.p.time_dep ? fused_t<STAB_NONE, true>(A, max_cnt, st, sm_count, work_counter)
+                        : fused_t<STAB_NONE, false>(A, max_cnt, st, sm_count, work_counter);
+}
+
+cudaError_t NSB_CAT(launch_ray_safety_, NSB_ELEM)(int64_t n_elem, const int32_t* conn, const double* coords, uint8_t* elem_fast, cudaStream_t st)
+{
+    fused_ray_safety_kernel<E><<<(unsigned)((n_elem + 127) / 128), 128, 0, st>>>(n_elem, conn, coords, elem_fast);
+    return cudaGetLastError();
+}
+}

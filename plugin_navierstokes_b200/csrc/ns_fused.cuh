@@ -1,0 +1,928 @@
+// ns_fused.cuh -- FUSED owner-computes FV1 assembly (diagonal stabilisation branch, fixed-point Jacobian): one persistent
+// CTA per SM assembles the CSR rows of one PATCH of grid nodes at a time (ns_patch.h). The SCVF records never leave the
+// SM: per patch
+//   load  : the patch tables and the corner data (coordinates, unknowns, SCV volumes) of the patch's elements are
+//           gathered into shared-memory columns,
+//   flux  : one lane per SCVF that touches a patch node evaluates geometry -> StdVel -> upwind (ray search) ->
+//           diffusion length -> FIELDS / no-stabilisation closure -> defect fluxes -> Jacobian coefficients and writes the
+//           lean record [F | n | cK | dK | pK] into its shared-memory slot (what fv1_flux_kernel<LEAN> wrote to HBM),
+//   rows  : lane = (patch node, corner k): for every adjacent element the lane sums its NINC incident records and adds
+//           5 values into the node's per-slot accumulators (the corners of one element are distinct nodes: conflict-free),
+//           then the node's NF rows are written ONCE, coalesced: out = {nu rho, 1} scale_a J0 + state part (+ lumped mass).
+// Compared with the two-kernel split path (ns_split.cuh) the 3 KB/element record round trip through HBM and the TMA
+// staging / ticket / header machinery of the rows kernel are gone; the price is that SCVFs on patch boundaries are
+// evaluated by both patches (see PatchPlan::n_scvf_evals).
+//
+// Everything that computes is written as NSB_HD "lane functions" of (thread index, shared-memory view): the CUDA kernel
+// calls them between barriers, and tests/cpp/emu_fused.cpp runs the very same functions thread by thread on the CPU so
+// that the arithmetic and the patch tables are parity-tested against the oracle without a GPU.
+//
+// Arithmetic restated from fv1/navier_stokes_fv1.cpp:250-778, fv1/stabilization.cpp:122-241,805-850,
+// upwind.cpp:52-80,133-172,381-430,505-575, fv1/diffusion_length.h:47-198 (same formulas as ns_owner.cuh).
+#pragma once
+#include "ns_base.h"
+#include "ns_patch.h"
+
+namespace nsb {
+
+template <int E> struct FusedCfg {
+    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, NINC = ET<E>::NINC, NSIDE = ET<E>::NSIDE;
+    static constexpr int NT = 512;                                  // threads per CTA
+    static constexpr int RS = LeanRec<E>::SZ;
+    static constexpr int RSTR = RS + 2;                             // record stride in shared memory: 16-byte accesses of adjacent slots hit distinct bank groups
+    static constexpr int NV = DIM + 2;                              // accumulated values per slot: D, C[DIM], PP
+    static constexpr int NPW = 32 / NSH;                            // patch nodes per warp in the rows phase
+    static constexpr int DSTR = NSH * DIM + 1, NSTR = NSH + 1;      // odd strides of the per-ip tables
+    static constexpr int NCOL = NSH * DIM + NSH * NF + NSH;         // doubles per element column: x, u, SCV volumes
+    // capacities of one patch (tile = node-box the grid is binned into; see ns_patch.h)
+    static constexpr int MAXW = 512;
+    static constexpr int MAXE = E == E_HEX ? 80 : (E == E_TET ? 160 : (E == E_QUAD ? 128 : 224));
+    static constexpr int MAXN = E == E_HEX ? 32 : (E == E_TET ? 24 : (E == E_QUAD ? 96 : 64));
+    static constexpr int MAXA = E == E_HEX ? 288 : (E == E_TET ? 480 : 448);
+    static PatchCaps caps()
+    {
+        PatchCaps c;
+        c.max_work = MAXW; c.max_elem = MAXE; c.max_node = MAXN; c.max_adj = MAXA;
+        if (E == E_HEX) { c.tile[0] = 4; c.tile[1] = 4; c.tile[2] = 2; }
+        else if (E == E_TET) { c.tile[0] = 2; c.tile[1] = 2; c.tile[2] = 2; }
+        else if (E == E_QUAD) { c.tile[0] = 12; c.tile[1] = 8; c.tile[2] = 1; }
+        else { c.tile[0] = 8; c.tile[1] = 8; c.tile[2] = 1; }
+        return c;
+    }
+};
+
+__host__ __device__ constexpr int fused_cnt_pad(int max_cnt) { return (max_cnt + 1) & ~1; }
+
+// byte offsets of the shared-memory regions
+template <int E> struct FusedLayout {
+    using C = FusedCfg<E>;
+    size_t o_rec, o_un, o_dnt, o_nt, o_lip, o_cor, o_side, o_iptab, o_inc, o_work, o_adj, o_nodes, o_efast, o_misc, total;
+    int cntp;
+    __host__ __device__ explicit FusedLayout(int max_cnt)
+    {
+        cntp = fused_cnt_pad(max_cnt);
+        size_t o = 0;
+        auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return at; };
+        o_rec = take(sizeof(double) * C::MAXW * C::RSTR);
+        const size_t cols = sizeof(double) * C::NCOL * C::MAXE, accs = sizeof(double) * (size_t)C::MAXN * C::NV * cntp;
+        o_un = take(cols > accs ? cols : accs);
+        o_dnt = take(sizeof(double) * C::NIP * C::DSTR);
+        o_nt = take(sizeof(double) * C::NIP * C::NSTR);
+        o_lip = take(sizeof(double) * C::NIP * 3);
+        o_cor = take(sizeof(double) * 24);
+        o_side = take(sizeof(int) * 24);
+        o_iptab = take(sizeof(int) * C::NIP * 12);
+        o_inc = take(sizeof(int) * C::NSH * C::NINC);
+        o_work = take(sizeof(uint32_t) * C::MAXW);
+        o_adj = take(sizeof(PatchAdj) * C::MAXA);
+        o_nodes = take(sizeof(PatchNode) * C::MAXN);
+        o_efast = take(C::MAXE);
+        o_misc = take(64);
+        total = o;
+    }
+};
+
+// view of the CTA's shared memory (or of the emulator's buffer)
+template <int E> struct FusedSmem {
+    double *rec, *xs, *us, *vs, *acc, *dnt, *Nt, *lip, *cortab;
+    int *sidetab, *iptab, *inctab;
+    uint32_t* work; PatchAdj* adj; PatchNode* nodes; uint8_t* efast; int* misc;
+    int cntp;
+    NSB_HD FusedSmem(unsigned char* base, const FusedLayout<E>& L)
+    {
+        using C = FusedCfg<E>;
+        rec = reinterpret_cast<double*>(base + L.o_rec);
+        xs = reinterpret_cast<double*>(base + L.o_un);
+        us = xs + C::NSH * C::DIM * C::MAXE;
+        vs = us + C::NSH * C::NF * C::MAXE;
+        acc = xs;                                                   // the accumulators alias the element columns (rows phase)
+        dnt = reinterpret_cast<double*>(base + L.o_dnt);
+        Nt = reinterpret_cast<double*>(base + L.o_nt);
+        lip = reinterpret_cast<double*>(base + L.o_lip);
+        cortab = reinterpret_cast<double*>(base + L.o_cor);
+        sidetab = reinterpret_cast<int*>(base + L.o_side);
+        iptab = reinterpret_cast<int*>(base + L.o_iptab);
+        inctab = reinterpret_cast<int*>(base + L.o_inc);
+        work = reinterpret_cast<uint32_t*>(base + L.o_work);
+        adj = reinterpret_cast<PatchAdj*>(base + L.o_adj);
+        nodes = reinterpret_cast<PatchNode*>(base + L.o_nodes);
+        efast = base + L.o_efast;
+        misc = reinterpret_cast<int*>(base + L.o_misc);
+        cntp = L.cntp;
+    }
+};
+
+// global-memory arguments
+struct FusedArgs {
+    KParams p;
+    int32_t n_patch;
+    const PatchHdr* hdr; const PatchNode* nodes; const int32_t* elems; const int32_t* pconn; const uint32_t* work; const PatchAdj* adj;
+    const double* coords; const double* scvvol; const double* nodevol;
+    const double* u; const double* s0; const double* s1; const double* j0;
+    double beta; double* val; double* def;
+    int* errflag;
+    const uint8_t* elem_fast;      // hex: 1 = element is star-shaped w.r.t. its ips -> predicted-side ray search allowed; null = never
+    int max_adj;                   // longest adjacency list of a node
+};
+
+// reference tables -> shared memory (block-wide, once per kernel). `tid` strides over `nthreads`.
+template <int E> NSB_DEV void fused_stage_tables(const FusedSmem<E>& S, int tid, int nthreads)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH, NIP = C::NIP, NINC = C::NINC;
+    for (int i = tid; i < 24; i += nthreads) {
+        S.cortab[i] = tab::CORNER[E][i / 3][i % 3];
+        const int v = tab::SIDE[E][i / 4][i % 4];
+        S.sidetab[i] = v < 0 ? 0 : v;
+    }
+    for (int i = tid; i < NIP * NSH * DIM; i += nthreads) S.dnt[(i / (NSH * DIM)) * C::DSTR + i % (NSH * DIM)] = tab::C_DNIP[E][i / (NSH * DIM)][(i / DIM) % NSH][i % DIM];
+    for (int i = tid; i < NIP * NSH; i += nthreads) S.Nt[(i / NSH) * C::NSTR + i % NSH] = tab::NIPSH[E][i / NSH][i % NSH];
+    for (int i = tid; i < NIP * 3; i += nthreads) S.lip[i] = tab::LIP[E][i / 3][i % 3];
+    for (int i = tid; i < NIP * 12; i += nthreads) {
+        const int ip = i / 12, j = i - ip * 12;
+        int v = 0;
+        if (j < 2) v = tab::EDGE[E][ip][j];
+        else if (DIM == 3) v = (j < 6) ? tab::SIDE[E][tab::SCVF_FA[E][ip]][j - 2] : tab::SIDE[E][tab::SCVF_FB[E][ip]][j - 6];
+        S.iptab[i] = v < 0 ? 0 : v;
+    }
+    for (int i = tid; i < NSH * NINC; i += nthreads)
+        S.inctab[i] = tab::INC[E][i / NINC][i % NINC] | (tab::INC_SIGN[E][i / NINC][i % NINC] < 0 ? 256 : 0);
+}
+
+// element column `el`, entry i
+#define NSB_FCOL(base, i) (base)[(i) * C::MAXE + el]
+
+// FV1Geometry of one SCVF from the element's shared column (see ip_geometry in ns_fv1.cuh)
+template <int E>
+NSB_HD void fused_ip_geometry(const FusedSmem<E>& S, int el, int ip, const double* cen, double* n, double* xip, double& ds,
+                              bool wantJ, double (*JI)[ET<E>::DIM])
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH;
+    const int f = S.iptab[ip * 12], t = S.iptab[ip * 12 + 1];
+    double c0[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) c0[d] = 0.5 * (NSB_FCOL(S.xs, f * DIM + d) + NSB_FCOL(S.xs, t * DIM + d));
+    if constexpr (DIM == 2) {
+        n[0] = cen[1] - c0[1]; n[1] = -(cen[0] - c0[0]);
+        xip[0] = 0.5 * (c0[0] + cen[0]); xip[1] = 0.5 * (c0[1] + cen[1]);
+        ds = 0.0;
+    } else {
+        constexpr int NFC = (E == E_TET) ? 3 : 4;
+        double c1[3] = {0, 0, 0}, c3[3] = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < NFC; q++) {
+            const int ka = S.iptab[ip * 12 + 2 + q], kb = S.iptab[ip * 12 + 6 + q];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { c1[d] += NSB_FCOL(S.xs, ka * 3 + d); c3[d] += NSB_FCOL(S.xs, kb * 3 + d); }
+        }
+        double a[3], b[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            c1[d] *= (1.0 / NFC); c3[d] *= (1.0 / NFC);
+            a[d] = cen[d] - c0[d]; b[d] = c3[d] - c1[d];
+            xip[d] = 0.25 * (c0[d] + c1[d] + cen[d] + c3[d]);
+        }
+        cross3(n, a, b);
+#pragma unroll
+        for (int d = 0; d < 3; d++) n[d] *= 0.5;
+        ds = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    }
+    if (wantJ) {
+        double JT[DIM][DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; i++)
+#pragma unroll
+            for (int j = 0; j < DIM; j++) JT[i][j] = 0.0;
+        const double* dn = S.dnt + ip * C::DSTR;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) {
+            double dk[DIM];
+#pragma unroll
+            for (int i = 0; i < DIM; i++) dk[i] = dn[k * DIM + i];
+#pragma unroll
+            for (int j = 0; j < DIM; j++) {
+                const double xkj = NSB_FCOL(S.xs, k * DIM + j);
+#pragma unroll
+                for (int i = 0; i < DIM; i++) JT[i][j] += dk[i] * xkj;
+            }
+        }
+        inv_mat<DIM>(JT, JI);
+    }
+}
+
+// One side of the ray search (ElementSideRayIntersection): segment (2-D) or the triangle(s) of side `s`
+// in reference order; the tests are those of side_ray_cut (ns_fv1.cuh). Returns the index of the hit triangle or -1 and
+// leaves the un-divided Cramer numerators in tn / n1 / n2 / bdet.
+template <int E>
+NSB_HD int fused_ray_side(const FusedSmem<E>& S, int el, int s, const double* from, const double* dir, double dn2,
+                          double& tn, double& n1, double& n2, double& bdet)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM;
+    constexpr double SM = 1e-12;                                     // NSB_RAY_SMALL
+    if constexpr (DIM == 2) {
+        const int p0 = S.sidetab[s * 4], p1 = S.sidetab[s * 4 + 1];
+        const double x0 = NSB_FCOL(S.xs, p0 * 2), y0 = NSB_FCOL(S.xs, p0 * 2 + 1);
+        const double ex = NSB_FCOL(S.xs, p1 * 2) - x0, ey = NSB_FCOL(S.xs, p1 * 2 + 1) - y0;
+        const double det = dir[0] * (-ey) + dir[1] * ex;
+        const double rx = x0 - from[0], ry = y0 - from[1];
+        const double t_n = rx * (-ey) + ry * ex, b_n = dir[0] * ry - dir[1] * rx;
+        const double sg = det > 0.0 ? 1.0 : -1.0, ad = fabs(det);
+        const bool hit = det * det > (SM * SM) * dn2 * (ex * ex + ey * ey) &&
+                         b_n * sg >= -SM * ad && b_n * sg <= (1.0 + SM) * ad && t_n * sg <= 0.0;
+        if (hit) { tn = t_n; n1 = b_n; n2 = 0.0; bdet = det; return 0; }
+        return -1;
+    } else {
+        constexpr int TPS = (E == E_HEX) ? 2 : 1;
+        const int p0 = S.sidetab[s * 4];
+        double ed[TPS + 1][3], r[3], q[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double x0 = NSB_FCOL(S.xs, p0 * 3 + d);
+            r[d] = from[d] - x0;
+#pragma unroll
+            for (int j = 0; j <= TPS; j++) ed[j][d] = NSB_FCOL(S.xs, S.sidetab[s * 4 + 1 + j] * 3 + d) - x0;
+        }
+        cross3(q, r, dir);
+        double eq[TPS + 1];
+#pragma unroll
+        for (int j = 0; j <= TPS; j++) eq[j] = dotv<3>(ed[j], q);
+        int res = -1;
+#pragma unroll
+        for (int kk = 0; kk < TPS; kk++) {
+            double nrm[3];
+            cross3(nrm, ed[kk], ed[kk + 1]);
+            const double det = -dotv<3>(dir, nrm);
+            const double t_n = dotv<3>(r, nrm);
+            const double b1n = eq[kk + 1], b2n = -eq[kk];
+            const double sg = det > 0.0 ? 1.0 : -1.0, ad = fabs(det);
+            const bool hit = res < 0 && det * det > (SM * SM) * dn2 * dotv<3>(nrm, nrm) &&
+                             b1n * sg >= -SM * ad && b2n * sg >= -SM * ad && (b1n + b2n) * sg <= (1.0 + SM) * ad && t_n * sg <= 0.0;
+            if (hit) { res = kk; tn = t_n; n1 = b1n; n2 = b2n; bdet = det; }
+        }
+        return res;
+    }
+}
+
+// Ray / element-boundary intersection. Hex with ray_fast: the cut side is PREDICTED from the ray direction in reference
+// coordinates (s = J^-1 dir; going upstream the first plane xi_i in {0, 1} reached) and confirmed with the exact tests of
+// the reference routine; only if the confirmation fails are the sides searched in reference order. For an element that is
+// star-shaped w.r.t. the ip (checked once per mesh, fused_ray_safety) exactly one boundary triangle is hit, so the predicted
+// side is the one the ordered search returns; cuts on an edge shared by two sides give the same point from either side.
+template <int E>
+NSB_HD bool fused_ray_cut(const FusedSmem<E>& S, int el, int ip, const double* from, const double* dir, bool fast,
+                          const double (*JI)[ET<E>::DIM], int& side_out, double* gcut, double* lcut)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NSIDE = C::NSIDE;
+    constexpr int TPS = (E == E_HEX) ? 2 : 1;
+    double tn = 0.0, n1 = 0.0, n2 = 0.0, bdet = 1.0;
+    const double dn2 = dotv<DIM>(dir, dir);
+    int side = -1, tri = -1;
+    if constexpr (E == E_HEX) {
+        if (fast) {
+            // upstream along xi(t) = xi_ip + t s, t < 0: plane xi_i = 0 is reached at t = -xi_i / s_i (s_i > 0), xi_i = 1 at (1 - xi_i) / s_i (s_i < 0)
+            float best = -3.0e38f; int bs = -1;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float si = (float)(JI[0][i] * dir[0] + JI[1][i] * dir[1] + JI[2][i] * dir[2]);
+                const float xi = (float)S.lip[ip * 3 + i];
+                if (si != 0.0f) {
+                    const float t = si > 0.0f ? -xi / si : (1.0f - xi) / si;
+                    // reference sides: zeta=0 -> 0, eta=0 -> 1, xi=1 -> 2, eta=1 -> 3, xi=0 -> 4, zeta=1 -> 5
+                    const int sd = i == 0 ? (si > 0.0f ? 4 : 2) : (i == 1 ? (si > 0.0f ? 1 : 3) : (si > 0.0f ? 0 : 5));
+                    if (t > best) { best = t; bs = sd; }
+                }
+            }
+            if (bs >= 0) {
+                tri = fused_ray_side<E>(S, el, bs, from, dir, dn2, tn, n1, n2, bdet);
+                if (tri >= 0) side = bs;
+            }
+        }
+    }
+    if (side < 0) {
+        for (int s = 0; s < NSIDE; s++) {
+            tri = fused_ray_side<E>(S, el, s, from, dir, dn2, tn, n1, n2, bdet);
+            if (tri >= 0) { side = s; break; }
+        }
+        if (side < 0) return false;
+    }
+    const double ibd = 1.0 / bdet;
+    if constexpr (DIM == 2) {
+        const double t = tn * ibd, bc = n1 * ibd;
+        const int p0 = S.sidetab[side * 4], p1 = S.sidetab[side * 4 + 1];
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            gcut[d] = from[d] + t * dir[d];
+            lcut[d] = (1 - bc) * S.cortab[p0 * 3 + d] + bc * S.cortab[p1 * 3 + d];
+        }
+    } else {
+        const double t = tn * ibd, b1 = n1 * ibd, b2 = n2 * ibd;
+        const int kk = TPS == 2 ? tri : 0;
+        const int p0 = S.sidetab[side * 4], p1 = S.sidetab[side * 4 + 1 + kk], p2 = S.sidetab[side * 4 + 2 + kk];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            gcut[d] = from[d] + t * dir[d];
+            lcut[d] = (1 - b1 - b2) * S.cortab[p0 * 3 + d] + b1 * S.cortab[p1 * 3 + d] + b2 * S.cortab[p2 * 3 + d];
+        }
+    }
+    side_out = side;
+    return true;
+}
+
+// upwind shapes of one ip (No / Full / Skewed / LPS); see upwind_uniform (ns_owner.cuh), upwind.cpp:52-80,133-172,381-430,505-575
+template <int E>
+NSB_HD bool fused_upwind(const FusedSmem<E>& S, int el, int ip, int type, bool fast, const double (*JI)[ET<E>::DIM],
+                         const double* n, const double* xip, const double* N, int from, int to, const double* vel,
+                         double* up, double& len)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH;
+    if (type == UPW_NO) {
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = N[k];
+        len = 1.0;
+        return true;
+    }
+    if (type == UPW_FULL) {
+        const double flux = dotv<DIM>(n, vel);
+        const int co = flux > 0.0 ? from : to;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = (k == co) ? 1.0 : 0.0;
+        double s = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) { const double t = xip[d] - NSB_FCOL(S.xs, co * DIM + d); s += t * t; }
+        len = sqrt(s);
+        return true;
+    }
+#pragma unroll
+    for (int k = 0; k < NSH; k++) up[k] = 0.0;
+    if (sqrt(dotv<DIM>(vel, vel)) < 1e-14) { len = 1.0; return true; }      // upwind.cpp:407-413, 531-537
+    int side = 0; double gc[DIM], lc[DIM];
+    if (!fused_ray_cut<E>(S, el, ip, xip, vel, fast, JI, side, gc, lc)) { len = 1.0; return false; }
+    constexpr int NSC = (DIM == 2) ? 2 : (E == E_TET ? 3 : 4);
+    if (type == UPW_SKEWED) {                                    // GetNodeNextToCut, upwind.cpp:337-379
+        double mn = 1.79769313486231570e308; int bestc = 0;
+#pragma unroll
+        for (int i = 0; i < NSC; i++) {
+            const int co = S.sidetab[side * 4 + i];
+            double dd = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { const double t = gc[d] - NSB_FCOL(S.xs, co * DIM + d); dd += t * t; }
+            if (dd < mn) { mn = dd; bestc = co; }
+        }
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = (k == bestc) ? 1.0 : 0.0;
+        double s = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) { const double t = xip[d] - NSB_FCOL(S.xs, bestc * DIM + d); s += t * t; }
+        len = sqrt(s);
+    } else {                                                     // LPS, upwind.cpp:562-573
+        double Nc[NSH];
+        lagrange<E>(lc, Nc);
+        int mask = 0;
+#pragma unroll
+        for (int i = 0; i < NSC; i++) mask |= 1 << S.sidetab[side * 4 + i];
+#pragma unroll
+        for (int k = 0; k < NSH; k++) up[k] = ((mask >> k) & 1) ? Nc[k] : 0.0;
+        len = sqrt(dist2<DIM>(xip, gc));
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flux phase: one SCVF (local element el, ip) -> lean record `fr` (shared memory). Same evaluation order as
+// fv1_flux_kernel<LEAN> (ns_owner.cuh). nd = global node ids of the element's corners (time-dependent closure only).
+// ------------------------------------------------------------------------------------------------
+template <int E, int STAB, bool TD>
+NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip, const int32_t* __restrict__ nd, double* __restrict__ fr)
+{
+    using C = FusedCfg<E>;
+    using LR = LeanRec<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH, NIP = C::NIP, NF = C::NF, P = DIM;
+    const KParams& p = A.p;
+    const bool td = TD && p.time_dep;
+    const double nurho = p.visc * p.rho;
+    const bool want_def = p.what & W_DEF_A, want_jac = p.what & W_JAC_A;
+    bool ok = true;
+    double cen[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) s += NSB_FCOL(S.xs, k * DIM + d);
+        cen[d] = s * (1.0 / NSH);
+    }
+    // COR diffusion length: element-wide statistics of the SCVF normals (diffusion_length.h:139-172)
+    double cmn = 0.0, cav = 0.0, cmd = 0.0;
+    if (STAB != STAB_NONE && p.diff_len == DIFF_COR) {
+        cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
+        for (int i = 0; i < NIP; i++) {
+            double nn_[DIM], xx_[DIM], dsi;
+            fused_ip_geometry<E>(S, el, i, cen, nn_, xx_, dsi, false, nullptr);
+            const double q = dotv<DIM>(nn_, nn_);
+            if (q < cmn) cmn = q;
+            cav += q;
+            if (DIM == 3 && dsi < cmd) cmd = dsi;
+        }
+        cav /= NIP;
+    }
+    const int from = S.iptab[ip * 12], to = S.iptab[ip * 12 + 1];
+    double n[DIM], xip[DIM], ds = 0.0, JI[DIM][DIM];
+    fused_ip_geometry<E>(S, el, ip, cen, n, xip, ds, true, JI);
+    const double* N = S.Nt + ip * C::NSTR;
+    // ---- StdVel from the `u` argument (:282-293) ----
+    double std[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) s += NSB_FCOL(S.us, k * NF + d) * N[k];
+        std[d] = s;
+    }
+    const double sn = dotv<DIM>(std, n);
+    const double prod = sn * p.rho;
+    // ---- the stabilisation's upwind ----
+    double up[NSH], uplen = 1.0;
+#pragma unroll
+    for (int k = 0; k < NSH; k++) up[k] = 0.0;
+    const bool fast = S.efast[el] != 0;
+    if (!p.stokes) ok &= fused_upwind<E>(S, el, ip, p.upw_stab, fast, JI, n, xip, N, from, to, std, up, uplen);
+    // ---- diagonal of the ip system and numerators sb_k = qa N_k + qb up_k (stabilization.cpp:166-236) ----
+    double inv = 0.0, qa = 0.0, qb = 0.0;
+    if (STAB != STAB_NONE) {
+        const double nn = dotv<DIM>(n, n);
+        qa = p.visc * diff_len_sq_inv<DIM>(p.diff_len, nn, NSB_FCOL(S.vs, from), NSB_FCOL(S.vs, to), ds, cmn, cav, cmd);
+        if (!p.stokes) qb = sqrt(dotv<DIM>(std, std)) / uplen;
+        double diag = qa;
+        if (td) diag += 1.0 / p.dt;
+        if (!p.stokes) diag += qb;
+        inv = 1.0 / diag;
+    }
+    // everything that uses the STABILISATION's upwind shapes happens here: the convective upwind below may overwrite `up`
+    if (want_jac) {                                              // continuity-row coefficients (:561-584)
+#pragma unroll
+        for (int k = 0; k < NSH; k++) {
+            double c;
+            if (STAB == STAB_NONE) c = N[k] * p.rho;
+            else { double s = qa * N[k]; if (!p.stokes) s += qb * up[k]; c = s * inv * p.rho; }
+            fr[LR::O_CK + k] = c;
+        }
+    }
+    double Us[DIM];                                              // upwind_vel of the stabilisation's upwind (upwind_interface.h:334-358)
+#pragma unroll
+    for (int d = 0; d < DIM; d++) Us[d] = 0.0;
+    if (!p.stokes) {
+#pragma unroll
+        for (int k = 0; k < NSH; k++)
+#pragma unroll
+            for (int d = 0; d < DIM; d++) Us[d] += up[k] * NSB_FCOL(S.us, k * NF + d);
+    }
+    double acc = 0.0;                                            // closure sum  sum_k sb_k (s_k . n)
+    if (STAB != STAB_NONE && want_def) {
+        if (!td) {
+#pragma unroll
+            for (int d = 0; d < DIM; d++) acc += (qa * std[d] + qb * Us[d]) * n[d];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NSH; k++) {
+                double sk = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) sk += A.s0[(int64_t)nd[k] * NF + d] * n[d];
+                double s = qa * N[k]; if (!p.stokes) s += qb * up[k];
+                acc += s * sk;
+            }
+        }
+    }
+    // ---- convective upwind, transported velocity, Peclet blend ----
+    double U[DIM], w = 1.0;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) U[d] = Us[d];
+    if (!p.stokes) {
+        if (p.upw_conv != p.upw_stab) {
+            double l2;
+            ok &= fused_upwind<E>(S, el, ip, p.upw_conv, fast, JI, n, xip, N, from, to, std, up, l2);
+#pragma unroll
+            for (int d = 0; d < DIM; d++) U[d] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NSH; k++)
+#pragma unroll
+                for (int d = 0; d < DIM; d++) U[d] += up[k] * NSB_FCOL(S.us, k * NF + d);
+        }
+        if (p.peclet) {                                           // peclet_blend :871-892
+            double dd = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { const double t = NSB_FCOL(S.xs, to * DIM + d) - NSB_FCOL(S.xs, from * DIM + d); dd += t * t; }
+            const double Pe = sn / dotv<DIM>(n, n) * sqrt(dd) / p.visc;
+            const double Pe2 = Pe * Pe;
+            w = Pe2 / (5.0 + Pe2);
+#pragma unroll
+            for (int d = 0; d < DIM; d++) U[d] = w * U[d] + (1.0 - w) * std[d];
+        }
+    }
+    // ---- Jacobian coefficients ----
+    if (want_jac) {
+        const double cw = prod * w, cpe = prod * (1.0 - w);
+#pragma unroll
+        for (int k = 0; k < NSH; k++) {
+            double D = 0.0;
+            if (!p.stokes) { D = up[k] * cw; if (p.peclet) D += cpe * N[k]; }
+            fr[LR::O_DK + k] = D;
+        }
+        // pressure column of the continuity row (:586-592): -G_k.n / diag, with G_k.n = dnt_k . (JI^T n)
+        double mv[DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; i++) {
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) s += JI[d][i] * n[d];
+            mv[i] = s * (-1.0 * inv);
+        }
+#pragma unroll
+        for (int k = 0; k < NSH; k++) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < DIM; i++) s += S.dnt[ip * C::DSTR + k * DIM + i] * mv[i];
+            fr[LR::O_PK + k] = s;
+        }
+#pragma unroll
+        for (int d = 0; d < DIM; d++) fr[LR::O_N + d] = n[d];
+    }
+    // ---- defect fluxes (:686-776): local gradient tensor first, mapped to global gradients once ----
+    if (want_def) {
+        double Lg[DIM][NF], L0[DIM][NF];
+#pragma unroll
+        for (int i = 0; i < DIM; i++)
+#pragma unroll
+            for (int q = 0; q < NF; q++) { Lg[i][q] = 0.0; L0[i][q] = 0.0; }
+        double pr = 0.0, oacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < NSH; k++) {
+            double dl[DIM], uk[NF];
+#pragma unroll
+            for (int i = 0; i < DIM; i++) dl[i] = S.dnt[ip * C::DSTR + k * DIM + i];
+#pragma unroll
+            for (int q = 0; q < NF; q++) uk[q] = NSB_FCOL(S.us, k * NF + q);
+#pragma unroll
+            for (int i = 0; i < DIM; i++)
+#pragma unroll
+                for (int q = 0; q < NF; q++) Lg[i][q] += dl[i] * uk[q];
+            pr += N[k] * uk[P];
+            if (STAB != STAB_NONE && td) {                       // the closure uses solution(0) (:296, :646)
+                double s0k[NF], o = 0.0;
+#pragma unroll
+                for (int q = 0; q < NF; q++) s0k[q] = A.s0[(int64_t)nd[k] * NF + q];
+#pragma unroll
+                for (int i = 0; i < DIM; i++)
+#pragma unroll
+                    for (int q = 0; q < NF; q++) L0[i][q] += dl[i] * s0k[q];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) o += A.s1[(int64_t)nd[k] * NF + d] * n[d];
+                oacc += N[k] * o;
+            }
+        }
+        double gv[DIM][DIM], gp[DIM], gp0[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            double sp_ = 0.0, sp0_ = 0.0;
+#pragma unroll
+            for (int i = 0; i < DIM; i++) { sp_ += JI[d][i] * Lg[i][P]; sp0_ += JI[d][i] * L0[i][P]; }
+            gp[d] = sp_; gp0[d] = sp0_;
+#pragma unroll
+            for (int q = 0; q < DIM; q++) {
+                double sv_ = 0.0;
+#pragma unroll
+                for (int i = 0; i < DIM; i++) sv_ += JI[d][i] * Lg[i][q];
+                gv[q][d] = sv_;
+            }
+        }
+        double F[NF];
+#pragma unroll
+        for (int d1 = 0; d1 < DIM; d1++) {
+            double df = 0.0;
+#pragma unroll
+            for (int d2 = 0; d2 < DIM; d2++) df += gv[d1][d2] * n[d2];
+            if (!p.laplace) {
+#pragma unroll
+                for (int d2 = 0; d2 < DIM; d2++) df += gv[d2][d1] * n[d2];
+            }
+            double f = df * (-1.0) * nurho;
+            if (!p.stokes) f += U[d1] * prod;
+            f += pr * n[d1];
+            F[d1] = f;
+        }
+        double cont;
+        if (STAB == STAB_NONE) cont = sn * p.rho;
+        else {
+            double gpn = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) gpn += (td ? gp0[d] : gp[d]) * n[d];
+            acc -= gpn * p.inv_rho;
+            if (p.has_source) {
+#pragma unroll
+                for (int d = 0; d < DIM; d++) acc += p.src[d] * n[d];
+            }
+            if (td) acc += oacc / p.dt;
+            cont = acc * inv * p.rho;
+        }
+        F[P] = cont;
+#pragma unroll
+        for (int f = 0; f < NF; f++) fr[LR::O_F + f] = F[f];
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lane functions of one patch (tid in [0, NT))
+// ------------------------------------------------------------------------------------------------
+// load: patch tables + element columns
+template <int E> NSB_HD void fused_load(const FusedArgs& A, const FusedSmem<E>& S, const PatchHdr& H, int tid)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF;
+    for (int i = tid; i < H.n_work; i += C::NT) S.work[i] = A.work[H.work0 + i];
+    for (int i = tid; i < H.n_adj; i += C::NT) S.adj[i] = A.adj[H.adj0 + i];
+    for (int i = tid; i < H.n_node; i += C::NT) S.nodes[i] = A.nodes[H.node0 + i];
+    for (int i = tid; i < H.n_elem * NSH; i += C::NT) {
+        const int el = i / NSH, k = i - el * NSH;
+        const int64_t e = A.elems[H.elem0 + el];
+        const int64_t ndk = A.pconn[(int64_t)(H.elem0 + el) * NSH + k];
+#pragma unroll
+        for (int f = 0; f < NF; f++) NSB_FCOL(S.us, k * NF + f) = A.u[ndk * NF + f];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) NSB_FCOL(S.xs, k * DIM + d) = A.coords[ndk * DIM + d];
+        NSB_FCOL(S.vs, k) = A.scvvol[e * NSH + k];
+        if (k == 0) S.efast[el] = A.elem_fast ? A.elem_fast[e] : (uint8_t)0;
+    }
+}
+
+// flux: returns false if a ray search failed (the reference throws, upwind.cpp:354)
+template <int E, int STAB, bool TD> NSB_HD bool fused_flux(const FusedArgs& A, const FusedSmem<E>& S, const PatchHdr& H, int tid)
+{
+    using C = FusedCfg<E>;
+    bool ok = true;
+    for (int w = tid; w < H.n_work; w += C::NT) {
+        const uint32_t wi = S.work[w];
+        const int el = wi & 255, ip = (wi >> 8) & 15, slot = wi >> 12;
+        ok &= fused_scvf<E, STAB, TD>(A, S, el, ip, A.pconn + (int64_t)(H.elem0 + el) * C::NSH, S.rec + slot * C::RSTR);
+    }
+    return ok;
+}
+
+// rows, step 1: clear the accumulators of the patch nodes
+template <int E> NSB_HD void fused_rows_zero(const FusedSmem<E>& S, const PatchHdr& H, int tid)
+{
+    using C = FusedCfg<E>;
+    const int n = H.n_node * C::NV * S.cntp;
+    for (int i = tid; i < n; i += C::NT) S.acc[i] = 0.0;
+}
+
+// rows, step 2: lane = (patch node nl, corner k) accumulates the adjacency entry j of its node (j is warp-uniform; the
+// device kernel separates the steps by __syncwarp). fs: the lane's defect sum (component k < NF).
+template <int E> NSB_HD void fused_rows_accum_step(const FusedArgs& A, const FusedSmem<E>& S, int nl, int k, int j, double& fs)
+{
+    using C = FusedCfg<E>;
+    using LR = LeanRec<E>;
+    constexpr int DIM = C::DIM, NF = C::NF, NINC = C::NINC, NV = C::NV;
+    const KParams& p = A.p;
+    const bool jac_a = p.what & W_JAC_A, def_a = p.what & W_DEF_A;
+    const PatchNode& Nd = S.nodes[nl];
+    if (j >= Nd.adj_cnt) return;
+    const PatchAdj& a = S.adj[Nd.adj_off + j];
+    double D = 0.0, PP = 0.0, Cn[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) Cn[d] = 0.0;
+#pragma unroll
+    for (int t = 0; t < NINC; t++) {
+        const double* rc = S.rec + a.slot[t] * C::RSTR;
+        const bool neg = S.inctab[a.la * NINC + t] & 256;
+        if (def_a && k < NF) { const double f = rc[LR::O_F + k]; fs += neg ? -f : f; }
+        if (jac_a) {
+            const double sg = neg ? -p.scale_a : p.scale_a;
+            D += sg * rc[LR::O_DK + k];
+            PP += sg * rc[LR::O_PK + k];
+            const double w = sg * rc[LR::O_CK + k];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) Cn[d] += w * rc[LR::O_N + d];
+        }
+    }
+    if (jac_a) {
+        double* accn = S.acc + nl * (NV * S.cntp);
+        const int slot = a.emap[k];
+        accn[slot] += D;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) accn[(1 + d) * S.cntp + slot] += Cn[d];
+        accn[(1 + DIM) * S.cntp + slot] += PP;
+    }
+}
+
+// rows, step 3 (lane k == 0 of the node): lumped mass on the diagonal (add_jac_M_elem :781-808)
+template <int E> NSB_HD void fused_rows_mass(const FusedArgs& A, const FusedSmem<E>& S, int nl)
+{
+    using C = FusedCfg<E>;
+    const KParams& p = A.p;
+    const PatchNode& Nd = S.nodes[nl];
+    if (!(p.what & W_JAC_M) || Nd.adj_cnt == 0) return;
+    const int self = S.adj[Nd.adj_off].self;
+    S.acc[nl * (C::NV * S.cntp) + self] += p.scale_m * A.nodevol[Nd.node] * p.rho;
+}
+
+// rows, step 4: defect entry (node, component k < NF)   (add_def_A_elem / add_def_M_elem / add_rhs_elem)
+template <int E> NSB_HD void fused_rows_defect(const FusedArgs& A, const FusedSmem<E>& S, int nl, int k, double fs)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NF = C::NF;
+    const KParams& p = A.p;
+    const int64_t a = S.nodes[nl].node;
+    double d = (p.what & W_DEF_A) ? fs : 0.0;
+    const bool need_vol = ((p.what & W_RHS) && p.has_source) || (p.what & W_DEF_M);
+    const double vol = (need_vol && k < DIM) ? A.nodevol[a] : 0.0;
+    if ((p.what & W_RHS) && p.has_source && k < DIM) d -= p.src[k] * vol * p.rho;
+    d *= p.scale_a;
+    if ((p.what & W_DEF_M) && k < DIM) d += p.scale_m * A.u[a * NF + k] * vol * p.rho;
+    double* q = A.def + a * NF + k;
+    *q = (A.beta == 0.0) ? d : A.beta * (*q) + d;
+}
+
+// rows, step 5: the NF rows of the node, written once. lane k of the node's NSH lanes handles the 16-byte chunks
+// k, k + NSH, ... of each row (3-D) or the entries k, k + NSH, ... (2-D).
+template <int E> NSB_HD void fused_rows_out(const FusedArgs& A, const FusedSmem<E>& S, int nl, int k)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NV = C::NV;
+    const KParams& p = A.p;
+    const bool jac_a = p.what & W_JAC_A;
+    const PatchNode& Nd = S.nodes[nl];
+    const int cnt = Nd.cnt, cntp = S.cntp;
+    const double* acc = S.acc + nl * (NV * cntp);
+    const double s_visc = p.visc * p.rho * p.scale_a, s_pres = p.scale_a;
+    double* out = A.val + Nd.b0 * (NF * NF);
+    const double* j0g = A.j0 + Nd.b0 * (DIM * NF);
+    const double beta = A.beta;
+    const int rowlen = cnt * NF;
+    if constexpr (NF == 4) {
+        const int n2 = 2 * cnt;                                  // 16-byte chunks per row
+#pragma unroll
+        for (int rf = 0; rf < NF; rf++) {
+            double* orow = out + rf * rowlen;
+            for (int i = k; i < n2; i += NSH) {
+                const int slot = i >> 1, cp = i & 1;
+                double vx, vy;
+                if (rf < DIM) {
+                    vx = 0.0; vy = 0.0;
+                    if (jac_a) {
+#ifdef __CUDA_ARCH__
+                        const double2 jv = __ldcs(reinterpret_cast<const double2*>(j0g + rf * rowlen) + i);
+                        vx = jv.x * s_visc; vy = jv.y * (cp ? s_pres : s_visc);
+#else
+                        const double* jv = j0g + rf * rowlen + 2 * i; vx = jv[0] * s_visc; vy = jv[1] * (cp ? s_pres : s_visc);
+#endif
+                    }
+                    const double D = acc[slot];
+                    if (rf == 2 * cp) vx += D;
+                    if (rf == 2 * cp + 1) vy += D;
+                } else {
+                    vx = acc[(1 + 2 * cp) * cntp + slot]; vy = acc[(2 + 2 * cp) * cntp + slot];
+                }
+#ifdef __CUDA_ARCH__
+                double2* o2 = reinterpret_cast<double2*>(orow) + i;
+                if (beta == 0.0) __stcs(o2, make_double2(vx, vy));
+                else { double2 o = *o2; o.x = beta * o.x + vx; o.y = beta * o.y + vy; *o2 = o; }
+#else
+                if (beta == 0.0) { orow[2 * i] = vx; orow[2 * i + 1] = vy; }
+                else { orow[2 * i] = beta * orow[2 * i] + vx; orow[2 * i + 1] = beta * orow[2 * i + 1] + vy; }
+#endif
+            }
+        }
+    } else {
+        for (int rf = 0; rf < NF; rf++) {
+            double* orow = out + rf * rowlen;
+            for (int i = k; i < rowlen; i += NSH) {
+                const int slot = i / NF, cf = i - slot * NF;
+                double v;
+                if (rf < DIM) {
+                    v = jac_a ? j0g[rf * rowlen + i] * (cf < DIM ? s_visc : s_pres) : 0.0;
+                    if (cf == rf) v += acc[slot];
+                } else v = acc[(1 + cf) * cntp + slot];
+                orow[i] = (beta == 0.0) ? v : beta * orow[i] + v;
+            }
+        }
+    }
+}
+
+// true when every boundary triangle of the element (sides in reference order, quadrilaterals as (p0,p1,p2), (p0,p2,p3)) is
+// seen from its inner side by every SCVF ip: the triangulated boundary is then star-shaped w.r.t. each ip, a ray from the
+// ip cuts exactly one triangle, and the predicted-side ray search of fused_ray_cut returns what the ordered search returns.
+template <int E> NSB_DEV bool fused_star_shaped(const double* x)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NSIDE = ET<E>::NSIDE;
+    if constexpr (DIM == 2) return true;
+    else {
+        constexpr int TPS = (E == E_HEX) ? 2 : 1;
+        bool ok = true;
+        for (int ip = 0; ip < NIP; ip++) {
+            double xi[3], N[NSH], xip[3] = {0, 0, 0};
+            for (int d = 0; d < 3; d++) xi[d] = tab::LIP[E][ip][d];
+            lagrange<E>(xi, N);
+            for (int k = 0; k < NSH; k++) for (int d = 0; d < 3; d++) xip[d] += N[k] * x[k * 3 + d];
+            int npos = 0, nneg = 0;
+            for (int s = 0; s < NSIDE; s++) for (int kk = 0; kk < TPS; kk++) {
+                const int p0 = tab::SIDE[E][s][0], p1 = tab::SIDE[E][s][1 + kk], p2 = tab::SIDE[E][s][2 + kk];
+                double e1[3], e2[3], r[3], nrm[3];
+                for (int d = 0; d < 3; d++) { e1[d] = x[p1 * 3 + d] - x[p0 * 3 + d]; e2[d] = x[p2 * 3 + d] - x[p0 * 3 + d]; r[d] = xip[d] - x[p0 * 3 + d]; }
+                cross3(nrm, e1, e2);
+                const double v = dotv<3>(r, nrm);
+                if (v * v > 1e-16 * dotv<3>(r, r) * dotv<3>(nrm, nrm)) { if (v > 0) npos++; else nneg++; }
+            }
+            if (!((npos == NSIDE * TPS && nneg == 0) || (nneg == NSIDE * TPS && npos == 0))) ok = false;
+        }
+        return ok;
+    }
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// the kernel: persistent CTAs, patches handed out by an atomic ticket
+// ------------------------------------------------------------------------------------------------
+template <int E, int STAB, bool TD>
+__global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const FusedArgs A, int max_cnt, unsigned long long* __restrict__ work_counter)
+{
+    using C = FusedCfg<E>;
+    constexpr int NSH = C::NSH, NF = C::NF, NPW = C::NPW, DIM = C::DIM;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FusedLayout<E> L(max_cnt);
+    const FusedSmem<E> S(smem_raw, L);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    fused_stage_tables<E>(S, tid, C::NT);
+    const int what = A.p.what;
+    const bool want_jac = what & (W_JAC_A | W_JAC_M), want_def = what & (W_DEF_A | W_DEF_M | W_RHS);
+    const bool flux_needed = what & (W_JAC_A | W_DEF_A);
+    const int jj = lane / NSH, k = lane - jj * NSH;
+    const bool lane_on = jj < NPW;
+    const int j0_lines = (max_cnt * DIM * NF * (int)sizeof(double) + 127) >> 7;
+    for (;;) {
+        if (tid == 0) S.misc[0] = (int)atomicAdd(work_counter, 1ULL);
+        __syncthreads();
+        const int pi = S.misc[0];
+        if (pi >= A.n_patch) break;
+        PatchHdr H;
+        {
+            const int4* hp = reinterpret_cast<const int4*>(A.hdr + pi);
+            const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+            H.node0 = h0.x; H.n_node = h0.y; H.elem0 = h0.z; H.n_elem = h0.w; H.work0 = h1.x; H.n_work = h1.y; H.adj0 = h1.z; H.n_adj = h1.w;
+        }
+        fused_load<E>(A, S, H, tid);
+        __syncthreads();
+        if (flux_needed) {
+            if (what & W_JAC_A) {                                // the J0 rows of the patch nodes are needed at the end of the patch: pull them into L2 now
+                for (int i = tid; i < H.n_node * j0_lines; i += C::NT) {
+                    const int nl = i / j0_lines, li = i - nl * j0_lines;
+                    const PatchNode& Nd = S.nodes[nl];
+                    if (li * 16 < Nd.cnt * (DIM * NF)) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.j0 + Nd.b0 * (DIM * NF) + li * 16));
+                }
+            }
+            if (!fused_flux<E, STAB, TD>(A, S, H, tid)) atomicExch(A.errflag, 1);
+        }
+        __syncthreads();
+        if (want_jac) fused_rows_zero<E>(S, H, tid);
+        __syncthreads();
+        for (int nl0 = warp * NPW; nl0 < H.n_node; nl0 += (C::NT / 32) * NPW) {
+            const int nl = nl0 + jj;
+            const bool on = lane_on && nl < H.n_node;
+            double fs = 0.0;
+            if (flux_needed) {
+                const int mycnt = on ? (int)S.nodes[nl].adj_cnt : 0;
+                const int mx = __reduce_max_sync(0xffffffffu, mycnt);
+                for (int j = 0; j < mx; j++) {
+                    if (on) fused_rows_accum_step<E>(A, S, nl, k, j, fs);
+                    __syncwarp();
+                }
+            }
+            if (on && k == 0) fused_rows_mass<E>(A, S, nl);
+            __syncwarp();
+            if (on && want_def && k < NF) fused_rows_defect<E>(A, S, nl, k, fs);
+            if (on && want_jac) fused_rows_out<E>(A, S, nl, k);
+        }
+    }
+}
+
+// once per mesh (hex): elem_fast[e] = 1 when element e is star-shaped w.r.t. every one of its ips
+template <int E>
+__global__ void fused_ray_safety_kernel(int64_t n_elem, const int32_t* __restrict__ conn, const double* __restrict__ coords, uint8_t* __restrict__ elem_fast)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elem) return;
+    double x[NSH * DIM];
+#pragma unroll
+    for (int k = 0; k < NSH; k++) {
+        const int64_t nd = conn[e * NSH + k];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) x[k * DIM + d] = coords[nd * DIM + d];
+    }
+    elem_fast[e] = fused_star_shaped<E>(x) ? 1 : 0;
+}
+#endif  // __CUDACC__
+
+}  // namespace nsb

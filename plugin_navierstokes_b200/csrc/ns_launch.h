@@ -26,6 +26,15 @@ struct LaunchInfo { int64_t launches = 0; };
     int lean_record_doubles_##E();
 NSB_DECL(0) NSB_DECL(1) NSB_DECL(2) NSB_DECL(3)
 #undef NSB_DECL
+struct FusedArgs;
+struct PatchCaps;
+#define NSB_DECLF(E)                                                                                  \
+    PatchCaps fused_caps_##E();                                                                       \
+    size_t fused_smem_bytes_##E(int max_cnt);                                                         \
+    cudaError_t launch_fused_##E(const FusedArgs& A, int max_cnt, cudaStream_t st, int sm_count, unsigned long long* work_counter); \
+    cudaError_t launch_ray_safety_##E(int64_t n_elem, const int32_t* conn, const double* coords, uint8_t* elem_fast, cudaStream_t st);
+NSB_DECLF(0) NSB_DECLF(1) NSB_DECLF(2) NSB_DECLF(3)
+#undef NSB_DECLF
 struct FvcrDev;
 cudaError_t launch_fvcr_0(int sc, const KParams& k, const FvcrDev& m, const int32_t* list, int64_t n_list, const double* u,
                           double* val, double* def, int* d_err, cudaStream_t st);

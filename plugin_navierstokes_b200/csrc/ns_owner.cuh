@@ -296,7 +296,6 @@ NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, con
 }
 
 // lean SCVF record of the split path (ns_split.cuh): [F | n | cK | dK | pK = -G_k.n / diag]
-template <int E> struct LeanRec;
 
 // LPE = lanes per element: the SCVFs of an element are dealt to LPE adjacent lanes (ip = ii * LPE + sub), the element's
 // unknowns / coordinates live once in a shared column used by all of them. LPE = 1 is the thread-per-element layout.

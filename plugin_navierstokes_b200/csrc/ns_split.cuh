@@ -21,13 +21,6 @@
 
 namespace nsb {
 
-template <int E> struct LeanRec {
-    static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NF = DIM + 1;
-    static constexpr int NSHP = (NSH + 1) & ~1;
-    static constexpr int O_F = 0, O_N = NF, HEAD = (NF + DIM + 1) & ~1;
-    static constexpr int O_CK = HEAD, O_DK = O_CK + NSHP, O_PK = O_DK + NSHP, RAW = O_PK + NSHP;
-    static constexpr int SZ = (RAW + 3) & ~3;              // hex 32 doubles = 256 B; tet / quad / tri 20 doubles = 160 B
-};
 
 // ---- static part, once per mesh ---------------------------------------------------------------------
 // J0 block row of node a: [rf < DIM][slot < cnt][cf < NF] at offset DIM*NF*brow[a]:

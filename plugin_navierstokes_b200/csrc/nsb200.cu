@@ -9,12 +9,16 @@
 #include <functional>
 #include <string>
 #include <thread>
+#include <unordered_map>
+#include <chrono>
 #include <vector>
 
 #include "../../include/nsb200.h"
 #include "ns_kernels.cuh"
 #include "ns_launch.h"
 #include "ns_fvcr.cuh"
+#include "ns_graph.h"
+#include "ns_fused.cuh"
 
 using namespace nsb;
 
@@ -22,6 +26,16 @@ namespace nsb {
 __global__ void scale_kernel(int64_t n, double beta, double* __restrict__ a)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] *= beta;
+}
+// once per mesh: SCV volume of every node (sum over the adjacent elements in adjacency order)
+__global__ void node_volume_kernel(int64_t n_node, const int64_t* __restrict__ adj_ptr, const int32_t* __restrict__ adj,
+                                   const double* __restrict__ scvvol, double* __restrict__ nodevol)
+{
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_node) return;
+    double s = 0.0;
+    for (int64_t q = adj_ptr[a]; q < adj_ptr[a + 1]; q++) s += scvvol[adj[q]];
+    nodevol[a] = s;
 }
 __global__ void pack_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ src, double* __restrict__ out)
 {
@@ -64,7 +78,16 @@ struct nsb_ctx {
     double *d_u = nullptr, *d_s0 = nullptr, *d_s1 = nullptr, *d_val = nullptr, *d_def = nullptr;
     double *d_jloc = nullptr, *d_dloc = nullptr;
     int64_t launches = 0;
+    int64_t dev_bytes = 0;                        // device memory held by the context (grid tables, caches, staging)
+    double setup_seconds = 0.0;                   // host preprocessing + table upload of the last nsb_upload_mesh*
     int sm_count = 148;
+    // fused patch kernel (ns_fused.cuh): per-patch tables, node volumes, per-element ray-search flags
+    bool fused_ok = false;
+    std::string fused_note;
+    PatchHdr* d_phdr = nullptr; PatchNode* d_pnodes = nullptr; int32_t* d_pelems = nullptr; int32_t* d_pconn = nullptr;
+    uint32_t* d_pwork = nullptr; PatchAdj* d_padj = nullptr; double* d_nodevol = nullptr; uint8_t* d_elem_fast = nullptr;
+    int32_t n_patch = 0; int max_adj = 0;
+    int64_t scvf_evals = 0, patch_table_bytes = 0;
 };
 
 static int set_err(nsb_ctx* c, int code, const char* fmt, ...)
@@ -76,20 +99,6 @@ static int set_err(nsb_ctx* c, int code, const char* fmt, ...)
 }
 #define CUDA_TRY(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
     return set_err(c, NSB_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); } while (0)
-
-template <class F> static void parallel_for(int64_t n, F fn)
-{
-    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    if (n < 4096) nt = 1;
-    std::vector<std::thread> th;
-    const int64_t chunk = (n + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; t++) {
-        const int64_t lo = t * chunk, hi = std::min(n, lo + chunk);
-        if (lo >= hi) break;
-        th.emplace_back([=]() { fn(lo, hi); });
-    }
-    for (auto& x : th) x.join();
-}
 
 static const int kNSH[4] = {3, 4, 4, 8}, kDIM[4] = {2, 2, 3, 3}, kNSIDE[4] = {3, 4, 4, 6};
 
@@ -148,6 +157,11 @@ static void free_mesh(nsb_ctx* c)
     cudaFree(c->d_scvvol); cudaFree(c->d_rec); cudaFree(c->d_brow); cudaFree(c->d_adj_ptr); cudaFree(c->d_emap);
     cudaFree(c->d_u); cudaFree(c->d_s0); cudaFree(c->d_s1); cudaFree(c->d_val); cudaFree(c->d_def);
     cudaFree(c->d_jloc); cudaFree(c->d_dloc); cudaFree(c->d_j0);
+    cudaFree(c->d_phdr); cudaFree(c->d_pnodes); cudaFree(c->d_pelems); cudaFree(c->d_pconn); cudaFree(c->d_pwork); cudaFree(c->d_padj);
+    cudaFree(c->d_nodevol); cudaFree(c->d_elem_fast);
+    c->d_phdr = nullptr; c->d_pnodes = nullptr; c->d_pelems = c->d_pconn = nullptr; c->d_pwork = nullptr; c->d_padj = nullptr;
+    c->d_nodevol = nullptr; c->d_elem_fast = nullptr; c->fused_ok = false; c->n_patch = 0; c->scvf_evals = 0; c->patch_table_bytes = 0;
+    c->dev_bytes = 0;
     c->d_j0 = nullptr; c->j0_laplace = -1; c->rec_lean = false;
 
     fvcr_free(c->fvcr);
@@ -171,6 +185,14 @@ extern "C" void nsb_destroy(nsb_ctx* c)
 extern "C" int nsb_set_stream(nsb_ctx* c, void* s)
 {
     if (!c) return NSB_ERR_INVALID;
+    if ((cudaStream_t)s == c->stream) return NSB_OK;
+    // work queued on the old stream (table builds, cached J0) must be visible to kernels on the new one
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaEvent_t ev;
+    CUDA_TRY(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventRecord(ev, c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent((cudaStream_t)s, ev, 0));
+    cudaEventDestroy(ev);
     c->stream = (cudaStream_t)s;          // NULL is the legacy default stream
     return NSB_OK;
 }
@@ -186,6 +208,20 @@ extern "C" int64_t nsb_num_dofs(const nsb_ctx* c) { return c ? c->n_dof : 0; }
 extern "C" int64_t nsb_nnz(const nsb_ctx* c) { return c ? c->nnz : 0; }
 extern "C" int nsb_num_colors(const nsb_ctx* c) { return c ? c->n_colors : 0; }
 extern "C" int64_t nsb_launch_count(const nsb_ctx* c) { return c ? c->launches : 0; }
+extern "C" int nsb_query(const nsb_ctx* c, int what, double* out)
+{
+    if (!c || !out) return NSB_ERR_INVALID;
+    switch (what) {
+        case NSB_Q_DEVICE_BYTES: *out = (double)c->dev_bytes; break;
+        case NSB_Q_SETUP_SECONDS: *out = c->setup_seconds; break;
+        case NSB_Q_FUSED: *out = c->fused_ok ? 1.0 : 0.0; break;
+        case NSB_Q_PATCHES: *out = (double)c->n_patch; break;
+        case NSB_Q_SCVF_EVALS: *out = (double)c->scvf_evals; break;
+        case NSB_Q_PATCH_TABLE_BYTES: *out = (double)c->patch_table_bytes; break;
+        default: return NSB_ERR_INVALID;
+    }
+    return NSB_OK;
+}
 extern "C" int nsb_synchronize(nsb_ctx* c)
 {
     if (!c) return NSB_ERR_INVALID;
@@ -194,72 +230,34 @@ extern "C" int nsb_synchronize(nsb_ctx* c)
     return NSB_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// grid preprocessing (host). "entities" are nodes (FV1) or sides (FVCR velocity dofs).
-// ------------------------------------------------------------------------------------------------
-struct EntityGraph {
-    std::vector<int64_t> adj_ptr;   // entity -> incident (element, local index)
-    std::vector<int32_t> adj;       // elem*per + local
-    std::vector<int64_t> brow;      // entity -> neighbouring entities (sorted, incl. itself)
-    std::vector<int32_t> bcol;
-    int max_cnt = 0;
-};
-
-static int build_entity_graph(nsb_ctx* c, int64_t n_elem, int64_t n_ent, int per, const int32_t* conn, EntityGraph& g)
-{
-    if ((double)n_elem * per >= 2147483647.0) return set_err(c, NSB_ERR_UNSUPPORTED, "grid too large for 32-bit adjacency ids");
-    g.adj_ptr.assign(n_ent + 1, 0);
-    for (int64_t e = 0; e < n_elem; e++) for (int k = 0; k < per; k++) {
-        const int32_t nd = conn[e * per + k];
-        if (nd < 0 || nd >= n_ent) return set_err(c, NSB_ERR_INVALID, "connectivity entry out of range (element %lld)", (long long)e);
-        g.adj_ptr[nd + 1]++;
-    }
-    for (int64_t i = 0; i < n_ent; i++) g.adj_ptr[i + 1] += g.adj_ptr[i];
-    g.adj.resize(g.adj_ptr[n_ent]);
-    { std::vector<int64_t> pos(g.adj_ptr.begin(), g.adj_ptr.end() - 1);
-      for (int64_t e = 0; e < n_elem; e++) for (int k = 0; k < per; k++) g.adj[pos[conn[e * per + k]]++] = (int32_t)(e * per + k); }
-    // neighbour lists: count, prefix, fill
-    std::vector<int32_t> cnt(n_ent);
-    auto gather = [&](int64_t i, std::vector<int32_t>& tmp) {
-        tmp.clear();
-        for (int64_t q = g.adj_ptr[i]; q < g.adj_ptr[i + 1]; q++) { const int64_t e = g.adj[q] / per; for (int k = 0; k < per; k++) tmp.push_back(conn[e * per + k]); }
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-    };
-    parallel_for(n_ent, [&](int64_t lo, int64_t hi) { std::vector<int32_t> tmp; for (int64_t i = lo; i < hi; i++) { gather(i, tmp); cnt[i] = (int32_t)tmp.size(); } });
-    g.brow.assign(n_ent + 1, 0);
-    g.max_cnt = 0;
-    for (int64_t i = 0; i < n_ent; i++) { g.brow[i + 1] = g.brow[i] + cnt[i]; g.max_cnt = std::max(g.max_cnt, (int)cnt[i]); }
-    g.bcol.resize(g.brow[n_ent]);
-    parallel_for(n_ent, [&](int64_t lo, int64_t hi) { std::vector<int32_t> tmp; for (int64_t i = lo; i < hi; i++) { gather(i, tmp); std::copy(tmp.begin(), tmp.end(), g.bcol.begin() + g.brow[i]); } });
-    return NSB_OK;
-}
-
-// slot of entity conn[e][k] in the neighbour list of entity conn[e][a]
-static void build_emap(int64_t n_elem, int per, const int32_t* conn, const EntityGraph& g, std::vector<uint8_t>& emap)
-{
-    emap.resize((size_t)n_elem * per * per);
-    parallel_for(n_elem, [&](int64_t lo, int64_t hi) {
-        for (int64_t e = lo; e < hi; e++) for (int a = 0; a < per; a++) {
-            const int32_t na = conn[e * per + a];
-            const int32_t* b = g.bcol.data() + g.brow[na]; const int32_t* en = g.bcol.data() + g.brow[na + 1];
-            for (int k = 0; k < per; k++) emap[(e * per + a) * per + k] = (uint8_t)(std::lower_bound(b, en, conn[e * per + k]) - b);
-        }
-    });
-}
-
-// greedy colouring: no two elements of a colour share an entity; order = colour-major, element-minor
+// greedy colouring: no two elements of a colour share an entity; order = colour-major, element-minor.
+// Colours 0..63 live in one 64-bit mask per entity; an entity whose elements need more (valence > 64 fans) gets extra
+// mask words on demand, so the colour count is unbounded and no two conflicting elements ever share a launch.
 static int color_elements(int64_t n_elem, int64_t n_ent, int per, const int32_t* conn, std::vector<int32_t>& order, std::vector<int64_t>& cptr)
 {
     std::vector<uint64_t> mask(n_ent, 0);
-    std::vector<uint8_t> col(n_elem);
+    std::unordered_map<int64_t, std::vector<uint64_t>> ext;       // entity -> masks of the colours 64.., grown on demand
+    std::vector<int32_t> col(n_elem);
     int ncol = 0;
     for (int64_t e = 0; e < n_elem; e++) {
         uint64_t used = 0;
         for (int k = 0; k < per; k++) used |= mask[conn[e * per + k]];
-        int cc = 0; while (cc < 63 && ((used >> cc) & 1)) cc++;
-        col[e] = (uint8_t)cc; ncol = std::max(ncol, cc + 1);
-        for (int k = 0; k < per; k++) mask[conn[e * per + k]] |= (uint64_t)1 << cc;
+        int cc = 0;
+        if (used != ~(uint64_t)0) { while ((used >> cc) & 1) cc++; }
+        else {
+            // all of 0..63 taken at the element's entities: search the extension words
+            for (int w = 0;; w++) {
+                uint64_t u = 0;
+                for (int k = 0; k < per; k++) { auto it = ext.find(conn[e * per + k]); if (it != ext.end() && (size_t)w < it->second.size()) u |= it->second[w]; }
+                if (u != ~(uint64_t)0) { int b = 0; while ((u >> b) & 1) b++; cc = 64 * (w + 1) + b; break; }
+            }
+        }
+        col[e] = cc; ncol = std::max(ncol, cc + 1);
+        for (int k = 0; k < per; k++) {
+            const int64_t en = conn[e * per + k];
+            if (cc < 64) mask[en] |= (uint64_t)1 << cc;
+            else { auto& v = ext[en]; const size_t w = (size_t)(cc / 64 - 1); if (v.size() <= w) v.resize(w + 1, 0); v[w] |= (uint64_t)1 << (cc % 64); }
+        }
     }
     cptr.assign(ncol + 1, 0);
     for (int64_t e = 0; e < n_elem; e++) cptr[col[e] + 1]++;
@@ -296,9 +294,15 @@ static void morton_order(int64_t n, int dim, const double* coords, std::vector<i
     for (int64_t i = 0; i < n; i++) order[i] = key[i].second;
 }
 
-template <class T> static cudaError_t upload(T** dptr, const T* h, size_t n)
+template <class T> static cudaError_t dev_malloc(nsb_ctx* c, T** dptr, size_t bytes)
 {
-    cudaError_t e = cudaMalloc((void**)dptr, std::max<size_t>(n, 1) * sizeof(T));
+    cudaError_t e = cudaMalloc((void**)dptr, std::max<size_t>(bytes, 1));
+    if (e == cudaSuccess) c->dev_bytes += (int64_t)std::max<size_t>(bytes, 1);
+    return e;
+}
+template <class T> static cudaError_t upload(nsb_ctx* c, T** dptr, const T* h, size_t n)
+{
+    cudaError_t e = dev_malloc(c, dptr, n * sizeof(T));
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice);
 }
@@ -314,8 +318,45 @@ static cudaError_t launch_scvvol(nsb_ctx* c)
     }
 }
 
+// per-patch tables of the fused kernel (ns_patch.h), node volumes, per-element ray-search flags. A grid the patch builder
+// cannot handle leaves fused_ok = false (the two-kernel split path is used) and the reason in fused_note.
+static int setup_fused(nsb_ctx* c, const int32_t* conn, const double* coords, const EntityGraph& g, const std::vector<uint8_t>& emap)
+{
+    c->fused_ok = false; c->fused_note.clear();
+    { const char* ev = getenv("NSB_FUSED"); if (ev && atoi(ev) == 0) { c->fused_note = "disabled by NSB_FUSED=0"; return NSB_OK; } }
+    size_t smem = 0; PatchCaps caps;
+    switch (c->elem) { case 0: smem = fused_smem_bytes_0(g.max_cnt); caps = fused_caps_0(); break; case 1: smem = fused_smem_bytes_1(g.max_cnt); caps = fused_caps_1(); break;
+                       case 2: smem = fused_smem_bytes_2(g.max_cnt); caps = fused_caps_2(); break; default: smem = fused_smem_bytes_3(g.max_cnt); caps = fused_caps_3(); }
+    if (smem > 227 * 1024) { c->fused_note = "block rows too long for the shared-memory accumulators"; return NSB_OK; }
+    PatchPlan plan; std::string perr;
+    if (!build_patch_plan(c->elem, c->n_elem, c->n_node, conn, coords, g.adj_ptr.data(), g.adj.data(), g.brow.data(), emap.data(), caps, plan, perr)) {
+        c->fused_note = perr; return NSB_OK;
+    }
+    CUDA_TRY(c, upload(c, &c->d_phdr, plan.hdr.data(), plan.hdr.size()));
+    CUDA_TRY(c, upload(c, &c->d_pnodes, plan.nodes.data(), plan.nodes.size()));
+    CUDA_TRY(c, upload(c, &c->d_pelems, plan.elems.data(), plan.elems.size()));
+    CUDA_TRY(c, upload(c, &c->d_pconn, plan.pconn.data(), plan.pconn.size()));
+    CUDA_TRY(c, upload(c, &c->d_pwork, plan.work.data(), plan.work.size()));
+    CUDA_TRY(c, upload(c, &c->d_padj, plan.adj.data(), plan.adj.size()));
+    c->n_patch = (int32_t)plan.hdr.size(); c->max_adj = plan.max_adj_per_node; c->scvf_evals = plan.n_scvf_evals;
+    c->patch_table_bytes = (int64_t)(plan.hdr.size() * sizeof(PatchHdr) + plan.nodes.size() * sizeof(PatchNode) + (plan.elems.size() + plan.pconn.size()) * 4 +
+                                     plan.work.size() * 4 + plan.adj.size() * sizeof(PatchAdj));
+    CUDA_TRY(c, dev_malloc(c, &c->d_nodevol, (size_t)c->n_node * sizeof(double)));
+    node_volume_kernel<<<(unsigned)((c->n_node + 255) / 256), 256, 0, c->stream>>>(c->n_node, c->d_adj_ptr, c->d_adj, c->d_scvvol, c->d_nodevol);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    if (c->elem == NSB_HEX && !(getenv("NSB_RAYFAST") && atoi(getenv("NSB_RAYFAST")) == 0)) {
+        CUDA_TRY(c, dev_malloc(c, &c->d_elem_fast, (size_t)c->n_elem));
+        CUDA_TRY(c, launch_ray_safety_3(c->n_elem, c->d_conn, c->d_coords, c->d_elem_fast, c->stream));
+        c->launches++;
+    }
+    c->fused_ok = true;
+    return NSB_OK;
+}
+
 extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coords)
 {
+    const auto t_start = std::chrono::steady_clock::now();
     if (!c) return NSB_ERR_INVALID;
     if (elem < 0 || elem > 3 || n_elem <= 0 || n_node <= 0 || !conn || !coords) return set_err(c, NSB_ERR_INVALID, "nsb_upload_mesh: bad arguments");
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -323,27 +364,30 @@ extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_n
     const int nsh = kNSH[elem], dim = kDIM[elem], nf = dim + 1;
     c->elem = elem; c->disc = NSB_DISC_FV1; c->n_elem = n_elem; c->n_node = n_node; c->n_side = 0;
     EntityGraph g;
-    int rc = build_entity_graph(c, n_elem, n_node, nsh, conn, g);
-    if (rc) return rc;
+    { const std::string ge = build_entity_graph(n_elem, n_node, nsh, conn, g);
+      if (!ge.empty()) return set_err(c, ge.find("too large") != std::string::npos ? NSB_ERR_UNSUPPORTED : NSB_ERR_INVALID, "%s", ge.c_str()); }
     if (g.max_cnt > 255) return set_err(c, NSB_ERR_UNSUPPORTED, "a node has %d neighbours (> 255)", g.max_cnt);
+    if ((double)n_node * nf >= 2147483647.0) return set_err(c, NSB_ERR_UNSUPPORTED, "grid has %lld dofs: column indices are 32-bit", (long long)(n_node * nf));
     std::vector<uint8_t> emap; build_emap(n_elem, nsh, conn, g, emap);
     std::vector<int32_t> order;
     c->n_colors = color_elements(n_elem, n_node, nsh, conn, order, c->h_color_ptr);
     c->max_cnt = g.max_cnt;
     c->n_dof = n_node * nf; c->nnz = g.brow[n_node] * nf * nf;
-    CUDA_TRY(c, upload(&c->d_conn, conn, (size_t)n_elem * nsh));
-    CUDA_TRY(c, upload(&c->d_coords, coords, (size_t)n_node * dim));
-    CUDA_TRY(c, upload(&c->d_brow, g.brow.data(), g.brow.size()));
-    CUDA_TRY(c, upload(&c->d_adj_ptr, g.adj_ptr.data(), g.adj_ptr.size()));
-    CUDA_TRY(c, upload(&c->d_adj, g.adj.data(), g.adj.size()));
-    CUDA_TRY(c, upload(&c->d_emap, emap.data(), emap.size()));
-    CUDA_TRY(c, upload(&c->d_color_order, order.data(), order.size()));
-    { std::vector<int32_t> zo; morton_order(n_node, dim, coords, zo); CUDA_TRY(c, upload(&c->d_node_order, zo.data(), zo.size())); }
-    CUDA_TRY(c, cudaMalloc(&c->d_scvvol, (size_t)n_elem * nsh * sizeof(double)));
+    CUDA_TRY(c, upload(c, &c->d_conn, conn, (size_t)n_elem * nsh));
+    CUDA_TRY(c, upload(c, &c->d_coords, coords, (size_t)n_node * dim));
+    CUDA_TRY(c, upload(c, &c->d_brow, g.brow.data(), g.brow.size()));
+    CUDA_TRY(c, upload(c, &c->d_adj_ptr, g.adj_ptr.data(), g.adj_ptr.size()));
+    CUDA_TRY(c, upload(c, &c->d_adj, g.adj.data(), g.adj.size()));
+    CUDA_TRY(c, upload(c, &c->d_emap, emap.data(), emap.size()));
+    CUDA_TRY(c, upload(c, &c->d_color_order, order.data(), order.size()));
+    { std::vector<int32_t> zo; morton_order(n_node, dim, coords, zo); CUDA_TRY(c, upload(c, &c->d_node_order, zo.data(), zo.size())); }
+    CUDA_TRY(c, dev_malloc(c, &c->d_scvvol, (size_t)n_elem * nsh * sizeof(double)));
     CUDA_TRY(c, launch_scvvol(c));
+    { const int rcf = setup_fused(c, conn, coords, g, emap); if (rcf) return rcf; }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->h_brow.swap(g.brow); c->h_bcol.swap(g.bcol);
     c->mesh_ready = true;
+    c->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     return NSB_OK;
 }
 
@@ -476,7 +520,9 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
     static const bool no_split = getenv("NSB_NOSPLIT") != nullptr;
     // (the split rows kernel keeps JP accumulator copies + the J0 rows per warp in shared memory: bounded row length only)
     const bool lean = !flow && !exact && !no_split && c->max_cnt <= 64;
-    {   // per-(element, ip) record table: [static SCVF geometry | flux record] or the lean record of the split path.
+    static const bool no_fused = getenv("NSB_NOFUSED") != nullptr;
+    const bool use_fused = lean && c->fused_ok && !no_fused;     // fused patch kernel: the SCVF records stay in shared memory
+    if (!use_fused) {   // per-(element, ip) record table: [static SCVF geometry | flux record] or the lean record of the split path.
         // The stride depends on the stabilisation (FLOW) and Jacobian flavour (exact Newton): (re)built on change.
         int stride = 0;
         if (lean) switch (c->elem) { case 0: stride = lean_record_doubles_0(); break; case 1: stride = lean_record_doubles_1(); break;
@@ -488,7 +534,7 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
             CUDA_TRY(c, cudaStreamSynchronize(c->stream));
             if (need > c->rec_bytes) {
                 cudaFree(c->d_rec); c->d_rec = nullptr; c->rec_bytes = 0; c->rec_stride = 0;
-                CUDA_TRY(c, cudaMalloc(&c->d_rec, need));
+                CUDA_TRY(c, dev_malloc(c, &c->d_rec, need));
                 c->rec_bytes = need;
             }
             if (!lean) {
@@ -506,7 +552,7 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
         const int dim = kDIM[c->elem], nf = dim + 1;
         if ((k.what & W_JAC_A) && c->j0_laplace != k.laplace) {
             const size_t nj0 = (size_t)c->h_brow[c->n_node] * dim * nf;
-            if (!c->d_j0) CUDA_TRY(c, cudaMalloc(&c->d_j0, std::max<size_t>(nj0, 1) * sizeof(double)));
+            if (!c->d_j0) CUDA_TRY(c, dev_malloc(c, &c->d_j0, nj0 * sizeof(double)));
             CUDA_TRY(c, cudaMemsetAsync(c->d_j0, 0, nj0 * sizeof(double), c->stream));
             switch (c->elem) { case 0: e = launch_j0_0(m, k.laplace, c->d_j0, c->stream, c->sm_count); break;
                                case 1: e = launch_j0_1(m, k.laplace, c->d_j0, c->stream, c->sm_count); break;
@@ -515,6 +561,22 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
             c->launches++;
             CUDA_TRY(c, e);
             c->j0_laplace = k.laplace;
+        }
+        if (use_fused) {
+            FusedArgs A;
+            memset(&A, 0, sizeof A);
+            A.p = k; A.n_patch = c->n_patch;
+            A.hdr = c->d_phdr; A.nodes = c->d_pnodes; A.elems = c->d_pelems; A.pconn = c->d_pconn; A.work = c->d_pwork; A.adj = c->d_padj;
+            A.coords = c->d_coords; A.scvvol = c->d_scvvol; A.nodevol = c->d_nodevol;
+            A.u = u; A.s0 = s0; A.s1 = s1; A.j0 = c->d_j0; A.beta = beta; A.val = val; A.def = def;
+            A.errflag = c->d_err; A.elem_fast = c->d_elem_fast; A.max_adj = c->max_adj;
+            switch (c->elem) { case 0: e = launch_fused_0(A, c->max_cnt, c->stream, c->sm_count, c->d_counter); break;
+                               case 1: e = launch_fused_1(A, c->max_cnt, c->stream, c->sm_count, c->d_counter); break;
+                               case 2: e = launch_fused_2(A, c->max_cnt, c->stream, c->sm_count, c->d_counter); break;
+                               default: e = launch_fused_3(A, c->max_cnt, c->stream, c->sm_count, c->d_counter); }
+            c->launches++;
+            CUDA_TRY(c, e);
+            return NSB_OK;
         }
 #define NSB_GO(fn) fn(k, m, c->d_rec, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter, c->d_j0)
         switch (c->elem) { case 0: e = NSB_GO(launch_split_0); break; case 1: e = NSB_GO(launch_split_1); break;
@@ -602,7 +664,7 @@ static int check_device_error(nsb_ctx* c)
 static int ensure(nsb_ctx* c, double** p, size_t n)
 {
     if (*p) return NSB_OK;
-    CUDA_TRY(c, cudaMalloc(p, std::max<size_t>(n, 1) * sizeof(double)));
+    CUDA_TRY(c, dev_malloc(c, p, n * sizeof(double)));
     return NSB_OK;
 }
 
@@ -731,12 +793,13 @@ extern "C" int nsb_upload_mesh_fvcr(nsb_ctx* c, int elem, int64_t n_elem, int64_
     c->elem = elem; c->disc = NSB_DISC_FVCR; c->n_elem = n_elem; c->n_node = n_node; c->n_side = n_side;
     for (int64_t i = 0; i < n_elem * nco; i++) if (conn[i] < 0 || conn[i] >= n_node) return set_err(c, NSB_ERR_INVALID, "connectivity entry out of range");
     EntityGraph g;
-    int rc = build_entity_graph(c, n_elem, n_side, ns, esides, g);
-    if (rc) return rc;
+    { const std::string ge = build_entity_graph(n_elem, n_side, ns, esides, g);
+      if (!ge.empty()) return set_err(c, ge.find("too large") != std::string::npos ? NSB_ERR_UNSUPPORTED : NSB_ERR_INVALID, "%s", ge.c_str()); }
     // scalar CSR: velocity rows (side s, d): neighbour sides x dim, then pressures of adjacent elements;
     // pressure row e: its sides x dim (sorted), then itself.
     const int64_t pbase = n_side * dim;
     c->n_dof = pbase + n_elem;
+    if ((double)c->n_dof >= 2147483647.0) return set_err(c, NSB_ERR_UNSUPPORTED, "grid has %lld dofs: column indices are 32-bit", (long long)c->n_dof);
     std::vector<int64_t>& rp = c->h_brow; std::vector<int32_t>& ci = c->h_bcol;
     rp.assign(c->n_dof + 1, 0);
     for (int64_t s = 0; s < n_side; s++) {
@@ -785,20 +848,20 @@ extern "C" int nsb_upload_mesh_fvcr(nsb_ctx* c, int elem, int64_t n_elem, int64_
     for (int64_t s = 0; s <= n_side; s++) srow[s] = s < n_side ? rp[s * dim] : rp[pbase];
     std::vector<int32_t> scnt(n_side);
     for (int64_t s = 0; s < n_side; s++) scnt[s] = (int32_t)(g.brow[s + 1] - g.brow[s]);
-    CUDA_TRY(c, upload(&c->d_conn, conn, (size_t)n_elem * nco));
-    CUDA_TRY(c, upload(&c->d_coords, coords, (size_t)n_node * dim));
-    CUDA_TRY(c, upload(&c->d_esides, esides, (size_t)n_elem * ns));
-    CUDA_TRY(c, upload(&c->d_color_order, order.data(), order.size()));
+    CUDA_TRY(c, upload(c, &c->d_conn, conn, (size_t)n_elem * nco));
+    CUDA_TRY(c, upload(c, &c->d_coords, coords, (size_t)n_node * dim));
+    CUDA_TRY(c, upload(c, &c->d_esides, esides, (size_t)n_elem * ns));
+    CUDA_TRY(c, upload(c, &c->d_color_order, order.data(), order.size()));
     FvcrDev& f = c->fvcr;
     f.n_elem = n_elem; f.n_node = n_node; f.n_side = n_side; f.nnz = c->nnz; f.n_dof = c->n_dof;
     f.conn = c->d_conn; f.coords = c->d_coords; f.esides = c->d_esides; f.color_order = c->d_color_order;
     f.n_colors = c->n_colors; f.color_ptr = nullptr;
-    CUDA_TRY(c, upload(&f.srow, srow.data(), srow.size()));
-    CUDA_TRY(c, upload(&f.scnt, scnt.data(), scnt.size()));
-    CUDA_TRY(c, upload(&f.emap, emap.data(), emap.size()));
-    CUDA_TRY(c, upload(&f.pslot, pslot.data(), pslot.size()));
-    CUDA_TRY(c, upload(&f.psort, psort.data(), psort.size()));
-    CUDA_TRY(c, upload(&f.sadj_ptr, g.adj_ptr.data(), g.adj_ptr.size()));
+    CUDA_TRY(c, upload(c, &f.srow, srow.data(), srow.size()));
+    CUDA_TRY(c, upload(c, &f.scnt, scnt.data(), scnt.size()));
+    CUDA_TRY(c, upload(c, &f.emap, emap.data(), emap.size()));
+    CUDA_TRY(c, upload(c, &f.pslot, pslot.data(), pslot.size()));
+    CUDA_TRY(c, upload(c, &f.psort, psort.data(), psort.size()));
+    CUDA_TRY(c, upload(c, &f.sadj_ptr, g.adj_ptr.data(), g.adj_ptr.size()));
     f.prow0 = rp[pbase];
     c->mesh_ready = true;
     return NSB_OK;

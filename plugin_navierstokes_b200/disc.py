@@ -227,6 +227,12 @@ class _DeviceDisc:
     def launch_count(self):
         return capi.lib().nsb_launch_count(self._ctx)
 
+    def query(self, what):
+        """instrumentation (capi.Q_*): device bytes, set-up seconds, fused-kernel statistics"""
+        out = C.c_double(0.0)
+        self._check(capi.lib().nsb_query(self._ctx, int(what), C.byref(out)))
+        return out.value
+
     def csr(self):
         """(rowptr int64 [ndof+1], colind int32 [nnz]) of the global Jacobian (sorted rows)"""
         rowptr = np.empty(self.num_dofs + 1, dtype=np.int64)
@@ -275,18 +281,28 @@ class _DeviceDisc:
         if on_dev:
             import torch
             assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous()
+            # stream contract: device-pointer calls run on torch's CURRENT stream of u's device, so they are
+            # ordered with the producers of u and with the consumers of the returned tensors like any torch op
+            self.use_stream(torch.cuda.current_stream(u.device).cuda_stream)
+            # a missing output is allocated zero-filled and the caller's beta is kept (same as the host path)
             if jac and values is None:
-                values = torch.empty(self.nnz, dtype=torch.float64, device=u.device)
-                beta = 0.0
+                values = torch.zeros(self.nnz, dtype=torch.float64, device=u.device)
             if dfc and defect is None:
-                defect = torch.empty(self.num_dofs, dtype=torch.float64, device=u.device)
-                beta = 0.0
+                defect = torch.zeros(self.num_dofs, dtype=torch.float64, device=u.device)
+            for name, t, n in (("values", values if jac else None, self.nnz), ("defect", defect if dfc else None, self.num_dofs)):
+                if t is not None and not (_is_torch(t) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == n):
+                    raise UGError("assemble: %s must be a contiguous float64 CUDA tensor with %d entries" % (name, n))
         else:
             u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+            if u.shape[0] != self.num_dofs:
+                raise UGError("assemble: u has %d entries, the grid has %d dofs" % (u.shape[0], self.num_dofs))
             if jac and values is None:
                 values = np.zeros(self.nnz)
             if dfc and defect is None:
                 defect = np.zeros(self.num_dofs)
+            for name, a, n in (("values", values if jac else None, self.nnz), ("defect", defect if dfc else None, self.num_dofs)):
+                if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == n):
+                    raise UGError("assemble: %s must be a C-contiguous float64 numpy array with %d entries" % (name, n))
         ts = None
         keep = []
         if time_series is not None:

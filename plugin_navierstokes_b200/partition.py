@@ -225,10 +225,16 @@ class InterfaceExchange:
             n = p["midx"].size + p["didx"].size
             p["buf"] = t.empty(n, dtype=t.float64, device=self.device)
 
+    def _on_current_stream(self, tensor):
+        """device kernels of the exchange run on torch's current stream: NCCL p2p ops are ordered against that stream"""
+        import torch
+        self.disc.use_stream(torch.cuda.current_stream(tensor.device).cuda_stream)
+
     def _pack(self, idx_t, src, out):
         if src.is_cuda:
             import ctypes as C
             from . import _capi as capi
+            self._on_current_stream(src)
             rc = capi.lib().nsb_pack(self.disc._ctx, idx_t.numel(), C.c_void_p(idx_t.data_ptr()), C.c_void_p(src.data_ptr()),
                                      C.c_void_p(out.data_ptr()))
             assert rc == 0
@@ -240,6 +246,7 @@ class InterfaceExchange:
         if dst.is_cuda:
             import ctypes as C
             from . import _capi as capi
+            self._on_current_stream(dst)
             rc = capi.lib().nsb_unpack_add(self.disc._ctx, idx_t.numel(), C.c_void_p(idx_t.data_ptr()), C.c_void_p(buf.data_ptr()),
                                            C.c_void_p(dst.data_ptr()))
             assert rc == 0
