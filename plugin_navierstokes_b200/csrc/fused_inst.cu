@@ -19,11 +19,10 @@ static cudaError_t fused_t(const FusedArgs& A, int max_cnt, cudaStream_t st, int
     auto kern = fv1_fused_kernel<E, STAB, TD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return e;
+    (void)work_counter;
     const int nblk = std::min<int64_t>(A.n_patch, sm_count);
     if (nblk <= 0) return cudaSuccess;
-    kern<<<nblk, FusedCfg<E>::NT, smem, st>>>(A, max_cnt, work_counter);
+    kern<<<nblk, FusedCfg<E>::NT, smem, st>>>(A, max_cnt);
     return cudaGetLastError();
 }
 

@@ -31,9 +31,14 @@ template <int E> struct FusedCfg {
     static constexpr int RS = LeanRec<E>::SZ;
     static constexpr int RSTR = RS + 2;                             // record stride in shared memory: 16-byte accesses of adjacent slots hit distinct bank groups
     static constexpr int NV = DIM + 2;                              // accumulated values per slot: D, C[DIM], PP
-    static constexpr int NPW = 32 / NSH;                            // patch nodes per warp in the rows phase
     static constexpr int DSTR = NSH * DIM + 1, NSTR = NSH + 1;      // odd strides of the per-ip tables
-    static constexpr int NCOL = NSH * DIM + NSH * NF + NSH;         // doubles per element column: x, u, SCV volumes
+    static constexpr int NCOL = NSH * DIM + NSH * NF + NSH;         // doubles per element: corner coordinates, unknowns, SCV volumes
+    static constexpr int CSTR = NCOL | 1;                           // element-major rows, odd stride: the lanes of a warp (same element, different
+                                                                    // corners / different elements, same corner) hit different banks
+    static constexpr int PARTS = 4;                                 // rows phase: PARTS * NSH lanes work on one patch node
+    static constexpr int NPW = 32 / (PARTS * NSH);                  // patch nodes a warp assembles at a time
+    static constexpr int NWARP = NT / 32;
+    static constexpr int JREG = NF == 4 ? 6 : 4;                    // J0 words (double2 / double) per lane and node prefetched in registers
     // capacities of one patch (tile = node-box the grid is binned into; see ns_patch.h)
     static constexpr int MAXW = 512;
     static constexpr int MAXE = E == E_HEX ? 80 : (E == E_TET ? 160 : (E == E_QUAD ? 128 : 224));
@@ -56,7 +61,7 @@ __host__ __device__ constexpr int fused_cnt_pad(int max_cnt) { return (max_cnt +
 // byte offsets of the shared-memory regions
 template <int E> struct FusedLayout {
     using C = FusedCfg<E>;
-    size_t o_rec, o_un, o_dnt, o_nt, o_lip, o_cor, o_side, o_iptab, o_inc, o_work, o_adj, o_nodes, o_efast, o_misc, total;
+    size_t o_rec, o_cols, o_acc, o_dnt, o_nt, o_lip, o_cor, o_side, o_iptab, o_inc, o_work, o_adj, o_nodes, o_efast, o_misc, total;
     int cntp;
     __host__ __device__ explicit FusedLayout(int max_cnt)
     {
@@ -64,8 +69,8 @@ template <int E> struct FusedLayout {
         size_t o = 0;
         auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return at; };
         o_rec = take(sizeof(double) * C::MAXW * C::RSTR);
-        const size_t cols = sizeof(double) * C::NCOL * C::MAXE, accs = sizeof(double) * (size_t)C::MAXN * C::NV * cntp;
-        o_un = take(cols > accs ? cols : accs);
+        o_cols = take(sizeof(double) * C::CSTR * C::MAXE);
+        o_acc = take(sizeof(double) * (size_t)C::NWARP * C::NPW * C::NV * cntp);
         o_dnt = take(sizeof(double) * C::NIP * C::DSTR);
         o_nt = take(sizeof(double) * C::NIP * C::NSTR);
         o_lip = take(sizeof(double) * C::NIP * 3);
@@ -74,8 +79,8 @@ template <int E> struct FusedLayout {
         o_iptab = take(sizeof(int) * C::NIP * 12);
         o_inc = take(sizeof(int) * C::NSH * C::NINC);
         o_work = take(sizeof(uint32_t) * C::MAXW);
-        o_adj = take(sizeof(PatchAdj) * C::MAXA);
-        o_nodes = take(sizeof(PatchNode) * C::MAXN);
+        o_adj = take(2 * sizeof(PatchAdj) * C::MAXA);               // ping-pong: the next patch's tables arrive while the rows are written
+        o_nodes = take(2 * sizeof(PatchNode) * C::MAXN);
         o_efast = take(C::MAXE);
         o_misc = take(64);
         total = o;
@@ -86,16 +91,16 @@ template <int E> struct FusedLayout {
 template <int E> struct FusedSmem {
     double *rec, *xs, *us, *vs, *acc, *dnt, *Nt, *lip, *cortab;
     int *sidetab, *iptab, *inctab;
-    uint32_t* work; PatchAdj* adj; PatchNode* nodes; uint8_t* efast; int* misc;
+    uint32_t* work; PatchAdj* adj; PatchNode* nodes; PatchAdj* adjbuf[2]; PatchNode* nodebuf[2]; uint8_t* efast; int* misc;
     int cntp;
     NSB_HD FusedSmem(unsigned char* base, const FusedLayout<E>& L)
     {
         using C = FusedCfg<E>;
         rec = reinterpret_cast<double*>(base + L.o_rec);
-        xs = reinterpret_cast<double*>(base + L.o_un);
-        us = xs + C::NSH * C::DIM * C::MAXE;
-        vs = us + C::NSH * C::NF * C::MAXE;
-        acc = xs;                                                   // the accumulators alias the element columns (rows phase)
+        xs = reinterpret_cast<double*>(base + L.o_cols);
+        us = xs + C::NSH * C::DIM;
+        vs = us + C::NSH * C::NF;
+        acc = reinterpret_cast<double*>(base + L.o_acc);            // [warp][node of the warp][NV][cntp]
         dnt = reinterpret_cast<double*>(base + L.o_dnt);
         Nt = reinterpret_cast<double*>(base + L.o_nt);
         lip = reinterpret_cast<double*>(base + L.o_lip);
@@ -104,8 +109,9 @@ template <int E> struct FusedSmem {
         iptab = reinterpret_cast<int*>(base + L.o_iptab);
         inctab = reinterpret_cast<int*>(base + L.o_inc);
         work = reinterpret_cast<uint32_t*>(base + L.o_work);
-        adj = reinterpret_cast<PatchAdj*>(base + L.o_adj);
-        nodes = reinterpret_cast<PatchNode*>(base + L.o_nodes);
+        adjbuf[0] = reinterpret_cast<PatchAdj*>(base + L.o_adj); adjbuf[1] = adjbuf[0] + C::MAXA;
+        nodebuf[0] = reinterpret_cast<PatchNode*>(base + L.o_nodes); nodebuf[1] = nodebuf[0] + C::MAXN;
+        adj = adjbuf[0]; nodes = nodebuf[0];
         efast = base + L.o_efast;
         misc = reinterpret_cast<int*>(base + L.o_misc);
         cntp = L.cntp;
@@ -150,7 +156,7 @@ template <int E> NSB_DEV void fused_stage_tables(const FusedSmem<E>& S, int tid,
 }
 
 // element column `el`, entry i
-#define NSB_FCOL(base, i) (base)[(i) * C::MAXE + el]
+#define NSB_FCOL(base, i) (base)[(i) + el * C::CSTR]
 
 // FV1Geometry of one SCVF from the element's shared column (see ip_geometry in ns_fv1.cuh)
 template <int E>
@@ -636,23 +642,58 @@ NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip
 // ------------------------------------------------------------------------------------------------
 // lane functions of one patch (tid in [0, NT))
 // ------------------------------------------------------------------------------------------------
-// load: patch tables + element columns
-template <int E> NSB_HD void fused_load(const FusedArgs& A, const FusedSmem<E>& S, const PatchHdr& H, int tid)
+// asynchronous global -> shared copies (cp.async, SASS LDGSTS): issued for the NEXT patch while the rows of the current one
+// are assembled, completed by fused_copy_wait before the barrier that hands the buffers to the next iteration.
+NSB_HD void fused_copy8(void* dst, const void* src)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
+    *reinterpret_cast<uint64_t*>(dst) = *reinterpret_cast<const uint64_t*>(src);
+#endif
+}
+NSB_HD void fused_copy16(void* dst, const void* src)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
+    reinterpret_cast<uint64_t*>(dst)[0] = reinterpret_cast<const uint64_t*>(src)[0];
+    reinterpret_cast<uint64_t*>(dst)[1] = reinterpret_cast<const uint64_t*>(src)[1];
+#endif
+}
+NSB_HD void fused_copy4(void* dst, const void* src)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
+    *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
+#endif
+}
+NSB_HD void fused_copy_wait()
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
+// load of one patch: tables -> work / adjbuf[par] / nodebuf[par], corner data of the patch's elements -> element rows.
+// Only the connectivity lookups are synchronous loads; everything else is an asynchronous copy.
+template <int E> NSB_HD void fused_load(const FusedArgs& A, const FusedSmem<E>& S, const PatchHdr& H, int par, int tid)
 {
     using C = FusedCfg<E>;
     constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF;
-    for (int i = tid; i < H.n_work; i += C::NT) S.work[i] = A.work[H.work0 + i];
-    for (int i = tid; i < H.n_adj; i += C::NT) S.adj[i] = A.adj[H.adj0 + i];
-    for (int i = tid; i < H.n_node; i += C::NT) S.nodes[i] = A.nodes[H.node0 + i];
+    for (int i = tid; i < H.n_work; i += C::NT) fused_copy4(S.work + i, A.work + H.work0 + i);
+    for (int i = tid; i < H.n_adj; i += C::NT) fused_copy16(S.adjbuf[par] + i, A.adj + H.adj0 + i);
+    for (int i = tid; i < H.n_node; i += C::NT) fused_copy16(S.nodebuf[par] + i, A.nodes + H.node0 + i);
     for (int i = tid; i < H.n_elem * NSH; i += C::NT) {
         const int el = i / NSH, k = i - el * NSH;
         const int64_t e = A.elems[H.elem0 + el];
         const int64_t ndk = A.pconn[(int64_t)(H.elem0 + el) * NSH + k];
 #pragma unroll
-        for (int f = 0; f < NF; f++) NSB_FCOL(S.us, k * NF + f) = A.u[ndk * NF + f];
+        for (int f = 0; f < NF; f++) fused_copy8(&NSB_FCOL(S.us, k * NF + f), A.u + ndk * NF + f);
 #pragma unroll
-        for (int d = 0; d < DIM; d++) NSB_FCOL(S.xs, k * DIM + d) = A.coords[ndk * DIM + d];
-        NSB_FCOL(S.vs, k) = A.scvvol[e * NSH + k];
+        for (int d = 0; d < DIM; d++) fused_copy8(&NSB_FCOL(S.xs, k * DIM + d), A.coords + ndk * DIM + d);
+        fused_copy8(&NSB_FCOL(S.vs, k), A.scvvol + e * NSH + k);
         if (k == 0) S.efast[el] = A.elem_fast ? A.elem_fast[e] : (uint8_t)0;
     }
 }
@@ -670,65 +711,72 @@ template <int E, int STAB, bool TD> NSB_HD bool fused_flux(const FusedArgs& A, c
     return ok;
 }
 
-// rows, step 1: clear the accumulators of the patch nodes
-template <int E> NSB_HD void fused_rows_zero(const FusedSmem<E>& S, const PatchHdr& H, int tid)
+// rows phase. PARTS * NSH lanes work on one patch node: lane (h, k) = (part h, corner k). For every adjacent element (in the
+// order of the global adjacency list) the lane sums the NINC incident SCVF records of its corner and adds its part
+//   h = 0: the convective diagonal D (+ the defect fluxes, k < NF)      h = 1: the pressure column PP of the continuity row
+//   h = 2: the velocity columns C[0 .. DIM-2] of the continuity row     h = 3: C[DIM-1]
+// into the per-slot accumulators of the node (`accn`, private to the node's lanes). The corners of one element are distinct
+// nodes and the parts own different accumulator arrays, so a step is conflict-free; steps are separated by __syncwarp.
+// step 1: clear the node's accumulators (`lg` = lane index within the node's PARTS * NSH lanes)
+template <int E> NSB_HD void fused_rows_zero(const FusedSmem<E>& S, double* accn, int lg)
 {
     using C = FusedCfg<E>;
-    const int n = H.n_node * C::NV * S.cntp;
-    for (int i = tid; i < n; i += C::NT) S.acc[i] = 0.0;
+    for (int i = lg; i < C::NV * S.cntp; i += C::PARTS * C::NSH) accn[i] = 0.0;
 }
 
-// rows, step 2: lane = (patch node nl, corner k) accumulates the adjacency entry j of its node (j is warp-uniform; the
-// device kernel separates the steps by __syncwarp). fs: the lane's defect sum (component k < NF).
-template <int E> NSB_HD void fused_rows_accum_step(const FusedArgs& A, const FusedSmem<E>& S, int nl, int k, int j, double& fs)
+// step 2: adjacency entry j of node nl
+template <int E> NSB_HD void fused_rows_accum_step(const FusedArgs& A, const FusedSmem<E>& S, double* accn, int nl, int h, int k, int j, double& fs)
 {
     using C = FusedCfg<E>;
     using LR = LeanRec<E>;
-    constexpr int DIM = C::DIM, NF = C::NF, NINC = C::NINC, NV = C::NV;
+    constexpr int DIM = C::DIM, NF = C::NF, NINC = C::NINC;
     const KParams& p = A.p;
     const bool jac_a = p.what & W_JAC_A, def_a = p.what & W_DEF_A;
     const PatchNode& Nd = S.nodes[nl];
     if (j >= Nd.adj_cnt) return;
     const PatchAdj& a = S.adj[Nd.adj_off + j];
-    double D = 0.0, PP = 0.0, Cn[DIM];
+    const int slot = a.emap[k];
+    if (h < 2) {
+        double V = 0.0;
+        const int off = h == 0 ? LR::O_DK : LR::O_PK;
 #pragma unroll
-    for (int d = 0; d < DIM; d++) Cn[d] = 0.0;
-#pragma unroll
-    for (int t = 0; t < NINC; t++) {
-        const double* rc = S.rec + a.slot[t] * C::RSTR;
-        const bool neg = S.inctab[a.la * NINC + t] & 256;
-        if (def_a && k < NF) { const double f = rc[LR::O_F + k]; fs += neg ? -f : f; }
-        if (jac_a) {
-            const double sg = neg ? -p.scale_a : p.scale_a;
-            D += sg * rc[LR::O_DK + k];
-            PP += sg * rc[LR::O_PK + k];
-            const double w = sg * rc[LR::O_CK + k];
-#pragma unroll
-            for (int d = 0; d < DIM; d++) Cn[d] += w * rc[LR::O_N + d];
+        for (int t = 0; t < NINC; t++) {
+            const double* rc = S.rec + a.slot[t] * C::RSTR;
+            const bool neg = S.inctab[a.la * NINC + t] & 256;
+            if (h == 0 && def_a && k < NF) { const double f = rc[LR::O_F + k]; fs += neg ? -f : f; }
+            if (jac_a) V += (neg ? -p.scale_a : p.scale_a) * rc[off + k];
         }
-    }
-    if (jac_a) {
-        double* accn = S.acc + nl * (NV * S.cntp);
-        const int slot = a.emap[k];
-        accn[slot] += D;
+        if (jac_a) accn[(h == 0 ? 0 : 1 + DIM) * S.cntp + slot] += V;
+    } else if (jac_a) {
+        constexpr int ND0 = DIM - 1;                              // h = 2: components 0 .. DIM-2, h = 3: component DIM-1
+        const int d0 = h == 2 ? 0 : ND0, d1 = h == 2 ? ND0 : DIM;
+        double Cn[DIM];
 #pragma unroll
-        for (int d = 0; d < DIM; d++) accn[(1 + d) * S.cntp + slot] += Cn[d];
-        accn[(1 + DIM) * S.cntp + slot] += PP;
+        for (int d = 0; d < DIM; d++) Cn[d] = 0.0;
+#pragma unroll
+        for (int t = 0; t < NINC; t++) {
+            const double* rc = S.rec + a.slot[t] * C::RSTR;
+            const bool neg = S.inctab[a.la * NINC + t] & 256;
+            const double w = (neg ? -p.scale_a : p.scale_a) * rc[LR::O_CK + k];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) if (d >= d0 && d < d1) Cn[d] += w * rc[LR::O_N + d];
+        }
+#pragma unroll
+        for (int d = 0; d < DIM; d++) if (d >= d0 && d < d1) accn[(1 + d) * S.cntp + slot] += Cn[d];
     }
 }
 
-// rows, step 3 (lane k == 0 of the node): lumped mass on the diagonal (add_jac_M_elem :781-808)
-template <int E> NSB_HD void fused_rows_mass(const FusedArgs& A, const FusedSmem<E>& S, int nl)
+// step 3 (one lane of the node): lumped mass on the diagonal (add_jac_M_elem :781-808)
+template <int E> NSB_HD void fused_rows_mass(const FusedArgs& A, const FusedSmem<E>& S, double* accn, int nl)
 {
-    using C = FusedCfg<E>;
     const KParams& p = A.p;
     const PatchNode& Nd = S.nodes[nl];
     if (!(p.what & W_JAC_M) || Nd.adj_cnt == 0) return;
     const int self = S.adj[Nd.adj_off].self;
-    S.acc[nl * (C::NV * S.cntp) + self] += p.scale_m * A.nodevol[Nd.node] * p.rho;
+    accn[self] += p.scale_m * A.nodevol[Nd.node] * p.rho;
 }
 
-// rows, step 4: defect entry (node, component k < NF)   (add_def_A_elem / add_def_M_elem / add_rhs_elem)
+// step 4: defect entry (node, component k < NF)   (add_def_A_elem / add_def_M_elem / add_rhs_elem)
 template <int E> NSB_HD void fused_rows_defect(const FusedArgs& A, const FusedSmem<E>& S, int nl, int k, double fs)
 {
     using C = FusedCfg<E>;
@@ -745,69 +793,104 @@ template <int E> NSB_HD void fused_rows_defect(const FusedArgs& A, const FusedSm
     *q = (A.beta == 0.0) ? d : A.beta * (*q) + d;
 }
 
-// rows, step 5: the NF rows of the node, written once. lane k of the node's NSH lanes handles the 16-byte chunks
-// k, k + NSH, ... of each row (3-D) or the entries k, k + NSH, ... (2-D).
-template <int E> NSB_HD void fused_rows_out(const FusedArgs& A, const FusedSmem<E>& S, int nl, int k)
+// step 5: the NF rows of node nl, written once by a whole warp (`lane`, `nlanes` = 32 on the device): consecutive lanes
+// write consecutive 16-byte chunks (3-D) / doubles (2-D) of the node's contiguous rows. The J0 words the lane needs are
+// word w = lane + i * nlanes of the node's DIM * NF * cnt doubles; the device passes the first JREG of them in registers
+// (fused_j0_prefetch, issued before the accumulation so that their latency is hidden), jpre == nullptr reads them here.
+template <int E> struct FusedJ0 { double v[FusedCfg<E>::JREG][FusedCfg<E>::NF == 4 ? 2 : 1]; };
+
+template <int E> NSB_HD void fused_j0_prefetch(const FusedArgs& A, const FusedSmem<E>& S, int nl, int lane, int nlanes, FusedJ0<E>& J)
 {
     using C = FusedCfg<E>;
-    constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NV = C::NV;
+    constexpr int DIM = C::DIM, NF = C::NF, W = NF == 4 ? 2 : 1;
+    const PatchNode& Nd = S.nodes[nl];
+    const int nw = Nd.cnt * (DIM * NF) / W;                      // J0 words of the node
+    const double* j0g = A.j0 + Nd.b0 * (DIM * NF);
+#pragma unroll
+    for (int i = 0; i < C::JREG; i++) {
+        const int w = lane + i * nlanes;
+        if (w < nw) {
+#ifdef __CUDA_ARCH__
+            if constexpr (W == 2) { const double2 t = __ldcs(reinterpret_cast<const double2*>(j0g) + w); J.v[i][0] = t.x; J.v[i][1] = t.y; }
+            else J.v[i][0] = __ldcs(j0g + w);
+#else
+            for (int q = 0; q < W; q++) J.v[i][q] = j0g[w * W + q];
+#endif
+        }
+    }
+}
+
+template <int E> NSB_HD void fused_rows_out(const FusedArgs& A, const FusedSmem<E>& S, const double* acc, int nl, int lane, int nlanes, const FusedJ0<E>* jpre)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NF = C::NF;
     const KParams& p = A.p;
     const bool jac_a = p.what & W_JAC_A;
     const PatchNode& Nd = S.nodes[nl];
     const int cnt = Nd.cnt, cntp = S.cntp;
-    const double* acc = S.acc + nl * (NV * cntp);
     const double s_visc = p.visc * p.rho * p.scale_a, s_pres = p.scale_a;
     double* out = A.val + Nd.b0 * (NF * NF);
     const double* j0g = A.j0 + Nd.b0 * (DIM * NF);
     const double beta = A.beta;
-    const int rowlen = cnt * NF;
     if constexpr (NF == 4) {
-        const int n2 = 2 * cnt;                                  // 16-byte chunks per row
-#pragma unroll
-        for (int rf = 0; rf < NF; rf++) {
-            double* orow = out + rf * rowlen;
-            for (int i = k; i < n2; i += NSH) {
-                const int slot = i >> 1, cp = i & 1;
-                double vx, vy;
-                if (rf < DIM) {
-                    vx = 0.0; vy = 0.0;
-                    if (jac_a) {
+        const int n2 = 2 * cnt, nw0 = DIM * n2, nwt = NF * n2;   // 16-byte chunks per row, in the J0 rows, in all rows
+        auto chunk = [&](int w, bool have, double jx, double jy) {
+            const int rf = (w >= n2) + (w >= 2 * n2) + (w >= 3 * n2);
+            const int i = w - rf * n2, slot = i >> 1, cp = i & 1;
+            double vx, vy;
+            if (w < nw0) {
+                vx = 0.0; vy = 0.0;
+                if (jac_a) {
+                    if (!have) {
 #ifdef __CUDA_ARCH__
-                        const double2 jv = __ldcs(reinterpret_cast<const double2*>(j0g + rf * rowlen) + i);
-                        vx = jv.x * s_visc; vy = jv.y * (cp ? s_pres : s_visc);
+                        const double2 t = __ldcs(reinterpret_cast<const double2*>(j0g) + w); jx = t.x; jy = t.y;
 #else
-                        const double* jv = j0g + rf * rowlen + 2 * i; vx = jv[0] * s_visc; vy = jv[1] * (cp ? s_pres : s_visc);
+                        jx = j0g[2 * w]; jy = j0g[2 * w + 1];
 #endif
                     }
-                    const double D = acc[slot];
-                    if (rf == 2 * cp) vx += D;
-                    if (rf == 2 * cp + 1) vy += D;
-                } else {
-                    vx = acc[(1 + 2 * cp) * cntp + slot]; vy = acc[(2 + 2 * cp) * cntp + slot];
+                    vx = jx * s_visc; vy = jy * (cp ? s_pres : s_visc);
                 }
+                const double D = acc[slot];
+                if (rf == 2 * cp) vx += D;
+                if (rf == 2 * cp + 1) vy += D;
+            } else {
+                vx = acc[(1 + 2 * cp) * cntp + slot]; vy = acc[(2 + 2 * cp) * cntp + slot];
+            }
 #ifdef __CUDA_ARCH__
-                double2* o2 = reinterpret_cast<double2*>(orow) + i;
-                if (beta == 0.0) __stcs(o2, make_double2(vx, vy));
-                else { double2 o = *o2; o.x = beta * o.x + vx; o.y = beta * o.y + vy; *o2 = o; }
+            double2* o2 = reinterpret_cast<double2*>(out) + w;
+            if (beta == 0.0) __stcs(o2, make_double2(vx, vy));
+            else { double2 o = *o2; o.x = beta * o.x + vx; o.y = beta * o.y + vy; *o2 = o; }
 #else
-                if (beta == 0.0) { orow[2 * i] = vx; orow[2 * i + 1] = vy; }
-                else { orow[2 * i] = beta * orow[2 * i] + vx; orow[2 * i + 1] = beta * orow[2 * i + 1] + vy; }
+            if (beta == 0.0) { out[2 * w] = vx; out[2 * w + 1] = vy; }
+            else { out[2 * w] = beta * out[2 * w] + vx; out[2 * w + 1] = beta * out[2 * w + 1] + vy; }
 #endif
-            }
+        };
+        // the first JREG rounds use the register-prefetched J0 words (compile-time register indices), the rest reads directly
+#pragma unroll
+        for (int it = 0; it < C::JREG; it++) {
+            const int w = lane + it * nlanes;
+            if (w < nwt) { if (jpre) chunk(w, true, jpre->v[it][0], jpre->v[it][1]); else chunk(w, false, 0.0, 0.0); }
         }
+        for (int w = lane + C::JREG * nlanes; w < nwt; w += nlanes) chunk(w, false, 0.0, 0.0);
     } else {
-        for (int rf = 0; rf < NF; rf++) {
-            double* orow = out + rf * rowlen;
-            for (int i = k; i < rowlen; i += NSH) {
-                const int slot = i / NF, cf = i - slot * NF;
-                double v;
-                if (rf < DIM) {
-                    v = jac_a ? j0g[rf * rowlen + i] * (cf < DIM ? s_visc : s_pres) : 0.0;
-                    if (cf == rf) v += acc[slot];
-                } else v = acc[(1 + cf) * cntp + slot];
-                orow[i] = (beta == 0.0) ? v : beta * orow[i] + v;
-            }
+        const int rowlen = cnt * NF, nw0 = DIM * rowlen, nwt = NF * rowlen;
+        auto entry = [&](int w, bool have, double jv) {
+            const int rf = w / rowlen, i = w - rf * rowlen;
+            const int slot = i / NF, cf = i - slot * NF;
+            double v;
+            if (w < nw0) {
+                v = 0.0;
+                if (jac_a) v = (have ? jv : j0g[w]) * (cf < DIM ? s_visc : s_pres);
+                if (cf == rf) v += acc[slot];
+            } else v = acc[(1 + cf) * cntp + slot];
+            out[w] = (beta == 0.0) ? v : beta * out[w] + v;
+        };
+#pragma unroll
+        for (int it = 0; it < C::JREG; it++) {
+            const int w = lane + it * nlanes;
+            if (w < nwt) { if (jpre) entry(w, true, jpre->v[it][0]); else entry(w, false, 0.0); }
         }
+        for (int w = lane + C::JREG * nlanes; w < nwt; w += nlanes) entry(w, false, 0.0);
     }
 }
 
@@ -846,64 +929,77 @@ template <int E> NSB_DEV bool fused_star_shaped(const double* x)
 // the kernel: persistent CTAs, patches handed out by an atomic ticket
 // ------------------------------------------------------------------------------------------------
 template <int E, int STAB, bool TD>
-__global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const FusedArgs A, int max_cnt, unsigned long long* __restrict__ work_counter)
+__global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const FusedArgs A, int max_cnt)
 {
     using C = FusedCfg<E>;
-    constexpr int NSH = C::NSH, NF = C::NF, NPW = C::NPW, DIM = C::DIM;
+    constexpr int NSH = C::NSH, NF = C::NF, NPW = C::NPW, NWARP = C::NWARP, LPN = C::PARTS * NSH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FusedLayout<E> L(max_cnt);
-    const FusedSmem<E> S(smem_raw, L);
+    FusedSmem<E> S(smem_raw, L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     fused_stage_tables<E>(S, tid, C::NT);
     const int what = A.p.what;
     const bool want_jac = what & (W_JAC_A | W_JAC_M), want_def = what & (W_DEF_A | W_DEF_M | W_RHS);
-    const bool flux_needed = what & (W_JAC_A | W_DEF_A);
-    const int jj = lane / NSH, k = lane - jj * NSH;
+    const bool flux_needed = what & (W_JAC_A | W_DEF_A), jac_a = what & W_JAC_A;
+    // rows phase: lane = (node jj of the NPW the warp assembles at a time, part h, corner k)
+    const int jj = lane / LPN, lg = lane - jj * LPN, h = lg / NSH, k = lg - h * NSH;
     const bool lane_on = jj < NPW;
-    const int j0_lines = (max_cnt * DIM * NF * (int)sizeof(double) + 127) >> 7;
-    for (;;) {
-        if (tid == 0) S.misc[0] = (int)atomicAdd(work_counter, 1ULL);
-        __syncthreads();
-        const int pi = S.misc[0];
-        if (pi >= A.n_patch) break;
+    double* const accw = S.acc + (size_t)warp * NPW * (C::NV * S.cntp);
+    double* const accn = accw + (lane_on ? jj : 0) * (C::NV * S.cntp);
+    auto load_hdr = [&](int pi) {
         PatchHdr H;
-        {
-            const int4* hp = reinterpret_cast<const int4*>(A.hdr + pi);
-            const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
-            H.node0 = h0.x; H.n_node = h0.y; H.elem0 = h0.z; H.n_elem = h0.w; H.work0 = h1.x; H.n_work = h1.y; H.adj0 = h1.z; H.n_adj = h1.w;
-        }
-        fused_load<E>(A, S, H, tid);
-        __syncthreads();
-        if (flux_needed) {
-            if (what & W_JAC_A) {                                // the J0 rows of the patch nodes are needed at the end of the patch: pull them into L2 now
-                for (int i = tid; i < H.n_node * j0_lines; i += C::NT) {
-                    const int nl = i / j0_lines, li = i - nl * j0_lines;
-                    const PatchNode& Nd = S.nodes[nl];
-                    if (li * 16 < Nd.cnt * (DIM * NF)) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.j0 + Nd.b0 * (DIM * NF) + li * 16));
-                }
+        const int4* hp = reinterpret_cast<const int4*>(A.hdr + pi);
+        const int4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+        H.node0 = h0.x; H.n_node = h0.y; H.elem0 = h0.z; H.n_elem = h0.w; H.work0 = h1.x; H.n_work = h1.y; H.adj0 = h1.z; H.n_adj = h1.w;
+        return H;
+    };
+    // static schedule: CTA b assembles the patches b, b + gridDim.x, ... ; the tables and corner data of the next patch are
+    // copied asynchronously (cp.async) into the buffers the rows phase does not use while the rows of the current one are written
+    int pi = blockIdx.x, par = 0;
+    if (pi >= A.n_patch) return;
+    PatchHdr H = load_hdr(pi);
+    fused_load<E>(A, S, H, par, tid);
+    for (;;) {
+        S.adj = S.adjbuf[par]; S.nodes = S.nodebuf[par];
+        fused_copy_wait();
+        __syncthreads();                                         // tables + element rows of this patch are in shared memory
+        const int pn = pi + (int)gridDim.x;
+        PatchHdr Hn = H;
+        if (pn < A.n_patch) Hn = load_hdr(pn);                   // consumed after the flux phase
+        if (flux_needed && !fused_flux<E, STAB, TD>(A, S, H, tid)) atomicExch(A.errflag, 1);
+        __syncthreads();                                         // records complete; element rows, work list and flags are dead
+        if (pn < A.n_patch) fused_load<E>(A, S, Hn, par ^ 1, tid);
+        for (int nl0 = warp * NPW; nl0 < H.n_node; nl0 += NWARP * NPW) {
+            FusedJ0<E> j0r[NPW];                                 // J0 rows of the warp's nodes -> registers (in flight during the accumulation)
+            if (jac_a) {
+#pragma unroll
+                for (int q = 0; q < NPW; q++) if (nl0 + q < H.n_node) fused_j0_prefetch<E>(A, S, nl0 + q, lane, 32, j0r[q]);
             }
-            if (!fused_flux<E, STAB, TD>(A, S, H, tid)) atomicExch(A.errflag, 1);
-        }
-        __syncthreads();
-        if (want_jac) fused_rows_zero<E>(S, H, tid);
-        __syncthreads();
-        for (int nl0 = warp * NPW; nl0 < H.n_node; nl0 += (C::NT / 32) * NPW) {
             const int nl = nl0 + jj;
             const bool on = lane_on && nl < H.n_node;
             double fs = 0.0;
+            if (on && want_jac) fused_rows_zero<E>(S, accn, lg);
+            __syncwarp();
             if (flux_needed) {
                 const int mycnt = on ? (int)S.nodes[nl].adj_cnt : 0;
                 const int mx = __reduce_max_sync(0xffffffffu, mycnt);
                 for (int j = 0; j < mx; j++) {
-                    if (on) fused_rows_accum_step<E>(A, S, nl, k, j, fs);
+                    if (on) fused_rows_accum_step<E>(A, S, accn, nl, h, k, j, fs);
                     __syncwarp();
                 }
             }
-            if (on && k == 0) fused_rows_mass<E>(A, S, nl);
+            if (on && lg == 0) fused_rows_mass<E>(A, S, accn, nl);
             __syncwarp();
-            if (on && want_def && k < NF) fused_rows_defect<E>(A, S, nl, k, fs);
-            if (on && want_jac) fused_rows_out<E>(A, S, nl, k);
+            if (on && want_def && h == 0 && k < NF) fused_rows_defect<E>(A, S, nl, k, fs);
+            if (want_jac) {
+#pragma unroll
+                for (int q = 0; q < NPW; q++)
+                    if (nl0 + q < H.n_node) fused_rows_out<E>(A, S, accw + q * (C::NV * S.cntp), nl0 + q, lane, 32, jac_a ? &j0r[q] : nullptr);
+            }
+            __syncwarp();                                        // the accumulators are reused by the warp's next nodes
         }
+        if (pn >= A.n_patch) break;
+        pi = pn; H = Hn; par ^= 1;
     }
 }
 

@@ -97,7 +97,7 @@ int run(int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coord
     const FusedLayout<E> L(g.max_cnt);
     std::vector<unsigned char> smem(L.total + 64);
     unsigned char* base = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
-    const FusedSmem<E> S(base, L);
+    FusedSmem<E> S(base, L);
     for (int tid = 0; tid < C::NT; tid++) fused_stage_tables<E>(S, tid, C::NT);
     const int what = kp.what;
     const bool want_jac = what & (W_JAC_A | W_JAC_M), want_def = what & (W_DEF_A | W_DEF_M | W_RHS), flux_needed = what & (W_JAC_A | W_DEF_A);
@@ -108,22 +108,30 @@ int run(int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coord
         const PatchHdr H = plan.hdr[pi];
         if (H.n_work > C::MAXW || H.n_elem > C::MAXE || H.n_node > C::MAXN || H.n_adj > C::MAXA) { err = "patch exceeds the kernel capacities"; return -1; }
         max_nodes = std::max<int64_t>(max_nodes, H.n_node); max_work = std::max<int64_t>(max_work, H.n_work); max_el = std::max<int64_t>(max_el, H.n_elem);
-        for (int tid = 0; tid < C::NT; tid++) fused_load<E>(A, S, H, tid);
+        const int par = pi & 1;
+        for (int tid = 0; tid < C::NT; tid++) fused_load<E>(A, S, H, par, tid);
+        S.adj = S.adjbuf[par]; S.nodes = S.nodebuf[par];
         if (flux_needed) {
             if (kp.stab == STAB_FIELDS) { for (int tid = 0; tid < C::NT; tid++) ok &= kp.time_dep ? fused_flux<E, STAB_FIELDS, true>(A, S, H, tid) : fused_flux<E, STAB_FIELDS, false>(A, S, H, tid); }
             else { for (int tid = 0; tid < C::NT; tid++) ok &= kp.time_dep ? fused_flux<E, STAB_NONE, true>(A, S, H, tid) : fused_flux<E, STAB_NONE, false>(A, S, H, tid); }
         }
-        if (want_jac) for (int tid = 0; tid < C::NT; tid++) fused_rows_zero<E>(S, H, tid);
         for (int nl = 0; nl < H.n_node; nl++) {
             if (node_seen[S.nodes[nl].node]++) { err = "a node belongs to two patches"; return -1; }
+            double* accn = S.acc + (size_t)(nl % (C::NWARP * C::NPW)) * (C::NV * S.cntp);      // the accumulator of the (warp, node slot) that gets this node
+            if (want_jac) for (int lg = 0; lg < C::PARTS * NSH; lg++) fused_rows_zero<E>(S, accn, lg);
             double fs[NSH];
-            for (int k = 0; k < NSH; k++) {
-                fs[k] = 0.0;
-                if (flux_needed) for (int j = 0; j < S.nodes[nl].adj_cnt; j++) fused_rows_accum_step<E>(A, S, nl, k, j, fs[k]);
-            }
-            fused_rows_mass<E>(A, S, nl);
+            for (int k = 0; k < NSH; k++) fs[k] = 0.0;
+            if (flux_needed)
+                for (int j = 0; j < S.nodes[nl].adj_cnt; j++)
+                    for (int h = 0; h < C::PARTS; h++) for (int k = 0; k < NSH; k++) { double dummy = 0.0; fused_rows_accum_step<E>(A, S, accn, nl, h, k, j, h == 0 ? fs[k] : dummy); }
+            fused_rows_mass<E>(A, S, accn, nl);
             if (want_def) for (int k = 0; k < NF; k++) fused_rows_defect<E>(A, S, nl, k, fs[k]);
-            if (want_jac) for (int k = 0; k < NSH; k++) fused_rows_out<E>(A, S, nl, k);
+            if (want_jac) {
+                // odd nodes exercise the register-prefetched J0 path of the device, even nodes the direct reads
+                FusedJ0<E> jr[32];
+                for (int lane = 0; lane < 32; lane++) fused_j0_prefetch<E>(A, S, nl, lane, 32, jr[lane]);
+                for (int lane = 0; lane < 32; lane++) fused_rows_out<E>(A, S, accn, nl, lane, 32, (nl & 1) ? &jr[lane] : nullptr);
+            }
         }
     }
     for (int64_t a = 0; a < n_node; a++) if (!node_seen[a]) { err = "a node belongs to no patch"; return -1; }

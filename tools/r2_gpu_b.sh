@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2, GPU call B: parity suite + bench + ncu of the fused kernel; tag = $1
+T=${1:-r2b}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/${T}_gputest.txt
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/${T}_bench_fused.json 2> gpurun_out/${T}_bench_fused.err
+timeout 600 python bench.py --cells 128 --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/${T}_bench_fused_n128.json 2>> gpurun_out/${T}_bench_fused.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fv1_fused -s 1 -c 1 -o gpurun_out/${T}_fused_n128 python bench.py --cells 128 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/${T}_ncu.log 2>&1
+echo done
