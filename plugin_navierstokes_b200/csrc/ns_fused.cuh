@@ -29,13 +29,14 @@ template <int E> struct FusedCfg {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, NINC = ET<E>::NINC, NSIDE = ET<E>::NSIDE;
     static constexpr int NT = 512;                                  // threads per CTA
     static constexpr int RS = LeanRec<E>::SZ;
-    static constexpr int RSTR = RS + 2;                             // record stride in shared memory: 16-byte accesses of adjacent slots hit distinct bank groups
+    static constexpr int RSTR = RS + 1;                             // odd record stride in shared memory: the lanes of a half-warp (adjacent slots, same field) hit distinct banks
+    static constexpr int GEO = 16;                                  // doubles per static SCVF geometry record: n[3] xip[3] JI[9] 1/L_d^2 (2-D: same slots, unused ones 0)
     static constexpr int NV = DIM + 2;                              // accumulated values per slot: D, C[DIM], PP
     static constexpr int DSTR = NSH * DIM + 1, NSTR = NSH + 1;      // odd strides of the per-ip tables
     static constexpr int NCOL = NSH * DIM + NSH * NF + NSH;         // doubles per element: corner coordinates, unknowns, SCV volumes
     static constexpr int CSTR = NCOL | 1;                           // element-major rows, odd stride: the lanes of a warp (same element, different
                                                                     // corners / different elements, same corner) hit different banks
-    static constexpr int PARTS = 4;                                 // rows phase: PARTS * NSH lanes work on one patch node
+    static constexpr int PARTS = 2;                                 // rows phase: PARTS * NSH lanes work on one patch node
     static constexpr int NPW = 32 / (PARTS * NSH);                  // patch nodes a warp assembles at a time
     static constexpr int NWARP = NT / 32;
     static constexpr int JREG = NF == 4 ? 6 : 4;                    // J0 words (double2 / double) per lane and node prefetched in registers
@@ -61,7 +62,7 @@ __host__ __device__ constexpr int fused_cnt_pad(int max_cnt) { return (max_cnt +
 // byte offsets of the shared-memory regions
 template <int E> struct FusedLayout {
     using C = FusedCfg<E>;
-    size_t o_rec, o_cols, o_acc, o_dnt, o_nt, o_lip, o_cor, o_side, o_iptab, o_inc, o_work, o_adj, o_nodes, o_efast, o_misc, total;
+    size_t o_rec, o_cols, o_acc, o_dnt, o_nt, o_lip, o_cor, o_side, o_iptab, o_inc, o_work, o_adj, o_nodes, o_efast, o_elid, o_misc, total;
     int cntp;
     __host__ __device__ explicit FusedLayout(int max_cnt)
     {
@@ -82,6 +83,7 @@ template <int E> struct FusedLayout {
         o_adj = take(2 * sizeof(PatchAdj) * C::MAXA);               // ping-pong: the next patch's tables arrive while the rows are written
         o_nodes = take(2 * sizeof(PatchNode) * C::MAXN);
         o_efast = take(C::MAXE);
+        o_elid = take(sizeof(int32_t) * C::MAXE);
         o_misc = take(64);
         total = o;
     }
@@ -91,7 +93,7 @@ template <int E> struct FusedLayout {
 template <int E> struct FusedSmem {
     double *rec, *xs, *us, *vs, *acc, *dnt, *Nt, *lip, *cortab;
     int *sidetab, *iptab, *inctab;
-    uint32_t* work; PatchAdj* adj; PatchNode* nodes; PatchAdj* adjbuf[2]; PatchNode* nodebuf[2]; uint8_t* efast; int* misc;
+    uint32_t* work; PatchAdj* adj0; PatchNode* nodes0; uint8_t* efast; int32_t* elem_id; int* misc;
     int cntp;
     NSB_HD FusedSmem(unsigned char* base, const FusedLayout<E>& L)
     {
@@ -109,13 +111,19 @@ template <int E> struct FusedSmem {
         iptab = reinterpret_cast<int*>(base + L.o_iptab);
         inctab = reinterpret_cast<int*>(base + L.o_inc);
         work = reinterpret_cast<uint32_t*>(base + L.o_work);
-        adjbuf[0] = reinterpret_cast<PatchAdj*>(base + L.o_adj); adjbuf[1] = adjbuf[0] + C::MAXA;
-        nodebuf[0] = reinterpret_cast<PatchNode*>(base + L.o_nodes); nodebuf[1] = nodebuf[0] + C::MAXN;
-        adj = adjbuf[0]; nodes = nodebuf[0];
+        adj0 = reinterpret_cast<PatchAdj*>(base + L.o_adj);           // two buffers each (ping-pong by patch parity): see FusedTab
+        nodes0 = reinterpret_cast<PatchNode*>(base + L.o_nodes);
+        elem_id = reinterpret_cast<int32_t*>(base + L.o_elid);
         efast = base + L.o_efast;
         misc = reinterpret_cast<int*>(base + L.o_misc);
         cntp = L.cntp;
     }
+};
+
+// the adjacency / node tables of the current patch (buffer `par` of the ping-pong pair)
+template <int E> struct FusedTab {
+    const PatchAdj* adj; const PatchNode* nodes;
+    NSB_HD FusedTab(const FusedSmem<E>& S, int par) : adj(S.adj0 + par * FusedCfg<E>::MAXA), nodes(S.nodes0 + par * FusedCfg<E>::MAXN) {}
 };
 
 // global-memory arguments
@@ -127,6 +135,7 @@ struct FusedArgs {
     const double* u; const double* s0; const double* s1; const double* j0;
     double beta; double* val; double* def;
     int* errflag;
+    const double* geo;             // static SCVF geometry records in work-item order ([scvf_evals][16]) or null: geometry on the fly
     const uint8_t* elem_fast;      // hex: 1 = element is star-shaped w.r.t. its ips -> predicted-side ray search allowed; null = never
     int max_adj;                   // longest adjacency list of a node
 };
@@ -401,8 +410,9 @@ NSB_HD bool fused_upwind(const FusedSmem<E>& S, int el, int ip, int type, bool f
 // flux phase: one SCVF (local element el, ip) -> lean record `fr` (shared memory). Same evaluation order as
 // fv1_flux_kernel<LEAN> (ns_owner.cuh). nd = global node ids of the element's corners (time-dependent closure only).
 // ------------------------------------------------------------------------------------------------
-template <int E, int STAB, bool TD>
-NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip, const int32_t* __restrict__ nd, double* __restrict__ fr)
+template <int E, int STAB, bool TD, bool GEOT>
+NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip, const int32_t* __restrict__ nd, const double* __restrict__ geo,
+                       double* __restrict__ fr)
 {
     using C = FusedCfg<E>;
     using LR = LeanRec<E>;
@@ -412,31 +422,44 @@ NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip
     const double nurho = p.visc * p.rho;
     const bool want_def = p.what & W_DEF_A, want_jac = p.what & W_JAC_A;
     bool ok = true;
-    double cen[DIM];
-#pragma unroll
-    for (int d = 0; d < DIM; d++) {
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < NSH; k++) s += NSB_FCOL(S.xs, k * DIM + d);
-        cen[d] = s * (1.0 / NSH);
-    }
-    // COR diffusion length: element-wide statistics of the SCVF normals (diffusion_length.h:139-172)
-    double cmn = 0.0, cav = 0.0, cmd = 0.0;
-    if (STAB != STAB_NONE && p.diff_len == DIFF_COR) {
-        cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
-        for (int i = 0; i < NIP; i++) {
-            double nn_[DIM], xx_[DIM], dsi;
-            fused_ip_geometry<E>(S, el, i, cen, nn_, xx_, dsi, false, nullptr);
-            const double q = dotv<DIM>(nn_, nn_);
-            if (q < cmn) cmn = q;
-            cav += q;
-            if (DIM == 3 && dsi < cmd) cmd = dsi;
-        }
-        cav /= NIP;
-    }
     const int from = S.iptab[ip * 12], to = S.iptab[ip * 12 + 1];
-    double n[DIM], xip[DIM], ds = 0.0, JI[DIM][DIM];
-    fused_ip_geometry<E>(S, el, ip, cen, n, xip, ds, true, JI);
+    double n[DIM], xip[DIM], JI[DIM][DIM], dlinv = 0.0;
+    if constexpr (GEOT) {
+        // static SCVF geometry record (fused_geom_record, built once per mesh): n | xip | J^-T | 1/L_d^2
+#pragma unroll
+        for (int d = 0; d < DIM; d++) { n[d] = geo[d]; xip[d] = geo[3 + d]; }
+#pragma unroll
+        for (int d = 0; d < DIM; d++)
+#pragma unroll
+            for (int i = 0; i < DIM; i++) JI[d][i] = geo[6 + d * DIM + i];
+        dlinv = geo[15];
+    } else {
+        double cen[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < NSH; k++) s += NSB_FCOL(S.xs, k * DIM + d);
+            cen[d] = s * (1.0 / NSH);
+        }
+        // COR diffusion length: element-wide statistics of the SCVF normals (diffusion_length.h:139-172)
+        double cmn = 0.0, cav = 0.0, cmd = 0.0;
+        if (STAB != STAB_NONE && p.diff_len == DIFF_COR) {
+            cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
+            for (int i = 0; i < NIP; i++) {
+                double nn_[DIM], xx_[DIM], dsi;
+                fused_ip_geometry<E>(S, el, i, cen, nn_, xx_, dsi, false, nullptr);
+                const double q = dotv<DIM>(nn_, nn_);
+                if (q < cmn) cmn = q;
+                cav += q;
+                if (DIM == 3 && dsi < cmd) cmd = dsi;
+            }
+            cav /= NIP;
+        }
+        double ds = 0.0;
+        fused_ip_geometry<E>(S, el, ip, cen, n, xip, ds, true, JI);
+        if (STAB != STAB_NONE) dlinv = diff_len_sq_inv<DIM>(p.diff_len, dotv<DIM>(n, n), NSB_FCOL(S.vs, from), NSB_FCOL(S.vs, to), ds, cmn, cav, cmd);
+    }
     const double* N = S.Nt + ip * C::NSTR;
     // ---- StdVel from the `u` argument (:282-293) ----
     double std[DIM];
@@ -458,8 +481,7 @@ NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip
     // ---- diagonal of the ip system and numerators sb_k = qa N_k + qb up_k (stabilization.cpp:166-236) ----
     double inv = 0.0, qa = 0.0, qb = 0.0;
     if (STAB != STAB_NONE) {
-        const double nn = dotv<DIM>(n, n);
-        qa = p.visc * diff_len_sq_inv<DIM>(p.diff_len, nn, NSB_FCOL(S.vs, from), NSB_FCOL(S.vs, to), ds, cmn, cav, cmd);
+        qa = p.visc * dlinv;
         if (!p.stokes) qb = sqrt(dotv<DIM>(std, std)) / uplen;
         double diag = qa;
         if (td) diag += 1.0 / p.dt;
@@ -683,8 +705,8 @@ template <int E> NSB_HD void fused_load(const FusedArgs& A, const FusedSmem<E>& 
     using C = FusedCfg<E>;
     constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF;
     for (int i = tid; i < H.n_work; i += C::NT) fused_copy4(S.work + i, A.work + H.work0 + i);
-    for (int i = tid; i < H.n_adj; i += C::NT) fused_copy16(S.adjbuf[par] + i, A.adj + H.adj0 + i);
-    for (int i = tid; i < H.n_node; i += C::NT) fused_copy16(S.nodebuf[par] + i, A.nodes + H.node0 + i);
+    for (int i = tid; i < H.n_adj; i += C::NT) fused_copy16(S.adj0 + par * C::MAXA + i, A.adj + H.adj0 + i);
+    for (int i = tid; i < H.n_node; i += C::NT) fused_copy16(S.nodes0 + par * C::MAXN + i, A.nodes + H.node0 + i);
     for (int i = tid; i < H.n_elem * NSH; i += C::NT) {
         const int el = i / NSH, k = i - el * NSH;
         const int64_t e = A.elems[H.elem0 + el];
@@ -694,27 +716,28 @@ template <int E> NSB_HD void fused_load(const FusedArgs& A, const FusedSmem<E>& 
 #pragma unroll
         for (int d = 0; d < DIM; d++) fused_copy8(&NSB_FCOL(S.xs, k * DIM + d), A.coords + ndk * DIM + d);
         fused_copy8(&NSB_FCOL(S.vs, k), A.scvvol + e * NSH + k);
-        if (k == 0) S.efast[el] = A.elem_fast ? A.elem_fast[e] : (uint8_t)0;
+        if (k == 0) { S.efast[el] = A.elem_fast ? A.elem_fast[e] : (uint8_t)0; S.elem_id[el] = (int32_t)e; }
     }
 }
 
 // flux: returns false if a ray search failed (the reference throws, upwind.cpp:354)
-template <int E, int STAB, bool TD> NSB_HD bool fused_flux(const FusedArgs& A, const FusedSmem<E>& S, const PatchHdr& H, int tid)
+template <int E, int STAB, bool TD, bool GEOT> NSB_HD bool fused_flux(const FusedArgs& A, const FusedSmem<E>& S, const PatchHdr& H, int tid)
 {
     using C = FusedCfg<E>;
     bool ok = true;
     for (int w = tid; w < H.n_work; w += C::NT) {
         const uint32_t wi = S.work[w];
         const int el = wi & 255, ip = (wi >> 8) & 15, slot = wi >> 12;
-        ok &= fused_scvf<E, STAB, TD>(A, S, el, ip, A.pconn + (int64_t)(H.elem0 + el) * C::NSH, S.rec + slot * C::RSTR);
+        ok &= fused_scvf<E, STAB, TD, GEOT>(A, S, el, ip, A.pconn + (int64_t)(H.elem0 + el) * C::NSH,
+                                            GEOT ? A.geo + (int64_t)(H.work0 + w) * C::GEO : nullptr, S.rec + slot * C::RSTR);
     }
     return ok;
 }
 
 // rows phase. PARTS * NSH lanes work on one patch node: lane (h, k) = (part h, corner k). For every adjacent element (in the
 // order of the global adjacency list) the lane sums the NINC incident SCVF records of its corner and adds its part
-//   h = 0: the convective diagonal D (+ the defect fluxes, k < NF)      h = 1: the pressure column PP of the continuity row
-//   h = 2: the velocity columns C[0 .. DIM-2] of the continuity row     h = 3: C[DIM-1]
+//   h = 0: the convective diagonal D, the pressure column PP of the continuity row (+ the defect fluxes, k < NF)
+//   h = 1: the velocity columns C[DIM] of the continuity row
 // into the per-slot accumulators of the node (`accn`, private to the node's lanes). The corners of one element are distinct
 // nodes and the parts own different accumulator arrays, so a step is conflict-free; steps are separated by __syncwarp.
 // step 1: clear the node's accumulators (`lg` = lane index within the node's PARTS * NSH lanes)
@@ -724,65 +747,72 @@ template <int E> NSB_HD void fused_rows_zero(const FusedSmem<E>& S, double* accn
     for (int i = lg; i < C::NV * S.cntp; i += C::PARTS * C::NSH) accn[i] = 0.0;
 }
 
-// step 2: adjacency entry j of node nl
-template <int E> NSB_HD void fused_rows_accum_step(const FusedArgs& A, const FusedSmem<E>& S, double* accn, int nl, int h, int k, int j, double& fs)
+// step 2: adjacency entry j of node nl. The 16-byte entry is read once (one LDS.128): record slots, local corner + the
+// orientation bits of the NINC incident SCVFs (bit 4 + t set: the node is the `to` end), CSR slots of the element's corners.
+template <int E> NSB_HD void fused_rows_accum_step(const FusedArgs& A, const FusedSmem<E>& S, const FusedTab<E>& T, double* accn, int nl, int h, int k, int j, double& fs)
 {
     using C = FusedCfg<E>;
     using LR = LeanRec<E>;
     constexpr int DIM = C::DIM, NF = C::NF, NINC = C::NINC;
     const KParams& p = A.p;
     const bool jac_a = p.what & W_JAC_A, def_a = p.what & W_DEF_A;
-    const PatchNode& Nd = S.nodes[nl];
+    const PatchNode& Nd = T.nodes[nl];
     if (j >= Nd.adj_cnt) return;
-    const PatchAdj& a = S.adj[Nd.adj_off + j];
-    const int slot = a.emap[k];
-    if (h < 2) {
-        double V = 0.0;
-        const int off = h == 0 ? LR::O_DK : LR::O_PK;
+    struct U4 { uint32_t x, y, z, w; };
+    const U4 a = *reinterpret_cast<const U4*>(T.adj + Nd.adj_off + j);
+    const uint32_t s01 = a.x, s2la = a.y;                        // slot[0] | slot[1] << 16,  slot[2] | la << 16 | self << 24
+    const uint32_t lab = s2la >> 16;
+    const uint32_t em = k < 4 ? a.z : a.w;                       // emap[0..3], emap[4..7]
+    const int slot = (em >> (8 * (k & 3))) & 255;
+    const int rs[3] = {(int)(s01 & 0xffff), (int)(s01 >> 16), (int)(s2la & 0xffff)};
+    if (h == 0) {
+        double D = 0.0, PP = 0.0;
 #pragma unroll
         for (int t = 0; t < NINC; t++) {
-            const double* rc = S.rec + a.slot[t] * C::RSTR;
-            const bool neg = S.inctab[a.la * NINC + t] & 256;
-            if (h == 0 && def_a && k < NF) { const double f = rc[LR::O_F + k]; fs += neg ? -f : f; }
-            if (jac_a) V += (neg ? -p.scale_a : p.scale_a) * rc[off + k];
+            const double* rc = S.rec + rs[t] * C::RSTR;
+            const bool neg = (lab >> (4 + t)) & 1;
+            if (def_a && k < NF) { const double f = rc[LR::O_F + k]; fs += neg ? -f : f; }
+            if (jac_a) {
+                const double sg = neg ? -p.scale_a : p.scale_a;
+                D += sg * rc[LR::O_DK + k];
+                PP += sg * rc[LR::O_PK + k];
+            }
         }
-        if (jac_a) accn[(h == 0 ? 0 : 1 + DIM) * S.cntp + slot] += V;
+        if (jac_a) { accn[slot] += D; accn[(1 + DIM) * S.cntp + slot] += PP; }
     } else if (jac_a) {
-        constexpr int ND0 = DIM - 1;                              // h = 2: components 0 .. DIM-2, h = 3: component DIM-1
-        const int d0 = h == 2 ? 0 : ND0, d1 = h == 2 ? ND0 : DIM;
         double Cn[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; d++) Cn[d] = 0.0;
 #pragma unroll
         for (int t = 0; t < NINC; t++) {
-            const double* rc = S.rec + a.slot[t] * C::RSTR;
-            const bool neg = S.inctab[a.la * NINC + t] & 256;
+            const double* rc = S.rec + rs[t] * C::RSTR;
+            const bool neg = (lab >> (4 + t)) & 1;
             const double w = (neg ? -p.scale_a : p.scale_a) * rc[LR::O_CK + k];
 #pragma unroll
-            for (int d = 0; d < DIM; d++) if (d >= d0 && d < d1) Cn[d] += w * rc[LR::O_N + d];
+            for (int d = 0; d < DIM; d++) Cn[d] += w * rc[LR::O_N + d];
         }
 #pragma unroll
-        for (int d = 0; d < DIM; d++) if (d >= d0 && d < d1) accn[(1 + d) * S.cntp + slot] += Cn[d];
+        for (int d = 0; d < DIM; d++) accn[(1 + d) * S.cntp + slot] += Cn[d];
     }
 }
 
 // step 3 (one lane of the node): lumped mass on the diagonal (add_jac_M_elem :781-808)
-template <int E> NSB_HD void fused_rows_mass(const FusedArgs& A, const FusedSmem<E>& S, double* accn, int nl)
+template <int E> NSB_HD void fused_rows_mass(const FusedArgs& A, const FusedTab<E>& T, double* accn, int nl)
 {
     const KParams& p = A.p;
-    const PatchNode& Nd = S.nodes[nl];
+    const PatchNode& Nd = T.nodes[nl];
     if (!(p.what & W_JAC_M) || Nd.adj_cnt == 0) return;
-    const int self = S.adj[Nd.adj_off].self;
+    const int self = T.adj[Nd.adj_off].self;
     accn[self] += p.scale_m * A.nodevol[Nd.node] * p.rho;
 }
 
 // step 4: defect entry (node, component k < NF)   (add_def_A_elem / add_def_M_elem / add_rhs_elem)
-template <int E> NSB_HD void fused_rows_defect(const FusedArgs& A, const FusedSmem<E>& S, int nl, int k, double fs)
+template <int E> NSB_HD void fused_rows_defect(const FusedArgs& A, const FusedTab<E>& T, int nl, int k, double fs)
 {
     using C = FusedCfg<E>;
     constexpr int DIM = C::DIM, NF = C::NF;
     const KParams& p = A.p;
-    const int64_t a = S.nodes[nl].node;
+    const int64_t a = T.nodes[nl].node;
     double d = (p.what & W_DEF_A) ? fs : 0.0;
     const bool need_vol = ((p.what & W_RHS) && p.has_source) || (p.what & W_DEF_M);
     const double vol = (need_vol && k < DIM) ? A.nodevol[a] : 0.0;
@@ -799,11 +829,11 @@ template <int E> NSB_HD void fused_rows_defect(const FusedArgs& A, const FusedSm
 // (fused_j0_prefetch, issued before the accumulation so that their latency is hidden), jpre == nullptr reads them here.
 template <int E> struct FusedJ0 { double v[FusedCfg<E>::JREG][FusedCfg<E>::NF == 4 ? 2 : 1]; };
 
-template <int E> NSB_HD void fused_j0_prefetch(const FusedArgs& A, const FusedSmem<E>& S, int nl, int lane, int nlanes, FusedJ0<E>& J)
+template <int E> NSB_HD void fused_j0_prefetch(const FusedArgs& A, const FusedTab<E>& T, int nl, int lane, int nlanes, FusedJ0<E>& J)
 {
     using C = FusedCfg<E>;
     constexpr int DIM = C::DIM, NF = C::NF, W = NF == 4 ? 2 : 1;
-    const PatchNode& Nd = S.nodes[nl];
+    const PatchNode& Nd = T.nodes[nl];
     const int nw = Nd.cnt * (DIM * NF) / W;                      // J0 words of the node
     const double* j0g = A.j0 + Nd.b0 * (DIM * NF);
 #pragma unroll
@@ -820,13 +850,13 @@ template <int E> NSB_HD void fused_j0_prefetch(const FusedArgs& A, const FusedSm
     }
 }
 
-template <int E> NSB_HD void fused_rows_out(const FusedArgs& A, const FusedSmem<E>& S, const double* acc, int nl, int lane, int nlanes, const FusedJ0<E>* jpre)
+template <int E> NSB_HD void fused_rows_out(const FusedArgs& A, const FusedSmem<E>& S, const FusedTab<E>& T, const double* acc, int nl, int lane, int nlanes, const FusedJ0<E>* jpre)
 {
     using C = FusedCfg<E>;
     constexpr int DIM = C::DIM, NF = C::NF;
     const KParams& p = A.p;
     const bool jac_a = p.what & W_JAC_A;
-    const PatchNode& Nd = S.nodes[nl];
+    const PatchNode& Nd = T.nodes[nl];
     const int cnt = Nd.cnt, cntp = S.cntp;
     const double s_visc = p.visc * p.rho * p.scale_a, s_pres = p.scale_a;
     double* out = A.val + Nd.b0 * (NF * NF);
@@ -894,6 +924,66 @@ template <int E> NSB_HD void fused_rows_out(const FusedArgs& A, const FusedSmem<
     }
 }
 
+// static SCVF geometry record of (element corners x [NSH][DIM], SCV volumes, ip): n | xip | J^-T | 1 / L_d^2 for the given
+// diffusion-length type (fv1/diffusion_length.h:47-198). Same formulas as fused_ip_geometry, reference tables read directly.
+template <int E> NSB_DEV void fused_geom_record(const double* x, const double* vol, int ip, int diff_len, double* r)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH, NIP = C::NIP;
+    double cen[DIM];
+    for (int d = 0; d < DIM; d++) { double s = 0; for (int k = 0; k < NSH; k++) s += x[k * DIM + d]; cen[d] = s * (1.0 / NSH); }
+    auto scvf = [&](int q, double* n, double* xip, double& ds) {
+        const int f = tab::EDGE[E][q][0], t = tab::EDGE[E][q][1];
+        double c0[DIM];
+        for (int d = 0; d < DIM; d++) c0[d] = 0.5 * (x[f * DIM + d] + x[t * DIM + d]);
+        if constexpr (DIM == 2) {
+            n[0] = cen[1] - c0[1]; n[1] = -(cen[0] - c0[0]);
+            xip[0] = 0.5 * (c0[0] + cen[0]); xip[1] = 0.5 * (c0[1] + cen[1]);
+            ds = 0.0;
+        } else {
+            constexpr int NFC = (E == E_TET) ? 3 : 4;
+            const int fa = tab::SCVF_FA[E][q], fb = tab::SCVF_FB[E][q];
+            double c1[3] = {0, 0, 0}, c3[3] = {0, 0, 0};
+            for (int i = 0; i < NFC; i++) {
+                const int ka = tab::SIDE[E][fa][i], kb = tab::SIDE[E][fb][i];
+                for (int d = 0; d < 3; d++) { c1[d] += x[ka * 3 + d]; c3[d] += x[kb * 3 + d]; }
+            }
+            double a[3], b[3];
+            for (int d = 0; d < 3; d++) {
+                c1[d] *= (1.0 / NFC); c3[d] *= (1.0 / NFC);
+                a[d] = cen[d] - c0[d]; b[d] = c3[d] - c1[d];
+                xip[d] = 0.25 * (c0[d] + c1[d] + cen[d] + c3[d]);
+            }
+            cross3(n, a, b);
+            for (int d = 0; d < 3; d++) n[d] *= 0.5;
+            ds = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+        }
+    };
+    double cmn = 0.0, cav = 0.0, cmd = 0.0;
+    if (diff_len == DIFF_COR) {
+        cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
+        for (int q = 0; q < NIP; q++) {
+            double nn_[DIM], xx_[DIM], dsi;
+            scvf(q, nn_, xx_, dsi);
+            const double v = dotv<DIM>(nn_, nn_);
+            if (v < cmn) cmn = v;
+            cav += v;
+            if (DIM == 3 && dsi < cmd) cmd = dsi;
+        }
+        cav /= NIP;
+    }
+    double n[DIM], xip[DIM], ds;
+    scvf(ip, n, xip, ds);
+    double JT[DIM][DIM], JI[DIM][DIM];
+    for (int i = 0; i < DIM; i++) for (int j = 0; j < DIM; j++) JT[i][j] = 0.0;
+    for (int k = 0; k < NSH; k++) for (int j = 0; j < DIM; j++) for (int i = 0; i < DIM; i++) JT[i][j] += tab::C_DNIP[E][ip][k][i] * x[k * DIM + j];
+    inv_mat<DIM>(JT, JI);
+    for (int q = 0; q < C::GEO; q++) r[q] = 0.0;
+    for (int d = 0; d < DIM; d++) { r[d] = n[d]; r[3 + d] = xip[d]; }
+    for (int d = 0; d < DIM; d++) for (int i = 0; i < DIM; i++) r[6 + d * DIM + i] = JI[d][i];
+    r[15] = diff_len_sq_inv<DIM>(diff_len, dotv<DIM>(n, n), vol[tab::EDGE[E][ip][0]], vol[tab::EDGE[E][ip][1]], ds, cmn, cav, cmd);
+}
+
 // true when every boundary triangle of the element (sides in reference order, quadrilaterals as (p0,p1,p2), (p0,p2,p3)) is
 // seen from its inner side by every SCVF ip: the triangulated boundary is then star-shaped w.r.t. each ip, a ray from the
 // ip cuts exactly one triangle, and the predicted-side ray search of fused_ray_cut returns what the ordered search returns.
@@ -928,14 +1018,14 @@ template <int E> NSB_DEV bool fused_star_shaped(const double* x)
 // ------------------------------------------------------------------------------------------------
 // the kernel: persistent CTAs, patches handed out by an atomic ticket
 // ------------------------------------------------------------------------------------------------
-template <int E, int STAB, bool TD>
+template <int E, int STAB, bool TD, bool GEOT>
 __global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const FusedArgs A, int max_cnt)
 {
     using C = FusedCfg<E>;
     constexpr int NSH = C::NSH, NF = C::NF, NPW = C::NPW, NWARP = C::NWARP, LPN = C::PARTS * NSH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FusedLayout<E> L(max_cnt);
-    FusedSmem<E> S(smem_raw, L);
+    const FusedSmem<E> S(smem_raw, L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     fused_stage_tables<E>(S, tid, C::NT);
     const int what = A.p.what;
@@ -960,20 +1050,24 @@ __global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const Fus
     PatchHdr H = load_hdr(pi);
     fused_load<E>(A, S, H, par, tid);
     for (;;) {
-        S.adj = S.adjbuf[par]; S.nodes = S.nodebuf[par];
+        const FusedTab<E> T(S, par);
         fused_copy_wait();
         __syncthreads();                                         // tables + element rows of this patch are in shared memory
         const int pn = pi + (int)gridDim.x;
         PatchHdr Hn = H;
         if (pn < A.n_patch) Hn = load_hdr(pn);                   // consumed after the flux phase
-        if (flux_needed && !fused_flux<E, STAB, TD>(A, S, H, tid)) atomicExch(A.errflag, 1);
+        if (flux_needed && !fused_flux<E, STAB, TD, GEOT>(A, S, H, tid)) atomicExch(A.errflag, 1);
         __syncthreads();                                         // records complete; element rows, work list and flags are dead
-        if (pn < A.n_patch) fused_load<E>(A, S, Hn, par ^ 1, tid);
+        if (pn < A.n_patch) {
+            fused_load<E>(A, S, Hn, par ^ 1, tid);
+            if (GEOT && flux_needed && tid < Hn.n_work)          // the next patch's geometry records: one 128-byte line per SCVF -> L2
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.geo + (int64_t)(Hn.work0 + tid) * C::GEO));
+        }
         for (int nl0 = warp * NPW; nl0 < H.n_node; nl0 += NWARP * NPW) {
             FusedJ0<E> j0r[NPW];                                 // J0 rows of the warp's nodes -> registers (in flight during the accumulation)
             if (jac_a) {
 #pragma unroll
-                for (int q = 0; q < NPW; q++) if (nl0 + q < H.n_node) fused_j0_prefetch<E>(A, S, nl0 + q, lane, 32, j0r[q]);
+                for (int q = 0; q < NPW; q++) if (nl0 + q < H.n_node) fused_j0_prefetch<E>(A, T, nl0 + q, lane, 32, j0r[q]);
             }
             const int nl = nl0 + jj;
             const bool on = lane_on && nl < H.n_node;
@@ -981,25 +1075,52 @@ __global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const Fus
             if (on && want_jac) fused_rows_zero<E>(S, accn, lg);
             __syncwarp();
             if (flux_needed) {
-                const int mycnt = on ? (int)S.nodes[nl].adj_cnt : 0;
+                const int mycnt = on ? (int)T.nodes[nl].adj_cnt : 0;
                 const int mx = __reduce_max_sync(0xffffffffu, mycnt);
                 for (int j = 0; j < mx; j++) {
-                    if (on) fused_rows_accum_step<E>(A, S, accn, nl, h, k, j, fs);
+                    if (on) fused_rows_accum_step<E>(A, S, T, accn, nl, h, k, j, fs);
                     __syncwarp();
                 }
             }
-            if (on && lg == 0) fused_rows_mass<E>(A, S, accn, nl);
+            if (on && lg == 0) fused_rows_mass<E>(A, T, accn, nl);
             __syncwarp();
-            if (on && want_def && h == 0 && k < NF) fused_rows_defect<E>(A, S, nl, k, fs);
+            if (on && want_def && h == 0 && k < NF) fused_rows_defect<E>(A, T, nl, k, fs);
             if (want_jac) {
 #pragma unroll
                 for (int q = 0; q < NPW; q++)
-                    if (nl0 + q < H.n_node) fused_rows_out<E>(A, S, accw + q * (C::NV * S.cntp), nl0 + q, lane, 32, jac_a ? &j0r[q] : nullptr);
+                    if (nl0 + q < H.n_node) fused_rows_out<E>(A, S, T, accw + q * (C::NV * S.cntp), nl0 + q, lane, 32, jac_a ? &j0r[q] : nullptr);
             }
             __syncwarp();                                        // the accumulators are reused by the warp's next nodes
         }
         if (pn >= A.n_patch) break;
         pi = pn; H = Hn; par ^= 1;
+    }
+}
+
+// once per mesh (and per diffusion-length type): static SCVF geometry records in work-item order. One CTA per patch.
+template <int E>
+__global__ void __launch_bounds__(FusedCfg<E>::NT) fused_geom_kernel(const FusedArgs A, int diff_len, double* __restrict__ geo)
+{
+    using C = FusedCfg<E>;
+    constexpr int DIM = C::DIM, NSH = C::NSH;
+    const PatchHdr H = A.hdr[blockIdx.x];
+    for (int w = threadIdx.x; w < H.n_work; w += blockDim.x) {
+        const uint32_t wi = A.work[H.work0 + w];
+        const int el = wi & 255, ip = (wi >> 8) & 15;
+        const int64_t e = A.elems[H.elem0 + el];
+        double x[NSH * DIM], vol[NSH];
+#pragma unroll
+        for (int k = 0; k < NSH; k++) {
+            const int64_t nd = A.pconn[(int64_t)(H.elem0 + el) * NSH + k];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) x[k * DIM + d] = A.coords[nd * DIM + d];
+            vol[k] = A.scvvol[e * NSH + k];
+        }
+        double r[C::GEO];
+        fused_geom_record<E>(x, vol, ip, diff_len, r);
+        double2* o = reinterpret_cast<double2*>(geo + (int64_t)(H.work0 + w) * C::GEO);
+#pragma unroll
+        for (int q = 0; q < C::GEO / 2; q++) o[q] = make_double2(r[2 * q], r[2 * q + 1]);
     }
 }
 

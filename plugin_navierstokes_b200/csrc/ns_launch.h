@@ -32,6 +32,7 @@ struct PatchCaps;
     PatchCaps fused_caps_##E();                                                                       \
     size_t fused_smem_bytes_##E(int max_cnt);                                                         \
     cudaError_t launch_fused_##E(const FusedArgs& A, int max_cnt, cudaStream_t st, int sm_count, unsigned long long* work_counter); \
+    cudaError_t launch_fused_geom_##E(const FusedArgs& A, int diff_len, double* geo, cudaStream_t st);                                \
     cudaError_t launch_ray_safety_##E(int64_t n_elem, const int32_t* conn, const double* coords, uint8_t* elem_fast, cudaStream_t st);
 NSB_DECLF(0) NSB_DECLF(1) NSB_DECLF(2) NSB_DECLF(3)
 #undef NSB_DECLF

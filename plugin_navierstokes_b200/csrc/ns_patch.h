@@ -28,7 +28,7 @@ namespace nsb {
 
 struct PatchHdr { int32_t node0, n_node, elem0, n_elem, work0, n_work, adj0, n_adj; };           // 32 B
 struct PatchNode { int64_t b0; int32_t node; uint16_t adj_off; uint8_t adj_cnt, cnt; };          // 16 B
-struct PatchAdj { uint16_t slot[3]; uint8_t la, self; uint8_t emap[8]; };                        // 16 B
+struct PatchAdj { uint16_t slot[3]; uint8_t la, self; uint8_t emap[8]; };                        // 16 B; la: bits 0-2 local corner, bit 4+t: SCVF t enters the node (sign -1)
 static_assert(sizeof(PatchHdr) == 32 && sizeof(PatchNode) == 16 && sizeof(PatchAdj) == 16, "table layouts are read as 16-byte words on the device");
 
 struct PatchCaps {
@@ -208,6 +208,7 @@ inline bool build_patch_plan(int elem, int64_t n_elem, int64_t n_node, const int
                     std::memset(&A, 0, sizeof A);
                     for (int t = 0; t < ninc; t++) A.slot[t] = slot_of[el * nip + inc[la][t]];
                     A.la = (uint8_t)la;
+                    for (int t = 0; t < ninc; t++) if (T.edge[inc[la][t]][1] == la) A.la |= (uint8_t)(16 << t);   // the node is the `to` end of SCVF t
                     for (int k = 0; k < nsh; k++) A.emap[k] = emap[((int64_t)e * nsh + la) * nsh + k];
                     A.self = A.emap[la];
                     P.adj.push_back(A);

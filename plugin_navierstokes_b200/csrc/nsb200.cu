@@ -86,6 +86,7 @@ struct nsb_ctx {
     std::string fused_note;
     PatchHdr* d_phdr = nullptr; PatchNode* d_pnodes = nullptr; int32_t* d_pelems = nullptr; int32_t* d_pconn = nullptr;
     uint32_t* d_pwork = nullptr; PatchAdj* d_padj = nullptr; double* d_nodevol = nullptr; uint8_t* d_elem_fast = nullptr;
+    double* d_geo = nullptr; int geo_diff_len = -1;   // static SCVF geometry records of the fused kernel (per diffusion-length type)
     int32_t n_patch = 0; int max_adj = 0;
     int64_t scvf_evals = 0, patch_table_bytes = 0;
 };
@@ -158,7 +159,8 @@ static void free_mesh(nsb_ctx* c)
     cudaFree(c->d_u); cudaFree(c->d_s0); cudaFree(c->d_s1); cudaFree(c->d_val); cudaFree(c->d_def);
     cudaFree(c->d_jloc); cudaFree(c->d_dloc); cudaFree(c->d_j0);
     cudaFree(c->d_phdr); cudaFree(c->d_pnodes); cudaFree(c->d_pelems); cudaFree(c->d_pconn); cudaFree(c->d_pwork); cudaFree(c->d_padj);
-    cudaFree(c->d_nodevol); cudaFree(c->d_elem_fast);
+    cudaFree(c->d_nodevol); cudaFree(c->d_elem_fast); cudaFree(c->d_geo);
+    c->d_geo = nullptr; c->geo_diff_len = -1;
     c->d_phdr = nullptr; c->d_pnodes = nullptr; c->d_pelems = c->d_pconn = nullptr; c->d_pwork = nullptr; c->d_padj = nullptr;
     c->d_nodevol = nullptr; c->d_elem_fast = nullptr; c->fused_ok = false; c->n_patch = 0; c->scvf_evals = 0; c->patch_table_bytes = 0;
     c->dev_bytes = 0;
@@ -570,6 +572,22 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
             A.coords = c->d_coords; A.scvvol = c->d_scvvol; A.nodevol = c->d_nodevol;
             A.u = u; A.s0 = s0; A.s1 = s1; A.j0 = c->d_j0; A.beta = beta; A.val = val; A.def = def;
             A.errflag = c->d_err; A.elem_fast = c->d_elem_fast; A.max_adj = c->max_adj;
+            // static SCVF geometry records (normal, ip, J^-T, 1/L_d^2) in work-item order: 128 B per SCVF evaluation, built once
+            // per mesh and diffusion-length type; NSB_GEOTAB=0 recomputes the geometry in every pass instead
+            static const bool geotab = !(getenv("NSB_GEOTAB") && atoi(getenv("NSB_GEOTAB")) == 0);
+            if (geotab && (k.what & (W_JAC_A | W_DEF_A))) {
+                if (!c->d_geo) CUDA_TRY(c, dev_malloc(c, &c->d_geo, (size_t)c->scvf_evals * 16 * sizeof(double)));
+                if (c->geo_diff_len != k.diff_len) {
+                    switch (c->elem) { case 0: e = launch_fused_geom_0(A, k.diff_len, c->d_geo, c->stream); break;
+                                       case 1: e = launch_fused_geom_1(A, k.diff_len, c->d_geo, c->stream); break;
+                                       case 2: e = launch_fused_geom_2(A, k.diff_len, c->d_geo, c->stream); break;
+                                       default: e = launch_fused_geom_3(A, k.diff_len, c->d_geo, c->stream); }
+                    c->launches++;
+                    CUDA_TRY(c, e);
+                    c->geo_diff_len = k.diff_len;
+                }
+                A.geo = c->d_geo;
+            }
             switch (c->elem) { case 0: e = launch_fused_0(A, c->max_cnt, c->stream, c->sm_count, c->d_counter); break;
                                case 1: e = launch_fused_1(A, c->max_cnt, c->stream, c->sm_count, c->d_counter); break;
                                case 2: e = launch_fused_2(A, c->max_cnt, c->stream, c->sm_count, c->d_counter); break;

@@ -19,7 +19,7 @@ namespace {
 
 template <int E>
 int run(int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coords, const KParams& kp, const double* u,
-        const double* s0, const double* s1, double beta, double* values, double* defect, int ray_fast, int64_t* stats, std::string& err)
+        const double* s0, const double* s1, double beta, double* values, double* defect, int ray_fast, int use_geo, int64_t* stats, std::string& err)
 {
     using C = FusedCfg<E>;
     constexpr int DIM = C::DIM, NSH = C::NSH, NF = C::NF, NINC = C::NINC, NIP = C::NIP;
@@ -31,7 +31,10 @@ int run(int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coord
     // topology tables of the patch builder == reference tables of the kernels
     for (int ip = 0; ip < NIP; ip++) for (int j = 0; j < 2; j++)
         if (patch_detail::topo(E).edge[ip][j] != tab::EDGE[E][ip][j]) { err = "ns_patch.h edge table differs from ref_tables.cuh"; return -1; }
-    for (int la = 0; la < NSH; la++) { int c = 0; for (int ip = 0; ip < NIP; ip++) if (tab::EDGE[E][ip][0] == la || tab::EDGE[E][ip][1] == la) { if (tab::INC[E][la][c] != ip) { err = "INC table is not in ascending ip order"; return -1; } c++; } }
+    for (int la = 0; la < NSH; la++) { int c = 0; for (int ip = 0; ip < NIP; ip++) if (tab::EDGE[E][ip][0] == la || tab::EDGE[E][ip][1] == la) {
+        if (tab::INC[E][la][c] != ip) { err = "INC table is not in ascending ip order"; return -1; }
+        if ((tab::INC_SIGN[E][la][c] < 0) != (tab::EDGE[E][ip][1] == la)) { err = "INC_SIGN differs from the edge orientation"; return -1; }
+        c++; } }
     // precomputed tables (scv_volume_kernel, node_volume_kernel, fv1_j0_kernel restated for the host)
     std::vector<double> scvvol((size_t)n_elem * NSH), nodevol(n_node, 0.0);
     for (int64_t e = 0; e < n_elem; e++) {
@@ -94,10 +97,29 @@ int run(int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coord
     A.u = u; A.s0 = s0; A.s1 = s1; A.j0 = j0.data();
     A.beta = beta; A.val = values; A.def = defect;
     A.errflag = nullptr; A.elem_fast = fast ? elem_fast.data() : nullptr; A.max_adj = plan.max_adj_per_node;
+    // static SCVF geometry records in work-item order (fused_geom_kernel)
+    std::vector<double> geo;
+    if (use_geo) {
+        geo.resize((size_t)plan.work.size() * C::GEO);
+        for (const PatchHdr& H : plan.hdr)
+            for (int w = 0; w < H.n_work; w++) {
+                const uint32_t wi = plan.work[H.work0 + w];
+                const int el = wi & 255, ip = (wi >> 8) & 15;
+                const int64_t ge = plan.elems[H.elem0 + el];
+                double x[NSH * DIM], vol[NSH];
+                for (int k = 0; k < NSH; k++) {
+                    const int64_t nd = plan.pconn[(int64_t)(H.elem0 + el) * NSH + k];
+                    for (int d = 0; d < DIM; d++) x[k * DIM + d] = coords[nd * DIM + d];
+                    vol[k] = scvvol[ge * NSH + k];
+                }
+                fused_geom_record<E>(x, vol, ip, kp.diff_len, geo.data() + (size_t)(H.work0 + w) * C::GEO);
+            }
+        A.geo = geo.data();
+    }
     const FusedLayout<E> L(g.max_cnt);
     std::vector<unsigned char> smem(L.total + 64);
     unsigned char* base = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
-    FusedSmem<E> S(base, L);
+    const FusedSmem<E> S(base, L);
     for (int tid = 0; tid < C::NT; tid++) fused_stage_tables<E>(S, tid, C::NT);
     const int what = kp.what;
     const bool want_jac = what & (W_JAC_A | W_JAC_M), want_def = what & (W_DEF_A | W_DEF_M | W_RHS), flux_needed = what & (W_JAC_A | W_DEF_A);
@@ -110,27 +132,29 @@ int run(int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coord
         max_nodes = std::max<int64_t>(max_nodes, H.n_node); max_work = std::max<int64_t>(max_work, H.n_work); max_el = std::max<int64_t>(max_el, H.n_elem);
         const int par = pi & 1;
         for (int tid = 0; tid < C::NT; tid++) fused_load<E>(A, S, H, par, tid);
-        S.adj = S.adjbuf[par]; S.nodes = S.nodebuf[par];
+        const FusedTab<E> T(S, par);
         if (flux_needed) {
-            if (kp.stab == STAB_FIELDS) { for (int tid = 0; tid < C::NT; tid++) ok &= kp.time_dep ? fused_flux<E, STAB_FIELDS, true>(A, S, H, tid) : fused_flux<E, STAB_FIELDS, false>(A, S, H, tid); }
-            else { for (int tid = 0; tid < C::NT; tid++) ok &= kp.time_dep ? fused_flux<E, STAB_NONE, true>(A, S, H, tid) : fused_flux<E, STAB_NONE, false>(A, S, H, tid); }
+#define EMU_FLUX(ST, TDV) { for (int tid = 0; tid < C::NT; tid++) ok &= use_geo ? fused_flux<E, ST, TDV, true>(A, S, H, tid) : fused_flux<E, ST, TDV, false>(A, S, H, tid); }
+            if (kp.stab == STAB_FIELDS) { if (kp.time_dep) EMU_FLUX(STAB_FIELDS, true) else EMU_FLUX(STAB_FIELDS, false) }
+            else { if (kp.time_dep) EMU_FLUX(STAB_NONE, true) else EMU_FLUX(STAB_NONE, false) }
+#undef EMU_FLUX
         }
         for (int nl = 0; nl < H.n_node; nl++) {
-            if (node_seen[S.nodes[nl].node]++) { err = "a node belongs to two patches"; return -1; }
+            if (node_seen[T.nodes[nl].node]++) { err = "a node belongs to two patches"; return -1; }
             double* accn = S.acc + (size_t)(nl % (C::NWARP * C::NPW)) * (C::NV * S.cntp);      // the accumulator of the (warp, node slot) that gets this node
             if (want_jac) for (int lg = 0; lg < C::PARTS * NSH; lg++) fused_rows_zero<E>(S, accn, lg);
             double fs[NSH];
             for (int k = 0; k < NSH; k++) fs[k] = 0.0;
             if (flux_needed)
-                for (int j = 0; j < S.nodes[nl].adj_cnt; j++)
-                    for (int h = 0; h < C::PARTS; h++) for (int k = 0; k < NSH; k++) { double dummy = 0.0; fused_rows_accum_step<E>(A, S, accn, nl, h, k, j, h == 0 ? fs[k] : dummy); }
-            fused_rows_mass<E>(A, S, accn, nl);
-            if (want_def) for (int k = 0; k < NF; k++) fused_rows_defect<E>(A, S, nl, k, fs[k]);
+                for (int j = 0; j < T.nodes[nl].adj_cnt; j++)
+                    for (int h = 0; h < C::PARTS; h++) for (int k = 0; k < NSH; k++) { double dummy = 0.0; fused_rows_accum_step<E>(A, S, T, accn, nl, h, k, j, h == 0 ? fs[k] : dummy); }
+            fused_rows_mass<E>(A, T, accn, nl);
+            if (want_def) for (int k = 0; k < NF; k++) fused_rows_defect<E>(A, T, nl, k, fs[k]);
             if (want_jac) {
                 // odd nodes exercise the register-prefetched J0 path of the device, even nodes the direct reads
                 FusedJ0<E> jr[32];
-                for (int lane = 0; lane < 32; lane++) fused_j0_prefetch<E>(A, S, nl, lane, 32, jr[lane]);
-                for (int lane = 0; lane < 32; lane++) fused_rows_out<E>(A, S, accn, nl, lane, 32, (nl & 1) ? &jr[lane] : nullptr);
+                for (int lane = 0; lane < 32; lane++) fused_j0_prefetch<E>(A, T, nl, lane, 32, jr[lane]);
+                for (int lane = 0; lane < 32; lane++) fused_rows_out<E>(A, S, T, accn, nl, lane, 32, (nl & 1) ? &jr[lane] : nullptr);
             }
         }
     }
@@ -147,15 +171,15 @@ int run(int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coord
 
 extern "C" int emu_fused_assemble(int elem, int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coords, const KParams* kp,
                                   const double* u, const double* s0, const double* s1, double beta, double* values, double* defect,
-                                  int ray_fast, int64_t* stats, char* errbuf, int errlen)
+                                  int ray_fast, int use_geo, int64_t* stats, char* errbuf, int errlen)
 {
     std::string err;
     int rc = -1;
     switch (elem) {
-        case 0: rc = run<0>(n_elem, n_node, conn, coords, *kp, u, s0, s1, beta, values, defect, ray_fast, stats, err); break;
-        case 1: rc = run<1>(n_elem, n_node, conn, coords, *kp, u, s0, s1, beta, values, defect, ray_fast, stats, err); break;
-        case 2: rc = run<2>(n_elem, n_node, conn, coords, *kp, u, s0, s1, beta, values, defect, ray_fast, stats, err); break;
-        case 3: rc = run<3>(n_elem, n_node, conn, coords, *kp, u, s0, s1, beta, values, defect, ray_fast, stats, err); break;
+        case 0: rc = run<0>(n_elem, n_node, conn, coords, *kp, u, s0, s1, beta, values, defect, ray_fast, use_geo, stats, err); break;
+        case 1: rc = run<1>(n_elem, n_node, conn, coords, *kp, u, s0, s1, beta, values, defect, ray_fast, use_geo, stats, err); break;
+        case 2: rc = run<2>(n_elem, n_node, conn, coords, *kp, u, s0, s1, beta, values, defect, ray_fast, use_geo, stats, err); break;
+        case 3: rc = run<3>(n_elem, n_node, conn, coords, *kp, u, s0, s1, beta, values, defect, ray_fast, use_geo, stats, err); break;
         default: err = "bad element type";
     }
     if (errbuf && errlen > 0) { std::strncpy(errbuf, err.c_str(), errlen - 1); errbuf[errlen - 1] = 0; }

@@ -51,7 +51,7 @@ def lib():
 
 def assemble(elem, conn, coords, u, what, upwind="full", stab="fields", diff="raw", visc=1e-2, density=1.0, stokes=False,
              laplace=False, peclet=False, source=None, stab_upwind=None, sol0=None, sol1=None, dt=0.0, scale_a=1.0, scale_m=1.0,
-             beta=0.0, values=None, defect=None, nnz=None, ray_fast=1):
+             beta=0.0, values=None, defect=None, nnz=None, ray_fast=1, use_geo=1):
     """returns (values, defect, stats) of the emulated fused kernel; stats = dict of patch statistics"""
     conn = np.ascontiguousarray(conn, dtype=np.int32)
     coords = np.ascontiguousarray(coords, dtype=np.float64)
@@ -80,9 +80,9 @@ def assemble(elem, conn, coords, u, what, upwind="full", stab="fields", diff="ra
     dp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     f = lib().emu_fused_assemble
     f.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(KParams), C.c_void_p, C.c_void_p, C.c_void_p,
-                  C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
+                  C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
     rc = f(ELEM[elem], conn.shape[0], coords.shape[0], dp(conn), dp(coords), C.byref(k), dp(u), dp(s0), dp(s1), beta,
-           dp(values), dp(defect), ray_fast, dp(stats), err, 512)
+           dp(values), dp(defect), ray_fast, use_geo, dp(stats), err, 512)
     if rc != 0:
         raise RuntimeError("emu_fused_assemble: %s" % err.value.decode())
     names = ["n_patch", "scvf_evals", "n_scvf", "max_nodes", "max_work", "max_elems", "ray_fast", "n_not_star_shaped"]

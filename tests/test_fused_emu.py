@@ -17,7 +17,7 @@ SIZES = {"tri": 11, "quad": 14, "tet": 4, "hex": 6}
 
 
 def _check(ora, elem, coords, conn, u, what=JAC_A | DEF_A, upwind="lps", stab="fields", diff="raw", sol0=None, sol1=None,
-           dt=0.0, scale_a=1.0, scale_m=1.0, ray_fast=1, **flags):
+           dt=0.0, scale_a=1.0, scale_m=1.0, ray_fast=1, use_geo=1, **flags):
     E = ora.ELEM[elem]
     rowptr, colind = ora.fv1_csr(E, conn, coords.shape[0])
     p = ora.make_params(elem=elem, upwind=upwind, stab=stab, diff_len=diff, kin_visc=flags.get("visc", 1e-2),
@@ -26,7 +26,7 @@ def _check(ora, elem, coords, conn, u, what=JAC_A | DEF_A, upwind="lps", stab="f
                         stab_upwind=flags.get("stab_upwind") or "same")
     ov, od = ora.assemble(p, conn, coords, u, rowptr, colind, what, sol0=sol0, sol1=sol1, scale_a=scale_a, scale_m=scale_m)
     gv, gd, st = fused_emu.assemble(elem, conn, coords, u, what, upwind=upwind, stab=stab, diff=diff, sol0=sol0, sol1=sol1, dt=dt,
-                                    scale_a=scale_a, scale_m=scale_m, nnz=colind.shape[0], ray_fast=ray_fast, **flags)
+                                    scale_a=scale_a, scale_m=scale_m, nnz=colind.shape[0], ray_fast=ray_fast, use_geo=use_geo, **flags)
     if what & (JAC_A | JAC_M):
         eg, ee = parity.entry_errors(gv, ov, rowptr)
         assert eg < TOL and ee < TOL, ("jacobian", elem, upwind, stab, eg, ee)
@@ -39,9 +39,11 @@ def _check(ora, elem, coords, conn, u, what=JAC_A | DEF_A, upwind="lps", stab="f
 @pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
 @pytest.mark.parametrize("upwind", ["no", "full", "skewed", "lps"])
 @pytest.mark.parametrize("stab", ["fields", "none"])
-def test_stationary_jac_def(ora, elem, upwind, stab):
+@pytest.mark.parametrize("geo", [1, 0], ids=["geotab", "onthefly"])
+def test_stationary_jac_def(ora, elem, upwind, stab, geo):
+    """geo = 1: static SCVF geometry records (the default of the device path), geo = 0: geometry recomputed per SCVF"""
     coords, conn, u = parity.make_case(elem, SIZES[elem], seed=2)
-    _check(ora, elem, coords, conn, u, upwind=upwind, stab=stab)
+    _check(ora, elem, coords, conn, u, upwind=upwind, stab=stab, use_geo=geo)
 
 
 @pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
@@ -56,6 +58,8 @@ def test_flags(ora, elem, flags):
         flags["source"] = flags["source"][:2]
     coords, conn, u = parity.make_case(elem, SIZES[elem], seed=4)
     _check(ora, elem, coords, conn, u, **flags)
+    if "diff" in flags:
+        _check(ora, elem, coords, conn, u, use_geo=0, **flags)
 
 
 @pytest.mark.parametrize("elem", ["hex", "tet", "quad", "tri"])
