@@ -36,10 +36,9 @@ template <int E> struct FusedCfg {
     static constexpr int NCOL = NSH * DIM + NSH * NF + NSH;         // doubles per element: corner coordinates, unknowns, SCV volumes
     static constexpr int CSTR = NCOL | 1;                           // element-major rows, odd stride: the lanes of a warp (same element, different
                                                                     // corners / different elements, same corner) hit different banks
-    static constexpr int PARTS = 2;                                 // rows phase: PARTS * NSH lanes work on one patch node
-    static constexpr int NPW = 32 / (PARTS * NSH);                  // patch nodes a warp assembles at a time
+    static constexpr int NPW = 32 / NSH;                            // rows phase, accumulation: lane = (one of NPW patch nodes, corner k)
     static constexpr int NWARP = NT / 32;
-    static constexpr int JREG = NF == 4 ? 6 : 4;                    // J0 words (double2 / double) per lane and node prefetched in registers
+    static constexpr int JIT = 2;                                   // rows phase, output: rounds of 32 words per matrix row held in registers (J0 prefetch)
     // capacities of one patch (tile = node-box the grid is binned into; see ns_patch.h)
     static constexpr int MAXW = 512;
     static constexpr int MAXE = E == E_HEX ? 80 : (E == E_TET ? 160 : (E == E_QUAD ? 128 : 224));
@@ -71,7 +70,7 @@ template <int E> struct FusedLayout {
         auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return at; };
         o_rec = take(sizeof(double) * C::MAXW * C::RSTR);
         o_cols = take(sizeof(double) * C::CSTR * C::MAXE);
-        o_acc = take(sizeof(double) * (size_t)C::NWARP * C::NPW * C::NV * cntp);
+        o_acc = take(sizeof(double) * (size_t)C::MAXN * C::NV * cntp);     // one accumulator block per patch node
         o_dnt = take(sizeof(double) * C::NIP * C::DSTR);
         o_nt = take(sizeof(double) * C::NIP * C::NSTR);
         o_lip = take(sizeof(double) * C::NIP * 3);
@@ -102,7 +101,7 @@ template <int E> struct FusedSmem {
         xs = reinterpret_cast<double*>(base + L.o_cols);
         us = xs + C::NSH * C::DIM;
         vs = us + C::NSH * C::NF;
-        acc = reinterpret_cast<double*>(base + L.o_acc);            // [warp][node of the warp][NV][cntp]
+        acc = reinterpret_cast<double*>(base + L.o_acc);            // [patch node][NV][cntp]
         dnt = reinterpret_cast<double*>(base + L.o_dnt);
         Nt = reinterpret_cast<double*>(base + L.o_nt);
         lip = reinterpret_cast<double*>(base + L.o_lip);
@@ -734,22 +733,21 @@ template <int E, int STAB, bool TD, bool GEOT> NSB_HD bool fused_flux(const Fuse
     return ok;
 }
 
-// rows phase. PARTS * NSH lanes work on one patch node: lane (h, k) = (part h, corner k). For every adjacent element (in the
-// order of the global adjacency list) the lane sums the NINC incident SCVF records of its corner and adds its part
-//   h = 0: the convective diagonal D, the pressure column PP of the continuity row (+ the defect fluxes, k < NF)
-//   h = 1: the velocity columns C[DIM] of the continuity row
-// into the per-slot accumulators of the node (`accn`, private to the node's lanes). The corners of one element are distinct
-// nodes and the parts own different accumulator arrays, so a step is conflict-free; steps are separated by __syncwarp.
-// step 1: clear the node's accumulators (`lg` = lane index within the node's PARTS * NSH lanes)
-template <int E> NSB_HD void fused_rows_zero(const FusedSmem<E>& S, double* accn, int lg)
+// rows phase, accumulation. lane = (patch node, corner k): for every adjacent element of the node (in the order of the global
+// adjacency list) the lane sums the NINC incident SCVF records of its corner and adds the convective diagonal D, the
+// velocity columns C[DIM] and the pressure column PP of the continuity row into the node's per-slot accumulators `accn`
+// (and the defect fluxes, k < NF, into `fs`). The corners of one element are distinct nodes: a step is conflict-free; every
+// lane of a warp runs the same code (no divergence between value types); steps are separated by __syncwarp on the device.
+// step 1: clear the node's accumulators (its NSH lanes)
+template <int E> NSB_HD void fused_rows_zero(const FusedSmem<E>& S, double* accn, int k)
 {
     using C = FusedCfg<E>;
-    for (int i = lg; i < C::NV * S.cntp; i += C::PARTS * C::NSH) accn[i] = 0.0;
+    for (int i = k; i < C::NV * S.cntp; i += C::NSH) accn[i] = 0.0;
 }
 
-// step 2: adjacency entry j of node nl. The 16-byte entry is read once (one LDS.128): record slots, local corner + the
-// orientation bits of the NINC incident SCVFs (bit 4 + t set: the node is the `to` end), CSR slots of the element's corners.
-template <int E> NSB_HD void fused_rows_accum_step(const FusedArgs& A, const FusedSmem<E>& S, const FusedTab<E>& T, double* accn, int nl, int h, int k, int j, double& fs)
+// step 2: adjacency entry j of node nl. The 16-byte entry is read once: record slots, local corner + the orientation bits of
+// the NINC incident SCVFs (bit 4 + t set: the node is the `to` end), CSR slots of the element's corners.
+template <int E> NSB_HD void fused_rows_accum_step(const FusedArgs& A, const FusedSmem<E>& S, const FusedTab<E>& T, double* accn, int nl, int k, int j, double& fs)
 {
     using C = FusedCfg<E>;
     using LR = LeanRec<E>;
@@ -760,39 +758,33 @@ template <int E> NSB_HD void fused_rows_accum_step(const FusedArgs& A, const Fus
     if (j >= Nd.adj_cnt) return;
     struct U4 { uint32_t x, y, z, w; };
     const U4 a = *reinterpret_cast<const U4*>(T.adj + Nd.adj_off + j);
-    const uint32_t s01 = a.x, s2la = a.y;                        // slot[0] | slot[1] << 16,  slot[2] | la << 16 | self << 24
-    const uint32_t lab = s2la >> 16;
+    const uint32_t lab = a.y >> 16;                              // la | orientation bits << 4 | self << 8
     const uint32_t em = k < 4 ? a.z : a.w;                       // emap[0..3], emap[4..7]
     const int slot = (em >> (8 * (k & 3))) & 255;
-    const int rs[3] = {(int)(s01 & 0xffff), (int)(s01 >> 16), (int)(s2la & 0xffff)};
-    if (h == 0) {
-        double D = 0.0, PP = 0.0;
+    const int rs[3] = {(int)(a.x & 0xffff), (int)(a.x >> 16), (int)(a.y & 0xffff)};
+    double D = 0.0, PP = 0.0, F = 0.0, Cn[DIM];
 #pragma unroll
-        for (int t = 0; t < NINC; t++) {
-            const double* rc = S.rec + rs[t] * C::RSTR;
-            const bool neg = (lab >> (4 + t)) & 1;
-            if (def_a && k < NF) { const double f = rc[LR::O_F + k]; fs += neg ? -f : f; }
-            if (jac_a) {
-                const double sg = neg ? -p.scale_a : p.scale_a;
-                D += sg * rc[LR::O_DK + k];
-                PP += sg * rc[LR::O_PK + k];
-            }
-        }
-        if (jac_a) { accn[slot] += D; accn[(1 + DIM) * S.cntp + slot] += PP; }
-    } else if (jac_a) {
-        double Cn[DIM];
+    for (int d = 0; d < DIM; d++) Cn[d] = 0.0;
 #pragma unroll
-        for (int d = 0; d < DIM; d++) Cn[d] = 0.0;
-#pragma unroll
-        for (int t = 0; t < NINC; t++) {
-            const double* rc = S.rec + rs[t] * C::RSTR;
-            const bool neg = (lab >> (4 + t)) & 1;
-            const double w = (neg ? -p.scale_a : p.scale_a) * rc[LR::O_CK + k];
+    for (int t = 0; t < NINC; t++) {
+        const double* rc = S.rec + rs[t] * C::RSTR;
+        const double sg = ((lab >> (4 + t)) & 1) ? -1.0 : 1.0;
+        if (def_a) F += sg * rc[LR::O_F + (k < NF ? k : 0)];
+        if (jac_a) {
+            D += sg * rc[LR::O_DK + k];
+            PP += sg * rc[LR::O_PK + k];
+            const double w = sg * rc[LR::O_CK + k];
 #pragma unroll
             for (int d = 0; d < DIM; d++) Cn[d] += w * rc[LR::O_N + d];
         }
+    }
+    fs += F;
+    if (jac_a) {
+        const double sa = p.scale_a;
+        accn[slot] += sa * D;
 #pragma unroll
-        for (int d = 0; d < DIM; d++) accn[(1 + d) * S.cntp + slot] += Cn[d];
+        for (int d = 0; d < DIM; d++) accn[(1 + d) * S.cntp + slot] += sa * Cn[d];
+        accn[(1 + DIM) * S.cntp + slot] += sa * PP;
     }
 }
 
@@ -823,31 +815,34 @@ template <int E> NSB_HD void fused_rows_defect(const FusedArgs& A, const FusedTa
     *q = (A.beta == 0.0) ? d : A.beta * (*q) + d;
 }
 
-// step 5: the NF rows of node nl, written once by a whole warp (`lane`, `nlanes` = 32 on the device): consecutive lanes
-// write consecutive 16-byte chunks (3-D) / doubles (2-D) of the node's contiguous rows. The J0 words the lane needs are
-// word w = lane + i * nlanes of the node's DIM * NF * cnt doubles; the device passes the first JREG of them in registers
-// (fused_j0_prefetch, issued before the accumulation so that their latency is hidden), jpre == nullptr reads them here.
-template <int E> struct FusedJ0 { double v[FusedCfg<E>::JREG][FusedCfg<E>::NF == 4 ? 2 : 1]; };
+// rows phase, output: the NF rows of node nl, written once by a whole warp (`lane`, `nlanes` = 32 on the device). Matrix row rf
+// (compile-time) is written in rounds of nlanes consecutive words (3-D: 16-byte chunks, 2-D: doubles), so that consecutive
+// lanes write consecutive addresses and no index arithmetic depends on rf at run time. The J0 words of the first JIT rounds of
+// every momentum row are passed in registers by the device (fused_j0_prefetch, issued before the accumulation phase so that
+// their latency is hidden); jpre == nullptr reads them here.
+template <int E> struct FusedJ0 { double v[FusedCfg<E>::DIM][FusedCfg<E>::JIT][FusedCfg<E>::NF == 4 ? 2 : 1]; };
 
 template <int E> NSB_HD void fused_j0_prefetch(const FusedArgs& A, const FusedTab<E>& T, int nl, int lane, int nlanes, FusedJ0<E>& J)
 {
     using C = FusedCfg<E>;
     constexpr int DIM = C::DIM, NF = C::NF, W = NF == 4 ? 2 : 1;
     const PatchNode& Nd = T.nodes[nl];
-    const int nw = Nd.cnt * (DIM * NF) / W;                      // J0 words of the node
+    const int nwr = Nd.cnt * NF / W;                             // words per row
     const double* j0g = A.j0 + Nd.b0 * (DIM * NF);
 #pragma unroll
-    for (int i = 0; i < C::JREG; i++) {
-        const int w = lane + i * nlanes;
-        if (w < nw) {
+    for (int rf = 0; rf < DIM; rf++)
+#pragma unroll
+        for (int it = 0; it < C::JIT; it++) {
+            const int i = lane + it * nlanes;
+            if (i < nwr) {
 #ifdef __CUDA_ARCH__
-            if constexpr (W == 2) { const double2 t = __ldcs(reinterpret_cast<const double2*>(j0g) + w); J.v[i][0] = t.x; J.v[i][1] = t.y; }
-            else J.v[i][0] = __ldcs(j0g + w);
+                if constexpr (W == 2) { const double2 t = __ldcs(reinterpret_cast<const double2*>(j0g) + rf * nwr + i); J.v[rf][it][0] = t.x; J.v[rf][it][1] = t.y; }
+                else J.v[rf][it][0] = __ldcs(j0g + rf * nwr + i);
 #else
-            for (int q = 0; q < W; q++) J.v[i][q] = j0g[w * W + q];
+                for (int q = 0; q < W; q++) J.v[rf][it][q] = j0g[(rf * nwr + i) * W + q];
 #endif
+            }
         }
-    }
 }
 
 template <int E> NSB_HD void fused_rows_out(const FusedArgs& A, const FusedSmem<E>& S, const FusedTab<E>& T, const double* acc, int nl, int lane, int nlanes, const FusedJ0<E>* jpre)
@@ -863,64 +858,78 @@ template <int E> NSB_HD void fused_rows_out(const FusedArgs& A, const FusedSmem<
     const double* j0g = A.j0 + Nd.b0 * (DIM * NF);
     const double beta = A.beta;
     if constexpr (NF == 4) {
-        const int n2 = 2 * cnt, nw0 = DIM * n2, nwt = NF * n2;   // 16-byte chunks per row, in the J0 rows, in all rows
-        auto chunk = [&](int w, bool have, double jx, double jy) {
-            const int rf = (w >= n2) + (w >= 2 * n2) + (w >= 3 * n2);
-            const int i = w - rf * n2, slot = i >> 1, cp = i & 1;
-            double vx, vy;
-            if (w < nw0) {
-                vx = 0.0; vy = 0.0;
-                if (jac_a) {
-                    if (!have) {
+        const int n2 = 2 * cnt;                                  // 16-byte chunks per row
+        // chunk i of row rf: slot = i / 2, column pair cp = i & 1
+        auto momentum = [&](int rf, int i, bool have, double jx, double jy) {
+            const int slot = i >> 1, cp = i & 1;
+            double vx = 0.0, vy = 0.0;
+            if (jac_a) {
+                if (!have) {
 #ifdef __CUDA_ARCH__
-                        const double2 t = __ldcs(reinterpret_cast<const double2*>(j0g) + w); jx = t.x; jy = t.y;
+                    const double2 t = __ldcs(reinterpret_cast<const double2*>(j0g) + rf * n2 + i); jx = t.x; jy = t.y;
 #else
-                        jx = j0g[2 * w]; jy = j0g[2 * w + 1];
+                    jx = j0g[2 * (rf * n2 + i)]; jy = j0g[2 * (rf * n2 + i) + 1];
 #endif
-                    }
-                    vx = jx * s_visc; vy = jy * (cp ? s_pres : s_visc);
                 }
-                const double D = acc[slot];
-                if (rf == 2 * cp) vx += D;
-                if (rf == 2 * cp + 1) vy += D;
-            } else {
-                vx = acc[(1 + 2 * cp) * cntp + slot]; vy = acc[(2 + 2 * cp) * cntp + slot];
+                vx = jx * s_visc; vy = jy * (cp ? s_pres : s_visc);
             }
+            const double D = acc[slot];
+            if (cp == (rf >> 1)) { if (rf & 1) vy += D; else vx += D; }
 #ifdef __CUDA_ARCH__
-            double2* o2 = reinterpret_cast<double2*>(out) + w;
+            double2* o2 = reinterpret_cast<double2*>(out) + rf * n2 + i;
             if (beta == 0.0) __stcs(o2, make_double2(vx, vy));
             else { double2 o = *o2; o.x = beta * o.x + vx; o.y = beta * o.y + vy; *o2 = o; }
 #else
-            if (beta == 0.0) { out[2 * w] = vx; out[2 * w + 1] = vy; }
-            else { out[2 * w] = beta * out[2 * w] + vx; out[2 * w + 1] = beta * out[2 * w + 1] + vy; }
+            double* o = out + 2 * (rf * n2 + i);
+            if (beta == 0.0) { o[0] = vx; o[1] = vy; } else { o[0] = beta * o[0] + vx; o[1] = beta * o[1] + vy; }
 #endif
         };
-        // the first JREG rounds use the register-prefetched J0 words (compile-time register indices), the rest reads directly
 #pragma unroll
-        for (int it = 0; it < C::JREG; it++) {
-            const int w = lane + it * nlanes;
-            if (w < nwt) { if (jpre) chunk(w, true, jpre->v[it][0], jpre->v[it][1]); else chunk(w, false, 0.0, 0.0); }
+        for (int rf = 0; rf < DIM; rf++) {
+#pragma unroll
+            for (int it = 0; it < C::JIT; it++) {
+                const int i = lane + it * nlanes;
+                if (i < n2) { if (jpre) momentum(rf, i, true, jpre->v[rf][it][0], jpre->v[rf][it][1]); else momentum(rf, i, false, 0.0, 0.0); }
+            }
+            for (int i = lane + C::JIT * nlanes; i < n2; i += nlanes) momentum(rf, i, false, 0.0, 0.0);
         }
-        for (int w = lane + C::JREG * nlanes; w < nwt; w += nlanes) chunk(w, false, 0.0, 0.0);
+        for (int i = lane; i < n2; i += nlanes) {                // continuity row: (C0, C1) | (C2, PP) per slot
+            const int slot = i >> 1, cp = i & 1;
+            const double vx = acc[(1 + 2 * cp) * cntp + slot], vy = acc[(2 + 2 * cp) * cntp + slot];
+#ifdef __CUDA_ARCH__
+            double2* o2 = reinterpret_cast<double2*>(out) + DIM * n2 + i;
+            if (beta == 0.0) __stcs(o2, make_double2(vx, vy));
+            else { double2 o = *o2; o.x = beta * o.x + vx; o.y = beta * o.y + vy; *o2 = o; }
+#else
+            double* o = out + 2 * (DIM * n2 + i);
+            if (beta == 0.0) { o[0] = vx; o[1] = vy; } else { o[0] = beta * o[0] + vx; o[1] = beta * o[1] + vy; }
+#endif
+        }
     } else {
-        const int rowlen = cnt * NF, nw0 = DIM * rowlen, nwt = NF * rowlen;
-        auto entry = [&](int w, bool have, double jv) {
-            const int rf = w / rowlen, i = w - rf * rowlen;
+        const int rowlen = cnt * NF;
+        auto momentum = [&](int rf, int i, bool have, double jv) {
             const int slot = i / NF, cf = i - slot * NF;
-            double v;
-            if (w < nw0) {
-                v = 0.0;
-                if (jac_a) v = (have ? jv : j0g[w]) * (cf < DIM ? s_visc : s_pres);
-                if (cf == rf) v += acc[slot];
-            } else v = acc[(1 + cf) * cntp + slot];
-            out[w] = (beta == 0.0) ? v : beta * out[w] + v;
+            double v = 0.0;
+            if (jac_a) v = (have ? jv : j0g[rf * rowlen + i]) * (cf < DIM ? s_visc : s_pres);
+            if (cf == rf) v += acc[slot];
+            double* o = out + rf * rowlen + i;
+            *o = (beta == 0.0) ? v : beta * (*o) + v;
         };
 #pragma unroll
-        for (int it = 0; it < C::JREG; it++) {
-            const int w = lane + it * nlanes;
-            if (w < nwt) { if (jpre) entry(w, true, jpre->v[it][0]); else entry(w, false, 0.0); }
+        for (int rf = 0; rf < DIM; rf++) {
+#pragma unroll
+            for (int it = 0; it < C::JIT; it++) {
+                const int i = lane + it * nlanes;
+                if (i < rowlen) { if (jpre) momentum(rf, i, true, jpre->v[rf][it][0]); else momentum(rf, i, false, 0.0); }
+            }
+            for (int i = lane + C::JIT * nlanes; i < rowlen; i += nlanes) momentum(rf, i, false, 0.0);
         }
-        for (int w = lane + C::JREG * nlanes; w < nwt; w += nlanes) entry(w, false, 0.0);
+        for (int i = lane; i < rowlen; i += nlanes) {
+            const int slot = i / NF, cf = i - slot * NF;
+            const double v = acc[(1 + cf) * cntp + slot];
+            double* o = out + DIM * rowlen + i;
+            *o = (beta == 0.0) ? v : beta * (*o) + v;
+        }
     }
 }
 
@@ -1022,7 +1031,7 @@ template <int E, int STAB, bool TD, bool GEOT>
 __global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const FusedArgs A, int max_cnt)
 {
     using C = FusedCfg<E>;
-    constexpr int NSH = C::NSH, NF = C::NF, NPW = C::NPW, NWARP = C::NWARP, LPN = C::PARTS * NSH;
+    constexpr int NSH = C::NSH, NF = C::NF, NPW = C::NPW, NWARP = C::NWARP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FusedLayout<E> L(max_cnt);
     const FusedSmem<E> S(smem_raw, L);
@@ -1031,11 +1040,9 @@ __global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const Fus
     const int what = A.p.what;
     const bool want_jac = what & (W_JAC_A | W_JAC_M), want_def = what & (W_DEF_A | W_DEF_M | W_RHS);
     const bool flux_needed = what & (W_JAC_A | W_DEF_A), jac_a = what & W_JAC_A;
-    // rows phase: lane = (node jj of the NPW the warp assembles at a time, part h, corner k)
-    const int jj = lane / LPN, lg = lane - jj * LPN, h = lg / NSH, k = lg - h * NSH;
+    // rows phase, accumulation: lane = (node jj of the NPW the warp handles at a time, corner k)
+    const int jj = lane / NSH, k = lane - jj * NSH;
     const bool lane_on = jj < NPW;
-    double* const accw = S.acc + (size_t)warp * NPW * (C::NV * S.cntp);
-    double* const accn = accw + (lane_on ? jj : 0) * (C::NV * S.cntp);
     auto load_hdr = [&](int pi) {
         PatchHdr H;
         const int4* hp = reinterpret_cast<const int4*>(A.hdr + pi);
@@ -1063,34 +1070,39 @@ __global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const Fus
             if (GEOT && flux_needed && tid < Hn.n_work)          // the next patch's geometry records: one 128-byte line per SCVF -> L2
                 asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.geo + (int64_t)(Hn.work0 + tid) * C::GEO));
         }
-        for (int nl0 = warp * NPW; nl0 < H.n_node; nl0 += NWARP * NPW) {
-            FusedJ0<E> j0r[NPW];                                 // J0 rows of the warp's nodes -> registers (in flight during the accumulation)
-            if (jac_a) {
+        // output assignment: warp w writes the rows of the nodes w, w + NWARP, ... ; their J0 rows are fetched into registers now
+        // (in flight during the accumulation), two nodes per round
+        FusedJ0<E> j0r[2];
+        if (jac_a) {
 #pragma unroll
-                for (int q = 0; q < NPW; q++) if (nl0 + q < H.n_node) fused_j0_prefetch<E>(A, T, nl0 + q, lane, 32, j0r[q]);
-            }
+            for (int q = 0; q < 2; q++) if (warp + q * NWARP < H.n_node) fused_j0_prefetch<E>(A, T, warp + q * NWARP, lane, 32, j0r[q]);
+        }
+        // accumulation: the first warps take NPW nodes each
+        for (int nl0 = warp * NPW; nl0 < H.n_node; nl0 += NWARP * NPW) {
             const int nl = nl0 + jj;
             const bool on = lane_on && nl < H.n_node;
+            double* const accn = S.acc + (size_t)(on ? nl : 0) * (C::NV * S.cntp);
             double fs = 0.0;
-            if (on && want_jac) fused_rows_zero<E>(S, accn, lg);
+            if (on && want_jac) fused_rows_zero<E>(S, accn, k);
             __syncwarp();
             if (flux_needed) {
                 const int mycnt = on ? (int)T.nodes[nl].adj_cnt : 0;
                 const int mx = __reduce_max_sync(0xffffffffu, mycnt);
                 for (int j = 0; j < mx; j++) {
-                    if (on) fused_rows_accum_step<E>(A, S, T, accn, nl, h, k, j, fs);
+                    if (on) fused_rows_accum_step<E>(A, S, T, accn, nl, k, j, fs);
                     __syncwarp();
                 }
             }
-            if (on && lg == 0) fused_rows_mass<E>(A, T, accn, nl);
-            __syncwarp();
-            if (on && want_def && h == 0 && k < NF) fused_rows_defect<E>(A, T, nl, k, fs);
-            if (want_jac) {
+            if (on && k == 0) fused_rows_mass<E>(A, T, accn, nl);
+            if (on && want_def && k < NF) fused_rows_defect<E>(A, T, nl, k, fs);
+        }
+        __syncthreads();                                         // accumulators complete
+        if (want_jac) {
 #pragma unroll
-                for (int q = 0; q < NPW; q++)
-                    if (nl0 + q < H.n_node) fused_rows_out<E>(A, S, T, accw + q * (C::NV * S.cntp), nl0 + q, lane, 32, jac_a ? &j0r[q] : nullptr);
-            }
-            __syncwarp();                                        // the accumulators are reused by the warp's next nodes
+            for (int q = 0; q < 2; q++)
+                if (warp + q * NWARP < H.n_node) fused_rows_out<E>(A, S, T, S.acc + (size_t)(warp + q * NWARP) * (C::NV * S.cntp), warp + q * NWARP, lane, 32, jac_a ? &j0r[q] : nullptr);
+            for (int nl = warp + 2 * NWARP; nl < H.n_node; nl += NWARP)
+                fused_rows_out<E>(A, S, T, S.acc + (size_t)nl * (C::NV * S.cntp), nl, lane, 32, nullptr);
         }
         if (pn >= A.n_patch) break;
         pi = pn; H = Hn; par ^= 1;

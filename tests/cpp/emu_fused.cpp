@@ -141,13 +141,13 @@ int run(int64_t n_elem, int64_t n_node, const int32_t* conn, const double* coord
         }
         for (int nl = 0; nl < H.n_node; nl++) {
             if (node_seen[T.nodes[nl].node]++) { err = "a node belongs to two patches"; return -1; }
-            double* accn = S.acc + (size_t)(nl % (C::NWARP * C::NPW)) * (C::NV * S.cntp);      // the accumulator of the (warp, node slot) that gets this node
-            if (want_jac) for (int lg = 0; lg < C::PARTS * NSH; lg++) fused_rows_zero<E>(S, accn, lg);
+            double* accn = S.acc + (size_t)nl * (C::NV * S.cntp);
+            if (want_jac) for (int k = 0; k < NSH; k++) fused_rows_zero<E>(S, accn, k);
             double fs[NSH];
             for (int k = 0; k < NSH; k++) fs[k] = 0.0;
             if (flux_needed)
                 for (int j = 0; j < T.nodes[nl].adj_cnt; j++)
-                    for (int h = 0; h < C::PARTS; h++) for (int k = 0; k < NSH; k++) { double dummy = 0.0; fused_rows_accum_step<E>(A, S, T, accn, nl, h, k, j, h == 0 ? fs[k] : dummy); }
+                    for (int k = 0; k < NSH; k++) fused_rows_accum_step<E>(A, S, T, accn, nl, k, j, fs[k]);
             fused_rows_mass<E>(A, T, accn, nl);
             if (want_def) for (int k = 0; k < NF; k++) fused_rows_defect<E>(A, T, nl, k, fs[k]);
             if (want_jac) {
