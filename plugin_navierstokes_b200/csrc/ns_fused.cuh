@@ -286,7 +286,7 @@ NSB_HD int fused_ray_side(const FusedSmem<E>& S, int el, int s, const double* fr
 // side is the one the ordered search returns; cuts on an edge shared by two sides give the same point from either side.
 template <int E>
 NSB_HD bool fused_ray_cut(const FusedSmem<E>& S, int el, int ip, const double* from, const double* dir, bool fast,
-                          const double (*JI)[ET<E>::DIM], int& side_out, double* gcut, double* lcut)
+                          const double* sref, int& side_out, double* gcut, double* lcut)
 {
     using C = FusedCfg<E>;
     constexpr int DIM = C::DIM, NSIDE = C::NSIDE;
@@ -300,7 +300,7 @@ NSB_HD bool fused_ray_cut(const FusedSmem<E>& S, int el, int ip, const double* f
             float best = -3.0e38f; int bs = -1;
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-                const float si = (float)(JI[0][i] * dir[0] + JI[1][i] * dir[1] + JI[2][i] * dir[2]);
+                const float si = (float)sref[i];               // s = J^-1 dir (reference-space direction of the ray)
                 const float xi = (float)S.lip[ip * 3 + i];
                 if (si != 0.0f) {
                     const float t = si > 0.0f ? -xi / si : (1.0f - xi) / si;
@@ -347,7 +347,7 @@ NSB_HD bool fused_ray_cut(const FusedSmem<E>& S, int el, int ip, const double* f
 
 // upwind shapes of one ip (No / Full / Skewed / LPS); see upwind_uniform (ns_owner.cuh), upwind.cpp:52-80,133-172,381-430,505-575
 template <int E>
-NSB_HD bool fused_upwind(const FusedSmem<E>& S, int el, int ip, int type, bool fast, const double (*JI)[ET<E>::DIM],
+NSB_HD bool fused_upwind(const FusedSmem<E>& S, int el, int ip, int type, bool fast, const double* sref,
                          const double* n, const double* xip, const double* N, int from, int to, const double* vel,
                          double* up, double& len)
 {
@@ -374,7 +374,7 @@ NSB_HD bool fused_upwind(const FusedSmem<E>& S, int el, int ip, int type, bool f
     for (int k = 0; k < NSH; k++) up[k] = 0.0;
     if (sqrt(dotv<DIM>(vel, vel)) < 1e-14) { len = 1.0; return true; }      // upwind.cpp:407-413, 531-537
     int side = 0; double gc[DIM], lc[DIM];
-    if (!fused_ray_cut<E>(S, el, ip, xip, vel, fast, JI, side, gc, lc)) { len = 1.0; return false; }
+    if (!fused_ray_cut<E>(S, el, ip, xip, vel, fast, sref, side, gc, lc)) { len = 1.0; return false; }
     constexpr int NSC = (DIM == 2) ? 2 : (E == E_TET ? 3 : 4);
     if (type == UPW_SKEWED) {                                    // GetNodeNextToCut, upwind.cpp:337-379
         double mn = 1.79769313486231570e308; int bestc = 0;
@@ -406,8 +406,11 @@ NSB_HD bool fused_upwind(const FusedSmem<E>& S, int el, int ip, int type, bool f
 }
 
 // ------------------------------------------------------------------------------------------------
-// flux phase: one SCVF (local element el, ip) -> lean record `fr` (shared memory). Same evaluation order as
-// fv1_flux_kernel<LEAN> (ns_owner.cuh). nd = global node ids of the element's corners (time-dependent closure only).
+// flux phase: one SCVF (local element el, ip) -> lean record `fr` (shared memory). Same arithmetic as fv1_flux_kernel<LEAN>
+// (ns_owner.cuh), staged so that few values are live across the ray search: with ~225 KB of the SM's 228 KB used as shared
+// memory there is no L1 left for register spills, so everything that has to survive the upwind search is parked in the record
+// itself (the upwind shapes live in the dK slots until they are scaled in place, the partial defect fluxes in the F slots,
+// J^-T n in the pK slots).  nd = global node ids of the element's corners (time-dependent closure only).
 // ------------------------------------------------------------------------------------------------
 template <int E, int STAB, bool TD, bool GEOT>
 NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip, const int32_t* __restrict__ nd, const double* __restrict__ geo,
@@ -416,68 +419,144 @@ NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip
     using C = FusedCfg<E>;
     using LR = LeanRec<E>;
     constexpr int DIM = C::DIM, NSH = C::NSH, NIP = C::NIP, NF = C::NF, P = DIM;
+    constexpr int O_GPN = LR::HEAD - 1;                          // scratch: the padding slot of the record head
+    static_assert(LR::HEAD - 1 >= NF + DIM && DIM <= LR::NSHP, "record scratch layout");
     const KParams& p = A.p;
     const bool td = TD && p.time_dep;
     const double nurho = p.visc * p.rho;
     const bool want_def = p.what & W_DEF_A, want_jac = p.what & W_JAC_A;
     bool ok = true;
     const int from = S.iptab[ip * 12], to = S.iptab[ip * 12 + 1];
-    double n[DIM], xip[DIM], JI[DIM][DIM], dlinv = 0.0;
-    if constexpr (GEOT) {
-        // static SCVF geometry record (fused_geom_record, built once per mesh): n | xip | J^-T | 1/L_d^2
+    const double* N = S.Nt + ip * C::NSTR;
+    double n[DIM], xip[DIM], std[DIM], sref[DIM], dlinv = 0.0, sn, oacc = 0.0;
+    {
+        // ---- stage 1: geometry, StdVel, and everything that needs J^-T (then J^-T is dead) ----
+        double JI[DIM][DIM];
+        if constexpr (GEOT) {
+            // static SCVF geometry record (fused_geom_record, built once per mesh): n | xip | J^-T | 1/L_d^2
 #pragma unroll
-        for (int d = 0; d < DIM; d++) { n[d] = geo[d]; xip[d] = geo[3 + d]; }
+            for (int d = 0; d < DIM; d++) { n[d] = geo[d]; xip[d] = geo[3 + d]; }
 #pragma unroll
-        for (int d = 0; d < DIM; d++)
+            for (int d = 0; d < DIM; d++)
 #pragma unroll
-            for (int i = 0; i < DIM; i++) JI[d][i] = geo[6 + d * DIM + i];
-        dlinv = geo[15];
-    } else {
-        double cen[DIM];
+                for (int i = 0; i < DIM; i++) JI[d][i] = geo[6 + d * DIM + i];
+            dlinv = geo[15];
+        } else {
+            double cen[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < NSH; k++) s += NSB_FCOL(S.xs, k * DIM + d);
+                cen[d] = s * (1.0 / NSH);
+            }
+            // COR diffusion length: element-wide statistics of the SCVF normals (diffusion_length.h:139-172)
+            double cmn = 0.0, cav = 0.0, cmd = 0.0;
+            if (STAB != STAB_NONE && p.diff_len == DIFF_COR) {
+                cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
+                for (int i = 0; i < NIP; i++) {
+                    double nn_[DIM], xx_[DIM], dsi;
+                    fused_ip_geometry<E>(S, el, i, cen, nn_, xx_, dsi, false, nullptr);
+                    const double q = dotv<DIM>(nn_, nn_);
+                    if (q < cmn) cmn = q;
+                    cav += q;
+                    if (DIM == 3 && dsi < cmd) cmd = dsi;
+                }
+                cav /= NIP;
+            }
+            double ds = 0.0;
+            fused_ip_geometry<E>(S, el, ip, cen, n, xip, ds, true, JI);
+            if (STAB != STAB_NONE) dlinv = diff_len_sq_inv<DIM>(p.diff_len, dotv<DIM>(n, n), NSB_FCOL(S.vs, from), NSB_FCOL(S.vs, to), ds, cmn, cav, cmd);
+        }
+        // StdVel from the `u` argument (:282-293)
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
             double s = 0;
 #pragma unroll
-            for (int k = 0; k < NSH; k++) s += NSB_FCOL(S.xs, k * DIM + d);
-            cen[d] = s * (1.0 / NSH);
+            for (int k = 0; k < NSH; k++) s += NSB_FCOL(S.us, k * NF + d) * N[k];
+            std[d] = s;
         }
-        // COR diffusion length: element-wide statistics of the SCVF normals (diffusion_length.h:139-172)
-        double cmn = 0.0, cav = 0.0, cmd = 0.0;
-        if (STAB != STAB_NONE && p.diff_len == DIFF_COR) {
-            cmn = 1.79769313486231570e308; cmd = 1.79769313486231570e308;
-            for (int i = 0; i < NIP; i++) {
-                double nn_[DIM], xx_[DIM], dsi;
-                fused_ip_geometry<E>(S, el, i, cen, nn_, xx_, dsi, false, nullptr);
-                const double q = dotv<DIM>(nn_, nn_);
-                if (q < cmn) cmn = q;
-                cav += q;
-                if (DIM == 3 && dsi < cmd) cmd = dsi;
+        sn = dotv<DIM>(std, n);
+        // reference-space direction of the upwind ray, J^-1 StdVel (predicted-side search), and J^-T n (pressure column)
+#pragma unroll
+        for (int i = 0; i < DIM; i++) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) { a += JI[d][i] * std[d]; b += JI[d][i] * n[d]; }
+            sref[i] = a;
+            fr[LR::O_PK + i] = b;                                // scratch until the pK coefficients are formed
+        }
+        // defect (:686-776), part 1: diffusive + pressure flux and grad p . n. The local gradient tensor is summed first and
+        // mapped to global gradients once.
+        if (want_def) {
+            double Lg[DIM][NF], L0[DIM];
+#pragma unroll
+            for (int i = 0; i < DIM; i++) {
+                L0[i] = 0.0;
+#pragma unroll
+                for (int q = 0; q < NF; q++) Lg[i][q] = 0.0;
             }
-            cav /= NIP;
+            double pr = 0.0;
+#pragma unroll
+            for (int k = 0; k < NSH; k++) {
+                double dl[DIM], uk[NF];
+#pragma unroll
+                for (int i = 0; i < DIM; i++) dl[i] = S.dnt[ip * C::DSTR + k * DIM + i];
+#pragma unroll
+                for (int q = 0; q < NF; q++) uk[q] = NSB_FCOL(S.us, k * NF + q);
+#pragma unroll
+                for (int i = 0; i < DIM; i++)
+#pragma unroll
+                    for (int q = 0; q < NF; q++) Lg[i][q] += dl[i] * uk[q];
+                pr += N[k] * uk[P];
+                if (STAB != STAB_NONE && td) {                   // the closure uses solution(0) (:296, :646) and the old solution
+                    const double p0k = A.s0[(int64_t)nd[k] * NF + P];
+                    double o = 0.0;
+#pragma unroll
+                    for (int i = 0; i < DIM; i++) L0[i] += dl[i] * p0k;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) o += A.s1[(int64_t)nd[k] * NF + d] * n[d];
+                    oacc += N[k] * o;
+                }
+            }
+            double gv[DIM][DIM], gpn = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                double sp_ = 0.0;
+#pragma unroll
+                for (int i = 0; i < DIM; i++) sp_ += JI[d][i] * (td ? L0[i] : Lg[i][P]);
+                gpn += sp_ * n[d];
+#pragma unroll
+                for (int q = 0; q < DIM; q++) {
+                    double sv_ = 0.0;
+#pragma unroll
+                    for (int i = 0; i < DIM; i++) sv_ += JI[d][i] * Lg[i][q];
+                    gv[q][d] = sv_;
+                }
+            }
+#pragma unroll
+            for (int d1 = 0; d1 < DIM; d1++) {
+                double df = 0.0;
+#pragma unroll
+                for (int d2 = 0; d2 < DIM; d2++) df += gv[d1][d2] * n[d2];
+                if (!p.laplace) {
+#pragma unroll
+                    for (int d2 = 0; d2 < DIM; d2++) df += gv[d2][d1] * n[d2];
+                }
+                fr[LR::O_F + d1] = df * (-1.0) * nurho + pr * n[d1];     // the convective part is added in stage 3
+            }
+            fr[O_GPN] = gpn;
         }
-        double ds = 0.0;
-        fused_ip_geometry<E>(S, el, ip, cen, n, xip, ds, true, JI);
-        if (STAB != STAB_NONE) dlinv = diff_len_sq_inv<DIM>(p.diff_len, dotv<DIM>(n, n), NSB_FCOL(S.vs, from), NSB_FCOL(S.vs, to), ds, cmn, cav, cmd);
     }
-    const double* N = S.Nt + ip * C::NSTR;
-    // ---- StdVel from the `u` argument (:282-293) ----
-    double std[DIM];
-#pragma unroll
-    for (int d = 0; d < DIM; d++) {
-        double s = 0;
-#pragma unroll
-        for (int k = 0; k < NSH; k++) s += NSB_FCOL(S.us, k * NF + d) * N[k];
-        std[d] = s;
-    }
-    const double sn = dotv<DIM>(std, n);
     const double prod = sn * p.rho;
-    // ---- the stabilisation's upwind ----
-    double up[NSH], uplen = 1.0;
+    // ---- stage 2: the stabilisation's upwind; its shapes live in the dK slots of the record ----
+    double* up = fr + LR::O_DK;
+    double uplen = 1.0;
 #pragma unroll
     for (int k = 0; k < NSH; k++) up[k] = 0.0;
     const bool fast = S.efast[el] != 0;
-    if (!p.stokes) ok &= fused_upwind<E>(S, el, ip, p.upw_stab, fast, JI, n, xip, N, from, to, std, up, uplen);
-    // ---- diagonal of the ip system and numerators sb_k = qa N_k + qb up_k (stabilization.cpp:166-236) ----
+    if (!p.stokes) ok &= fused_upwind<E>(S, el, ip, p.upw_stab, fast, sref, n, xip, N, from, to, std, up, uplen);
+    // diagonal of the ip system and numerators sb_k = qa N_k + qb up_k (stabilization.cpp:166-236)
     double inv = 0.0, qa = 0.0, qb = 0.0;
     if (STAB != STAB_NONE) {
         qa = p.visc * dlinv;
@@ -488,48 +567,53 @@ NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip
         inv = 1.0 / diag;
     }
     // everything that uses the STABILISATION's upwind shapes happens here: the convective upwind below may overwrite `up`
-    if (want_jac) {                                              // continuity-row coefficients (:561-584)
+    double U[DIM];                                               // upwind_vel of the stabilisation's upwind (upwind_interface.h:334-358)
+#pragma unroll
+    for (int d = 0; d < DIM; d++) U[d] = 0.0;
+    {
+        const double ci = inv * p.rho;
+        double acc = 0.0;                                        // time-dependent closure sum  sum_k sb_k (s0_k . n)
 #pragma unroll
         for (int k = 0; k < NSH; k++) {
-            double c;
-            if (STAB == STAB_NONE) c = N[k] * p.rho;
-            else { double s = qa * N[k]; if (!p.stokes) s += qb * up[k]; c = s * inv * p.rho; }
-            fr[LR::O_CK + k] = c;
-        }
-    }
-    double Us[DIM];                                              // upwind_vel of the stabilisation's upwind (upwind_interface.h:334-358)
+            const double upk = p.stokes ? 0.0 : up[k];
+            const double sb = qa * N[k] + qb * upk;
+            if (want_jac) fr[LR::O_CK + k] = (STAB == STAB_NONE) ? N[k] * p.rho : sb * ci;       // continuity-row coefficients (:561-584)
 #pragma unroll
-    for (int d = 0; d < DIM; d++) Us[d] = 0.0;
-    if (!p.stokes) {
-#pragma unroll
-        for (int k = 0; k < NSH; k++)
-#pragma unroll
-            for (int d = 0; d < DIM; d++) Us[d] += up[k] * NSB_FCOL(S.us, k * NF + d);
-    }
-    double acc = 0.0;                                            // closure sum  sum_k sb_k (s_k . n)
-    if (STAB != STAB_NONE && want_def) {
-        if (!td) {
-#pragma unroll
-            for (int d = 0; d < DIM; d++) acc += (qa * std[d] + qb * Us[d]) * n[d];
-        } else {
-#pragma unroll
-            for (int k = 0; k < NSH; k++) {
+            for (int d = 0; d < DIM; d++) U[d] += upk * NSB_FCOL(S.us, k * NF + d);
+            if (STAB != STAB_NONE && want_def && td) {
                 double sk = 0.0;
 #pragma unroll
                 for (int d = 0; d < DIM; d++) sk += A.s0[(int64_t)nd[k] * NF + d] * n[d];
-                double s = qa * N[k]; if (!p.stokes) s += qb * up[k];
-                acc += s * sk;
+                acc += sb * sk;
             }
         }
-    }
-    // ---- convective upwind, transported velocity, Peclet blend ----
-    double U[DIM], w = 1.0;
+        // defect, part 2: continuity flux (stab_vel . n) rho
+        if (want_def) {
+            double cont;
+            if (STAB == STAB_NONE) cont = sn * p.rho;
+            else {
+                if (!td) {
+                    // stationary FIELDS: sum_k (qa N_k + qb up_k) (u_k . n) = (qa StdVel + qb U_up) . n
 #pragma unroll
-    for (int d = 0; d < DIM; d++) U[d] = Us[d];
+                    for (int d = 0; d < DIM; d++) acc += (qa * std[d] + qb * U[d]) * n[d];
+                }
+                acc -= fr[O_GPN] * p.inv_rho;
+                if (p.has_source) {
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) acc += p.src[d] * n[d];
+                }
+                if (td) acc += oacc / p.dt;
+                cont = acc * ci;
+            }
+            fr[LR::O_F + P] = cont;
+        }
+    }
+    // ---- stage 3: convective upwind, transported velocity, Peclet blend ----
+    double w = 1.0;
     if (!p.stokes) {
         if (p.upw_conv != p.upw_stab) {
             double l2;
-            ok &= fused_upwind<E>(S, el, ip, p.upw_conv, fast, JI, n, xip, N, from, to, std, up, l2);
+            ok &= fused_upwind<E>(S, el, ip, p.upw_conv, fast, sref, n, xip, N, from, to, std, up, l2);
 #pragma unroll
             for (int d = 0; d < DIM; d++) U[d] = 0.0;
 #pragma unroll
@@ -547,25 +631,24 @@ NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip
 #pragma unroll
             for (int d = 0; d < DIM; d++) U[d] = w * U[d] + (1.0 - w) * std[d];
         }
+        if (want_def) {
+#pragma unroll
+            for (int d = 0; d < DIM; d++) fr[LR::O_F + d] += U[d] * prod;
+        }
     }
-    // ---- Jacobian coefficients ----
+    // ---- stage 4: Jacobian coefficients ----
     if (want_jac) {
         const double cw = prod * w, cpe = prod * (1.0 - w);
 #pragma unroll
-        for (int k = 0; k < NSH; k++) {
+        for (int k = 0; k < NSH; k++) {                          // convective diagonal (:430-468): the upwind shapes are scaled in place
             double D = 0.0;
             if (!p.stokes) { D = up[k] * cw; if (p.peclet) D += cpe * N[k]; }
-            fr[LR::O_DK + k] = D;
+            up[k] = D;
         }
-        // pressure column of the continuity row (:586-592): -G_k.n / diag, with G_k.n = dnt_k . (JI^T n)
+        // pressure column of the continuity row (:586-592): -G_k.n / diag, with G_k.n = dnt_k . (J^-T n)
         double mv[DIM];
 #pragma unroll
-        for (int i = 0; i < DIM; i++) {
-            double s = 0.0;
-#pragma unroll
-            for (int d = 0; d < DIM; d++) s += JI[d][i] * n[d];
-            mv[i] = s * (-1.0 * inv);
-        }
+        for (int i = 0; i < DIM; i++) mv[i] = fr[LR::O_PK + i] * (-1.0 * inv);
 #pragma unroll
         for (int k = 0; k < NSH; k++) {
             double s = 0.0;
@@ -575,87 +658,6 @@ NSB_HD bool fused_scvf(const FusedArgs& A, const FusedSmem<E>& S, int el, int ip
         }
 #pragma unroll
         for (int d = 0; d < DIM; d++) fr[LR::O_N + d] = n[d];
-    }
-    // ---- defect fluxes (:686-776): local gradient tensor first, mapped to global gradients once ----
-    if (want_def) {
-        double Lg[DIM][NF], L0[DIM][NF];
-#pragma unroll
-        for (int i = 0; i < DIM; i++)
-#pragma unroll
-            for (int q = 0; q < NF; q++) { Lg[i][q] = 0.0; L0[i][q] = 0.0; }
-        double pr = 0.0, oacc = 0.0;
-#pragma unroll
-        for (int k = 0; k < NSH; k++) {
-            double dl[DIM], uk[NF];
-#pragma unroll
-            for (int i = 0; i < DIM; i++) dl[i] = S.dnt[ip * C::DSTR + k * DIM + i];
-#pragma unroll
-            for (int q = 0; q < NF; q++) uk[q] = NSB_FCOL(S.us, k * NF + q);
-#pragma unroll
-            for (int i = 0; i < DIM; i++)
-#pragma unroll
-                for (int q = 0; q < NF; q++) Lg[i][q] += dl[i] * uk[q];
-            pr += N[k] * uk[P];
-            if (STAB != STAB_NONE && td) {                       // the closure uses solution(0) (:296, :646)
-                double s0k[NF], o = 0.0;
-#pragma unroll
-                for (int q = 0; q < NF; q++) s0k[q] = A.s0[(int64_t)nd[k] * NF + q];
-#pragma unroll
-                for (int i = 0; i < DIM; i++)
-#pragma unroll
-                    for (int q = 0; q < NF; q++) L0[i][q] += dl[i] * s0k[q];
-#pragma unroll
-                for (int d = 0; d < DIM; d++) o += A.s1[(int64_t)nd[k] * NF + d] * n[d];
-                oacc += N[k] * o;
-            }
-        }
-        double gv[DIM][DIM], gp[DIM], gp0[DIM];
-#pragma unroll
-        for (int d = 0; d < DIM; d++) {
-            double sp_ = 0.0, sp0_ = 0.0;
-#pragma unroll
-            for (int i = 0; i < DIM; i++) { sp_ += JI[d][i] * Lg[i][P]; sp0_ += JI[d][i] * L0[i][P]; }
-            gp[d] = sp_; gp0[d] = sp0_;
-#pragma unroll
-            for (int q = 0; q < DIM; q++) {
-                double sv_ = 0.0;
-#pragma unroll
-                for (int i = 0; i < DIM; i++) sv_ += JI[d][i] * Lg[i][q];
-                gv[q][d] = sv_;
-            }
-        }
-        double F[NF];
-#pragma unroll
-        for (int d1 = 0; d1 < DIM; d1++) {
-            double df = 0.0;
-#pragma unroll
-            for (int d2 = 0; d2 < DIM; d2++) df += gv[d1][d2] * n[d2];
-            if (!p.laplace) {
-#pragma unroll
-                for (int d2 = 0; d2 < DIM; d2++) df += gv[d2][d1] * n[d2];
-            }
-            double f = df * (-1.0) * nurho;
-            if (!p.stokes) f += U[d1] * prod;
-            f += pr * n[d1];
-            F[d1] = f;
-        }
-        double cont;
-        if (STAB == STAB_NONE) cont = sn * p.rho;
-        else {
-            double gpn = 0.0;
-#pragma unroll
-            for (int d = 0; d < DIM; d++) gpn += (td ? gp0[d] : gp[d]) * n[d];
-            acc -= gpn * p.inv_rho;
-            if (p.has_source) {
-#pragma unroll
-                for (int d = 0; d < DIM; d++) acc += p.src[d] * n[d];
-            }
-            if (td) acc += oacc / p.dt;
-            cont = acc * inv * p.rho;
-        }
-        F[P] = cont;
-#pragma unroll
-        for (int f = 0; f < NF; f++) fr[LR::O_F + f] = F[f];
     }
     return ok;
 }
@@ -1043,6 +1045,7 @@ __global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const Fus
     // rows phase, accumulation: lane = (node jj of the NPW the warp handles at a time, corner k)
     const int jj = lane / NSH, k = lane - jj * NSH;
     const bool lane_on = jj < NPW;
+    const int j0_lines = (max_cnt * C::DIM * NF * (int)sizeof(double) + 127) >> 7;
     auto load_hdr = [&](int pi) {
         PatchHdr H;
         const int4* hp = reinterpret_cast<const int4*>(A.hdr + pi);
@@ -1063,19 +1066,28 @@ __global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const Fus
         const int pn = pi + (int)gridDim.x;
         PatchHdr Hn = H;
         if (pn < A.n_patch) Hn = load_hdr(pn);                   // consumed after the flux phase
+        if (jac_a) {                                             // the J0 rows of the patch nodes are read at the end of the patch: pull them into L2 now
+            for (int i = tid; i < H.n_node * j0_lines; i += C::NT) {
+                const int nl = i / j0_lines, li = i - nl * j0_lines;
+                const PatchNode& Nd = T.nodes[nl];
+                if (li * 16 < Nd.cnt * (C::DIM * NF)) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.j0 + Nd.b0 * (C::DIM * NF) + li * 16));
+            }
+        }
+        if (pn < A.n_patch) {                                    // ... and the tables of the next patch (loaded right after the flux phase)
+            const int nb = (Hn.n_elem * NSH * 4 + 127) >> 7, nw = (Hn.n_work * 4 + 127) >> 7, na = (Hn.n_adj * 16 + 127) >> 7;
+            const char* q = nullptr;
+            if (tid < nb) q = reinterpret_cast<const char*>(A.pconn + (int64_t)Hn.elem0 * NSH) + tid * 128;
+            else if (tid < nb + nw) q = reinterpret_cast<const char*>(A.work + Hn.work0) + (tid - nb) * 128;
+            else if (tid < nb + nw + na) q = reinterpret_cast<const char*>(A.adj + Hn.adj0) + (tid - nb - nw) * 128;
+            else if (tid < nb + nw + na + 4) q = reinterpret_cast<const char*>(A.elems + Hn.elem0) + (tid - nb - nw - na) * 128;
+            if (q) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(q));
+        }
         if (flux_needed && !fused_flux<E, STAB, TD, GEOT>(A, S, H, tid)) atomicExch(A.errflag, 1);
         __syncthreads();                                         // records complete; element rows, work list and flags are dead
         if (pn < A.n_patch) {
             fused_load<E>(A, S, Hn, par ^ 1, tid);
             if (GEOT && flux_needed && tid < Hn.n_work)          // the next patch's geometry records: one 128-byte line per SCVF -> L2
                 asm volatile("prefetch.global.L2 [%0];\n" ::"l"(A.geo + (int64_t)(Hn.work0 + tid) * C::GEO));
-        }
-        // output assignment: warp w writes the rows of the nodes w, w + NWARP, ... ; their J0 rows are fetched into registers now
-        // (in flight during the accumulation), two nodes per round
-        FusedJ0<E> j0r[2];
-        if (jac_a) {
-#pragma unroll
-            for (int q = 0; q < 2; q++) if (warp + q * NWARP < H.n_node) fused_j0_prefetch<E>(A, T, warp + q * NWARP, lane, 32, j0r[q]);
         }
         // accumulation: the first warps take NPW nodes each
         for (int nl0 = warp * NPW; nl0 < H.n_node; nl0 += NWARP * NPW) {
@@ -1098,11 +1110,13 @@ __global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const Fus
         }
         __syncthreads();                                         // accumulators complete
         if (want_jac) {
-#pragma unroll
-            for (int q = 0; q < 2; q++)
-                if (warp + q * NWARP < H.n_node) fused_rows_out<E>(A, S, T, S.acc + (size_t)(warp + q * NWARP) * (C::NV * S.cntp), warp + q * NWARP, lane, 32, jac_a ? &j0r[q] : nullptr);
-            for (int nl = warp + 2 * NWARP; nl < H.n_node; nl += NWARP)
-                fused_rows_out<E>(A, S, T, S.acc + (size_t)nl * (C::NV * S.cntp), nl, lane, 32, nullptr);
+            // output: warp w writes the rows of the nodes w, w + NWARP, ...; the J0 words of a node (L2-resident: prefetched during
+            // the flux phase) are loaded in one batch before the node's rows are formed
+            for (int nl = warp; nl < H.n_node; nl += NWARP) {
+                FusedJ0<E> jr;
+                if (jac_a) fused_j0_prefetch<E>(A, T, nl, lane, 32, jr);
+                fused_rows_out<E>(A, S, T, S.acc + (size_t)nl * (C::NV * S.cntp), nl, lane, 32, jac_a ? &jr : nullptr);
+            }
         }
         if (pn >= A.n_patch) break;
         pi = pn; H = Hn; par ^= 1;
