@@ -24,6 +24,7 @@ struct MeshDev {
     const int32_t* node_order;  // Z-curve traversal order of the nodes (rows kernel), may be null
     int32_t l2_hints;           // rows kernel of the split path: L2 eviction-priority hints on the bulk copies
     int32_t ticket_group;       // rows kernel of the split path: nodes per atomic ticket
+    const uint8_t* elem_fast;   // hex: 1 = element is star-shaped w.r.t. its ips (predicted-side ray search allowed), may be null
 };
 
 enum { SC_COLORED = 1, SC_ATOMIC = 2, SC_LOCAL = 3 };

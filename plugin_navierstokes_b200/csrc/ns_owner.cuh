@@ -87,7 +87,8 @@ NSB_DEV double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const doub
 // thread's shared column xs. Same tests as side_ray_cut (ns_fv1.cuh), first hit in reference order wins.
 template <int E, int BS>
 NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const double* from, const double* dir,
-                             int& side_out, double* gcut, double* lcut, const int* __restrict__ sidetab, const double* __restrict__ cortab)
+                             int& side_out, double* gcut, double* lcut, const int* __restrict__ sidetab, const double* __restrict__ cortab,
+                             int pred_side = -1)
 {
     constexpr int DIM = ET<E>::DIM, NSIDE = ET<E>::NSIDE;
     constexpr double S = NSB_RAY_SMALL;
@@ -123,17 +124,24 @@ NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const doubl
         const double dn2 = dotv<3>(dir, dir);
         constexpr int TPS = (E == E_HEX) ? 2 : 1;
         const unsigned amask = __activemask();
-        for (int s = 0; s < NSIDE; s++) {
+        // hex, element star-shaped w.r.t. its ips (ns_fused.cuh, fused_star_shaped): the side predicted from the ray direction in
+        // reference coordinates is confirmed with the exact tests first; exactly one boundary triangle is hit in that case, so the
+        // ordered search below (run for the lanes whose confirmation failed) would return the same side
+        const bool use_pred = __any_sync(amask, pred_side >= 0);
+        for (int s = use_pred ? -1 : 0; s < NSIDE; s++) {
+            if (s >= 0 && __all_sync(amask, found)) break;
             // a quadrilateral side is cut as the triangles (p0,p1,p2), (p0,p2,p3): both share r = from - x(p0), q = r x dir
             // and the diagonal edge; evaluating them together halves the dependent chains (same operations per value)
-            const int p0 = tab::C_SIDE[E][s][0];
+            const int sx = s < 0 ? (pred_side >= 0 ? pred_side : 0) : s;       // lane-dependent in the prediction round
+            const bool lane_try = s >= 0 || pred_side >= 0;
+            const int p0 = s < 0 ? sidetab[sx * 4] : tab::C_SIDE[E][s][0];
             double ed[TPS + 1][3], r[3], q[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 const double x0 = NSB_COL(xs, p0 * 3 + d);
                 r[d] = from[d] - x0;
 #pragma unroll
-                for (int j = 0; j <= TPS; j++) ed[j][d] = NSB_COL(xs, tab::C_SIDE[E][s][1 + j] * 3 + d) - x0;
+                for (int j = 0; j <= TPS; j++) ed[j][d] = NSB_COL(xs, (s < 0 ? sidetab[sx * 4 + 1 + j] : tab::C_SIDE[E][s][1 + j]) * 3 + d) - x0;
             }
             cross3(q, r, dir);
             double eq[TPS + 1];
@@ -147,12 +155,11 @@ NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const doubl
                 const double t_n = dotv<3>(r, nrm);
                 const double b1n = eq[kk + 1], b2n = -eq[kk];
                 const double sg = det > 0.0 ? 1.0 : -1.0, ad = fabs(det);
-                const bool hit = !found && det * det > (S * S) * dn2 * dotv<3>(nrm, nrm) &&
+                const bool hit = lane_try && !found && det * det > (S * S) * dn2 * dotv<3>(nrm, nrm) &&
                                  b1n * sg >= -S * ad && b2n * sg >= -S * ad && (b1n + b2n) * sg <= (1.0 + S) * ad && t_n * sg <= 0.0;
-                if (hit) { found = true; best = s * TPS + kk; tn = t_n; n1 = b1n; n2 = b2n; bdet = det; }
+                if (hit) { found = true; best = sx * TPS + kk; tn = t_n; n1 = b1n; n2 = b2n; bdet = det; }
             }
-            // the first hit wins (sides in reference order): stop as soon as every element of the warp has one
-            if (__all_sync(amask, found)) break;
+            // the first hit wins (sides in reference order): the loop head stops as soon as every element of the warp has one
         }
         if (!found) return false;
         const double ibd = 1.0 / bdet;                            // one reciprocal instead of three dependent divisions
@@ -173,7 +180,7 @@ NSB_DEV bool ray_cut_uniform(const double* __restrict__ xs, int tid, const doubl
 template <int E, int BS>
 NSB_DEV bool upwind_uniform(int type, const double* __restrict__ xs, int tid, const double* n, const double* xip,
                             const double* N, int from, int to, const double* vel, double* up, double& len,
-                            const int* __restrict__ sidetab, const double* __restrict__ cortab)
+                            const int* __restrict__ sidetab, const double* __restrict__ cortab, int pred_side = -1)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
     if (type == UPW_NO) {
@@ -197,7 +204,7 @@ NSB_DEV bool upwind_uniform(int type, const double* __restrict__ xs, int tid, co
     for (int k = 0; k < NSH; k++) up[k] = 0.0;
     if (sqrt(dotv<DIM>(vel, vel)) < 1e-14) { len = 1.0; return true; }      // upwind.cpp:407-413, 531-537
     int side = 0; double gc[DIM], lc[DIM];
-    if (!ray_cut_uniform<E, BS>(xs, tid, xip, vel, side, gc, lc, sidetab, cortab)) { len = 1.0; return false; }
+    if (!ray_cut_uniform<E, BS>(xs, tid, xip, vel, side, gc, lc, sidetab, cortab, pred_side)) { len = 1.0; return false; }
     constexpr int NSC = (DIM == 2) ? 2 : (E == E_TET ? 3 : 4);
     if (type == UPW_SKEWED) {                                    // GetNodeNextToCut, upwind.cpp:337-379
         double mn = 1.79769313486231570e308; int bestc = 0;
@@ -296,6 +303,24 @@ NSB_DEV void ip_geometry_col(const double* __restrict__ xs, int tid, int ip, con
 }
 
 // lean SCVF record of the split path (ns_split.cuh): [F | n | cK | dK | pK = -G_k.n / diag]
+
+// hex: side of the reference element the ray from the ip along -dir leaves through, predicted in reference coordinates
+// (s = J^-1 dir; going upstream the first plane xi_i in {0, 1} reached); see fused_ray_cut in ns_fused.cuh
+NSB_DEV int predict_hex_side(const double (*JI)[3], const double* dir, int ip)
+{
+    float best = -3.0e38f; int bs = -1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float si = (float)(JI[0][i] * dir[0] + JI[1][i] * dir[1] + JI[2][i] * dir[2]);
+        const float xi = (float)tab::LIP[E_HEX][ip][i];
+        if (si != 0.0f) {
+            const float t = si > 0.0f ? -xi / si : (1.0f - xi) / si;
+            const int sd = i == 0 ? (si > 0.0f ? 4 : 2) : (i == 1 ? (si > 0.0f ? 1 : 3) : (si > 0.0f ? 0 : 5));
+            if (t > best) { best = t; bs = sd; }
+        }
+    }
+    return bs;
+}
 
 // LPE = lanes per element: the SCVFs of an element are dealt to LPE adjacent lanes (ip = ii * LPE + sub), the element's
 // unknowns / coordinates live once in a shared column used by all of them. LPE = 1 is the thread-per-element layout.
@@ -415,13 +440,21 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
         double up[NSH], dnm[NSH], uplen = 1.0, dnlen = 1.0;
 #pragma unroll
         for (int k = 0; k < NSH; k++) { up[k] = 0.0; dnm[k] = 0.0; }
+        // predicted cut side of the upwind ray (hex elements that are star-shaped w.r.t. their ips, flagged once per mesh)
+        int pred_up = -1, pred_dn = -1;
+        if constexpr (E == E_HEX) {
+            if ((want_def || (LEAN && want_jac)) && !p.stokes && m.elem_fast && m.elem_fast[e] && (p.upw_stab >= UPW_SKEWED || p.upw_conv >= UPW_SKEWED)) {
+                pred_up = predict_hex_side(JI, std, ip);
+                if (FLOW) { double ng[3] = {-std[0], -std[1], -std[2]}; pred_dn = predict_hex_side(JI, ng, ip); }
+            }
+        }
         if (!p.stokes) {
-            ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, std, up, uplen, sidetab, cortab);
+            ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, std, up, uplen, sidetab, cortab, pred_up);
             if (FLOW) {                                          // update_downwind, upwind_interface.h:157-165
                 double neg[DIM], dn[NSH];
 #pragma unroll
                 for (int d = 0; d < DIM; d++) neg[d] = -1.0 * std[d];
-                ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, neg, dn, dnlen, sidetab, cortab);
+                ok &= upwind_uniform<E, BS>(p.upw_stab, xs, tid, n, xip, N, from, to, neg, dn, dnlen, sidetab, cortab, pred_dn);
 #pragma unroll
                 for (int k = 0; k < NSH; k++) dnm[k] = dn[k] - up[k];
             }
@@ -495,7 +528,7 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
         if (!p.stokes) {
             if (p.upw_conv != p.upw_stab) {
                 double l2;
-                ok &= upwind_uniform<E, BS>(p.upw_conv, xs, tid, n, xip, N, from, to, std, up, l2, sidetab, cortab);
+                ok &= upwind_uniform<E, BS>(p.upw_conv, xs, tid, n, xip, N, from, to, std, up, l2, sidetab, cortab, pred_up);
 #pragma unroll
                 for (int d = 0; d < DIM; d++) U[d] = 0.0;
 #pragma unroll

@@ -325,7 +325,13 @@ static cudaError_t launch_scvvol(nsb_ctx* c)
 static int setup_fused(nsb_ctx* c, const int32_t* conn, const double* coords, const EntityGraph& g, const std::vector<uint8_t>& emap)
 {
     c->fused_ok = false; c->fused_note.clear();
-    { const char* ev = getenv("NSB_FUSED"); if (ev && atoi(ev) == 0) { c->fused_note = "disabled by NSB_FUSED=0"; return NSB_OK; } }
+    // NSB_FUSED: unset = automatic (the fused kernel serves the 2-D element types, where it is faster than the two-kernel split
+    // path: quad 1024^2 1.15 vs 1.44 ms, tri 1.72 vs 2.01 ms; for hex / tet the split path is faster),
+    // 1 = every element type, 0 = never
+    { const char* ev = getenv("NSB_FUSED");
+      const int modef = ev ? atoi(ev) : -1;
+      if (modef == 0) { c->fused_note = "disabled by NSB_FUSED=0"; return NSB_OK; }
+      if (modef < 0 && (c->elem == NSB_HEX || c->elem == NSB_TET)) { c->fused_note = "automatic choice: split path for 3-D elements (NSB_FUSED=1 overrides)"; return NSB_OK; } }
     size_t smem = 0; PatchCaps caps;
     switch (c->elem) { case 0: smem = fused_smem_bytes_0(g.max_cnt); caps = fused_caps_0(); break; case 1: smem = fused_smem_bytes_1(g.max_cnt); caps = fused_caps_1(); break;
                        case 2: smem = fused_smem_bytes_2(g.max_cnt); caps = fused_caps_2(); break; default: smem = fused_smem_bytes_3(g.max_cnt); caps = fused_caps_3(); }
@@ -347,11 +353,6 @@ static int setup_fused(nsb_ctx* c, const int32_t* conn, const double* coords, co
     node_volume_kernel<<<(unsigned)((c->n_node + 255) / 256), 256, 0, c->stream>>>(c->n_node, c->d_adj_ptr, c->d_adj, c->d_scvvol, c->d_nodevol);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
-    if (c->elem == NSB_HEX && !(getenv("NSB_RAYFAST") && atoi(getenv("NSB_RAYFAST")) == 0)) {
-        CUDA_TRY(c, dev_malloc(c, &c->d_elem_fast, (size_t)c->n_elem));
-        CUDA_TRY(c, launch_ray_safety_3(c->n_elem, c->d_conn, c->d_coords, c->d_elem_fast, c->stream));
-        c->launches++;
-    }
     c->fused_ok = true;
     return NSB_OK;
 }
@@ -385,6 +386,12 @@ extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_n
     { std::vector<int32_t> zo; morton_order(n_node, dim, coords, zo); CUDA_TRY(c, upload(c, &c->d_node_order, zo.data(), zo.size())); }
     CUDA_TRY(c, dev_malloc(c, &c->d_scvvol, (size_t)n_elem * nsh * sizeof(double)));
     CUDA_TRY(c, launch_scvvol(c));
+    if (c->elem == NSB_HEX && !(getenv("NSB_RAYFAST") && atoi(getenv("NSB_RAYFAST")) == 0)) {
+        // per-element flag: star-shaped w.r.t. every ip -> the upwind ray search may start with the predicted side
+        CUDA_TRY(c, dev_malloc(c, &c->d_elem_fast, (size_t)c->n_elem));
+        CUDA_TRY(c, launch_ray_safety_3(c->n_elem, c->d_conn, c->d_coords, c->d_elem_fast, c->stream));
+        c->launches++;
+    }
     { const int rcf = setup_fused(c, conn, coords, g, emap); if (rcf) return rcf; }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->h_brow.swap(g.brow); c->h_bcol.swap(g.bcol);
@@ -484,6 +491,7 @@ static MeshDev mesh_view(const nsb_ctx* c)
     m.brow = c->d_brow; m.emap = c->d_emap; m.adj_ptr = c->d_adj_ptr; m.adj = c->d_adj; m.max_cnt = c->max_cnt;
     m.node_order = getenv("NSB_ZORDER") ? c->d_node_order : nullptr;   // opt-in: measured neutral on B200 (profiles/)
     { const char* ev = getenv("NSB_L2HINT"); m.l2_hints = ev ? atoi(ev) : 0; }
+    m.elem_fast = c->d_elem_fast;
     { const char* ev = getenv("NSB_TICKET_GROUP"); const int v = ev ? atoi(ev) : 4; m.ticket_group = v >= 1 ? v : 4; }
     return m;
 }

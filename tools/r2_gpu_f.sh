@@ -1,0 +1,11 @@
+#!/bin/bash
+T=${1:-r2f}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/${T}_gputest.txt
+NSB_FUSED=1 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/${T}_gputest_fused.txt
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
+NSB_RAYFAST=0 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/${T}_bench_norayfast.json 2>> gpurun_out/${T}_bench.err
+timeout 900 python tools/quick_bench.py 96 > gpurun_out/${T}_quick96.txt 2>&1
+NSB_FUSED=1 timeout 900 python tools/quick_bench.py 96 > gpurun_out/${T}_quick96_fused.txt 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fv1_flux -s 1 -c 1 -o gpurun_out/${T}_flux_n128 python bench.py --cells 128 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/${T}_ncu.log 2>&1
+echo done
