@@ -65,7 +65,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
     if (k.what & (W_JAC_A | W_DEF_A)) {
-        const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * BS + NIP * NSH * DIM + NIP * NSH + 24) + sizeof(int) * (NIP * 12 + 24);
+        const size_t smem_a = sizeof(double) * (NSB_CSTR(E) * BS + NIP * NSH * DIM + NIP * NSH + 24) + sizeof(int) * (NIP * 12 + 24);
         static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 2; }();
         auto ka = minb == 2 ? fv1_flux_kernel<E, STAB, EXACT, BS, 2> : minb == 4 ? fv1_flux_kernel<E, STAB, EXACT, BS, 4> : fv1_flux_kernel<E, STAB, EXACT, BS, 3>;
         e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
@@ -116,7 +116,7 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
         static const int FMB = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 0; }();
         auto go = [&](auto ka, int lpe) -> cudaError_t {
             const int epb = BS / lpe;
-            const size_t smem_a = sizeof(double) * ((NSH * DIM + NSH + NSH * NF) * epb + NIP * (NSH * DIM + 1) + NIP * (NSH + 1) + 24) + sizeof(int) * (NIP * 12 + 24);
+            const size_t smem_a = sizeof(double) * (NSB_CSTR(E) * epb + NIP * (NSH * DIM + 1) + NIP * (NSH + 1) + 24) + sizeof(int) * (NIP * 12 + 24);
             cudaError_t e2 = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
             if (e2 != cudaSuccess) return e2;
             ka<<<(unsigned)((m.n_elem + epb - 1) / epb), BS, smem_a, st>>>(k, m, u, s0, s1, rec, d_err);

@@ -81,7 +81,10 @@ template <int E, bool FLOWREC, bool EXACT> struct FluxRec {
 NSB_DEV double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // thread-private column in shared memory: element i of the calling thread
-#define NSB_COL(base, i) (base)[(i) * BS + tid]
+// element-major rows with an odd stride: the lanes that share an element (LPE > 1) read different corners from different banks,
+// lanes of different elements read the same corner from different banks (measured: the [i * BS + tid] layout gave 4-way conflicts)
+#define NSB_CSTR(E_) ((ET<E_>::NSH * (2 * ET<E_>::DIM + 2)) | 1)
+#define NSB_COL(base, i) (base)[(i) + tid * NSB_CSTR(E)]
 
 // ray / side intersection with warp-uniform side tables (constant memory); corner coordinates in the
 // thread's shared column xs. Same tests as side_ray_cut (ns_fv1.cuh), first hit in reference order wins.
@@ -343,10 +346,10 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
     constexpr int L_N = NF, L_CK = (NF + DIM + 1) & ~1, L_DK = L_CK + NSHP, L_PK = L_DK + NSHP;   // = LeanRec<E> offsets
     constexpr int LRSZ = (L_PK + NSHP + 3) & ~3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* xs = reinterpret_cast<double*>(smem_raw);            // [NSH*DIM][BS]
-    double* vs = xs + NSH * DIM * BS;                            // [NSH][BS]
-    double* us = vs + NSH * BS;                                  // [NSH*NF][BS] nodal unknowns (the `u` argument)
-    double* dnt = us + NSH * NF * BS;                            // [NIP][DSTR] local shape gradients at the ips
+    double* xs = reinterpret_cast<double*>(smem_raw);            // [BS][NSB_CSTR]: corner coordinates | SCV volumes | nodal unknowns (the `u` argument)
+    double* vs = xs + NSH * DIM;
+    double* us = vs + NSH;
+    double* dnt = xs + NSB_CSTR(E) * BS;                         // [NIP][DSTR] local shape gradients at the ips
     double* Nt = dnt + NIP * DSTR;                               // [NIP][NSTR] shape values at the ips
     double* cortab = Nt + NIP * NSTR;                            // [8][3]      reference corners (tab::CORNER)
     int* sidetab = reinterpret_cast<int*>(cortab + 24);          // [6][4]      corners of the sides (tab::SIDE)
