@@ -116,7 +116,8 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
         static const int FMB = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 0; }();
         auto go = [&](auto ka, int lpe) -> cudaError_t {
             const int epb = BS / lpe;
-            const size_t smem_a = sizeof(double) * (NSB_CSTR(E) * epb + NIP * (NSH * DIM + 1) + NIP * (NSH + 1) + 24) + sizeof(int) * (NIP * 12 + 24);
+            size_t smem_a = sizeof(double) * (NSB_CSTR(E) * epb + NIP * (NSH * DIM + 1) + NIP * (NSH + 1) + 24) + sizeof(int) * (NIP * 12 + 24);
+            if (lpe > 1) smem_a += 16 + sizeof(double) * BS * (LeanRec<E>::SZ + 2);      // staged lean records (one slot per lane)
             cudaError_t e2 = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
             if (e2 != cudaSuccess) return e2;
             ka<<<(unsigned)((m.n_elem + epb - 1) / epb), BS, smem_a, st>>>(k, m, u, s0, s1, rec, d_err);

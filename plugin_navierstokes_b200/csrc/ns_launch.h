@@ -36,6 +36,14 @@ struct PatchCaps;
     cudaError_t launch_ray_safety_##E(int64_t n_elem, const int32_t* conn, const double* coords, uint8_t* elem_fast, cudaStream_t st);
 NSB_DECLF(0) NSB_DECLF(1) NSB_DECLF(2) NSB_DECLF(3)
 #undef NSB_DECLF
+struct TileArgs;
+#define NSB_DECLT(E)                                                                                  \
+    PatchCaps tile_caps_##E();                                                                        \
+    size_t tile_smem_bytes_##E();                                                                     \
+    int tile_max_cnt_##E();                                                                           \
+    cudaError_t launch_tile_##E(const TileArgs& A, cudaStream_t st, int sm_count);
+NSB_DECLT(2) NSB_DECLT(3)
+#undef NSB_DECLT
 struct FvcrDev;
 cudaError_t launch_fvcr_0(int sc, const KParams& k, const FvcrDev& m, const int32_t* list, int64_t n_list, const double* u,
                           double* val, double* def, int* d_err, cudaStream_t st);

@@ -79,6 +79,7 @@ template <int E, bool FLOWREC, bool EXACT> struct FluxRec {
 };
 
 NSB_DEV double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+NSB_DEV unsigned smem_u32(const void* q) { return (unsigned)__cvta_generic_to_shared(q); }
 
 // thread-private column in shared memory: element i of the calling thread
 // element-major rows with an odd stride: the lanes that share an element (LPE > 1) read different corners from different banks,
@@ -354,6 +355,13 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
     double* cortab = Nt + NIP * NSTR;                            // [8][3]      reference corners (tab::CORNER)
     int* sidetab = reinterpret_cast<int*>(cortab + 24);          // [6][4]      corners of the sides (tab::SIDE)
     int* iptab = sidetab + 24;                                   // [NIP][12]   from, to, face corners (LPE > 1)
+    // STAGED (split path, LPE > 1): the lean record is assembled in a lane-private shared-memory slot (stride padded by 16 B:
+    // the 16-byte stores of a quarter-warp hit disjoint banks) and leaves the SM as ONE 256-byte bulk store (cp.async.bulk
+    // shared -> global, SASS UBLKCP). Written straight to global memory the 16-byte stores of a warp touch 32 different sectors
+    // each: the LSU data pipe was 84 % busy with them (ncu, profiles/r2_ncu_summary.md).
+    constexpr bool STAGED = LEAN && LPE > 1;
+    constexpr int SSTR = LRSZ + 2;
+    double* stg = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(iptab + NIP * 12) + 15) & ~(uintptr_t)15);
     for (int i = threadIdx.x; i < 24; i += NT) {
         cortab[i] = tab::CORNER[E][i / 3][i % 3];
         const int v = tab::SIDE[E][i / 4][i % 4];
@@ -422,8 +430,13 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
 
     for (int ii = 0; ii < NIP / LPE; ii++) {
         const int ip = ii * LPE + sub;
-        double* fr = LEAN ? rec + (e * NIP + ip) * LRSZ                     // lean record of the split path
-                          : rec + (e * NIP + ip) * (R::SZ + FR::SZ) + R::SZ;      // flux part of the combined SCVF record
+        double* const frg = LEAN ? rec + (e * NIP + ip) * LRSZ                     // lean record of the split path
+                                 : rec + (e * NIP + ip) * (R::SZ + FR::SZ) + R::SZ;      // flux part of the combined SCVF record
+        double* fr = frg;
+        if constexpr (STAGED) {
+            if (ii > 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the previous record has left the slot
+            fr = stg + threadIdx.x * SSTR;
+        }
         const int from = SMT ? iptab[ip * 12] : tab::C_EDGE[E][ip][0], to = SMT ? iptab[ip * 12 + 1] : tab::C_EDGE[E][ip][1];
         double n[DIM], xip[DIM], ds = 0.0, JI[DIM][DIM];
         ip_geometry_col<E, BS, DSTR, SMT>(xs, tid, ip, cen, dnt, n, xip, ds, want_def || (LEAN && want_jac), JI, iptab);
@@ -710,7 +723,13 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
 #pragma unroll
             for (int f = 0; f < NF; f++) fr[FR::O_F + f] = F[f];
         }
+        if constexpr (STAGED) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(frg), "r"(smem_u32(fr)), "r"((unsigned)(LRSZ * sizeof(double))) : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
     }
+    if constexpr (STAGED) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     if (!ok) atomicExch(errflag, 1);
 }
 
@@ -751,7 +770,6 @@ template <int E> __host__ __device__ constexpr size_t rows_tab_bytes(int max_cnt
 }
 
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on a warp-private mbarrier ----
-NSB_DEV unsigned smem_u32(const void* q) { return (unsigned)__cvta_generic_to_shared(q); }
 NSB_DEV void mbar_init(unsigned long long* bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");

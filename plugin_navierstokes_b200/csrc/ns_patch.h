@@ -10,7 +10,9 @@
 //   nodes[]  : global node id, first value index of its block row, row length, range of its adjacency entries
 //   elems[]  : global element ids of the elements touching a patch node (ascending)
 //   pconn[]  : global node ids of their corners (saves one dependent load in the kernel)
-//   work[]   : one entry per SCVF to evaluate: local element | ip << 8 | record slot << 12
+//   work[]   : one entry per SCVF to evaluate: local element | ip << 8 | record slot << 12, sorted by ip (a warp of the flux
+//              phase then reads the reference tables of one or two ips)
+//   lnodes[] / ecorner[] (tile kernel only): the patch's local nodes and the element -> local node table
 //   adj[]    : per (patch node, adjacent element), in the order of the global adjacency list (ascending element id =
 //              the summation order of every owner-computes kernel in this library): record slots of the NINC incident
 //              SCVFs, local corner, CSR slots of the element's corners in the node's block row
@@ -26,13 +28,14 @@
 
 namespace nsb {
 
-struct PatchHdr { int32_t node0, n_node, elem0, n_elem, work0, n_work, adj0, n_adj; };           // 32 B
+struct PatchHdr { int32_t node0, n_node, elem0, n_elem, work0, n_work, adj0, n_adj, lnode0, n_lnode, pad0, pad1; };   // 48 B
 struct PatchNode { int64_t b0; int32_t node; uint16_t adj_off; uint8_t adj_cnt, cnt; };          // 16 B
 struct PatchAdj { uint16_t slot[3]; uint8_t la, self; uint8_t emap[8]; };                        // 16 B; la: bits 0-2 local corner, bit 4+t: SCVF t enters the node (sign -1)
-static_assert(sizeof(PatchHdr) == 32 && sizeof(PatchNode) == 16 && sizeof(PatchAdj) == 16, "table layouts are read as 16-byte words on the device");
+static_assert(sizeof(PatchHdr) == 48 && sizeof(PatchNode) == 16 && sizeof(PatchAdj) == 16, "table layouts are read as 16-byte words on the device");
 
 struct PatchCaps {
     int max_work, max_elem, max_node, max_adj;
+    int max_lnode = 0;                 // > 0: build the local-node tables (lnodes / ecorner) of the tile kernel, at most this many per patch (<= 256)
     int tile[3];                       // tile edge lengths in grid cells (estimated spacing) the nodes are binned into
 };
 
@@ -40,6 +43,8 @@ struct PatchPlan {
     std::vector<PatchHdr> hdr;
     std::vector<PatchNode> nodes;
     std::vector<int32_t> elems, pconn;
+    std::vector<int32_t> lnodes;       // tile kernel (ns_tile.cuh): global ids of the patch's local nodes (every corner of a patch element), ascending
+    std::vector<uint8_t> ecorner;      // ... and the local node id of corner k of patch element el, [elems][nsh]
     std::vector<uint32_t> work;
     std::vector<PatchAdj> adj;
     int64_t n_scvf_evals = 0;          // = work.size(); / (n_elem * nip) = redundancy of the flux phase
@@ -153,8 +158,14 @@ inline bool build_patch_plan(int elem, int64_t n_elem, int64_t n_node, const int
             int64_t nwork = 0;
             for (int32_t e : elems) for (int ip = 0; ip < nip; ip++)
                 if (in_patch(conn[(int64_t)e * nsh + T.edge[ip][0]]) || in_patch(conn[(int64_t)e * nsh + T.edge[ip][1]])) nwork++;
+            std::vector<int32_t> ln;                           // local nodes (tile kernel)
+            if (caps.max_lnode > 0) {
+                for (int32_t e : elems) for (int k = 0; k < nsh; k++) ln.push_back(conn[(int64_t)e * nsh + k]);
+                std::sort(ln.begin(), ln.end());
+                ln.erase(std::unique(ln.begin(), ln.end()), ln.end());
+            }
             const bool fits = nwork <= caps.max_work && (int64_t)elems.size() <= caps.max_elem && (int64_t)nd.size() <= caps.max_node &&
-                              nadj <= caps.max_adj && maxadj <= 255;
+                              nadj <= caps.max_adj && maxadj <= 255 && (int64_t)ln.size() <= std::min(caps.max_lnode > 0 ? caps.max_lnode : 256, 256);
             if (!fits) {
                 if (nd.size() == 1) { L.err = "a single node exceeds the patch capacities (valence too high for the fused kernel)"; return; }
                 // split at the median of the axis with the largest extent
@@ -179,20 +190,28 @@ inline bool build_patch_plan(int elem, int64_t n_elem, int64_t n_node, const int
             H.node0 = (int32_t)P.nodes.size(); H.n_node = (int32_t)nd.size();
             H.elem0 = (int32_t)P.elems.size(); H.n_elem = (int32_t)elems.size();
             H.work0 = (int32_t)P.work.size(); H.adj0 = (int32_t)P.adj.size();
+            H.lnode0 = (int32_t)P.lnodes.size(); H.n_lnode = (int32_t)ln.size(); H.pad0 = H.pad1 = 0;
+            P.lnodes.insert(P.lnodes.end(), ln.begin(), ln.end());
             // work items, slot = running index; slot of (local element, ip) for the adjacency table
             std::vector<uint16_t> slot_of(elems.size() * nip, 0xffff);
             uint32_t nw = 0;
             for (size_t el = 0; el < elems.size(); el++) {
                 const int64_t e = elems[el];
                 P.elems.push_back((int32_t)e);
-                for (int k = 0; k < nsh; k++) P.pconn.push_back(conn[e * nsh + k]);
-                for (int ip = 0; ip < nip; ip++)
+                for (int k = 0; k < nsh; k++) {
+                    P.pconn.push_back(conn[e * nsh + k]);
+                    if (caps.max_lnode > 0) P.ecorner.push_back((uint8_t)(std::lower_bound(ln.begin(), ln.end(), conn[e * nsh + k]) - ln.begin()));
+                }
+            }
+            for (int ip = 0; ip < nip; ip++)
+                for (size_t el = 0; el < elems.size(); el++) {
+                    const int64_t e = elems[el];
                     if (in_patch(conn[e * nsh + T.edge[ip][0]]) || in_patch(conn[e * nsh + T.edge[ip][1]])) {
                         slot_of[el * nip + ip] = (uint16_t)nw;
                         P.work.push_back((uint32_t)el | ((uint32_t)ip << 8) | (nw << 12));
                         nw++;
                     }
-            }
+                }
             H.n_work = (int32_t)nw;
             uint32_t aoff = 0;
             for (int32_t n : nd) {
@@ -232,12 +251,14 @@ inline bool build_patch_plan(int elem, int64_t n_elem, int64_t n_node, const int
         if (!used[t]) continue;
         Local& L = locals[t];
         if (!L.err.empty()) { err = L.err; return false; }
-        const int32_t n0 = (int32_t)out.nodes.size(), e0 = (int32_t)out.elems.size(), w0 = (int32_t)out.work.size(), a0 = (int32_t)out.adj.size();
+        const int32_t n0 = (int32_t)out.nodes.size(), e0 = (int32_t)out.elems.size(), w0 = (int32_t)out.work.size(), a0 = (int32_t)out.adj.size(), l0 = (int32_t)out.lnodes.size();
         if ((double)out.adj.size() + L.p.adj.size() >= 2147483647.0 || (double)out.work.size() + L.p.work.size() >= 2147483647.0) { err = "grid too large for 32-bit patch tables"; return false; }
-        for (PatchHdr H : L.p.hdr) { H.node0 += n0; H.elem0 += e0; H.work0 += w0; H.adj0 += a0; out.hdr.push_back(H); }
+        for (PatchHdr H : L.p.hdr) { H.node0 += n0; H.elem0 += e0; H.work0 += w0; H.adj0 += a0; H.lnode0 += l0; out.hdr.push_back(H); }
         out.nodes.insert(out.nodes.end(), L.p.nodes.begin(), L.p.nodes.end());
         out.elems.insert(out.elems.end(), L.p.elems.begin(), L.p.elems.end());
         out.pconn.insert(out.pconn.end(), L.p.pconn.begin(), L.p.pconn.end());
+        out.lnodes.insert(out.lnodes.end(), L.p.lnodes.begin(), L.p.lnodes.end());
+        out.ecorner.insert(out.ecorner.end(), L.p.ecorner.begin(), L.p.ecorner.end());
         out.work.insert(out.work.end(), L.p.work.begin(), L.p.work.end());
         out.adj.insert(out.adj.end(), L.p.adj.begin(), L.p.adj.end());
         out.max_adj_per_node = std::max(out.max_adj_per_node, L.p.max_adj_per_node);

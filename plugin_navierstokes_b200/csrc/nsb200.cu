@@ -19,6 +19,7 @@
 #include "ns_fvcr.cuh"
 #include "ns_graph.h"
 #include "ns_fused.cuh"
+#include "ns_tile.cuh"
 
 using namespace nsb;
 
@@ -89,6 +90,9 @@ struct nsb_ctx {
     double* d_geo = nullptr; int geo_diff_len = -1;   // static SCVF geometry records of the fused kernel (per diffusion-length type)
     int32_t n_patch = 0; int max_adj = 0;
     int64_t scvf_evals = 0, patch_table_bytes = 0;
+    // fused tile kernel (ns_tile.cuh, 3-D element types): the patch tables above built with the tile capacities + local-node tables
+    bool tile_ok = false;
+    int32_t* d_plnodes = nullptr; uint8_t* d_pecorner = nullptr;
 };
 
 static int set_err(nsb_ctx* c, int code, const char* fmt, ...)
@@ -160,6 +164,7 @@ static void free_mesh(nsb_ctx* c)
     cudaFree(c->d_jloc); cudaFree(c->d_dloc); cudaFree(c->d_j0);
     cudaFree(c->d_phdr); cudaFree(c->d_pnodes); cudaFree(c->d_pelems); cudaFree(c->d_pconn); cudaFree(c->d_pwork); cudaFree(c->d_padj);
     cudaFree(c->d_nodevol); cudaFree(c->d_elem_fast); cudaFree(c->d_geo);
+    cudaFree(c->d_plnodes); cudaFree(c->d_pecorner); c->d_plnodes = nullptr; c->d_pecorner = nullptr; c->tile_ok = false;
     c->d_geo = nullptr; c->geo_diff_len = -1;
     c->d_phdr = nullptr; c->d_pnodes = nullptr; c->d_pelems = c->d_pconn = nullptr; c->d_pwork = nullptr; c->d_padj = nullptr;
     c->d_nodevol = nullptr; c->d_elem_fast = nullptr; c->fused_ok = false; c->n_patch = 0; c->scvf_evals = 0; c->patch_table_bytes = 0;
@@ -216,7 +221,7 @@ extern "C" int nsb_query(const nsb_ctx* c, int what, double* out)
     switch (what) {
         case NSB_Q_DEVICE_BYTES: *out = (double)c->dev_bytes; break;
         case NSB_Q_SETUP_SECONDS: *out = c->setup_seconds; break;
-        case NSB_Q_FUSED: *out = c->fused_ok ? 1.0 : 0.0; break;
+        case NSB_Q_FUSED: *out = c->fused_ok ? 1.0 : (c->tile_ok ? 2.0 : 0.0); break;
         case NSB_Q_PATCHES: *out = (double)c->n_patch; break;
         case NSB_Q_SCVF_EVALS: *out = (double)c->scvf_evals; break;
         case NSB_Q_PATCH_TABLE_BYTES: *out = (double)c->patch_table_bytes; break;
@@ -324,17 +329,25 @@ static cudaError_t launch_scvvol(nsb_ctx* c)
 // cannot handle leaves fused_ok = false (the two-kernel split path is used) and the reason in fused_note.
 static int setup_fused(nsb_ctx* c, const int32_t* conn, const double* coords, const EntityGraph& g, const std::vector<uint8_t>& emap)
 {
-    c->fused_ok = false; c->fused_note.clear();
-    // NSB_FUSED: unset = automatic (the fused kernel serves the 2-D element types, where it is faster than the two-kernel split
-    // path: quad 1024^2 1.15 vs 1.44 ms, tri 1.72 vs 2.01 ms; for hex / tet the split path is faster),
-    // 1 = every element type, 0 = never
-    { const char* ev = getenv("NSB_FUSED");
-      const int modef = ev ? atoi(ev) : -1;
-      if (modef == 0) { c->fused_note = "disabled by NSB_FUSED=0"; return NSB_OK; }
-      if (modef < 0 && (c->elem == NSB_HEX || c->elem == NSB_TET)) { c->fused_note = "automatic choice: split path for 3-D elements (NSB_FUSED=1 overrides)"; return NSB_OK; } }
+    c->fused_ok = false; c->tile_ok = false; c->fused_note.clear();
+    // 2-D element types: fused patch kernel (ns_fused.cuh; quad 1024^2 1.15 vs 1.44 ms, tri 1.72 vs 2.01 ms against the split path).
+    // 3-D element types: fused tile kernel (ns_tile.cuh, two CTAs per SM, compressed records); NSB_TILE=0 selects the two-kernel
+    // split path, NSB_FUSED=1 the patch kernel of ns_fused.cuh. NSB_FUSED=0 disables every fused kernel.
+    const bool three_d = (c->elem == NSB_HEX || c->elem == NSB_TET);
+    const char* evf = getenv("NSB_FUSED"); const int modef = evf ? atoi(evf) : -1;
+    const char* evt = getenv("NSB_TILE"); const int modet = evt ? atoi(evt) : -1;
+    if (modef == 0) { c->fused_note = "disabled by NSB_FUSED=0"; return NSB_OK; }
+    const bool want_tile = three_d && modef != 1;
+    if (want_tile && modet == 0) { c->fused_note = "disabled by NSB_TILE=0: split path"; return NSB_OK; }
     size_t smem = 0; PatchCaps caps;
-    switch (c->elem) { case 0: smem = fused_smem_bytes_0(g.max_cnt); caps = fused_caps_0(); break; case 1: smem = fused_smem_bytes_1(g.max_cnt); caps = fused_caps_1(); break;
-                       case 2: smem = fused_smem_bytes_2(g.max_cnt); caps = fused_caps_2(); break; default: smem = fused_smem_bytes_3(g.max_cnt); caps = fused_caps_3(); }
+    if (want_tile) {
+        const int mc = c->elem == NSB_HEX ? tile_max_cnt_3() : tile_max_cnt_2();
+        if (g.max_cnt > mc) { c->fused_note = "a block row has more column slots than the tile kernel has lanes: split path"; return NSB_OK; }
+        if (c->elem == NSB_HEX) { smem = tile_smem_bytes_3(); caps = tile_caps_3(); } else { smem = tile_smem_bytes_2(); caps = tile_caps_2(); }
+    } else {
+        switch (c->elem) { case 0: smem = fused_smem_bytes_0(g.max_cnt); caps = fused_caps_0(); break; case 1: smem = fused_smem_bytes_1(g.max_cnt); caps = fused_caps_1(); break;
+                           case 2: smem = fused_smem_bytes_2(g.max_cnt); caps = fused_caps_2(); break; default: smem = fused_smem_bytes_3(g.max_cnt); caps = fused_caps_3(); }
+    }
     if (smem > 227 * 1024) { c->fused_note = "block rows too long for the shared-memory accumulators"; return NSB_OK; }
     PatchPlan plan; std::string perr;
     if (!build_patch_plan(c->elem, c->n_elem, c->n_node, conn, coords, g.adj_ptr.data(), g.adj.data(), g.brow.data(), emap.data(), caps, plan, perr)) {
@@ -343,17 +356,21 @@ static int setup_fused(nsb_ctx* c, const int32_t* conn, const double* coords, co
     CUDA_TRY(c, upload(c, &c->d_phdr, plan.hdr.data(), plan.hdr.size()));
     CUDA_TRY(c, upload(c, &c->d_pnodes, plan.nodes.data(), plan.nodes.size()));
     CUDA_TRY(c, upload(c, &c->d_pelems, plan.elems.data(), plan.elems.size()));
-    CUDA_TRY(c, upload(c, &c->d_pconn, plan.pconn.data(), plan.pconn.size()));
+    if (!want_tile) CUDA_TRY(c, upload(c, &c->d_pconn, plan.pconn.data(), plan.pconn.size()));
     CUDA_TRY(c, upload(c, &c->d_pwork, plan.work.data(), plan.work.size()));
     CUDA_TRY(c, upload(c, &c->d_padj, plan.adj.data(), plan.adj.size()));
+    if (want_tile) {
+        CUDA_TRY(c, upload(c, &c->d_plnodes, plan.lnodes.data(), plan.lnodes.size()));
+        CUDA_TRY(c, upload(c, &c->d_pecorner, plan.ecorner.data(), plan.ecorner.size()));
+    }
     c->n_patch = (int32_t)plan.hdr.size(); c->max_adj = plan.max_adj_per_node; c->scvf_evals = plan.n_scvf_evals;
-    c->patch_table_bytes = (int64_t)(plan.hdr.size() * sizeof(PatchHdr) + plan.nodes.size() * sizeof(PatchNode) + (plan.elems.size() + plan.pconn.size()) * 4 +
-                                     plan.work.size() * 4 + plan.adj.size() * sizeof(PatchAdj));
+    c->patch_table_bytes = (int64_t)(plan.hdr.size() * sizeof(PatchHdr) + plan.nodes.size() * sizeof(PatchNode) + (plan.elems.size() + (want_tile ? plan.lnodes.size() : plan.pconn.size())) * 4 +
+                                     plan.work.size() * 4 + plan.adj.size() * sizeof(PatchAdj) + plan.ecorner.size());
     CUDA_TRY(c, dev_malloc(c, &c->d_nodevol, (size_t)c->n_node * sizeof(double)));
     node_volume_kernel<<<(unsigned)((c->n_node + 255) / 256), 256, 0, c->stream>>>(c->n_node, c->d_adj_ptr, c->d_adj, c->d_scvvol, c->d_nodevol);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
-    c->fused_ok = true;
+    if (want_tile) c->tile_ok = true; else c->fused_ok = true;
     return NSB_OK;
 }
 
@@ -532,7 +549,9 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
     const bool lean = !flow && !exact && !no_split && c->max_cnt <= 64;
     static const bool no_fused = getenv("NSB_NOFUSED") != nullptr;
     const bool use_fused = lean && c->fused_ok && !no_fused;     // fused patch kernel: the SCVF records stay in shared memory
-    if (!use_fused) {   // per-(element, ip) record table: [static SCVF geometry | flux record] or the lean record of the split path.
+    // fused tile kernel (3-D): one upwind object for stabilisation and convection (the compressed record carries one set of upwind shapes)
+    const bool use_tile = lean && c->tile_ok && !no_fused && (k.stokes || k.upw_conv == k.upw_stab);
+    if (!use_fused && !use_tile) {   // per-(element, ip) record table: [static SCVF geometry | flux record] or the lean record of the split path.
         // The stride depends on the stabilisation (FLOW) and Jacobian flavour (exact Newton): (re)built on change.
         int stride = 0;
         if (lean) switch (c->elem) { case 0: stride = lean_record_doubles_0(); break; case 1: stride = lean_record_doubles_1(); break;
@@ -571,6 +590,19 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
             c->launches++;
             CUDA_TRY(c, e);
             c->j0_laplace = k.laplace;
+        }
+        if (use_tile) {
+            TileArgs A;
+            memset(&A, 0, sizeof A);
+            A.p = k; A.n_tile = c->n_patch;
+            A.hdr = c->d_phdr; A.nodes = c->d_pnodes; A.elems = c->d_pelems; A.lnodes = c->d_plnodes; A.ecorner = c->d_pecorner; A.work = c->d_pwork; A.adj = c->d_padj;
+            A.coords = c->d_coords; A.scvvol = c->d_scvvol; A.nodevol = c->d_nodevol;
+            A.u = u; A.s0 = s0; A.s1 = s1; A.j0 = c->d_j0; A.beta = beta; A.val = val; A.def = def;
+            A.errflag = c->d_err; A.elem_fast = c->d_elem_fast;
+            e = c->elem == NSB_HEX ? launch_tile_3(A, c->stream, c->sm_count) : launch_tile_2(A, c->stream, c->sm_count);
+            c->launches++;
+            CUDA_TRY(c, e);
+            return NSB_OK;
         }
         if (use_fused) {
             FusedArgs A;

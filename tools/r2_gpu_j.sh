@@ -1,0 +1,11 @@
+#!/bin/bash
+# split-path iteration: parity + bench at 128^3 with the split path (NSB_TILE=0) + optional ncu
+T=${1:-r2j}
+mkdir -p gpurun_out
+NSB_TILE=0 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/${T}_gputest.txt
+NSB_TILE=0 timeout 300 python bench.py --cells 128 --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/${T}_bench_n128.json 2> gpurun_out/${T}_bench.err
+NSB_TILE=0 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/${T}_bench.json 2>> gpurun_out/${T}_bench.err
+if [ "$2" = "ncu" ]; then
+NSB_TILE=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fv1_ -s 2 -c 2 -o gpurun_out/${T}_n128 python bench.py --cells 128 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/${T}_ncu.log 2>&1
+fi
+echo done
