@@ -117,7 +117,7 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
         auto go = [&](auto ka, int lpe) -> cudaError_t {
             const int epb = BS / lpe;
             size_t smem_a = sizeof(double) * (NSB_CSTR(E) * epb + NIP * (NSH * DIM + 1) + NIP * (NSH + 1) + 24) + sizeof(int) * (NIP * 12 + 24);
-            if (lpe > 1) smem_a += 16 + sizeof(double) * BS * (LeanRec<E>::SZ + 2);      // staged lean records (one slot per lane)
+            if (lpe > 1) smem_a += 16 + sizeof(double) * BS * (SplitRec<E>::COMP ? SplitRec<E>::SZ : LeanRec<E>::SZ + 2);   // staged records (one slot per lane)
             cudaError_t e2 = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
             if (e2 != cudaSuccess) return e2;
             ka<<<(unsigned)((m.n_elem + epb - 1) / epb), BS, smem_a, st>>>(k, m, u, s0, s1, rec, d_err);
@@ -132,7 +132,31 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
         if (e != cudaSuccess) return e;
     }
     static const int WPB = [] { const char* ev = getenv("NSB_SPLIT_WPB"); const int v = ev ? atoi(ev) : 2; return (v >= 1 && v <= 2) ? v : 2; }();
-    constexpr size_t tab_bytes = (sizeof(int32_t) * NSH * ET<E>::NINC + 15) & ~(size_t)15;
+    if constexpr (SplitRec<E>::COMP) {
+        // owner-lane rows kernel: one lane per column slot of the block row (NSB_SPLIT_OWNER=0: accumulator-copy kernel)
+        static const bool owner = !(getenv("NSB_SPLIT_OWNER") && atoi(getenv("NSB_SPLIT_OWNER")) == 0);
+        if (owner && m.max_cnt <= 32) {
+            static const int omb = [] { const char* ev = getenv("NSB_OWNER_MINB"); return ev ? atoi(ev) : 8; }();
+            const size_t smem_o = split_tab_bytes<E>() + ((sizeof(OwnWS<E>) + 15) & ~(size_t)15) * 2;
+            const bool fast_o = k.what == (W_JAC_A | W_DEF_A) && beta == 0.0;
+            auto ko = omb == 8 ? (fast_o ? fv1_rows_owner_kernel<E, 8, true> : fv1_rows_owner_kernel<E, 8, false>)
+                    : omb == 12 ? (fast_o ? fv1_rows_owner_kernel<E, 12, true> : fv1_rows_owner_kernel<E, 12, false>)
+                                : (fast_o ? fv1_rows_owner_kernel<E, 10, true> : fv1_rows_owner_kernel<E, 10, false>);
+            e = cudaFuncSetAttribute(ko, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_o);
+            if (e != cudaSuccess) return e;
+            int occ_o = 1;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_o, ko, 64, smem_o);
+            if (e != cudaSuccess) return e;
+            if (occ_o < 1) return cudaErrorLaunchOutOfResources;
+            const int64_t nblk_o = std::min<int64_t>((m.n_node + 1) / 2, (int64_t)sm_count * occ_o);
+            if (nblk_o <= 0) return cudaSuccess;
+            e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+            if (e != cudaSuccess) return e;
+            ko<<<(unsigned)nblk_o, 64, smem_o, st>>>(k, m, rec, j0, u, beta, val, def, work_counter);
+            return cudaGetLastError();
+        }
+    }
+    constexpr size_t tab_bytes = split_tab_bytes<E>();
     const size_t smem = tab_bytes + split_warp_bytes<E, CHP, J0D>(m.max_cnt) * WPB;
     const bool fast = k.what == (W_JAC_A | W_DEF_A) && beta == 0.0;
     auto kb = fast ? fv1_rows_split_kernel<E, CHP, MINB, J0D, true> : fv1_rows_split_kernel<E, CHP, MINB, J0D, false>;
@@ -170,7 +194,7 @@ cudaError_t NSB_CAT(launch_j0_, NSB_ELEM)(const MeshDev& m, int laplace, double*
     fv1_j0_kernel<E><<<(unsigned)nblk, 128, 0, st>>>(m, laplace, j0);
     return cudaGetLastError();
 }
-int NSB_CAT(lean_record_doubles_, NSB_ELEM)() { return LeanRec<E>::SZ; }
+int NSB_CAT(lean_record_doubles_, NSB_ELEM)() { return SplitRec<E>::SZ; }
 
 // doubles per combined SCVF record [geometry | flux] for the given stabilisation / Jacobian flavour
 int NSB_CAT(scvf_record_doubles_, NSB_ELEM)(bool flow, bool exact)

@@ -144,4 +144,15 @@ template <int E> struct LeanRec {
     static constexpr int SZ = (RAW + 3) & ~3;              // hex 32 doubles = 256 B; tet / quad / tri 20 doubles = 160 B
 };
 
+// compressed SCVF record of the split path for the 3-D element types (and of the fused tile kernel, ns_tile.cuh):
+//   [ F[4] | n[3] alpha | beta cw | cpe mv0 | mv1 mv2 | up[NSH] ]     (hex 22 doubles = 176 B, tet 18 doubles = 144 B)
+// from which the consumer forms, with the constant tables N_k(ip), dN_k(ip):
+//   cK_k = alpha N_k + beta up_k (continuity row, :561-584), dK_k = cw up_k + cpe N_k (convective diagonal, :430-468),
+//   pK_k = dN_k . mv (-G_k.n / diag, :586-592). One set of upwind shapes: stabilisation and convection use the same upwind.
+template <int E> struct CompRec {
+    static constexpr int NSH = ET<E>::NSH;
+    static constexpr int O_F = 0, O_N = 4, O_AL = 7, O_BE = 8, O_CW = 9, O_CPE = 10, O_MV = 11, O_UP = 14, SZ = 14 + NSH, HEAD = 4;
+    static constexpr int TSTR = NSH * 4 + 2;                // doubles per ip of the consumer's table [ip][k] -> (dN0, dN1, dN2, N), 16-byte rows, ip rows in distinct banks
+};
+
 }  // namespace nsb

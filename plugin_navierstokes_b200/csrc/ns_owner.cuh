@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
     static_assert(!LEAN || (!FLOW && !EXACT), "the split path covers FIELDS / no stabilisation with the fixed-point Jacobian");
     constexpr int NSHP = (NSH + 1) & ~1;
     constexpr int L_N = NF, L_CK = (NF + DIM + 1) & ~1, L_DK = L_CK + NSHP, L_PK = L_DK + NSHP;   // = LeanRec<E> offsets
-    constexpr int LRSZ = (L_PK + NSHP + 3) & ~3;
+    constexpr bool CREC = LEAN && DIM == 3;                       // compressed record (CompRec<E>, ns_base.h)
+    constexpr int LRSZ = CREC ? 14 + NSH : (L_PK + NSHP + 3) & ~3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* xs = reinterpret_cast<double*>(smem_raw);            // [BS][NSB_CSTR]: corner coordinates | SCV volumes | nodal unknowns (the `u` argument)
     double* vs = xs + NSH * DIM;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
     // shared -> global, SASS UBLKCP). Written straight to global memory the 16-byte stores of a warp touch 32 different sectors
     // each: the LSU data pipe was 84 % busy with them (ncu, profiles/r2_ncu_summary.md).
     constexpr bool STAGED = LEAN && LPE > 1;
-    constexpr int SSTR = LRSZ + 2;
+    constexpr int SSTR = CREC ? LRSZ : LRSZ + 2;                  // (an odd number of 16-byte units)
     double* stg = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(iptab + NIP * 12) + 15) & ~(uintptr_t)15);
     for (int i = threadIdx.x; i < 24; i += NT) {
         cortab[i] = tab::CORNER[E][i / 3][i % 3];
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
         };
         // everything that uses the STABILISATION's upwind shapes happens here: the convective upwind below may overwrite `up`
         constexpr int W_CK = LEAN ? L_CK : FR::O_CK, W_DK = LEAN ? L_DK : FR::O_DK;
-        if (want_jac) {                                          // continuity-row coefficients (:561-584)
+        if (want_jac && !CREC) {                                 // continuity-row coefficients (:561-584)
             if constexpr (NSH % 2 == 0) {
 #pragma unroll
                 for (int k = 0; k < NSH; k += 2) {
@@ -564,7 +565,30 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
             }
         }
         // ---- Jacobian coefficients ----
-        if (want_jac) {
+        if constexpr (CREC) {
+            if (want_jac) {
+                // compressed record: the consumer forms cK_k = alpha N_k + beta up_k, dK_k = cw up_k + cpe N_k, pK_k = dN_k . mv
+                const double ci = inv * p.rho;
+                const double alpha = (STAB == STAB_NONE) ? p.rho : qa * ci, beta = (STAB == STAB_NONE || p.stokes) ? 0.0 : qb * ci;
+                const double cw = p.stokes ? 0.0 : prod * w, cpe = (p.stokes || !p.peclet) ? 0.0 : prod * (1.0 - w);
+                double mv[DIM];
+#pragma unroll
+                for (int i = 0; i < DIM; i++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) s += JI[d][i] * n[d];
+                    mv[i] = s * (-1.0 * inv);
+                }
+                *reinterpret_cast<double2*>(fr + 4) = make_double2(n[0], n[1]);
+                *reinterpret_cast<double2*>(fr + 6) = make_double2(n[DIM - 1], alpha);
+                *reinterpret_cast<double2*>(fr + 8) = make_double2(beta, cw);
+                *reinterpret_cast<double2*>(fr + 10) = make_double2(cpe, mv[0]);
+                *reinterpret_cast<double2*>(fr + 12) = make_double2(mv[1], mv[DIM - 1]);
+#pragma unroll
+                for (int k = 0; k < NSH; k += 2) *reinterpret_cast<double2*>(fr + 14 + k) = make_double2(p.stokes ? 0.0 : up[k], p.stokes ? 0.0 : up[k + 1]);
+            }
+        }
+        if (want_jac && !CREC) {
             const double cw = prod * w, cpe = prod * (1.0 - w);
             if constexpr (NSH % 2 == 0) {
 #pragma unroll

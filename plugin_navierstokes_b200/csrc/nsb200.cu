@@ -337,8 +337,8 @@ static int setup_fused(nsb_ctx* c, const int32_t* conn, const double* coords, co
     const char* evf = getenv("NSB_FUSED"); const int modef = evf ? atoi(evf) : -1;
     const char* evt = getenv("NSB_TILE"); const int modet = evt ? atoi(evt) : -1;
     if (modef == 0) { c->fused_note = "disabled by NSB_FUSED=0"; return NSB_OK; }
-    const bool want_tile = three_d && modef != 1;
-    if (want_tile && modet == 0) { c->fused_note = "disabled by NSB_TILE=0: split path"; return NSB_OK; }
+    const bool want_tile = three_d;
+    if (want_tile && modet != 1) { c->fused_note = "3-D element types: two-kernel split path (NSB_TILE=1 selects the fused tile kernel)"; return NSB_OK; }
     size_t smem = 0; PatchCaps caps;
     if (want_tile) {
         const int mc = c->elem == NSB_HEX ? tile_max_cnt_3() : tile_max_cnt_2();
@@ -546,11 +546,13 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
     // velocity components in the continuity row and exact Newton adds full blocks: those keep the general rows kernel.
     static const bool no_split = getenv("NSB_NOSPLIT") != nullptr;
     // (the split rows kernel keeps JP accumulator copies + the J0 rows per warp in shared memory: bounded row length only)
-    const bool lean = !flow && !exact && !no_split && c->max_cnt <= 64;
+    // (3-D: the compressed record of the split path carries ONE set of upwind shapes -> same upwind for stabilisation and convection)
+    const bool one_upwind = k.stokes || k.upw_conv == k.upw_stab || kDIM[c->elem] == 2;
+    const bool lean = !flow && !exact && !no_split && c->max_cnt <= 64 && one_upwind;
     static const bool no_fused = getenv("NSB_NOFUSED") != nullptr;
     const bool use_fused = lean && c->fused_ok && !no_fused;     // fused patch kernel: the SCVF records stay in shared memory
     // fused tile kernel (3-D): one upwind object for stabilisation and convection (the compressed record carries one set of upwind shapes)
-    const bool use_tile = lean && c->tile_ok && !no_fused && (k.stokes || k.upw_conv == k.upw_stab);
+    const bool use_tile = lean && c->tile_ok && !no_fused;
     if (!use_fused && !use_tile) {   // per-(element, ip) record table: [static SCVF geometry | flux record] or the lean record of the split path.
         // The stride depends on the stabilisation (FLOW) and Jacobian flavour (exact Newton): (re)built on change.
         int stride = 0;
