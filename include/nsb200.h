@@ -127,6 +127,27 @@ int  nsb_prep_elem_loop(nsb_ctx *ctx);
 int  nsb_assemble(nsb_ctx *ctx, int what, int scatter_mode, const double *u, const nsb_time_series *ts,
                   double scale_a, double scale_m, double beta, double *values, double *defect, int location);
 
+/* GPU-resident hand-off of the Jacobian: like nsb_assemble, but the CSR values stay in a context-owned device
+ * buffer (beta applies to it) and only the vectors cross the host link. Replaces the copy of the assembled SparseMatrix
+ * (ugcore AssembleJacobian -> J, navier_stokes_base.h:200; instationary combination fv1/navier_stokes_fv1.cpp:268-280
+ * through scale_a = theta dt, scale_m = 1) to a host solver by a device-resident operator:
+ *   nsb_resident_jacobian : device pointer of the values (pattern = nsb_get_csr) for a GPU solver,
+ *   nsb_apply_jacobian    : y = alpha J x + beta y (matrix-vector product / residual d - J dx of a Krylov or defect-correction
+ *                           loop); values == NULL selects the resident Jacobian, x / y per `location`. */
+int  nsb_assemble_resident(nsb_ctx *ctx, int what, int scatter_mode, const double *u, const nsb_time_series *ts,
+                           double scale_a, double scale_m, double beta, double *defect, int location);
+int  nsb_resident_jacobian(nsb_ctx *ctx, double **dev_values);
+int  nsb_apply_jacobian(nsb_ctx *ctx, const double *values, double alpha, const double *x, double beta, double *y, int location);
+
+/* Dirichlet post-pass: what ugcore's DirichletBoundary does for NavierStokesWall (velocity = 0,
+ * bnd/wall_impl.h:44-70) and NavierStokesInflowFV1 (velocity = user data, fv1/bnd/inflow_fv1_impl.h:42-82) after the
+ * element loop: adjust_jacobian (row := unit row), adjust_defect (entry := 0), adjust_solution (entry := value).
+ * dofs: scalar dof indices (host pointer, copied). values == NULL: the resident Jacobian; otherwise a device pointer.
+ * nsb_adjust_vector: vec[dofs[i]] := g ? g[i] : 0  (g: host pointer with one value per Dirichlet dof). */
+int  nsb_set_dirichlet(nsb_ctx *ctx, int64_t n, const int64_t *dofs);
+int  nsb_adjust_jacobian(nsb_ctx *ctx, double *values);
+int  nsb_adjust_vector(nsb_ctx *ctx, double *vec, const double *g, int location);
+
 /* NSB_DEVICE calls are asynchronous: element-level failures (the reference's UG_THROW inside upwind /
  * stabilisation code, upwind.cpp:354, stabilization.cpp:292,641) are latched on the device; this call
  * synchronises and reports them (NSB_ERR_GEOMETRY). NSB_HOST calls do it implicitly. */

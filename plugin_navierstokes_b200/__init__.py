@@ -12,4 +12,4 @@ from .disc import (NavierStokes, NavierStokesFV1, NavierStokesFVCR, UGError,    
                    NavierStokesNoUpwind, NavierStokesFullUpwind, NavierStokesSkewedUpwind,
                    NavierStokesLinearProfileSkewedUpwind, NavierStokesPositiveUpwind, NavierStokesRegularUpwind,
                    NavierStokesFIELDSStabilization, NavierStokesFLOWStabilization,
-                   NavierStokesFV1WithoutStabilization)
+                   NavierStokesFV1WithoutStabilization, NavierStokesWall, NavierStokesInflowFV1, ThetaTimeStep)

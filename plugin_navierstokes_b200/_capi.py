@@ -22,6 +22,8 @@ SYMBOLS = [
     "nsb_upload_mesh", "nsb_upload_mesh_fvcr", "nsb_num_dofs", "nsb_nnz", "nsb_num_colors", "nsb_get_csr",
     "nsb_prep_elem_loop", "nsb_assemble", "nsb_local_contributions", "nsb_pack", "nsb_unpack_add",
     "nsb_launch_count", "nsb_synchronize", "nsb_version", "nsb_check_errors", "nsb_query",
+    "nsb_assemble_resident", "nsb_resident_jacobian", "nsb_apply_jacobian", "nsb_set_dirichlet", "nsb_adjust_jacobian",
+    "nsb_adjust_vector",
 ]
 
 
@@ -84,5 +86,11 @@ def lib():
     L.nsb_check_errors.argtypes = [vp]
     L.nsb_version.restype = C.c_char_p
     L.nsb_query.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    L.nsb_assemble_resident.argtypes = [vp, i32, i32, vp, C.POINTER(TimeSeries), C.c_double, C.c_double, C.c_double, vp, i32]
+    L.nsb_resident_jacobian.argtypes = [vp, C.POINTER(vp)]
+    L.nsb_apply_jacobian.argtypes = [vp, vp, C.c_double, vp, C.c_double, vp, i32]
+    L.nsb_set_dirichlet.argtypes = [vp, i64, vp]
+    L.nsb_adjust_jacobian.argtypes = [vp, vp]
+    L.nsb_adjust_vector.argtypes = [vp, vp, vp, i32]
     _lib = L
     return L

@@ -38,6 +38,93 @@ __global__ void node_volume_kernel(int64_t n_node, const int64_t* __restrict__ a
     for (int64_t q = adj_ptr[a]; q < adj_ptr[a + 1]; q++) s += scvvol[adj[q]];
     nodevol[a] = s;
 }
+// ---- GPU-resident consumer of the assembled Jacobian: y = alpha * J x + beta * y ----
+// FV1 block CSR (ns_graph.h): warp per node = NF consecutive rows, lane = column slot (stride 32): the 4 (3) x 4 (3) block is
+// read once with 16-byte loads where NF == 4; fixed-order butterfly reduction -> bitwise deterministic.
+template <int NF>
+__global__ void __launch_bounds__(128) bcsr_spmv_kernel(int64_t n_node, const int64_t* __restrict__ brow, const int32_t* __restrict__ bcol,
+                                                        const double* __restrict__ val, const double* __restrict__ x, double alpha, double beta,
+                                                        double* __restrict__ y)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t a = warp0; a < n_node; a += nwarp) {
+        const int64_t b0 = brow[a];
+        const int cnt = (int)(brow[a + 1] - b0);
+        const double* v = val + b0 * (NF * NF);
+        double s[NF];
+#pragma unroll
+        for (int r = 0; r < NF; r++) s[r] = 0.0;
+        for (int b = lane; b < cnt; b += 32) {
+            const int64_t c = bcol[b0 + b];
+            double xc[NF];
+            if (NF == 4) { const double2 p = __ldg(reinterpret_cast<const double2*>(x + c * 4)), q = __ldg(reinterpret_cast<const double2*>(x + c * 4) + 1); xc[0] = p.x; xc[1] = p.y; xc[2] = q.x; xc[NF - 1] = q.y; }
+            else { for (int f = 0; f < NF; f++) xc[f] = x[c * NF + f]; }
+#pragma unroll
+            for (int r = 0; r < NF; r++) {
+                const double* row = v + ((int64_t)r * cnt + b) * NF;
+                if (NF == 4) { const double2 p = __ldcs(reinterpret_cast<const double2*>(row)), q = __ldcs(reinterpret_cast<const double2*>(row) + 1); s[r] += p.x * xc[0] + p.y * xc[1] + q.x * xc[2] + q.y * xc[NF - 1]; }
+                else { for (int f = 0; f < NF; f++) s[r] += row[f] * xc[f]; }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NF; r++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+        if (lane < NF) {
+            double sv = s[0];
+#pragma unroll
+            for (int r = 1; r < NF; r++) if (lane == r) sv = s[r];
+            double* q = y + a * NF + lane;
+            *q = (beta == 0.0) ? alpha * sv : alpha * sv + beta * (*q);
+        }
+    }
+}
+// scalar CSR (FVCR): warp per row
+__global__ void __launch_bounds__(128) csr_spmv_kernel(int64_t n_row, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                                       const double* __restrict__ val, const double* __restrict__ x, double alpha, double beta,
+                                                       double* __restrict__ y)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n_row; r += nwarp) {
+        double s = 0.0;
+        for (int64_t q = rowptr[r] + lane; q < rowptr[r + 1]; q += 32) s += __ldcs(val + q) * x[colind[q]];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[r] = (beta == 0.0) ? alpha * s : alpha * s + beta * y[r];
+    }
+}
+// ---- Dirichlet post-pass (ugcore DirichletBoundary::adjust_jacobian / adjust_defect / adjust_solution as used by
+// NavierStokesWall, bnd/wall_impl.h:44-70, and NavierStokesInflowFV1, fv1/bnd/inflow_fv1_impl.h:42-82) ----
+// scalar row r of the (block) CSR matrix := unit row. rowinfo: FV1 -> block layout, FVCR -> scalar rowptr.
+template <int NF>
+__global__ void dirichlet_rows_bcsr_kernel(int64_t n, const int64_t* __restrict__ dofs, const int64_t* __restrict__ brow, const int32_t* __restrict__ bcol,
+                                           double* __restrict__ val)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarp) {
+        const int64_t dof = dofs[i], a = dof / NF; const int rf = (int)(dof - a * NF);
+        const int64_t b0 = brow[a]; const int cnt = (int)(brow[a + 1] - b0);
+        double* row = val + b0 * (NF * NF) + (int64_t)rf * cnt * NF;
+        for (int j = lane; j < cnt * NF; j += 32) { const int b = j / NF, cf = j - b * NF; row[j] = (bcol[b0 + b] == a && cf == rf) ? 1.0 : 0.0; }
+    }
+}
+__global__ void dirichlet_rows_csr_kernel(int64_t n, const int64_t* __restrict__ dofs, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                          double* __restrict__ val)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarp) {
+        const int64_t r = dofs[i];
+        for (int64_t q = rowptr[r] + lane; q < rowptr[r + 1]; q += 32) val[q] = (colind[q] == r) ? 1.0 : 0.0;
+    }
+}
+__global__ void dirichlet_set_kernel(int64_t n, const int64_t* __restrict__ dofs, const double* __restrict__ g, double* __restrict__ v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[dofs[i]] = g ? g[i] : 0.0;
+}
 __global__ void pack_kernel(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ src, double* __restrict__ out)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = src[idx[i]];
@@ -90,6 +177,11 @@ struct nsb_ctx {
     double* d_geo = nullptr; int geo_diff_len = -1;   // static SCVF geometry records of the fused kernel (per diffusion-length type)
     int32_t n_patch = 0; int max_adj = 0;
     int64_t scvf_evals = 0, patch_table_bytes = 0;
+    // GPU-resident Jacobian hand-off + Dirichlet post-pass
+    int32_t* d_bcol = nullptr; int64_t* d_rowptr = nullptr;   // block columns (FV1) / scalar pattern (FVCR), uploaded on first use
+    double* d_jres = nullptr;                                  // resident CSR values (nsb_assemble_resident)
+    double *d_xin = nullptr, *d_yout = nullptr;                // staging of nsb_apply_jacobian(NSB_HOST)
+    int64_t* d_dir = nullptr; int64_t n_dir = 0; double* d_dirval = nullptr;
     // fused tile kernel (ns_tile.cuh, 3-D element types): the patch tables above built with the tile capacities + local-node tables
     bool tile_ok = false;
     int32_t* d_plnodes = nullptr; uint8_t* d_pecorner = nullptr;
@@ -164,6 +256,8 @@ static void free_mesh(nsb_ctx* c)
     cudaFree(c->d_jloc); cudaFree(c->d_dloc); cudaFree(c->d_j0);
     cudaFree(c->d_phdr); cudaFree(c->d_pnodes); cudaFree(c->d_pelems); cudaFree(c->d_pconn); cudaFree(c->d_pwork); cudaFree(c->d_padj);
     cudaFree(c->d_nodevol); cudaFree(c->d_elem_fast); cudaFree(c->d_geo);
+    cudaFree(c->d_bcol); cudaFree(c->d_rowptr); cudaFree(c->d_jres); cudaFree(c->d_xin); cudaFree(c->d_yout); cudaFree(c->d_dir); cudaFree(c->d_dirval);
+    c->d_bcol = nullptr; c->d_rowptr = nullptr; c->d_jres = nullptr; c->d_xin = c->d_yout = nullptr; c->d_dir = nullptr; c->n_dir = 0; c->d_dirval = nullptr;
     cudaFree(c->d_plnodes); cudaFree(c->d_pecorner); c->d_plnodes = nullptr; c->d_pecorner = nullptr; c->tile_ok = false;
     c->d_geo = nullptr; c->geo_diff_len = -1;
     c->d_phdr = nullptr; c->d_pnodes = nullptr; c->d_pelems = c->d_pconn = nullptr; c->d_pwork = nullptr; c->d_padj = nullptr;
@@ -812,6 +906,158 @@ extern "C" int nsb_local_contributions(nsb_ctx* c, int what, const double* u, co
         CUDA_TRY(c, cudaMemcpyAsync(Jloc, dj, sizeof(double) * nJ, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(dloc, ddl, sizeof(double) * nd, cudaMemcpyDeviceToHost, c->stream));
         return check_device_error(c);
+    }
+    return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GPU-resident Jacobian and Dirichlet post-pass (8f-1)
+// ------------------------------------------------------------------------------------------------
+static int ensure_pattern(nsb_ctx* c)
+{
+    if (c->d_bcol) return NSB_OK;
+    CUDA_TRY(c, upload(c, &c->d_bcol, c->h_bcol.data(), c->h_bcol.size()));
+    if (c->disc == NSB_DISC_FVCR) CUDA_TRY(c, upload(c, &c->d_rowptr, c->h_brow.data(), c->h_brow.size()));
+    return NSB_OK;
+}
+
+extern "C" int nsb_assemble_resident(nsb_ctx* c, int what, int mode, const double* u, const nsb_time_series* ts, double sa, double sm,
+                                     double beta, double* defect, int location)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_assemble_resident: no grid uploaded");
+    if (!u) return set_err(c, NSB_ERR_INVALID, "nsb_assemble_resident: u == NULL");
+    const bool jac = what & (NSB_JAC_A | NSB_JAC_M), dfc = what & (NSB_DEF_A | NSB_DEF_M | NSB_RHS);
+    if (dfc && !defect) return set_err(c, NSB_ERR_INVALID, "nsb_assemble_resident: defect pointer missing");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc;
+    if (jac && !c->d_jres) {
+        if ((rc = ensure(c, &c->d_jres, c->nnz))) return rc;
+        CUDA_TRY(c, cudaMemsetAsync(c->d_jres, 0, sizeof(double) * c->nnz, c->stream));
+    }
+    if (location == NSB_DEVICE) return nsb_assemble(c, what, mode, u, ts, sa, sm, beta, c->d_jres, defect, NSB_DEVICE);
+    // host vectors, device-resident matrix: u (and the time series) in, defect out
+    KParams k;
+    if ((rc = resolve_params(c, k, what, ts, sa, sm))) return rc;
+    const size_t nb = sizeof(double) * c->n_dof;
+    if ((rc = ensure(c, &c->d_u, c->n_dof))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, nb, cudaMemcpyHostToDevice, c->stream));
+    nsb_time_series dts; const nsb_time_series* pts = nullptr;
+    if (ts && ts->sol0) {
+        if ((rc = ensure(c, &c->d_s0, c->n_dof)) || (rc = ensure(c, &c->d_s1, c->n_dof))) return rc;
+        if (!ts->sol1) return set_err(c, NSB_ERR_SETUP, "NavierStokes::add_jac_A_elem:  Stabilization needs exactly two time points.");
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_s0, ts->sol0, nb, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_s1, ts->sol1, nb, cudaMemcpyHostToDevice, c->stream));
+        dts.sol0 = c->d_s0; dts.sol1 = c->d_s1; dts.dt = ts->dt; pts = &dts;
+    }
+    if (dfc) { if ((rc = ensure(c, &c->d_def, c->n_dof))) return rc;
+               if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(c->d_def, defect, nb, cudaMemcpyHostToDevice, c->stream)); }
+    if ((rc = nsb_assemble(c, what, mode, c->d_u, pts, sa, sm, beta, c->d_jres, c->d_def, NSB_DEVICE))) return rc;
+    if (dfc) CUDA_TRY(c, cudaMemcpyAsync(defect, c->d_def, nb, cudaMemcpyDeviceToHost, c->stream));
+    return check_device_error(c);
+}
+
+extern "C" int nsb_resident_jacobian(nsb_ctx* c, double** dev_values)
+{
+    if (!c || !dev_values) return NSB_ERR_INVALID;
+    if (!c->d_jres) return set_err(c, NSB_ERR_INVALID, "nsb_resident_jacobian: nothing assembled yet (nsb_assemble_resident)");
+    *dev_values = c->d_jres;
+    return NSB_OK;
+}
+
+static int spmv_launch(nsb_ctx* c, const double* val, double alpha, const double* x, double beta, double* y)
+{
+    int rc = ensure_pattern(c);
+    if (rc) return rc;
+    const int64_t nrows = c->disc == NSB_DISC_FVCR ? c->n_dof : c->n_node;
+    const unsigned nblk = (unsigned)std::min<int64_t>((nrows + 3) / 4, (int64_t)c->sm_count * 16);
+    if (c->disc == NSB_DISC_FVCR) csr_spmv_kernel<<<nblk, 128, 0, c->stream>>>(c->n_dof, c->d_rowptr, c->d_bcol, val, x, alpha, beta, y);
+    else if (kDIM[c->elem] == 3) bcsr_spmv_kernel<4><<<nblk, 128, 0, c->stream>>>(c->n_node, c->d_brow, c->d_bcol, val, x, alpha, beta, y);
+    else bcsr_spmv_kernel<3><<<nblk, 128, 0, c->stream>>>(c->n_node, c->d_brow, c->d_bcol, val, x, alpha, beta, y);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return NSB_OK;
+}
+
+extern "C" int nsb_apply_jacobian(nsb_ctx* c, const double* values, double alpha, const double* x, double beta, double* y, int location)
+{
+    if (!c || !x || !y) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_apply_jacobian: no grid uploaded");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const double* val = values ? values : c->d_jres;        // NULL = the resident Jacobian
+    if (!val) return set_err(c, NSB_ERR_INVALID, "nsb_apply_jacobian: no resident Jacobian (nsb_assemble_resident) and values == NULL");
+    if (location == NSB_DEVICE) return spmv_launch(c, val, alpha, x, beta, y);
+    int rc;
+    const size_t nb = sizeof(double) * c->n_dof;
+    if ((rc = ensure(c, &c->d_xin, c->n_dof)) || (rc = ensure(c, &c->d_yout, c->n_dof))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_xin, x, nb, cudaMemcpyHostToDevice, c->stream));
+    if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(c->d_yout, y, nb, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = spmv_launch(c, val, alpha, c->d_xin, beta, c->d_yout))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(y, c->d_yout, nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return NSB_OK;
+}
+
+extern "C" int nsb_set_dirichlet(nsb_ctx* c, int64_t n, const int64_t* dofs)
+{
+    if (!c || n < 0 || (n > 0 && !dofs)) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_set_dirichlet: no grid uploaded");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    for (int64_t i = 0; i < n; i++) if (dofs[i] < 0 || dofs[i] >= c->n_dof) return set_err(c, NSB_ERR_INVALID, "nsb_set_dirichlet: dof %lld out of range", (long long)dofs[i]);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_dir); c->d_dir = nullptr; c->n_dir = 0;
+    cudaFree(c->d_dirval); c->d_dirval = nullptr;
+    if (n == 0) return NSB_OK;
+    CUDA_TRY(c, upload(c, &c->d_dir, dofs, (size_t)n));
+    c->n_dir = n;
+    return NSB_OK;
+}
+
+extern "C" int nsb_adjust_jacobian(nsb_ctx* c, double* values)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (c->n_dir == 0) return NSB_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    double* val = values ? values : c->d_jres;
+    if (!val) return set_err(c, NSB_ERR_INVALID, "nsb_adjust_jacobian: no resident Jacobian and values == NULL");
+    int rc = ensure_pattern(c);
+    if (rc) return rc;
+    const unsigned nblk = (unsigned)std::min<int64_t>((c->n_dir + 3) / 4, (int64_t)c->sm_count * 16);
+    if (c->disc == NSB_DISC_FVCR) dirichlet_rows_csr_kernel<<<nblk, 128, 0, c->stream>>>(c->n_dir, c->d_dir, c->d_rowptr, c->d_bcol, val);
+    else if (kDIM[c->elem] == 3) dirichlet_rows_bcsr_kernel<4><<<nblk, 128, 0, c->stream>>>(c->n_dir, c->d_dir, c->d_brow, c->d_bcol, val);
+    else dirichlet_rows_bcsr_kernel<3><<<nblk, 128, 0, c->stream>>>(c->n_dir, c->d_dir, c->d_brow, c->d_bcol, val);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return NSB_OK;
+}
+
+// vec[dof_i] := g[i] (g == NULL: 0). adjust_defect: g = NULL; adjust_solution: g = Dirichlet values (host pointer, n_dir entries)
+extern "C" int nsb_adjust_vector(nsb_ctx* c, double* vec, const double* g, int location)
+{
+    if (!c || !vec) return NSB_ERR_INVALID;
+    if (c->n_dir == 0) return NSB_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const double* dg = nullptr;
+    if (g) {
+        int rc = ensure(c, &c->d_dirval, (size_t)c->n_dir);
+        if (rc) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_dirval, g, sizeof(double) * c->n_dir, cudaMemcpyHostToDevice, c->stream));
+        dg = c->d_dirval;
+    }
+    double* dv = vec;
+    const size_t nb = sizeof(double) * c->n_dof;
+    if (location == NSB_HOST) {
+        int rc = ensure(c, &c->d_yout, c->n_dof);
+        if (rc) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_yout, vec, nb, cudaMemcpyHostToDevice, c->stream));
+        dv = c->d_yout;
+    }
+    dirichlet_set_kernel<<<(unsigned)std::min<int64_t>((c->n_dir + 255) / 256, (int64_t)c->sm_count * 8), 256, 0, c->stream>>>(c->n_dir, c->d_dir, dg, dv);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    if (location == NSB_HOST) {
+        CUDA_TRY(c, cudaMemcpyAsync(vec, dv, nb, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
     return NSB_OK;
 }

@@ -320,6 +320,81 @@ class _DeviceDisc:
         self._check(rc)
         return values, defect
 
+    # ---- GPU-resident Jacobian (nsb_assemble_resident / nsb_apply_jacobian) and Dirichlet post-pass ----
+    def assemble_resident(self, what, u, defect=None, time_series=None, scale_a=1.0, scale_m=1.0, beta=0.0, scatter_mode=None):
+        """like assemble(), but the CSR values stay in a context-owned device buffer: only u (and the time series) go to the
+        device and the defect comes back. Returns the defect."""
+        L = capi.lib()
+        p = self._params()
+        self._check(L.nsb_set_params(self._context(), C.byref(p)))
+        on_dev = _is_torch(u)
+        dfc = bool(what & (capi.DEF_A | capi.DEF_M | capi.RHS))
+        if on_dev:
+            import torch
+            self.use_stream(torch.cuda.current_stream(u.device).cuda_stream)
+            if dfc and defect is None:
+                defect = torch.zeros(self.num_dofs, dtype=torch.float64, device=u.device)
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+            if dfc and defect is None:
+                defect = np.zeros(self.num_dofs)
+        ts = None
+        keep = []
+        if time_series is not None:
+            s0, s1, dt = time_series
+            if not on_dev:
+                s0 = np.ascontiguousarray(s0, dtype=np.float64).reshape(-1)
+                s1 = np.ascontiguousarray(s1, dtype=np.float64).reshape(-1)
+            keep = [s0, s1]
+            ts = capi.TimeSeries(self._ptr(s0), self._ptr(s1), float(dt))
+        mode = self.scatter_mode if scatter_mode is None else scatter_mode
+        rc = L.nsb_assemble_resident(self._ctx, what, mode, self._ptr(u), C.byref(ts) if ts is not None else None,
+                                     float(scale_a), float(scale_m), float(beta), self._ptr(defect) if dfc else None,
+                                     capi.DEVICE if on_dev else capi.HOST)
+        del keep
+        self._check(rc)
+        return defect
+
+    def resident_jacobian_ptr(self):
+        """device pointer (int) of the resident CSR values, pattern = csr()"""
+        out = C.c_void_p()
+        self._check(capi.lib().nsb_resident_jacobian(self._ctx, C.byref(out)))
+        return out.value
+
+    def apply_jacobian(self, x, y=None, alpha=1.0, beta=0.0, values=None):
+        """y = alpha * J x + beta * y with the resident Jacobian (values=None) or a CUDA tensor of CSR values"""
+        on_dev = _is_torch(x)
+        if on_dev:
+            import torch
+            self.use_stream(torch.cuda.current_stream(x.device).cuda_stream)
+            if y is None:
+                y = torch.zeros(self.num_dofs, dtype=torch.float64, device=x.device)
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+            if y is None:
+                y = np.zeros(self.num_dofs)
+        self._check(capi.lib().nsb_apply_jacobian(self._ctx, self._ptr(values), float(alpha), self._ptr(x), float(beta), self._ptr(y),
+                                                  capi.DEVICE if on_dev else capi.HOST))
+        return y
+
+    def set_dirichlet(self, dofs):
+        dofs = np.ascontiguousarray(dofs, dtype=np.int64).reshape(-1)
+        self._check(capi.lib().nsb_set_dirichlet(self._context(), dofs.size, dofs.ctypes.data))
+        self._n_dirichlet = int(dofs.size)
+
+    def adjust_jacobian(self, values=None):
+        """Dirichlet rows := unit rows, in the resident Jacobian (values=None) or a CUDA tensor of CSR values"""
+        self._check(capi.lib().nsb_adjust_jacobian(self._ctx, self._ptr(values)))
+
+    def adjust_vector(self, vec, g=None):
+        """vec[dirichlet dofs] := g (host array, one value per Dirichlet dof) or 0: adjust_solution / adjust_defect"""
+        if g is not None:
+            g = np.ascontiguousarray(g, dtype=np.float64).reshape(-1)
+            if g.size != getattr(self, "_n_dirichlet", -1):
+                raise UGError("adjust_vector: one value per Dirichlet dof expected")
+        self._check(capi.lib().nsb_adjust_vector(self._ctx, self._ptr(vec), self._ptr(g), capi.DEVICE if _is_torch(vec) else capi.HOST))
+        return vec
+
     def assemble_jacobian(self, u, **kw):
         return self.assemble(capi.JAC_A, u, **kw)[0]
 
@@ -512,3 +587,87 @@ def NavierStokes(fcts, subsets, disc_type=None, device=0):
     if disc_type in ("fv", "fe", "fecr"):
         raise UGError("NavierStokes: disc type '%s' is outside the device assembly path (fv1, fvcr)" % disc_type)
     raise UGError("NavierStokes: no disc type '%s' available. Use 'fv1', 'fv', 'fvcr', 'fe' or 'fecr'." % disc_type)
+
+
+# ------------------------------------------------------------------------------------------------
+# boundary conditions that are Dirichlet constraints on the velocity
+# ------------------------------------------------------------------------------------------------
+class _DirichletVelocity:
+    """collects (node, value) pairs of the velocity components and applies ugcore's DirichletBoundary post-pass
+    (adjust_jacobian / adjust_defect / adjust_solution) through the C ABI (nsb_set_dirichlet, nsb_adjust_*)."""
+
+    def __init__(self, master):
+        fcts = master.symb_fcts() if hasattr(master, "symb_fcts") else master._fcts
+        self._master = master
+        self._dim = len(fcts) - 1
+        if len(fcts) != self._dim + 1 or self._dim not in (2, 3):
+            raise UGError("This Boundary Condition works on exactly dim+1 (velocity+pressure) components, but %d components given." % len(fcts))
+        self._nodes, self._vals = [], []
+
+    def _add(self, nodes, values):
+        nodes = np.asarray(nodes, dtype=np.int64).reshape(-1)
+        values = np.broadcast_to(np.asarray(values, dtype=np.float64), (nodes.size, self._dim))
+        self._nodes.append(nodes)
+        self._vals.append(np.array(values))
+
+    def dirichlet(self):
+        """(dofs int64, values float64) of all constrained velocity dofs (FV1 numbering node*(dim+1)+d)"""
+        if not self._nodes:
+            return np.zeros(0, dtype=np.int64), np.zeros(0)
+        nodes = np.concatenate(self._nodes)
+        vals = np.concatenate(self._vals, axis=0)
+        nf = self._dim + 1
+        dofs = (nodes[:, None] * nf + np.arange(self._dim)[None, :]).reshape(-1)
+        v = vals.reshape(-1)
+        dofs, first = np.unique(dofs, return_index=True)     # a node in two boundary subsets: first registration wins
+        return dofs, v[first]
+
+    def apply(self, disc=None):
+        """register the constraint with the device context of `disc` (default: the master disc)"""
+        d = disc if disc is not None else self._master
+        dofs, vals = self.dirichlet()
+        d.set_dirichlet(dofs)
+        self._applied_vals = vals
+        return dofs, vals
+
+
+class NavierStokesWall(_DirichletVelocity):
+    """bnd/wall_impl.h:44-70: velocity = 0 on the wall subsets (registered at register_navier_stokes.cpp)"""
+
+    def add(self, boundary_nodes):
+        self._add(boundary_nodes, 0.0)
+
+
+class NavierStokesInflowFV1(_DirichletVelocity):
+    """fv1/bnd/inflow_fv1_impl.h:42-82: velocity = user data on the inflow subsets (Dirichlet part). The Neumann term of the
+    continuity equation over the boundary faces (ugcore NeumannBoundaryFV1) is not part of the device path yet."""
+
+    def add(self, user, boundary_nodes, coords=None):
+        if callable(user):
+            if coords is None:
+                raise UGError("NavierStokesInflow::add: coordinates needed to evaluate the user data")
+            vals = np.array([user(*coords[n]) for n in np.asarray(boundary_nodes).reshape(-1)], dtype=np.float64)
+        else:
+            vals = user
+        self._add(boundary_nodes, vals)
+
+
+class ThetaTimeStep:
+    """instationary combination (ugcore ThetaTimeStep drives add_jac_A/M, add_def_A/M with the scales
+    s_m = 1, s_a = theta dt at the new time point and s_m = -1, s_a = (1 - theta) dt at the old one,
+    fv1/navier_stokes_fv1.cpp:268-280,617-629): J = M + theta dt A(u_new),
+    d = M u_new - M u_old + dt [theta A(u_new) + (1 - theta) A(u_old)]. Two passes over the mesh, the second accumulates
+    (beta = 1); the Jacobian stays on the device (assemble_resident)."""
+
+    def __init__(self, disc, theta=1.0):
+        self.disc, self.theta = disc, float(theta)
+
+    def assemble(self, u_new, u_old, dt, scatter_mode=None):
+        d, th = self.disc, self.theta
+        full = capi.JAC_A | capi.JAC_M | capi.DEF_A | capi.DEF_M | capi.RHS
+        ts = (u_new, u_old, dt)
+        defect = d.assemble_resident(full, u_new, time_series=ts, scale_a=th * dt, scale_m=1.0, scatter_mode=scatter_mode)
+        a_old = (capi.DEF_A | capi.RHS) if th < 1.0 else 0
+        defect = d.assemble_resident(capi.DEF_M | a_old, u_old, defect=defect, time_series=ts, scale_a=(1.0 - th) * dt, scale_m=-1.0,
+                                     beta=1.0, scatter_mode=scatter_mode)
+        return defect
