@@ -182,7 +182,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config3: FV1 hex %d^3 per GPU, LPS upwind + FIELDS/RAW, nu=1e-2, Jacobian+defect (A part)" % args.n,
+        "config": {"workload": "config3: FV1 hex, LPS upwind + FIELDS/RAW, nu=1e-2, Jacobian+defect (A part); each step = a bounded "
+                               "sample of %d^3 = %d elements of the %d^3-per-GPU workload (a per-element rate)" % (n_sample, n_sample ** 3, args.n),
+                   "sample_cells": n_sample, "sample_elements": n_sample ** 3,
                    "reference_kind": "oracle port of the UG4 element routines (UG4 itself not buildable: ugcore absent)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -201,6 +203,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e-full", action="store_true", help="skip the full-matrix D2H variant of the end-to-end leg")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the owner-row check against the single-domain oracle")
+    ap.add_argument("--parity-n", type=int, default=6, help="N > 1: cells per direction per rank of the parity problem")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -289,32 +294,84 @@ def main():
     ms_per_step = total_ms / args.steps
     value = total_elems / (ms_per_step * 1e-3)
 
+    setup_s = disc.query(capi.Q_SETUP_SECONDS)
+    dev_bytes = disc.query(capi.Q_DEVICE_BYTES)
+
+    # ---- N > 1: numerics of the multi-GPU path, checked after the timed region on a small block problem: owner rows (matrix AND
+    # defect, interface rows included) after the NCCL interface summation against the single-domain CPU oracle ----
+    parity_maxrel = None
+    if world > 1 and not args.no_parity:
+        from plugin_navierstokes_b200 import partition
+        from oracle import oracle as ora            # the checker, outside every timed region
+        pn = args.parity_n
+        pp = partition.block_problem(pn, rank, world)
+        pd = pkg.NavierStokes("u,v,w,p", "Inner", "fv1", device=local)
+        pd.set_kinematic_viscosity(VISC); pd.set_upwind(UPWIND); pd.set_stabilization(STAB)
+        pd.set_grid("hex", pp["conn"], pp["coords"])
+        pu = torch.from_numpy(np.ascontiguousarray(pp["u"].reshape(-1))).to(dev)
+        pv, pdf = pd.assemble(what, pu, scatter_mode=mode)
+        pex = partition.InterfaceExchange(pd, pp["iface"], dev)
+        pex.sum_to_owner(pv, pdf)
+        torch.cuda.synchronize()
+        pd.check_errors()
+        gc, gconn, gu = partition.block_problem_global(pn, world)
+        prm = ora.make_params(elem="hex", upwind=UPWIND, stab=STAB, kin_visc=VISC)
+        grp, gci = ora.fv1_csr(ora.HEX, gconn, gc.shape[0])
+        gv, gd = ora.assemble(prm, gconn, gc, gu.reshape(-1), grp, gci, ora.JAC_A | ora.DEF_A, nthreads=max(1, (os.cpu_count() or 1) // world))
+        lrp, lci = pd.csr()
+        em, ed = partition.owner_rows_error(lrp, lci, pv.cpu().numpy(), pdf.cpu().numpy(), pp["iface"]["l2g"], pex.owner, rank, grp, gci, gv, gd, 4)
+        pt = torch.tensor([em, ed], dtype=torch.float64, device=dev)
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        parity_maxrel = {"matrix_rows": float(pt[0].item()), "defect": float(pt[1].item()),
+                         "problem": "hex %d^3 per rank, %d ranks, owner rows after sum_to_owner vs the single-domain oracle, relative to the largest entry" % (pn, world)}
+        pd.close()
+        del pv, pdf, pu
+
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
-    e2e = None
+    # e2e: the GPU-resident hand-off (nsb_assemble_resident + nsb_apply_jacobian): u goes up, the Jacobian stays on the device
+    #      where its consumer runs (matrix-vector product of the solver), defect and J*x come back.
+    # e2e_full_matrix: nsb_assemble(NSB_HOST), every CSR value returned to the host (a CPU solver's hand-off).
+    e2e, e2e_full = None, None
     if not args.no_e2e:
         try:
             hu = torch.from_numpy(np.ascontiguousarray(u.reshape(-1))).pin_memory()
-            hv = torch.empty(nnz, dtype=torch.float64).pin_memory()
             hd = torch.empty(n_dof, dtype=torch.float64).pin_memory()
+            hx = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, n_dof)).pin_memory()
+            hy = torch.empty(n_dof, dtype=torch.float64).pin_memory()
             del vals
             torch.cuda.empty_cache()
-            disc.assemble(what, hu.numpy(), values=hv.numpy(), defect=hd.numpy(), scatter_mode=mode)   # warm-up, allocates staging
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                disc.assemble(what, hu.numpy(), values=hv.numpy(), defect=hd.numpy(), scatter_mode=mode)
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / args.e2e_steps
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e = {"value": total_elems / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(8 * n_dof),
-                   "d2h_bytes_per_step": int(8 * (nnz + n_dof)),
-                   "note": "nsb_assemble(NSB_HOST): u from pinned host memory, CSR values + defect returned to pinned host memory"}
+
+            def timed(fn, steps):
+                fn()                                                   # warm-up, allocates staging
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    fn()
+                torch.cuda.synchronize()
+                tt = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return float(tt.item())
+
+            def resident_step():
+                disc.assemble_resident(what, hu.numpy(), defect=hd.numpy(), scatter_mode=mode)
+                disc.apply_jacobian(hx.numpy(), y=hy.numpy())
+
+            dt = timed(resident_step, max(args.e2e_steps, 3))
+            e2e = {"value": total_elems / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * 2 * n_dof), "d2h_bytes_per_step": int(8 * 2 * n_dof),
+                   "ms_per_step": dt * 1e3,
+                   "note": "nsb_assemble_resident(NSB_HOST) + nsb_apply_jacobian(NSB_HOST): u and x from pinned host memory, the CSR values "
+                           "stay on the device (GPU-resident hand-off, SURVEY 8f-2), defect and J*x returned to pinned host memory"}
+            if not args.no_e2e_full:
+                hv = torch.empty(nnz, dtype=torch.float64).pin_memory()
+                dtf = timed(lambda: disc.assemble(what, hu.numpy(), values=hv.numpy(), defect=hd.numpy(), scatter_mode=mode), args.e2e_steps)
+                e2e_full = {"value": total_elems / dtf, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_dof), "d2h_bytes_per_step": int(8 * (nnz + n_dof)),
+                            "ms_per_step": dtf * 1e3,
+                            "note": "nsb_assemble(NSB_HOST): u from pinned host memory, CSR values + defect returned to pinned host memory (host-solver hand-off; PCIe-bound)"}
         except Exception as ex:       # noqa: BLE001
-            e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+            e2e = e2e or {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -324,16 +381,26 @@ def main():
         if not args.no_cpu:
             threads = os.cpu_count() or 1
             r, ne_s, dt = cpu_baseline(args.ref_n, threads, sweeps=5)
+            n1 = max(8, args.ref_n // 3)
+            r1, ne_1, dt1 = cpu_baseline(n1, 1, sweeps=2)             # the UG4-like single-thread loop
             cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "hex %d^3 (%d elements) of the same workload, Jacobian sweep + defect sweep, best of 5 (%.1f s each)" % (args.ref_n, ne_s, dt)}
-        traffic, share = None, None
+                   "sample": "hex %d^3 (%d elements) of the same workload, Jacobian sweep + defect sweep, best of 5 (%.1f s each)" % (args.ref_n, ne_s, dt),
+                   "single_core": {"value": r1, "unit": UNIT, "cores": 1, "sample": "hex %d^3 (%d elements), best of 2 (%.1f s each)" % (n1, ne_1, dt1)}}
+        # DRAM traffic of one pass: from the ncu capture of THIS kernel code (profiles/traffic.json carries the digest of the
+        # CUDA sources it was taken with, written by tools/ncu_summary.py); a stale capture is not reported
+        traffic, share, traffic_note = None, None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
+                import build as _build
                 tj = json.load(open(tp))
-                bpe = tj["bytes_per_element"].get(args.mode)
-                traffic = bpe * n_elem if bpe else None          # per launch (= pass), scaled from the ncu capture
-                share = tj.get("kernel_share_ncu") if args.mode == "gather" else None
+                if tj.get("sources_digest") == _build._sources_digest():
+                    bpe = tj["bytes_per_element"].get(args.mode)
+                    traffic = bpe * n_elem if bpe else None          # per launch (= pass), scaled from the ncu capture
+                    share = tj.get("kernel_share_ncu") if args.mode == "gather" else None
+                    traffic_note = tj.get("note")
+                else:
+                    traffic_note = "profiles/traffic.json was captured with other kernel sources (stale): not reported"
             except Exception:
                 traffic = None
         out = {
@@ -343,13 +410,17 @@ def main():
             "config": {"workload": "config3: FV1 hex %d^3 per GPU (%d elements/GPU), LPS upwind + FIELDS/RAW, nu=1e-2, "
                                    "Jacobian+defect (A part) into global CSR" % (args.n, n_elem),
                        "scatter": args.mode, "l2": "inputs+outputs (%.1f GB) exceed L2, no flush needed" % (abytes / 1e9),
-                       "algorithmic_bytes_per_element": abytes / n_elem, "nnz": int(nnz), "colors": disc.num_colors},
+                       "algorithmic_bytes_per_element": abytes / n_elem, "nnz": int(nnz), "colors": disc.num_colors,
+                       "setup_s": setup_s, "device_bytes_resident": int(dev_bytes),
+                       "setup_note": "host preprocessing + table upload of nsb_upload_mesh, outside the timed region; the static Jacobian part J0 is built by the first pass"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kms,
-                         "kernel": "fv1 %s (all launches of one assembly pass: flux kernel + rows kernel)" % args.mode,
-                         "kernel_share_ncu": share},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                         "kernel": "fv1 %s (all launches of one assembly pass: fv1_flux_kernel + fv1_rows_owner_kernel)" % args.mode,
+                         "kernel_share_ncu": share, "traffic_note": traffic_note},
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_full_matrix": e2e_full, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if parity_maxrel is not None:
+            out["parity_maxrel"] = parity_maxrel
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -85,17 +85,55 @@ def block_problem(n, rank, world, noise=0.01):
     K, J, I = np.meshgrid(i + bz * n, i + by * n, i + bx * n, indexing="ij")
     gx, gy = px * n + 1, py * n + 1
     l2g = (I + gx * (J + gy * K)).ravel().astype(np.int64)
-    x, y, z = (np.pi * coords[:, d] for d in range(3))
-    xi = [1.0 + noise * gid_noise(l2g, 3, k) for k in range(3)]
-    u = np.stack([np.sin(x) * np.cos(y) * np.cos(z) * xi[0] + 0.05,
-                  -0.5 * np.cos(x) * np.sin(y) * np.cos(z) * xi[1] - 0.03,
-                  -0.5 * np.cos(x) * np.cos(y) * np.sin(z) * xi[2] + 0.02,
-                  np.cos(x) * np.cos(y) * np.cos(z)], axis=1)
+    u = block_state(coords, l2g, noise)
     # candidates for shared nodes: the block faces
     li = np.arange(n + 1)
     Kl, Jl, Il = np.meshgrid(li, li, li, indexing="ij")
     onface = ((Il == 0) | (Il == n) | (Jl == 0) | (Jl == n) | (Kl == 0) | (Kl == n)).ravel()
     return dict(coords=coords, conn=conn, u=u, iface=dict(l2g=l2g, boundary=np.nonzero(onface)[0]))
+
+
+def block_state(coords, gid, noise=0.01):
+    """the state of block_problem as a function of the coordinates and the GLOBAL node ids"""
+    x, y, z = (np.pi * coords[:, d] for d in range(3))
+    xi = [1.0 + noise * gid_noise(gid, 3, k) for k in range(3)]
+    return np.stack([np.sin(x) * np.cos(y) * np.cos(z) * xi[0] + 0.05,
+                     -0.5 * np.cos(x) * np.sin(y) * np.cos(z) * xi[1] - 0.03,
+                     -0.5 * np.cos(x) * np.cos(y) * np.sin(z) * xi[2] + 0.02,
+                     np.cos(x) * np.cos(y) * np.cos(z)], axis=1)
+
+
+def block_problem_global(n, world, noise=0.01):
+    """the single-domain version of block_problem: (coords, conn, u) of the whole (px n) x (py n) x (pz n) mesh, node ids =
+    the global ids of block_problem's l2g"""
+    from . import meshgen
+    px, py, pz = block_dims(world)
+    coords, conn = meshgen.hex_grid(px * n, py * n, pz * n)
+    return coords, conn, block_state(coords, np.arange(coords.shape[0], dtype=np.int64), noise)
+
+
+def owner_rows_error(rowptr, colind, vals, dfc, l2g, owner, rank, g_rowptr, g_colind, g_vals, g_dfc, nf, nodes=None):
+    """largest deviation of the OWNER's rows (matrix entries at the columns the rank holds, and defect entries) from the
+    single-domain result, relative to the largest magnitude of the global matrix / defect. nodes: local nodes to check
+    (default: every node the rank owns); rows of shared nodes are complete only after InterfaceExchange.sum_to_owner."""
+    import scipy.sparse as sp
+    n_g = g_rowptr.size - 1
+    G = sp.csr_matrix((g_vals, g_colind, g_rowptr), shape=(n_g, n_g))
+    sel = np.nonzero(owner == rank)[0] if nodes is None else np.asarray(nodes)
+    sel = sel[owner[sel] == rank]
+    emax, dmax = 0.0, 0.0
+    gscale, dscale = np.abs(g_vals).max(), np.abs(g_dfc).max()
+    rows_l = (sel[:, None] * nf + np.arange(nf)[None, :]).reshape(-1)
+    rows_g = (l2g[sel][:, None] * nf + np.arange(nf)[None, :]).reshape(-1)
+    for rl, rg in zip(rows_l, rows_g):
+        seg = slice(rowptr[rl], rowptr[rl + 1])
+        cl = colind[seg]
+        cg = l2g[cl // nf] * nf + cl % nf
+        ref = np.asarray(G[rg, cg].todense()).reshape(-1)
+        emax = max(emax, float(np.abs(vals[seg] - ref).max()) if cl.size else 0.0)
+    if dfc is not None and rows_l.size:
+        dmax = float(np.abs(dfc[rows_l] - g_dfc[rows_g]).max())
+    return emax / gscale, dmax / dscale
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -45,7 +45,8 @@ def _worker(rank, world, port, q):
         ex.copy_from_owner(cons)                                 # unique -> consistent over NCCL
         torch.cuda.synchronize()
         disc.check_errors()
-        q.put((rank, l2g, dfc.cpu().numpy(), ex.owner.copy(), ex.launches, cons.cpu().numpy()))
+        rowptr, colind = disc.csr()
+        q.put((rank, l2g, dfc.cpu().numpy(), ex.owner.copy(), ex.launches, cons.cpu().numpy(), vals.cpu().numpy(), rowptr, colind))
     finally:
         dist.destroy_process_group()
 
@@ -69,9 +70,14 @@ def test_two_gpu_defect_matches_single_domain(ora):
     u = meshgen.state_vortex3d(coords, seed=2, noise=0.05)
     prm = ora.make_params(elem="hex", upwind="lps", stab="fields", kin_visc=1e-2)
     rowptr, colind = ora.fv1_csr(ora.HEX, conn, coords.shape[0])
-    _, gd = ora.assemble(prm, conn, coords, u, rowptr, colind, ora.DEF_A)
+    gv, gd = ora.assemble(prm, conn, coords, u, rowptr, colind, ora.JAC_A | ora.DEF_A)
+    from plugin_navierstokes_b200 import partition
+    for rank, l2g, d, own, launches, cons, lv, lrp, lci in res:
+        # the summed MATRIX rows of every node the rank owns (interface rows included), at the columns the rank holds
+        em, ed = partition.owner_rows_error(lrp, lci, lv, d, l2g, own, rank, rowptr, colind, gv, gd, 4)
+        assert em < 1e-12 and ed < 1e-12, (rank, em, ed)
     gd = gd.reshape(-1, 4)
-    for rank, l2g, d, own, launches, cons in res:
+    for rank, l2g, d, own, launches, cons, lv, lrp, lci in res:
         mine = own == rank
         assert np.abs(d.reshape(-1, 4)[mine] - gd[l2g[mine]]).max() < 1e-12 * np.abs(gd).max()
         assert np.abs(cons.reshape(-1, 4) - gd[l2g]).max() < 1e-12 * np.abs(gd).max()     # every copy, after copy_from_owner
