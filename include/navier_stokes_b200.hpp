@@ -32,7 +32,11 @@ namespace nsb200 {
 struct UGError : std::runtime_error { using std::runtime_error::runtime_error; };   // stands for UG_THROW
 #define NSB_UG_THROW(msg) throw ::nsb200::UGError(msg)
 
-#ifndef NSB_WITH_UG4
+#ifdef NSB_WITH_UG4
+// ugcore's own types (the mock of tests/cpp/mock_ug when NSB_UG4_MOCK is defined; the real headers are included by the
+// translation unit before this one otherwise)
+using ug::number; using ug::LocalVector; using ug::LocalMatrix; using ug::ReferenceObjectID;
+#else
 typedef double number;
 enum ReferenceObjectID { ROID_TRIANGLE = 2, ROID_QUADRILATERAL = 3, ROID_TETRAHEDRON = 4, ROID_HEXAHEDRON = 5 };
 // u(fct, dof) / J(rfct, rdof, cfct, cdof): ugcore lib_disc/common/local_algebra.h access syntax
@@ -170,6 +174,8 @@ class NavierStokesDeviceDisc {
     void add_def_M_elem(LocalVector& d, const LocalVector&) { add_vec(d, m_dM); }
     void add_rhs_elem(LocalVector& d) { add_vec(d, m_rhs); }
     void fsh_elem_loop() {}                                       // fv1/navier_stokes_fv1.cpp:201-205
+    /// FVCR adapter: validation only (the device path has no per-element Crouzeix-Raviart blocks)
+    void prep_elem_loop_fast_only() { push_params(); check(nsb_prep_elem_loop(m_ctx)); }
 
     const char* last_error() const { return nsb_last_error(m_ctx); }
 
