@@ -148,6 +148,15 @@ int  nsb_set_dirichlet(nsb_ctx *ctx, int64_t n, const int64_t *dofs);
 int  nsb_adjust_jacobian(nsb_ctx *ctx, double *values);
 int  nsb_adjust_vector(nsb_ctx *ctx, double *vec, const double *g, int location);
 
+/* Per-ip data imports: the reference evaluates UserData for viscosity / density / source at the integration points
+ * (m_imKinViscosity, m_imDensitySCVF at the SCVF ips; m_imDensitySCV, m_imSourceSCV at the SCV ips; m_imSourceSCVF at the SCVF
+ * ips -- fv1/navier_stokes_fv1.cpp:184-197, read at :336,351,390,393,708,805,835,866 and fv1/stabilization.cpp:151,198,229).
+ * The caller evaluates its data at those points (any C++ / Lua UserData, e.g. a turbulent viscosity) and hands the arrays
+ * over; data == NULL returns to the constant of nsb_params. Layouts: [n_elem][nip], [n_elem][nsh], sources x dim. FV1 only; the
+ * element kernels honour them (NSB_SCATTER_GATHER is served by the coloured element kernel while any array is set). */
+enum { NSB_IP_KIN_VISC_SCVF = 0, NSB_IP_DENSITY_SCVF = 1, NSB_IP_DENSITY_SCV = 2, NSB_IP_SOURCE_SCVF = 3, NSB_IP_SOURCE_SCV = 4 };
+int  nsb_set_ip_data(nsb_ctx *ctx, int kind, const double *data, int location);
+
 /* NSB_DEVICE calls are asynchronous: element-level failures (the reference's UG_THROW inside upwind /
  * stabilisation code, upwind.cpp:354, stabilization.cpp:292,641) are latched on the device; this call
  * synchronises and reports them (NSB_ERR_GEOMETRY). NSB_HOST calls do it implicitly. */

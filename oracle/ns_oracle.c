@@ -612,6 +612,14 @@ typedef struct {
 } Stab;
 
 #define U_(f,sh)  (u[(f)*nsh+(sh)])
+/* per-ip data imports (m_imKinViscosity[ip], m_imDensitySCVF[ip], m_imDensitySCV[ip], m_imSourceSCV(F)[ip]) or the constants */
+#define VISC(ip)    (p->ip_visc ? p->ip_visc[p->elem_index*nip+(ip)] : p->kin_visc)
+#define RHOF(ip)    (p->ip_rho_scvf ? p->ip_rho_scvf[p->elem_index*nip+(ip)] : p->density)
+#define RHOV(sh)    (p->ip_rho_scv ? p->ip_rho_scv[p->elem_index*nsh+(sh)] : p->density)
+#define HAS_SRCF    (p->has_source || p->ip_src_scvf)
+#define SRCF(ip,d)  (p->ip_src_scvf ? p->ip_src_scvf[(p->elem_index*nip+(ip))*dim+(d)] : p->source[d])
+#define HAS_SRCV    (p->has_source || p->ip_src_scv)
+#define SRCV(sh,d)  (p->ip_src_scv ? p->ip_src_scv[(p->elem_index*nsh+(sh))*dim+(d)] : p->source[d])
 
 /* NavierStokesFIELDSStabilization::update, stabilization.cpp:122-404 */
 static int stab_fields(const ora_params *p, const Geom *g, const double *u /*vCornerValue*/,
@@ -622,7 +630,7 @@ static int stab_fields(const ora_params *p, const Geom *g, const double *u /*vCo
     if (!bStokes) if (upwind_compute(p->stab_upwind, g, stdvel, &s->up)) return -1;
     double dl[MAXIP]; if (diff_length(p->diff_len, g, dl)) return -1;
     double a[MAXIP], b[MAXIP];
-    for (int ip = 0; ip < nip; ip++) a[ip] = p->kin_visc * dl[ip];
+    for (int ip = 0; ip < nip; ip++) a[ip] = VISC(ip) * dl[ip];
     if (!bStokes) for (int ip = 0; ip < nip; ip++) b[ip] = sqrt(vdot(stdvel[ip], stdvel[ip], dim)) / s->up.len[ip];
     /* off-diagonal vel shapes are never written by FIELDS (stale in the reference): poison */
     for (int ip = 0; ip < nip; ip++) for (int d = 0; d < 3; d++) for (int d2 = 0; d2 < 3; d2++)
@@ -635,14 +643,14 @@ static int stab_fields(const ora_params *p, const Geom *g, const double *u /*vCo
             if (!bStokes) diag += b[ip];
             for (int d = 0; d < dim; d++) {
                 double rhs = 0.0;
-                if (p->has_source) rhs = p->source[d];
+                if (HAS_SRCF) rhs = SRCF(ip,d);
                 if (uold) { double o = 0.0; for (int sh = 0; sh < nsh; sh++) o += g->N[ip][sh]*uold[d*nsh+sh]; rhs += o/dt; }
                 for (int k = 0; k < nsh; k++) {
                     double sumVel = a[ip]*g->N[ip][k];
                     if (!bStokes) sumVel += b[ip]*s->up.sh[ip][k];
                     rhs += sumVel*U_(d,k);
                     s->sv[ip][d][d][k] = sumVel/diag;
-                    double sumP = -1.0*g->G[ip][k][d]/p->density;
+                    double sumP = -1.0*g->G[ip][k][d]/RHOF(ip);
                     rhs += sumP*U_(P,k);
                     s->sp[ip][d][k] = sumP/diag;
                 }
@@ -664,7 +672,7 @@ static int stab_fields(const ora_params *p, const Geom *g, const double *u /*vCo
             for (int ip = 0; ip < nip; ip++) for (int k = 0; k < nsh; k++) {
                 cV[k][ip] = a[ip]*g->N[ip][k];
                 cV[k][ip] += b[ip]*s->up.sh[ip][k];
-                cP[k][ip] = -1.0*g->G[ip][k][d]/p->density;
+                cP[k][ip] = -1.0*g->G[ip][k][d]/RHOF(ip);
             }
             for (int k = 0; k < nsh; k++) {
                 lu_solve(&lu, cV[k], x); for (int ip = 0; ip < nip; ip++) s->sv[ip][d][d][k] = x[ip];
@@ -672,7 +680,7 @@ static int stab_fields(const ora_params *p, const Geom *g, const double *u /*vCo
             }
             for (int ip = 0; ip < nip; ip++) {
                 f[ip] = 0.0;
-                if (p->has_source) f[ip] = p->source[d];
+                if (HAS_SRCF) f[ip] = SRCF(ip,d);
                 if (uold) { double o = 0.0; for (int sh = 0; sh < nsh; sh++) o += g->N[ip][sh]*uold[d*nsh+sh]; f[ip] += o/dt; }
             }
             for (int k = 0; k < nsh; k++) for (int ip = 0; ip < nip; ip++) {
@@ -700,7 +708,7 @@ static int stab_flow(const ora_params *p, const Geom *g, const double *u, const 
     }
     double dl[MAXIP]; if (diff_length(p->diff_len, g, dl)) return -1;
     double a[MAXIP], b[MAXIP], c[MAXIP];
-    for (int ip = 0; ip < nip; ip++) a[ip] = p->kin_visc * dl[ip];
+    for (int ip = 0; ip < nip; ip++) a[ip] = VISC(ip) * dl[ip];
     if (!bStokes) for (int ip = 0; ip < nip; ip++) {
         double norm = sqrt(vdot(stdvel[ip], stdvel[ip], dim));
         b[ip] = norm / s->up.len[ip];
@@ -713,7 +721,7 @@ static int stab_flow(const ora_params *p, const Geom *g, const double *u, const 
             if (!bStokes) diag += b[ip];
             for (int d = 0; d < dim; d++) {
                 double rhs = 0.0;
-                if (p->has_source) rhs = p->source[d];
+                if (HAS_SRCF) rhs = SRCF(ip,d);
                 if (uold) { double o = 0.0; for (int sh = 0; sh < nsh; sh++) o += g->N[ip][sh]*uold[d*nsh+sh]; rhs += o/dt; }
                 for (int k = 0; k < nsh; k++) {
                     double sumVel = a[ip]*g->N[ip][k];
@@ -730,7 +738,7 @@ static int stab_flow(const ora_params *p, const Geom *g, const double *u, const 
                         rhs += sumVel2*U_(d2,k);
                         s->sv[ip][d][d2][k] = sumVel2/diag;
                     }
-                    double sumP = -1.0*g->G[ip][k][d]/p->density;
+                    double sumP = -1.0*g->G[ip][k][d]/RHOF(ip);
                     rhs += sumP*U_(P,k);
                     s->sp[ip][d][k] = sumP/diag;
                 }
@@ -752,7 +760,7 @@ static int stab_flow(const ora_params *p, const Geom *g, const double *u, const 
         double cV[3][MAXSH][MAXIP], cP[MAXSH][MAXIP], x[MAXIP], f[MAXIP];
         for (int d = 0; d < dim; d++) {
             for (int ip = 0; ip < nip; ip++) for (int k = 0; k < nsh; k++) {
-                cP[k][ip] = -1.0*g->G[ip][k][d]/p->density;
+                cP[k][ip] = -1.0*g->G[ip][k][d]/RHOF(ip);
                 cV[d][k][ip] = a[ip]*g->N[ip][k];
                 cV[d][k][ip] += b[ip]*s->up.sh[ip][k];
                 cV[d][k][ip] += c[ip]*(s->down.sh[ip][k] - s->up.sh[ip][k]);
@@ -772,7 +780,7 @@ static int stab_flow(const ora_params *p, const Geom *g, const double *u, const 
                 f[ip] += U_(P,k)*cP[k][ip];
             }
             for (int ip = 0; ip < nip; ip++) {
-                if (p->has_source) f[ip] += p->source[d];
+                if (HAS_SRCF) f[ip] += SRCF(ip,d);
                 if (uold) { double o = 0.0; for (int sh = 0; sh < nsh; sh++) o += g->N[ip][sh]*uold[d*nsh+sh]; f[ip] += o/dt; }
             }
             lu_solve(&lu, f, x);
@@ -871,8 +879,8 @@ static int fv1_jac_A(const ora_params *p, const FV1Ctx *c, const double *u, doub
 {
     const Geom *g = &c->g; const Stab *stab = &c->stab, *convStab = &c->stab; const Upw *upwind = c->upw;
     int dim = g->dim, nsh = g->nsh, nip = g->nip, P = dim, L = (dim+1)*nsh;
-    double visc = p->kin_visc, rho = p->density;
     for (int ip = 0; ip < nip; ip++) {
+        const double visc = VISC(ip), rho = RHOF(ip);
         int f = g->from[ip], t = g->to[ip]; const double *n = g->n[ip];
         for (int sh = 0; sh < nsh; sh++) {
             double flux_sh = -1.0*visc*rho*vdot(g->G[ip][sh], n, dim);
@@ -967,8 +975,8 @@ static int fv1_def_A(const ora_params *p, const FV1Ctx *c, const double *u, doub
 {
     const Geom *g = &c->g; const Stab *stab = &c->stab; const Upw *upwind = c->upw;
     int dim = g->dim, nsh = g->nsh, nip = g->nip, P = dim;
-    double visc = p->kin_visc, rho = p->density;
     for (int ip = 0; ip < nip; ip++) {
+        const double visc = VISC(ip), rho = RHOF(ip);
         int f = g->from[ip], t = g->to[ip]; const double *n = g->n[ip];
         double gradVel[3][3], diff[3];
         for (int d1 = 0; d1 < dim; d1++) for (int d2 = 0; d2 < dim; d2++) {
@@ -1010,10 +1018,10 @@ int ora_fv1_elem(const ora_params *p, const double *coords, const double *u,
         if ((what & ORA_DEF_A) && fv1_def_A(p, &c, u, dloc)) return -1;
     } else if (geom_update(&c.g, p->elem, coords)) return -1;
     /* add_jac_M_elem :781-808, add_def_M_elem :811-838, add_rhs_elem :841-869 */
-    if (what & ORA_JAC_M) for (int sh = 0; sh < nsh; sh++) for (int d1 = 0; d1 < dim; d1++) JL(d1,sh,d1,sh) += c.g.vol[sh]*p->density;
-    if (what & ORA_DEF_M) for (int sh = 0; sh < nsh; sh++) for (int d1 = 0; d1 < dim; d1++) DL(d1,sh) += U_(d1,sh)*c.g.vol[sh]*p->density;
-    if ((what & ORA_RHS) && p->has_source)
-        for (int sh = 0; sh < nsh; sh++) for (int d1 = 0; d1 < dim; d1++) DL(d1,sh) += p->source[d1]*c.g.vol[sh]*p->density;
+    if (what & ORA_JAC_M) for (int sh = 0; sh < nsh; sh++) for (int d1 = 0; d1 < dim; d1++) JL(d1,sh,d1,sh) += c.g.vol[sh]*RHOV(sh);
+    if (what & ORA_DEF_M) for (int sh = 0; sh < nsh; sh++) for (int d1 = 0; d1 < dim; d1++) DL(d1,sh) += U_(d1,sh)*c.g.vol[sh]*RHOV(sh);
+    if ((what & ORA_RHS) && HAS_SRCV)
+        for (int sh = 0; sh < nsh; sh++) for (int d1 = 0; d1 < dim; d1++) DL(d1,sh) += SRCV(sh,d1)*c.g.vol[sh]*RHOV(sh);
     return 0;
 }
 
@@ -1396,11 +1404,13 @@ static int colour_elements(int64_t n_elem, int64_t n_ent, int per, const int32_t
     return ncol;
 }
 
-static int assemble_one(const ora_params *p, int64_t e, int64_t n_ent, const int32_t *conn,
+static int assemble_one(const ora_params *p0, int64_t e, int64_t n_ent, const int32_t *conn,
                         const double *coords, const int32_t *es, const double *u, const double *sol0,
                         const double *sol1, const int64_t *rowptr, const int32_t *colind, int what,
                         double scale_a, double scale_m, double *values, double *defect)
 {
+    ora_params pe = *p0; pe.elem_index = e;                   /* the per-ip imports are read at this element's slice */
+    const ora_params *p = &pe;
     int nco = ora_elem_nsh(p->elem), dim = ora_elem_dim(p->elem);
     double xc[MAXSH*3], ul[MAXL], s0[MAXL], s1[MAXL], Jl[MAXL*MAXL], dl[MAXL];
     int64_t gidx[MAXL]; int L;

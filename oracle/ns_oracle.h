@@ -52,6 +52,14 @@ typedef struct {
     double  kin_visc, density;
     double  source[3];
     double  dt;
+    /* per-ip data imports (fv1/navier_stokes_fv1.cpp:184-197; FV1 only; NULL = the constants above). Global arrays over the
+     * elements, the element routines read the slice of element `elem_index` (set per element by ora_assemble). */
+    const double *ip_visc;       /* [n_elem][nip]       m_imKinViscosity at the SCVF ips   */
+    const double *ip_rho_scvf;   /* [n_elem][nip]       m_imDensitySCVF                    */
+    const double *ip_rho_scv;    /* [n_elem][nsh]       m_imDensitySCV (mass / rhs parts)  */
+    const double *ip_src_scvf;   /* [n_elem][nip][dim]  m_imSourceSCVF (closure)           */
+    const double *ip_src_scv;    /* [n_elem][nsh][dim]  m_imSourceSCV  (add_rhs_elem)      */
+    int64_t elem_index;
 } ora_params;
 
 /* FV1 geometry of one element, for the geometry tests. Arrays sized for hex. */

@@ -32,7 +32,10 @@ class Params(C.Structure):
                 ("defect_upwind", C.c_int32), ("time_dependent", C.c_int32), ("has_source", C.c_int32),
                 ("pad0", C.c_int32), ("exact_jac", C.c_double), ("grad_div", C.c_double),
                 ("kin_visc", C.c_double), ("density", C.c_double), ("source", C.c_double * 3),
-                ("dt", C.c_double)]
+                ("dt", C.c_double),
+                # per-ip data imports (FV1): global arrays [n_elem][nip] / [n_elem][nsh] (x dim for the sources), NULL = constants
+                ("ip_visc", C.c_void_p), ("ip_rho_scvf", C.c_void_p), ("ip_rho_scv", C.c_void_p), ("ip_src_scvf", C.c_void_p),
+                ("ip_src_scv", C.c_void_p), ("elem_index", C.c_int64)]
 
 
 class FV1Geom(C.Structure):
@@ -228,9 +231,28 @@ def fvcr_csr(elem, elem_sides, n_side):
     return rowptr, colind
 
 
+IP_KINDS = ("visc", "rho_scvf", "rho_scv", "src_scvf", "src_scv")
+
+
 def assemble(p, conn, coords, u, rowptr, colind, what, sol0=None, sol1=None, elem_sides=None, n_side=0,
-             scale_a=1.0, scale_m=1.0, nthreads=1, values=None, defect=None):
-    """Serial (or coloured-threaded) element loop + scatter. returns (values, defect)."""
+             scale_a=1.0, scale_m=1.0, nthreads=1, values=None, defect=None, ip_data=None):
+    """Serial (or coloured-threaded) element loop + scatter. returns (values, defect).
+    ip_data: {kind: array} per-ip data imports (FV1), kinds = IP_KINDS, arrays [n_elem][nip | nsh]([dim])."""
+    keep = {}
+    for kind in IP_KINDS:
+        a = None if ip_data is None else ip_data.get(kind)
+        if a is not None:
+            a = keep[kind] = np.ascontiguousarray(a, dtype=np.float64)
+        setattr(p, "ip_" + kind, a.ctypes.data if a is not None else None)
+    try:
+        return _assemble(p, conn, coords, u, rowptr, colind, what, sol0, sol1, elem_sides, n_side, scale_a, scale_m, nthreads, values, defect)
+    finally:
+        for kind in IP_KINDS:
+            setattr(p, "ip_" + kind, None)
+
+
+def _assemble(p, conn, coords, u, rowptr, colind, what, sol0=None, sol1=None, elem_sides=None, n_side=0,
+              scale_a=1.0, scale_m=1.0, nthreads=1, values=None, defect=None):
     conn = np.ascontiguousarray(conn, dtype=np.int32)
     coords = _f64(coords)
     u, sol0, sol1 = _f64(u), _f64(sol0), _f64(sol1)

@@ -23,8 +23,9 @@ SYMBOLS = [
     "nsb_prep_elem_loop", "nsb_assemble", "nsb_local_contributions", "nsb_pack", "nsb_unpack_add",
     "nsb_launch_count", "nsb_synchronize", "nsb_version", "nsb_check_errors", "nsb_query",
     "nsb_assemble_resident", "nsb_resident_jacobian", "nsb_apply_jacobian", "nsb_set_dirichlet", "nsb_adjust_jacobian",
-    "nsb_adjust_vector",
+    "nsb_adjust_vector", "nsb_set_ip_data",
 ]
+IP_KIN_VISC_SCVF, IP_DENSITY_SCVF, IP_DENSITY_SCV, IP_SOURCE_SCVF, IP_SOURCE_SCV = range(5)
 
 
 class Params(C.Structure):
@@ -92,5 +93,6 @@ def lib():
     L.nsb_set_dirichlet.argtypes = [vp, i64, vp]
     L.nsb_adjust_jacobian.argtypes = [vp, vp]
     L.nsb_adjust_vector.argtypes = [vp, vp, vp, i32]
+    L.nsb_set_ip_data.argtypes = [vp, i32, vp, i32]
     _lib = L
     return L

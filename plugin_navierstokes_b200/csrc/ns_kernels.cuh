@@ -25,6 +25,12 @@ struct MeshDev {
     int32_t l2_hints;           // rows kernel of the split path: L2 eviction-priority hints on the bulk copies
     int32_t ticket_group;       // rows kernel of the split path: nodes per atomic ticket
     const uint8_t* elem_fast;   // hex: 1 = element is star-shaped w.r.t. its ips (predicted-side ray search allowed), may be null
+    // per-ip data imports (fv1/navier_stokes_fv1.cpp:184-197), null = the constants of KParams; element kernels only
+    const double* ip_visc;      // [n_elem][NIP]       m_imKinViscosity at the SCVF ips
+    const double* ip_rho_scvf;  // [n_elem][NIP]       m_imDensitySCVF
+    const double* ip_rho_scv;   // [n_elem][NSH]       m_imDensitySCV (mass / rhs parts)
+    const double* ip_src_scvf;  // [n_elem][NIP][DIM]  m_imSourceSCVF (closure of the stabilisation)
+    const double* ip_src_scv;   // [n_elem][NSH][DIM]  m_imSourceSCV (add_rhs_elem)
 };
 
 enum { SC_COLORED = 1, SC_ATOMIC = 2, SC_LOCAL = 3 };
@@ -110,7 +116,17 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
     }
     if (active && col < NIP) {
         const double* ps0 = p.time_dep ? ws.s0 : ws.u;
-        const bool ok = ip_eval<E, PAC>(p, ws.x, ws.u, ps0, ws.s1, ws.vol, col, cmn, cav, cmd, ws.rec[col]);
+        bool ok;
+        if (m.ip_visc || m.ip_rho_scvf || m.ip_src_scvf) {
+            // per-ip data imports: every use of viscosity / density / source in the ip evaluation is local to the ip
+            // (m_imKinViscosity[ip], m_imDensitySCVF[ip], (*pSource)[ip]; fv1/navier_stokes_fv1.cpp:336-772, stabilization.cpp:151-229)
+            KParams pl = p;
+            const int64_t gi = e * NIP + col;
+            if (m.ip_visc) pl.visc = m.ip_visc[gi];
+            if (m.ip_rho_scvf) { pl.rho = m.ip_rho_scvf[gi]; pl.inv_rho = 1.0 / pl.rho; }
+            if (m.ip_src_scvf) { pl.has_source = 1; for (int d = 0; d < DIM; d++) pl.src[d] = m.ip_src_scvf[gi * DIM + d]; }
+            ok = ip_eval<E, PAC>(pl, ws.x, ws.u, ps0, ws.s1, ws.vol, col, cmn, cav, cmd, ws.rec[col]);
+        } else ok = ip_eval<E, PAC>(p, ws.x, ws.u, ps0, ws.s1, ws.vol, col, cmn, cav, cmd, ws.rec[col]);
         if (!ok) atomicExch(errflag, 1);
     }
     __syncwarp();
@@ -134,7 +150,7 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
             for (int i = 0; i < L; i++) acc[i] *= p.scale_a;
         }
         if ((p.what & W_JAC_M) && cf < DIM) {           // add_jac_M_elem :781-808
-            const double mv = p.scale_m * ws.vol[k] * p.rho;
+            const double mv = p.scale_m * ws.vol[k] * (m.ip_rho_scv ? m.ip_rho_scv[e * NSH + k] : p.rho);
 #pragma unroll
             for (int a = 0; a < NSH; a++)
 #pragma unroll
@@ -173,9 +189,11 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
                 d += (double)tab::INC_SIGN[E][k][t] * ws.rec[ip].F[cf];
             }
         }
-        if ((p.what & W_RHS) && p.has_source && cf < DIM) d -= p.src[cf] * ws.vol[k] * p.rho;   // add_rhs_elem :841-869
+        const double rho_v = m.ip_rho_scv ? m.ip_rho_scv[e * NSH + k] : p.rho;
+        if ((p.what & W_RHS) && (p.has_source || m.ip_src_scv) && cf < DIM)
+            d -= (m.ip_src_scv ? m.ip_src_scv[(e * NSH + k) * DIM + cf] : p.src[cf]) * ws.vol[k] * rho_v;   // add_rhs_elem :841-869
         d *= p.scale_a;
-        if ((p.what & W_DEF_M) && cf < DIM) d += p.scale_m * ws.u[k * NF + cf] * ws.vol[k] * p.rho;   // :811-838
+        if ((p.what & W_DEF_M) && cf < DIM) d += p.scale_m * ws.u[k * NF + cf] * ws.vol[k] * rho_v;   // :811-838
         if (SC == SC_LOCAL) dloc[e * (int64_t)L + cf * NSH + k] = d;
         else {
             double* q = def + (int64_t)ws.node[k] * NF + cf;

@@ -177,6 +177,7 @@ struct nsb_ctx {
     double* d_geo = nullptr; int geo_diff_len = -1;   // static SCVF geometry records of the fused kernel (per diffusion-length type)
     int32_t n_patch = 0; int max_adj = 0;
     int64_t scvf_evals = 0, patch_table_bytes = 0;
+    double* d_ip[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // per-ip data imports (nsb_set_ip_data), indexed by NSB_IP_*
     // GPU-resident Jacobian hand-off + Dirichlet post-pass
     int32_t* d_bcol = nullptr; int64_t* d_rowptr = nullptr;   // block columns (FV1) / scalar pattern (FVCR), uploaded on first use
     double* d_jres = nullptr;                                  // resident CSR values (nsb_assemble_resident)
@@ -256,6 +257,7 @@ static void free_mesh(nsb_ctx* c)
     cudaFree(c->d_jloc); cudaFree(c->d_dloc); cudaFree(c->d_j0);
     cudaFree(c->d_phdr); cudaFree(c->d_pnodes); cudaFree(c->d_pelems); cudaFree(c->d_pconn); cudaFree(c->d_pwork); cudaFree(c->d_padj);
     cudaFree(c->d_nodevol); cudaFree(c->d_elem_fast); cudaFree(c->d_geo);
+    for (int i = 0; i < 5; i++) { cudaFree(c->d_ip[i]); c->d_ip[i] = nullptr; }
     cudaFree(c->d_bcol); cudaFree(c->d_rowptr); cudaFree(c->d_jres); cudaFree(c->d_xin); cudaFree(c->d_yout); cudaFree(c->d_dir); cudaFree(c->d_dirval);
     c->d_bcol = nullptr; c->d_rowptr = nullptr; c->d_jres = nullptr; c->d_xin = c->d_yout = nullptr; c->d_dir = nullptr; c->n_dir = 0; c->d_dirval = nullptr;
     cudaFree(c->d_plnodes); cudaFree(c->d_pecorner); c->d_plnodes = nullptr; c->d_pecorner = nullptr; c->tile_ok = false;
@@ -603,6 +605,8 @@ static MeshDev mesh_view(const nsb_ctx* c)
     m.node_order = getenv("NSB_ZORDER") ? c->d_node_order : nullptr;   // opt-in: measured neutral on B200 (profiles/)
     { const char* ev = getenv("NSB_L2HINT"); m.l2_hints = ev ? atoi(ev) : 0; }
     m.elem_fast = c->d_elem_fast;
+    m.ip_visc = c->d_ip[NSB_IP_KIN_VISC_SCVF]; m.ip_rho_scvf = c->d_ip[NSB_IP_DENSITY_SCVF]; m.ip_rho_scv = c->d_ip[NSB_IP_DENSITY_SCV];
+    m.ip_src_scvf = c->d_ip[NSB_IP_SOURCE_SCVF]; m.ip_src_scv = c->d_ip[NSB_IP_SOURCE_SCV];
     { const char* ev = getenv("NSB_TICKET_GROUP"); const int v = ev ? atoi(ev) : 4; m.ticket_group = v >= 1 ? v : 4; }
     return m;
 }
@@ -754,7 +758,9 @@ static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u,
                         double beta, double* val, double* def)
 {
     const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
-    if (mode == NSB_SCATTER_GATHER && (needs_dense(k) || k.pac)) mode = NSB_SCATTER_COLORED;   // dense ip systems / PAC need whole elements
+    const bool ip_data = c->d_ip[0] || c->d_ip[1] || c->d_ip[2] || c->d_ip[3] || c->d_ip[4];
+    if (ip_data && needs_dense(k)) return set_err(c, NSB_ERR_UNSUPPORTED, "per-ip data imports with PositiveUpwind (dense ip systems) are not provided on the device path");
+    if (mode == NSB_SCATTER_GATHER && (needs_dense(k) || k.pac || ip_data)) mode = NSB_SCATTER_COLORED;   // dense ip systems / PAC / per-ip data: element kernels
     if (mode == NSB_SCATTER_GATHER) return launch_gather(c, k, u, s0, s1, beta, val, def);
     // element kernels accumulate into beta*old
     if (jac) {
@@ -994,6 +1000,27 @@ extern "C" int nsb_apply_jacobian(nsb_ctx* c, const double* values, double alpha
     if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(c->d_yout, y, nb, cudaMemcpyHostToDevice, c->stream));
     if ((rc = spmv_launch(c, val, alpha, c->d_xin, beta, c->d_yout))) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(y, c->d_yout, nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return NSB_OK;
+}
+
+// per-ip data imports (fv1/navier_stokes_fv1.cpp:184-197: m_imKinViscosity / m_imDensitySCVF at the SCVF ips, m_imDensitySCV /
+// m_imSourceSCV at the SCV ips, m_imSourceSCVF at the SCVF ips). data == NULL returns to the constant of nsb_params.
+extern "C" int nsb_set_ip_data(nsb_ctx* c, int kind, const double* data, int location)
+{
+    if (!c || kind < 0 || kind > 4) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_set_ip_data: no grid uploaded");
+    if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_ip_data: FV1 only");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    static const int kNIP[4] = {3, 4, 6, 12};
+    const int dim = kDIM[c->elem], nsh = kNSH[c->elem], nip = kNIP[c->elem];
+    const size_t per = kind == NSB_IP_KIN_VISC_SCVF || kind == NSB_IP_DENSITY_SCVF ? (size_t)nip : kind == NSB_IP_DENSITY_SCV ? (size_t)nsh
+                     : kind == NSB_IP_SOURCE_SCVF ? (size_t)nip * dim : (size_t)nsh * dim;
+    if (!data) { cudaFree(c->d_ip[kind]); c->d_ip[kind] = nullptr; return NSB_OK; }
+    if (!c->d_ip[kind]) CUDA_TRY(c, dev_malloc(c, &c->d_ip[kind], (size_t)c->n_elem * per * sizeof(double)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_ip[kind], data, (size_t)c->n_elem * per * sizeof(double),
+                                location == NSB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return NSB_OK;
 }

@@ -147,15 +147,32 @@ class _DeviceDisc:
         self.scatter_mode = capi.SCATTER_GATHER
 
     # ---- NavierStokesBase (register_navier_stokes.cpp:105-126) ----
+    # UserData imports: a number (constant), or a callable f(x) -> value evaluated by the HOST at the integration points the
+    # reference evaluates its imports at (fv1/navier_stokes_fv1.cpp:184-197) and handed to the device as per-ip arrays
+    # (nsb_set_ip_data); Lua callback NAMES (the const char* overloads) cannot be resolved outside a Lua state.
     def set_kinematic_viscosity(self, v):
-        if callable(v) or isinstance(v, str):
-            raise UGError("device path: kinematic viscosity must be a number (Lua/UserData callbacks cannot run on device)")
-        self._visc = float(v)
+        if isinstance(v, str):
+            raise UGError("device path: Lua callback names cannot be resolved (pass a number or a Python callable)")
+        self._ip_fn = getattr(self, "_ip_fn", {})
+        if callable(v):
+            self._ip_fn["visc"] = v
+            self._visc = float("nan") if self._visc is None else self._visc      # "data given"
+        else:
+            self._ip_fn.pop("visc", None)
+            self._visc = float(v)
+        self._ip_dirty = True
 
     def set_source(self, v):
-        if callable(v) or isinstance(v, str):
-            raise UGError("device path: source must be a constant vector")
-        self._source = [float(x) for x in v]
+        if isinstance(v, str):
+            raise UGError("device path: Lua callback names cannot be resolved (pass a vector or a Python callable)")
+        self._ip_fn = getattr(self, "_ip_fn", {})
+        if callable(v):
+            self._ip_fn["source"] = v
+            self._source = None
+        else:
+            self._ip_fn.pop("source", None)
+            self._source = [float(x) for x in v]
+        self._ip_dirty = True
 
     def set_exact_jacobian(self, v):
         # bool overload -> 1.0/0.0, number overload -> factor (navier_stokes_base.h)
@@ -163,9 +180,15 @@ class _DeviceDisc:
 
     # ---- IncompressibleNavierStokesBase (incompressible_navier_stokes_plugin.cpp:244-266) ----
     def set_density(self, v):
-        if callable(v) or isinstance(v, str):
-            raise UGError("device path: density must be a number")
-        self._density = float(v)
+        if isinstance(v, str):
+            raise UGError("device path: Lua callback names cannot be resolved (pass a number or a Python callable)")
+        self._ip_fn = getattr(self, "_ip_fn", {})
+        if callable(v):
+            self._ip_fn["density"] = v
+        else:
+            self._ip_fn.pop("density", None)
+            self._density = float(v)
+        self._ip_dirty = True
 
     def set_peclet_blend(self, b):
         self._peclet = bool(b)
@@ -377,6 +400,46 @@ class _DeviceDisc:
                                                   capi.DEVICE if on_dev else capi.HOST))
         return y
 
+    # ---- per-ip data imports ----
+    _IP_KINDS = {"visc": capi.IP_KIN_VISC_SCVF, "rho_scvf": capi.IP_DENSITY_SCVF, "rho_scv": capi.IP_DENSITY_SCV,
+                 "src_scvf": capi.IP_SOURCE_SCVF, "src_scv": capi.IP_SOURCE_SCV}
+
+    def set_ip_data(self, kind, data):
+        """per-ip array of one import (kind: visc | rho_scvf | rho_scv | src_scvf | src_scv; layouts of nsb_set_ip_data), None clears it"""
+        k = self._IP_KINDS[kind]
+        if data is None:
+            self._check(capi.lib().nsb_set_ip_data(self._context(), k, None, capi.HOST))
+            return
+        if _is_torch(data):
+            self._check(capi.lib().nsb_set_ip_data(self._context(), k, C.c_void_p(data.data_ptr()), capi.DEVICE))
+        else:
+            a = np.ascontiguousarray(data, dtype=np.float64)
+            self._check(capi.lib().nsb_set_ip_data(self._context(), k, a.ctypes.data, capi.HOST))
+
+    def _push_ip_data(self):
+        """evaluates callable UserData at the integration points of the uploaded grid (once per change)"""
+        fns = getattr(self, "_ip_fn", {})
+        if not getattr(self, "_ip_dirty", False) or getattr(self, "_grid_host", None) is None:
+            return
+        from . import meshgen
+        elem, conn, coords = self._grid_host
+        name = {v: k for k, v in _ELEMS.items()}[elem]
+        xf = meshgen.fv1_scvf_ips(name, conn, coords)
+        xv = meshgen.fv1_scv_ips(name, conn, coords)
+
+        def ev(fn, x, ncomp):
+            flat = x.reshape(-1, x.shape[-1])
+            out = np.array([np.atleast_1d(fn(*pt)) for pt in flat], dtype=np.float64)
+            return out.reshape(x.shape[:-1] + ((ncomp,) if ncomp > 1 else ()))
+
+        dim = coords.shape[1]
+        self.set_ip_data("visc", ev(fns["visc"], xf, 1) if "visc" in fns else None)
+        self.set_ip_data("rho_scvf", ev(fns["density"], xf, 1) if "density" in fns else None)
+        self.set_ip_data("rho_scv", ev(fns["density"], xv, 1) if "density" in fns else None)
+        self.set_ip_data("src_scvf", ev(fns["source"], xf, dim) if "source" in fns else None)
+        self.set_ip_data("src_scv", ev(fns["source"], xv, dim) if "source" in fns else None)
+        self._ip_dirty = False
+
     def set_dirichlet(self, dofs):
         dofs = np.ascontiguousarray(dofs, dtype=np.int64).reshape(-1)
         self._check(capi.lib().nsb_set_dirichlet(self._context(), dofs.size, dofs.ctypes.data))
@@ -468,8 +531,11 @@ class NavierStokesFV1(_DeviceDisc):
         self._check(capi.lib().nsb_upload_mesh(self._context(), e, conn.shape[0], coords.shape[0],
                                                conn.ctypes.data, coords.ctypes.data))
         self._n_elem = conn.shape[0]
+        self._grid_host = (e, conn, coords) if getattr(self, "_ip_fn", None) else (e, conn, coords)
+        self._ip_dirty = bool(getattr(self, "_ip_fn", {}))
 
     def _params(self):
+        self._push_ip_data()
         p = capi.Params()
         capi.lib().nsb_params_default(C.byref(p))
         p.disc = capi.DISC_FV1

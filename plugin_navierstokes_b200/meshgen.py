@@ -184,3 +184,35 @@ def state_taylor_green(coords, t=0.0, nu=1.0 / 1600, seed=5, noise=0.0):
 
 def random_state(n, nf, seed=0, scale=1.0):
     return scale * np.random.default_rng(seed).uniform(-1, 1, size=(n, nf))
+
+
+# ----------------------------------------------------------------------------------------------------
+# integration points of the FV1 geometry: where the reference evaluates its UserData imports
+# ----------------------------------------------------------------------------------------------------
+_EDGES = {"tri": [(0, 1), (1, 2), (2, 0)], "quad": [(0, 1), (1, 2), (2, 3), (3, 0)],
+          "tet": [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)],
+          "hex": [(0, 1), (1, 2), (2, 3), (3, 0), (0, 4), (1, 5), (2, 6), (3, 7), (4, 5), (5, 6), (6, 7), (7, 4)]}
+_FACES = {"tet": [(0, 2, 1), (1, 2, 3), (0, 3, 2), (0, 1, 3)],
+          "hex": [(0, 3, 2, 1), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7), (4, 5, 6, 7)]}
+
+
+def fv1_scvf_ips(elem, conn, coords):
+    """global positions of the SCVF integration points, [n_elem][nip][dim]: the centroid of the SCVF (2-D: midpoint of edge
+    midpoint and element barycentre; 3-D: mean of edge midpoint, the two adjacent face centres and the barycentre)"""
+    x = coords[conn]                                        # [n_elem][nsh][dim]
+    cen = x.mean(axis=1)
+    out = []
+    for (a, b) in _EDGES[elem]:
+        mid = 0.5 * (x[:, a] + x[:, b])
+        if coords.shape[1] == 2:
+            out.append(0.5 * (mid + cen))
+        else:
+            fs = [f for f in _FACES[elem] if a in f and b in f]
+            fc = [x[:, list(f)].mean(axis=1) for f in fs]
+            out.append(0.25 * (mid + fc[0] + cen + fc[1]))
+    return np.stack(out, axis=1)
+
+
+def fv1_scv_ips(elem, conn, coords):
+    """global positions of the SCV integration points, [n_elem][nsh][dim]: the corners (ugcore FV1Geometry SCV::global_ip)"""
+    return coords[conn].copy()

@@ -39,6 +39,117 @@ def rcb_partition(centroids, n_parts):
     return part
 
 
+def dual_graph(conn, n_node, min_shared):
+    """element dual graph (scipy CSR, symmetric): elements are adjacent when they share at least `min_shared` nodes
+    (= a face for min_shared = dim)"""
+    import scipy.sparse as sp
+    ne, nsh = conn.shape
+    A = sp.csr_matrix((np.ones(ne * nsh, dtype=np.int32), (np.repeat(np.arange(ne), nsh), conn.reshape(-1))), shape=(ne, n_node))
+    G = (A @ A.T).tocsr()
+    G.setdiag(0)
+    G.data = (G.data >= min_shared).astype(np.int32)
+    G.eliminate_zeros()
+    return G
+
+
+def _bisect_graph(G, idx, frac, passes=8):
+    """splits the sub-graph of elements `idx` into (left, right) with |left| ~ frac * |idx|: breadth-first level-set growing from
+    a pseudo-peripheral element (the METIS "graph growing" initial partition), then Fiduccia-Mattheyses-style boundary
+    refinement: elements with positive gain (more neighbours on the other side) change sides, largest gain first, the
+    balance kept within one per cent"""
+    from scipy.sparse.csgraph import breadth_first_order
+    sub = G[idx][:, idx].tocsr()
+    n = idx.size
+    target = int(round(n * frac))
+    # pseudo-peripheral start: two BFS sweeps (disconnected remainders are appended in index order)
+    start = 0
+    for _ in range(2):
+        order = breadth_first_order(sub, start, directed=False, return_predecessors=False)
+        start = int(order[-1])
+    order = breadth_first_order(sub, start, directed=False, return_predecessors=False)
+    if order.size < n:
+        rest = np.setdiff1d(np.arange(n), order, assume_unique=False)
+        order = np.concatenate([order, rest])
+    side = np.ones(n, dtype=np.int8)
+    side[order[:target]] = 0
+    indptr, indices = sub.indptr, sub.indices
+    deg = np.diff(indptr)
+    tol = max(1, n // 100)
+    for _ in range(passes):
+        nb_side = side[indices]
+        ext = np.add.reduceat(np.where(nb_side != np.repeat(side, deg), 1, 0), indptr[:-1]) if indices.size else np.zeros(n, int)
+        ext[deg == 0] = 0
+        gain = 2 * ext - deg                                   # cut edges removed minus cut edges created
+        cand = np.nonzero(gain > 0)[0]
+        if cand.size == 0:
+            break
+        cand = cand[np.argsort(-gain[cand], kind="stable")]
+        n0 = int((side == 0).sum())
+        moved = 0
+        locked = np.zeros(n, dtype=bool)
+        for v in cand:
+            if locked[v]:
+                continue
+            s_ = side[v]
+            new_n0 = n0 + (1 if s_ == 1 else -1)
+            if abs(new_n0 - target) > tol:
+                continue
+            nb = indices[indptr[v]:indptr[v + 1]]
+            e_now = int((side[nb] != s_).sum())
+            if 2 * e_now - nb.size <= 0:                       # the gain changed through earlier moves of this pass
+                continue
+            side[v] = 1 - s_
+            n0 = new_n0
+            locked[nb] = True                                   # neighbours wait for the next pass (their gains are stale)
+            moved += 1
+        if moved == 0:
+            break
+    return idx[side == 0], idx[side == 1]
+
+
+def graph_partition(conn, n_node, n_parts, dim=None):
+    """graph partitioner for unstructured grids (configs 2 and 4: channel with cylinder, tetrahedra): recursive bisection of the
+    element dual graph (face neighbours) by level-set growing + boundary refinement -- the METIS recipe without the multilevel
+    coarsening. Returns the part id per element. Compared with rcb_partition it needs no coordinates and follows the mesh
+    topology (holes, graded regions)."""
+    ne, nsh = conn.shape
+    G = dual_graph(conn, n_node, face_nodes(nsh, dim))
+    part = np.zeros(ne, dtype=np.int32)
+
+    def split(idx, lo, n):
+        if n == 1 or idx.size == 0:
+            part[idx] = lo
+            return
+        nl = n // 2
+        a, b = _bisect_graph(G, idx, nl / n)
+        split(a, lo, nl)
+        split(b, lo + nl, n - nl)
+
+    split(np.arange(ne), 0, n_parts)
+    return part
+
+
+def face_nodes(nsh, dim):
+    """nodes two face-neighbours share: tri / quad 2, tet 3, hex 4 (nsh = 4 is a quad in 2-D and a tet in 3-D)"""
+    return 2 if nsh == 3 or (nsh == 4 and dim == 2) else (3 if nsh == 4 else 4)
+
+
+def best_partition(conn, coords, n_parts):
+    """the partition with the smaller interface (edge cut of the dual graph) of graph_partition and rcb_partition"""
+    dim = coords.shape[1]
+    ms = face_nodes(conn.shape[1], dim)
+    pg = graph_partition(conn, coords.shape[0], n_parts, dim=dim)
+    pr = rcb_partition(coords[conn].mean(axis=1), n_parts)
+    cg, cr = edge_cut(conn, coords.shape[0], pg, ms), edge_cut(conn, coords.shape[0], pr, ms)
+    return (pg, "graph", cg) if cg <= cr else (pr, "rcb", cr)
+
+
+def edge_cut(conn, n_node, part, min_shared):
+    """number of dual-graph edges between different parts (interface faces)"""
+    G = dual_graph(conn, n_node, min_shared).tocoo()
+    return int((part[G.row] != part[G.col]).sum() // 2)
+
+
 def local_mesh(conn, coords, part, rank):
     """the rank's elements with local node numbering. returns (conn_local, coords_local, l2g)"""
     mine = conn[part == rank]

@@ -183,3 +183,21 @@ def test_block_problem_owner_rows_match_the_single_domain_mesh(world):
     assert sum(r[3] for r in res) > 0                       # some nodes are slaves somewhere
     for rank, em, ed, _ in res:
         assert em < 1e-12 and ed < 1e-12, (rank, em, ed)
+
+
+@pytest.mark.parametrize("nparts", [2, 4, 8])
+def test_graph_partitioner_on_the_channel_with_cylinder(nparts):
+    """config 2 (unstructured channel + cylinder): the graph partitioner (level-set growing + boundary refinement on the element
+    dual graph) is balanced and cuts fewer faces than coordinate bisection; every element gets exactly one part"""
+    coords, conn = meshgen.tri_grid(132, 28, lo=(0, 0), hi=(2.2, 0.41), jitter=0.2, seed=2, hole=(0.2, 0.2, 0.05))
+    pg = partition.graph_partition(conn, coords.shape[0], nparts, dim=2)
+    pr = partition.rcb_partition(coords[conn].mean(axis=1), nparts)
+    sizes = np.bincount(pg, minlength=nparts)
+    assert sizes.sum() == conn.shape[0] and sizes.min() > 0
+    assert sizes.max() <= 1.04 * conn.shape[0] / nparts
+    cg, cr = partition.edge_cut(conn, coords.shape[0], pg, 2), partition.edge_cut(conn, coords.shape[0], pr, 2)
+    assert cg < cr, (cg, cr)
+    best, kind, cut = partition.best_partition(conn, coords, nparts)
+    assert kind == "graph" and cut == cg
+    # the interface machinery accepts it: local meshes cover every element once
+    assert sum(partition.local_mesh(conn, coords, pg, r)[0].shape[0] for r in range(nparts)) == conn.shape[0]
