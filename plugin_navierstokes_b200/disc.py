@@ -423,7 +423,7 @@ class _DeviceDisc:
             return
         from . import meshgen
         elem, conn, coords = self._grid_host
-        name = {v: k for k, v in _ELEMS.items()}[elem]
+        name = ("tri", "quad", "tet", "hex")[elem]
         xf = meshgen.fv1_scvf_ips(name, conn, coords)
         xv = meshgen.fv1_scv_ips(name, conn, coords)
 
