@@ -65,7 +65,8 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
     if (k.what & (W_JAC_A | W_DEF_A)) {
-        const size_t smem_a = sizeof(double) * (NSB_CSTR(E) * BS + NIP * NSH * DIM + NIP * NSH + 24) + sizeof(int) * (NIP * 12 + 24);
+        const size_t smem_a = sizeof(double) * (NSB_CSTR(E) * BS + NIP * NSH * DIM + NIP * NSH + 24) + sizeof(int) * (NIP * 12 + 24)
+                              + 16 + sizeof(double) * BS * flux_stage_stride(FluxRec<E, STAB == STAB_FLOW, EXACT>::SZ);   // staged flux records (one slot per lane)
         static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 2; }();
         auto ka = minb == 2 ? fv1_flux_kernel<E, STAB, EXACT, BS, 2> : minb == 4 ? fv1_flux_kernel<E, STAB, EXACT, BS, 4> : fv1_flux_kernel<E, STAB, EXACT, BS, 3>;
         e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
@@ -117,7 +118,7 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
         auto go = [&](auto ka, int lpe) -> cudaError_t {
             const int epb = BS / lpe;
             size_t smem_a = sizeof(double) * (NSB_CSTR(E) * epb + NIP * (NSH * DIM + 1) + NIP * (NSH + 1) + 24) + sizeof(int) * (NIP * 12 + 24);
-            if (lpe > 1) smem_a += 16 + sizeof(double) * BS * (SplitRec<E>::COMP ? SplitRec<E>::SZ : LeanRec<E>::SZ + 2);   // staged records (one slot per lane)
+            smem_a += 16 + sizeof(double) * BS * flux_stage_stride(SplitRec<E>::SZ);   // staged records (one slot per lane)
             cudaError_t e2 = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
             if (e2 != cudaSuccess) return e2;
             ka<<<(unsigned)((m.n_elem + epb - 1) / epb), BS, smem_a, st>>>(k, m, u, s0, s1, rec, d_err);

@@ -80,6 +80,8 @@ template <int E, bool FLOWREC, bool EXACT> struct FluxRec {
 
 NSB_DEV double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 NSB_DEV unsigned smem_u32(const void* q) { return (unsigned)__cvta_generic_to_shared(q); }
+// stride (doubles) of the staged records of the flux kernel: an odd number of 16-byte units
+__host__ __device__ constexpr int flux_stage_stride(int rsz) { return ((rsz / 2) % 2 == 0) ? rsz + 2 : rsz; }
 
 // thread-private column in shared memory: element i of the calling thread
 // element-major rows with an odd stride: the lanes that share an element (LPE > 1) read different corners from different banks,
@@ -356,12 +358,14 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
     double* cortab = Nt + NIP * NSTR;                            // [8][3]      reference corners (tab::CORNER)
     int* sidetab = reinterpret_cast<int*>(cortab + 24);          // [6][4]      corners of the sides (tab::SIDE)
     int* iptab = sidetab + 24;                                   // [NIP][12]   from, to, face corners (LPE > 1)
-    // STAGED (split path, LPE > 1): the lean record is assembled in a lane-private shared-memory slot (stride padded by 16 B:
-    // the 16-byte stores of a quarter-warp hit disjoint banks) and leaves the SM as ONE 256-byte bulk store (cp.async.bulk
-    // shared -> global, SASS UBLKCP). Written straight to global memory the 16-byte stores of a warp touch 32 different sectors
-    // each: the LSU data pipe was 84 % busy with them (ncu, profiles/r2_ncu_summary.md).
-    constexpr bool STAGED = LEAN && LPE > 1;
-    constexpr int SSTR = CREC ? LRSZ : LRSZ + 2;                  // (an odd number of 16-byte units)
+    // STAGED: the record (lean / compressed record of the split path, flux half of the combined record otherwise) is assembled
+    // in a lane-private shared-memory slot (an odd number of 16-byte units apart: the 16-byte stores of a quarter-warp hit
+    // disjoint banks) and leaves the SM as ONE bulk store (cp.async.bulk shared -> global, SASS UBLKCP). Written straight to
+    // global memory the 16-byte stores of a warp touch 32 different sectors each: the LSU data pipe was 84 % busy with them
+    // (ncu, profiles/r2_ncu_summary.md).
+    constexpr bool STAGED = true;
+    constexpr int RSZ = LEAN ? LRSZ : FR::SZ;                     // doubles per staged record (a multiple of 2)
+    constexpr int SSTR = flux_stage_stride(RSZ);
     double* stg = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(iptab + NIP * 12) + 15) & ~(uintptr_t)15);
     for (int i = threadIdx.x; i < 24; i += NT) {
         cortab[i] = tab::CORNER[E][i / 3][i % 3];
@@ -749,7 +753,7 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
         }
         if constexpr (STAGED) {
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(frg), "r"(smem_u32(fr)), "r"((unsigned)(LRSZ * sizeof(double))) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(frg), "r"(smem_u32(fr)), "r"((unsigned)(RSZ * sizeof(double))) : "memory");
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
     }
