@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
 #pragma unroll
                 for (int rf = 0; rf < NF; rf++) {
                     double* q = val + base + rf * rstride;
-                    if (SC == SC_ATOMIC) atomicAdd(q, acc[a * NF + rf]); else *q += acc[a * NF + rf];
+                    atomicAdd(q, acc[a * NF + rf]);
                 }
             }
         }
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
         if (SC == SC_LOCAL) dloc[e * (int64_t)L + cf * NSH + k] = d;
         else {
             double* q = def + (int64_t)ws.node[k] * NF + cf;
-            if (SC == SC_ATOMIC) atomicAdd(q, d); else *q += d;
+            atomicAdd(q, d);
         }
     }
 }

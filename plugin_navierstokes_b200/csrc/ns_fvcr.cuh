@@ -335,13 +335,13 @@ __global__ void __launch_bounds__(128) fvcr_elem_kernel(KParams p, FvcrDev m, co
 #pragma unroll
             for (int d1 = 0; d1 < DIM; d1++) {
                 double* q = val + ws.rowbase[a] + (int64_t)d1 * ws.rowlen[a] + off;
-                if (SC == SC_ATOMIC) atomicAdd(q, acc[a * DIM + d1]); else *q += acc[a * DIM + d1];
+                atomicAdd(q, acc[a * DIM + d1]);
             }
         }
         {
             const int64_t off = col < PI ? (int64_t)m.psort[e * NS + nsl] * DIM + d2 : (int64_t)NS * DIM;
             double* q = val + m.prow0 + e * (int64_t)L + off;
-            if (SC == SC_ATOMIC) atomicAdd(q, acc[PI]); else *q += acc[PI];
+            atomicAdd(q, acc[PI]);
         }
     }
     if (p.what & (W_DEF_A | W_DEF_M | W_RHS)) {
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(128) fvcr_elem_kernel(KParams p, FvcrDev m, co
             d *= p.scale_a;
             if (p.what & W_DEF_M) d += p.scale_m * ws.u[col] * ws.vol * p.rho;           // :702-729
             double* q = def + (int64_t)ws.side[s] * DIM + d1;
-            if (SC == SC_ATOMIC) atomicAdd(q, d); else *q += d;
+            atomicAdd(q, d);
         } else {
             if (p.what & W_DEF_A) {                                                      // :648-654
                 for (int sd = 0; sd < NS; sd++)
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(128) fvcr_elem_kernel(KParams p, FvcrDev m, co
             }
             d *= p.scale_a;
             double* q = def + pbase + e;
-            if (SC == SC_ATOMIC) atomicAdd(q, d); else *q += d;
+            atomicAdd(q, d);
         }
     }
 }

@@ -173,8 +173,7 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
 #pragma unroll
                 for (int rf = 0; rf < NF; rf++) {
                     double* q = val + base + rf * rstride;
-                    if (SC == SC_ATOMIC) atomicAdd(q, acc[a * NF + rf]);
-                    else *q += acc[a * NF + rf];
+                    atomicAdd(q, acc[a * NF + rf]);
                 }
             }
         }
@@ -197,7 +196,7 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
         if (SC == SC_LOCAL) dloc[e * (int64_t)L + cf * NSH + k] = d;
         else {
             double* q = def + (int64_t)ws.node[k] * NF + cf;
-            if (SC == SC_ATOMIC) atomicAdd(q, d); else *q += d;
+            atomicAdd(q, d);
         }
     }
 }
