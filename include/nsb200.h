@@ -148,6 +148,23 @@ int  nsb_set_dirichlet(nsb_ctx *ctx, int64_t n, const int64_t *dofs);
 int  nsb_adjust_jacobian(nsb_ctx *ctx, double *values);
 int  nsb_adjust_vector(nsb_ctx *ctx, double *vec, const double *g, int location);
 
+/* Boundary element discs on the FV1 boundary faces. A boundary side is given as (element, local side index in
+ * the reference-element numbering); it contributes one boundary face per side corner (FV1Geometry BF).
+ *   NSB_BND_OUTFLOW : NavierStokesNoNormalStressOutflowFV1::add_jac_A_elem / add_def_A_elem
+ *                     (fv1/bnd/no_normal_stress_outflow_fv1.cpp:343-427): tangential diffusive flux, outflow-only convective
+ *                     flux, continuity flux; constant viscosity / density of nsb_params.
+ *   NSB_BND_INFLOW  : the NeumannBoundaryFV1 part of NavierStokesInflowFV1 (fv1/bnd/inflow_fv1_impl.h:42-82, :69): the given
+ *                     velocity enters the continuity equation, defect(p, node) += scale_a data . n. data: host pointer,
+ *                     [n_side][4][dim] = the vector datum at the ip of boundary face j of side q at (q*4 + j)*dim (the velocity
+ *                     Dirichlet rows of the same condition go through nsb_set_dirichlet).
+ * nsb_set_boundary_faces replaces the sides of that kind (n_side = 0 removes them). nsb_assemble_boundary ADDS the registered
+ * contributions (what: NSB_JAC_A | NSB_DEF_A, scaled by scale_a) to values / defect, to be called after nsb_assemble* and
+ * before the Dirichlet post-pass. values: device pointer, NULL = the resident Jacobian; u / defect per `location`.
+ * Owner-computes (one thread per boundary node, faces in a fixed order): bitwise deterministic. */
+enum { NSB_BND_OUTFLOW = 0, NSB_BND_INFLOW = 1 };
+int  nsb_set_boundary_faces(nsb_ctx *ctx, int kind, int64_t n_side, const int32_t *elem, const int32_t *side, const double *data);
+int  nsb_assemble_boundary(nsb_ctx *ctx, int what, const double *u, double scale_a, double *values, double *defect, int location);
+
 /* Per-ip data imports: the reference evaluates UserData for viscosity / density / source at the integration points
  * (m_imKinViscosity, m_imDensitySCVF at the SCVF ips; m_imDensitySCV, m_imSourceSCV at the SCV ips; m_imSourceSCVF at the SCVF
  * ips -- fv1/navier_stokes_fv1.cpp:184-197, read at :336,351,390,393,708,805,835,866 and fv1/stabilization.cpp:151,198,229).

@@ -321,6 +321,162 @@ int ora_fv1_geometry(int elem, const double *coords, ora_fv1_geom *out)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Boundary faces of FV1Geometry (ugcore fv1_geom.cpp, BF -- absent here, OUR SPEC like App. B-2):
+ * a boundary side contributes one BF per side corner. 2-D: segment [corner, edge midpoint];
+ * 3-D: quadrilateral [corner, midpoint of the edge to the next side corner, side centre, midpoint
+ * of the edge to the previous side corner]. ip = mean of the BF corners (same construction on the
+ * reference element for the local ip); normal = (dy,-dx) / 0.5 (c2-c0)x(c3-c1), turned so that it
+ * points away from the element barycentre; volume = |normal|; shapes and global gradients of ALL
+ * element shape functions at the BF ip.
+ * Used by NavierStokesNoNormalStressOutflowFV1 (fv1/bnd/no_normal_stress_outflow_fv1.cpp:192-427)
+ * and the NeumannBoundaryFV1 part of NavierStokesInflowFV1 (fv1/bnd/inflow_fv1_impl.h:42-82).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { int node_id; double n[3], xip[3], lip[3], N[MAXSH], G[MAXSH][3], vol; } BFace;
+static inline int64_t csr_find(const int64_t *rowptr, const int32_t *colind, int64_t row, int32_t col);
+static double mat_inverse(int dim, const double a[3][3], double inv[3][3]);
+
+static void bf_corners(const RefElem *r, int side, int j, const double (*x)[3], double (*c)[3], int *nc)
+{
+    const int ns = r->side_n[side], co = r->side[side][j];
+    for (int d = 0; d < 3; d++) c[0][d] = x[co][d];
+    if (r->dim == 2) {
+        const int other = r->side[side][1 - j];
+        for (int d = 0; d < 3; d++) c[1][d] = 0.5 * (x[co][d] + x[other][d]);
+        *nc = 2; return;
+    }
+    const int nx = r->side[side][(j + 1) % ns], pv = r->side[side][(j + ns - 1) % ns];
+    for (int d = 0; d < 3; d++) { c[1][d] = 0.5 * (x[co][d] + x[nx][d]); c[3][d] = 0.5 * (x[co][d] + x[pv][d]); }
+    avg_pts(c[2], x, r->side[side], ns, 3);
+    *nc = 4;
+}
+
+static int bf_update(BFace *bf, int elem, const double *coords, int side, int j)
+{
+    const RefElem *r = get_ref(elem);
+    if (!r) return fail("bf_update: unknown element type");
+    if (side < 0 || side >= r->nside || j < 0 || j >= r->side_n[side]) return fail("bf_update: bad side / corner");
+    const int dim = r->dim, nsh = r->nsh;
+    double x[MAXSH][3], c[4][3], lc[4][3], bary[3], sc[3];
+    int nc, all[MAXSH];
+    for (int i = 0; i < nsh; i++) { all[i] = i; for (int d = 0; d < 3; d++) x[i][d] = d < dim ? coords[i*dim+d] : 0.0; }
+    bf->node_id = r->side[side][j];
+    bf_corners(r, side, j, x, c, &nc);
+    bf_corners(r, side, j, r->corner, lc, &nc);
+    for (int d = 0; d < 3; d++) { double s = 0, t = 0; for (int k = 0; k < nc; k++) { s += c[k][d]; t += lc[k][d]; } bf->xip[d] = s / nc; bf->lip[d] = t / nc; }
+    scvf_normal(dim, c, bf->n);
+    avg_pts(bary, x, all, nsh, dim); avg_pts(sc, x, r->side[side], r->side_n[side], dim);
+    { double o[3] = {sc[0]-bary[0], sc[1]-bary[1], dim == 3 ? sc[2]-bary[2] : 0.0};
+      if (vdot(bf->n, o, dim) < 0) for (int d = 0; d < 3; d++) bf->n[d] = -bf->n[d]; }
+    bf->vol = sqrt(vdot(bf->n, bf->n, dim));
+    double lg[MAXSH][3], JT[3][3] = {{0}}, JTinv[3][3] = {{0}};
+    lagrange_shapes(elem, bf->lip, bf->N, lg);
+    for (int i = 0; i < dim; i++) for (int jj = 0; jj < dim; jj++) { double s = 0; for (int k = 0; k < nsh; k++) s += lg[k][i] * x[k][jj]; JT[i][jj] = s; }
+    if (!(fabs(mat_inverse(dim, JT, JTinv)) > 0)) return fail("FV1Geometry: singular element Jacobian");
+    for (int k = 0; k < nsh; k++) for (int jj = 0; jj < 3; jj++) {
+        double s = 0; if (jj < dim) for (int i = 0; i < dim; i++) s += JTinv[jj][i] * lg[k][i];
+        bf->G[k][jj] = s;
+    }
+    return 0;
+}
+
+int ora_fv1_bf_geometry(int elem, const double *coords, int side, int j, int *node_id, double *normal, double *xip,
+                        double *shape, double *ggrad)
+{
+    BFace bf;
+    if (bf_update(&bf, elem, coords, side, j)) return -1;
+    const int dim = ora_elem_dim(elem), nsh = ora_elem_nsh(elem);
+    *node_id = bf.node_id;
+    for (int d = 0; d < dim; d++) { normal[d] = bf.n[d]; xip[d] = bf.xip[d]; }
+    for (int k = 0; k < nsh; k++) { shape[k] = bf.N[k]; for (int d = 0; d < dim; d++) ggrad[k*dim+d] = bf.G[k][d]; }
+    return 0;
+}
+
+int ora_side_corners(int elem, int side)
+{ const RefElem *r = get_ref(elem); return (r && side >= 0 && side < r->nside) ? r->side_n[side] : -1; }
+int ora_side_corner(int elem, int side, int j)
+{ const RefElem *r = get_ref(elem); return (r && side >= 0 && side < r->nside && j >= 0 && j < r->side_n[side]) ? r->side[side][j] : -1; }
+
+/* Boundary contributions of the listed (element, side) pairs, ADDED to values / defect (scaled by scale_a).
+ * kind 0: NavierStokesNoNormalStressOutflowFV1::add_jac_A_elem / add_def_A_elem
+ *         (fv1/bnd/no_normal_stress_outflow_fv1.cpp:343-427 with diffusive_flux_Jac :192-236, diffusive_flux_defect :239-279,
+ *          convective_flux_Jac :282-313, convective_flux_defect :316-338); constant viscosity / density.
+ * kind 1: NeumannBoundaryFV1 with vector data on the pressure function (the continuity-equation part of NavierStokesInflowFV1,
+ *         fv1/bnd/inflow_fv1_impl.h:42-82; ugcore neumann_boundary_fv1.cpp VectorData::add_rhs_elem, absent: rhs(p, co) -= data . n,
+ *         i.e. defect(p, co) += scale_a data . n). data [n_side][4][dim] at the BF ips (side-corner order, unused slots ignored). */
+int ora_fv1_boundary(const ora_params *p, int kind, int64_t n_side, const int32_t *belem, const int32_t *bside, const double *data,
+                     const int32_t *conn, const double *coords, const double *u, const int64_t *rowptr, const int32_t *colind,
+                     int what, double scale_a, double *values, double *defect)
+{
+    const RefElem *r = get_ref(p->elem);
+    if (!r) return fail("ora_fv1_boundary: unknown element type");
+    const int dim = r->dim, nsh = r->nsh, nf = dim + 1, P = dim;
+    for (int64_t b = 0; b < n_side; b++) {
+        const int64_t e = belem[b]; const int side = bside[b];
+        double xc[MAXSH*3], ul[MAXSH][4];
+        for (int k = 0; k < nsh; k++) {
+            const int64_t nd = conn[e*nsh+k];
+            for (int d = 0; d < dim; d++) xc[k*dim+d] = coords[nd*dim+d];
+            for (int f = 0; f < nf; f++) ul[k][f] = u ? u[nd*nf+f] : 0.0;
+        }
+        if (side < 0 || side >= r->nside) return fail("ora_fv1_boundary: bad side");
+        for (int j = 0; j < r->side_n[side]; j++) {
+            BFace bf;
+            if (bf_update(&bf, p->elem, xc, side, j)) return -1;
+            const int co = bf.node_id; const int64_t row0 = (int64_t)conn[e*nsh+co]*nf;
+            if (kind == 1) {
+                if (what & (ORA_DEF_A|ORA_RHS)) { double s = 0; for (int d = 0; d < dim; d++) s += data[(b*4+j)*dim+d] * bf.n[d]; defect[row0+P] += scale_a * s; }
+                continue;
+            }
+            const double nurho = p->kin_visc * p->density;
+            double std_[3] = {0,0,0};
+            for (int k = 0; k < nsh; k++) for (int d = 0; d < dim; d++) std_[d] += ul[k][d] * bf.N[k];
+            double flux = vdot(std_, bf.n, dim) * p->density;                  /* :296, :326 */
+            if (what & ORA_JAC_A) {
+                for (int sh = 0; sh < nsh; sh++) {
+                    double T[3][3], ns_[3];
+                    const double gn = vdot(bf.G[sh], bf.n, dim);
+                    for (int d1 = 0; d1 < dim; d1++) for (int d2 = 0; d2 < dim; d2++) {
+                        T[d1][d2] = d1 == d2 ? gn : 0.0;
+                        if (!p->laplace) T[d1][d2] += bf.G[sh][d1] * bf.n[d2];
+                    }
+                    for (int d2 = 0; d2 < dim; d2++) { double s = 0; for (int d1 = 0; d1 < dim; d1++) s += T[d1][d2] * bf.n[d1]; ns_[d2] = s; }   /* TransposedMatVecMult :219 */
+                    const int64_t col0 = (int64_t)conn[e*nsh+sh]*nf;
+                    for (int d1 = 0; d1 < dim; d1++) for (int d2 = 0; d2 < dim; d2++) {
+                        double v = (T[d1][d2] - bf.n[d1] * ns_[d2]) * (-nurho);
+                        if (d1 == d2 && !p->stokes) v += (flux < 0 ? 0.0 : flux) * bf.N[sh];
+                        int64_t q = csr_find(rowptr, colind, row0+d1, (int32_t)(col0+d2));
+                        if (q < 0) return fail("ora_fv1_boundary: entry not in CSR pattern");
+                        values[q] += scale_a * v;
+                    }
+                    for (int d2 = 0; d2 < dim; d2++) {
+                        int64_t q = csr_find(rowptr, colind, row0+P, (int32_t)(col0+d2));
+                        if (q < 0) return fail("ora_fv1_boundary: entry not in CSR pattern");
+                        values[q] += scale_a * bf.N[sh] * bf.n[d2] * p->density;
+                    }
+                }
+            }
+            if (what & ORA_DEF_A) {
+                double gv[3][3], df[3];
+                for (int d1 = 0; d1 < dim; d1++) for (int d2 = 0; d2 < dim; d2++) { double s = 0; for (int sh = 0; sh < nsh; sh++) s += bf.G[sh][d2] * ul[sh][d1]; gv[d1][d2] = s; }
+                for (int d1 = 0; d1 < dim; d1++) {
+                    double s = 0; for (int d2 = 0; d2 < dim; d2++) s += gv[d1][d2] * bf.n[d2];
+                    if (!p->laplace) for (int d2 = 0; d2 < dim; d2++) s += gv[d2][d1] * bf.n[d2];
+                    df[d1] = s;
+                }
+                const double dn = vdot(df, bf.n, dim);
+                for (int d1 = 0; d1 < dim; d1++) {
+                    double v = (df[d1] - dn * bf.n[d1]) * (-nurho);                  /* VecScaleAppend(diffFlux, -dot, normal) :270: NOT normalised */
+                    if (!p->stokes) v += (flux < 0 ? 0.0 : flux) * std_[d1];
+                    defect[row0+d1] += scale_a * v;
+                }
+                defect[row0+P] += scale_a * vdot(std_, bf.n, dim) * p->density;
+            }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * ElementSideRayIntersection (ugcore lib_disc/common/geometry_util.h -- App. B-4, our spec).
  * Sides are visited in reference order; 3-D sides are tested as triangle (p0,p1,p2) and, for
  * quadrilateral sides, (p0,p2,p3); the first hit with t<=0 (upwind search, bPositive=false)

@@ -129,6 +129,18 @@ int  ora_assemble(const ora_params *p, int64_t n_elem, int64_t n_node_or_side,
                   int what, double scale_a, double scale_m,
                   double *values, double *defect, int nthreads);
 
+/* ---- boundary faces (FV1Geometry BF, our spec) and the boundary discs on them ---- */
+int  ora_side_corners(int elem, int side);
+int  ora_side_corner(int elem, int side, int j);
+int  ora_fv1_bf_geometry(int elem, const double *coords, int side, int j, int *node_id, double *normal /*[dim]*/,
+                         double *xip /*[dim]*/, double *shape /*[nsh]*/, double *ggrad /*[nsh][dim]*/);
+/* kind 0: NavierStokesNoNormalStressOutflowFV1 (fv1/bnd/no_normal_stress_outflow_fv1.cpp:192-427);
+ * kind 1: NeumannBoundaryFV1 part of NavierStokesInflowFV1 (fv1/bnd/inflow_fv1_impl.h:42-82), data [n_side][4][dim] */
+int  ora_fv1_boundary(const ora_params *p, int kind, int64_t n_side, const int32_t *belem, const int32_t *bside,
+                      const double *data, const int32_t *conn, const double *coords, const double *u,
+                      const int64_t *rowptr, const int32_t *colind, int what, double scale_a,
+                      double *values, double *defect);
+
 const char *ora_last_error(void);
 
 #ifdef __cplusplus

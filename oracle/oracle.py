@@ -89,6 +89,11 @@ def lib():
         L.ora_fvcr_csr.argtypes = [C.c_int, C.c_int64, C.c_int64, ip32, ip64, ip32]
         L.ora_assemble.argtypes = [C.POINTER(Params), C.c_int64, C.c_int64, ip32, dp, ip32, dp, dp, dp,
                                    ip64, ip32, C.c_int, C.c_double, C.c_double, dp, dp, C.c_int]
+        L.ora_side_corners.argtypes = [C.c_int, C.c_int]
+        L.ora_side_corner.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ora_fv1_bf_geometry.argtypes = [C.c_int, dp, C.c_int, C.c_int, C.POINTER(C.c_int), dp, dp, dp, dp]
+        L.ora_fv1_boundary.argtypes = [C.POINTER(Params), C.c_int, C.c_int64, ip32, ip32, dp, ip32, dp, dp, ip64, ip32,
+                                       C.c_int, C.c_double, dp, dp]
         _lib = L
     return _lib
 
@@ -265,4 +270,38 @@ def _assemble(p, conn, coords, u, rowptr, colind, what, sol0=None, sol1=None, el
     _chk(lib().ora_assemble(C.byref(p), conn.shape[0], n_ent, _i32(conn), _dp(coords), _i32(es), _dp(u),
                             _dp(sol0), _dp(sol1), _i64(rowptr), _i32(colind), what, scale_a, scale_m,
                             _dp(values), _dp(defect), nthreads))
+    return values, defect
+
+
+# ---- boundary faces and the boundary discs on them ----
+BND_OUTFLOW, BND_INFLOW = 0, 1
+
+
+def side_corners(elem, side):
+    """element corners of a side in reference order"""
+    n = lib().ora_side_corners(elem, side)
+    return [lib().ora_side_corner(elem, side, j) for j in range(n)]
+
+
+def fv1_bf_geometry(elem, coords, side, j):
+    """boundary face j of a side: (node_id, normal[dim], xip[dim], shape[nsh], ggrad[nsh][dim])"""
+    dim, nsh = DIM[elem], NSH[elem]
+    coords = _f64(coords)
+    nid = C.c_int(0)
+    n, x, N, G = np.zeros(dim), np.zeros(dim), np.zeros(nsh), np.zeros((nsh, dim))
+    _chk(lib().ora_fv1_bf_geometry(elem, _dp(coords), side, j, C.byref(nid), _dp(n), _dp(x), _dp(N), _dp(G)))
+    return nid.value, n, x, N, G
+
+
+def fv1_boundary(p, kind, belem, bside, conn, coords, u, rowptr, colind, what, data=None, scale_a=1.0, values=None, defect=None):
+    """adds the boundary-disc contributions of the (element, side) pairs to values / defect. returns (values, defect)"""
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    belem, bside = np.ascontiguousarray(belem, dtype=np.int32), np.ascontiguousarray(bside, dtype=np.int32)
+    coords, u, data = _f64(coords), _f64(u), _f64(data)
+    if values is None:
+        values = np.zeros(colind.shape[0])
+    if defect is None:
+        defect = np.zeros(rowptr.shape[0] - 1)
+    _chk(lib().ora_fv1_boundary(C.byref(p), kind, belem.shape[0], _i32(belem), _i32(bside), _dp(data), _i32(conn), _dp(coords),
+                                _dp(u), _i64(rowptr), _i32(colind), what, scale_a, _dp(values), _dp(defect)))
     return values, defect

@@ -12,4 +12,5 @@ from .disc import (NavierStokes, NavierStokesFV1, NavierStokesFVCR, UGError,    
                    NavierStokesNoUpwind, NavierStokesFullUpwind, NavierStokesSkewedUpwind,
                    NavierStokesLinearProfileSkewedUpwind, NavierStokesPositiveUpwind, NavierStokesRegularUpwind,
                    NavierStokesFIELDSStabilization, NavierStokesFLOWStabilization,
-                   NavierStokesFV1WithoutStabilization, NavierStokesWall, NavierStokesInflowFV1, ThetaTimeStep)
+                   NavierStokesFV1WithoutStabilization, NavierStokesWall, NavierStokesInflowFV1, NavierStokesNoNormalStressOutflowFV1,
+                   NavierStokesNoNormalStressOutflow, ThetaTimeStep)

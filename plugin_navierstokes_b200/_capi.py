@@ -23,8 +23,9 @@ SYMBOLS = [
     "nsb_prep_elem_loop", "nsb_assemble", "nsb_local_contributions", "nsb_pack", "nsb_unpack_add",
     "nsb_launch_count", "nsb_synchronize", "nsb_version", "nsb_check_errors", "nsb_query",
     "nsb_assemble_resident", "nsb_resident_jacobian", "nsb_apply_jacobian", "nsb_set_dirichlet", "nsb_adjust_jacobian",
-    "nsb_adjust_vector", "nsb_set_ip_data",
+    "nsb_adjust_vector", "nsb_set_ip_data", "nsb_set_boundary_faces", "nsb_assemble_boundary",
 ]
+BND_OUTFLOW, BND_INFLOW = 0, 1
 IP_KIN_VISC_SCVF, IP_DENSITY_SCVF, IP_DENSITY_SCV, IP_SOURCE_SCVF, IP_SOURCE_SCV = range(5)
 
 
@@ -94,5 +95,7 @@ def lib():
     L.nsb_adjust_jacobian.argtypes = [vp, vp]
     L.nsb_adjust_vector.argtypes = [vp, vp, vp, i32]
     L.nsb_set_ip_data.argtypes = [vp, i32, vp, i32]
+    L.nsb_set_boundary_faces.argtypes = [vp, i32, i64, vp, vp, vp]
+    L.nsb_assemble_boundary.argtypes = [vp, i32, vp, C.c_double, vp, vp, i32]
     _lib = L
     return L

@@ -20,6 +20,7 @@
 #include "ns_graph.h"
 #include "ns_fused.cuh"
 #include "ns_tile.cuh"
+#include "ns_bnd.cuh"
 
 using namespace nsb;
 
@@ -183,6 +184,9 @@ struct nsb_ctx {
     double* d_jres = nullptr;                                  // resident CSR values (nsb_assemble_resident)
     double *d_xin = nullptr, *d_yout = nullptr;                // staging of nsb_apply_jacobian(NSB_HOST)
     int64_t* d_dir = nullptr; int64_t n_dir = 0; double* d_dirval = nullptr;
+    // boundary faces of the boundary discs (ns_bnd.cuh), per kind: BFs sorted by grid node
+    struct BndSet { int64_t n_bnode = 0, n_bf = 0; int32_t* d_bnode = nullptr; int64_t* d_bptr = nullptr; nsb::BndFace* d_bf = nullptr; double* d_data = nullptr; };
+    BndSet bnd[2];
     // fused tile kernel (ns_tile.cuh, 3-D element types): the patch tables above built with the tile capacities + local-node tables
     bool tile_ok = false;
     int32_t* d_plnodes = nullptr; uint8_t* d_pecorner = nullptr;
@@ -260,6 +264,7 @@ static void free_mesh(nsb_ctx* c)
     for (int i = 0; i < 5; i++) { cudaFree(c->d_ip[i]); c->d_ip[i] = nullptr; }
     cudaFree(c->d_bcol); cudaFree(c->d_rowptr); cudaFree(c->d_jres); cudaFree(c->d_xin); cudaFree(c->d_yout); cudaFree(c->d_dir); cudaFree(c->d_dirval);
     c->d_bcol = nullptr; c->d_rowptr = nullptr; c->d_jres = nullptr; c->d_xin = c->d_yout = nullptr; c->d_dir = nullptr; c->n_dir = 0; c->d_dirval = nullptr;
+    for (auto& b : c->bnd) { cudaFree(b.d_bnode); cudaFree(b.d_bptr); cudaFree(b.d_bf); cudaFree(b.d_data); b = nsb_ctx::BndSet(); }
     cudaFree(c->d_plnodes); cudaFree(c->d_pecorner); c->d_plnodes = nullptr; c->d_pecorner = nullptr; c->tile_ok = false;
     c->d_geo = nullptr; c->geo_diff_len = -1;
     c->d_phdr = nullptr; c->d_pnodes = nullptr; c->d_pelems = c->d_pconn = nullptr; c->d_pwork = nullptr; c->d_padj = nullptr;
@@ -1085,6 +1090,92 @@ extern "C" int nsb_adjust_vector(nsb_ctx* c, double* vec, const double* g, int l
     if (location == NSB_HOST) {
         CUDA_TRY(c, cudaMemcpyAsync(vec, dv, nb, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// boundary element discs on the FV1 boundary faces (ns_bnd.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_set_boundary_faces(nsb_ctx* c, int kind, int64_t n_side, const int32_t* elem, const int32_t* side, const double* data)
+{
+    if (!c || kind < 0 || kind > 1) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_set_boundary_faces: no grid uploaded");
+    if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_boundary_faces: FV1 only");
+    if (n_side < 0 || (n_side > 0 && (!elem || !side))) return NSB_ERR_INVALID;
+    if (kind == NSB_BND_INFLOW && n_side > 0 && !data) return set_err(c, NSB_ERR_INVALID, "nsb_set_boundary_faces: the inflow condition needs its vector data at the boundary-face ips");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    nsb_ctx::BndSet& b = c->bnd[kind];
+    cudaFree(b.d_bnode); cudaFree(b.d_bptr); cudaFree(b.d_bf); cudaFree(b.d_data); b = nsb_ctx::BndSet();
+    if (n_side == 0) return NSB_OK;
+    const int nsh = kNSH[c->elem], dim = kDIM[c->elem], nside = kNSIDE[c->elem];
+    static const int side_n[4] = {2, 2, 3, 4};
+    static const int8_t sides[4][6][4] = {{{0, 1, -1, -1}, {1, 2, -1, -1}, {2, 0, -1, -1}}, {{0, 1, -1, -1}, {1, 2, -1, -1}, {2, 3, -1, -1}, {3, 0, -1, -1}},
+                                          {{0, 2, 1, -1}, {1, 2, 3, -1}, {0, 3, 2, -1}, {0, 1, 3, -1}},
+                                          {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}}};
+    std::vector<int32_t> conn((size_t)c->n_elem * nsh);
+    CUDA_TRY(c, cudaMemcpy(conn.data(), c->d_conn, conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const int sn = side_n[c->elem];
+    struct Key { int32_t node; int64_t b; int j; };
+    std::vector<Key> keys; keys.reserve((size_t)n_side * sn);
+    for (int64_t q = 0; q < n_side; q++) {
+        if (elem[q] < 0 || elem[q] >= c->n_elem || side[q] < 0 || side[q] >= nside) return set_err(c, NSB_ERR_INVALID, "nsb_set_boundary_faces: bad (element, side) pair %lld", (long long)q);
+        for (int j = 0; j < sn; j++) keys.push_back({conn[(size_t)elem[q] * nsh + sides[c->elem][side[q]][j]], q, j});
+    }
+    std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) { return x.node != y.node ? x.node < y.node : (x.b != y.b ? x.b < y.b : x.j < y.j); });
+    std::vector<int32_t> bnode; std::vector<int64_t> bptr; std::vector<nsb::BndFace> bf(keys.size());
+    for (size_t i = 0; i < keys.size(); i++) {
+        if (i == 0 || keys[i].node != keys[i - 1].node) { bnode.push_back(keys[i].node); bptr.push_back((int64_t)i); }
+        bf[i].elem = elem[keys[i].b]; bf[i].side = (int16_t)side[keys[i].b]; bf[i].j = (int16_t)keys[i].j;
+        bf[i].data = kind == NSB_BND_INFLOW ? (int32_t)(keys[i].b * 4 + keys[i].j) : -1;
+    }
+    bptr.push_back((int64_t)keys.size());
+    b.n_bnode = (int64_t)bnode.size(); b.n_bf = (int64_t)bf.size();
+    CUDA_TRY(c, upload(c, &b.d_bnode, bnode.data(), bnode.size()));
+    CUDA_TRY(c, upload(c, &b.d_bptr, bptr.data(), bptr.size()));
+    CUDA_TRY(c, upload(c, &b.d_bf, bf.data(), bf.size()));
+    if (kind == NSB_BND_INFLOW) CUDA_TRY(c, upload(c, &b.d_data, data, (size_t)n_side * 4 * dim));
+    return NSB_OK;
+}
+
+extern "C" int nsb_assemble_boundary(nsb_ctx* c, int what, const double* u, double sa, double* values, double* defect, int location)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_assemble_boundary: no grid uploaded");
+    if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_assemble_boundary: FV1 only");
+    const bool jac = what & NSB_JAC_A, dfc = what & (NSB_DEF_A | NSB_RHS);
+    if (dfc && !defect) return set_err(c, NSB_ERR_INVALID, "nsb_assemble_boundary: defect pointer missing");
+    if (!u) return set_err(c, NSB_ERR_INVALID, "nsb_assemble_boundary: u == NULL");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    double* dv = jac ? (values ? values : c->d_jres) : nullptr;          // values: device pointer, NULL = the resident Jacobian
+    if (jac && !dv) return set_err(c, NSB_ERR_INVALID, "nsb_assemble_boundary: no resident Jacobian (nsb_assemble_resident) and values == NULL");
+    KParams k;
+    int rc = resolve_params(c, k, what & (NSB_JAC_A | NSB_DEF_A | NSB_RHS), nullptr, sa, 1.0);
+    if (rc) return rc;
+    const double* du = u; double* dd = defect;
+    const size_t nb = sizeof(double) * c->n_dof;
+    if (location == NSB_HOST) {
+        if ((rc = ensure(c, &c->d_u, c->n_dof))) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, nb, cudaMemcpyHostToDevice, c->stream)); du = c->d_u;
+        if (dfc) { if ((rc = ensure(c, &c->d_def, c->n_dof))) return rc; dd = c->d_def;
+                   CUDA_TRY(c, cudaMemcpyAsync(dd, defect, nb, cudaMemcpyHostToDevice, c->stream)); }
+    }
+    const MeshDev m = mesh_view(c);
+    for (int kind = 0; kind < 2; kind++) {
+        const nsb_ctx::BndSet& b = c->bnd[kind];
+        if (b.n_bnode == 0) continue;
+        if (kind == NSB_BND_INFLOW && !dfc) continue;
+        const unsigned nblk = (unsigned)((b.n_bnode + 63) / 64);
+#define NSB_BND(EE) fv1_boundary_kernel<EE><<<nblk, 64, 0, c->stream>>>(k, m, kind, b.n_bnode, b.d_bnode, b.d_bptr, b.d_bf, b.d_data, du, dv, dfc ? dd : nullptr, c->d_err)
+        switch (c->elem) { case NSB_TRI: NSB_BND(E_TRI); break; case NSB_QUAD: NSB_BND(E_QUAD); break; case NSB_TET: NSB_BND(E_TET); break; default: NSB_BND(E_HEX); }
+#undef NSB_BND
+        c->launches++;
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    if (location == NSB_HOST) {
+        if (dfc) CUDA_TRY(c, cudaMemcpyAsync(defect, dd, nb, cudaMemcpyDeviceToHost, c->stream));
+        return check_device_error(c);
     }
     return NSB_OK;
 }

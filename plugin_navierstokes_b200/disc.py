@@ -458,6 +458,40 @@ class _DeviceDisc:
         self._check(capi.lib().nsb_adjust_vector(self._ctx, self._ptr(vec), self._ptr(g), capi.DEVICE if _is_torch(vec) else capi.HOST))
         return vec
 
+    # ---- boundary element discs on the FV1 boundary faces (nsb_set_boundary_faces / nsb_assemble_boundary) ----
+    def set_boundary_faces(self, kind, elems, sides, data=None):
+        elems = np.ascontiguousarray(elems, dtype=np.int32).reshape(-1)
+        sides = np.ascontiguousarray(sides, dtype=np.int32).reshape(-1)
+        if elems.size != sides.size:
+            raise UGError("set_boundary_faces: one local side index per element expected")
+        if data is not None:
+            data = np.ascontiguousarray(data, dtype=np.float64)
+            if data.size != elems.size * 4 * (len(self._fcts) - 1):
+                raise UGError("set_boundary_faces: data must be [n_side][4][dim]")
+        self._check(capi.lib().nsb_set_boundary_faces(self._context(), kind, elems.size, self._ptr(elems), self._ptr(sides), self._ptr(data)))
+
+    def assemble_boundary(self, what, u, values=None, defect=None, scale_a=1.0):
+        """ADDS the contributions of the registered boundary discs (outflow, inflow continuity term) to the resident Jacobian
+        (values=None) or a CUDA tensor of CSR values, and to `defect`; call after assemble*/assemble_resident and before the
+        Dirichlet post-pass. Returns defect."""
+        L = capi.lib()
+        p = self._params()
+        self._check(L.nsb_set_params(self._context(), C.byref(p)))
+        on_dev = _is_torch(u)
+        dfc = bool(what & (capi.DEF_A | capi.RHS))
+        if dfc and defect is None:
+            raise UGError("assemble_boundary: the defect to add to is missing")
+        if on_dev:
+            import torch
+            self.use_stream(torch.cuda.current_stream(u.device).cuda_stream)
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+            if dfc and (defect.dtype != np.float64 or not defect.flags.c_contiguous):
+                raise UGError("assemble_boundary: defect must be a contiguous float64 array")
+        self._check(L.nsb_assemble_boundary(self._ctx, what, self._ptr(u), float(scale_a), self._ptr(values), self._ptr(defect) if dfc else None,
+                                            capi.DEVICE if on_dev else capi.HOST))
+        return defect
+
     def assemble_jacobian(self, u, **kw):
         return self.assemble(capi.JAC_A, u, **kw)[0]
 
@@ -705,10 +739,17 @@ class NavierStokesWall(_DirichletVelocity):
 
 
 class NavierStokesInflowFV1(_DirichletVelocity):
-    """fv1/bnd/inflow_fv1_impl.h:42-82: velocity = user data on the inflow subsets (Dirichlet part). The Neumann term of the
-    continuity equation over the boundary faces (ugcore NeumannBoundaryFV1) is not part of the device path yet."""
+    """fv1/bnd/inflow_fv1_impl.h:42-82: velocity = user data on the inflow subsets. Two parts, as in the reference (:69, :77):
+    the Dirichlet rows of the velocity (nsb_set_dirichlet) and, when the boundary SIDES are given, the NeumannBoundaryFV1 term of
+    the continuity equation over their boundary faces (nsb_set_boundary_faces(NSB_BND_INFLOW): defect(p) += user . n)."""
 
-    def add(self, user, boundary_nodes, coords=None):
+    def __init__(self, master):
+        super().__init__(master)
+        self._be, self._bs, self._bdata = [], [], []
+
+    def add(self, user, boundary_nodes, coords=None, sides=None, conn=None, elem=None):
+        """sides = (elements, local sides) of the inflow boundary (e.g. meshgen.boundary_sides) adds the continuity term; conn / elem
+        (and coords) are then needed to locate the boundary-face ips where `user` is evaluated"""
         if callable(user):
             if coords is None:
                 raise UGError("NavierStokesInflow::add: coordinates needed to evaluate the user data")
@@ -716,6 +757,51 @@ class NavierStokesInflowFV1(_DirichletVelocity):
         else:
             vals = user
         self._add(boundary_nodes, vals)
+        if sides is not None:
+            from . import meshgen
+            be, bs = sides
+            if conn is None or elem is None or coords is None:
+                raise UGError("NavierStokesInflow::add: conn, elem and coords needed for the boundary faces")
+            xip = meshgen.fv1_bf_ips(elem, conn, coords, be, bs)
+            if callable(user):
+                data = np.array([[user(*xip[q, j]) for j in range(4)] for q in range(len(be))], dtype=np.float64)
+            else:
+                data = np.broadcast_to(np.asarray(user, dtype=np.float64).reshape(-1)[: self._dim], xip.shape).copy()
+            self._be.append(np.asarray(be)); self._bs.append(np.asarray(bs)); self._bdata.append(data.reshape(len(be), 4, self._dim))
+
+    def apply(self, disc=None):
+        d = disc if disc is not None else self._master
+        if self._be:
+            d.set_boundary_faces(capi.BND_INFLOW, np.concatenate(self._be), np.concatenate(self._bs), np.concatenate(self._bdata, axis=0))
+        return super().apply(disc)
+
+
+class NavierStokesNoNormalStressOutflowFV1:
+    """fv1/bnd/no_normal_stress_outflow_fv1.cpp:192-427 ("NavierStokesNoNormalStressOutflow" with the master's disc scheme,
+    register_navier_stokes.cpp): zero normal stress on the outflow boundary -- tangential diffusive flux, convective flux without
+    back-flow and the continuity flux over the boundary faces of the given sides, added to the Jacobian / defect of the master
+    disc by disc.assemble_boundary()."""
+
+    def __init__(self, master):
+        fcts = master.symb_fcts() if hasattr(master, "symb_fcts") else master._fcts
+        if len(fcts) not in (3, 4):
+            raise UGError("NavierStokesNoNormalStressOutflow::set_functions: This Boundary Condition works on exactly dim+1 "
+                          "(velocity+pressure) components, but %d components given." % len(fcts))
+        self._master = master
+        self._be, self._bs = [], []
+
+    def add(self, elems, sides):
+        """boundary sides as (element, local side) pairs (the reference names boundary subsets)"""
+        self._be.append(np.asarray(elems, dtype=np.int32).reshape(-1))
+        self._bs.append(np.asarray(sides, dtype=np.int32).reshape(-1))
+
+    def apply(self, disc=None):
+        d = disc if disc is not None else self._master
+        if self._be:
+            d.set_boundary_faces(capi.BND_OUTFLOW, np.concatenate(self._be), np.concatenate(self._bs))
+
+
+NavierStokesNoNormalStressOutflow = NavierStokesNoNormalStressOutflowFV1
 
 
 class ThetaTimeStep:

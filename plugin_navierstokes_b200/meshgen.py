@@ -216,3 +216,45 @@ def fv1_scvf_ips(elem, conn, coords):
 def fv1_scv_ips(elem, conn, coords):
     """global positions of the SCV integration points, [n_elem][nsh][dim]: the corners (ugcore FV1Geometry SCV::global_ip)"""
     return coords[conn].copy()
+
+
+# ----------------------------------------------------------------------------------------------------
+# boundary sides and boundary-face integration points (FV1Geometry BF; boundary discs of SURVEY 8f-1)
+# ----------------------------------------------------------------------------------------------------
+def boundary_sides(elem, conn, coords=None, where=None):
+    """(element, local side) pairs of the sides that belong to exactly one element. where(centres [n][dim]) -> bool mask selects
+    a part of the boundary by the side centres (the role of ugcore's boundary subsets)."""
+    es, n_side = element_sides(elem, conn)
+    count = np.bincount(es.reshape(-1), minlength=n_side)
+    be, bs = np.nonzero(count[es] == 1)
+    if where is not None:
+        cen = np.stack([coords[conn[be, k]] for k in range(conn.shape[1])], axis=1)      # [n][nsh][dim]
+        sc = np.zeros((be.size, coords.shape[1]))
+        for s, corners in enumerate(SIDES[elem]):
+            m = bs == s
+            sc[m] = cen[m][:, list(corners)].mean(axis=1)
+        keep = np.asarray(where(sc), dtype=bool)
+        be, bs = be[keep], bs[keep]
+    return be.astype(np.int32), bs.astype(np.int32)
+
+
+def fv1_bf_ips(elem, conn, coords, belem, bside):
+    """global positions of the boundary-face ips of the given sides, [n_side][4][dim] (slot j = side corner j; unused slots 0):
+    mean of the BF corners -- 2-D [corner, edge midpoint]; 3-D [corner, midpoint to the next side corner, side centre, midpoint to
+    the previous side corner]"""
+    dim = coords.shape[1]
+    out = np.zeros((len(belem), 4, dim))
+    x = coords[conn[belem]]                                 # [n][nsh][dim]
+    for s, corners in enumerate(SIDES[elem]):
+        m = np.asarray(bside) == s
+        if not m.any():
+            continue
+        xs = x[m][:, list(corners)]                         # [n][ns][dim]
+        ns = len(corners)
+        for j in range(ns):
+            if dim == 2:
+                out[m, j] = 0.5 * (xs[:, j] + 0.5 * (xs[:, j] + xs[:, 1 - j]))
+            else:
+                nx, pv = (j + 1) % ns, (j + ns - 1) % ns
+                out[m, j] = 0.25 * (xs[:, j] + 0.5 * (xs[:, j] + xs[:, nx]) + xs.mean(axis=1) + 0.5 * (xs[:, j] + xs[:, pv]))
+    return out
