@@ -161,9 +161,30 @@ int  nsb_adjust_vector(nsb_ctx *ctx, double *vec, const double *g, int location)
  * contributions (what: NSB_JAC_A | NSB_DEF_A, scaled by scale_a) to values / defect, to be called after nsb_assemble* and
  * before the Dirichlet post-pass. values: device pointer, NULL = the resident Jacobian; u / defect per `location`.
  * Owner-computes (one thread per boundary node, faces in a fixed order): bitwise deterministic. */
-enum { NSB_BND_OUTFLOW = 0, NSB_BND_INFLOW = 1 };
+enum { NSB_BND_OUTFLOW = 0, NSB_BND_INFLOW = 1, NSB_BND_TURB_ZERO = 2 /* setTurbulenceZeroBoundaries, see nsb_turbulent_viscosity */ };
 int  nsb_set_boundary_faces(nsb_ctx *ctx, int kind, int64_t n_side, const int32_t *elem, const int32_t *side, const double *data);
 int  nsb_assemble_boundary(nsb_ctx *ctx, int what, const double *u, double scale_a, double *values, double *defect, int location);
+
+/* Turbulent viscosity as a device-side provider of the per-ip kinematic viscosity:
+ * FV1SmagorinskyTurbViscData (fv1/turbulent_viscosity_fv1.h:200-383; assembleDeformationTensor
+ * fv1/turbulent_viscosity_fv1_impl.h:504-616, FNorm :755-762, update :819-852, evaluate turbulent_viscosity_fv1.h:321-379):
+ * nu_t(node) = c vol^(2/dim) sqrt(2 D:D) from the deformation tensor of `u` over the node's control volume, then
+ * nu(ip) = sum_sh N_sh(ip) nu_t(sh) + the kinematic viscosity of nsb_params, written into the NSB_IP_KIN_VISC_SCVF import table
+ * on the device (no host round trip) -- call it before nsb_assemble*, as the reference calls update() before an assembly.
+ * setTurbulenceZeroBoundaries: the boundary sides registered as NSB_BND_TURB_ZERO add their BF closure terms; zero_nodes
+ * (host pointer, the vertices of those subsets) keep nu_t = 0. nu_t: optional output [n_node] per `location`.
+ * NSB_TURB_OFF removes the table again. The dynamic model (FV1DynamicTurbViscData) is not available on the device. */
+enum { NSB_TURB_OFF = -1, NSB_TURB_SMAGORINSKY = 0 };
+int  nsb_turbulent_viscosity(nsb_ctx *ctx, int model, double c, const double *u, int64_t n_zero, const int64_t *zero_nodes,
+                             double *nu_t, int location);
+
+/* Diagnostics of navier_stokes_tools.h on the device:
+ *   NSB_DIAG_VORTICITY      vorticityFV1 (:386-525), FV1 grids: out [n_node] = d_x v - d_y u, SCV-volume weighted per vertex;
+ *   NSB_DIAG_KINETIC_ENERGY kineticEnergy (:850-965), FVCR grids: out [1] = sum_e vol_e |u(barycentre)|^2 / sum_e vol_e;
+ *   NSB_DIAG_CFL            cflNumber (:731-848), FVCR grids: out [1] = max dt |(x_i - x_j) . u(barycentre)| / |x_i - x_j|^2.
+ * Fixed-order reductions (bitwise deterministic). u / out per `location`. */
+enum { NSB_DIAG_VORTICITY = 0, NSB_DIAG_KINETIC_ENERGY = 1, NSB_DIAG_CFL = 2 };
+int  nsb_diagnostic(nsb_ctx *ctx, int kind, const double *u, double dt, double *out, int location);
 
 /* Per-ip data imports: the reference evaluates UserData for viscosity / density / source at the integration points
  * (m_imKinViscosity, m_imDensitySCVF at the SCVF ips; m_imDensitySCV, m_imSourceSCV at the SCV ips; m_imSourceSCVF at the SCVF

@@ -1456,6 +1456,136 @@ int ora_fvcr_elem(const ora_params *p, const double *coords, const double *u, in
 }
 
 /* ------------------------------------------------------------------------------------------
+ * turbulent viscosity (Smagorinsky) as per-ip kinematic viscosity, and diagnostics
+ * ---------------------------------------------------------------------------------------- */
+/* FV1SmagorinskyTurbViscData (fv1/turbulent_viscosity_fv1.h:200-383):
+ *  - assembleDeformationTensor (fv1/turbulent_viscosity_fv1_impl.h:504-616): per node a
+ *      D_a = 1/vol_a [ sum_scvf +-(1/2)(u_ip n^T + n u_ip^T)  +  sum_{BF in the turbulence-zero subsets} (1/2)(u_a n^T + n u_a^T) ],
+ *      u_ip = sum_sh shape(ip, sh) u_sh, + at scvf.from(), - at scvf.to(); vol_a = sum of the SCV volumes;
+ *  - update (:819-852): nu_t(a) = c delta^2 FNorm(D_a), delta = vol_a^(1/dim), FNorm = sqrt(2 sum D_ij^2) (:755-762); nodes of the
+ *    turbulence-zero subsets keep 0;
+ *  - evaluate (turbulent_viscosity_fv1.h:321-379): value(ip) = sum_sh N_sh(ip) nu_t(vertex sh) + kinematic viscosity.
+ * u [n_node][dim+1]; zero_node [n_node] flags (may be NULL); (belem, bside) the turbulence-zero boundary sides.
+ * out: nu_t [n_node], ip_visc [n_elem][nip] (either may be NULL). */
+int ora_fv1_smagorinsky(int elem, int64_t n_elem, int64_t n_node, const int32_t *conn, const double *coords, const double *u,
+                        double c, double kin_visc, int64_t n_bside, const int32_t *belem, const int32_t *bside,
+                        const uint8_t *zero_node, double *nu_t, double *ip_visc)
+{
+    const RefElem *r = get_ref(elem);
+    if (!r) return fail("ora_fv1_smagorinsky: unknown element type");
+    const int dim = r->dim, nsh = r->nsh, nip = r->nedge, nf = dim + 1;
+    double *D = calloc((size_t)n_node * 9, sizeof *D), *vol = calloc((size_t)n_node, sizeof *vol), *nt = calloc((size_t)n_node, sizeof *nt);
+    int rc = 0;
+    for (int64_t e = 0; e < n_elem && !rc; e++) {
+        double xc[MAXSH*3]; Geom g;
+        for (int k = 0; k < nsh; k++) for (int d = 0; d < dim; d++) xc[k*dim+d] = coords[(int64_t)conn[e*nsh+k]*dim+d];
+        if ((rc = geom_update(&g, elem, xc))) break;
+        for (int k = 0; k < nsh; k++) vol[conn[e*nsh+k]] += g.vol[k];
+        for (int ip = 0; ip < nip; ip++) {
+            double v[3] = {0,0,0};
+            for (int k = 0; k < nsh; k++) for (int d = 0; d < dim; d++) v[d] += g.N[ip][k] * u[(int64_t)conn[e*nsh+k]*nf+d];
+            const int64_t a = conn[e*nsh+g.from[ip]], b = conn[e*nsh+g.to[ip]];
+            for (int i = 0; i < dim; i++) for (int j = 0; j < dim; j++) {
+                const double f = 0.5 * (v[i] * g.n[ip][j] + v[j] * g.n[ip][i]);
+                D[a*9+i*3+j] += f; D[b*9+i*3+j] -= f;
+            }
+        }
+    }
+    for (int64_t b = 0; b < n_bside && !rc; b++) {
+        const int64_t e = belem[b];
+        double xc[MAXSH*3];
+        for (int k = 0; k < nsh; k++) for (int d = 0; d < dim; d++) xc[k*dim+d] = coords[(int64_t)conn[e*nsh+k]*dim+d];
+        for (int j = 0; j < r->side_n[bside[b]] && !rc; j++) {
+            BFace bf;
+            if ((rc = bf_update(&bf, elem, xc, bside[b], j))) break;
+            const int64_t a = conn[e*nsh+bf.node_id];
+            for (int i = 0; i < dim; i++) for (int jj = 0; jj < dim; jj++)
+                D[a*9+i*3+jj] += 0.5 * (u[a*nf+i] * bf.n[jj] + u[a*nf+jj] * bf.n[i]);
+        }
+    }
+    for (int64_t a = 0; a < n_node && !rc; a++) {
+        if (!(vol[a] > 0) || (zero_node && zero_node[a])) { nt[a] = 0.0; continue; }
+        double s = 0;
+        for (int i = 0; i < dim; i++) for (int j = 0; j < dim; j++) { const double t = D[a*9+i*3+j] / vol[a]; s += t * t; }
+        const double delta = pow(vol[a], 1.0 / dim);
+        nt[a] = c * delta * delta * sqrt(2.0 * s);
+    }
+    if (!rc && nu_t) memcpy(nu_t, nt, sizeof(double) * (size_t)n_node);
+    if (!rc && ip_visc)
+        for (int64_t e = 0; e < n_elem; e++) for (int ip = 0; ip < nip; ip++) {
+            double s = 0; for (int k = 0; k < nsh; k++) s += r->shape_ip[ip][k] * nt[conn[e*nsh+k]];
+            ip_visc[e*nip+ip] = s + kin_visc;
+        }
+    free(D); free(vol); free(nt);
+    return rc;
+}
+
+/* vorticityFV1 (navier_stokes_tools.h:386-525): per element and corner co
+ *   localvort = sum_sh (u(sh)[1] scv.global_grad(sh)[0] - u(sh)[0] scv.global_grad(sh)[1]) * scv.volume()
+ * (global gradients at the SCV ip = the corner, ugcore FV1Geometry SCV, our spec), summed per vertex, divided by the vertex volume. */
+int ora_fv1_vorticity(int elem, int64_t n_elem, int64_t n_node, const int32_t *conn, const double *coords, const double *u, double *vort)
+{
+    const RefElem *r = get_ref(elem);
+    if (!r) return fail("ora_fv1_vorticity: unknown element type");
+    const int dim = r->dim, nsh = r->nsh, nf = dim + 1;
+    double *vol = calloc((size_t)n_node, sizeof *vol);
+    memset(vort, 0, sizeof(double) * (size_t)n_node);
+    int rc = 0;
+    for (int64_t e = 0; e < n_elem && !rc; e++) {
+        double xc[MAXSH*3], x[MAXSH][3]; Geom g;
+        for (int k = 0; k < nsh; k++) for (int d = 0; d < 3; d++) { x[k][d] = d < dim ? coords[(int64_t)conn[e*nsh+k]*dim+d] : 0.0; if (d < dim) xc[k*dim+d] = x[k][d]; }
+        if ((rc = geom_update(&g, elem, xc))) break;
+        for (int co = 0; co < nsh; co++) {
+            double N[MAXSH], lg[MAXSH][3], JT[3][3] = {{0}}, JTinv[3][3] = {{0}}, w = 0;
+            lagrange_shapes(elem, r->corner[co], N, lg);
+            for (int i = 0; i < dim; i++) for (int j = 0; j < dim; j++) { double s = 0; for (int k = 0; k < nsh; k++) s += lg[k][i] * x[k][j]; JT[i][j] = s; }
+            if (!(fabs(mat_inverse(dim, JT, JTinv)) > 0)) { rc = fail("FV1Geometry: singular element Jacobian"); break; }
+            for (int k = 0; k < nsh; k++) {
+                double G[2];
+                for (int j = 0; j < 2; j++) { double s = 0; for (int i = 0; i < dim; i++) s += JTinv[j][i] * lg[k][i]; G[j] = s; }
+                w += u[(int64_t)conn[e*nsh+k]*nf+1] * G[0] - u[(int64_t)conn[e*nsh+k]*nf+0] * G[1];
+            }
+            vort[conn[e*nsh+co]] += w * g.vol[co];
+            vol[conn[e*nsh+co]] += g.vol[co];
+        }
+    }
+    for (int64_t a = 0; a < n_node; a++) if (vol[a] > 0) vort[a] /= vol[a];
+    free(vol);
+    return rc;
+}
+
+/* kineticEnergy (navier_stokes_tools.h:850-965) and cflNumber (:731-848) of a Crouzeix-Raviart velocity field:
+ *   value_e = sum_s N^CR_s(barycentre) u_s,  E = sum_e vol_e |value_e|^2 / sum_e vol_e   (vol_e = sum of the CR SCV volumes);
+ *   cfl = max_e max_{i<j} dt |(x_i - x_j) . value_e| / |x_i - x_j|^2,  x_s = SCV ip of side s.
+ * u: FVCR dof vector (side*dim+d). out[0] = kinetic energy, out[1] = max CFL number. */
+int ora_fvcr_diagnostics(int elem, int64_t n_elem, const int32_t *conn, const double *coords, const int32_t *es, const double *u,
+                         double dt, double *out)
+{
+    if (elem != ORA_TRI && elem != ORA_TET) return fail("ora_fvcr_diagnostics: simplices only");
+    const int dim = ora_elem_dim(elem), nco = ora_elem_nsh(elem), ns = ora_elem_nside(elem);
+    double E = 0, V = 0, cfl = 0;
+    for (int64_t e = 0; e < n_elem; e++) {
+        double xc[MAXSH*3], N[6], lb[3] = {0,0,0}; CRGeom g;
+        for (int k = 0; k < nco; k++) for (int d = 0; d < dim; d++) xc[k*dim+d] = coords[(int64_t)conn[e*nco+k]*dim+d];
+        if (cr_geom_update(&g, elem, xc)) return -1;
+        for (int d = 0; d < dim; d++) lb[d] = 1.0 / (dim + 1);          /* global_to_local(barycentre) of an affine simplex */
+        cr_shapes(elem, lb, N, NULL);
+        double val[3] = {0,0,0}, ve = 0;
+        for (int s = 0; s < ns; s++) { for (int d = 0; d < dim; d++) val[d] += N[s] * u[(int64_t)es[e*ns+s]*dim+d]; ve += g.vol[s]; }
+        for (int d = 0; d < dim; d++) E += ve * val[d] * val[d];
+        V += ve;
+        for (int i = 0; i < ns; i++) for (int j = i+1; j < ns; j++) {
+            double sub[3], q = 0, dd = 0;
+            for (int d = 0; d < dim; d++) { sub[d] = g.scv_xip[i][d] - g.scv_xip[j][d]; q += sub[d] * val[d]; dd += sub[d] * sub[d]; }
+            const double l = dt * 1.0 / dd * fabs(q);
+            if (l > cfl) cfl = l;
+        }
+    }
+    out[0] = E / V; out[1] = cfl;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Global level: CSR pattern = full element coupling incl. explicit zeros (App. B-7), dof
  * numbering App. B-8, serial element loop with AddLocalMatrixToGlobal-style scatter.
  * ---------------------------------------------------------------------------------------- */

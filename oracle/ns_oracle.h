@@ -141,6 +141,15 @@ int  ora_fv1_boundary(const ora_params *p, int kind, int64_t n_side, const int32
                       const int64_t *rowptr, const int32_t *colind, int what, double scale_a,
                       double *values, double *defect);
 
+/* ---- Smagorinsky turbulent viscosity as per-ip viscosity (fv1/turbulent_viscosity_fv1.h:200-383,
+ * fv1/turbulent_viscosity_fv1_impl.h:504-616,755-762,819-852) and diagnostics (navier_stokes_tools.h:386-525,731-965) ---- */
+int  ora_fv1_smagorinsky(int elem, int64_t n_elem, int64_t n_node, const int32_t *conn, const double *coords, const double *u,
+                         double c, double kin_visc, int64_t n_bside, const int32_t *belem, const int32_t *bside,
+                         const uint8_t *zero_node, double *nu_t, double *ip_visc);
+int  ora_fv1_vorticity(int elem, int64_t n_elem, int64_t n_node, const int32_t *conn, const double *coords, const double *u, double *vort);
+int  ora_fvcr_diagnostics(int elem, int64_t n_elem, const int32_t *conn, const double *coords, const int32_t *elem_sides,
+                          const double *u, double dt, double *out /*[2]: kinetic energy, max CFL*/);
+
 const char *ora_last_error(void);
 
 #ifdef __cplusplus

@@ -94,6 +94,10 @@ def lib():
         L.ora_fv1_bf_geometry.argtypes = [C.c_int, dp, C.c_int, C.c_int, C.POINTER(C.c_int), dp, dp, dp, dp]
         L.ora_fv1_boundary.argtypes = [C.POINTER(Params), C.c_int, C.c_int64, ip32, ip32, dp, ip32, dp, dp, ip64, ip32,
                                        C.c_int, C.c_double, dp, dp]
+        L.ora_fv1_smagorinsky.argtypes = [C.c_int, C.c_int64, C.c_int64, ip32, dp, dp, C.c_double, C.c_double, C.c_int64, ip32, ip32,
+                                          C.POINTER(C.c_uint8), dp, dp]
+        L.ora_fv1_vorticity.argtypes = [C.c_int, C.c_int64, C.c_int64, ip32, dp, dp, dp]
+        L.ora_fvcr_diagnostics.argtypes = [C.c_int, C.c_int64, ip32, dp, ip32, dp, C.c_double, dp]
         _lib = L
     return _lib
 
@@ -305,3 +309,40 @@ def fv1_boundary(p, kind, belem, bside, conn, coords, u, rowptr, colind, what, d
     _chk(lib().ora_fv1_boundary(C.byref(p), kind, belem.shape[0], _i32(belem), _i32(bside), _dp(data), _i32(conn), _dp(coords),
                                 _dp(u), _i64(rowptr), _i32(colind), what, scale_a, _dp(values), _dp(defect)))
     return values, defect
+
+
+# ---- turbulent viscosity and diagnostics ----
+def fv1_smagorinsky(elem, conn, coords, u, c=0.05, kin_visc=0.0, belem=None, bside=None, zero_nodes=None):
+    """FV1SmagorinskyTurbViscData: returns (nu_t [n_node], ip_visc [n_elem][nip] = interpolated nu_t + kin_visc)"""
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    coords, u = _f64(coords), _f64(u)
+    n_node = coords.shape[0]
+    nb = 0 if belem is None else len(belem)
+    be = None if belem is None else np.ascontiguousarray(belem, dtype=np.int32)
+    bs = None if bside is None else np.ascontiguousarray(bside, dtype=np.int32)
+    z = None
+    if zero_nodes is not None:
+        z = np.zeros(n_node, dtype=np.uint8)
+        z[np.asarray(zero_nodes, dtype=np.int64)] = 1
+    nut, ipv = np.zeros(n_node), np.zeros((conn.shape[0], NIP[elem]))
+    _chk(lib().ora_fv1_smagorinsky(elem, conn.shape[0], n_node, _i32(conn), _dp(coords), _dp(u), c, kin_visc, nb, _i32(be), _i32(bs),
+                                   None if z is None else z.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(nut), _dp(ipv)))
+    return nut, ipv
+
+
+def fv1_vorticity(elem, conn, coords, u):
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    coords, u = _f64(coords), _f64(u)
+    vort = np.zeros(coords.shape[0])
+    _chk(lib().ora_fv1_vorticity(elem, conn.shape[0], coords.shape[0], _i32(conn), _dp(coords), _dp(u), _dp(vort)))
+    return vort
+
+
+def fvcr_diagnostics(elem, conn, coords, elem_sides, u, dt=1.0):
+    """(kinetic energy, max CFL number) of a Crouzeix-Raviart velocity field"""
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    es = np.ascontiguousarray(elem_sides, dtype=np.int32)
+    coords, u = _f64(coords), _f64(u)
+    out = np.zeros(2)
+    _chk(lib().ora_fvcr_diagnostics(elem, conn.shape[0], _i32(conn), _dp(coords), _i32(es), _dp(u), dt, _dp(out)))
+    return out[0], out[1]

@@ -46,6 +46,46 @@ NSB_DEV void bf_corner_set(const double (*x)[ET<E>::DIM], int side, int j, doubl
     }
 }
 
+// outward, area-scaled normal and local ip of boundary face j of a side (x: global element corners)
+template <int E>
+NSB_DEV void bf_normal_lip(const double (*x)[ET<E>::DIM], int side, int j, double* n, double* lip)
+{
+    constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
+    double xr[NSH][DIM], c[4][DIM], lc[4][DIM];
+#pragma unroll
+    for (int k = 0; k < NSH; k++)
+#pragma unroll
+        for (int d = 0; d < DIM; d++) xr[k][d] = tab::CORNER[E][k][d];
+    int nc;
+    bf_corner_set<E>(x, side, j, c, nc);
+    bf_corner_set<E>(xr, side, j, lc, nc);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) { double t = 0.0; for (int k = 0; k < nc; k++) t += lc[k][d]; lip[d] = t / nc; }
+    if constexpr (DIM == 2) { n[0] = c[1][1] - c[0][1]; n[1] = -(c[1][0] - c[0][0]); }
+    else {
+        double av[3], bv[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { av[d] = c[2][d] - c[0][d]; bv[d] = c[3][d] - c[1][d]; }
+        cross3(n, av, bv);
+#pragma unroll
+        for (int d = 0; d < 3; d++) n[d] *= 0.5;
+    }
+    // outward: away from the element barycentre
+    const int ns = tab::SIDE_N[E][side];
+    double o = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+        double bary = 0.0, sc = 0.0;
+        for (int k = 0; k < NSH; k++) bary += x[k][d];
+        for (int k = 0; k < ns; k++) sc += x[tab::SIDE[E][side][k]][d];
+        o += n[d] * (sc / ns - bary / NSH);
+    }
+    if (o < 0) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) n[d] = -n[d];
+    }
+}
+
 template <int E>
 __global__ void __launch_bounds__(64) fv1_boundary_kernel(KParams p, MeshDev m, int kind, int64_t n_bnode, const int32_t* __restrict__ bnode,
                                                           const int64_t* __restrict__ bptr, const BndFace* __restrict__ bf,
@@ -66,45 +106,17 @@ __global__ void __launch_bounds__(64) fv1_boundary_kernel(KParams p, MeshDev m, 
     for (int64_t q = bptr[i]; q < bptr[i + 1]; q++) {
         const BndFace f = bf[q];
         const int32_t* nd = m.conn + (int64_t)f.elem * NSH;
-        double x[NSH][DIM], xr[NSH][DIM], ul[NSH][NF];
+        double x[NSH][DIM], ul[NSH][NF];
 #pragma unroll
         for (int k = 0; k < NSH; k++) {
             const int64_t g = nd[k];
 #pragma unroll
-            for (int d = 0; d < DIM; d++) { x[k][d] = m.coords[g * DIM + d]; xr[k][d] = tab::CORNER[E][k][d]; }
+            for (int d = 0; d < DIM; d++) x[k][d] = m.coords[g * DIM + d];
 #pragma unroll
             for (int c = 0; c < NF; c++) ul[k][c] = u ? u[g * NF + c] : 0.0;
         }
-        double c[4][DIM], lc[4][DIM], n[DIM], lip[DIM];
-        int nc;
-        bf_corner_set<E>(x, f.side, f.j, c, nc);
-        bf_corner_set<E>(xr, f.side, f.j, lc, nc);
-#pragma unroll
-        for (int d = 0; d < DIM; d++) { double t = 0.0; for (int k = 0; k < nc; k++) t += lc[k][d]; lip[d] = t / nc; }
-        if constexpr (DIM == 2) { n[0] = c[1][1] - c[0][1]; n[1] = -(c[1][0] - c[0][0]); }
-        else {
-            double av[3], bv[3];
-#pragma unroll
-            for (int d = 0; d < 3; d++) { av[d] = c[2][d] - c[0][d]; bv[d] = c[3][d] - c[1][d]; }
-            cross3(n, av, bv);
-#pragma unroll
-            for (int d = 0; d < 3; d++) n[d] *= 0.5;
-        }
-        {   // outward: away from the element barycentre
-            const int ns = tab::SIDE_N[E][f.side];
-            double o = 0.0;
-#pragma unroll
-            for (int d = 0; d < DIM; d++) {
-                double bary = 0.0, sc = 0.0;
-                for (int k = 0; k < NSH; k++) bary += x[k][d];
-                for (int k = 0; k < ns; k++) sc += x[tab::SIDE[E][f.side][k]][d];
-                o += n[d] * (sc / ns - bary / NSH);
-            }
-            if (o < 0) {
-#pragma unroll
-                for (int d = 0; d < DIM; d++) n[d] = -n[d];
-            }
-        }
+        double n[DIM], lip[DIM];
+        bf_normal_lip<E>(x, f.side, f.j, n, lip);
         if (kind == 1) {
             if (want_def) {
                 double s = 0.0;

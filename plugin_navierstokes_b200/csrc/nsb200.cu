@@ -21,6 +21,7 @@
 #include "ns_fused.cuh"
 #include "ns_tile.cuh"
 #include "ns_bnd.cuh"
+#include "ns_turb.cuh"
 
 using namespace nsb;
 
@@ -186,7 +187,8 @@ struct nsb_ctx {
     int64_t* d_dir = nullptr; int64_t n_dir = 0; double* d_dirval = nullptr;
     // boundary faces of the boundary discs (ns_bnd.cuh), per kind: BFs sorted by grid node
     struct BndSet { int64_t n_bnode = 0, n_bf = 0; int32_t* d_bnode = nullptr; int64_t* d_bptr = nullptr; nsb::BndFace* d_bf = nullptr; double* d_data = nullptr; };
-    BndSet bnd[2];
+    BndSet bnd[3];
+    int32_t* d_bidx = nullptr; double* d_dbf = nullptr; uint8_t* d_zflag = nullptr; double* d_nut = nullptr; double* d_diag = nullptr;   // turbulent viscosity / diagnostics scratch
     // fused tile kernel (ns_tile.cuh, 3-D element types): the patch tables above built with the tile capacities + local-node tables
     bool tile_ok = false;
     int32_t* d_plnodes = nullptr; uint8_t* d_pecorner = nullptr;
@@ -264,6 +266,7 @@ static void free_mesh(nsb_ctx* c)
     for (int i = 0; i < 5; i++) { cudaFree(c->d_ip[i]); c->d_ip[i] = nullptr; }
     cudaFree(c->d_bcol); cudaFree(c->d_rowptr); cudaFree(c->d_jres); cudaFree(c->d_xin); cudaFree(c->d_yout); cudaFree(c->d_dir); cudaFree(c->d_dirval);
     c->d_bcol = nullptr; c->d_rowptr = nullptr; c->d_jres = nullptr; c->d_xin = c->d_yout = nullptr; c->d_dir = nullptr; c->n_dir = 0; c->d_dirval = nullptr;
+    cudaFree(c->d_bidx); cudaFree(c->d_dbf); cudaFree(c->d_zflag); cudaFree(c->d_nut); cudaFree(c->d_diag); c->d_bidx = nullptr; c->d_dbf = nullptr; c->d_zflag = nullptr; c->d_nut = nullptr; c->d_diag = nullptr;
     for (auto& b : c->bnd) { cudaFree(b.d_bnode); cudaFree(b.d_bptr); cudaFree(b.d_bf); cudaFree(b.d_data); b = nsb_ctx::BndSet(); }
     cudaFree(c->d_plnodes); cudaFree(c->d_pecorner); c->d_plnodes = nullptr; c->d_pecorner = nullptr; c->tile_ok = false;
     c->d_geo = nullptr; c->geo_diff_len = -1;
@@ -1099,7 +1102,7 @@ extern "C" int nsb_adjust_vector(nsb_ctx* c, double* vec, const double* g, int l
 // ------------------------------------------------------------------------------------------------
 extern "C" int nsb_set_boundary_faces(nsb_ctx* c, int kind, int64_t n_side, const int32_t* elem, const int32_t* side, const double* data)
 {
-    if (!c || kind < 0 || kind > 1) return NSB_ERR_INVALID;
+    if (!c || kind < 0 || kind > 2) return NSB_ERR_INVALID;
     if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_set_boundary_faces: no grid uploaded");
     if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_boundary_faces: FV1 only");
     if (n_side < 0 || (n_side > 0 && (!elem || !side))) return NSB_ERR_INVALID;
@@ -1108,6 +1111,7 @@ extern "C" int nsb_set_boundary_faces(nsb_ctx* c, int kind, int64_t n_side, cons
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     nsb_ctx::BndSet& b = c->bnd[kind];
     cudaFree(b.d_bnode); cudaFree(b.d_bptr); cudaFree(b.d_bf); cudaFree(b.d_data); b = nsb_ctx::BndSet();
+    if (kind == NSB_BND_TURB_ZERO) { cudaFree(c->d_bidx); cudaFree(c->d_dbf); c->d_bidx = nullptr; c->d_dbf = nullptr; }
     if (n_side == 0) return NSB_OK;
     const int nsh = kNSH[c->elem], dim = kDIM[c->elem], nside = kNSIDE[c->elem];
     static const int side_n[4] = {2, 2, 3, 4};
@@ -1136,6 +1140,13 @@ extern "C" int nsb_set_boundary_faces(nsb_ctx* c, int kind, int64_t n_side, cons
     CUDA_TRY(c, upload(c, &b.d_bptr, bptr.data(), bptr.size()));
     CUDA_TRY(c, upload(c, &b.d_bf, bf.data(), bf.size()));
     if (kind == NSB_BND_INFLOW) CUDA_TRY(c, upload(c, &b.d_data, data, (size_t)n_side * 4 * dim));
+    if (kind == NSB_BND_TURB_ZERO) {
+        std::vector<int32_t> bidx((size_t)c->n_node, -1);
+        for (size_t i = 0; i < bnode.size(); i++) bidx[bnode[i]] = (int32_t)i;
+        cudaFree(c->d_bidx); cudaFree(c->d_dbf); c->d_bidx = nullptr; c->d_dbf = nullptr;
+        CUDA_TRY(c, upload(c, &c->d_bidx, bidx.data(), bidx.size()));
+        CUDA_TRY(c, dev_malloc(c, &c->d_dbf, sizeof(double) * bnode.size() * dim * dim));
+    }
     return NSB_OK;
 }
 
@@ -1177,6 +1188,103 @@ extern "C" int nsb_assemble_boundary(nsb_ctx* c, int what, const double* u, doub
         if (dfc) CUDA_TRY(c, cudaMemcpyAsync(defect, dd, nb, cudaMemcpyDeviceToHost, c->stream));
         return check_device_error(c);
     }
+    return NSB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Smagorinsky viscosity as device-side provider of the per-ip viscosity import; diagnostics (ns_turb.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_turbulent_viscosity(nsb_ctx* c, int model, double cmodel, const double* u, int64_t n_zero, const int64_t* zero_nodes,
+                                       double* nu_t, int location)
+{
+    if (!c) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_turbulent_viscosity: no grid uploaded");
+    if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_turbulent_viscosity: FV1 only");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (model == NSB_TURB_OFF) return nsb_set_ip_data(c, NSB_IP_KIN_VISC_SCVF, nullptr, NSB_HOST);
+    if (model != NSB_TURB_SMAGORINSKY) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_turbulent_viscosity: only the Smagorinsky model is available on the device");
+    if (!u) return set_err(c, NSB_ERR_INVALID, "nsb_turbulent_viscosity: u == NULL");
+    if (!c->prm.kin_visc_set) return set_err(c, NSB_ERR_SETUP, "NavierStokes::prep_elem_loop: Kinematic Viscosity has not been set, but is required.");
+    int rc;
+    const double* du = u;
+    if (location == NSB_HOST) {
+        if ((rc = ensure(c, &c->d_u, c->n_dof))) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, sizeof(double) * c->n_dof, cudaMemcpyHostToDevice, c->stream)); du = c->d_u;
+    }
+    if ((rc = ensure(c, &c->d_nut, (size_t)c->n_node))) return rc;
+    cudaFree(c->d_zflag); c->d_zflag = nullptr;
+    if (n_zero > 0) {
+        if (!zero_nodes) return NSB_ERR_INVALID;
+        std::vector<uint8_t> z((size_t)c->n_node, 0);
+        for (int64_t i = 0; i < n_zero; i++) {
+            if (zero_nodes[i] < 0 || zero_nodes[i] >= c->n_node) return set_err(c, NSB_ERR_INVALID, "nsb_turbulent_viscosity: bad node index");
+            z[zero_nodes[i]] = 1;
+        }
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, upload(c, &c->d_zflag, z.data(), z.size()));
+    }
+    const int nip = c->elem == NSB_HEX ? 12 : (c->elem == NSB_TET ? 6 : kNSH[c->elem]);
+    double*& ipv = c->d_ip[NSB_IP_KIN_VISC_SCVF];
+    if (!ipv) CUDA_TRY(c, dev_malloc(c, &ipv, sizeof(double) * (size_t)c->n_elem * nip));
+    const MeshDev m = mesh_view(c);
+    const nsb_ctx::BndSet& b = c->bnd[NSB_BND_TURB_ZERO];
+    const unsigned nb_node = (unsigned)((c->n_node + 127) / 128), nb_ip = (unsigned)((c->n_elem * nip + 255) / 256);
+#define NSB_TURB(EE) do { \
+        if (b.n_bnode > 0) fv1_smagorinsky_bf_kernel<EE><<<(unsigned)((b.n_bnode + 63) / 64), 64, 0, c->stream>>>(m, du, b.n_bnode, b.d_bnode, b.d_bptr, b.d_bf, c->d_dbf); \
+        fv1_smagorinsky_kernel<EE><<<nb_node, 128, 0, c->stream>>>(m, du, cmodel, b.n_bnode > 0 ? c->d_bidx : nullptr, c->d_dbf, c->d_zflag, c->d_nut); \
+        fv1_ip_visc_kernel<EE><<<nb_ip, 256, 0, c->stream>>>(m, c->d_nut, c->prm.kin_visc, ipv); } while (0)
+    switch (c->elem) { case NSB_TRI: NSB_TURB(E_TRI); break; case NSB_QUAD: NSB_TURB(E_QUAD); break; case NSB_TET: NSB_TURB(E_TET); break; default: NSB_TURB(E_HEX); }
+#undef NSB_TURB
+    c->launches += b.n_bnode > 0 ? 3 : 2;
+    CUDA_TRY(c, cudaGetLastError());
+    if (nu_t) {
+        if (location == NSB_HOST) { CUDA_TRY(c, cudaMemcpyAsync(nu_t, c->d_nut, sizeof(double) * c->n_node, cudaMemcpyDeviceToHost, c->stream)); CUDA_TRY(c, cudaStreamSynchronize(c->stream)); }
+        else CUDA_TRY(c, cudaMemcpyAsync(nu_t, c->d_nut, sizeof(double) * c->n_node, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return NSB_OK;
+}
+
+extern "C" int nsb_diagnostic(nsb_ctx* c, int kind, const double* u, double dt, double* out, int location)
+{
+    if (!c || !u || !out) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_diagnostic: no grid uploaded");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc;
+    const double* du = u;
+    if (location == NSB_HOST) {
+        if ((rc = ensure(c, &c->d_u, c->n_dof))) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, sizeof(double) * c->n_dof, cudaMemcpyHostToDevice, c->stream)); du = c->d_u;
+    }
+    if (kind == NSB_DIAG_VORTICITY) {
+        if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_diagnostic: the vorticity of a Crouzeix-Raviart field (vorticityFVCR) is not available on the device");
+        double* dv = out;
+        if (location == NSB_HOST) { if ((rc = ensure(c, &c->d_nut, (size_t)c->n_node))) return rc; dv = c->d_nut; }
+        const MeshDev m = mesh_view(c);
+        const unsigned nb = (unsigned)((c->n_node + 127) / 128);
+        switch (c->elem) {
+            case NSB_TRI: fv1_vorticity_kernel<E_TRI><<<nb, 128, 0, c->stream>>>(m, du, dv, c->d_err); break;
+            case NSB_QUAD: fv1_vorticity_kernel<E_QUAD><<<nb, 128, 0, c->stream>>>(m, du, dv, c->d_err); break;
+            case NSB_TET: fv1_vorticity_kernel<E_TET><<<nb, 128, 0, c->stream>>>(m, du, dv, c->d_err); break;
+            default: fv1_vorticity_kernel<E_HEX><<<nb, 128, 0, c->stream>>>(m, du, dv, c->d_err);
+        }
+        c->launches++;
+        CUDA_TRY(c, cudaGetLastError());
+        if (location == NSB_HOST) { CUDA_TRY(c, cudaMemcpyAsync(out, dv, sizeof(double) * c->n_node, cudaMemcpyDeviceToHost, c->stream)); return check_device_error(c); }
+        return NSB_OK;
+    }
+    if (kind != NSB_DIAG_KINETIC_ENERGY && kind != NSB_DIAG_CFL) return NSB_ERR_INVALID;
+    if (c->disc != NSB_DISC_FVCR) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_diagnostic: kineticEnergy / cflNumber work on a Crouzeix-Raviart velocity (navier_stokes_tools.h:731-965)");
+    const int64_t nblk = (c->n_elem + 255) / 256;
+    if (!c->d_diag) CUDA_TRY(c, dev_malloc(c, &c->d_diag, sizeof(double) * (size_t)(nblk * 3 + 2)));
+    double* res = c->d_diag + nblk * 3;
+    if (c->elem == NSB_TRI) fvcr_diag_kernel<E_TRI><<<(unsigned)nblk, 256, 0, c->stream>>>(c->fvcr, du, dt, c->d_diag);
+    else fvcr_diag_kernel<E_TET><<<(unsigned)nblk, 256, 0, c->stream>>>(c->fvcr, du, dt, c->d_diag);
+    diag_final_kernel<<<1, 256, 0, c->stream>>>(nblk, c->d_diag, res);
+    c->launches += 2;
+    CUDA_TRY(c, cudaGetLastError());
+    const double* src = res + (kind == NSB_DIAG_CFL ? 1 : 0);
+    CUDA_TRY(c, cudaMemcpyAsync(out, src, sizeof(double), location == NSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    if (location == NSB_HOST) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return NSB_OK;
 }
 

@@ -492,6 +492,34 @@ class _DeviceDisc:
                                             capi.DEVICE if on_dev else capi.HOST))
         return defect
 
+    # ---- diagnostics of navier_stokes_tools.h on the device (nsb_diagnostic) ----
+    def _diagnostic(self, kind, u, dt, n_out):
+        on_dev = _is_torch(u)
+        if on_dev:
+            import torch
+            self.use_stream(torch.cuda.current_stream(u.device).cuda_stream)
+            out = torch.zeros(n_out, dtype=torch.float64, device=u.device)
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+            out = np.zeros(n_out)
+        self._context()
+        self._check(capi.lib().nsb_diagnostic(self._ctx, kind, self._ptr(u), float(dt), self._ptr(out), capi.DEVICE if on_dev else capi.HOST))
+        return out
+
+    def vorticity(self, u):
+        """vorticityFV1 (navier_stokes_tools.h:386-525): d_x v - d_y u per vertex (FV1 grids)"""
+        return self._diagnostic(capi.DIAG_VORTICITY, u, 0.0, self.num_dofs // len(self._fcts))
+
+    def kinetic_energy(self, u):
+        """kineticEnergy (navier_stokes_tools.h:850-965), Crouzeix-Raviart velocity (FVCR grids)"""
+        r = self._diagnostic(capi.DIAG_KINETIC_ENERGY, u, 0.0, 1)
+        return float(r[0])
+
+    def cfl_number(self, u, dt):
+        """cflNumber (navier_stokes_tools.h:731-848), Crouzeix-Raviart velocity (FVCR grids)"""
+        r = self._diagnostic(capi.DIAG_CFL, u, dt, 1)
+        return float(r[0])
+
     def assemble_jacobian(self, u, **kw):
         return self.assemble(capi.JAC_A, u, **kw)[0]
 
@@ -802,6 +830,60 @@ class NavierStokesNoNormalStressOutflowFV1:
 
 
 NavierStokesNoNormalStressOutflow = NavierStokesNoNormalStressOutflowFV1
+
+
+class FV1SmagorinskyTurbViscData:
+    """fv1/turbulent_viscosity_fv1.h:200-383 ("NavierStokesFV1SmagorinskyTurbViscData", register_fv1.cpp): Smagorinsky eddy
+    viscosity nu_t = c delta^2 |S| at the vertices from the deformation tensor of the current solution, interpolated to the SCVF
+    ips and added to the kinematic viscosity. update(u) runs on the device and fills the per-ip viscosity import of the master
+    disc (nsb_turbulent_viscosity) -- the role of passing this object to set_kinematic_viscosity() in the reference."""
+
+    def __init__(self, master, c=0.05):
+        self._master, self._c = master, float(c)
+        self._be, self._bs, self._zero = [], [], []
+        self.nu_t = None
+
+    def set_model_parameter(self, c):
+        self._c = float(c)
+
+    def set_kinematic_viscosity(self, v):
+        self._master.set_kinematic_viscosity(v)
+
+    def set_turbulence_zero_bnd(self, elems, sides, nodes):
+        """setTurbulenceZeroBoundaries: boundary sides (BF closure of the deformation tensor) and the vertices of those subsets
+        (nu_t = 0)"""
+        self._be.append(np.asarray(elems, dtype=np.int32).reshape(-1))
+        self._bs.append(np.asarray(sides, dtype=np.int32).reshape(-1))
+        self._zero.append(np.asarray(nodes, dtype=np.int64).reshape(-1))
+        self._dirty = True
+
+    def update(self, u, want_nodal=False):
+        d = self._master
+        L = capi.lib()
+        p = d._params()                                          # flushes pending constant / callable imports first
+        d._check(L.nsb_set_params(d._context(), C.byref(p)))
+        if getattr(self, "_dirty", False):
+            d.set_boundary_faces(capi.BND_TURB_ZERO, np.concatenate(self._be), np.concatenate(self._bs))
+            self._dirty = False
+        zero = np.ascontiguousarray(np.concatenate(self._zero), dtype=np.int64) if self._zero else np.zeros(0, dtype=np.int64)
+        on_dev = _is_torch(u)
+        out = None
+        if on_dev:
+            import torch
+            d.use_stream(torch.cuda.current_stream(u.device).cuda_stream)
+            if want_nodal:
+                out = torch.zeros(d.num_dofs // len(d._fcts), dtype=torch.float64, device=u.device)
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+            if want_nodal:
+                out = np.zeros(d.num_dofs // len(d._fcts))
+        d._check(L.nsb_turbulent_viscosity(d._ctx, capi.TURB_SMAGORINSKY, self._c, d._ptr(u), zero.size, d._ptr(zero) if zero.size else None,
+                                           d._ptr(out), capi.DEVICE if on_dev else capi.HOST))
+        self.nu_t = out
+        return out
+
+    def disable(self):
+        self._master._check(capi.lib().nsb_turbulent_viscosity(self._master._context(), capi.TURB_OFF, 0.0, None, 0, None, None, capi.HOST))
 
 
 class ThetaTimeStep:
