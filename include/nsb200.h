@@ -186,6 +186,16 @@ int  nsb_turbulent_viscosity(nsb_ctx *ctx, int model, double c, const double *u,
 enum { NSB_DIAG_VORTICITY = 0, NSB_DIAG_KINETIC_ENERGY = 1, NSB_DIAG_CFL = 2 };
 int  nsb_diagnostic(nsb_ctx *ctx, int kind, const double *u, double dt, double *out, int location);
 
+/* DiscConstraintFVCR (fvcr/disc_constraint_fvcr.h:164-1198) in its default configuration (:254-300: linear-upwind
+ * and linear-pressure correction of the DEFECT, not adaptive, no limiter): adjust_defect (:1149-1171) -> add_defect (:770-1147).
+ * ADDS the correction of the state u to `defect` (call after nsb_assemble*, per time point with its stiffness scale s_a as the
+ * reference does). lin_upwind / lin_pressure = bLinUpConvDefect / bLinPressureDefect. zero_grad_sides (host pointer): the sides of
+ * the zero-gradient subsets (set_zero_grad_bnd :288-292) -- elements touching one are skipped. Owner-computes over the side ->
+ * element adjacency: bitwise deterministic. FVCR grids (simplices). Not available: bAdaptive (hanging nodes), the Jacobian
+ * variants (bLinUpConvJacobian / bLinPressureJacobian) and the limiter. */
+int  nsb_fvcr_constraint_defect(nsb_ctx *ctx, const double *u, double s_a, int lin_upwind, int lin_pressure, int64_t n_zero,
+                                const int64_t *zero_grad_sides, double *defect, int location);
+
 /* Per-ip data imports: the reference evaluates UserData for viscosity / density / source at the integration points
  * (m_imKinViscosity, m_imDensitySCVF at the SCVF ips; m_imDensitySCV, m_imSourceSCV at the SCV ips; m_imSourceSCVF at the SCVF
  * ips -- fv1/navier_stokes_fv1.cpp:184-197, read at :336,351,390,393,708,805,835,866 and fv1/stabilization.cpp:151,198,229).

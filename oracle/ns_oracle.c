@@ -1586,6 +1586,87 @@ int ora_fvcr_diagnostics(int elem, int64_t n_elem, const int32_t *conn, const do
 }
 
 /* ------------------------------------------------------------------------------------------
+ * DiscConstraintFVCR (fvcr/disc_constraint_fvcr.h:164-1198), the default configuration
+ * init(u, bLinUpConvDefect = true, false, bLinPressureDefect = true, false, bAdaptive = false, bLimiter = false) (:254-300):
+ * post-assembly correction of the DEFECT of the FVCR discretisation (adjust_defect :1149-1171 -> add_defect :770-1147)
+ *   1. side gradients (:780-870): acGrad(side) = sum_elem vol_scv * [sum_sh u_sh,d0 grad_sh,d1] / sum_elem vol_scv
+ *   2. per element (skipped if one of its sides lies in a zero-gradient subset, :321-327, :1022-1024):
+ *      StdVel(ip) = sum_sh u_sh shape_sh(ip);  flux = s_a StdVel . n;  base = flux > 0 ? from : to   (:1103-1108)
+ *      linear upwind: upwindVel_d1 = acGrad(base)_d1 . (x_ip - x_scv(base)); d(d1, from) += upwindVel flux, d(d1, to) -= (:1118-1128)
+ *      linear pressure (:1058-1090, :1109-1133): pGrad = 1/|elem| sum_sides n_side * (boundary side ? p_e : (p_e + p_nb)/2),
+ *      pressure = s_a pGrad . (x_ip - barycentre);  d(d1, from) += pressure n_d1,  d(d1, to) -= pressure n_d1
+ * (hanging nodes / bAdaptive, the Jacobian variants and the limiter are out of scope). u: FVCR dof vector; zero_grad_side
+ * [n_side] flags or NULL; the correction is ADDED to defect.
+ * ---------------------------------------------------------------------------------------- */
+int ora_fvcr_constraint_defect(int elem, int64_t n_elem, int64_t n_side, const int32_t *conn, const double *coords, const int32_t *es,
+                               const double *u, double s_a, int lin_upwind, int lin_pressure, const uint8_t *zero_grad_side,
+                               double *defect)
+{
+    if (elem != ORA_TRI && elem != ORA_TET) return fail("ora_fvcr_constraint_defect: simplices only");
+    const int dim = ora_elem_dim(elem), nco = ora_elem_nsh(elem), ns = ora_elem_nside(elem), nip = elem == ORA_TRI ? 3 : 6;
+    double *grad = calloc((size_t)n_side * 9, sizeof *grad), *vol = calloc((size_t)n_side, sizeof *vol);
+    int64_t *nb = malloc(sizeof(int64_t) * (size_t)n_side * 2);
+    for (int64_t i = 0; i < n_side * 2; i++) nb[i] = -1;
+    int rc = 0;
+    for (int64_t e = 0; e < n_elem && !rc; e++) {
+        double xc[MAXSH*3]; CRGeom g;
+        for (int k = 0; k < nco; k++) for (int d = 0; d < dim; d++) xc[k*dim+d] = coords[(int64_t)conn[e*nco+k]*dim+d];
+        if ((rc = cr_geom_update(&g, elem, xc))) break;
+        double gg[3][3] = {{0}};
+        for (int d0 = 0; d0 < dim; d0++) for (int sh = 0; sh < ns; sh++) for (int d1 = 0; d1 < dim; d1++)
+            gg[d0][d1] += u[(int64_t)es[e*ns+sh]*dim+d0] * g.G[0][sh][d1];
+        for (int s = 0; s < ns; s++) {
+            const int64_t sd = es[e*ns+s];
+            for (int d0 = 0; d0 < dim; d0++) for (int d1 = 0; d1 < dim; d1++) grad[sd*9+d0*3+d1] += gg[d0][d1] * g.vol[s];
+            vol[sd] += g.vol[s];
+            if (nb[sd*2] < 0) nb[sd*2] = e; else nb[sd*2+1] = e;
+        }
+    }
+    for (int64_t sd = 0; sd < n_side; sd++) if (vol[sd] > 0) for (int i = 0; i < 9; i++) grad[sd*9+i] /= vol[sd];
+    const int64_t pbase = n_side * dim;
+    for (int64_t e = 0; e < n_elem && !rc; e++) {
+        int skip = 0;
+        if (zero_grad_side) for (int s = 0; s < ns; s++) if (zero_grad_side[es[e*ns+s]]) skip = 1;
+        if (skip) continue;
+        double xc[MAXSH*3]; CRGeom g;
+        for (int k = 0; k < nco; k++) for (int d = 0; d < dim; d++) xc[k*dim+d] = coords[(int64_t)conn[e*nco+k]*dim+d];
+        if ((rc = cr_geom_update(&g, elem, xc))) break;
+        double pg[3] = {0,0,0};
+        if (lin_pressure) {
+            const double pe = u[pbase+e];
+            double ve = 0;
+            for (int s = 0; s < ns; s++) {
+                const int64_t sd = es[e*ns+s];
+                const int64_t other = nb[sd*2] == e ? nb[sd*2+1] : nb[sd*2];
+                const double pv = other < 0 ? pe : 0.5 * (pe + u[pbase+other]);
+                for (int d = 0; d < dim; d++) pg[d] += g.scv_n[s][d] * pv;
+                ve += g.vol[s];
+            }
+            for (int d = 0; d < dim; d++) pg[d] /= ve;
+        }
+        for (int ip = 0; ip < nip; ip++) {
+            double sv[3] = {0,0,0};
+            for (int sh = 0; sh < ns; sh++) for (int d = 0; d < dim; d++) sv[d] += u[(int64_t)es[e*ns+sh]*dim+d] * g.N[ip][sh];
+            const double flux = s_a * vdot(sv, g.n[ip], dim);
+            const int base = flux > 0 ? g.from[ip] : g.to[ip];
+            double pressure = 0;
+            if (lin_pressure) { double q = 0; for (int j = 0; j < dim; j++) q += pg[j] * (g.xip[ip][j] - g.bary[j]); pressure = s_a * q; }
+            const int64_t sf = es[e*ns+g.from[ip]], st = es[e*ns+g.to[ip]], sb = es[e*ns+base];
+            for (int d1 = 0; d1 < dim; d1++) {
+                if (lin_upwind) {
+                    double uv = 0;
+                    for (int d2 = 0; d2 < dim; d2++) uv += grad[sb*9+d1*3+d2] * (g.xip[ip][d2] - g.scv_xip[base][d2]);
+                    defect[sf*dim+d1] += uv * flux; defect[st*dim+d1] -= uv * flux;
+                }
+                if (lin_pressure) { defect[sf*dim+d1] += pressure * g.n[ip][d1]; defect[st*dim+d1] -= pressure * g.n[ip][d1]; }
+            }
+        }
+    }
+    free(grad); free(vol); free(nb);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Global level: CSR pattern = full element coupling incl. explicit zeros (App. B-7), dof
  * numbering App. B-8, serial element loop with AddLocalMatrixToGlobal-style scatter.
  * ---------------------------------------------------------------------------------------- */

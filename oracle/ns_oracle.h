@@ -150,6 +150,12 @@ int  ora_fv1_vorticity(int elem, int64_t n_elem, int64_t n_node, const int32_t *
 int  ora_fvcr_diagnostics(int elem, int64_t n_elem, const int32_t *conn, const double *coords, const int32_t *elem_sides,
                           const double *u, double dt, double *out /*[2]: kinetic energy, max CFL*/);
 
+/* ---- DiscConstraintFVCR, default configuration (fvcr/disc_constraint_fvcr.h:254-300,770-1171): linear-upwind and
+ * linear-pressure correction of the FVCR defect, ADDED to defect ---- */
+int  ora_fvcr_constraint_defect(int elem, int64_t n_elem, int64_t n_side, const int32_t *conn, const double *coords,
+                                const int32_t *elem_sides, const double *u, double s_a, int lin_upwind, int lin_pressure,
+                                const uint8_t *zero_grad_side, double *defect);
+
 const char *ora_last_error(void);
 
 #ifdef __cplusplus

@@ -98,6 +98,8 @@ def lib():
                                           C.POINTER(C.c_uint8), dp, dp]
         L.ora_fv1_vorticity.argtypes = [C.c_int, C.c_int64, C.c_int64, ip32, dp, dp, dp]
         L.ora_fvcr_diagnostics.argtypes = [C.c_int, C.c_int64, ip32, dp, ip32, dp, C.c_double, dp]
+        L.ora_fvcr_constraint_defect.argtypes = [C.c_int, C.c_int64, C.c_int64, ip32, dp, ip32, dp, C.c_double, C.c_int, C.c_int,
+                                                 C.POINTER(C.c_uint8), dp]
         _lib = L
     return _lib
 
@@ -346,3 +348,20 @@ def fvcr_diagnostics(elem, conn, coords, elem_sides, u, dt=1.0):
     out = np.zeros(2)
     _chk(lib().ora_fvcr_diagnostics(elem, conn.shape[0], _i32(conn), _dp(coords), _i32(es), _dp(u), dt, _dp(out)))
     return out[0], out[1]
+
+
+def fvcr_constraint_defect(elem, conn, coords, elem_sides, n_side, u, s_a=1.0, lin_upwind=True, lin_pressure=True, zero_grad_sides=None,
+                           defect=None):
+    """DiscConstraintFVCR (default configuration): adds the linear-upwind / linear-pressure defect correction. returns defect"""
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    es = np.ascontiguousarray(elem_sides, dtype=np.int32)
+    coords, u = _f64(coords), _f64(u)
+    if defect is None:
+        defect = np.zeros(u.shape[0])
+    z = None
+    if zero_grad_sides is not None:
+        z = np.zeros(n_side, dtype=np.uint8)
+        z[np.asarray(zero_grad_sides, dtype=np.int64)] = 1
+    _chk(lib().ora_fvcr_constraint_defect(elem, conn.shape[0], n_side, _i32(conn), _dp(coords), _i32(es), _dp(u), s_a, int(lin_upwind),
+                                          int(lin_pressure), None if z is None else z.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(defect)))
+    return defect

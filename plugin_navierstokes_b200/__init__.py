@@ -13,4 +13,4 @@ from .disc import (NavierStokes, NavierStokesFV1, NavierStokesFVCR, UGError,    
                    NavierStokesLinearProfileSkewedUpwind, NavierStokesPositiveUpwind, NavierStokesRegularUpwind,
                    NavierStokesFIELDSStabilization, NavierStokesFLOWStabilization,
                    NavierStokesFV1WithoutStabilization, NavierStokesWall, NavierStokesInflowFV1, NavierStokesNoNormalStressOutflowFV1,
-                   NavierStokesNoNormalStressOutflow, FV1SmagorinskyTurbViscData, ThetaTimeStep)
+                   NavierStokesNoNormalStressOutflow, FV1SmagorinskyTurbViscData, DiscConstraintFVCR, ThetaTimeStep)

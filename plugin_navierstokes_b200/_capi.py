@@ -24,7 +24,7 @@ SYMBOLS = [
     "nsb_launch_count", "nsb_synchronize", "nsb_version", "nsb_check_errors", "nsb_query",
     "nsb_assemble_resident", "nsb_resident_jacobian", "nsb_apply_jacobian", "nsb_set_dirichlet", "nsb_adjust_jacobian",
     "nsb_adjust_vector", "nsb_set_ip_data", "nsb_set_boundary_faces", "nsb_assemble_boundary",
-    "nsb_turbulent_viscosity", "nsb_diagnostic",
+    "nsb_turbulent_viscosity", "nsb_diagnostic", "nsb_fvcr_constraint_defect",
 ]
 BND_OUTFLOW, BND_INFLOW, BND_TURB_ZERO = 0, 1, 2
 TURB_OFF, TURB_SMAGORINSKY = -1, 0
@@ -102,5 +102,6 @@ def lib():
     L.nsb_assemble_boundary.argtypes = [vp, i32, vp, C.c_double, vp, vp, i32]
     L.nsb_turbulent_viscosity.argtypes = [vp, i32, C.c_double, vp, i64, vp, vp, i32]
     L.nsb_diagnostic.argtypes = [vp, i32, vp, C.c_double, vp, i32]
+    L.nsb_fvcr_constraint_defect.argtypes = [vp, vp, C.c_double, i32, i32, i64, vp, vp, i32]
     _lib = L
     return L

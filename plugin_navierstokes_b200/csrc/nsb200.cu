@@ -22,6 +22,7 @@
 #include "ns_tile.cuh"
 #include "ns_bnd.cuh"
 #include "ns_turb.cuh"
+#include "ns_crc.cuh"
 
 using namespace nsb;
 
@@ -188,6 +189,7 @@ struct nsb_ctx {
     // boundary faces of the boundary discs (ns_bnd.cuh), per kind: BFs sorted by grid node
     struct BndSet { int64_t n_bnode = 0, n_bf = 0; int32_t* d_bnode = nullptr; int64_t* d_bptr = nullptr; nsb::BndFace* d_bf = nullptr; double* d_data = nullptr; };
     BndSet bnd[3];
+    int32_t* d_sadj = nullptr; double* d_sgrad = nullptr; uint8_t* d_zgrad = nullptr;   // DiscConstraintFVCR (ns_crc.cuh): side -> element adjacency, side gradients, zero-gradient sides
     int32_t* d_bidx = nullptr; double* d_dbf = nullptr; uint8_t* d_zflag = nullptr; double* d_nut = nullptr; double* d_diag = nullptr;   // turbulent viscosity / diagnostics scratch
     // fused tile kernel (ns_tile.cuh, 3-D element types): the patch tables above built with the tile capacities + local-node tables
     bool tile_ok = false;
@@ -266,6 +268,7 @@ static void free_mesh(nsb_ctx* c)
     for (int i = 0; i < 5; i++) { cudaFree(c->d_ip[i]); c->d_ip[i] = nullptr; }
     cudaFree(c->d_bcol); cudaFree(c->d_rowptr); cudaFree(c->d_jres); cudaFree(c->d_xin); cudaFree(c->d_yout); cudaFree(c->d_dir); cudaFree(c->d_dirval);
     c->d_bcol = nullptr; c->d_rowptr = nullptr; c->d_jres = nullptr; c->d_xin = c->d_yout = nullptr; c->d_dir = nullptr; c->n_dir = 0; c->d_dirval = nullptr;
+    cudaFree(c->d_sadj); cudaFree(c->d_sgrad); cudaFree(c->d_zgrad); c->d_sadj = nullptr; c->d_sgrad = nullptr; c->d_zgrad = nullptr;
     cudaFree(c->d_bidx); cudaFree(c->d_dbf); cudaFree(c->d_zflag); cudaFree(c->d_nut); cudaFree(c->d_diag); c->d_bidx = nullptr; c->d_dbf = nullptr; c->d_zflag = nullptr; c->d_nut = nullptr; c->d_diag = nullptr;
     for (auto& b : c->bnd) { cudaFree(b.d_bnode); cudaFree(b.d_bptr); cudaFree(b.d_bf); cudaFree(b.d_data); b = nsb_ctx::BndSet(); }
     cudaFree(c->d_plnodes); cudaFree(c->d_pecorner); c->d_plnodes = nullptr; c->d_pecorner = nullptr; c->tile_ok = false;
@@ -1288,6 +1291,54 @@ extern "C" int nsb_diagnostic(nsb_ctx* c, int kind, const double* u, double dt, 
     return NSB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// DiscConstraintFVCR, default configuration (ns_crc.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int nsb_fvcr_constraint_defect(nsb_ctx* c, const double* u, double s_a, int lin_upwind, int lin_pressure, int64_t n_zero,
+                                          const int64_t* zero_grad_sides, double* defect, int location)
+{
+    if (!c || !u || !defect) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_fvcr_constraint_defect: no grid uploaded");
+    if (c->disc != NSB_DISC_FVCR) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_fvcr_constraint_defect: FVCR only");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc;
+    const int dim = kDIM[c->elem];
+    const double* du = u; double* dd = defect;
+    const size_t nb = sizeof(double) * c->n_dof;
+    if (location == NSB_HOST) {
+        if ((rc = ensure(c, &c->d_u, c->n_dof)) || (rc = ensure(c, &c->d_def, c->n_dof))) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, nb, cudaMemcpyHostToDevice, c->stream)); du = c->d_u;
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_def, defect, nb, cudaMemcpyHostToDevice, c->stream)); dd = c->d_def;
+    }
+    if ((rc = ensure(c, &c->d_sgrad, (size_t)c->n_side * dim * dim))) return rc;
+    cudaFree(c->d_zgrad); c->d_zgrad = nullptr;
+    if (n_zero > 0) {
+        if (!zero_grad_sides) return NSB_ERR_INVALID;
+        std::vector<uint8_t> z((size_t)c->n_side, 0);
+        for (int64_t i = 0; i < n_zero; i++) {
+            if (zero_grad_sides[i] < 0 || zero_grad_sides[i] >= c->n_side) return set_err(c, NSB_ERR_INVALID, "nsb_fvcr_constraint_defect: bad side index");
+            z[zero_grad_sides[i]] = 1;
+        }
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, upload(c, &c->d_zgrad, z.data(), z.size()));
+    }
+    const unsigned nblk = (unsigned)((c->n_side + 127) / 128);
+    if (c->elem == NSB_TRI) {
+        if (lin_upwind) fvcr_side_grad_kernel<E_TRI><<<nblk, 128, 0, c->stream>>>(c->fvcr, c->d_sadj, du, c->d_sgrad, c->d_err);
+        fvcr_constraint_defect_kernel<E_TRI><<<nblk, 128, 0, c->stream>>>(c->fvcr, c->d_sadj, du, c->d_sgrad, c->d_zgrad, s_a, lin_upwind, lin_pressure, dd);
+    } else {
+        if (lin_upwind) fvcr_side_grad_kernel<E_TET><<<nblk, 128, 0, c->stream>>>(c->fvcr, c->d_sadj, du, c->d_sgrad, c->d_err);
+        fvcr_constraint_defect_kernel<E_TET><<<nblk, 128, 0, c->stream>>>(c->fvcr, c->d_sadj, du, c->d_sgrad, c->d_zgrad, s_a, lin_upwind, lin_pressure, dd);
+    }
+    c->launches += lin_upwind ? 2 : 1;
+    CUDA_TRY(c, cudaGetLastError());
+    if (location == NSB_HOST) {
+        CUDA_TRY(c, cudaMemcpyAsync(defect, dd, nb, cudaMemcpyDeviceToHost, c->stream));
+        return check_device_error(c);
+    }
+    return NSB_OK;
+}
+
 extern "C" int nsb_pack(nsb_ctx* c, int64_t n, const int64_t* idx, const double* src, double* out)
 {
     if (!c) return NSB_ERR_INVALID;
@@ -1394,6 +1445,7 @@ extern "C" int nsb_upload_mesh_fvcr(nsb_ctx* c, int elem, int64_t n_elem, int64_
     CUDA_TRY(c, upload(c, &f.pslot, pslot.data(), pslot.size()));
     CUDA_TRY(c, upload(c, &f.psort, psort.data(), psort.size()));
     CUDA_TRY(c, upload(c, &f.sadj_ptr, g.adj_ptr.data(), g.adj_ptr.size()));
+    CUDA_TRY(c, upload(c, &c->d_sadj, g.adj.data(), g.adj.size()));
     f.prow0 = rp[pbase];
     c->mesh_ready = true;
     return NSB_OK;

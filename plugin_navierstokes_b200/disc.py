@@ -886,6 +886,48 @@ class FV1SmagorinskyTurbViscData:
         self._master._check(capi.lib().nsb_turbulent_viscosity(self._master._context(), capi.TURB_OFF, 0.0, None, 0, None, None, capi.HOST))
 
 
+class DiscConstraintFVCR:
+    """fvcr/disc_constraint_fvcr.h:164-1198 ("DiscConstraintFVCR", register_fvcr.cpp): post-assembly correction of the FVCR defect
+    by a linear upwind reconstruction of the convected velocity (side gradients) and a linear pressure reconstruction. Same
+    constructor flags as the reference; available on the device: the defect variants of the default configuration."""
+
+    def __init__(self, disc, bLinUpConvDefect=True, bLinUpConvJacobian=False, bLinPressureDefect=True, bLinPressureJacobian=False,
+                 bAdaptive=False, bLimiter=False, zero_grad_sides=None):
+        if disc.disc_type() != "fvcr":
+            raise UGError("DiscConstraintFVCR: works on the Crouzeix-Raviart discretisation")
+        if bLinUpConvJacobian or bLinPressureJacobian or bAdaptive or bLimiter:
+            raise UGError("DiscConstraintFVCR: device path provides the defect corrections only (no Jacobian variants, hanging nodes or limiter)")
+        self._disc, self._up, self._pr = disc, bool(bLinUpConvDefect), bool(bLinPressureDefect)
+        self._zero = np.zeros(0, dtype=np.int64)
+        if zero_grad_sides is not None:
+            self.set_zero_grad_bnd(zero_grad_sides)
+
+    def set_zero_grad_bnd(self, sides):
+        self._zero = np.ascontiguousarray(sides, dtype=np.int64).reshape(-1)
+
+    def set_limiter(self, b):
+        if b:
+            raise UGError("DiscConstraintFVCR: the limiter is not available on the device path")
+
+    def adjust_defect(self, d, u, scale_stiff=1.0):
+        """d += correction(u) (adjust_defect :1149-1171; with a time series call once per time point with its stiffness scale)"""
+        dsc = self._disc
+        on_dev = _is_torch(u)
+        if on_dev:
+            import torch
+            dsc.use_stream(torch.cuda.current_stream(u.device).cuda_stream)
+        else:
+            u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+            if d.dtype != np.float64 or not d.flags.c_contiguous:
+                raise UGError("adjust_defect: defect must be a contiguous float64 array")
+        if not self._up and not self._pr:
+            return d
+        z = self._zero
+        dsc._check(capi.lib().nsb_fvcr_constraint_defect(dsc._context(), dsc._ptr(u), float(scale_stiff), int(self._up), int(self._pr), z.size,
+                                                         dsc._ptr(z) if z.size else None, dsc._ptr(d), capi.DEVICE if on_dev else capi.HOST))
+        return d
+
+
 class ThetaTimeStep:
     """instationary combination (ugcore ThetaTimeStep drives add_jac_A/M, add_def_A/M with the scales
     s_m = 1, s_a = theta dt at the new time point and s_m = -1, s_a = (1 - theta) dt at the old one,
