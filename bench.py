@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=96, help="cells per direction of the CPU sample (96^3 = 0.88 M elements, ~2 s per sweep pair on 16 cores)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange after the whole assembly instead of behind the interior rows")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e-full", action="store_true", help="skip the full-matrix D2H variant of the end-to-end leg")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the owner-row check against the single-domain oracle")
@@ -246,13 +247,24 @@ def main():
     vals = torch.empty(nnz, dtype=torch.float64, device=dev)
     dfc = torch.empty(n_dof, dtype=torch.float64, device=dev)
     exch = None
+    overlap = False
     if world > 1:
         from plugin_navierstokes_b200 import partition
         exch = partition.InterfaceExchange(disc, prob["iface"], dev)
+        overlap = not args.no_overlap
+        if overlap:
+            exch.enable_overlap()          # interface rows first; the exchange then runs behind the interior rows
 
     def step():
-        disc.assemble(what, ud, values=vals, defect=dfc, scatter_mode=mode)
-        if exch is not None:
+        if exch is None:
+            disc.assemble(what, ud, values=vals, defect=dfc, scatter_mode=mode)
+        elif overlap:
+            disc.assemble(what | capi.PHASE_PRIORITY, ud, values=vals, defect=dfc, scatter_mode=mode)
+            works = exch.start_sum_to_owner(vals, dfc)
+            disc.assemble(what | capi.PHASE_REST, ud, values=vals, defect=dfc, scatter_mode=mode)
+            exch.finish_sum_to_owner(works, vals, dfc)
+        else:
+            disc.assemble(what, ud, values=vals, defect=dfc, scatter_mode=mode)
             exch.sum_to_owner(vals, dfc)
 
     for _ in range(args.warmup):
@@ -271,10 +283,14 @@ def main():
     ev[0].record()
     for i in range(args.steps):
         ev[2 * i + 1].record()
-        disc.assemble(what, ud, values=vals, defect=dfc, scatter_mode=mode)
-        ev[2 * i + 2].record()
-        if exch is not None:
-            exch.sum_to_owner(vals, dfc)
+        if exch is not None and overlap:
+            step()                          # assembly and exchange interleaved: the pair of events brackets both
+            ev[2 * i + 2].record()
+        else:
+            disc.assemble(what, ud, values=vals, defect=dfc, scatter_mode=mode)
+            ev[2 * i + 2].record()
+            if exch is not None:
+                exch.sum_to_owner(vals, dfc)
     ev[-1].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -421,6 +437,10 @@ def main():
         }
         if parity_maxrel is not None:
             out["parity_maxrel"] = parity_maxrel
+        if world > 1:
+            out["config"]["interface_exchange"] = ("overlapped: interface rows first (NSB_PHASE_PRIORITY), NCCL p2p behind the interior rows"
+                                                   if overlap else "after the assembly pass")
+            out["config"]["exchange_bytes_per_rank"] = exch.bytes_per_exchange()
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -196,6 +196,18 @@ int  nsb_diagnostic(nsb_ctx *ctx, int kind, const double *u, double dt, double *
 int  nsb_fvcr_constraint_defect(nsb_ctx *ctx, const double *u, double s_a, int lin_upwind, int lin_pressure, int64_t n_zero,
                                 const int64_t *zero_grad_sides, double *defect, int location);
 
+/* Phased assembly for the overlap of the interface exchange with the interior assembly ("hide behind interior
+ * assembly"; replaces the blocking slave -> master summation of fvcr/pcr_ilut.h:182-194). nsb_set_priority_nodes names the grid
+ * nodes (host pointer; n = 0 clears) whose CSR rows / defect entries are produced first -- the interface nodes of a partition.
+ *   nsb_assemble(what | NSB_PHASE_PRIORITY, ...)  flux kernel + the rows of the priority nodes
+ *   ... the caller packs / sends the interface rows on another stream ...
+ *   nsb_assemble(what | NSB_PHASE_REST, ...)      the remaining rows, from the SCVF records of the first call (same u, same
+ *                                                 parameters, same pointers; device pointers only)
+ * Without a phase flag the pass is unchanged (one launch over the same node order). Paths without a separate rows kernel
+ * (element kernels, fused 2-D kernel, FVCR) do the whole pass in the priority phase; the second call is then a no-op. */
+enum { NSB_PHASE_PRIORITY = 256, NSB_PHASE_REST = 512 };
+int  nsb_set_priority_nodes(nsb_ctx *ctx, int64_t n, const int64_t *nodes);
+
 /* Per-ip data imports: the reference evaluates UserData for viscosity / density / source at the integration points
  * (m_imKinViscosity, m_imDensitySCVF at the SCVF ips; m_imDensitySCV, m_imSourceSCV at the SCV ips; m_imSourceSCVF at the SCVF
  * ips -- fv1/navier_stokes_fv1.cpp:184-197, read at :336,351,390,393,708,805,835,866 and fv1/stabilization.cpp:151,198,229).

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libnsb200.so")
 TRI, QUAD, TET, HEX = 0, 1, 2, 3
 DISC_FV1, DISC_FVCR = 0, 1
 JAC_A, DEF_A, JAC_M, DEF_M, RHS = 1, 2, 4, 8, 16
+PHASE_PRIORITY, PHASE_REST = 256, 512
 SCATTER_GATHER, SCATTER_COLORED, SCATTER_ATOMIC = 0, 1, 2
 HOST, DEVICE = 0, 1
 Q_DEVICE_BYTES, Q_SETUP_SECONDS, Q_FUSED, Q_PATCHES, Q_SCVF_EVALS, Q_PATCH_TABLE_BYTES = range(6)
@@ -24,7 +25,7 @@ SYMBOLS = [
     "nsb_launch_count", "nsb_synchronize", "nsb_version", "nsb_check_errors", "nsb_query",
     "nsb_assemble_resident", "nsb_resident_jacobian", "nsb_apply_jacobian", "nsb_set_dirichlet", "nsb_adjust_jacobian",
     "nsb_adjust_vector", "nsb_set_ip_data", "nsb_set_boundary_faces", "nsb_assemble_boundary",
-    "nsb_turbulent_viscosity", "nsb_diagnostic", "nsb_fvcr_constraint_defect",
+    "nsb_turbulent_viscosity", "nsb_diagnostic", "nsb_fvcr_constraint_defect", "nsb_set_priority_nodes",
 ]
 BND_OUTFLOW, BND_INFLOW, BND_TURB_ZERO = 0, 1, 2
 TURB_OFF, TURB_SMAGORINSKY = -1, 0
@@ -102,6 +103,7 @@ def lib():
     L.nsb_assemble_boundary.argtypes = [vp, i32, vp, C.c_double, vp, vp, i32]
     L.nsb_turbulent_viscosity.argtypes = [vp, i32, C.c_double, vp, i64, vp, vp, i32]
     L.nsb_diagnostic.argtypes = [vp, i32, vp, C.c_double, vp, i32]
+    L.nsb_set_priority_nodes.argtypes = [vp, i64, vp]
     L.nsb_fvcr_constraint_defect.argtypes = [vp, vp, C.c_double, i32, i32, i64, vp, vp, i32]
     _lib = L
     return L

@@ -36,6 +36,15 @@ cudaError_t NSB_CAT(launch_elem_, NSB_ELEM)(NSB_ELEM_ARGS)
     return elem_sc<SC_LOCAL, false>(NSB_FWD);
 }
 
+// first ticket of a rows launch (0, or the first node behind the priority nodes of a phased assembly)
+static __global__ void set_ticket_kernel(unsigned long long* counter, unsigned long long v) { *counter = v; }
+static cudaError_t set_ticket(unsigned long long* counter, int64_t v, cudaStream_t st)
+{
+    if (v == 0) return cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    set_ticket_kernel<<<1, 1, 0, st>>>(counter, (unsigned long long)v);
+    return cudaGetLastError();
+}
+
 // owner-computes path: (A) flux kernel, thread per element  ->  (B) rows kernel, warp per node
 template <int STAB, bool EXACT, int CHP, int MINB>
 static cudaError_t rows_t(const KParams& k, const MeshDev& m, const double* rec, const double* u, double beta, double* val,
@@ -53,8 +62,9 @@ static cudaError_t rows_t(const KParams& k, const MeshDev& m, const double* rec,
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, WPB * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
-    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+    const int64_t nblk = std::min<int64_t>((m.n_node - m.node_begin + WPB - 1) / WPB, (int64_t)sm_count * occ);
+    if (nblk <= 0) return cudaSuccess;
+    e = set_ticket(work_counter, m.node_begin, st);
     if (e != cudaSuccess) return e;
     kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, rec, u, beta, val, def, work_counter);
     return cudaGetLastError();
@@ -64,7 +74,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
 {
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
-    if (k.what & (W_JAC_A | W_DEF_A)) {
+    if ((k.what & (W_JAC_A | W_DEF_A)) && !m.skip_flux) {
         const size_t smem_a = sizeof(double) * (NSB_CSTR(E) * BS + NIP * NSH * DIM + NIP * NSH + 24) + sizeof(int) * (NIP * 12 + 24)
                               + 16 + sizeof(double) * BS * flux_stage_stride(FluxRec<E, STAB == STAB_FLOW, EXACT>::SZ);   // staged flux records (one slot per lane)
         static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 2; }();
@@ -111,7 +121,7 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
 {
     constexpr int NF = ET<E>::DIM + 1, NIP = ET<E>::NIP, NSH = ET<E>::NSH, DIM = ET<E>::DIM, BS = 128;
     cudaError_t e;
-    if (k.what & (W_JAC_A | W_DEF_A)) {
+    if ((k.what & (W_JAC_A | W_DEF_A)) && !m.skip_flux) {
         // NSB_FLUX_LPE = lanes per element (hex: 1 or 4), NSB_FLUX_MINB = blocks/SM the registers are bounded for
         static const int LPEV = [] { const char* ev = getenv("NSB_FLUX_LPE"); return ev ? atoi(ev) : 4; }();
         static const int FMB = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 0; }();
@@ -149,9 +159,9 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_o, ko, 64, smem_o);
             if (e != cudaSuccess) return e;
             if (occ_o < 1) return cudaErrorLaunchOutOfResources;
-            const int64_t nblk_o = std::min<int64_t>((m.n_node + 1) / 2, (int64_t)sm_count * occ_o);
+            const int64_t nblk_o = std::min<int64_t>((m.n_node - m.node_begin + 1) / 2, (int64_t)sm_count * occ_o);
             if (nblk_o <= 0) return cudaSuccess;
-            e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+            e = set_ticket(work_counter, m.node_begin, st);
             if (e != cudaSuccess) return e;
             ko<<<(unsigned)nblk_o, 64, smem_o, st>>>(k, m, rec, j0, u, beta, val, def, work_counter);
             return cudaGetLastError();
@@ -167,9 +177,9 @@ static cudaError_t split_t(NSB_GATHER_ARGS, const double* j0)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, WPB * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    const int64_t nblk = std::min<int64_t>((m.n_node + WPB - 1) / WPB, (int64_t)sm_count * occ);
+    const int64_t nblk = std::min<int64_t>((m.n_node - m.node_begin + WPB - 1) / WPB, (int64_t)sm_count * occ);
     if (nblk <= 0) return cudaSuccess;
-    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+    e = set_ticket(work_counter, m.node_begin, st);
     if (e != cudaSuccess) return e;
     kb<<<(unsigned)nblk, WPB * 32, smem, st>>>(k, m, rec, j0, u, beta, val, def, work_counter);
     return cudaGetLastError();

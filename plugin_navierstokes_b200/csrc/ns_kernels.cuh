@@ -31,6 +31,10 @@ struct MeshDev {
     const double* ip_rho_scv;   // [n_elem][NSH]       m_imDensitySCV (mass / rhs parts)
     const double* ip_src_scvf;  // [n_elem][NIP][DIM]  m_imSourceSCVF (closure of the stabilisation)
     const double* ip_src_scv;   // [n_elem][NSH][DIM]  m_imSourceSCV (add_rhs_elem)
+    // phased owner-computes assembly (nsb_set_priority_nodes): the rows kernels hand out the tickets [node_begin, n_node) of the
+    // node order; skip_flux = the SCVF records of the previous phase are still valid (host-side launch logic only)
+    int64_t node_begin;
+    int32_t skip_flux;
 };
 
 enum { SC_COLORED = 1, SC_ATOMIC = 2, SC_LOCAL = 3 };

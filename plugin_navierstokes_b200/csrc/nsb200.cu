@@ -169,6 +169,7 @@ struct nsb_ctx {
     double *d_u = nullptr, *d_s0 = nullptr, *d_s1 = nullptr, *d_val = nullptr, *d_def = nullptr;
     double *d_jloc = nullptr, *d_dloc = nullptr;
     int64_t launches = 0;
+    int64_t n_prio = 0;                           // nsb_set_priority_nodes: d_node_order = [priority nodes | the rest], assembled in two phases on request
     int64_t dev_bytes = 0;                        // device memory held by the context (grid tables, caches, staging)
     double setup_seconds = 0.0;                   // host preprocessing + table upload of the last nsb_upload_mesh*
     int sm_count = 148;
@@ -276,7 +277,7 @@ static void free_mesh(nsb_ctx* c)
     c->d_phdr = nullptr; c->d_pnodes = nullptr; c->d_pelems = c->d_pconn = nullptr; c->d_pwork = nullptr; c->d_padj = nullptr;
     c->d_nodevol = nullptr; c->d_elem_fast = nullptr; c->fused_ok = false; c->n_patch = 0; c->scvf_evals = 0; c->patch_table_bytes = 0;
     c->dev_bytes = 0;
-    c->d_j0 = nullptr; c->j0_laplace = -1; c->rec_lean = false;
+    c->d_j0 = nullptr; c->j0_laplace = -1; c->rec_lean = false; c->n_prio = 0;
 
     fvcr_free(c->fvcr);
     c->d_conn = c->d_adj = c->d_color_order = c->d_esides = c->d_node_order = nullptr; c->d_coords = c->d_scvvol = c->d_rec = nullptr; c->rec_bytes = 0; c->rec_stride = 0;
@@ -613,7 +614,8 @@ static MeshDev mesh_view(const nsb_ctx* c)
     MeshDev m;
     m.n_elem = c->n_elem; m.n_node = c->n_node; m.conn = c->d_conn; m.coords = c->d_coords; m.scvvol = c->d_scvvol;
     m.brow = c->d_brow; m.emap = c->d_emap; m.adj_ptr = c->d_adj_ptr; m.adj = c->d_adj; m.max_cnt = c->max_cnt;
-    m.node_order = getenv("NSB_ZORDER") ? c->d_node_order : nullptr;   // opt-in: measured neutral on B200 (profiles/)
+    m.node_order = (c->n_prio > 0 || getenv("NSB_ZORDER")) ? c->d_node_order : nullptr;   // priority order, or the opt-in Z-curve (measured neutral on B200, profiles/)
+    m.node_begin = 0; m.skip_flux = 0;
     { const char* ev = getenv("NSB_L2HINT"); m.l2_hints = ev ? atoi(ev) : 0; }
     m.elem_fast = c->d_elem_fast;
     m.ip_visc = c->d_ip[NSB_IP_KIN_VISC_SCVF]; m.ip_rho_scvf = c->d_ip[NSB_IP_DENSITY_SCVF]; m.ip_rho_scv = c->d_ip[NSB_IP_DENSITY_SCV];
@@ -645,9 +647,14 @@ static int launch_elem(nsb_ctx* c, int sc, const KParams& k, const int32_t* list
 }
 
 static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const double* s0, const double* s1, double beta,
-                         double* val, double* def)
+                         double* val, double* def, int phase = 0)
 {
     const MeshDev m = mesh_view(c);
+    // phased assembly (nsb_set_priority_nodes): phase 1 = flux kernel + the rows of the priority nodes, phase 2 = the remaining rows
+    // from the records of phase 1. Paths without a separate rows kernel do everything in phase 1.
+    MeshDev mp = m;
+    if (phase == 1 && c->n_prio > 0) mp.n_node = c->n_prio;
+    if (phase == 2) { mp.node_begin = c->n_prio; mp.skip_flux = 1; }
     cudaError_t e;
     static const int kNIP[4] = {3, 4, 6, 12};
     const bool flow = k.stab == STAB_FLOW, exact = !k.stokes && k.exact_jac != 0.0;
@@ -702,6 +709,7 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
             CUDA_TRY(c, e);
             c->j0_laplace = k.laplace;
         }
+        if ((use_tile || use_fused) && phase == 2) return NSB_OK;
         if (use_tile) {
             TileArgs A;
             memset(&A, 0, sizeof A);
@@ -747,32 +755,33 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
             CUDA_TRY(c, e);
             return NSB_OK;
         }
-#define NSB_GO(fn) fn(k, m, c->d_rec, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter, c->d_j0)
+#define NSB_GO(fn) fn(k, mp, c->d_rec, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter, c->d_j0)
         switch (c->elem) { case 0: e = NSB_GO(launch_split_0); break; case 1: e = NSB_GO(launch_split_1); break;
                            case 2: e = NSB_GO(launch_split_2); break; default: e = NSB_GO(launch_split_3); }
 #undef NSB_GO
-        const bool flux_needed = k.what & (W_JAC_A | W_DEF_A);
+        const bool flux_needed = (k.what & (W_JAC_A | W_DEF_A)) && phase != 2;
         c->launches += flux_needed ? 2 : 1;
         CUDA_TRY(c, e);
         return NSB_OK;
     }
-#define NSB_GO(fn) fn(k, m, c->d_rec, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter)
+#define NSB_GO(fn) fn(k, mp, c->d_rec, u, s0, s1, beta, val, def, c->d_err, c->stream, c->sm_count, c->d_counter)
     switch (c->elem) { case 0: e = NSB_GO(launch_gather_0); break; case 1: e = NSB_GO(launch_gather_1); break;
                        case 2: e = NSB_GO(launch_gather_2); break; default: e = NSB_GO(launch_gather_3); }
 #undef NSB_GO
-    c->launches += (k.what & (W_JAC_A | W_DEF_A)) ? 2 : 1;
+    c->launches += ((k.what & (W_JAC_A | W_DEF_A)) && phase != 2) ? 2 : 1;
     CUDA_TRY(c, e);
     return NSB_OK;
 }
 
 static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u, const double* s0, const double* s1,
-                        double beta, double* val, double* def)
+                        double beta, double* val, double* def, int phase = 0)
 {
     const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
     const bool ip_data = c->d_ip[0] || c->d_ip[1] || c->d_ip[2] || c->d_ip[3] || c->d_ip[4];
     if (ip_data && needs_dense(k)) return set_err(c, NSB_ERR_UNSUPPORTED, "per-ip data imports with PositiveUpwind (dense ip systems) are not provided on the device path");
     if (mode == NSB_SCATTER_GATHER && (needs_dense(k) || k.pac || ip_data)) mode = NSB_SCATTER_COLORED;   // dense ip systems / PAC / per-ip data: element kernels
-    if (mode == NSB_SCATTER_GATHER) return launch_gather(c, k, u, s0, s1, beta, val, def);
+    if (mode == NSB_SCATTER_GATHER) return launch_gather(c, k, u, s0, s1, beta, val, def, phase);
+    if (phase == 2) return NSB_OK;                               // element kernels: everything happened in phase 1
     // element kernels accumulate into beta*old
     if (jac) {
         if (beta == 0.0) CUDA_TRY(c, cudaMemsetAsync(val, 0, sizeof(double) * c->nnz, c->stream));
@@ -795,8 +804,9 @@ static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u,
 }
 
 // FVCR: element kernel with coloured (deterministic) or atomic scatter; the owner-computes path is FV1-only
-static int assemble_fvcr(nsb_ctx* c, const KParams& k, int mode, const double* u, double beta, double* val, double* def)
+static int assemble_fvcr(nsb_ctx* c, const KParams& k, int mode, const double* u, double beta, double* val, double* def, int phase = 0)
 {
+    if (phase == 2) return NSB_OK;
     const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
     if (mode == NSB_SCATTER_GATHER) mode = NSB_SCATTER_COLORED;
     if (jac) {
@@ -845,6 +855,9 @@ extern "C" int nsb_assemble(nsb_ctx* c, int what, int mode, const double* u, con
     if (!c) return NSB_ERR_INVALID;
     if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: no grid uploaded");
     if (!u) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: u == NULL");
+    const int phase = (what & NSB_PHASE_PRIORITY) ? 1 : (what & NSB_PHASE_REST) ? 2 : 0;
+    what &= ~(NSB_PHASE_PRIORITY | NSB_PHASE_REST);
+    if (phase && location != NSB_DEVICE) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: the phased assembly works on device pointers");
     const bool jac = what & (NSB_JAC_A | NSB_JAC_M), dfc = what & (NSB_DEF_A | NSB_DEF_M | NSB_RHS);
     if ((jac && !values) || (dfc && !defect)) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: output pointer missing for requested part");
     if (!jac && !dfc) return NSB_OK;
@@ -869,8 +882,8 @@ extern "C" int nsb_assemble(nsb_ctx* c, int what, int mode, const double* u, con
         if (dfc) { if ((rc = ensure(c, &c->d_def, c->n_dof))) return rc; dd = c->d_def;
                    if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(dd, defect, nb, cudaMemcpyHostToDevice, c->stream)); }
     }
-    if (c->disc == NSB_DISC_FVCR) rc = assemble_fvcr(c, k, mode, du, beta, dv, dd);
-    else rc = assemble_fv1(c, k, mode, du, ds0, ds1, beta, dv, dd);
+    if (c->disc == NSB_DISC_FVCR) rc = assemble_fvcr(c, k, mode, du, beta, dv, dd, phase);
+    else rc = assemble_fv1(c, k, mode, du, ds0, ds1, beta, dv, dd, phase);
     if (rc) return rc;
     if (location == NSB_HOST) {
         if (jac) CUDA_TRY(c, cudaMemcpyAsync(values, dv, sizeof(double) * c->nnz, cudaMemcpyDeviceToHost, c->stream));
@@ -1336,6 +1349,29 @@ extern "C" int nsb_fvcr_constraint_defect(nsb_ctx* c, const double* u, double s_
         CUDA_TRY(c, cudaMemcpyAsync(defect, dd, nb, cudaMemcpyDeviceToHost, c->stream));
         return check_device_error(c);
     }
+    return NSB_OK;
+}
+
+// Nodes whose rows are assembled FIRST (e.g. the interface nodes of a partition): the owner-computes rows kernels walk the node
+// order [priority nodes | the rest]; nsb_assemble(what | NSB_PHASE_PRIORITY) stops behind the priority rows,
+// nsb_assemble(what | NSB_PHASE_REST) finishes the pass.
+extern "C" int nsb_set_priority_nodes(nsb_ctx* c, int64_t n, const int64_t* nodes)
+{
+    if (!c || n < 0 || (n > 0 && !nodes)) return NSB_ERR_INVALID;
+    if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_set_priority_nodes: no grid uploaded");
+    if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_priority_nodes: FV1 only");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    std::vector<uint8_t> flag((size_t)c->n_node, 0);
+    std::vector<int32_t> order; order.reserve((size_t)c->n_node);
+    for (int64_t i = 0; i < n; i++) {
+        if (nodes[i] < 0 || nodes[i] >= c->n_node) return set_err(c, NSB_ERR_INVALID, "nsb_set_priority_nodes: node %lld out of range", (long long)nodes[i]);
+        if (!flag[nodes[i]]) { flag[nodes[i]] = 1; order.push_back((int32_t)nodes[i]); }
+    }
+    c->n_prio = (int64_t)order.size();
+    for (int64_t a = 0; a < c->n_node; a++) if (!flag[a]) order.push_back((int32_t)a);
+    if (!c->d_node_order) CUDA_TRY(c, dev_malloc(c, &c->d_node_order, sizeof(int32_t) * (size_t)c->n_node));
+    CUDA_TRY(c, cudaMemcpy(c->d_node_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice));
     return NSB_OK;
 }
 

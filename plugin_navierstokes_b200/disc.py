@@ -440,6 +440,12 @@ class _DeviceDisc:
         self.set_ip_data("src_scv", ev(fns["source"], xv, dim) if "source" in fns else None)
         self._ip_dirty = False
 
+    def set_priority_nodes(self, nodes):
+        """grid nodes whose rows are assembled first (nsb_set_priority_nodes); assemble(what | capi.PHASE_PRIORITY, ...) then
+        assemble(what | capi.PHASE_REST, ...) split the pass behind them (device tensors only). Empty list clears."""
+        nodes = np.ascontiguousarray(nodes, dtype=np.int64).reshape(-1)
+        self._check(capi.lib().nsb_set_priority_nodes(self._context(), nodes.size, self._ptr(nodes) if nodes.size else None))
+
     def set_dirichlet(self, dofs):
         dofs = np.ascontiguousarray(dofs, dtype=np.int64).reshape(-1)
         self._check(capi.lib().nsb_set_dirichlet(self._context(), dofs.size, dofs.ctypes.data))

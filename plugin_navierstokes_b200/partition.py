@@ -403,11 +403,18 @@ class InterfaceExchange:
         else:
             dst.index_add_(0, idx_t, buf)
 
-    def sum_to_owner(self, vals, dfc, zero_slaves=False):
-        """vals / dfc: the rank's additive CSR values / defect (torch tensors). After the call the owner's entries of
-        shared rows hold the sum over all ranks (for the columns the pair shares); with zero_slaves the slave copies
-        are cleared (PST_UNIQUE), otherwise they keep their partial values."""
-        dist, t = self.dist, self.torch
+    def enable_overlap(self):
+        """interface-first assembly: the shared nodes become the priority nodes of the disc, so that
+        assemble(what | PHASE_PRIORITY) -> start_sum_to_owner -> assemble(what | PHASE_REST) -> finish_sum_to_owner
+        hides the exchange behind the assembly of the interior rows"""
+        nodes = np.unique(np.concatenate([loc for loc, _ in self.shared.values()])) if self.shared else np.zeros(0, dtype=np.int64)
+        self.disc.set_priority_nodes(nodes)
+        return nodes
+
+    def start_sum_to_owner(self, vals, dfc):
+        """packs the slave rows and posts the sends / receives (NCCL orders them behind the pack kernels on the current stream
+        and runs them on its own stream); returns the pending work handles for finish_sum_to_owner"""
+        dist = self.dist
         ops = []
         for p in self.plans:
             nm = p["midx"].size
@@ -419,9 +426,11 @@ class InterfaceExchange:
                 ops.append(dist.P2POp(dist.isend, p["buf"], p["peer"]))
             else:
                 ops.append(dist.P2POp(dist.irecv, p["buf"], p["peer"]))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def finish_sum_to_owner(self, works, vals, dfc, zero_slaves=False):
+        for w in works:
+            w.wait()                                                     # the current stream waits for the transfers
         for p in self.plans:
             nm = p["midx"].size
             if p["role"] == "recv":
@@ -434,6 +443,12 @@ class InterfaceExchange:
                     vals[p["midx_t"]] = 0.0
                 if dfc is not None:
                     dfc[p["didx_t"]] = 0.0
+
+    def sum_to_owner(self, vals, dfc, zero_slaves=False):
+        """vals / dfc: the rank's additive CSR values / defect (torch tensors). After the call the owner's entries of
+        shared rows hold the sum over all ranks (for the columns the pair shares); with zero_slaves the slave copies
+        are cleared (PST_UNIQUE), otherwise they keep their partial values."""
+        self.finish_sum_to_owner(self.start_sum_to_owner(vals, dfc), vals, dfc, zero_slaves)
 
     def copy_from_owner(self, vec):
         """owner -> copies over the same dof lists in the reverse direction (additive/unique -> consistent): after the

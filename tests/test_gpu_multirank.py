@@ -41,6 +41,16 @@ def _worker(rank, world, port, q):
         vals, dfc = disc.assemble(capi.JAC_A | capi.DEF_A, ud)
         ex = partition.InterfaceExchange(disc, dict(l2g=l2g, boundary=None), torch.device("cuda", rank))
         ex.sum_to_owner(vals, dfc)
+        # overlapped variant: interface rows first, exchange behind the interior rows -- bitwise the same sums
+        ex.enable_overlap()
+        what = capi.JAC_A | capi.DEF_A
+        v2, d2 = torch.empty_like(vals), torch.empty_like(dfc)
+        disc.assemble(what | capi.PHASE_PRIORITY, ud, values=v2, defect=d2)
+        works = ex.start_sum_to_owner(v2, d2)
+        disc.assemble(what | capi.PHASE_REST, ud, values=v2, defect=d2)
+        ex.finish_sum_to_owner(works, v2, d2)
+        torch.cuda.synchronize()
+        assert torch.equal(v2, vals) and torch.equal(d2, dfc)
         cons = dfc.clone()
         ex.copy_from_owner(cons)                                 # unique -> consistent over NCCL
         torch.cuda.synchronize()
