@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--ref-n", type=int, default=96, help="cells per direction of the CPU sample (96^3 = 0.88 M elements, ~2 s per sweep pair on 16 cores)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-nccl-priority", action="store_true", help="N > 1: default-priority NCCL stream")
+    ap.add_argument("--overlap", action="store_true", help="N > 1: force the interface-first split (default from 4 ranks on)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange after the whole assembly instead of behind the interior rows")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e-full", action="store_true", help="skip the full-matrix D2H variant of the end-to-end leg")
@@ -225,7 +227,15 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pgo = None
+        if not args.no_nccl_priority:
+            # the NCCL stream gets a high priority: its few CTAs are scheduled ahead of the pending blocks of the interior rows
+            # kernel, so the transfers really run behind the assembly (the persistent rows kernel otherwise fills every SM first)
+            try:
+                pgo = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            except Exception:
+                pgo = None
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=pgo)
     dev = torch.device("cuda", local)
 
     prob = build_problem(args.n, rank, world)
@@ -251,7 +261,9 @@ def main():
     if world > 1:
         from plugin_navierstokes_b200 import partition
         exch = partition.InterfaceExchange(disc, prob["iface"], dev)
-        overlap = not args.no_overlap
+        # measured on 8 x B200 (profiles/r2_bench_8gpu*.json): 20.57 ms overlapped vs 21.00 ms; at 2 GPUs (one face per rank) the extra
+        # launch costs more than the hidden transfer (20.41 vs 20.26 ms), so the split is used from 4 ranks on
+        overlap = (not args.no_overlap) and (world >= 4 or args.overlap)
         if overlap:
             exch.enable_overlap()          # interface rows first; the exchange then runs behind the interior rows
 
