@@ -239,7 +239,9 @@ enum {
     NSB_Q_FUSED = 2,            /* 1 when the fused patch kernel serves NSB_SCATTER_GATHER on this grid             */
     NSB_Q_PATCHES = 3,          /* number of node patches                                                           */
     NSB_Q_SCVF_EVALS = 4,       /* SCVF evaluations per pass of the fused kernel (>= n_elem * nip: patch overlap)   */
-    NSB_Q_PATCH_TABLE_BYTES = 5 /* bytes of the per-patch tables read by every pass                                 */
+    NSB_Q_PATCH_TABLE_BYTES = 5,/* bytes of the per-patch tables read by every pass                                 */
+    NSB_Q_LAST_SCATTER = 6      /* NSB_SCATTER_* mode that actually served the last nsb_assemble*: GATHER requests are served by the
+                                   coloured element kernels for FVCR, PositiveUpwind (dense ip systems), PAC and per-ip data      */
 };
 int  nsb_query(const nsb_ctx *ctx, int what, double *out);
 int64_t nsb_launch_count(const nsb_ctx *ctx);          /* kernels launched by this context so far       */

@@ -101,8 +101,8 @@ template <int E> NSB_DEV bool cr_upwind_ip(int type, const CRWS<E>& ws, const do
     return true;
 }
 
-template <int E, int SC>
-__global__ void __launch_bounds__(128) fvcr_elem_kernel(KParams p, FvcrDev m, const int32_t* __restrict__ elem_list,
+template <int E, int SC, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) fvcr_elem_kernel(KParams p, FvcrDev m, const int32_t* __restrict__ elem_list,
                                                         int64_t n_list, const double* __restrict__ u,
                                                         double* __restrict__ val, double* __restrict__ def,
                                                         int* __restrict__ errflag)

@@ -169,6 +169,7 @@ struct nsb_ctx {
     double *d_u = nullptr, *d_s0 = nullptr, *d_s1 = nullptr, *d_val = nullptr, *d_def = nullptr;
     double *d_jloc = nullptr, *d_dloc = nullptr;
     int64_t launches = 0;
+    int last_scatter = -1;                        // scatter mode that served the last assembly (NSB_Q_LAST_SCATTER)
     int64_t n_prio = 0;                           // nsb_set_priority_nodes: d_node_order = [priority nodes | the rest], assembled in two phases on request
     int64_t dev_bytes = 0;                        // device memory held by the context (grid tables, caches, staging)
     double setup_seconds = 0.0;                   // host preprocessing + table upload of the last nsb_upload_mesh*
@@ -333,6 +334,7 @@ extern "C" int nsb_query(const nsb_ctx* c, int what, double* out)
         case NSB_Q_PATCHES: *out = (double)c->n_patch; break;
         case NSB_Q_SCVF_EVALS: *out = (double)c->scvf_evals; break;
         case NSB_Q_PATCH_TABLE_BYTES: *out = (double)c->patch_table_bytes; break;
+        case NSB_Q_LAST_SCATTER: *out = (double)c->last_scatter; break;
         default: return NSB_ERR_INVALID;
     }
     return NSB_OK;
@@ -780,6 +782,7 @@ static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u,
     const bool ip_data = c->d_ip[0] || c->d_ip[1] || c->d_ip[2] || c->d_ip[3] || c->d_ip[4];
     if (ip_data && needs_dense(k)) return set_err(c, NSB_ERR_UNSUPPORTED, "per-ip data imports with PositiveUpwind (dense ip systems) are not provided on the device path");
     if (mode == NSB_SCATTER_GATHER && (needs_dense(k) || k.pac || ip_data)) mode = NSB_SCATTER_COLORED;   // dense ip systems / PAC / per-ip data: element kernels
+    c->last_scatter = mode;
     if (mode == NSB_SCATTER_GATHER) return launch_gather(c, k, u, s0, s1, beta, val, def, phase);
     if (phase == 2) return NSB_OK;                               // element kernels: everything happened in phase 1
     // element kernels accumulate into beta*old
@@ -809,6 +812,7 @@ static int assemble_fvcr(nsb_ctx* c, const KParams& k, int mode, const double* u
     if (phase == 2) return NSB_OK;
     const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
     if (mode == NSB_SCATTER_GATHER) mode = NSB_SCATTER_COLORED;
+    c->last_scatter = mode;
     if (jac) {
         if (beta == 0.0) CUDA_TRY(c, cudaMemsetAsync(val, 0, sizeof(double) * c->nnz, c->stream));
         else if (beta != 1.0) { scale_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->nnz, beta, val); c->launches++; }

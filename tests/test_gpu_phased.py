@@ -57,3 +57,29 @@ def test_two_phases_equal_one_pass(elem, n, kw, mode):
     with pytest.raises(pkg.UGError):
         disc.assemble(JD | capi.PHASE_PRIORITY, u.reshape(-1))                           # host vectors: no phases
     disc.close()
+
+
+def test_served_scatter_mode_is_reported():
+    """a GATHER request that the owner-computes path cannot serve is routed to the coloured element kernels -- and says so"""
+    import torch
+    from plugin_navierstokes_b200 import meshgen
+    coords, conn, u = parity.make_case("hex", 4, seed=1)
+    disc = pkg.NavierStokesFV1("u,v,w,p", "Inner")
+    parity.configure(disc, upwind="lps", stab="fields")
+    disc.set_grid("hex", conn, coords)
+    disc.assemble(JD, u.reshape(-1), scatter_mode=capi.SCATTER_GATHER)
+    assert disc.query(capi.Q_LAST_SCATTER) == capi.SCATTER_GATHER
+    disc.assemble(JD, u.reshape(-1), scatter_mode=capi.SCATTER_ATOMIC)
+    assert disc.query(capi.Q_LAST_SCATTER) == capi.SCATTER_ATOMIC
+    parity.configure(disc, upwind="positive", stab="flow")
+    disc.assemble(JD, u.reshape(-1), scatter_mode=capi.SCATTER_GATHER)
+    assert disc.query(capi.Q_LAST_SCATTER) == capi.SCATTER_COLORED                  # dense ip systems
+    disc.close()
+    coords, conn = meshgen.make_mesh("tet", 3, jitter=0.1, seed=1)
+    es, n_side = meshgen.element_sides("tet", conn)
+    d2 = pkg.NavierStokesFVCR("u,v,w,p", "Inner")
+    d2.set_kinematic_viscosity(1e-2); d2.set_upwind("full")
+    d2.set_grid("tet", conn, coords, es, n_side)
+    d2.assemble(JD, np.zeros(d2.num_dofs), scatter_mode=capi.SCATTER_GATHER)
+    assert d2.query(capi.Q_LAST_SCATTER) == capi.SCATTER_COLORED
+    d2.close()
