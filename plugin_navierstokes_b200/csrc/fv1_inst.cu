@@ -77,7 +77,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     if ((k.what & (W_JAC_A | W_DEF_A)) && !m.skip_flux) {
         const size_t smem_a = sizeof(double) * (NSB_CSTR(E) * BS + NIP * NSH * DIM + NIP * NSH + 24) + sizeof(int) * (NIP * 12 + 24)
                               + 16 + sizeof(double) * BS * flux_stage_stride(FluxRec<E, STAB == STAB_FLOW, EXACT>::SZ);   // staged flux records (one slot per lane)
-        static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : 2; }();
+        static const int minb = [] { const char* ev = getenv("NSB_FLUX_MINB"); return ev ? atoi(ev) : (DIM == 2 ? 4 : 2); }();   // 2-D: 4 blocks/SM (config 1: 6.85 -> 6.71 ms)
         auto ka = minb == 2 ? fv1_flux_kernel<E, STAB, EXACT, BS, 2> : minb == 4 ? fv1_flux_kernel<E, STAB, EXACT, BS, 4> : fv1_flux_kernel<E, STAB, EXACT, BS, 3>;
         e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
         if (e != cudaSuccess) return e;
@@ -88,7 +88,7 @@ template <int STAB, bool EXACT> static cudaError_t gather_t(NSB_GATHER_ARGS)
     // experiment knobs (hex only): NSB_ROWS_CH = adjacent elements staged per round, NSB_ROWS_MINB = blocks/SM the
     // register allocation is bounded for
     // measured best on B200 for hex (profiles/r1_history.md): 4 elements per round, 96 registers, 2 warps per block
-    static const int WPB = [] { const char* ev = getenv("NSB_ROWS_WPB"); const int v = ev ? atoi(ev) : (E == 3 ? 2 : 3); return (v >= 1 && v <= 3) ? v : 3; }();
+    static const int WPB = [] { const char* ev = getenv("NSB_ROWS_WPB"); const int v = ev ? atoi(ev) : 2; return (v >= 1 && v <= 3) ? v : 2; }();   // 2 warps per block (config 1: 7.14 -> 6.85 ms)
     static const int CHV = [] { const char* ev = getenv("NSB_ROWS_CH"); return ev ? atoi(ev) : 4; }();
     static const int MINBV = [] { const char* ev = getenv("NSB_ROWS_MINB"); return ev ? atoi(ev) : 6; }();
     if constexpr (E == 3) {

@@ -61,20 +61,37 @@ def fv1(name, elem, coords, conn, u, upwind, stab, what, exact=0.0, td=None, vis
 def main():
     sc = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
     JD = capi.JAC_A | capi.DEF_A
+    sel = set(int(x) for x in os.environ.get("NSB_CONFIGS", "1,2,3,4,5").split(","))   # subset of the configurations (knob sweeps)
     # config 1: 2-D cavity, quads, FullUpwind + FIELDS/RAW, exact Jacobian
     n = int(2048 * sc)
-    coords, conn = meshgen.quad_grid(n, n)
-    fv1("config1 quad %d^2 FULL+FIELDS exact_jacobian=1" % n, "quad", coords, conn, meshgen.state_cavity2d(coords, seed=1), "full", "fields", JD, exact=1.0)
+    if 1 in sel:
+      coords, conn = meshgen.quad_grid(n, n)
+      fv1("config1 quad %d^2 FULL+FIELDS exact_jacobian=1" % n, "quad", coords, conn, meshgen.state_cavity2d(coords, seed=1), "full", "fields", JD, exact=1.0)
     # config 2: channel with cylinder, triangles, LPS + FIELDS (headline upwind of the config)
     nx, ny = int(2816 * sc), int(524 * sc)
-    coords, conn = meshgen.tri_grid(nx, ny, lo=(0, 0), hi=(2.2, 0.41), jitter=0.2, seed=2, hole=(0.2, 0.2, 0.05))
-    fv1("config2 tri channel+cylinder %dx%d LPS+FIELDS" % (nx, ny), "tri", coords, conn, meshgen.state_channel2d(coords, seed=2), "lps", "fields", JD, visc=1e-3)
+    if 2 in sel:
+      coords, conn = meshgen.tri_grid(nx, ny, lo=(0, 0), hi=(2.2, 0.41), jitter=0.2, seed=2, hole=(0.2, 0.2, 0.05))
+      fv1("config2 tri channel+cylinder %dx%d LPS+FIELDS" % (nx, ny), "tri", coords, conn, meshgen.state_channel2d(coords, seed=2), "lps", "fields", JD, visc=1e-3)
     # config 3 (reduced size; contract size in bench.py): hex, LPS + FIELDS
     n = int(128 * sc)
-    coords, conn = meshgen.hex_grid(n, n, n)
-    fv1("config3 hex %d^3 LPS+FIELDS" % n, "hex", coords, conn, meshgen.state_vortex3d(coords, seed=3), "lps", "fields", JD)
+    if 3 in sel:
+      coords, conn = meshgen.hex_grid(n, n, n)
+      fv1("config3 hex %d^3 LPS+FIELDS" % n, "hex", coords, conn, meshgen.state_vortex3d(coords, seed=3), "lps", "fields", JD)
     # config 4: tets (Kuhn) + jitter, FVCR, Full upwind, time-dependent
     n = int(64 * sc)
+    if 4 in sel:
+      fvcr4(n)
+    # config 5: Taylor-Green, hex, FLOW + PositiveUpwind (dense ip systems), instationary parts
+    n = int(96 * sc)
+    if 5 in sel:
+      coords, conn = meshgen.hex_grid(n, n, n, lo=(0, 0, 0), hi=(2 * np.pi,) * 3)
+      u = meshgen.state_taylor_green(coords, t=0.0)
+      uo = meshgen.state_taylor_green(coords, t=-1e-2)
+      fv1("config5 hex %d^3 FLOW+POSITIVE instationary (A + M defect)" % n, "hex", coords, conn, u, "positive", "flow", JD | capi.DEF_M, td=(uo, 1e-2), visc=1.0 / 1600)
+
+
+def fvcr4(n):
+    JD = capi.JAC_A | capi.DEF_A
     coords, conn = meshgen.tet_grid(4 * n, n, n, lo=(0, 0, 0), hi=(2.5, 0.41, 0.41), jitter=0.2, seed=4)
     es, n_side = meshgen.element_sides("tet", conn)
     rng = np.random.default_rng(4)
@@ -88,12 +105,6 @@ def main():
     ms = timeit(disc, JD | capi.DEF_M, ud, None)
     report("config4 tet %dx%dx%d x6 FVCR FULL (A + M defect)" % (4 * n, n, n), conn.shape[0], 4, 3, coords.shape[0], disc.num_dofs, disc.nnz, 1, ms, (disc.launch_count - l0) // 8)
     disc.close()
-    # config 5: Taylor-Green, hex, FLOW + PositiveUpwind (dense ip systems), instationary parts
-    n = int(96 * sc)
-    coords, conn = meshgen.hex_grid(n, n, n, lo=(0, 0, 0), hi=(2 * np.pi,) * 3)
-    u = meshgen.state_taylor_green(coords, t=0.0)
-    uo = meshgen.state_taylor_green(coords, t=-1e-2)
-    fv1("config5 hex %d^3 FLOW+POSITIVE instationary (A + M defect)" % n, "hex", coords, conn, u, "positive", "flow", JD | capi.DEF_M, td=(uo, 1e-2), visc=1.0 / 1600)
 
 
 if __name__ == "__main__":
