@@ -49,7 +49,11 @@ enum {
     NSB_SCATTER_ATOMIC = 2     /* element kernel, red.global.add.f64 */
 };
 
-enum { NSB_HOST = 0, NSB_DEVICE = 1 };   /* where u / values / defect pointers live */
+enum { NSB_HOST = 0, NSB_DEVICE = 1,     /* where u / values / defect pointers live */
+       NSB_HOST_ASYNC = 2 };             /* nsb_assemble_resident / nsb_apply_jacobian only: (pinned) host buffers, the copies are queued on the
+                                            context's own H2D / D2H streams and the call returns at once, so that x goes up while the assembly
+                                            runs and the defect comes back while the product runs. nsb_synchronize completes the calls (the
+                                            buffers must stay alive and untouched until then), nsb_check_errors reports element-level failures */
 
 /* State of NavierStokesFV1 / NavierStokesFVCR and their bases that the element routines read.
  * Defaults (nsb_params_default) mirror navier_stokes_base.cpp:53-67,

@@ -14,7 +14,7 @@ DISC_FV1, DISC_FVCR = 0, 1
 JAC_A, DEF_A, JAC_M, DEF_M, RHS = 1, 2, 4, 8, 16
 PHASE_PRIORITY, PHASE_REST = 256, 512
 SCATTER_GATHER, SCATTER_COLORED, SCATTER_ATOMIC = 0, 1, 2
-HOST, DEVICE = 0, 1
+HOST, DEVICE, HOST_ASYNC = 0, 1, 2
 Q_DEVICE_BYTES, Q_SETUP_SECONDS, Q_FUSED, Q_PATCHES, Q_SCVF_EVALS, Q_PATCH_TABLE_BYTES, Q_LAST_SCATTER = range(7)
 OK, ERR_INVALID, ERR_SETUP, ERR_CUDA, ERR_GEOMETRY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 

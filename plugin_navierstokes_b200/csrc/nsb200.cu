@@ -187,6 +187,9 @@ struct nsb_ctx {
     int32_t* d_bcol = nullptr; int64_t* d_rowptr = nullptr;   // block columns (FV1) / scalar pattern (FVCR), uploaded on first use
     double* d_jres = nullptr;                                  // resident CSR values (nsb_assemble_resident)
     double *d_xin = nullptr, *d_yout = nullptr;                // staging of nsb_apply_jacobian(NSB_HOST)
+    // NSB_HOST_ASYNC: copy streams + events that order the staging buffers between the context stream and the copies
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_x_in = nullptr, ev_spmv = nullptr, ev_def_out = nullptr, ev_y_out = nullptr;
     int64_t* d_dir = nullptr; int64_t n_dir = 0; double* d_dirval = nullptr;
     // boundary faces of the boundary discs (ns_bnd.cuh), per kind: BFs sorted by grid node
     struct BndSet { int64_t n_bnode = 0, n_bf = 0; int32_t* d_bnode = nullptr; int64_t* d_bptr = nullptr; nsb::BndFace* d_bf = nullptr; double* d_data = nullptr; };
@@ -294,6 +297,8 @@ extern "C" void nsb_destroy(nsb_ctx* c)
     cudaStreamSynchronize(c->stream);
     free_mesh(c);
     cudaFree(c->d_err); cudaFree(c->d_counter);
+    if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_x_in);
+                    cudaEventDestroy(c->ev_spmv); cudaEventDestroy(c->ev_def_out); cudaEventDestroy(c->ev_y_out); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -344,6 +349,7 @@ extern "C" int nsb_synchronize(nsb_ctx* c)
     if (!c) return NSB_ERR_INVALID;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->s_h2d) { CUDA_TRY(c, cudaStreamSynchronize(c->s_h2d)); CUDA_TRY(c, cudaStreamSynchronize(c->s_d2h)); }   // NSB_HOST_ASYNC copies
     return NSB_OK;
 }
 
@@ -861,6 +867,7 @@ extern "C" int nsb_assemble(nsb_ctx* c, int what, int mode, const double* u, con
     if (!u) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: u == NULL");
     const int phase = (what & NSB_PHASE_PRIORITY) ? 1 : (what & NSB_PHASE_REST) ? 2 : 0;
     what &= ~(NSB_PHASE_PRIORITY | NSB_PHASE_REST);
+    if (location != NSB_HOST && location != NSB_DEVICE) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: location must be NSB_HOST or NSB_DEVICE");
     if (phase && location != NSB_DEVICE) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: the phased assembly works on device pointers");
     const bool jac = what & (NSB_JAC_A | NSB_JAC_M), dfc = what & (NSB_DEF_A | NSB_DEF_M | NSB_RHS);
     if ((jac && !values) || (dfc && !defect)) return set_err(c, NSB_ERR_INVALID, "nsb_assemble: output pointer missing for requested part");
@@ -955,6 +962,16 @@ static int ensure_pattern(nsb_ctx* c)
     return NSB_OK;
 }
 
+// NSB_HOST_ASYNC: an H2D and a D2H copy stream beside the context stream. An event that was never recorded counts as complete.
+static int ensure_async(nsb_ctx* c)
+{
+    if (c->s_h2d) return NSB_OK;
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&c->ev_main, &c->ev_x_in, &c->ev_spmv, &c->ev_def_out, &c->ev_y_out}) CUDA_TRY(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return NSB_OK;
+}
+
 extern "C" int nsb_assemble_resident(nsb_ctx* c, int what, int mode, const double* u, const nsb_time_series* ts, double sa, double sm,
                                      double beta, double* defect, int location)
 {
@@ -970,6 +987,9 @@ extern "C" int nsb_assemble_resident(nsb_ctx* c, int what, int mode, const doubl
         CUDA_TRY(c, cudaMemsetAsync(c->d_jres, 0, sizeof(double) * c->nnz, c->stream));
     }
     if (location == NSB_DEVICE) return nsb_assemble(c, what, mode, u, ts, sa, sm, beta, c->d_jres, defect, NSB_DEVICE);
+    const bool async = location == NSB_HOST_ASYNC;
+    if (async) { if ((rc = ensure_async(c))) return rc;
+                 CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_def_out, 0)); }     // the previous defect has left the staging buffer
     // host vectors, device-resident matrix: u (and the time series) in, defect out
     KParams k;
     if ((rc = resolve_params(c, k, what, ts, sa, sm))) return rc;
@@ -987,6 +1007,15 @@ extern "C" int nsb_assemble_resident(nsb_ctx* c, int what, int mode, const doubl
     if (dfc) { if ((rc = ensure(c, &c->d_def, c->n_dof))) return rc;
                if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(c->d_def, defect, nb, cudaMemcpyHostToDevice, c->stream)); }
     if ((rc = nsb_assemble(c, what, mode, c->d_u, pts, sa, sm, beta, c->d_jres, c->d_def, NSB_DEVICE))) return rc;
+    if (async) {                                                 // defect leaves on the D2H stream behind whatever the caller queues next
+        if (dfc) {
+            CUDA_TRY(c, cudaEventRecord(c->ev_main, c->stream));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->s_d2h, c->ev_main, 0));
+            CUDA_TRY(c, cudaMemcpyAsync(defect, c->d_def, nb, cudaMemcpyDeviceToHost, c->s_d2h));
+            CUDA_TRY(c, cudaEventRecord(c->ev_def_out, c->s_d2h));
+        }
+        return NSB_OK;                                           // nsb_synchronize + nsb_check_errors complete the call
+    }
     if (dfc) CUDA_TRY(c, cudaMemcpyAsync(defect, c->d_def, nb, cudaMemcpyDeviceToHost, c->stream));
     return check_device_error(c);
 }
@@ -1024,6 +1053,24 @@ extern "C" int nsb_apply_jacobian(nsb_ctx* c, const double* values, double alpha
     int rc;
     const size_t nb = sizeof(double) * c->n_dof;
     if ((rc = ensure(c, &c->d_xin, c->n_dof)) || (rc = ensure(c, &c->d_yout, c->n_dof))) return rc;
+    if (location == NSB_HOST_ASYNC) {
+        // x goes up on the H2D stream while the context stream is still busy (e.g. with the assembly queued before this call);
+        // J x leaves on the D2H stream. The staging buffers are handed over through events; nsb_synchronize completes the call.
+        if ((rc = ensure_async(c))) return rc;
+        CUDA_TRY(c, cudaStreamWaitEvent(c->s_h2d, c->ev_spmv, 0));               // the previous product has read x
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_xin, x, nb, cudaMemcpyHostToDevice, c->s_h2d));
+        if (beta != 0.0) { CUDA_TRY(c, cudaStreamWaitEvent(c->s_h2d, c->ev_y_out, 0));
+                           CUDA_TRY(c, cudaMemcpyAsync(c->d_yout, y, nb, cudaMemcpyHostToDevice, c->s_h2d)); }
+        CUDA_TRY(c, cudaEventRecord(c->ev_x_in, c->s_h2d));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_x_in, 0));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_y_out, 0));             // the previous result has left the staging buffer
+        if ((rc = spmv_launch(c, val, alpha, c->d_xin, beta, c->d_yout))) return rc;
+        CUDA_TRY(c, cudaEventRecord(c->ev_spmv, c->stream));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->s_d2h, c->ev_spmv, 0));
+        CUDA_TRY(c, cudaMemcpyAsync(y, c->d_yout, nb, cudaMemcpyDeviceToHost, c->s_d2h));
+        CUDA_TRY(c, cudaEventRecord(c->ev_y_out, c->s_d2h));
+        return NSB_OK;
+    }
     CUDA_TRY(c, cudaMemcpyAsync(c->d_xin, x, nb, cudaMemcpyHostToDevice, c->stream));
     if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(c->d_yout, y, nb, cudaMemcpyHostToDevice, c->stream));
     if ((rc = spmv_launch(c, val, alpha, c->d_xin, beta, c->d_yout))) return rc;

@@ -268,6 +268,7 @@ class _DeviceDisc:
 
     def synchronize(self):
         self._check(capi.lib().nsb_synchronize(self._ctx))
+        self._async_keep = []                                   # buffers of asynchronous calls are complete now
 
     def check_errors(self):
         self._check(capi.lib().nsb_check_errors(self._ctx))
@@ -344,9 +345,12 @@ class _DeviceDisc:
         return values, defect
 
     # ---- GPU-resident Jacobian (nsb_assemble_resident / nsb_apply_jacobian) and Dirichlet post-pass ----
-    def assemble_resident(self, what, u, defect=None, time_series=None, scale_a=1.0, scale_m=1.0, beta=0.0, scatter_mode=None):
+    def assemble_resident(self, what, u, defect=None, time_series=None, scale_a=1.0, scale_m=1.0, beta=0.0, scatter_mode=None,
+                          asynchronous=False):
         """like assemble(), but the CSR values stay in a context-owned device buffer: only u (and the time series) go to the
-        device and the defect comes back. Returns the defect."""
+        device and the defect comes back. Returns the defect.
+        asynchronous=True (host arrays, NSB_HOST_ASYNC): the call returns once the work is queued; the copies run on the context's
+        copy streams. Pass C-contiguous float64 arrays (pinned for real overlap); they are complete after synchronize()."""
         L = capi.lib()
         p = self._params()
         self._check(L.nsb_set_params(self._context(), C.byref(p)))
@@ -358,6 +362,13 @@ class _DeviceDisc:
             if dfc and defect is None:
                 defect = torch.zeros(self.num_dofs, dtype=torch.float64, device=u.device)
         else:
+            if asynchronous:
+                for a in (u, defect) + (tuple(time_series[:2]) if time_series is not None else ()):
+                    if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
+                        raise UGError("assemble_resident(asynchronous=True): pass C-contiguous float64 numpy arrays")
+                if dfc and defect is None:
+                    raise UGError("assemble_resident(asynchronous=True): pass the defect array")
+                self._async_keep = getattr(self, "_async_keep", []) + [u, defect]
             u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
             if dfc and defect is None:
                 defect = np.zeros(self.num_dofs)
@@ -373,7 +384,9 @@ class _DeviceDisc:
         mode = self.scatter_mode if scatter_mode is None else scatter_mode
         rc = L.nsb_assemble_resident(self._ctx, what, mode, self._ptr(u), C.byref(ts) if ts is not None else None,
                                      float(scale_a), float(scale_m), float(beta), self._ptr(defect) if dfc else None,
-                                     capi.DEVICE if on_dev else capi.HOST)
+                                     capi.DEVICE if on_dev else (capi.HOST_ASYNC if asynchronous else capi.HOST))
+        if asynchronous and not on_dev:
+            self._async_keep += keep
         del keep
         self._check(rc)
         return defect
@@ -384,8 +397,10 @@ class _DeviceDisc:
         self._check(capi.lib().nsb_resident_jacobian(self._ctx, C.byref(out)))
         return out.value
 
-    def apply_jacobian(self, x, y=None, alpha=1.0, beta=0.0, values=None):
-        """y = alpha * J x + beta * y with the resident Jacobian (values=None) or a CUDA tensor of CSR values"""
+    def apply_jacobian(self, x, y=None, alpha=1.0, beta=0.0, values=None, asynchronous=False):
+        """y = alpha * J x + beta * y with the resident Jacobian (values=None) or a CUDA tensor of CSR values.
+        asynchronous=True (host arrays, NSB_HOST_ASYNC): x goes up on the H2D stream while the context stream is still busy,
+        y is complete after synchronize()."""
         on_dev = _is_torch(x)
         if on_dev:
             import torch
@@ -393,11 +408,16 @@ class _DeviceDisc:
             if y is None:
                 y = torch.zeros(self.num_dofs, dtype=torch.float64, device=x.device)
         else:
+            if asynchronous:
+                for a in (x, y):
+                    if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
+                        raise UGError("apply_jacobian(asynchronous=True): pass C-contiguous float64 numpy arrays for x and y")
+                self._async_keep = getattr(self, "_async_keep", []) + [x, y]
             x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
             if y is None:
                 y = np.zeros(self.num_dofs)
         self._check(capi.lib().nsb_apply_jacobian(self._ctx, self._ptr(values), float(alpha), self._ptr(x), float(beta), self._ptr(y),
-                                                  capi.DEVICE if on_dev else capi.HOST))
+                                                  capi.DEVICE if on_dev else (capi.HOST_ASYNC if asynchronous else capi.HOST)))
         return y
 
     # ---- per-ip data imports ----

@@ -157,3 +157,32 @@ def test_wall_and_inflow_dirichlet_post_pass(ora, elem, n):
     h = disc.adjust_vector(np.ones(u.size))
     assert np.all(h[dofs] == 0.0) and h.sum() == u.size - dofs.size
     disc.close()
+
+
+@pytest.mark.parametrize("elem,n", [("hex", 8), ("tri", 16)])
+def test_resident_async_host_handoff_equals_synchronous(elem, n):
+    """NSB_HOST_ASYNC (copies on the context's copy streams, completed by nsb_synchronize) returns the bits of the NSB_HOST calls,
+    also when the staging buffers are reused by back-to-back steps with changing inputs"""
+    import torch
+    coords, conn, u = parity.make_case(elem, n, seed=7)
+    dim = coords.shape[1]
+    disc = pkg.NavierStokesFV1("u,v,w,p" if dim == 3 else "u,v,p", "Inner")
+    parity.configure(disc, upwind="lps", stab="fields")
+    disc.set_grid(elem, conn, coords)
+    nd = u.size
+    rng = np.random.default_rng(3)
+    hu = torch.empty(nd, dtype=torch.float64).pin_memory(); hd = torch.empty(nd, dtype=torch.float64).pin_memory()
+    hx = torch.empty(nd, dtype=torch.float64).pin_memory(); hy = torch.empty(nd, dtype=torch.float64).pin_memory()
+    for step in range(3):
+        us = u.reshape(-1) * (1.0 + 0.1 * step)
+        xs = rng.uniform(-1, 1, nd)
+        d_ref = disc.assemble_resident(JD, us).copy()
+        y_ref = disc.apply_jacobian(xs).copy()
+        hu.numpy()[:] = us; hx.numpy()[:] = xs; hd.numpy()[:] = np.nan; hy.numpy()[:] = np.nan
+        disc.assemble_resident(JD, hu.numpy(), defect=hd.numpy(), asynchronous=True)
+        disc.apply_jacobian(hx.numpy(), y=hy.numpy(), asynchronous=True)
+        disc.synchronize(); disc.check_errors()
+        assert np.array_equal(hd.numpy(), d_ref) and np.array_equal(hy.numpy(), y_ref)
+    with pytest.raises(pkg.UGError):
+        disc.apply_jacobian(hx.numpy()[::2], y=hy.numpy(), asynchronous=True)
+    disc.close()
