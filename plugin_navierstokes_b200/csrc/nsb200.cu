@@ -812,12 +812,16 @@ static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u,
     return set_err(c, NSB_ERR_INVALID, "unknown scatter mode %d", mode);
 }
 
-// FVCR: element kernel with coloured (deterministic) or atomic scatter; the owner-computes path is FV1-only
+// FVCR: element kernel with coloured or atomic scatter (both deterministic for beta == 0, see below); the owner-computes path is FV1-only
 static int assemble_fvcr(nsb_ctx* c, const KParams& k, int mode, const double* u, double beta, double* val, double* def, int phase = 0)
 {
     if (phase == 2) return NSB_OK;
     const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
-    if (mode == NSB_SCATTER_GATHER) mode = NSB_SCATTER_COLORED;
+    // A CR velocity dof lives on an element side, which has at most TWO elements; two different sides share at most one element
+    // and the pressure dof belongs to one. With beta == 0 every entry is therefore 0 + a (+ b), and a + b == b + a exactly: the
+    // single-launch reduction in element order returns the bits of the coloured sweeps (tests/test_gpu_parity_fvcr.py), without
+    // streaming the value array once per colour. beta != 0 adds a third term -> coloured sweeps.
+    if (mode == NSB_SCATTER_GATHER) mode = (beta == 0.0) ? NSB_SCATTER_ATOMIC : NSB_SCATTER_COLORED;
     c->last_scatter = mode;
     if (jac) {
         if (beta == 0.0) CUDA_TRY(c, cudaMemsetAsync(val, 0, sizeof(double) * c->nnz, c->stream));

@@ -679,7 +679,9 @@ class NavierStokesFVCR(_DeviceDisc):
     def __init__(self, fcts, subsets="", device=0):
         super().__init__(fcts, subsets, device)
         self._defect_upwind = True                     # fvcr/navier_stokes_fvcr.cpp:82
-        self.scatter_mode = capi.SCATTER_COLORED
+        # GATHER = the deterministic default: one launch of order-free reductions for beta == 0 (a CR entry has at most two
+        # contributions), coloured sweeps otherwise (nsb200.cu: assemble_fvcr)
+        self.scatter_mode = capi.SCATTER_GATHER
 
     def disc_type(self):
         return "fvcr"

@@ -1,0 +1,122 @@
+"""Host-side mirror of the solution-level evaluation tools of the plugin (incompressible/navier_stokes_tools.h).
+
+DrivenCavityLinesEval (navier_stokes_tools.h:571-713, registered in incompressible_navier_stokes_plugin.cpp:202) evaluates the
+velocity of a 2-D lid-driven-cavity solution at the sample points of the literature tables the reference carries (Ghia, Ghia & Shin
+1982; Botella & Peyret 1998 for Re = 1000) -- u on the vertical line x = 0.5, v on the horizontal line y = 0.5 -- and reports the
+maximum and the average difference (DrivenCavityEvalAtPoints, :539-569). These tables are the only known-answer data the reference
+holds for the path this package accelerates; tests/test_gpu_cavity.py uses them as the solution-level check of the whole chain
+(assembly, boundary conditions, Dirichlet post-pass, resident Jacobian, linear solve).
+
+The grid function is P1 / Q1 on triangles / quadrilaterals in the FV1 dof layout node * 3 + fct (u, v, p); point evaluation
+follows ugcore's GlobalGridFunctionNumberData::evaluate_global: find the element containing the point, map to local coordinates,
+evaluate the Lagrange shapes."""
+import numpy as np
+
+# sample positions of the Ghia tables (navier_stokes_tools.h:578-591)
+GHIA_VERT_X = 0.5
+GHIA_VERT_Y = (0.0000, 0.0547, 0.0625, 0.0703, 0.1016, 0.1719, 0.2813, 0.4531, 0.5000, 0.6172, 0.7344, 0.8516, 0.9531, 0.9609, 0.9688,
+               0.9766, 1.0000)
+GHIA_HORIZ_Y = 0.5
+GHIA_HORIZ_X = (0.0000, 0.0625, 0.0703, 0.0781, 0.0938, 0.1563, 0.2266, 0.2344, 0.5000, 0.8047, 0.8594, 0.9063, 0.9453, 0.9531, 0.9609,
+                0.9688, 1.0000)
+# u(x = 0.5, y) and v(x, y = 0.5) per Reynolds number (navier_stokes_tools.h:580-598; Botella :614-617)
+_VERT = {
+    100: (0., -0.03717, -0.04192, -0.04775, -0.06434, -0.10150, -0.15662, -0.2109, -0.20581, -0.13641, 0.00332, 0.23151, 0.68717, 0.73722,
+          0.78871, 0.84123, 1.),
+    400: (0., -0.08186, -0.09266, -0.10338, -0.14612, -0.24299, -0.32726, -0.17119, -0.11477, 0.02135, 0.16256, 0.29093, 0.55892, 0.61756,
+          0.68439, 0.75837, 1.),
+    1000: (0., -0.18109, -0.20196, -0.22220, -0.29730, -0.38289, -0.27805, -0.10648, -0.06080, 0.05702, 0.18719, 0.33304, 0.46604, 0.51117,
+           0.57492, 0.65928, 1.),
+}
+_HORIZ = {
+    100: (0.00000, 0.09233, 0.10091, 0.10890, 0.12317, 0.16077, 0.17507, 0.17527, 0.05454, -0.24533, -0.22445, -0.16914, -0.10313, -0.08864,
+          -0.07391, -0.05906, 0.00000),
+    400: (0.00000, 0.18360, 0.19713, 0.20920, 0.22965, 0.28124, 0.30203, 0.30174, 0.05186, -0.38598, -0.44993, -0.3827, -0.22847, -0.19254,
+          -0.15663, -0.12146, 0.00000),
+    1000: (0.00000, 0.27485, 0.29012, 0.30353, 0.32627, 0.37095, 0.33075, 0.32235, 0.02526, -0.31966, -0.42665, -0.51550, -0.39188, -0.33714,
+           -0.27669, -0.21388, 0.00000),
+}
+_VERT_BOTELLA_1000 = (0.0000000, -0.1812881, -0.2023300, -0.2228955, -0.3004561, -0.3885691, -0.2803696, -0.1081999, -0.0620561, 0.0570178,
+                      0.1886747, 0.3372212, 0.4723329, 0.5169277, 0.5808359, 0.6644227, 1.0000000)
+_HORIZ_BOTELLA_1000 = (0.0000000, 0.2807056, 0.2962703, 0.3099097, 0.3330442, 0.3769189, 0.3339924, 0.3253592, 0.0257995, -0.3202137,
+                       -0.4264545, -0.5264392, -0.4103754, -0.3553213, -0.2936869, -0.2279225, 0.0000000)
+
+
+def _local_coordinates(xe, pt):
+    """local coordinates of pt in the triangle / quadrilateral with corners xe (reference numbering); None when outside"""
+    tol = 1e-10
+    if xe.shape[0] == 3:
+        T = np.array([xe[1] - xe[0], xe[2] - xe[0]]).T
+        xi = np.linalg.solve(T, pt - xe[0])
+        return xi if xi.min() >= -tol and xi.sum() <= 1 + tol else None
+    xi = np.array([0.5, 0.5])
+    for _ in range(30):                                   # Newton on the bilinear map
+        x, y = xi
+        N = np.array([(1 - x) * (1 - y), x * (1 - y), x * y, (1 - x) * y])
+        dN = np.array([[-(1 - y), -(1 - x)], [(1 - y), -x], [y, x], [-y, (1 - x)]])
+        r = N @ xe - pt
+        if np.abs(r).max() < 1e-14:
+            break
+        xi = xi - np.linalg.solve((dN.T @ xe).T, r)
+    return xi if xi.min() >= -tol and xi.max() <= 1 + tol else None
+
+
+def evaluate_global(u, coords, conn, fct, points, nf=3):
+    """value of component fct of the P1 / Q1 grid function u (layout node * nf + fct) at each point"""
+    u = np.asarray(u, dtype=np.float64).reshape(-1, nf)
+    xe_all = coords[conn]                                 # [n_elem][nsh][2]
+    lo, hi = xe_all.min(axis=1), xe_all.max(axis=1)
+    out = np.empty(len(points))
+    for i, pt in enumerate(np.asarray(points, dtype=np.float64)):
+        cand = np.nonzero(np.all((lo <= pt + 1e-12) & (hi >= pt - 1e-12), axis=1))[0]
+        for e in cand:
+            xi = _local_coordinates(xe_all[e], pt)
+            if xi is None:
+                continue
+            if conn.shape[1] == 3:
+                N = np.array([1 - xi[0] - xi[1], xi[0], xi[1]])
+            else:
+                x, y = xi
+                N = np.array([(1 - x) * (1 - y), x * (1 - y), x * y, (1 - x) * y])
+            out[i] = N @ u[conn[e], fct]
+            break
+        else:
+            raise ValueError("evaluate_global: point %s is outside the grid" % (pt,))
+    return out
+
+
+def _eval_at_points(u, coords, conn, fct, points, reference):
+    """DrivenCavityEvalAtPoints (navier_stokes_tools.h:539-569): measured values, reference values, max and average difference"""
+    val = evaluate_global(u, coords, conn, fct, points)
+    ref = np.asarray(reference, dtype=np.float64)
+    diff = np.abs(ref - val)
+    return {"positions": np.asarray(points), "measure": val, "reference": ref, "max_diff": float(diff.max()), "average_diff": float(diff.mean())}
+
+
+def DrivenCavityLinesEval(u, coords, conn, Re, vel_cmp=(0, 1), log=None):
+    """mirror of DrivenCavityLinesEval(u, {"u","v"}, Re): returns {source: {"vertical": {...}, "horizontal": {...}}} with the tables the
+    reference prints (Ghia for Re in 100 / 400 / 1000, Botella & Peyret for Re = 1000); an unknown Re gives an empty dict, as the
+    reference prints nothing then. log: optional callable receiving the lines the reference writes with UG_LOG."""
+    Re = int(Re)
+    out = {}
+    vert_pts = [(GHIA_VERT_X, y) for y in GHIA_VERT_Y]
+    horiz_pts = [(x, GHIA_HORIZ_Y) for x in GHIA_HORIZ_X]
+    sources = []
+    if Re in _VERT:
+        sources.append(("Ghia", _VERT[Re], _HORIZ[Re]))
+    if Re == 1000:
+        sources.append(("Botella/Peyret", _VERT_BOTELLA_1000, _HORIZ_BOTELLA_1000))
+    for name, vert, horiz in sources:
+        res = {"vertical": _eval_at_points(u, coords, conn, vel_cmp[0], vert_pts, vert),
+               "horizontal": _eval_at_points(u, coords, conn, vel_cmp[1], horiz_pts, horiz)}
+        out[name] = res
+        if log:
+            for line, what in (("vertical", "u values on a vertical line through x = 0.5"), ("horizontal", "v values on a horizontal line through y = 0.5")):
+                log("  ------ %s, Re = %d: %s  ------" % (name, Re, what))
+                r = res[line]
+                for i in range(len(r["measure"])):
+                    log("%2d  (%.4f, %.4f)  %.8f  %.7f  %.3e" % (i + 1, r["positions"][i][0], r["positions"][i][1], r["measure"][i], r["reference"][i],
+                                                                 abs(r["measure"][i] - r["reference"][i])))
+                log("\t     Max Diff: %g" % r["max_diff"])
+                log("\t Average Diff: %g" % r["average_diff"])
+    return out

@@ -35,3 +35,24 @@ def test_cavity_converges_and_satisfies_the_oracle_defect(ora, dim, cells):
     lid = np.isclose(coords[:, dim - 1], hi[dim - 1])
     assert np.allclose(uh.reshape(-1, nf)[lid, 0], 1.0) and np.allclose(uh.reshape(-1, nf)[on_bnd & ~lid, :dim], 0.0)
     disc.close()
+
+
+def test_cavity_re100_reproduces_the_reference_ghia_tables():
+    """Solution-level known-answer check against the only golden data the reference carries for this path: the Ghia et al. centre-line
+    velocities embedded in DrivenCavityLinesEval (incompressible/navier_stokes_tools.h:578-598). The cavity at Re = 100 is solved on
+    the device (FV1, LPS upwind + FIELDS, walls / lid through the Dirichlet post-pass, resident Jacobian) and evaluated with the
+    mirror of that function: the differences shrink with the mesh width and reach plotting accuracy at 64^2."""
+    import cavity
+    from plugin_navierstokes_b200 import tools
+    res = {}
+    for cells in (32, 64):
+        disc, coords, conn, u, hist = cavity.solve(2, cells, re=100.0, verbose=False, upwind="lps")
+        assert hist[-1] < 1e-8 * hist[0]
+        res[cells] = tools.DrivenCavityLinesEval(u.cpu().numpy(), coords, conn, 100)["Ghia"]
+        disc.close()
+    v32, v64 = res[32]["vertical"], res[64]["vertical"]
+    h32, h64 = res[32]["horizontal"], res[64]["horizontal"]
+    # measured on B200 (profiles/r2_cavity_ghia.txt): 32^2 0.0264 / 0.0231, 64^2 0.0119 / 0.0072, 96^2 0.0067 / 0.0020
+    assert v64["max_diff"] < 0.015 and v64["average_diff"] < 0.006
+    assert h64["max_diff"] < 0.010 and h64["average_diff"] < 0.003
+    assert v64["max_diff"] < 0.6 * v32["max_diff"] and h64["max_diff"] < 0.6 * h32["max_diff"]

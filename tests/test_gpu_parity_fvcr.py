@@ -92,6 +92,28 @@ def test_fvcr_mass_rhs_and_scales(ora, elem, n):
         assert eg < TOL and ee < TOL
 
 
+@pytest.mark.parametrize("elem,n", [("tri", 24), ("tet", 8)])
+def test_fvcr_gather_is_bitwise_the_coloured_result(elem, n):
+    """NSB_SCATTER_GATHER serves FVCR (beta = 0) with ONE launch of fire-and-forget reductions in element order: a CR entry has at
+    most two contributions (a side has two elements), 0 + a + b == 0 + b + a exactly, so the bits equal the coloured sweeps and
+    do not change from run to run; beta != 0 takes the coloured sweeps"""
+    coords, conn, es, n_side, u = _case(elem, n, seed=11)
+    disc = pkg.NavierStokesFVCR(FCTS[coords.shape[1]], "Inner")
+    disc.set_kinematic_viscosity(1e-3); disc.set_upwind("lps"); disc.set_exact_jacobian(1.0)
+    disc.set_grid(elem, conn, coords, es, n_side)
+    what = capi.JAC_A | capi.DEF_A | capi.JAC_M | capi.DEF_M
+    cv, cd = disc.assemble(what, u, scale_a=0.7, scatter_mode=capi.SCATTER_COLORED)
+    for _ in range(5):
+        gv, gd = disc.assemble(what, u, scale_a=0.7, scatter_mode=capi.SCATTER_GATHER)
+        assert np.array_equal(gv, cv) and np.array_equal(gd, cd)
+    # accumulate (beta = 1): served by the coloured sweeps, same bits as an explicit coloured request
+    gv2, gd2 = disc.assemble(what, u, scale_a=0.7, values=cv.copy(), defect=cd.copy(), beta=1.0, scatter_mode=capi.SCATTER_GATHER)
+    cv2, cd2 = disc.assemble(what, u, scale_a=0.7, values=cv.copy(), defect=cd.copy(), beta=1.0, scatter_mode=capi.SCATTER_COLORED)
+    assert np.array_equal(gv2, cv2) and np.array_equal(gd2, cd2)
+    assert np.allclose(gv2, 2.0 * cv, rtol=1e-13, atol=1e-13 * np.abs(cv).max())
+    disc.close()
+
+
 def test_fvcr_errors():
     coords, conn = meshgen.make_mesh("tri", 3)
     d = pkg.NavierStokesFVCR("u,v,p", "Inner")

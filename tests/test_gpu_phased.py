@@ -81,5 +81,8 @@ def test_served_scatter_mode_is_reported():
     d2.set_kinematic_viscosity(1e-2); d2.set_upwind("full")
     d2.set_grid("tet", conn, coords, es, n_side)
     d2.assemble(JD, np.zeros(d2.num_dofs), scatter_mode=capi.SCATTER_GATHER)
-    assert d2.query(capi.Q_LAST_SCATTER) == capi.SCATTER_COLORED
+    assert d2.query(capi.Q_LAST_SCATTER) == capi.SCATTER_ATOMIC       # CR: every entry has at most two contributions, 0 + a + b is order-free
+    v = np.zeros(d2.nnz); d = np.zeros(d2.num_dofs)
+    d2.assemble(JD, np.zeros(d2.num_dofs), values=v, defect=d, beta=1.0, scatter_mode=capi.SCATTER_GATHER)
+    assert d2.query(capi.Q_LAST_SCATTER) == capi.SCATTER_COLORED      # beta != 0: a third term, coloured sweeps
     d2.close()

@@ -1,0 +1,61 @@
+"""host-side mirror of the solution-level tools (plugin_navierstokes_b200/tools.py; reference: incompressible/navier_stokes_tools.h):
+point evaluation of P1 / Q1 grid functions and the driven-cavity line evaluation against the reference's literature tables"""
+import numpy as np
+import pytest
+
+from plugin_navierstokes_b200 import meshgen, tools
+
+
+@pytest.mark.parametrize("elem", ["tri", "quad"])
+def test_evaluate_global_reproduces_the_interpolated_field(elem):
+    coords, conn = meshgen.make_mesh(elem, 9, jitter=0.2, seed=4)
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0.02, 0.98, (40, 2))
+    # a linear field is reproduced exactly on both element types
+    u = np.zeros((coords.shape[0], 3))
+    u[:, 0] = 0.3 + 2.0 * coords[:, 0] - 1.5 * coords[:, 1]
+    u[:, 1] = -0.7 * coords[:, 0]
+    got = tools.evaluate_global(u.reshape(-1), coords, conn, 0, pts)
+    assert np.allclose(got, 0.3 + 2.0 * pts[:, 0] - 1.5 * pts[:, 1], atol=1e-12)
+    got = tools.evaluate_global(u.reshape(-1), coords, conn, 1, pts)
+    assert np.allclose(got, -0.7 * pts[:, 0], atol=1e-12)
+    # grid nodes return the nodal values; points on element boundaries are found
+    got = tools.evaluate_global(u.reshape(-1), coords, conn, 0, coords[::7])
+    assert np.allclose(got, u[::7, 0], atol=1e-12)
+    with pytest.raises(ValueError):
+        tools.evaluate_global(u.reshape(-1), coords, conn, 0, [(1.5, 0.5)])
+
+
+def test_bilinear_field_on_an_axis_aligned_quad_grid():
+    coords, conn = meshgen.quad_grid(8, 8)
+    u = np.zeros((coords.shape[0], 3))
+    u[:, 0] = coords[:, 0] * coords[:, 1]                        # in the Q1 space of an axis-aligned grid
+    pts = np.random.default_rng(1).uniform(0, 1, (30, 2))
+    got = tools.evaluate_global(u.reshape(-1), coords, conn, 0, pts)
+    assert np.allclose(got, pts[:, 0] * pts[:, 1], atol=1e-12)
+
+
+def test_driven_cavity_lines_eval_tables():
+    """feeding the tabulated profile back gives zero difference at the sample points that are grid nodes; table shapes, sources and
+    the lid / wall end points follow navier_stokes_tools.h:578-617"""
+    for Re in (100, 400, 1000):
+        assert len(tools._VERT[Re]) == 17 and len(tools._HORIZ[Re]) == 17
+        assert tools._VERT[Re][0] == 0.0 and tools._VERT[Re][-1] == 1.0          # wall, lid
+        assert tools._HORIZ[Re][0] == 0.0 and tools._HORIZ[Re][-1] == 0.0        # walls
+    # a grid whose node lines are exactly the Ghia sample positions: u(0.5, y_i) := table -> max diff 0
+    xs = np.array(sorted(set(tools.GHIA_HORIZ_X)))
+    ys = np.array(sorted(set(tools.GHIA_VERT_Y)))
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    coords = np.stack([X.ravel(), Y.ravel()], axis=1)
+    nx, ny = xs.size, ys.size
+    conn = np.array([[j * nx + i, j * nx + i + 1, (j + 1) * nx + i + 1, (j + 1) * nx + i] for j in range(ny - 1) for i in range(nx - 1)], dtype=np.int32)
+    u = np.zeros((coords.shape[0], 3))
+    u[:, 0] = np.interp(coords[:, 1], tools.GHIA_VERT_Y, tools._VERT[100])
+    u[:, 1] = np.interp(coords[:, 0], tools.GHIA_HORIZ_X, tools._HORIZ[100])
+    lines = []
+    out = tools.DrivenCavityLinesEval(u.reshape(-1), coords, conn, 100, log=lines.append)
+    assert set(out) == {"Ghia"}
+    assert out["Ghia"]["vertical"]["max_diff"] < 1e-14 and out["Ghia"]["horizontal"]["max_diff"] < 1e-14
+    assert any("Max Diff" in l for l in lines) and any("Ghia, Re = 100" in l for l in lines)
+    assert set(tools.DrivenCavityLinesEval(u.reshape(-1), coords, conn, 1000)) == {"Ghia", "Botella/Peyret"}
+    assert tools.DrivenCavityLinesEval(u.reshape(-1), coords, conn, 123) == {}

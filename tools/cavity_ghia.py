@@ -1,0 +1,22 @@
+"""lid-driven cavity solved on the device (examples/cavity.py) against the literature tables of the reference's
+DrivenCavityLinesEval (incompressible/navier_stokes_tools.h:578-617):  python tools/cavity_ghia.py [Re] [cells ...]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "examples")); sys.path.insert(0, ROOT)
+import warnings
+warnings.filterwarnings("ignore")
+import cavity
+from plugin_navierstokes_b200 import tools
+
+re = float(sys.argv[1]) if len(sys.argv) > 1 else 100.0
+sizes = [int(a) for a in sys.argv[2:]] or [32, 64, 96]
+for cells in sizes:
+    for upw in ("lps", "full"):
+        t0 = time.time()
+        disc, coords, conn, u, hist = cavity.solve(2, cells, re=re, verbose=False, upwind=upw)
+        out = tools.DrivenCavityLinesEval(u.cpu().numpy(), coords, conn, int(re))
+        for src, r in out.items():
+            print("Re %4d  %3d^2 quads  %-4s upwind + FIELDS  %2d iterations (defect x %.1e)  %-14s u(0.5, y): max %.4f avg %.4f | v(x, 0.5): max %.4f avg %.4f  [%.1f s]"
+                  % (re, cells, upw, len(hist) - 1, hist[-1] / hist[0], src, r["vertical"]["max_diff"], r["vertical"]["average_diff"],
+                     r["horizontal"]["max_diff"], r["horizontal"]["average_diff"], time.time() - t0), flush=True)
+        disc.close()

@@ -16,7 +16,12 @@ except Exception:
     pass
 
 
+MODES = {"gather": capi.SCATTER_GATHER, "colored": capi.SCATTER_COLORED, "atomic": capi.SCATTER_ATOMIC}
+
+
 def timeit(disc, what, ud, ts, reps=5):
+    if os.environ.get("NSB_SCATTER"):                      # scatter-mode comparison: NSB_SCATTER=gather|colored|atomic
+        disc.scatter_mode = MODES[os.environ["NSB_SCATTER"]]
     vals = torch.empty(disc.nnz, dtype=torch.float64, device="cuda")
     dfc = torch.empty(disc.num_dofs, dtype=torch.float64, device="cuda")
     for _ in range(3):
