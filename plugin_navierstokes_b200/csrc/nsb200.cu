@@ -45,13 +45,13 @@ __global__ void node_volume_kernel(int64_t n_node, const int64_t* __restrict__ a
 // FV1 block CSR (ns_graph.h): warp per node = NF consecutive rows, lane = column slot (stride 32): the 4 (3) x 4 (3) block is
 // read once with 16-byte loads where NF == 4; fixed-order butterfly reduction -> bitwise deterministic.
 template <int NF>
-__global__ void __launch_bounds__(128) bcsr_spmv_kernel(int64_t n_node, const int64_t* __restrict__ brow, const int32_t* __restrict__ bcol,
+__global__ void __launch_bounds__(128) bcsr_spmv_kernel(int64_t row0, int64_t n_node, const int64_t* __restrict__ brow, const int32_t* __restrict__ bcol,
                                                         const double* __restrict__ val, const double* __restrict__ x, double alpha, double beta,
                                                         double* __restrict__ y)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t a = warp0; a < n_node; a += nwarp) {
+    for (int64_t a = row0 + warp0; a < n_node; a += nwarp) {      // block rows [row0, n_node)
         const int64_t b0 = brow[a];
         const int cnt = (int)(brow[a + 1] - b0);
         const double* v = val + b0 * (NF * NF);
@@ -84,13 +84,13 @@ __global__ void __launch_bounds__(128) bcsr_spmv_kernel(int64_t n_node, const in
     }
 }
 // scalar CSR (FVCR): warp per row
-__global__ void __launch_bounds__(128) csr_spmv_kernel(int64_t n_row, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+__global__ void __launch_bounds__(128) csr_spmv_kernel(int64_t row0, int64_t n_row, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                                                        const double* __restrict__ val, const double* __restrict__ x, double alpha, double beta,
                                                        double* __restrict__ y)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < n_row; r += nwarp) {
+    for (int64_t r = row0 + warp0; r < n_row; r += nwarp) {
         double s = 0.0;
         for (int64_t q = rowptr[r] + lane; q < rowptr[r + 1]; q += 32) s += __ldcs(val + q) * x[colind[q]];
 #pragma unroll
@@ -141,6 +141,7 @@ __global__ void unpack_add_kernel(int64_t n, const int64_t* __restrict__ idx, co
 
 static std::string g_create_error;
 
+#define NSB_ASYNC_CHUNKS 4      // row chunks of the NSB_HOST_ASYNC product (the result leaves chunk by chunk)
 struct nsb_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -189,7 +190,7 @@ struct nsb_ctx {
     double *d_xin = nullptr, *d_yout = nullptr;                // staging of nsb_apply_jacobian(NSB_HOST)
     // NSB_HOST_ASYNC: copy streams + events that order the staging buffers between the context stream and the copies
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_x_in = nullptr, ev_spmv = nullptr, ev_def_out = nullptr, ev_y_out = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_x_in = nullptr, ev_spmv = nullptr, ev_def_out = nullptr, ev_y_out = nullptr, ev_chunk[NSB_ASYNC_CHUNKS] = {};
     int64_t* d_dir = nullptr; int64_t n_dir = 0; double* d_dirval = nullptr;
     // boundary faces of the boundary discs (ns_bnd.cuh), per kind: BFs sorted by grid node
     struct BndSet { int64_t n_bnode = 0, n_bf = 0; int32_t* d_bnode = nullptr; int64_t* d_bptr = nullptr; nsb::BndFace* d_bf = nullptr; double* d_data = nullptr; };
@@ -298,7 +299,8 @@ extern "C" void nsb_destroy(nsb_ctx* c)
     free_mesh(c);
     cudaFree(c->d_err); cudaFree(c->d_counter);
     if (c->s_h2d) { cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_x_in);
-                    cudaEventDestroy(c->ev_spmv); cudaEventDestroy(c->ev_def_out); cudaEventDestroy(c->ev_y_out); }
+                    cudaEventDestroy(c->ev_spmv); cudaEventDestroy(c->ev_def_out); cudaEventDestroy(c->ev_y_out);
+                    for (int i = 0; i < NSB_ASYNC_CHUNKS; i++) cudaEventDestroy(c->ev_chunk[i]); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -973,6 +975,7 @@ static int ensure_async(nsb_ctx* c)
     CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&c->ev_main, &c->ev_x_in, &c->ev_spmv, &c->ev_def_out, &c->ev_y_out}) CUDA_TRY(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (int i = 0; i < NSB_ASYNC_CHUNKS; i++) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     return NSB_OK;
 }
 
@@ -1032,15 +1035,18 @@ extern "C" int nsb_resident_jacobian(nsb_ctx* c, double** dev_values)
     return NSB_OK;
 }
 
-static int spmv_launch(nsb_ctx* c, const double* val, double alpha, const double* x, double beta, double* y)
+// rows [r0, r1) of y = alpha J x + beta y (block rows for FV1, scalar rows for FVCR); r1 < 0 = all rows
+static int spmv_launch(nsb_ctx* c, const double* val, double alpha, const double* x, double beta, double* y, int64_t r0 = 0, int64_t r1 = -1)
 {
     int rc = ensure_pattern(c);
     if (rc) return rc;
     const int64_t nrows = c->disc == NSB_DISC_FVCR ? c->n_dof : c->n_node;
-    const unsigned nblk = (unsigned)std::min<int64_t>((nrows + 3) / 4, (int64_t)c->sm_count * 16);
-    if (c->disc == NSB_DISC_FVCR) csr_spmv_kernel<<<nblk, 128, 0, c->stream>>>(c->n_dof, c->d_rowptr, c->d_bcol, val, x, alpha, beta, y);
-    else if (kDIM[c->elem] == 3) bcsr_spmv_kernel<4><<<nblk, 128, 0, c->stream>>>(c->n_node, c->d_brow, c->d_bcol, val, x, alpha, beta, y);
-    else bcsr_spmv_kernel<3><<<nblk, 128, 0, c->stream>>>(c->n_node, c->d_brow, c->d_bcol, val, x, alpha, beta, y);
+    if (r1 < 0) r1 = nrows;
+    if (r1 <= r0) return NSB_OK;
+    const unsigned nblk = (unsigned)std::min<int64_t>((r1 - r0 + 3) / 4, (int64_t)c->sm_count * 16);
+    if (c->disc == NSB_DISC_FVCR) csr_spmv_kernel<<<nblk, 128, 0, c->stream>>>(r0, r1, c->d_rowptr, c->d_bcol, val, x, alpha, beta, y);
+    else if (kDIM[c->elem] == 3) bcsr_spmv_kernel<4><<<nblk, 128, 0, c->stream>>>(r0, r1, c->d_brow, c->d_bcol, val, x, alpha, beta, y);
+    else bcsr_spmv_kernel<3><<<nblk, 128, 0, c->stream>>>(r0, r1, c->d_brow, c->d_bcol, val, x, alpha, beta, y);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return NSB_OK;
@@ -1068,10 +1074,18 @@ extern "C" int nsb_apply_jacobian(nsb_ctx* c, const double* values, double alpha
         CUDA_TRY(c, cudaEventRecord(c->ev_x_in, c->s_h2d));
         CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_x_in, 0));
         CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_y_out, 0));             // the previous result has left the staging buffer
-        if ((rc = spmv_launch(c, val, alpha, c->d_xin, beta, c->d_yout))) return rc;
-        CUDA_TRY(c, cudaEventRecord(c->ev_spmv, c->stream));
-        CUDA_TRY(c, cudaStreamWaitEvent(c->s_d2h, c->ev_spmv, 0));
-        CUDA_TRY(c, cudaMemcpyAsync(y, c->d_yout, nb, cudaMemcpyDeviceToHost, c->s_d2h));
+        // the product runs in row chunks; the rows of a chunk leave on the D2H stream while the next chunk is computed
+        const int64_t nrows = c->disc == NSB_DISC_FVCR ? c->n_dof : c->n_node;
+        const int64_t per_row = c->disc == NSB_DISC_FVCR ? 1 : kDIM[c->elem] + 1;
+        const int nch = nrows >= 64 * NSB_ASYNC_CHUNKS ? NSB_ASYNC_CHUNKS : 1;
+        for (int ch = 0; ch < nch; ch++) {
+            const int64_t r0 = nrows * ch / nch, r1 = nrows * (ch + 1) / nch;
+            if ((rc = spmv_launch(c, val, alpha, c->d_xin, beta, c->d_yout, r0, r1))) return rc;
+            cudaEvent_t ev = ch + 1 < nch ? c->ev_chunk[ch] : c->ev_spmv;
+            CUDA_TRY(c, cudaEventRecord(ev, c->stream));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->s_d2h, ev, 0));
+            CUDA_TRY(c, cudaMemcpyAsync(y + r0 * per_row, c->d_yout + r0 * per_row, sizeof(double) * (size_t)((r1 - r0) * per_row), cudaMemcpyDeviceToHost, c->s_d2h));
+        }
         CUDA_TRY(c, cudaEventRecord(c->ev_y_out, c->s_d2h));
         return NSB_OK;
     }
