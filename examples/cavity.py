@@ -68,14 +68,17 @@ def direct_with_refinement(disc, jv, rowptr_t, colind_t, b, steps=2):
     return x, float(r.norm()) / max(float(b.norm()), 1e-300)
 
 
-def solve(dim=2, cells=16, re=100.0, picard_tol=1e-8, verbose=True, linear="direct", upwind=None):
+def solve(dim=2, cells=16, re=100.0, picard_tol=1e-8, verbose=True, linear="direct", upwind=None, elem=None, jitter=0.0):
     """upwind: default FullUpwind in 2-D (config 1), LinearProfileSkewedUpwind in 3-D (config 3; on coarse 3-D grids the fixed-point
     iteration with FullUpwind ends in a 2-cycle when a face flux changes sign -- the upwind corner jumps, the LPS cut point moves
     continuously)"""
     upwind = upwind or ("full" if dim == 2 else "lps")
     dev = torch.device("cuda", 0)
-    if dim == 2:
-        coords, conn = meshgen.quad_grid(cells, cells)
+    if dim == 2 and elem == "tri":                              # unstructured variant: jittered triangles
+        coords, conn = meshgen.tri_grid(cells, cells, jitter=jitter, seed=1)
+        fcts = "u,v,p"
+    elif dim == 2:
+        coords, conn = meshgen.quad_grid(cells, cells, jitter=jitter, seed=1)
         elem, fcts = "quad", "u,v,p"
     else:
         coords, conn = meshgen.hex_grid(cells, cells, cells)
