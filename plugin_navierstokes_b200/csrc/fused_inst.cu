@@ -20,7 +20,7 @@ static cudaError_t fused_t(const FusedArgs& A, int max_cnt, cudaStream_t st, int
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     (void)work_counter;
-    const int nblk = std::min<int64_t>(A.n_patch, sm_count);
+    const int nblk = (int)std::min<int64_t>(A.n_patch, (int64_t)sm_count * FusedCfg<E>::CTAS);
     if (nblk <= 0) return cudaSuccess;
     kern<<<nblk, FusedCfg<E>::NT, smem, st>>>(A, max_cnt);
     return cudaGetLastError();

@@ -27,7 +27,11 @@ namespace nsb {
 
 template <int E> struct FusedCfg {
     static constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH, NIP = ET<E>::NIP, NF = DIM + 1, NINC = ET<E>::NINC, NSIDE = ET<E>::NSIDE;
-    static constexpr int NT = 512;                                  // threads per CTA
+    // threads per CTA. 2-D: 256 threads and half-size patches so that TWO CTAs are resident per SM (about 82 KB of shared memory
+    // each): the phases of a patch are separated by block-wide barriers (flux -> accumulate -> output, 47 % of the stall samples
+    // with one 512-thread CTA per SM), a second CTA fills the SM while the first one waits
+    static constexpr int NT = ET<E>::DIM == 2 ? 256 : 512;
+    static constexpr int CTAS = ET<E>::DIM == 2 ? 2 : 1;           // resident CTAs per SM the kernel is bounded for
     static constexpr int RS = LeanRec<E>::SZ;
     static constexpr int RSTR = RS + 1;                             // odd record stride in shared memory: the lanes of a half-warp (adjacent slots, same field) hit distinct banks
     static constexpr int GEO = 16;                                  // doubles per static SCVF geometry record: n[3] xip[3] JI[9] 1/L_d^2 (2-D: same slots, unused ones 0)
@@ -40,18 +44,18 @@ template <int E> struct FusedCfg {
     static constexpr int NWARP = NT / 32;
     static constexpr int JIT = 2;                                   // rows phase, output: rounds of 32 words per matrix row held in registers (J0 prefetch)
     // capacities of one patch (tile = node-box the grid is binned into; see ns_patch.h)
-    static constexpr int MAXW = 512;
-    static constexpr int MAXE = E == E_HEX ? 80 : (E == E_TET ? 160 : (E == E_QUAD ? 128 : 224));
-    static constexpr int MAXN = E == E_HEX ? 32 : (E == E_TET ? 24 : (E == E_QUAD ? 96 : 64));
-    static constexpr int MAXA = E == E_HEX ? 288 : (E == E_TET ? 480 : 448);
+    static constexpr int MAXW = ET<E>::DIM == 2 ? 256 : 512;
+    static constexpr int MAXE = E == E_HEX ? 80 : (E == E_TET ? 160 : (E == E_QUAD ? 64 : 112));
+    static constexpr int MAXN = E == E_HEX ? 32 : (E == E_TET ? 24 : (E == E_QUAD ? 48 : 32));
+    static constexpr int MAXA = E == E_HEX ? 288 : (E == E_TET ? 480 : 224);
     static PatchCaps caps()
     {
         PatchCaps c;
         c.max_work = MAXW; c.max_elem = MAXE; c.max_node = MAXN; c.max_adj = MAXA;
         if (E == E_HEX) { c.tile[0] = 4; c.tile[1] = 4; c.tile[2] = 2; }
         else if (E == E_TET) { c.tile[0] = 2; c.tile[1] = 2; c.tile[2] = 2; }
-        else if (E == E_QUAD) { c.tile[0] = 12; c.tile[1] = 8; c.tile[2] = 1; }
-        else { c.tile[0] = 8; c.tile[1] = 8; c.tile[2] = 1; }
+        else if (E == E_QUAD) { c.tile[0] = 8; c.tile[1] = 6; c.tile[2] = 1; }      // 48 nodes, 63 quadrilaterals, 252 SCVFs
+        else { c.tile[0] = 6; c.tile[1] = 5; c.tile[2] = 1; }                        // 30 nodes, 84 triangles, 252 SCVFs
         return c;
     }
 };
@@ -1030,7 +1034,7 @@ template <int E> NSB_DEV bool fused_star_shaped(const double* x)
 // the kernel: persistent CTAs, patches handed out by an atomic ticket
 // ------------------------------------------------------------------------------------------------
 template <int E, int STAB, bool TD, bool GEOT>
-__global__ void __launch_bounds__(FusedCfg<E>::NT, 1) fv1_fused_kernel(const FusedArgs A, int max_cnt)
+__global__ void __launch_bounds__(FusedCfg<E>::NT, FusedCfg<E>::CTAS) fv1_fused_kernel(const FusedArgs A, int max_cnt)
 {
     using C = FusedCfg<E>;
     constexpr int NSH = C::NSH, NF = C::NF, NPW = C::NPW, NWARP = C::NWARP;
