@@ -890,6 +890,16 @@ static int ensure(nsb_ctx* c, double** p, size_t n)
     return NSB_OK;
 }
 
+// The staging buffers (d_def, d_yout) may still be read by the D2H stream of an earlier NSB_HOST_ASYNC call: order the context
+// stream behind those copies before a host-pointer call reuses them.
+static int order_after_async_copies(nsb_ctx* c)
+{
+    if (!c->s_d2h) return NSB_OK;
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_def_out, 0));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_y_out, 0));
+    return NSB_OK;
+}
+
 extern "C" int nsb_assemble(nsb_ctx* c, int what, int mode, const double* u, const nsb_time_series* ts, double sa, double sm,
                             double beta, double* values, double* defect, int location)
 {
@@ -911,6 +921,7 @@ extern "C" int nsb_assemble(nsb_ctx* c, int what, int mode, const double* u, con
     double *dv = values, *dd = defect;
     if (location == NSB_HOST) {
         const size_t nb = sizeof(double) * c->n_dof;
+        if ((rc = order_after_async_copies(c))) return rc;
         if ((rc = ensure(c, &c->d_u, c->n_dof))) return rc;
         CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, nb, cudaMemcpyHostToDevice, c->stream)); du = c->d_u;
         if (k.time_dep || (c->disc == NSB_DISC_FVCR && ds0)) {
@@ -1020,8 +1031,8 @@ extern "C" int nsb_assemble_resident(nsb_ctx* c, int what, int mode, const doubl
     }
     if (location == NSB_DEVICE) return nsb_assemble(c, what, mode, u, ts, sa, sm, beta, c->d_jres, defect, NSB_DEVICE);
     const bool async = location == NSB_HOST_ASYNC;
-    if (async) { if ((rc = ensure_async(c))) return rc;
-                 CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_def_out, 0)); }     // the previous defect has left the staging buffer
+    if (async && (rc = ensure_async(c))) return rc;
+    if ((rc = order_after_async_copies(c))) return rc;
     // host vectors, device-resident matrix: u (and the time series) in, defect out
     KParams k;
     if ((rc = resolve_params(c, k, what, ts, sa, sm))) return rc;
@@ -1114,6 +1125,7 @@ extern "C" int nsb_apply_jacobian(nsb_ctx* c, const double* values, double alpha
         CUDA_TRY(c, cudaEventRecord(c->ev_y_out, c->s_d2h));
         return NSB_OK;
     }
+    if ((rc = order_after_async_copies(c))) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(c->d_xin, x, nb, cudaMemcpyHostToDevice, c->stream));
     if (beta != 0.0) CUDA_TRY(c, cudaMemcpyAsync(c->d_yout, y, nb, cudaMemcpyHostToDevice, c->stream));
     if ((rc = spmv_launch(c, val, alpha, c->d_xin, beta, c->d_yout))) return rc;
@@ -1277,6 +1289,7 @@ extern "C" int nsb_assemble_boundary(nsb_ctx* c, int what, const double* u, doub
     const double* du = u; double* dd = defect;
     const size_t nb = sizeof(double) * c->n_dof;
     if (location == NSB_HOST) {
+        if ((rc = order_after_async_copies(c))) return rc;
         if ((rc = ensure(c, &c->d_u, c->n_dof))) return rc;
         CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, nb, cudaMemcpyHostToDevice, c->stream)); du = c->d_u;
         if (dfc) { if ((rc = ensure(c, &c->d_def, c->n_dof))) return rc; dd = c->d_def;
@@ -1413,6 +1426,7 @@ extern "C" int nsb_fvcr_constraint_defect(nsb_ctx* c, const double* u, double s_
     const double* du = u; double* dd = defect;
     const size_t nb = sizeof(double) * c->n_dof;
     if (location == NSB_HOST) {
+        if ((rc = order_after_async_copies(c))) return rc;
         if ((rc = ensure(c, &c->d_u, c->n_dof)) || (rc = ensure(c, &c->d_def, c->n_dof))) return rc;
         CUDA_TRY(c, cudaMemcpyAsync(c->d_u, u, nb, cudaMemcpyHostToDevice, c->stream)); du = c->d_u;
         CUDA_TRY(c, cudaMemcpyAsync(c->d_def, defect, nb, cudaMemcpyHostToDevice, c->stream)); dd = c->d_def;

@@ -183,6 +183,19 @@ def test_resident_async_host_handoff_equals_synchronous(elem, n):
         disc.apply_jacobian(hx.numpy(), y=hy.numpy(), asynchronous=True)
         disc.synchronize(); disc.check_errors()
         assert np.array_equal(hd.numpy(), d_ref) and np.array_equal(hy.numpy(), y_ref)
+    # a synchronous host-pointer call right behind asynchronous ones (no nsb_synchronize in between) reuses the staging buffers:
+    # the context stream is ordered behind the pending copies, both results are right
+    ua, ub = u.reshape(-1) * 0.9, u.reshape(-1) * 1.2
+    da_ref = disc.assemble_resident(JD, ua).copy(); ya_ref = disc.apply_jacobian(xs).copy()
+    db_ref = disc.assemble_resident(JD, ub).copy(); yb_ref = disc.apply_jacobian(xs).copy()
+    hu.numpy()[:] = ua; hd.numpy()[:] = np.nan; hy.numpy()[:] = np.nan
+    disc.assemble_resident(JD, hu.numpy(), defect=hd.numpy(), asynchronous=True)
+    disc.apply_jacobian(hx.numpy(), y=hy.numpy(), asynchronous=True)
+    db = disc.assemble_resident(JD, ub)
+    yb = disc.apply_jacobian(xs)
+    disc.synchronize()
+    assert np.array_equal(db, db_ref) and np.array_equal(yb, yb_ref)
+    assert np.array_equal(hd.numpy(), da_ref) and np.array_equal(hy.numpy(), ya_ref)
     with pytest.raises(pkg.UGError):
         disc.apply_jacobian(hx.numpy()[::2], y=hy.numpy(), asynchronous=True)
     disc.close()
