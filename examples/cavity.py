@@ -138,6 +138,52 @@ def solve(dim=2, cells=16, re=100.0, picard_tol=1e-8, verbose=True, linear="dire
     return disc, coords, conn, u, hist
 
 
+def solve_fvcr(cells=16, re=100.0, picard_tol=1e-8, verbose=True, upwind="full", jitter=0.0):
+    """the same cavity with NavierStokesFVCR on triangles (Crouzeix-Raviart velocities on the sides, piecewise constant pressure; no
+    stabilisation needed): Dirichlet values on the boundary SIDES (lid = sides with midpoint on y = 1), pressure of element 0 pinned.
+    Returns (disc, coords, conn, elem_sides, u, history)."""
+    dev = torch.device("cuda", 0)
+    coords, conn = meshgen.tri_grid(cells, cells, jitter=jitter, seed=1)
+    es, n_side = meshgen.element_sides("tri", conn)
+    disc = pkg.NavierStokesFVCR("u,v,p", "Inner")
+    disc.set_kinematic_viscosity(1.0 / re)
+    disc.set_upwind(upwind)
+    disc.set_grid("tri", conn, coords, es, n_side)
+    mid = np.zeros((n_side, 2))
+    cnt = np.zeros(n_side)
+    for k, sd in enumerate(meshgen.SIDES["tri"]):
+        np.add.at(mid, es[:, k], coords[conn[:, list(sd)]].mean(axis=1))
+        np.add.at(cnt, es[:, k], 1)
+    mid /= cnt[:, None]
+    bnd = np.nonzero(cnt == 1)[0]                               # a boundary side has one element
+    lid = np.isclose(mid[bnd, 1], coords[:, 1].max())
+    dofs = np.concatenate([bnd * 2, bnd * 2 + 1, [n_side * 2]])            # u, v on the boundary sides + pressure of element 0
+    vals_bc = np.concatenate([lid.astype(np.float64), np.zeros(bnd.size), [0.0]])
+    order = np.argsort(dofs)
+    dofs, vals_bc = dofs[order], vals_bc[order]
+    disc.set_dirichlet(dofs)
+    u = torch.zeros(disc.num_dofs, dtype=torch.float64, device=dev)
+    disc.adjust_vector(u, vals_bc)
+    what = capi.JAC_A | capi.DEF_A
+    rowptr, colind = disc.csr()
+    rowptr_t, colind_t = torch.from_numpy(rowptr).to(dev), torch.from_numpy(colind.astype(np.int64)).to(dev)
+    hist = []
+    for it in range(40):
+        d = disc.assemble_resident(what, u)
+        disc.adjust_jacobian()
+        disc.adjust_vector(d)
+        dn = float(d.norm())
+        hist.append(dn)
+        if verbose:
+            print("iteration %2d   |defect| = %.3e" % (it, dn))
+        if dn < picard_tol * max(hist[0], 1e-300) or dn < 1e-13:
+            break
+        jv = _wrap(disc.resident_jacobian_ptr(), disc.nnz, dev)
+        du, res = direct_with_refinement(disc, jv, rowptr_t, colind_t, -d)
+        u = u + du
+    return disc, coords, conn, es, u, hist
+
+
 def _diag_index(rowptr, colind, dev):
     rows = np.repeat(np.arange(rowptr.size - 1), np.diff(rowptr))
     return torch.from_numpy(np.nonzero(colind == rows)[0]).to(dev)

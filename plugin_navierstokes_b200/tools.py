@@ -85,18 +85,44 @@ def evaluate_global(u, coords, conn, fct, points, nf=3):
     return out
 
 
-def _eval_at_points(u, coords, conn, fct, points, reference):
+def evaluate_global_cr(u, coords, conn, elem_sides, fct, points, dim=2):
+    """value of velocity component fct of a Crouzeix-Raviart grid function on triangles (FVCR layout side * dim + fct) at each point:
+    sum over the element sides of u_side * (1 - 2 lambda_o), lambda_o = barycentric coordinate of the corner opposite the side"""
+    from . import meshgen
+    u = np.asarray(u, dtype=np.float64)
+    sides = meshgen.SIDES["tri"]
+    opp = [[c for c in range(3) if c not in sd][0] for sd in sides]
+    xe_all = coords[conn]
+    lo, hi = xe_all.min(axis=1), xe_all.max(axis=1)
+    out = np.empty(len(points))
+    for i, pt in enumerate(np.asarray(points, dtype=np.float64)):
+        cand = np.nonzero(np.all((lo <= pt + 1e-12) & (hi >= pt - 1e-12), axis=1))[0]
+        vals = []
+        for e in cand:
+            xi = _local_coordinates(xe_all[e], pt)
+            if xi is None:
+                continue
+            lam = np.array([1 - xi[0] - xi[1], xi[0], xi[1]])
+            vals.append(sum(u[elem_sides[e, s] * dim + fct] * (1.0 - 2.0 * lam[opp[s]]) for s in range(3)))
+        if not vals:
+            raise ValueError("evaluate_global_cr: point %s is outside the grid" % (pt,))
+        out[i] = np.mean(vals)                            # CR functions jump across sides: a point on a side takes the mean of its elements
+    return out
+
+
+def _eval_at_points(u, coords, conn, fct, points, reference, elem_sides=None):
     """DrivenCavityEvalAtPoints (navier_stokes_tools.h:539-569): measured values, reference values, max and average difference"""
-    val = evaluate_global(u, coords, conn, fct, points)
+    val = evaluate_global(u, coords, conn, fct, points) if elem_sides is None else evaluate_global_cr(u, coords, conn, elem_sides, fct, points)
     ref = np.asarray(reference, dtype=np.float64)
     diff = np.abs(ref - val)
     return {"positions": np.asarray(points), "measure": val, "reference": ref, "max_diff": float(diff.max()), "average_diff": float(diff.mean())}
 
 
-def DrivenCavityLinesEval(u, coords, conn, Re, vel_cmp=(0, 1), log=None):
+def DrivenCavityLinesEval(u, coords, conn, Re, vel_cmp=(0, 1), log=None, elem_sides=None):
     """mirror of DrivenCavityLinesEval(u, {"u","v"}, Re): returns {source: {"vertical": {...}, "horizontal": {...}}} with the tables the
     reference prints (Ghia for Re in 100 / 400 / 1000, Botella & Peyret for Re = 1000); an unknown Re gives an empty dict, as the
-    reference prints nothing then. log: optional callable receiving the lines the reference writes with UG_LOG."""
+    reference prints nothing then. log: optional callable receiving the lines the reference writes with UG_LOG.
+    elem_sides: the grid function is Crouzeix-Raviart on triangles (FVCR layout), as the reference's function accepts both spaces."""
     Re = int(Re)
     out = {}
     vert_pts = [(GHIA_VERT_X, y) for y in GHIA_VERT_Y]
@@ -107,8 +133,8 @@ def DrivenCavityLinesEval(u, coords, conn, Re, vel_cmp=(0, 1), log=None):
     if Re == 1000:
         sources.append(("Botella/Peyret", _VERT_BOTELLA_1000, _HORIZ_BOTELLA_1000))
     for name, vert, horiz in sources:
-        res = {"vertical": _eval_at_points(u, coords, conn, vel_cmp[0], vert_pts, vert),
-               "horizontal": _eval_at_points(u, coords, conn, vel_cmp[1], horiz_pts, horiz)}
+        res = {"vertical": _eval_at_points(u, coords, conn, vel_cmp[0], vert_pts, vert, elem_sides),
+               "horizontal": _eval_at_points(u, coords, conn, vel_cmp[1], horiz_pts, horiz, elem_sides)}
         out[name] = res
         if log:
             for line, what in (("vertical", "u values on a vertical line through x = 0.5"), ("horizontal", "v values on a horizontal line through y = 0.5")):

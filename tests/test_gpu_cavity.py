@@ -56,3 +56,20 @@ def test_cavity_re100_reproduces_the_reference_ghia_tables():
     assert v64["max_diff"] < 0.015 and v64["average_diff"] < 0.006
     assert h64["max_diff"] < 0.010 and h64["average_diff"] < 0.003
     assert v64["max_diff"] < 0.6 * v32["max_diff"] and h64["max_diff"] < 0.6 * h32["max_diff"]
+
+
+def test_fvcr_cavity_re100_converges_to_the_reference_ghia_tables():
+    """the same known-answer check for NavierStokesFVCR (Crouzeix-Raviart velocities on triangle sides, FullUpwind, Dirichlet values on
+    the boundary sides): first-order convergence to the Ghia table of the reference (profiles/r2_cavity_ghia.txt: u on x = 0.5
+    max 0.072 / 0.046 / 0.026 at 16^2 / 32^2 / 64^2)"""
+    import cavity
+    from plugin_navierstokes_b200 import tools
+    res = {}
+    for cells in (16, 32):
+        disc, coords, conn, es, u, hist = cavity.solve_fvcr(cells, re=100.0, verbose=False, upwind="full")
+        assert hist[-1] < 1e-7 * hist[0]
+        res[cells] = tools.DrivenCavityLinesEval(u.cpu().numpy(), coords, conn, 100, elem_sides=es)["Ghia"]
+        disc.close()
+    assert res[32]["vertical"]["max_diff"] < 0.055 and res[32]["horizontal"]["max_diff"] < 0.11
+    assert res[32]["vertical"]["max_diff"] < 0.75 * res[16]["vertical"]["max_diff"]
+    assert res[32]["horizontal"]["max_diff"] < 0.75 * res[16]["horizontal"]["max_diff"]

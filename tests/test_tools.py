@@ -59,3 +59,19 @@ def test_driven_cavity_lines_eval_tables():
     assert any("Max Diff" in l for l in lines) and any("Ghia, Re = 100" in l for l in lines)
     assert set(tools.DrivenCavityLinesEval(u.reshape(-1), coords, conn, 1000)) == {"Ghia", "Botella/Peyret"}
     assert tools.DrivenCavityLinesEval(u.reshape(-1), coords, conn, 123) == {}
+
+
+def test_evaluate_global_cr_reproduces_linear_fields():
+    """a linear field interpolated at the side midpoints is reproduced exactly by the Crouzeix-Raviart evaluation"""
+    coords, conn = meshgen.make_mesh("tri", 7, jitter=0.2, seed=2)
+    es, n_side = meshgen.element_sides("tri", conn)
+    mid = np.zeros((n_side, 2)); cnt = np.zeros(n_side)
+    for k, sd in enumerate(meshgen.SIDES["tri"]):
+        np.add.at(mid, es[:, k], coords[conn[:, list(sd)]].mean(axis=1)); np.add.at(cnt, es[:, k], 1)
+    mid /= cnt[:, None]
+    u = np.zeros(n_side * 2 + conn.shape[0])
+    u[0:n_side * 2:2] = 1.0 + 0.5 * mid[:, 0] - 2.0 * mid[:, 1]
+    u[1:n_side * 2:2] = -0.25 * mid[:, 0]
+    pts = np.random.default_rng(5).uniform(0.03, 0.97, (25, 2))
+    assert np.allclose(tools.evaluate_global_cr(u, coords, conn, es, 0, pts), 1.0 + 0.5 * pts[:, 0] - 2.0 * pts[:, 1], atol=1e-12)
+    assert np.allclose(tools.evaluate_global_cr(u, coords, conn, es, 1, pts), -0.25 * pts[:, 0], atol=1e-12)

@@ -15,11 +15,16 @@ jit = float(os.environ.get("NSB_CAVITY_JITTER", "0"))
 for cells in sizes:
     for upw in ("lps", "full"):
         t0 = time.time()
-        disc, coords, conn, u, hist = cavity.solve(2, cells, re=re, verbose=False, upwind=upw, elem=elem, jitter=jit)
-        out = tools.DrivenCavityLinesEval(u.cpu().numpy(), coords, conn, int(re))
+        if os.environ.get("NSB_CAVITY_DISC") == "fvcr":        # NavierStokesFVCR on triangles
+            elem = "FVCR tri"
+            disc, coords, conn, es, u, hist = cavity.solve_fvcr(cells, re=re, verbose=False, upwind=upw, jitter=jit)
+            out = tools.DrivenCavityLinesEval(u.cpu().numpy(), coords, conn, int(re), elem_sides=es)
+        else:
+            disc, coords, conn, u, hist = cavity.solve(2, cells, re=re, verbose=False, upwind=upw, elem=elem, jitter=jit)
+            out = tools.DrivenCavityLinesEval(u.cpu().numpy(), coords, conn, int(re))
         for src, r in out.items():
             label = "%3d^2 %ss%s" % (cells, elem, " (jitter %.2f)" % jit if jit else "")
-            print("Re %4d  %s  %-4s upwind + FIELDS  %2d iterations (defect x %.1e)  %-14s u(0.5, y): max %.4f avg %.4f | v(x, 0.5): max %.4f avg %.4f  [%.1f s]"
-                  % (re, label, upw, len(hist) - 1, hist[-1] / hist[0], src, r["vertical"]["max_diff"], r["vertical"]["average_diff"],
+            print("Re %4d  %s  %-4s upwind%s  %2d iterations (defect x %.1e)  %-14s u(0.5, y): max %.4f avg %.4f | v(x, 0.5): max %.4f avg %.4f  [%.1f s]"
+                  % (re, label, upw, "" if elem.startswith("FVCR") else " + FIELDS", len(hist) - 1, hist[-1] / hist[0], src, r["vertical"]["max_diff"], r["vertical"]["average_diff"],
                      r["horizontal"]["max_diff"], r["horizontal"]["average_diff"], time.time() - t0), flush=True)
         disc.close()
