@@ -184,6 +184,57 @@ def solve_fvcr(cells=16, re=100.0, picard_tol=1e-8, verbose=True, upwind="full",
     return disc, coords, conn, es, u, hist
 
 
+def solve_extruded(elem="hex", cells=16, re=100.0, picard_tol=1e-8, verbose=True, upwind="lps"):
+    """the 2-D cavity on the 3-D element types: the unit square extruded by ONE cell in z (hexahedra, or their Kuhn split into six
+    tetrahedra), w = 0 at every node, no boundary disc on the two z faces (zero flux through them): the solution is the 2-D one,
+    constant in z, so the literature tables of DrivenCavityLinesEval apply to FV1 on hexahedra / tetrahedra as well.
+    Returns (disc, coords2d, conn2d, u2d, history): the z-averaged solution on the quadrilateral grid of the bottom layer, FV1 2-D
+    layout node * 3 + (u, v, p)."""
+    dev = torch.device("cuda", 0)
+    h = 1.0 / cells
+    gen = meshgen.hex_grid if elem == "hex" else meshgen.tet_grid
+    coords, conn = gen(cells, cells, 1, hi=(1.0, 1.0, h))
+    nf = 4
+    disc = pkg.NavierStokesFV1("u,v,w,p", "Inner")
+    disc.set_kinematic_viscosity(1.0 / re)
+    disc.set_upwind(upwind)
+    disc.set_stabilization("fields")
+    disc.set_grid(elem, conn, coords)
+    x, y = coords[:, 0], coords[:, 1]
+    wall = np.isclose(x, 0.0) | np.isclose(x, 1.0) | np.isclose(y, 0.0) | np.isclose(y, 1.0)
+    lid = np.isclose(y, 1.0)
+    wn = np.nonzero(wall)[0]
+    dofs = np.concatenate([wn * nf, wn * nf + 1, np.arange(coords.shape[0]) * nf + 2, [nf - 1]])
+    vals_bc = np.concatenate([lid[wn].astype(np.float64), np.zeros(wn.size), np.zeros(coords.shape[0]), [0.0]])
+    order = np.argsort(dofs)
+    dofs, vals_bc = dofs[order], vals_bc[order]
+    disc.set_dirichlet(dofs)
+    u = torch.zeros(disc.num_dofs, dtype=torch.float64, device=dev)
+    disc.adjust_vector(u, vals_bc)
+    what = capi.JAC_A | capi.DEF_A
+    rowptr, colind = disc.csr()
+    rowptr_t, colind_t = torch.from_numpy(rowptr).to(dev), torch.from_numpy(colind.astype(np.int64)).to(dev)
+    hist = []
+    for it in range(40):
+        d = disc.assemble_resident(what, u)
+        disc.adjust_jacobian()
+        disc.adjust_vector(d)
+        dn = float(d.norm())
+        hist.append(dn)
+        if verbose:
+            print("iteration %2d   |defect| = %.3e" % (it, dn))
+        if dn < picard_tol * max(hist[0], 1e-300) or dn < 1e-13:
+            break
+        jv = _wrap(disc.resident_jacobian_ptr(), disc.nnz, dev)
+        du, res = direct_with_refinement(disc, jv, rowptr_t, colind_t, -d)
+        u = u + du
+    n2 = (cells + 1) ** 2                                         # both generators number x fastest, then y, then z
+    uh = u.cpu().numpy().reshape(-1, nf)
+    u2d = 0.5 * (uh[:n2] + uh[n2:2 * n2])[:, [0, 1, 3]]
+    coords2d, conn2d = meshgen.quad_grid(cells, cells)
+    return disc, coords2d, conn2d, np.ascontiguousarray(u2d).reshape(-1), hist
+
+
 def _diag_index(rowptr, colind, dev):
     rows = np.repeat(np.arange(rowptr.size - 1), np.diff(rowptr))
     return torch.from_numpy(np.nonzero(colind == rows)[0]).to(dev)

@@ -73,3 +73,21 @@ def test_fvcr_cavity_re100_converges_to_the_reference_ghia_tables():
     assert res[32]["vertical"]["max_diff"] < 0.055 and res[32]["horizontal"]["max_diff"] < 0.11
     assert res[32]["vertical"]["max_diff"] < 0.75 * res[16]["vertical"]["max_diff"]
     assert res[32]["horizontal"]["max_diff"] < 0.75 * res[16]["horizontal"]["max_diff"]
+
+
+@pytest.mark.parametrize("elem", ["hex", "tet"])
+def test_extruded_cavity_pins_the_3d_element_types_to_the_ghia_tables(elem):
+    """FV1 on hexahedra / tetrahedra solving the 2-D problem (the square extruded by one cell in z, w = 0, zero flux through the
+    z faces): converges to the reference's Ghia table like the quadrilateral run (profiles/r2_cavity_ghia.txt: hex 0.046 / 0.027,
+    tet 0.027 / 0.015 at 16^2 / 32^2 for u on x = 0.5, LPS upwind)"""
+    import cavity
+    from plugin_navierstokes_b200 import tools
+    res = {}
+    for cells in (16, 32):
+        disc, c2, q2, u2, hist = cavity.solve_extruded(elem, cells, re=100.0, verbose=False, upwind="lps")
+        assert hist[-1] < 1e-7 * hist[0]
+        res[cells] = tools.DrivenCavityLinesEval(u2, c2, q2, 100)["Ghia"]
+        disc.close()
+    assert res[32]["vertical"]["max_diff"] < 0.032 and res[32]["horizontal"]["max_diff"] < 0.030
+    assert res[32]["vertical"]["max_diff"] < 0.7 * res[16]["vertical"]["max_diff"]
+    assert res[32]["horizontal"]["max_diff"] < 0.7 * res[16]["horizontal"]["max_diff"]

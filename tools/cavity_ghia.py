@@ -19,6 +19,10 @@ for cells in sizes:
             elem = "FVCR tri"
             disc, coords, conn, es, u, hist = cavity.solve_fvcr(cells, re=re, verbose=False, upwind=upw, jitter=jit)
             out = tools.DrivenCavityLinesEval(u.cpu().numpy(), coords, conn, int(re), elem_sides=es)
+        elif os.environ.get("NSB_CAVITY_DISC") in ("hex", "tet"):  # 3-D element types on the one-cell extrusion of the square
+            elem = "extruded " + os.environ["NSB_CAVITY_DISC"]
+            disc, coords, conn, u2d, hist = cavity.solve_extruded(os.environ["NSB_CAVITY_DISC"], cells, re=re, verbose=False, upwind=upw)
+            out = tools.DrivenCavityLinesEval(u2d, coords, conn, int(re))
         else:
             disc, coords, conn, u, hist = cavity.solve(2, cells, re=re, verbose=False, upwind=upw, elem=elem, jitter=jit)
             out = tools.DrivenCavityLinesEval(u.cpu().numpy(), coords, conn, int(re))
