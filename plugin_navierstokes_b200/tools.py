@@ -110,6 +110,38 @@ def evaluate_global_cr(u, coords, conn, elem_sides, fct, points, dim=2):
     return out
 
 
+def interpolateCRToLagrange(u_cr, coords, conn, elem_sides, n_side):
+    """mirror of interpolateCRToLagrange (navier_stokes_tools.h:53-229, registered as "CRToLagrange"): nodal (Lagrange P1) velocities
+    from a Crouzeix-Raviart function on simplices. Per element and corner i the CR function is evaluated at the local ip of the FV1
+    sub-control volume of the corner (:196-201), weighted with the SCV volume (:195, :205) and divided by the summed nodal volume at
+    the end (:216-228). u_cr: FVCR layout side * dim + d (pressures behind the velocities are ignored). Returns [n_node][dim]."""
+    from . import meshgen
+    coords = np.asarray(coords, dtype=np.float64)
+    dim = coords.shape[1]
+    nco = dim + 1
+    elem = "tri" if dim == 2 else "tet"
+    if conn.shape[1] != nco:
+        raise ValueError("interpolateCRToLagrange: simplices only")
+    sides = meshgen.SIDES[elem]
+    opp = [[c for c in range(nco) if c not in sd][0] for sd in sides]
+    # barycentric coordinates of the SCV ip of corner i = mean of the SCV corners (node, edge midpoints, (face centres,) barycentre)
+    own, other = (7.0 / 12.0, 5.0 / 24.0) if dim == 2 else (15.0 / 32.0, 17.0 / 96.0)
+    vel = np.asarray(u_cr, dtype=np.float64)[:n_side * dim].reshape(n_side, dim)
+    x = coords[conn]                                       # [ne][nco][dim]
+    e = x[:, 1:, :] - x[:, :1, :]
+    vol = np.abs(np.linalg.det(e)) / (2.0 if dim == 2 else 6.0)
+    scv = vol / nco                                        # simplex: every SCV holds 1 / (dim + 1) of the element
+    out = np.zeros((coords.shape[0], dim))
+    vsum = np.zeros(coords.shape[0])
+    us = vel[elem_sides]                                   # [ne][nside][dim]
+    for i in range(nco):
+        lam = np.full(nco, other); lam[i] = own
+        shape = np.array([1.0 - dim * lam[opp[s]] for s in range(len(sides))])      # CR shapes at the SCV ip
+        np.add.at(out, conn[:, i], scv[:, None] * np.einsum("s,esd->ed", shape, us))
+        np.add.at(vsum, conn[:, i], scv)
+    return out / vsum[:, None]
+
+
 def _eval_at_points(u, coords, conn, fct, points, reference, elem_sides=None):
     """DrivenCavityEvalAtPoints (navier_stokes_tools.h:539-569): measured values, reference values, max and average difference"""
     val = evaluate_global(u, coords, conn, fct, points) if elem_sides is None else evaluate_global_cr(u, coords, conn, elem_sides, fct, points)

@@ -75,3 +75,43 @@ def test_evaluate_global_cr_reproduces_linear_fields():
     pts = np.random.default_rng(5).uniform(0.03, 0.97, (25, 2))
     assert np.allclose(tools.evaluate_global_cr(u, coords, conn, es, 0, pts), 1.0 + 0.5 * pts[:, 0] - 2.0 * pts[:, 1], atol=1e-12)
     assert np.allclose(tools.evaluate_global_cr(u, coords, conn, es, 1, pts), -0.25 * pts[:, 0], atol=1e-12)
+
+
+@pytest.mark.parametrize("elem", ["tri", "tet"])
+def test_interpolate_cr_to_lagrange(elem):
+    """against a plain loop over elements / corners / sides with the SCV ip built from the SCV corners (navier_stokes_tools.h:149-228)"""
+    n = 5 if elem == "tri" else 3
+    coords, conn = meshgen.make_mesh(elem, n, jitter=0.2, seed=6)
+    es, n_side = meshgen.element_sides(elem, conn)
+    dim = coords.shape[1]
+    rng = np.random.default_rng(2)
+    u = np.concatenate([rng.uniform(-1, 1, n_side * dim), rng.uniform(-1, 1, conn.shape[0])])
+    got = tools.interpolateCRToLagrange(u, coords, conn, es, n_side)
+    sides = meshgen.SIDES[elem]
+    nco = dim + 1
+    ref = np.zeros((coords.shape[0], dim)); vs = np.zeros(coords.shape[0])
+    import itertools
+    for e in range(conn.shape[0]):
+        x = coords[conn[e]]
+        vol = abs(np.linalg.det(x[1:] - x[0])) / (2.0 if dim == 2 else 6.0)
+        for i in range(nco):
+            # SCV corners in barycentric coordinates: the node, the midpoints of its edges, (the centres of its faces,) the barycentre
+            pts = [np.eye(nco)[i]]
+            for j in range(nco):
+                if j != i:
+                    b = np.zeros(nco); b[[i, j]] = 0.5; pts.append(b)
+            if dim == 3:
+                for j, k in itertools.combinations([c for c in range(nco) if c != i], 2):
+                    b = np.zeros(nco); b[[i, j, k]] = 1.0 / 3.0; pts.append(b)
+            pts.append(np.full(nco, 1.0 / nco))
+            lam = np.mean(pts, axis=0)
+            val = np.zeros(dim)
+            for s, sd in enumerate(sides):
+                o = [c for c in range(nco) if c not in sd][0]
+                val += (1.0 - dim * lam[o]) * u[es[e, s] * dim:es[e, s] * dim + dim]
+            ref[conn[e, i]] += vol / nco * val; vs[conn[e, i]] += vol / nco
+    ref /= vs[:, None]
+    assert np.allclose(got, ref, atol=1e-13)
+    # a constant field is reproduced
+    uc = np.concatenate([np.tile([0.7, -0.2, 0.4][:dim], n_side), np.zeros(conn.shape[0])])
+    assert np.allclose(tools.interpolateCRToLagrange(uc, coords, conn, es, n_side), [0.7, -0.2, 0.4][:dim], atol=1e-13)
