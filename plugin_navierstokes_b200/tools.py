@@ -142,6 +142,102 @@ def interpolateCRToLagrange(u_cr, coords, conn, elem_sides, n_side):
     return out / vsum[:, None]
 
 
+_REF_CORNERS = {
+    "tri": np.array([(0, 0), (1, 0), (0, 1)], dtype=np.float64),
+    "quad": np.array([(0, 0), (1, 0), (1, 1), (0, 1)], dtype=np.float64),
+    "tet": np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], dtype=np.float64),
+    "hex": np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)], dtype=np.float64),
+}
+
+
+def _lagrange(elem, xi):
+    """P1 / Q1 shapes and local gradients at the local point xi"""
+    rc = _REF_CORNERS[elem]
+    if elem in ("tri", "tet"):
+        N = np.concatenate([[1.0 - xi.sum()], xi])
+        dN = np.vstack([-np.ones(len(xi)), np.eye(len(xi))])
+        return N, dN
+    f = np.where(rc > 0.5, xi, 1.0 - xi)                   # [nsh][dim] factors
+    sg = np.where(rc > 0.5, 1.0, -1.0)
+    N = f.prod(axis=1)
+    dN = np.empty_like(f)
+    for d in range(rc.shape[1]):
+        other = np.delete(f, d, axis=1).prod(axis=1)
+        dN[:, d] = sg[:, d] * other
+    return N, dN
+
+
+def _side_rule(n_corner, order):
+    """quadrature on the reference side: Gauss-Legendre on [0, 1], its tensor product on the unit square, or a symmetric rule on the
+    unit triangle (degree 1 or 2), exact for polynomials of the requested order -> (points [n][dim-1], weights [n])"""
+    ng = max(1, order // 2 + 1)
+    g, w = np.polynomial.legendre.leggauss(ng)
+    g, w = 0.5 * (g + 1.0), 0.5 * w
+    if n_corner == 2:
+        return g[:, None], w
+    if n_corner == 4:
+        P = np.array([(a, b) for a in g for b in g]); W = np.array([wa * wb for wa in w for wb in w])
+        return P, W
+    if order <= 1:
+        return np.array([[1.0 / 3.0, 1.0 / 3.0]]), np.array([0.5])
+    if order <= 2:
+        return np.array([[1.0 / 6.0, 1.0 / 6.0], [2.0 / 3.0, 1.0 / 6.0], [1.0 / 6.0, 2.0 / 3.0]]), np.full(3, 1.0 / 6.0)
+    raise ValueError("DragLift: triangle sides are integrated with rules up to order 2")
+
+
+def DragLift(u, coords, conn, elem, belem, bside, kin_visco, density, quad_order=2):
+    """mirror of DragLift(u, "u,v(,w),p", BndSubsets, InnerSubsets, kinVisco, density, quadOrder) (navier_stokes_tools.h:981-1228) for
+    FV1 grid functions (layout node * (dim + 1) + fct): boundary integral over the given sides (belem, bside) = (element, local side),
+    e.g. from meshgen.boundary_sides(where=...), with the INNER normal n (:1122-1124) and the tangent t = (n[dim-1], .., -n[0])
+    (:1127-1129):   drag += w det ( nu rho (grad u n) . t  n[dim-1] - p n[0] ),   lift -= w det ( nu rho (grad u n) . t  n[0] + p n[dim-1] )
+    (:1200-1206). Returns [drag, lift]."""
+    from . import meshgen
+    coords = np.asarray(coords, dtype=np.float64)
+    dim = coords.shape[1]
+    nf = dim + 1
+    uu = np.asarray(u, dtype=np.float64).reshape(-1, nf)
+    rc = _REF_CORNERS[elem]
+    drag = lift = 0.0
+    for e, sd in zip(np.asarray(belem), np.asarray(bside)):
+        cs = list(meshgen.SIDES[elem][sd])
+        xe = coords[conn[e]]                               # element corners
+        ue = uu[conn[e]]
+        xs, ls = xe[cs], rc[cs]                            # side corners, global and local
+        P, W = _side_rule(len(cs), quad_order)
+        for q, wq in zip(P, W):
+            # point on the reference side -> local element coordinates -> shapes; side Jacobian for the surface measure
+            if len(cs) == 2:
+                sh = np.array([1.0 - q[0], q[0]]); dsh = np.array([[-1.0], [1.0]])
+            elif len(cs) == 3:
+                sh = np.array([1.0 - q[0] - q[1], q[0], q[1]]); dsh = np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])
+            else:
+                a, b = q
+                sh = np.array([(1 - a) * (1 - b), a * (1 - b), a * b, (1 - a) * b])
+                dsh = np.array([[-(1 - b), -(1 - a)], [(1 - b), -a], [b, a], [-b, (1 - a)]])
+            xi = sh @ ls
+            JTs = dsh.T @ xs                               # [dim-1][dim]
+            det = np.sqrt(np.linalg.det(JTs @ JTs.T))      # SqrtGramDeterminant
+            if dim == 2:
+                nrm = np.array([JTs[0, 1], -JTs[0, 0]])
+            else:
+                nrm = np.cross(JTs[0], JTs[1])
+            nrm /= np.linalg.norm(nrm)
+            if nrm @ (xs.mean(axis=0) - xe.mean(axis=0)) < 0:      # outer normal of the element at this side ...
+                nrm = -nrm
+            nrm = -nrm                                     # ... turned into the inner one (:1124)
+            tng = np.zeros(dim); tng[0] = nrm[dim - 1]; tng[dim - 1] = -nrm[0]
+            N, dN = _lagrange(elem, xi)
+            JT = dN.T @ xe                                 # [dim][dim]
+            G = dN @ np.linalg.inv(JT).T                   # global gradients [nsh][dim]
+            grad_vel = ue[:, :dim].T @ G                   # (d1, d2) = d u_d1 / d x_d2
+            pressure = N @ ue[:, dim]
+            flux = grad_vel @ nrm
+            shear = kin_visco * density * (flux @ tng)
+            drag += wq * det * (shear * nrm[dim - 1] - pressure * nrm[0])
+            lift -= wq * det * (shear * nrm[0] + pressure * nrm[dim - 1])
+    return [drag, lift]
+
+
 def _eval_at_points(u, coords, conn, fct, points, reference, elem_sides=None):
     """DrivenCavityEvalAtPoints (navier_stokes_tools.h:539-569): measured values, reference values, max and average difference"""
     val = evaluate_global(u, coords, conn, fct, points) if elem_sides is None else evaluate_global_cr(u, coords, conn, elem_sides, fct, points)

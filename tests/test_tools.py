@@ -115,3 +115,29 @@ def test_interpolate_cr_to_lagrange(elem):
     # a constant field is reproduced
     uc = np.concatenate([np.tile([0.7, -0.2, 0.4][:dim], n_side), np.zeros(conn.shape[0])])
     assert np.allclose(tools.interpolateCRToLagrange(uc, coords, conn, es, n_side), [0.7, -0.2, 0.4][:dim], atol=1e-13)
+
+
+@pytest.mark.parametrize("elem", ["tri", "quad", "tet", "hex"])
+def test_drag_lift_on_analytic_fields(elem):
+    """DragLift mirror (navier_stokes_tools.h:981-1228) on fields the P1 / Q1 space holds exactly: linear pressure over the whole
+    outer boundary of the unit box, Couette shear on the bottom wall"""
+    n = 6 if elem in ("tri", "quad") else 3
+    coords, conn = meshgen.make_mesh(elem, n, jitter=0.15, seed=3)
+    dim = coords.shape[1]
+    nf = dim + 1
+    a, b, c, nu, rho = 0.7, -0.4, 1.3, 0.05, 1.2
+    last = dim - 1
+    u = np.zeros((coords.shape[0], nf))
+    u[:, dim] = 2.0 + a * coords[:, 0] + b * coords[:, last]
+    be, bs = meshgen.boundary_sides(elem, conn)
+    drag, lift = tools.DragLift(u.reshape(-1), coords, conn, elem, be, bs, nu, rho, quad_order=2)
+    # - int p n_x with the inner normal: int (p(1, .) - p(0, .)) = a ; lift likewise = b
+    assert abs(drag - a) < 1e-12 and abs(lift - b) < 1e-12
+    # Couette flow u = (c x_last, 0, ..), constant pressure, bottom wall only: inner normal e_last, t = (1, .., 0):
+    # drag = nu rho c * area, lift = -p * area
+    u = np.zeros((coords.shape[0], nf))
+    u[:, 0] = c * coords[:, last]
+    u[:, dim] = 0.3
+    be, bs = meshgen.boundary_sides(elem, conn, coords, where=lambda x: np.isclose(x[:, last], 0.0))
+    drag, lift = tools.DragLift(u.reshape(-1), coords, conn, elem, be, bs, nu, rho, quad_order=2)
+    assert abs(drag - nu * rho * c) < 1e-12 and abs(lift + 0.3) < 1e-12
