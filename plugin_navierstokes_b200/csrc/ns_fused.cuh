@@ -160,7 +160,7 @@ template <int E> NSB_DEV void fused_stage_tables(const FusedSmem<E>& S, int tid,
         const int ip = i / 12, j = i - ip * 12;
         int v = 0;
         if (j < 2) v = tab::EDGE[E][ip][j];
-        else if (DIM == 3) v = (j < 6) ? tab::SIDE[E][tab::SCVF_FA[E][ip]][j - 2] : tab::SIDE[E][tab::SCVF_FB[E][ip]][j - 6];
+        else if (DIM == 3 && j < 10) v = (j < 6) ? tab::SIDE[E][tab::SCVF_FA[E][ip]][j - 2] : tab::SIDE[E][tab::SCVF_FB[E][ip]][j - 6];   // slots 10, 11 are padding
         S.iptab[i] = v < 0 ? 0 : v;
     }
     for (int i = tid; i < NSH * NINC; i += nthreads)

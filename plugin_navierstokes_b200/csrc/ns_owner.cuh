@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(NT, MINB) fv1_flux_kernel(KParams p, MeshDev m
             const int ip = i / 12, j = i - ip * 12;
             int v = 0;
             if (j < 2) v = tab::EDGE[E][ip][j];
-            else if (DIM == 3) v = (j < 6) ? tab::SIDE[E][tab::SCVF_FA[E][ip]][j - 2] : tab::SIDE[E][tab::SCVF_FB[E][ip]][j - 6];
+            else if (DIM == 3 && j < 10) v = (j < 6) ? tab::SIDE[E][tab::SCVF_FA[E][ip]][j - 2] : tab::SIDE[E][tab::SCVF_FB[E][ip]][j - 6];   // slots 10, 11 are padding
             iptab[i] = v < 0 ? 0 : v;
         }
     }
@@ -911,6 +911,7 @@ __global__ void __launch_bounds__(96, MINB) fv1_rows_kernel(KParams p, MeshDev m
         const int64_t b0 = m.brow[a];
         const int cnt = (int)(m.brow[a + 1] - b0);
         const int rowlen = cnt * NF;
+        __syncwarp();                                            // every lane has read the previous node's rows out of rowacc (compute-sanitizer racecheck)
         if (want_jac) for (int i = lane; i < NF * rowlen; i += 32) rowacc[i] = 0.0;
         double fsum[NF], vsum = 0.0;                             // per-lane partial defect fluxes / SCV volumes
 #pragma unroll

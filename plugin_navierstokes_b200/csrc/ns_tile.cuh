@@ -151,7 +151,7 @@ template <int E> __device__ __forceinline__ void tile_stage_tables(const TileSme
         const int ip = i / 12, j = i - ip * 12;
         int v = 0;
         if (j < 2) v = tab::EDGE[E][ip][j];
-        else v = (j < 6) ? tab::SIDE[E][tab::SCVF_FA[E][ip]][j - 2] : tab::SIDE[E][tab::SCVF_FB[E][ip]][j - 6];
+        else if (j < 10) v = (j < 6) ? tab::SIDE[E][tab::SCVF_FA[E][ip]][j - 2] : tab::SIDE[E][tab::SCVF_FB[E][ip]][j - 6];   // slots 10, 11 are padding
         S.iptab[i] = v < 0 ? 0 : v;
     }
     for (int i = tid; i < NSH * NINC; i += nthreads)
