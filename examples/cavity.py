@@ -68,7 +68,7 @@ def direct_with_refinement(disc, jv, rowptr_t, colind_t, b, steps=2):
     return x, float(r.norm()) / max(float(b.norm()), 1e-300)
 
 
-def solve(dim=2, cells=16, re=100.0, picard_tol=1e-8, verbose=True, linear="direct", upwind=None, elem=None, jitter=0.0):
+def solve(dim=2, cells=16, re=100.0, picard_tol=1e-8, verbose=True, linear="direct", upwind=None, elem=None, jitter=0.0, stab="fields"):
     """upwind: default FullUpwind in 2-D (config 1), LinearProfileSkewedUpwind in 3-D (config 3; on coarse 3-D grids the fixed-point
     iteration with FullUpwind ends in a 2-cycle when a face flux changes sign -- the upwind corner jumps, the LPS cut point moves
     continuously)"""
@@ -87,7 +87,7 @@ def solve(dim=2, cells=16, re=100.0, picard_tol=1e-8, verbose=True, linear="dire
     disc = pkg.NavierStokesFV1(fcts, "Inner")
     disc.set_kinematic_viscosity(1.0 / re)
     disc.set_upwind(upwind)
-    disc.set_stabilization("fields")
+    disc.set_stabilization(stab)
     disc.set_grid(elem, conn, coords)
     # boundary conditions: no-slip walls, moving lid (top), one pressure dof pinned (all-Dirichlet velocity problem)
     lo, hi = coords.min(axis=0), coords.max(axis=0)
