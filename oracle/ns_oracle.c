@@ -47,7 +47,7 @@ typedef struct {
     int ready;
 } RefElem;
 
-static RefElem g_ref[4];
+static RefElem g_ref[5];
 
 static const double TRI_CO[3][3]  = {{0,0,0},{1,0,0},{0,1,0}};
 static const double QUAD_CO[4][3] = {{0,0,0},{1,0,0},{1,1,0},{0,1,0}};
@@ -59,11 +59,16 @@ static const int TET_ED[6][2]  = {{0,1},{1,2},{2,0},{0,3},{1,3},{2,3}};
 static const int HEX_ED[12][2] = {{0,1},{1,2},{2,3},{3,0},{0,4},{1,5},{2,6},{3,7},{4,5},{5,6},{6,7},{7,4}};
 static const int TET_FA[4][4]  = {{0,2,1,-1},{1,2,3,-1},{0,3,2,-1},{0,1,3,-1}};
 static const int HEX_FA[6][4]  = {{0,3,2,1},{0,1,5,4},{1,2,6,5},{2,3,7,6},{3,0,4,7},{4,5,6,7}};
+/* prism (ugcore ReferencePrism: bottom triangle 0,1,2, top triangle 3,4,5; sides: bottom, three quadrilaterals, top) */
+static const double PRISM_CO[6][3] = {{0,0,0},{1,0,0},{0,1,0},{0,0,1},{1,0,1},{0,1,1}};
+static const int PRISM_ED[9][2] = {{0,1},{1,2},{2,0},{0,3},{1,4},{2,5},{3,4},{4,5},{5,3}};
+static const int PRISM_FA[5][4] = {{0,2,1,-1},{0,1,4,3},{1,2,5,4},{2,0,3,5},{3,4,5,-1}};
+static const int PRISM_FN[5]    = {3,4,4,4,3};
 
-int ora_elem_nsh(int e)  { static const int v[4] = {3,4,4,8};  return (e>=0&&e<4)? v[e] : -1; }
-int ora_elem_nip(int e)  { static const int v[4] = {3,4,6,12}; return (e>=0&&e<4)? v[e] : -1; }
-int ora_elem_dim(int e)  { static const int v[4] = {2,2,3,3};  return (e>=0&&e<4)? v[e] : -1; }
-int ora_elem_nside(int e){ static const int v[4] = {3,4,4,6};  return (e>=0&&e<4)? v[e] : -1; }
+int ora_elem_nsh(int e)  { static const int v[5] = {3,4,4,8,6};  return (e>=0&&e<5)? v[e] : -1; }
+int ora_elem_nip(int e)  { static const int v[5] = {3,4,6,12,9}; return (e>=0&&e<5)? v[e] : -1; }
+int ora_elem_dim(int e)  { static const int v[5] = {2,2,3,3,3};  return (e>=0&&e<5)? v[e] : -1; }
+int ora_elem_nside(int e){ static const int v[5] = {3,4,4,6,5};  return (e>=0&&e<5)? v[e] : -1; }
 
 /* P1/Q1 Lagrange shapes and local gradients (ugcore LagrangeP1<RefElem>) */
 static void lagrange_shapes(int elem, const double *xi, double *N, double (*dN)[3])
@@ -96,6 +101,15 @@ static void lagrange_shapes(int elem, const double *xi, double *N, double (*dN)[
             if (dN) { dN[i][0]=sx*fy*fz; dN[i][1]=fx*sy*fz; dN[i][2]=fx*fy*sz; }
         }
         break;
+    case ORA_PRISM: {
+        /* P1 on the triangle times P1 along the axis (ugcore LagrangeP1<ReferencePrism>) */
+        const double l[3] = {1-x-y, x, y}, dl[3][2] = {{-1,-1},{1,0},{0,1}};
+        for (i = 0; i < 6; i++) {
+            const int t = i % 3; const double fz = i < 3 ? 1-z : z, sz = i < 3 ? -1.0 : 1.0;
+            N[i] = l[t]*fz;
+            if (dN) { dN[i][0]=dl[t][0]*fz; dN[i][1]=dl[t][1]*fz; dN[i][2]=l[t]*sz; }
+        }
+        break; }
     }
 }
 
@@ -141,7 +155,7 @@ static void scvf_normal(int dim, const double (*c)[3], double *n)
 
 static const RefElem *get_ref(int elem)
 {
-    if (elem < 0 || elem > 3) return NULL;
+    if (elem < 0 || elem > 4) return NULL;
     RefElem *r = &g_ref[elem];
     if (r->ready) return r;
 #pragma omp critical(ora_ref_init)
@@ -151,14 +165,15 @@ static const RefElem *get_ref(int elem)
         t.nside = ora_elem_nside(elem);
         for (int i = 0; i < t.nsh; i++) for (int d = 0; d < 3; d++)
             t.corner[i][d] = elem==ORA_TRI ? TRI_CO[i][d] : elem==ORA_QUAD ? QUAD_CO[i][d]
-                           : elem==ORA_TET ? TET_CO[i][d] : HEX_CO[i][d];
+                           : elem==ORA_TET ? TET_CO[i][d] : elem==ORA_HEX ? HEX_CO[i][d] : PRISM_CO[i][d];
         for (int i = 0; i < t.nedge; i++) for (int k = 0; k < 2; k++)
             t.edge[i][k] = elem==ORA_TRI ? TRI_ED[i][k] : elem==ORA_QUAD ? QUAD_ED[i][k]
-                         : elem==ORA_TET ? TET_ED[i][k] : HEX_ED[i][k];
+                         : elem==ORA_TET ? TET_ED[i][k] : elem==ORA_HEX ? HEX_ED[i][k] : PRISM_ED[i][k];
         for (int s = 0; s < t.nside; s++) {
             if (t.dim == 2) { t.side_n[s] = 2; t.side[s][0] = t.edge[s][0]; t.side[s][1] = t.edge[s][1]; }
             else if (elem == ORA_TET) { t.side_n[s] = 3; for (int k=0;k<3;k++) t.side[s][k] = TET_FA[s][k]; }
-            else { t.side_n[s] = 4; for (int k=0;k<4;k++) t.side[s][k] = HEX_FA[s][k]; }
+            else if (elem == ORA_HEX) { t.side_n[s] = 4; for (int k=0;k<4;k++) t.side[s][k] = HEX_FA[s][k]; }
+            else { t.side_n[s] = PRISM_FN[s]; for (int k=0;k<4;k++) t.side[s][k] = PRISM_FA[s][k]; }
         }
         for (int ip = 0; ip < t.nedge; ip++) {
             if (t.dim == 3) {
@@ -285,6 +300,31 @@ static int geom_update(Geom *g, int elem, const double *coords)
             /* 0.5*|(c2-c0) x (c3-c1)| with c = (corner, m1, bary, m2) */
             double ax = bc[0]-g->x[i][0], ay = bc[1]-g->x[i][1], bx = m2[0]-m1[0], by = m2[1]-m1[1];
             g->vol[i] = 0.5*fabs(ax*by - ay*bx);
+        }
+    } else if (elem == ORA_PRISM) {
+        /* SCV of corner i = hexahedron (corner, edge midpoint, triangle centre, edge midpoint | axis-edge midpoint, quadrilateral
+           centre, barycentre, quadrilateral centre); volume of the trilinear hexahedron through these eight points */
+        int all[6] = {0,1,2,3,4,5}; double bc[3]; avg_pts(bc, g->x, all, 6, 3);
+        for (int i = 0; i < 6; i++) {
+            const int base = i < 3 ? 0 : 3, t = i - base, a = base + (t+1)%3, b = base + (t+2)%3, up = i < 3 ? i+3 : i-3;
+            const int tri = i < 3 ? 0 : 4;
+            int qa = -1, qb = -1;
+            for (int s2 = 1; s2 <= 3; s2++) {
+                int hi = 0, ha = 0, hb = 0;
+                for (int k = 0; k < 4; k++) { hi |= r->side[s2][k]==i; ha |= r->side[s2][k]==a; hb |= r->side[s2][k]==b; }
+                if (hi && ha) qa = s2;
+                if (hi && hb) qb = s2;
+            }
+            double p[8][3]; int e2[2];
+            for (int d = 0; d < 3; d++) p[0][d] = g->x[i][d];
+            e2[0] = i; e2[1] = a;  avg_pts(p[1], g->x, e2, 2, 3);
+            avg_pts(p[2], g->x, r->side[tri], 3, 3);
+            e2[1] = b;             avg_pts(p[3], g->x, e2, 2, 3);
+            e2[1] = up;            avg_pts(p[4], g->x, e2, 2, 3);
+            avg_pts(p[5], g->x, r->side[qa], 4, 3);
+            for (int d = 0; d < 3; d++) p[6][d] = bc[d];
+            avg_pts(p[7], g->x, r->side[qb], 4, 3);
+            g->vol[i] = fabs(hex_volume(p));
         }
     } else {
         /* SCV of corner i = trilinear image of the reference octant adjacent to corner i */

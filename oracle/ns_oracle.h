@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-enum { ORA_TRI = 0, ORA_QUAD = 1, ORA_TET = 2, ORA_HEX = 3 };
+enum { ORA_TRI = 0, ORA_QUAD = 1, ORA_TET = 2, ORA_HEX = 3, ORA_PRISM = 4 };
 enum { ORA_UPWIND_NONE = 0, ORA_UPWIND_NO = 1, ORA_UPWIND_FULL = 2, ORA_UPWIND_SKEWED = 3,
        ORA_UPWIND_LPS = 4, ORA_UPWIND_POSITIVE = 5 };
 enum { ORA_STAB_FIELDS = 0, ORA_STAB_FLOW = 1, ORA_STAB_NONE = 2 };
@@ -36,7 +36,7 @@ enum { ORA_JAC_A = 1, ORA_DEF_A = 2, ORA_JAC_M = 4, ORA_DEF_M = 8, ORA_RHS = 16 
  *  fv1/navier_stokes_fv1.cpp:62-87, fvcr/navier_stokes_fvcr.cpp:63-88). */
 typedef struct {
     int32_t disc;          /* ORA_DISC_*                                             */
-    int32_t elem;          /* ORA_TRI..ORA_HEX                                       */
+    int32_t elem;          /* ORA_TRI..ORA_PRISM                                      */
     int32_t conv_upwind;   /* upwind of the convective term (m_spConvUpwind)         */
     int32_t stab;          /* FV1 stabilisation (m_spStab)                           */
     int32_t stab_upwind;   /* upwind attached to the stabilisation (stab->upwind())  */

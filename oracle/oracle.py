@@ -12,17 +12,17 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libns_oracle.so")
 
-TRI, QUAD, TET, HEX = 0, 1, 2, 3
-ELEM = {"tri": TRI, "quad": QUAD, "tet": TET, "hex": HEX}
+TRI, QUAD, TET, HEX, PRISM = 0, 1, 2, 3, 4
+ELEM = {"tri": TRI, "quad": QUAD, "tet": TET, "hex": HEX, "prism": PRISM}
 UPWIND = {None: 0, "none": 0, "no": 1, "full": 2, "skewed": 3, "lps": 4, "linearprofileskewed": 4,
           "positive": 5, "pos": 5}
 STAB = {"fields": 0, "flow": 1, "none": 2}
 DIFF = {"raw": 0, "fivepoint": 1, "cor": 2}
 JAC_A, DEF_A, JAC_M, DEF_M, RHS = 1, 2, 4, 8, 16
-NSH = {TRI: 3, QUAD: 4, TET: 4, HEX: 8}
-NIP = {TRI: 3, QUAD: 4, TET: 6, HEX: 12}
-DIM = {TRI: 2, QUAD: 2, TET: 3, HEX: 3}
-NSIDE = {TRI: 3, QUAD: 4, TET: 4, HEX: 6}
+NSH = {TRI: 3, QUAD: 4, TET: 4, HEX: 8, PRISM: 6}
+NIP = {TRI: 3, QUAD: 4, TET: 6, HEX: 12, PRISM: 9}
+DIM = {TRI: 2, QUAD: 2, TET: 3, HEX: 3, PRISM: 3}
+NSIDE = {TRI: 3, QUAD: 4, TET: 4, HEX: 6, PRISM: 5}
 
 
 class Params(C.Structure):

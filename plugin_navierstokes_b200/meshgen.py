@@ -8,8 +8,8 @@ import itertools
 
 import numpy as np
 
-ELEM_NSH = {"tri": 3, "quad": 4, "tet": 4, "hex": 8}
-ELEM_DIM = {"tri": 2, "quad": 2, "tet": 3, "hex": 3}
+ELEM_NSH = {"tri": 3, "quad": 4, "tet": 4, "hex": 8, "prism": 6}
+ELEM_DIM = {"tri": 2, "quad": 2, "tet": 3, "hex": 3, "prism": 3}
 
 # sides of the reference elements (corner lists), SURVEY App. B-1
 SIDES = {
@@ -17,6 +17,7 @@ SIDES = {
     "quad": [(0, 1), (1, 2), (2, 3), (3, 0)],
     "tet": [(0, 2, 1), (1, 2, 3), (0, 3, 2), (0, 1, 3)],
     "hex": [(0, 3, 2, 1), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7), (4, 5, 6, 7)],
+    "prism": [(0, 2, 1), (0, 1, 4, 3), (1, 2, 5, 4), (2, 0, 3, 5), (3, 4, 5)],
 }
 
 
@@ -111,6 +112,14 @@ def tet_grid(nx, ny, nz, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), jitter=0.0, see
     return coords, conn
 
 
+def prism_grid(nx, ny, nz, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), jitter=0.0, seed=0):
+    """every cell of the structured grid split into two prisms along the diagonal 0-2 of its bottom face (prism corner order:
+    bottom triangle counter-clockwise, then the top triangle above it)"""
+    coords, hexes = hex_grid(nx, ny, nz, lo, hi, jitter, seed)
+    conn = hexes[:, [[0, 1, 2, 4, 5, 6], [0, 2, 3, 4, 6, 7]]].reshape(-1, 6).astype(np.int32)
+    return coords, conn
+
+
 def make_mesh(elem, n, **kw):
     """convenience: n elements per direction (tri/tet: n cells, split)."""
     if elem == "quad":
@@ -121,6 +130,8 @@ def make_mesh(elem, n, **kw):
         return hex_grid(n, n, n, **kw)
     if elem == "tet":
         return tet_grid(n, n, n, **kw)
+    if elem == "prism":
+        return prism_grid(n, n, n, **kw)
     raise ValueError(elem)
 
 
@@ -191,9 +202,11 @@ def random_state(n, nf, seed=0, scale=1.0):
 # ----------------------------------------------------------------------------------------------------
 _EDGES = {"tri": [(0, 1), (1, 2), (2, 0)], "quad": [(0, 1), (1, 2), (2, 3), (3, 0)],
           "tet": [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)],
-          "hex": [(0, 1), (1, 2), (2, 3), (3, 0), (0, 4), (1, 5), (2, 6), (3, 7), (4, 5), (5, 6), (6, 7), (7, 4)]}
+          "hex": [(0, 1), (1, 2), (2, 3), (3, 0), (0, 4), (1, 5), (2, 6), (3, 7), (4, 5), (5, 6), (6, 7), (7, 4)],
+          "prism": [(0, 1), (1, 2), (2, 0), (0, 3), (1, 4), (2, 5), (3, 4), (4, 5), (5, 3)]}
 _FACES = {"tet": [(0, 2, 1), (1, 2, 3), (0, 3, 2), (0, 1, 3)],
-          "hex": [(0, 3, 2, 1), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7), (4, 5, 6, 7)]}
+          "hex": [(0, 3, 2, 1), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7), (4, 5, 6, 7)],
+          "prism": SIDES["prism"]}
 
 
 def fv1_scvf_ips(elem, conn, coords):

@@ -28,6 +28,7 @@ def jittered_ref_element(elem, seed=0, amp=0.15, scale=1.0, shift=0.0):
         "quad": [[0, 0], [1, 0], [1, 1], [0, 1]],
         "tet": [[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]],
         "hex": [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]],
+        "prism": [[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [0, 1, 1]],
     }[elem]
     x = np.array(ref, dtype=float)
     rng = np.random.default_rng(seed)

@@ -8,7 +8,7 @@ import pytest
 
 from tests.conftest import jittered_ref_element
 
-ELEMS = ["tri", "quad", "tet", "hex"]
+ELEMS = ["tri", "quad", "tet", "hex", "prism"]
 
 
 def _elem_volume(elem, x):
@@ -19,6 +19,18 @@ def _elem_volume(elem, x):
     if elem == "quad":
         a, b = x[2] - x[0], x[3] - x[1]
         return 0.5 * abs(a[0] * b[1] - a[1] * b[0])
+    if elem == "prism":
+        # 3-point (degree 2) triangle rule x 2-point Gauss along the axis: exact for det J of the prism map
+        vol = 0.0
+        for (a, b) in ((1 / 6, 1 / 6), (2 / 3, 1 / 6), (1 / 6, 2 / 3)):
+            for c in (0.5 - 0.5 / np.sqrt(3), 0.5 + 0.5 / np.sqrt(3)):
+                lam, dl = np.array([1 - a - b, a, b]), np.array([[-1, -1], [1, 0], [0, 1]], float)
+                dN = np.zeros((6, 3))
+                for k in range(6):
+                    fz, sz = (1 - c, -1.0) if k < 3 else (c, 1.0)
+                    dN[k] = [dl[k % 3, 0] * fz, dl[k % 3, 1] * fz, lam[k % 3] * sz]
+                vol += np.linalg.det(dN.T @ x) / 12
+        return abs(vol)
     # hex: 2x2x2 Gauss quadrature of det J (exact for a trilinear map)
     gp = np.array([0.5 - 0.5 / np.sqrt(3), 0.5 + 0.5 / np.sqrt(3)])
     ref = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
@@ -117,7 +129,7 @@ def test_ip_is_mean_of_scvf_corners(ora, elem):
 @pytest.mark.parametrize("elem", ELEMS)
 def test_side_ray_intersection(ora, elem):
     rng = np.random.default_rng(7)
-    x = jittered_ref_element(elem, seed=3, amp=0.1 if elem in ("tri", "tet") else 0.0)
+    x = jittered_ref_element(elem, seed=3, amp=0.1 if elem in ("tri", "tet") else 0.0)   # planar quadrilateral sides
     E = ora.ELEM[elem]
     g = ora.fv1_geometry(E, x)
     for ip in range(g["nip"]):
@@ -146,6 +158,9 @@ def _p1_shapes(elem, xi):
     if elem == "quad":
         x, y = xi
         return np.array([(1 - x) * (1 - y), x * (1 - y), x * y, (1 - x) * y])
+    if elem == "prism":
+        lam = np.array([1 - xi[0] - xi[1], xi[0], xi[1]])
+        return np.concatenate([lam * (1 - xi[2]), lam * xi[2]])
     ref = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
     return np.array([np.prod(np.where(r > 0.5, xi, 1 - xi)) for r in ref])
 
@@ -153,6 +168,8 @@ def _p1_shapes(elem, xi):
 def _on_ref_boundary(elem, xi, tol=1e-10):
     if elem in ("quad", "hex"):
         return (np.abs(xi) < tol).any() or (np.abs(xi - 1) < tol).any()
+    if elem == "prism":
+        return (np.abs(xi) < tol).any() or abs(xi[0] + xi[1] - 1) < tol or abs(xi[2] - 1) < tol
     return (np.abs(xi) < tol).any() or abs(xi.sum() - 1) < tol
 
 

@@ -11,7 +11,7 @@ import scipy.sparse as sp
 from plugin_navierstokes_b200 import meshgen
 from tests.conftest import jittered_ref_element
 
-ELEMS = ["tri", "quad", "tet", "hex"]
+ELEMS = ["tri", "quad", "tet", "hex", "prism"]
 UPWINDS = ["no", "full", "skewed", "lps", "positive"]
 STABS = ["fields", "flow", "none"]
 
@@ -259,7 +259,7 @@ def test_fvcr_rhs_has_no_density(ora):
 # ----------------------------------------------------------------------------------------------
 # global loop
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("elem,n", [("tri", 5), ("quad", 5), ("tet", 3), ("hex", 3)])
+@pytest.mark.parametrize("elem,n", [("tri", 5), ("quad", 5), ("tet", 3), ("hex", 3), ("prism", 3)])
 def test_csr_pattern_is_full_element_coupling(ora, elem, n):
     E = ora.ELEM[elem]
     coords, conn = meshgen.make_mesh(elem, n, jitter=0.2, seed=1)
@@ -276,7 +276,7 @@ def test_csr_pattern_is_full_element_coupling(ora, elem, n):
     assert np.array_equal(A.indptr, rowptr) and np.array_equal(A.indices, colind)
 
 
-@pytest.mark.parametrize("elem,n", [("quad", 4), ("hex", 2), ("tri", 4), ("tet", 2)])
+@pytest.mark.parametrize("elem,n", [("quad", 4), ("hex", 2), ("tri", 4), ("tet", 2), ("prism", 2)])
 def test_global_assembly_is_sum_of_local(ora, elem, n):
     E = ora.ELEM[elem]
     dim, nsh = ora.DIM[E], ora.NSH[E]
