@@ -20,7 +20,8 @@ UNITS = [("nsb200.cu", [], "nsb200.o")]
 UNITS += [("fv1_inst.cu", ["-DNSB_ELEM=%d" % e], "fv1_e%d.o" % e) for e in range(4)]
 UNITS += [("fused_inst.cu", ["-DNSB_ELEM=%d" % e], "fused_e%d.o" % e) for e in range(4)]
 UNITS += [("tile_inst.cu", ["-DNSB_ELEM=%d" % e], "tile_e%d.o" % e) for e in (2, 3)]
-UNITS += [("dense_inst.cu", ["-DNSB_ELEM=%d" % e], "dense_e%d.o" % e) for e in range(4)]
+UNITS += [("dense_inst.cu", ["-DNSB_ELEM=%d" % e], "dense_e%d.o" % e) for e in range(5)]
+UNITS += [("prism_inst.cu", [], "prism_e4.o")]
 UNITS += [("fvcr_inst.cu", ["-DNSB_ELEM=%d" % e], "fvcr_e%d.o" % e) for e in (0, 2)]
 
 

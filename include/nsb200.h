@@ -28,7 +28,8 @@ typedef enum {
     NSB_ERR_UNSUPPORTED = -5
 } nsb_status;
 
-enum { NSB_TRI = 0, NSB_QUAD = 1, NSB_TET = 2, NSB_HEX = 3 };
+enum { NSB_TRI = 0, NSB_QUAD = 1, NSB_TET = 2, NSB_HEX = 3,
+       NSB_PRISM = 4 /* FV1 only (fv1/navier_stokes_fv1.cpp:1542); served by the element kernels */ };
 enum { NSB_DISC_FV1 = 0, NSB_DISC_FVCR = 1 };
 /* upwind_interface.cpp:43-62 (CreateNavierStokesUpwind: "no","full","skewed","lps","pos") */
 enum { NSB_UPWIND_UNSET = 0, NSB_UPWIND_NO = 1, NSB_UPWIND_FULL = 2, NSB_UPWIND_SKEWED = 3,

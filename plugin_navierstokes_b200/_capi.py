@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnsb200.so")
 
-TRI, QUAD, TET, HEX = 0, 1, 2, 3
+TRI, QUAD, TET, HEX, PRISM = 0, 1, 2, 3, 4
 DISC_FV1, DISC_FVCR = 0, 1
 JAC_A, DEF_A, JAC_M, DEF_M, RHS = 1, 2, 4, 8, 16
 PHASE_PRIORITY, PHASE_REST = 256, 512

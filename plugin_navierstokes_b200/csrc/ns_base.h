@@ -21,7 +21,7 @@
 
 namespace nsb {
 
-enum { E_TRI = 0, E_QUAD = 1, E_TET = 2, E_HEX = 3 };
+enum { E_TRI = 0, E_QUAD = 1, E_TET = 2, E_HEX = 3, E_PRISM = 4 };
 enum { UPW_NONE = 0, UPW_NO = 1, UPW_FULL = 2, UPW_SKEWED = 3, UPW_LPS = 4, UPW_POSITIVE = 5 };
 enum { STAB_FIELDS = 0, STAB_FLOW = 1, STAB_NONE = 2 };
 enum { DIFF_RAW = 0, DIFF_FIVEPOINT = 1, DIFF_COR = 2 };
@@ -32,6 +32,18 @@ template <> struct ET<E_TRI>  { static constexpr int DIM = 2, NSH = 3, NIP = 3, 
 template <> struct ET<E_QUAD> { static constexpr int DIM = 2, NSH = 4, NIP = 4,  NSIDE = 4, NINC = 2; };
 template <> struct ET<E_TET>  { static constexpr int DIM = 3, NSH = 4, NIP = 6,  NSIDE = 4, NINC = 3; };
 template <> struct ET<E_HEX>  { static constexpr int DIM = 3, NSH = 8, NIP = 12, NSIDE = 6, NINC = 3; };
+template <> struct ET<E_PRISM> { static constexpr int DIM = 3, NSH = 6, NIP = 9, NSIDE = 5, NINC = 3; };   // element kernels only (fv1 / dense)
+
+// reference-element tables by element type: the four original types index the [4][..] tables, the prism its own arrays
+template <int E> NSB_DEV int t_edge(int ip, int j) { if constexpr (E == E_PRISM) return tab::P_EDGE[ip][j]; else return tab::EDGE[E][ip][j]; }
+template <int E> NSB_DEV int t_side(int s, int i) { if constexpr (E == E_PRISM) return tab::P_SIDE[s][i]; else return tab::SIDE[E][s][i]; }
+template <int E> NSB_DEV int t_side_n(int s) { if constexpr (E == E_PRISM) return tab::P_SIDE_N[s]; else return tab::SIDE_N[E][s]; }
+template <int E> NSB_DEV int t_fa(int ip) { if constexpr (E == E_PRISM) return tab::P_SCVF_FA[ip]; else return tab::SCVF_FA[E][ip]; }
+template <int E> NSB_DEV int t_fb(int ip) { if constexpr (E == E_PRISM) return tab::P_SCVF_FB[ip]; else return tab::SCVF_FB[E][ip]; }
+template <int E> NSB_DEV double t_lip(int ip, int d) { if constexpr (E == E_PRISM) return tab::P_LIP[ip][d]; else return tab::LIP[E][ip][d]; }
+template <int E> NSB_DEV double t_corner(int k, int d) { if constexpr (E == E_PRISM) return tab::P_CORNER[k][d]; else return tab::CORNER[E][k][d]; }
+template <int E> NSB_DEV int t_inc(int k, int t) { if constexpr (E == E_PRISM) return tab::P_INC[k][t]; else return tab::INC[E][k][t]; }
+template <int E> NSB_DEV int t_inc_sign(int k, int t) { if constexpr (E == E_PRISM) return tab::P_INC_SIGN[k][t]; else return tab::INC_SIGN[E][k][t]; }
 
 // Runtime-uniform state of the disc (NavierStokesFV1 members; fv1/navier_stokes_fv1.h:604-614).
 struct KParams {
@@ -53,6 +65,10 @@ template <int E> NSB_HD void lagrange(const double* xi, double* N)
     else if constexpr (E == E_QUAD) {
         const double x = xi[0], y = xi[1];
         N[0] = (1 - x) * (1 - y); N[1] = x * (1 - y); N[2] = x * y; N[3] = (1 - x) * y;
+    } else if constexpr (E == E_PRISM) {
+        // P1 on the triangle times P1 along the axis (ugcore LagrangeP1<ReferencePrism>)
+        const double l0 = 1.0 - xi[0] - xi[1], l1 = xi[0], l2 = xi[1], z = xi[2];
+        N[0] = l0 * (1 - z); N[1] = l1 * (1 - z); N[2] = l2 * (1 - z); N[3] = l0 * z; N[4] = l1 * z; N[5] = l2 * z;
     } else {
         const double x = xi[0], y = xi[1], z = xi[2];
         const double a0 = (1 - x) * (1 - y), a1 = x * (1 - y), a2 = x * y, a3 = (1 - x) * y;
@@ -71,6 +87,15 @@ template <int E> NSB_HD void lagrange_grad(const double* xi, double (*dN)[ET<E>:
         const double x = xi[0], y = xi[1];
         dN[0][0] = -(1 - y); dN[0][1] = -(1 - x); dN[1][0] = (1 - y); dN[1][1] = -x;
         dN[2][0] = y;        dN[2][1] = x;        dN[3][0] = -y;      dN[3][1] = (1 - x);
+    } else if constexpr (E == E_PRISM) {
+        const double l[3] = {1.0 - xi[0] - xi[1], xi[0], xi[1]}, z = xi[2];
+        const double dl[3][2] = {{-1, -1}, {1, 0}, {0, 1}};
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int t = k % 3;
+            const double fz = k < 3 ? 1 - z : z, sz = k < 3 ? -1.0 : 1.0;
+            dN[k][0] = dl[t][0] * fz; dN[k][1] = dl[t][1] * fz; dN[k][2] = l[t] * sz;
+        }
     } else {
         const double x = xi[0], y = xi[1], z = xi[2];
         const double fx[2] = {1 - x, x}, fy[2] = {1 - y, y}, fz[2] = {1 - z, z};

@@ -55,7 +55,7 @@ template <int E, class WS> NSB_DEV void positive_upwind(WS& ws, int lane, double
 #pragma unroll
         for (int d = 0; d < DIM; d++) v[d] = sgn * ws.std[ip][d];
         const double normsq = dotv<DIM>(v, v);
-        const int f = tab::EDGE[E][ip][0], t = tab::EDGE[E][ip][1];
+        const int f = t_edge<E>(ip, 0), t = t_edge<E>(ip, 1);
         int has = 1; double fl = 0.0;
         if (fabs(normsq) <= eps) has = 0;
         else {
@@ -74,9 +74,9 @@ template <int E, class WS> NSB_DEV void positive_upwind(WS& ws, int lane, double
         double m_in = 0.0, m_out = 0.0;
 #pragma unroll
         for (int q = 0; q < NINC; q++) {
-            const int ip = tab::INC[E][sh][q];
+            const int ip = t_inc<E>(sh, q);
             if (!ws.cl.has[ip]) continue;
-            const double f = (double)tab::INC_SIGN[E][sh][q] * ws.cl.flux[ip];
+            const double f = (double)t_inc_sign<E>(sh, q) * ws.cl.flux[ip];
             ips[cnt] = ip; fl[cnt] = f; cnt++;
             m_in += -1.0 * fmin(f, 0.0); m_out += fmax(f, 0.0);
         }
@@ -112,7 +112,7 @@ template <int E, class WS> NSB_DEV bool simple_upwind(WS& ws, int lane, int type
     if (lane < NIP) {
         const int ip = lane;
         IpGeo<E> g;
-        g.from = tab::EDGE[E][ip][0]; g.to = tab::EDGE[E][ip][1]; g.ds = ws.ds[ip];
+        g.from = t_edge<E>(ip, 0); g.to = t_edge<E>(ip, 1); g.ds = ws.ds[ip];
 #pragma unroll
         for (int d = 0; d < DIM; d++) { g.n[d] = ws.n[ip][d]; g.xip[d] = ws.xip[ip][d]; }
 #pragma unroll
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
         if (p.diff_len == DIFF_COR) cor_stats<E>(ws.nn, ws.ds, cmn, cav, cmd);
         if (lane < NIP) {
             const int ip = lane;
-            const int f = tab::EDGE[E][ip][0], t = tab::EDGE[E][ip][1];
+            const int f = t_edge<E>(ip, 0), t = t_edge<E>(ip, 1);
             ws.cl.a[ip] = p.visc * diff_len_sq_inv<DIM>(p.diff_len, ws.nn[ip], ws.vol[f], ws.vol[t], ws.ds[ip], cmn, cav, cmd);
             double b = 0.0, c = 0.0;
             if (!p.stokes) {
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
     double std[DIM], U[DIM], w = 1.0, up[NSH], cvx[NSH];
     if (lane < NIP) {
         const int ip = lane;
-        g.from = tab::EDGE[E][ip][0]; g.to = tab::EDGE[E][ip][1];
+        g.from = t_edge<E>(ip, 0); g.to = t_edge<E>(ip, 1);
 #pragma unroll
         for (int d = 0; d < DIM; d++) { g.n[d] = ws.n[ip][d]; std[d] = ws.std[ip][d]; U[d] = 0.0; }
 #pragma unroll
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(128) fv1_dense_kernel(KParams p, MeshDev m, co
         double d = 0.0;
         if (p.what & W_DEF_A) {
 #pragma unroll
-            for (int t = 0; t < ET<E>::NINC; t++) d += (double)tab::INC_SIGN[E][k][t] * ws.rec[tab::INC[E][k][t]].F[cf];
+            for (int t = 0; t < ET<E>::NINC; t++) d += (double)t_inc_sign<E>(k, t) * ws.rec[t_inc<E>(k, t)].F[cf];
         }
         if ((p.what & W_RHS) && p.has_source && cf < DIM) d -= p.src[cf] * ws.vol[k] * p.rho;
         d *= p.scale_a;

@@ -27,7 +27,7 @@ template <int E> struct IpGeo {
 template <int E> NSB_DEV void ip_geometry(const double* __restrict__ x, int ip, IpGeo<E>& g)
 {
     constexpr int DIM = ET<E>::DIM, NSH = ET<E>::NSH;
-    const int f = tab::EDGE[E][ip][0], t = tab::EDGE[E][ip][1];
+    const int f = t_edge<E>(ip, 0), t = t_edge<E>(ip, 1);
     g.from = f; g.to = t;
     double cen[DIM], c0[DIM];
 #pragma unroll
@@ -45,19 +45,35 @@ template <int E> NSB_DEV void ip_geometry(const double* __restrict__ x, int ip, 
         g.ds = 0.0;
     } else {
         // SCVF corners [edge midpoint, centre of face A, barycentre, centre of face B]
-        const int fa = tab::SCVF_FA[E][ip], fb = tab::SCVF_FB[E][ip];
+        const int fa = t_fa<E>(ip), fb = t_fb<E>(ip);
         constexpr int NFC = (E == E_TET) ? 3 : 4;
         double c1[3] = {0, 0, 0}, c3[3] = {0, 0, 0};
+        double w1 = 1.0 / NFC, w3 = 1.0 / NFC;
+        if constexpr (E == E_PRISM) {
+            // mixed sides: triangle (3 corners) or quadrilateral (4)
+            const int na = t_side_n<E>(fa), nb = t_side_n<E>(fb);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (q < na) { const int ka = t_side<E>(fa, q);
+#pragma unroll
+                    for (int d = 0; d < 3; d++) c1[d] += x[ka * 3 + d]; }
+                if (q < nb) { const int kb = t_side<E>(fb, q);
+#pragma unroll
+                    for (int d = 0; d < 3; d++) c3[d] += x[kb * 3 + d]; }
+            }
+            w1 = 1.0 / na; w3 = 1.0 / nb;
+        } else {
 #pragma unroll
         for (int q = 0; q < NFC; q++) {
             const int ka = tab::SIDE[E][fa][q], kb = tab::SIDE[E][fb][q];
 #pragma unroll
             for (int d = 0; d < 3; d++) { c1[d] += x[ka * 3 + d]; c3[d] += x[kb * 3 + d]; }
         }
+        }
         double a[3], b[3];
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            c1[d] *= (1.0 / NFC); c3[d] *= (1.0 / NFC);
+            if constexpr (E == E_PRISM) { c1[d] *= w1; c3[d] *= w3; } else { c1[d] *= (1.0 / NFC); c3[d] *= (1.0 / NFC); }
             a[d] = cen[d] - c0[d]; b[d] = c3[d] - c1[d];
             g.xip[d] = 0.25 * (c0[d] + c1[d] + cen[d] + c3[d]);
         }
@@ -69,7 +85,7 @@ template <int E> NSB_DEV void ip_geometry(const double* __restrict__ x, int ip, 
     // shapes and global gradients at the local ip
     double xi[DIM];
 #pragma unroll
-    for (int d = 0; d < DIM; d++) xi[d] = tab::LIP[E][ip][d];
+    for (int d = 0; d < DIM; d++) xi[d] = t_lip<E>(ip, d);
     lagrange<E>(xi, g.N);
     double dN[NSH][DIM];
     lagrange_grad<E>(xi, dN);
@@ -119,6 +135,35 @@ template <int E> NSB_DEV double scv_volume(const double* __restrict__ x, int co)
         }
         const double ax = bc[0] - x[co * 2], ay = bc[1] - x[co * 2 + 1], bx = m2[0] - m1[0], by = m2[1] - m1[1];
         return 0.5 * fabs(ax * by - ay * bx);
+    } else if constexpr (E == E_PRISM) {
+        // hexahedron (corner, edge midpoint, triangle centre, edge midpoint | axis-edge midpoint, quadrilateral centre,
+        // barycentre, quadrilateral centre): volume of the trilinear hexahedron through these eight points
+        const int base = co < 3 ? 0 : 3, t = co - base, ca = base + (t + 1) % 3, cb = base + (t + 2) % 3, up = co < 3 ? co + 3 : co - 3;
+        const int oa = ca < 3 ? ca + 3 : ca - 3, ob = cb < 3 ? cb + 3 : cb - 3;
+        double p[8][3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double xc = x[co * 3 + d], xa = x[ca * 3 + d], xb = x[cb * 3 + d], xu = x[up * 3 + d], xoa = x[oa * 3 + d], xob = x[ob * 3 + d];
+            p[0][d] = xc;
+            p[1][d] = (xc + xa) / 2;
+            p[2][d] = (xc + xa + xb) / 3;
+            p[3][d] = (xc + xb) / 2;
+            p[4][d] = (xc + xu) / 2;
+            p[5][d] = (xc + xa + xoa + xu) / 4;
+            p[6][d] = (x[d] + x[3 + d] + x[6 + d] + x[9 + d] + x[12 + d] + x[15 + d]) / 6;
+            p[7][d] = (xc + xb + xob + xu) / 4;
+        }
+        double a[3], b[3], c[3], tt[3], v = 0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) { a[d] = (p[6][d] - p[1][d]) + (p[7][d] - p[0][d]); b[d] = p[6][d] - p[3][d]; c[d] = p[2][d] - p[0][d]; }
+        cross3(tt, b, c); v += dotv<3>(a, tt);
+#pragma unroll
+        for (int d = 0; d < 3; d++) { a[d] = p[7][d] - p[0][d]; b[d] = (p[6][d] - p[3][d]) + (p[5][d] - p[0][d]); c[d] = p[6][d] - p[4][d]; }
+        cross3(tt, b, c); v += dotv<3>(a, tt);
+#pragma unroll
+        for (int d = 0; d < 3; d++) { a[d] = p[6][d] - p[1][d]; b[d] = p[5][d] - p[0][d]; c[d] = (p[6][d] - p[4][d]) + (p[2][d] - p[0][d]); }
+        cross3(tt, b, c); v += dotv<3>(a, tt);
+        return fabs(v) * (1.0 / 12.0);
     } else {
         // trilinear image of the reference octant adjacent to corner `co`; exact volume by the
         // long-diagonal formula
@@ -171,6 +216,7 @@ template <int E> __host__ __device__ constexpr int edge_corner(int ip, int j)
     if (E == E_TRI)  { constexpr int T[3][2]  = {{0,1},{1,2},{2,0}}; return T[ip][j]; }
     if (E == E_QUAD) { constexpr int T[4][2]  = {{0,1},{1,2},{2,3},{3,0}}; return T[ip][j]; }
     if (E == E_TET)  { constexpr int T[6][2]  = {{0,1},{1,2},{2,0},{0,3},{1,3},{2,3}}; return T[ip][j]; }
+    if (E == E_PRISM) { constexpr int T[9][2] = {{0,1},{1,2},{2,0},{0,3},{1,4},{2,5},{3,4},{4,5},{5,3}}; return T[ip][j]; }
     constexpr int T[12][2] = {{0,1},{1,2},{2,3},{3,0},{0,4},{1,5},{2,6},{3,7},{4,5},{5,6},{6,7},{7,4}};
     return T[ip][j];
 }
@@ -179,8 +225,15 @@ template <int E> __host__ __device__ constexpr int side_corner(int s, int i)
     if (E == E_TRI)  { constexpr int T[3][2] = {{0,1},{1,2},{2,0}}; return T[s][i]; }
     if (E == E_QUAD) { constexpr int T[4][2] = {{0,1},{1,2},{2,3},{3,0}}; return T[s][i]; }
     if (E == E_TET)  { constexpr int T[4][3] = {{0,2,1},{1,2,3},{0,3,2},{0,1,3}}; return T[s][i]; }
+    if (E == E_PRISM) { constexpr int T[5][4] = {{0,2,1,0},{0,1,4,3},{1,2,5,4},{2,0,3,5},{3,4,5,3}}; return T[s][i]; }
     constexpr int T[6][4] = {{0,3,2,1},{0,1,5,4},{1,2,6,5},{2,3,7,6},{3,0,4,7},{4,5,6,7}};
     return T[s][i];
+}
+// corners of a side: only the prism mixes triangles and quadrilaterals
+template <int E> __host__ __device__ constexpr int side_ncorner(int s)
+{
+    if (E == E_PRISM) return (s == 0 || s == 4) ? 3 : 4;
+    return ET<E>::DIM == 2 ? 2 : (E == E_TET ? 3 : 4);
 }
 
 // All candidate segments / triangles are tested in reference order with compile-time corner indices; the
@@ -214,21 +267,21 @@ template <int E> NSB_DEV bool side_ray_cut(const double* __restrict__ x, const d
         });
         if (!found) return false;
         const double t = tn / bdet, bc = n1 / bdet;
-        const int p0 = tab::SIDE[E][best][0], p1 = tab::SIDE[E][best][1];
+        const int p0 = t_side<E>(best, 0), p1 = t_side<E>(best, 1);
 #pragma unroll
         for (int d = 0; d < 2; d++) {
             gcut[d] = from[d] + t * dir[d];
-            lcut[d] = (1 - bc) * tab::CORNER[E][p0][d] + bc * tab::CORNER[E][p1][d];
+            lcut[d] = (1 - bc) * t_corner<E>(p0, d) + bc * t_corner<E>(p1, d);
         }
         side_out = best;
         return true;
     } else {
         const double dn2 = dotv<3>(dir, dir);
-        constexpr int TPS = (E == E_HEX) ? 2 : 1;            // triangles per side
+        constexpr int TPS = (E == E_HEX || E == E_PRISM) ? 2 : 1;            // triangles per side
         static_for<NSIDE * TPS>([&](auto ic) {
             constexpr int i = decltype(ic)::value, s = i / TPS, kk = i % TPS;
-            constexpr int p0 = side_corner<E>(s, 0), p1 = side_corner<E>(s, 1 + kk), p2 = side_corner<E>(s, 2 + kk);
-            if (!found) {
+            constexpr int p0 = side_corner<E>(s, 0), p1 = side_corner<E>(s, 1 + kk), p2 = side_corner<E>(s, (2 + kk) & 3);
+            if (kk + 3 <= side_ncorner<E>(s) && !found) {
                 double e1[3], e2[3], r[3], nrm[3], q[3];
 #pragma unroll
                 for (int d = 0; d < 3; d++) { e1[d] = x[p1 * 3 + d] - x[p0 * 3 + d]; e2[d] = x[p2 * 3 + d] - x[p0 * 3 + d]; r[d] = from[d] - x[p0 * 3 + d]; }
@@ -248,11 +301,11 @@ template <int E> NSB_DEV bool side_ray_cut(const double* __restrict__ x, const d
         if (!found) return false;
         const double t = tn / bdet, b1 = n1 / bdet, b2 = n2 / bdet;
         const int s = best / TPS, kk = best - s * TPS;
-        const int p0 = tab::SIDE[E][s][0], p1 = tab::SIDE[E][s][1 + kk], p2 = tab::SIDE[E][s][2 + kk];
+        const int p0 = t_side<E>(s, 0), p1 = t_side<E>(s, 1 + kk), p2 = t_side<E>(s, 2 + kk);
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             gcut[d] = from[d] + t * dir[d];
-            lcut[d] = (1 - b1 - b2) * tab::CORNER[E][p0][d] + b1 * tab::CORNER[E][p1][d] + b2 * tab::CORNER[E][p2][d];
+            lcut[d] = (1 - b1 - b2) * t_corner<E>(p0, d) + b1 * t_corner<E>(p1, d) + b2 * t_corner<E>(p2, d);
         }
         side_out = s;
         return true;
@@ -293,7 +346,8 @@ template <int E> NSB_DEV bool upwind_ip(int type, const double* __restrict__ x, 
         double mn = 1.79769313486231570e308; int best = 0;
 #pragma unroll
         for (int i = 0; i < NSC; i++) {
-            const int co = tab::SIDE[E][side][i];
+            if (E == E_PRISM && i >= t_side_n<E>(side)) continue;
+            const int co = t_side<E>(side, i);
             const double dd = dist2<DIM>(gc, x + co * DIM);
             if (dd < mn) { mn = dd; best = co; }
         }
@@ -305,7 +359,7 @@ template <int E> NSB_DEV bool upwind_ip(int type, const double* __restrict__ x, 
         lagrange<E>(lc, Nc);
         int mask = 0;
 #pragma unroll
-        for (int i = 0; i < NSC; i++) mask |= 1 << tab::SIDE[E][side][i];
+        for (int i = 0; i < NSC; i++) if (E != E_PRISM || i < t_side_n<E>(side)) mask |= 1 << t_side<E>(side, i);
 #pragma unroll
         for (int k = 0; k < NSH; k++) up[k] = ((mask >> k) & 1) ? Nc[k] : 0.0;
         len = sqrt(dist2<DIM>(g.xip, gc));

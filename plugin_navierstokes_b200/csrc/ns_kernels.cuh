@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(128) fv1_elem_kernel(KParams p, MeshDev m, con
         if (p.what & W_DEF_A) {
 #pragma unroll
             for (int t = 0; t < ET<E>::NINC; t++) {
-                const int ip = tab::INC[E][k][t];
-                d += (double)tab::INC_SIGN[E][k][t] * ws.rec[ip].F[cf];
+                const int ip = t_inc<E>(k, t);
+                d += (double)t_inc_sign<E>(k, t) * ws.rec[ip].F[cf];
             }
         }
         const double rho_v = m.ip_rho_scv ? m.ip_rho_scv[e * NSH + k] : p.rho;

@@ -16,6 +16,7 @@
 #include "../../include/nsb200.h"
 #include "ns_kernels.cuh"
 #include "ns_launch.h"
+#include "ns_launch_prism.h"
 #include "ns_fvcr.cuh"
 #include "ns_graph.h"
 #include "ns_fused.cuh"
@@ -212,7 +213,7 @@ static int set_err(nsb_ctx* c, int code, const char* fmt, ...)
 #define CUDA_TRY(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
     return set_err(c, NSB_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); } while (0)
 
-static const int kNSH[4] = {3, 4, 4, 8}, kDIM[4] = {2, 2, 3, 3}, kNSIDE[4] = {3, 4, 4, 6};
+static const int kNSH[5] = {3, 4, 4, 8, 6}, kDIM[5] = {2, 2, 3, 3, 3}, kNSIDE[5] = {3, 4, 4, 6, 5};
 
 // ------------------------------------------------------------------------------------------------
 extern "C" const char* nsb_version(void) { return "nsb200 0.1 (sm_100a)"; }
@@ -461,6 +462,7 @@ static cudaError_t launch_scvvol(nsb_ctx* c)
         case 0: return launch_scvvol_0(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol, c->stream);
         case 1: return launch_scvvol_1(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol, c->stream);
         case 2: return launch_scvvol_2(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol, c->stream);
+        case NSB_PRISM: return launch_scvvol_4(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol, c->stream);
         default: return launch_scvvol_3(c->n_elem, c->d_conn, c->d_coords, c->d_scvvol, c->stream);
     }
 }
@@ -518,7 +520,7 @@ extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_n
 {
     const auto t_start = std::chrono::steady_clock::now();
     if (!c) return NSB_ERR_INVALID;
-    if (elem < 0 || elem > 3 || n_elem <= 0 || n_node <= 0 || !conn || !coords) return set_err(c, NSB_ERR_INVALID, "nsb_upload_mesh: bad arguments");
+    if (elem < 0 || elem > NSB_PRISM || n_elem <= 0 || n_node <= 0 || !conn || !coords) return set_err(c, NSB_ERR_INVALID, "nsb_upload_mesh: bad arguments");
     CUDA_TRY(c, cudaSetDevice(c->device));
     free_mesh(c);
     const int nsh = kNSH[elem], dim = kDIM[elem], nf = dim + 1;
@@ -552,7 +554,7 @@ extern "C" int nsb_upload_mesh(nsb_ctx* c, int elem, int64_t n_elem, int64_t n_n
         CUDA_TRY(c, launch_ray_safety_3(c->n_elem, c->d_conn, c->d_coords, c->d_elem_fast, c->stream));
         c->launches++;
     }
-    { const int rcf = setup_fused(c, conn, coords, g, emap); if (rcf) return rcf; }
+    if (c->elem != NSB_PRISM) { const int rcf = setup_fused(c, conn, coords, g, emap); if (rcf) return rcf; }   // prisms: element kernels only
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->h_brow.swap(g.brow); c->h_bcol.swap(g.bcol);
     c->mesh_ready = true;
@@ -672,9 +674,9 @@ static int launch_elem(nsb_ctx* c, int sc, const KParams& k, const int32_t* list
     cudaError_t e;
 #define NSB_GO(fn) fn(sc, k, m, list, n_list, u, s0, s1, val, def, jl, dl, c->d_err, c->stream)
     if (needs_dense(k)) switch (c->elem) { case 0: e = NSB_GO(launch_dense_0); break; case 1: e = NSB_GO(launch_dense_1); break;
-                                           case 2: e = NSB_GO(launch_dense_2); break; default: e = NSB_GO(launch_dense_3); }
+                                           case 2: e = NSB_GO(launch_dense_2); break; case NSB_PRISM: e = NSB_GO(launch_dense_4); break; default: e = NSB_GO(launch_dense_3); }
     else switch (c->elem) { case 0: e = NSB_GO(launch_elem_0); break; case 1: e = NSB_GO(launch_elem_1); break;
-                            case 2: e = NSB_GO(launch_elem_2); break; default: e = NSB_GO(launch_elem_3); }
+                            case 2: e = NSB_GO(launch_elem_2); break; case NSB_PRISM: e = NSB_GO(launch_elem_4); break; default: e = NSB_GO(launch_elem_3); }
 #undef NSB_GO
     c->launches++;
     CUDA_TRY(c, e);
@@ -691,7 +693,7 @@ static int launch_gather(nsb_ctx* c, const KParams& k, const double* u, const do
     if (phase == 1 && c->n_prio > 0) mp.n_node = c->n_prio;
     if (phase == 2) { mp.node_begin = c->n_prio; mp.skip_flux = 1; }
     cudaError_t e;
-    static const int kNIP[4] = {3, 4, 6, 12};
+    static const int kNIP[5] = {3, 4, 6, 12, 9};
     const bool flow = k.stab == STAB_FLOW, exact = !k.stokes && k.exact_jac != 0.0;
     // split path (ns_split.cuh): static Jacobian part J0 cached per mesh + lean flux records. FLOW couples the
     // velocity components in the continuity row and exact Newton adds full blocks: those keep the general rows kernel.
@@ -814,7 +816,7 @@ static int assemble_fv1(nsb_ctx* c, const KParams& k, int mode, const double* u,
     const bool jac = k.what & (W_JAC_A | W_JAC_M), dfc = k.what & (W_DEF_A | W_DEF_M | W_RHS);
     const bool ip_data = c->d_ip[0] || c->d_ip[1] || c->d_ip[2] || c->d_ip[3] || c->d_ip[4];
     if (ip_data && needs_dense(k)) return set_err(c, NSB_ERR_UNSUPPORTED, "per-ip data imports with PositiveUpwind (dense ip systems) are not provided on the device path");
-    if (mode == NSB_SCATTER_GATHER && (needs_dense(k) || k.pac || ip_data)) mode = NSB_SCATTER_COLORED;   // dense ip systems / PAC / per-ip data: element kernels
+    if (mode == NSB_SCATTER_GATHER && (needs_dense(k) || k.pac || ip_data || c->elem == NSB_PRISM)) mode = NSB_SCATTER_COLORED;   // dense ip systems / PAC / per-ip data / prisms: element kernels
     c->last_scatter = mode;
     if (mode == NSB_SCATTER_GATHER) return launch_gather(c, k, u, s0, s1, beta, val, def, phase);
     if (phase == 2) return NSB_OK;                               // element kernels: everything happened in phase 1
@@ -1143,7 +1145,7 @@ extern "C" int nsb_set_ip_data(nsb_ctx* c, int kind, const double* data, int loc
     if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_ip_data: FV1 only");
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    static const int kNIP[4] = {3, 4, 6, 12};
+    static const int kNIP[5] = {3, 4, 6, 12, 9};
     const int dim = kDIM[c->elem], nsh = kNSH[c->elem], nip = kNIP[c->elem];
     const size_t per = kind == NSB_IP_KIN_VISC_SCVF || kind == NSB_IP_DENSITY_SCVF ? (size_t)nip : kind == NSB_IP_DENSITY_SCV ? (size_t)nsh
                      : kind == NSB_IP_SOURCE_SCVF ? (size_t)nip * dim : (size_t)nsh * dim;
@@ -1226,7 +1228,7 @@ extern "C" int nsb_set_boundary_faces(nsb_ctx* c, int kind, int64_t n_side, cons
 {
     if (!c || kind < 0 || kind > 2) return NSB_ERR_INVALID;
     if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_set_boundary_faces: no grid uploaded");
-    if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_boundary_faces: FV1 only");
+    if (c->disc != NSB_DISC_FV1 || c->elem == NSB_PRISM) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_boundary_faces: FV1 on tri / quad / tet / hex only");
     if (n_side < 0 || (n_side > 0 && (!elem || !side))) return NSB_ERR_INVALID;
     if (kind == NSB_BND_INFLOW && n_side > 0 && !data) return set_err(c, NSB_ERR_INVALID, "nsb_set_boundary_faces: the inflow condition needs its vector data at the boundary-face ips");
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -1322,7 +1324,7 @@ extern "C" int nsb_turbulent_viscosity(nsb_ctx* c, int model, double cmodel, con
 {
     if (!c) return NSB_ERR_INVALID;
     if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_turbulent_viscosity: no grid uploaded");
-    if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_turbulent_viscosity: FV1 only");
+    if (c->disc != NSB_DISC_FV1 || c->elem == NSB_PRISM) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_turbulent_viscosity: FV1 on tri / quad / tet / hex only");
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (model == NSB_TURB_OFF) return nsb_set_ip_data(c, NSB_IP_KIN_VISC_SCVF, nullptr, NSB_HOST);
     if (model != NSB_TURB_SMAGORINSKY) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_turbulent_viscosity: only the Smagorinsky model is available on the device");
@@ -1371,6 +1373,7 @@ extern "C" int nsb_diagnostic(nsb_ctx* c, int kind, const double* u, double dt, 
 {
     if (!c || !u || !out) return NSB_ERR_INVALID;
     if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_diagnostic: no grid uploaded");
+    if (c->elem == NSB_PRISM) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_diagnostic: not provided for prisms");
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc;
     const double* du = u;

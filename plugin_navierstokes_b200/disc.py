@@ -19,11 +19,11 @@ _UPWIND_NAMES = {  # upwind_interface.cpp:46-61 (trimmed, case-insensitive)
 }
 _STAB_NAMES = {"fields": 0, "flow": 1}                      # stabilization.cpp:52-53
 _DIFF_NAMES = {"raw": 0, "fivepoint": 1, "cor": 2}          # stabilization.cpp:94-96
-_ELEMS = {"tri": capi.TRI, "quad": capi.QUAD, "tet": capi.TET, "hex": capi.HEX,
+_ELEMS = {"tri": capi.TRI, "quad": capi.QUAD, "tet": capi.TET, "hex": capi.HEX, "prism": capi.PRISM,
           "triangle": capi.TRI, "quadrilateral": capi.QUAD, "tetrahedron": capi.TET, "hexahedron": capi.HEX}
-_NSH = {capi.TRI: 3, capi.QUAD: 4, capi.TET: 4, capi.HEX: 8}
-_DIM = {capi.TRI: 2, capi.QUAD: 2, capi.TET: 3, capi.HEX: 3}
-_NSIDE = {capi.TRI: 3, capi.QUAD: 4, capi.TET: 4, capi.HEX: 6}
+_NSH = {capi.TRI: 3, capi.QUAD: 4, capi.TET: 4, capi.HEX: 8, capi.PRISM: 6}
+_DIM = {capi.TRI: 2, capi.QUAD: 2, capi.TET: 3, capi.HEX: 3, capi.PRISM: 3}
+_NSIDE = {capi.TRI: 3, capi.QUAD: 4, capi.TET: 4, capi.HEX: 6, capi.PRISM: 5}
 
 
 class UGError(RuntimeError):
@@ -443,7 +443,7 @@ class _DeviceDisc:
             return
         from . import meshgen
         elem, conn, coords = self._grid_host
-        name = ("tri", "quad", "tet", "hex")[elem]
+        name = ("tri", "quad", "tet", "hex", "prism")[elem]
         xf = meshgen.fv1_scvf_ips(name, conn, coords)
         xv = meshgen.fv1_scv_ips(name, conn, coords)
 
@@ -702,7 +702,7 @@ class NavierStokesFVCR(_DeviceDisc):
         conn = np.ascontiguousarray(conn, dtype=np.int32)
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         if elem_sides is None:
-            name = {capi.TRI: "tri", capi.QUAD: "quad", capi.TET: "tet", capi.HEX: "hex"}[e]
+            name = {capi.TRI: "tri", capi.QUAD: "quad", capi.TET: "tet", capi.HEX: "hex", capi.PRISM: "prism"}[e]
             elem_sides, n_side = meshgen.element_sides(name, conn)
         es = np.ascontiguousarray(elem_sides, dtype=np.int32)
         self._elem = e
