@@ -38,7 +38,7 @@ struct UGError : std::runtime_error { using std::runtime_error::runtime_error; }
 using ug::number; using ug::LocalVector; using ug::LocalMatrix; using ug::ReferenceObjectID;
 #else
 typedef double number;
-enum ReferenceObjectID { ROID_TRIANGLE = 2, ROID_QUADRILATERAL = 3, ROID_TETRAHEDRON = 4, ROID_HEXAHEDRON = 5 };
+enum ReferenceObjectID { ROID_TRIANGLE = 2, ROID_QUADRILATERAL = 3, ROID_TETRAHEDRON = 4, ROID_HEXAHEDRON = 5, ROID_PRISM = 6 };
 // u(fct, dof) / J(rfct, rdof, cfct, cdof): ugcore lib_disc/common/local_algebra.h access syntax
 struct LocalVector {
     std::vector<number> v; int nfct = 0, ndof = 0;
@@ -130,7 +130,7 @@ class NavierStokesDeviceDisc {
     {
         ctx();
         m_elem = elem_type; m_n_elem = n_elem;
-        static const int nsh[4] = {3, 4, 4, 8}, nside[4] = {3, 4, 4, 6};
+        static const int nsh[5] = {3, 4, 4, 8, 6}, nside[5] = {3, 4, 4, 6, 5};
         if (m_prm.disc == NSB_DISC_FV1) { check(nsb_upload_mesh(m_ctx, elem_type, n_elem, n_node, conn, coords)); m_nsh = nsh[elem_type]; m_L = m_nsh * (m_dim + 1); }
         else { check(nsb_upload_mesh_fvcr(m_ctx, elem_type, n_elem, n_node, n_side, conn, elem_sides, coords)); m_nsh = nside[elem_type]; m_L = m_nsh * m_dim + 1; }
     }

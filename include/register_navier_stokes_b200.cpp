@@ -203,7 +203,7 @@ class NavierStokesFV1 : public IncompressibleNavierStokesBase<TDomain> {
     void register_all_funcs()
     {
         if (dim == 2) { register_func<Triangle, void>(); register_func<Quadrilateral, void>(); }
-        else { register_func<Tetrahedron, void>(); register_func<Hexahedron, void>(); }
+        else { register_func<Tetrahedron, void>(); register_func<Hexahedron, void>(); register_func<Prism, void>(); }
     }
     template <typename TElem, typename TFVGeom> void register_func()
     {

@@ -42,12 +42,13 @@ template <int N> struct MathVector { number v[N]; number& operator[](int i) { re
 enum ReferenceObjectID { ROID_UNKNOWN = -1, ROID_VERTEX, ROID_EDGE, ROID_TRIANGLE, ROID_QUADRILATERAL, ROID_TETRAHEDRON, ROID_HEXAHEDRON,
                          ROID_PRISM, ROID_PYRAMID, ROID_OCTAHEDRON, NUM_REFERENCE_OBJECTS };
 struct GridObject { virtual ~GridObject() {} };
-struct Triangle : GridObject {}; struct Quadrilateral : GridObject {}; struct Tetrahedron : GridObject {}; struct Hexahedron : GridObject {};
+struct Triangle : GridObject {}; struct Quadrilateral : GridObject {}; struct Tetrahedron : GridObject {}; struct Hexahedron : GridObject {}; struct Prism : GridObject {};
 template <class TElem> struct geometry_traits;
 template <> struct geometry_traits<Triangle> { enum { REFERENCE_OBJECT_ID = ROID_TRIANGLE }; };
 template <> struct geometry_traits<Quadrilateral> { enum { REFERENCE_OBJECT_ID = ROID_QUADRILATERAL }; };
 template <> struct geometry_traits<Tetrahedron> { enum { REFERENCE_OBJECT_ID = ROID_TETRAHEDRON }; };
 template <> struct geometry_traits<Hexahedron> { enum { REFERENCE_OBJECT_ID = ROID_HEXAHEDRON }; };
+template <> struct geometry_traits<Prism> { enum { REFERENCE_OBJECT_ID = ROID_PRISM }; };
 
 // lib_disc/common/local_algebra.h access syntax: u(fct, dof), J(rfct, rdof, cfct, cdof)
 struct LocalVector {

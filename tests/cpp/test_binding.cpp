@@ -38,7 +38,7 @@ int main(int argc, char** argv)
         NavierStokesFV1<Domain3d> d3(std::vector<std::string>{"u", "v", "w", "p"}, std::vector<std::string>{"Inner"});
         EXPECT(d.disc_type() == "fv1" && d3.disc_type() == "fv1" && d.requests_local_time_series() && d.symb_fcts().size() == 3);
         EXPECT(d.has_slots(ROID_TRIANGLE) && d.has_slots(ROID_QUADRILATERAL) && !d.has_slots(ROID_HEXAHEDRON));
-        EXPECT(d3.has_slots(ROID_TETRAHEDRON) && d3.has_slots(ROID_HEXAHEDRON) && !d3.has_slots(ROID_TRIANGLE));
+        EXPECT(d3.has_slots(ROID_TETRAHEDRON) && d3.has_slots(ROID_HEXAHEDRON) && d3.has_slots(ROID_PRISM) && !d3.has_slots(ROID_PYRAMID) && !d3.has_slots(ROID_TRIANGLE));
         EXPECT(throws([&] { d.set_pac_upwind(true); }, "Upwind must be specified previously"));
         d.set_upwind(make_sp<NavierStokesLinearProfileSkewedUpwind<2> >());
         EXPECT(throws([&] { d.set_pac_upwind(true); }, "Stabilization must be specified previously"));
