@@ -1257,8 +1257,60 @@ static int cr_opposite(int elem, int side) {
     static const int opp[4] = {3,0,1,2};
     return opp[side];
 }
+/* Crouzeix-Raviart (rotated bi-/trilinear, Rannacher-Turek point-value variant) shapes on quadrilaterals / hexahedra:
+   span {1, x, y, x^2 - y^2} resp. {1, x, y, z, x^2 - y^2, y^2 - z^2}, nodal at the side centres (ugcore
+   CrouzeixRaviartLSFS<ReferenceQuadrilateral / ReferenceHexahedron> -- our spec). The coefficients are obtained once by
+   inverting the 4 x 4 / 6 x 6 generalised Vandermonde matrix. */
+static double g_crq_coef[2][6][6]; static int g_crq_ready[2];
+static void crq_basis(int dim, const double *x, double *b, double (*db)[3])
+{
+    if (dim == 2) {
+        b[0] = 1; b[1] = x[0]; b[2] = x[1]; b[3] = x[0]*x[0]-x[1]*x[1];
+        if (db) { double t[4][3] = {{0,0,0},{1,0,0},{0,1,0},{2*x[0],-2*x[1],0}}; memcpy(db, t, sizeof t); }
+    } else {
+        b[0] = 1; b[1] = x[0]; b[2] = x[1]; b[3] = x[2]; b[4] = x[0]*x[0]-x[1]*x[1]; b[5] = x[1]*x[1]-x[2]*x[2];
+        if (db) { double t[6][3] = {{0,0,0},{1,0,0},{0,1,0},{0,0,1},{2*x[0],-2*x[1],0},{0,2*x[1],-2*x[2]}}; memcpy(db, t, sizeof t); }
+    }
+}
+static const RefElem *get_ref(int elem);
+static void crq_init(int elem)
+{
+    const int w = elem == ORA_QUAD ? 0 : 1;
+    if (g_crq_ready[w]) return;
+#pragma omp critical(ora_crq_init)
+    if (!g_crq_ready[w]) {
+        const RefElem *r = get_ref(elem); const int n = r->nside, dim = r->dim;
+        double V[6][12];                                         /* [V | I] -> [I | V^-1], Gauss-Jordan with partial pivoting */
+        for (int sd = 0; sd < n; sd++) {
+            double c[3]; avg_pts(c, r->corner, r->side[sd], r->side_n[sd], dim); if (dim == 2) c[2] = 0;
+            double b[6]; crq_basis(dim, c, b, NULL);
+            for (int j = 0; j < n; j++) { V[sd][j] = b[j]; V[sd][n+j] = sd == j; }
+        }
+        for (int k = 0; k < n; k++) {
+            int pv = k; for (int i = k+1; i < n; i++) if (fabs(V[i][k]) > fabs(V[pv][k])) pv = i;
+            for (int j = 0; j < 2*n; j++) { double t = V[k][j]; V[k][j] = V[pv][j]; V[pv][j] = t; }
+            double piv = V[k][k]; for (int j = 0; j < 2*n; j++) V[k][j] /= piv;
+            for (int i = 0; i < n; i++) if (i != k) { double f = V[i][k]; for (int j = 0; j < 2*n; j++) V[i][j] -= f*V[k][j]; }
+        }
+        /* N_s(x) = sum_j coef[s][j] b_j(x) with V coef^T = I  ->  coef[s][j] = (V^-1)[j][s] */
+        for (int sd = 0; sd < n; sd++) for (int j = 0; j < n; j++) g_crq_coef[w][sd][j] = V[j][n+sd];
+        g_crq_ready[w] = 1;
+    }
+}
 static void cr_shapes(int elem, const double *xi, double *N, double (*dN)[3])
 {
+    if (elem == ORA_QUAD || elem == ORA_HEX) {
+        crq_init(elem);
+        const int w = elem == ORA_QUAD ? 0 : 1, n = elem == ORA_QUAD ? 4 : 6, dim = elem == ORA_QUAD ? 2 : 3;
+        double b[6], db[6][3];
+        crq_basis(dim, xi, b, db);
+        for (int sd = 0; sd < n; sd++) {
+            double v = 0, g[3] = {0,0,0};
+            for (int j = 0; j < n; j++) { v += g_crq_coef[w][sd][j]*b[j]; for (int d = 0; d < 3; d++) g[d] += g_crq_coef[w][sd][j]*db[j][d]; }
+            N[sd] = v; if (dN) for (int d = 0; d < 3; d++) dN[sd][d] = g[d];
+        }
+        return;
+    }
     double lam[4], dl[4][3]; int nco = elem == ORA_TRI ? 3 : 4, dim = elem == ORA_TRI ? 2 : 3;
     lagrange_shapes(elem, xi, lam, dl);
     for (int s = 0; s < nco; s++) {
@@ -1270,7 +1322,8 @@ static void cr_shapes(int elem, const double *xi, double *N, double (*dN)[3])
 
 static int cr_geom_update(CRGeom *g, int elem, const double *coords)
 {
-    if (elem != ORA_TRI && elem != ORA_TET) return fail("CRFVGeometry oracle: simplices only");
+    if (elem != ORA_TRI && elem != ORA_TET && elem != ORA_QUAD && elem != ORA_HEX) return fail("CRFVGeometry oracle: tri / quad / tet / hex only");
+    const int simplex = elem == ORA_TRI || elem == ORA_TET;
     const RefElem *r = get_ref(elem);
     int dim = r->dim, nco = r->nsh, nside = r->nside;
     g->elem = elem; g->dim = dim; g->nco = nco; g->nsh = nside; g->nip = dim == 2 ? nco : r->nedge;
@@ -1279,7 +1332,7 @@ static int cr_geom_update(CRGeom *g, int elem, const double *coords)
     avg_pts(g->bary, g->x, all, nco, dim);
     double lbary[3]; avg_pts(lbary, r->corner, all, nco, dim);
     /* JTInv (constant on simplices) */
-    double JT[3][3] = {{0}}, JTinv[3][3] = {{0}}, lam[4], dl[4][3], z[3] = {0,0,0};
+    double JT[3][3] = {{0}}, JTinv[3][3] = {{0}}, lam[MAXSH], dl[MAXSH][3], z[3] = {0,0,0};
     lagrange_shapes(elem, z, lam, dl);
     for (int i = 0; i < dim; i++) for (int j = 0; j < dim; j++) { double s = 0; for (int k = 0; k < nco; k++) s += dl[k][i]*g->x[k][j]; JT[i][j] = s; }
     double det = mat_inverse(dim, JT, JTinv);
@@ -1293,6 +1346,20 @@ static int cr_geom_update(CRGeom *g, int elem, const double *coords)
         if (dim == 2) {
             const double *a = g->x[r->side[s][0]], *b = g->x[r->side[s][1]];
             nn[0] = b[1]-a[1]; nn[1] = -(b[0]-a[0]);
+            if (!simplex)                                  /* triangle (side, barycentre) */
+                g->vol[s] = 0.5*fabs((b[0]-a[0])*(g->bary[1]-a[1]) - (b[1]-a[1])*(g->bary[0]-a[0]));
+        } else if (r->side_n[s] == 4) {
+            /* quadrilateral side: area vector 0.5 (c2-c0) x (c3-c1); SCV = pyramid (side, barycentre), its volume as the two
+               tetrahedra of the side split along its diagonal 0-2 (the split of the ray search) */
+            const double *c0 = g->x[r->side[s][0]], *c1 = g->x[r->side[s][1]], *c2 = g->x[r->side[s][2]], *c3 = g->x[r->side[s][3]];
+            double d1[3], d2[3], a1[3], a2[3], a3[3], t[3];
+            for (int d = 0; d < 3; d++) { d1[d] = c2[d]-c0[d]; d2[d] = c3[d]-c1[d]; }
+            vcross(nn, d1, d2); for (int d = 0; d < 3; d++) nn[d] *= 0.5;
+            for (int d = 0; d < 3; d++) { a1[d] = c1[d]-c0[d]; a2[d] = c2[d]-c0[d]; a3[d] = g->bary[d]-c0[d]; }
+            vcross(t, a1, a2); double v = fabs(vdot(t, a3, 3));
+            for (int d = 0; d < 3; d++) a1[d] = c3[d]-c0[d];
+            vcross(t, a2, a1); v += fabs(vdot(t, a3, 3));
+            g->vol[s] = v/6.0;
         } else {
             double e1[3], e2[3];
             for (int d = 0; d < 3; d++) { e1[d] = g->x[r->side[s][1]][d]-g->x[r->side[s][0]][d]; e2[d] = g->x[r->side[s][2]][d]-g->x[r->side[s][0]][d]; }
@@ -1328,6 +1395,11 @@ static int cr_geom_update(CRGeom *g, int elem, const double *coords)
         for (int d = 0; d < 3; d++) g->n[ip][d] = sg*nn[d];
         double dN[6][3];
         cr_shapes(elem, g->lip[ip], g->N[ip], dN);
+        if (!simplex) {                                    /* JTInv at the local ip (bi-/trilinear element map) */
+            lagrange_shapes(elem, g->lip[ip], lam, dl);
+            for (int i = 0; i < dim; i++) for (int j = 0; j < dim; j++) { double sm = 0; for (int k = 0; k < nco; k++) sm += dl[k][i]*g->x[k][j]; JT[i][j] = sm; }
+            if (!(fabs(mat_inverse(dim, JT, JTinv)) > 0)) return fail("CRFVGeometry: singular element Jacobian");
+        }
         for (int k = 0; k < nside; k++) {
             for (int j = 0; j < 3; j++) g->G[ip][k][j] = 0;
             for (int j = 0; j < dim; j++) { double s = 0; for (int i = 0; i < dim; i++) s += JTinv[j][i]*dN[k][i]; g->G[ip][k][j] = s; }

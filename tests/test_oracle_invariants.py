@@ -216,7 +216,7 @@ def test_prep_elem_loop_errors(ora):
 # ----------------------------------------------------------------------------------------------
 # FVCR
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("elem", ["tri", "tet"])
+@pytest.mark.parametrize("elem", ["tri", "tet", "quad", "hex"])
 @pytest.mark.parametrize("upwind", ["no", "full", "skewed", "lps"])
 def test_fvcr_invariants(ora, elem, upwind):
     E = ora.ELEM[elem]
@@ -303,7 +303,7 @@ def test_global_assembly_is_sum_of_local(ora, elem, n):
     assert np.allclose(v2, vals, rtol=1e-13, atol=1e-15) and np.allclose(d2, dfc, rtol=1e-13, atol=1e-15)
 
 
-@pytest.mark.parametrize("elem,n", [("tri", 4), ("tet", 2)])
+@pytest.mark.parametrize("elem,n", [("tri", 4), ("tet", 2), ("quad", 4), ("hex", 2)])
 def test_fvcr_global(ora, elem, n):
     E = ora.ELEM[elem]
     dim = ora.DIM[E]
