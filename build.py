@@ -22,6 +22,7 @@ UNITS += [("fused_inst.cu", ["-DNSB_ELEM=%d" % e], "fused_e%d.o" % e) for e in r
 UNITS += [("tile_inst.cu", ["-DNSB_ELEM=%d" % e], "tile_e%d.o" % e) for e in (2, 3)]
 UNITS += [("dense_inst.cu", ["-DNSB_ELEM=%d" % e], "dense_e%d.o" % e) for e in range(5)]
 UNITS += [("prism_inst.cu", [], "prism_e4.o")]
+UNITS += [("fvcrq_inst.cu", ["-DNSB_ELEM=%d" % e], "fvcrq_e%d.o" % e) for e in (1, 3)]
 UNITS += [("fvcr_inst.cu", ["-DNSB_ELEM=%d" % e], "fvcr_e%d.o" % e) for e in (0, 2)]
 
 

@@ -862,8 +862,12 @@ static int assemble_fvcr(nsb_ctx* c, const KParams& k, int mode, const double* u
     }
     auto go = [&](int sc, const int32_t* list, int64_t n) -> cudaError_t {
         c->launches++;
-        return c->elem == NSB_TRI ? launch_fvcr_0(sc, k, c->fvcr, list, n, u, val, def, c->d_err, c->stream)
-                                  : launch_fvcr_2(sc, k, c->fvcr, list, n, u, val, def, c->d_err, c->stream);
+        switch (c->elem) {
+            case NSB_TRI: return launch_fvcr_0(sc, k, c->fvcr, list, n, u, val, def, c->d_err, c->stream);
+            case NSB_QUAD: return launch_fvcrq_1(sc, k, c->fvcr, list, n, u, val, def, c->d_err, c->stream);   // non-affine CR geometry (ns_fvcr_q.cuh)
+            case NSB_HEX: return launch_fvcrq_3(sc, k, c->fvcr, list, n, u, val, def, c->d_err, c->stream);
+            default: return launch_fvcr_2(sc, k, c->fvcr, list, n, u, val, def, c->d_err, c->stream);
+        }
     };
     if (mode == NSB_SCATTER_ATOMIC) { CUDA_TRY(c, go(SC_ATOMIC, nullptr, c->n_elem)); return NSB_OK; }
     for (int col = 0; col < c->n_colors; col++) {
@@ -1400,6 +1404,7 @@ extern "C" int nsb_diagnostic(nsb_ctx* c, int kind, const double* u, double dt, 
     }
     if (kind != NSB_DIAG_KINETIC_ENERGY && kind != NSB_DIAG_CFL) return NSB_ERR_INVALID;
     if (c->disc != NSB_DISC_FVCR) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_diagnostic: kineticEnergy / cflNumber work on a Crouzeix-Raviart velocity (navier_stokes_tools.h:731-965)");
+    if (c->elem != NSB_TRI && c->elem != NSB_TET) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_diagnostic: kineticEnergy / cflNumber are provided on simplices only");
     const int64_t nblk = (c->n_elem + 255) / 256;
     if (!c->d_diag) CUDA_TRY(c, dev_malloc(c, &c->d_diag, sizeof(double) * (size_t)(nblk * 3 + 2)));
     double* res = c->d_diag + nblk * 3;
@@ -1423,6 +1428,7 @@ extern "C" int nsb_fvcr_constraint_defect(nsb_ctx* c, const double* u, double s_
     if (!c || !u || !defect) return NSB_ERR_INVALID;
     if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_fvcr_constraint_defect: no grid uploaded");
     if (c->disc != NSB_DISC_FVCR) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_fvcr_constraint_defect: FVCR only");
+    if (c->elem != NSB_TRI && c->elem != NSB_TET) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_fvcr_constraint_defect: simplices only");
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc;
     const int dim = kDIM[c->elem];
@@ -1515,7 +1521,7 @@ extern "C" int nsb_upload_mesh_fvcr(nsb_ctx* c, int elem, int64_t n_elem, int64_
                                     const int32_t* esides, const double* coords)
 {
     if (!c) return NSB_ERR_INVALID;
-    if ((elem != NSB_TRI && elem != NSB_TET)) return set_err(c, NSB_ERR_UNSUPPORTED, "FVCR: simplices (tri, tet) only; hanging-node / quad / hex CR geometries are out of scope");
+    if (elem != NSB_TRI && elem != NSB_TET && elem != NSB_QUAD && elem != NSB_HEX) return set_err(c, NSB_ERR_UNSUPPORTED, "FVCR: tri / quad / tet / hex only; hanging-node, prism and pyramid CR geometries are out of scope");
     if (n_elem <= 0 || n_node <= 0 || n_side <= 0 || !conn || !esides || !coords) return set_err(c, NSB_ERR_INVALID, "nsb_upload_mesh_fvcr: bad arguments");
     CUDA_TRY(c, cudaSetDevice(c->device));
     free_mesh(c);

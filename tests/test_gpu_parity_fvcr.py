@@ -31,7 +31,7 @@ def _case(elem, n, seed=0):
     return coords, conn, es, n_side, u
 
 
-@pytest.mark.parametrize("elem,n", [("tri", 7), ("tet", 3)])
+@pytest.mark.parametrize("elem,n", [("tri", 7), ("tet", 3), ("quad", 6), ("hex", 3)])
 @pytest.mark.parametrize("mode", ["colored", "atomic", "gather"])
 @pytest.mark.parametrize("upwind", ["no", "full", "skewed", "lps"])
 @pytest.mark.parametrize("flags", [dict(), dict(peclet=True, exact=1.0), dict(laplace=True, grad_div=0.3), dict(defect_upwind=False, exact=0.5),
@@ -67,7 +67,7 @@ def test_fvcr_jac_def(ora, elem, n, mode, upwind, flags):
     assert eg < TOL and ee < TOL, ("defect", eg, ee)
 
 
-@pytest.mark.parametrize("elem,n", [("tri", 6), ("tet", 3)])
+@pytest.mark.parametrize("elem,n", [("tri", 6), ("tet", 3), ("quad", 5), ("hex", 3)])
 def test_fvcr_mass_rhs_and_scales(ora, elem, n):
     """config 4: instationary parts on the side SCVs; rhs without density (fvcr/navier_stokes_fvcr.cpp:757)"""
     coords, conn, es, n_side, u = _case(elem, n, seed=3)
@@ -92,7 +92,7 @@ def test_fvcr_mass_rhs_and_scales(ora, elem, n):
         assert eg < TOL and ee < TOL
 
 
-@pytest.mark.parametrize("elem,n", [("tri", 24), ("tet", 8)])
+@pytest.mark.parametrize("elem,n", [("tri", 24), ("tet", 8), ("quad", 16), ("hex", 6)])
 def test_fvcr_gather_is_bitwise_the_coloured_result(elem, n):
     """NSB_SCATTER_GATHER serves FVCR (beta = 0) with ONE launch of fire-and-forget reductions in element order: a CR entry has at
     most two contributions (a side has two elements), 0 + a + b == 0 + b + a exactly, so the bits equal the coloured sweeps and
@@ -124,6 +124,13 @@ def test_fvcr_errors():
     d.set_upwind("positive")
     with pytest.raises(pkg.UGError, match="No update function registered"):
         d.prep_elem_loop()
+    q, cq = meshgen.make_mesh("prism", 2)
+    with pytest.raises(pkg.UGError, match="prism and pyramid CR geometries are out of scope"):
+        pkg.NavierStokesFVCR("u,v,w,p", "Inner").set_grid("prism", cq, q, np.zeros((cq.shape[0], 5), np.int32), 1)
+    # the CR diagnostics and the constraint stay on simplices
     q, cq = meshgen.make_mesh("quad", 3)
-    with pytest.raises(pkg.UGError, match="simplices"):
-        pkg.NavierStokesFVCR("u,v,p", "Inner").set_grid("quad", cq, q)
+    d4 = pkg.NavierStokesFVCR("u,v,p", "Inner")
+    d4.set_grid("quad", cq, q)
+    out = np.zeros(1)
+    u4 = np.zeros(d4.num_dofs)
+    assert capi.lib().nsb_diagnostic(d4._context(), 1, u4.ctypes.data, 0.1, out.ctypes.data, capi.HOST) == capi.ERR_UNSUPPORTED
