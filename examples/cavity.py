@@ -138,20 +138,20 @@ def solve(dim=2, cells=16, re=100.0, picard_tol=1e-8, verbose=True, linear="dire
     return disc, coords, conn, u, hist
 
 
-def solve_fvcr(cells=16, re=100.0, picard_tol=1e-8, verbose=True, upwind="full", jitter=0.0):
-    """the same cavity with NavierStokesFVCR on triangles (Crouzeix-Raviart velocities on the sides, piecewise constant pressure; no
+def solve_fvcr(cells=16, re=100.0, picard_tol=1e-8, verbose=True, upwind="full", jitter=0.0, elem="tri"):
+    """the same cavity with NavierStokesFVCR on triangles or quadrilaterals (Crouzeix-Raviart velocities on the sides, piecewise constant pressure; no
     stabilisation needed): Dirichlet values on the boundary SIDES (lid = sides with midpoint on y = 1), pressure of element 0 pinned.
     Returns (disc, coords, conn, elem_sides, u, history)."""
     dev = torch.device("cuda", 0)
-    coords, conn = meshgen.tri_grid(cells, cells, jitter=jitter, seed=1)
-    es, n_side = meshgen.element_sides("tri", conn)
+    coords, conn = (meshgen.tri_grid if elem == "tri" else meshgen.quad_grid)(cells, cells, jitter=jitter, seed=1)
+    es, n_side = meshgen.element_sides(elem, conn)
     disc = pkg.NavierStokesFVCR("u,v,p", "Inner")
     disc.set_kinematic_viscosity(1.0 / re)
     disc.set_upwind(upwind)
-    disc.set_grid("tri", conn, coords, es, n_side)
+    disc.set_grid(elem, conn, coords, es, n_side)
     mid = np.zeros((n_side, 2))
     cnt = np.zeros(n_side)
-    for k, sd in enumerate(meshgen.SIDES["tri"]):
+    for k, sd in enumerate(meshgen.SIDES[elem]):
         np.add.at(mid, es[:, k], coords[conn[:, list(sd)]].mean(axis=1))
         np.add.at(cnt, es[:, k], 1)
     mid /= cnt[:, None]

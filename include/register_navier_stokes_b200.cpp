@@ -261,7 +261,8 @@ class NavierStokesFVCR : public IncompressibleNavierStokesBase<TDomain> {
     static void no_compat() { UG_THROW("NavierStokesFVCR (device path): per-element slots are not available, assemble whole grids with assemble_jacobian / assemble_defect"); }
     void register_all_funcs()
     {
-        if (dim == 2) register_func<Triangle, void>(); else register_func<Tetrahedron, void>();
+        if (dim == 2) { register_func<Triangle, void>(); register_func<Quadrilateral, void>(); }
+        else { register_func<Tetrahedron, void>(); register_func<Hexahedron, void>(); }
     }
     template <typename TElem, typename TFVGeom> void register_func()
     {

@@ -86,12 +86,14 @@ def evaluate_global(u, coords, conn, fct, points, nf=3):
 
 
 def evaluate_global_cr(u, coords, conn, elem_sides, fct, points, dim=2):
-    """value of velocity component fct of a Crouzeix-Raviart grid function on triangles (FVCR layout side * dim + fct) at each point:
-    sum over the element sides of u_side * (1 - 2 lambda_o), lambda_o = barycentric coordinate of the corner opposite the side"""
+    """value of velocity component fct of a Crouzeix-Raviart grid function (FVCR layout side * dim + fct) at each point. Triangles:
+    sum over the element sides of u_side * (1 - 2 lambda_o), lambda_o = barycentric coordinate of the corner opposite the side;
+    quadrilaterals: the rotated bilinear shapes nodal at the side midpoints (span {1, x, y, x^2 - y^2})"""
     from . import meshgen
     u = np.asarray(u, dtype=np.float64)
-    sides = meshgen.SIDES["tri"]
-    opp = [[c for c in range(3) if c not in sd][0] for sd in sides]
+    quad = conn.shape[1] == 4
+    sides = meshgen.SIDES["quad" if quad else "tri"]
+    opp = None if quad else [[c for c in range(3) if c not in sd][0] for sd in sides]
     xe_all = coords[conn]
     lo, hi = xe_all.min(axis=1), xe_all.max(axis=1)
     out = np.empty(len(points))
@@ -102,8 +104,14 @@ def evaluate_global_cr(u, coords, conn, elem_sides, fct, points, dim=2):
             xi = _local_coordinates(xe_all[e], pt)
             if xi is None:
                 continue
-            lam = np.array([1 - xi[0] - xi[1], xi[0], xi[1]])
-            vals.append(sum(u[elem_sides[e, s] * dim + fct] * (1.0 - 2.0 * lam[opp[s]]) for s in range(3)))
+            if quad:
+                x, y = xi
+                q = x * x - y * y
+                N = [0.75 + x - 2 * y - q, -0.25 + y + q, -0.25 + x - q, 0.75 - 2 * x + y + q]
+            else:
+                lam = np.array([1 - xi[0] - xi[1], xi[0], xi[1]])
+                N = [1.0 - 2.0 * lam[opp[s]] for s in range(3)]
+            vals.append(sum(u[elem_sides[e, s] * dim + fct] * N[s] for s in range(len(sides))))
         if not vals:
             raise ValueError("evaluate_global_cr: point %s is outside the grid" % (pt,))
         out[i] = np.mean(vals)                            # CR functions jump across sides: a point on a side takes the mean of its elements

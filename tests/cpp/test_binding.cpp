@@ -58,9 +58,9 @@ int main(int argc, char** argv)
         d.set_exact_jacobian(true); d.set_exact_jacobian(0.5); d.set_source(std::vector<number>{0.1, 0.2});
         NavierStokesFVCR<Domain3d> c("u,v,w,p", "Inner");
         NavierStokesFVCR<Domain2d> c2(std::vector<std::string>{"u", "v", "p"}, std::vector<std::string>{"Inner"});
-        EXPECT(c.disc_type() == "fvcr" && c.use_hanging() && c.has_slots(ROID_TETRAHEDRON) && !c.has_slots(ROID_HEXAHEDRON) && c2.has_slots(ROID_TRIANGLE));
+        EXPECT(c.disc_type() == "fvcr" && c.use_hanging() && c.has_slots(ROID_TETRAHEDRON) && c.has_slots(ROID_HEXAHEDRON) && !c.has_slots(ROID_PRISM) && c2.has_slots(ROID_TRIANGLE) && c2.has_slots(ROID_QUADRILATERAL));
         c.set_upwind(make_sp<NavierStokesFullUpwind<3> >()); c.set_upwind(std::string("no")); c.set_defect_upwind(false);
-        EXPECT(throws([&] { IElemDisc<Domain3d>& b = c; b.do_prep_elem_loop(ROID_HEXAHEDRON, 0); }, "no function registered"));
+        EXPECT(throws([&] { IElemDisc<Domain3d>& b = c; b.do_prep_elem_loop(ROID_PRISM, 0); }, "no function registered"));
         printf(fails ? "FAILED\n" : "OK\n");
         return fails ? 1 : 0;
     }

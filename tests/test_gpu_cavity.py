@@ -75,6 +75,24 @@ def test_fvcr_cavity_re100_converges_to_the_reference_ghia_tables():
     assert res[32]["horizontal"]["max_diff"] < 0.75 * res[16]["horizontal"]["max_diff"]
 
 
+def test_fvcr_cavity_on_quadrilaterals_converges_to_the_reference_ghia_tables():
+    """NavierStokesFVCR on quadrilaterals (rotated bilinear Crouzeix-Raviart velocities): the same known-answer check, pins the CR
+    geometry / shapes of the non-affine element types at the level of the discretisation error (measured on B200,
+    profiles/r2_cavity_fvcr_quads.txt: u on x = 0.5 max 0.115 / 0.079, v on y = 0.5 max 0.058 / 0.038 at 16^2 / 32^2, FullUpwind)"""
+    import cavity
+    from plugin_navierstokes_b200 import tools
+    res = {}
+    for cells in (16, 32):
+        disc, coords, conn, es, u, hist = cavity.solve_fvcr(cells, re=100.0, verbose=False, upwind="full", elem="quad")
+        assert hist[-1] < 1e-7 * hist[0]
+        res[cells] = tools.DrivenCavityLinesEval(u.cpu().numpy(), coords, conn, 100, elem_sides=es)["Ghia"]
+        disc.close()
+    print("FVCR quads", {c: (res[c]["vertical"]["max_diff"], res[c]["horizontal"]["max_diff"]) for c in res})
+    assert res[32]["vertical"]["max_diff"] < 0.09 and res[32]["horizontal"]["max_diff"] < 0.05
+    assert res[32]["vertical"]["max_diff"] < 0.8 * res[16]["vertical"]["max_diff"]
+    assert res[32]["horizontal"]["max_diff"] < 0.8 * res[16]["horizontal"]["max_diff"]
+
+
 @pytest.mark.parametrize("elem", ["hex", "tet"])
 def test_extruded_cavity_pins_the_3d_element_types_to_the_ghia_tables(elem):
     """FV1 on hexahedra / tetrahedra solving the 2-D problem (the square extruded by one cell in z, w = 0, zero flux through the

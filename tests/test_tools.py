@@ -61,12 +61,14 @@ def test_driven_cavity_lines_eval_tables():
     assert tools.DrivenCavityLinesEval(u.reshape(-1), coords, conn, 123) == {}
 
 
-def test_evaluate_global_cr_reproduces_linear_fields():
-    """a linear field interpolated at the side midpoints is reproduced exactly by the Crouzeix-Raviart evaluation"""
-    coords, conn = meshgen.make_mesh("tri", 7, jitter=0.2, seed=2)
-    es, n_side = meshgen.element_sides("tri", conn)
+@pytest.mark.parametrize("elem,jitter", [("tri", 0.2), ("quad", 0.0)])
+def test_evaluate_global_cr_reproduces_linear_fields(elem, jitter):
+    """a linear field interpolated at the side midpoints is reproduced exactly by the Crouzeix-Raviart evaluation (quadrilaterals:
+    rotated bilinear shapes, exact for fields linear in the local coordinates -> parallelograms)"""
+    coords, conn = meshgen.make_mesh(elem, 7, jitter=jitter, seed=2)
+    es, n_side = meshgen.element_sides(elem, conn)
     mid = np.zeros((n_side, 2)); cnt = np.zeros(n_side)
-    for k, sd in enumerate(meshgen.SIDES["tri"]):
+    for k, sd in enumerate(meshgen.SIDES[elem]):
         np.add.at(mid, es[:, k], coords[conn[:, list(sd)]].mean(axis=1)); np.add.at(cnt, es[:, k], 1)
     mid /= cnt[:, None]
     u = np.zeros(n_side * 2 + conn.shape[0])
