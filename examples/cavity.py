@@ -185,14 +185,14 @@ def solve_fvcr(cells=16, re=100.0, picard_tol=1e-8, verbose=True, upwind="full",
 
 
 def solve_extruded(elem="hex", cells=16, re=100.0, picard_tol=1e-8, verbose=True, upwind="lps"):
-    """the 2-D cavity on the 3-D element types: the unit square extruded by ONE cell in z (hexahedra, or their Kuhn split into six
-    tetrahedra), w = 0 at every node, no boundary disc on the two z faces (zero flux through them): the solution is the 2-D one,
+    """the 2-D cavity on the 3-D element types: the unit square extruded by ONE cell in z (hexahedra, their Kuhn split into six
+    tetrahedra, or their split into two prisms), w = 0 at every node, no boundary disc on the two z faces (zero flux through them): the solution is the 2-D one,
     constant in z, so the literature tables of DrivenCavityLinesEval apply to FV1 on hexahedra / tetrahedra as well.
     Returns (disc, coords2d, conn2d, u2d, history): the z-averaged solution on the quadrilateral grid of the bottom layer, FV1 2-D
     layout node * 3 + (u, v, p)."""
     dev = torch.device("cuda", 0)
     h = 1.0 / cells
-    gen = meshgen.hex_grid if elem == "hex" else meshgen.tet_grid
+    gen = {"hex": meshgen.hex_grid, "tet": meshgen.tet_grid, "prism": meshgen.prism_grid}[elem]   # prisms: every cell split into two
     coords, conn = gen(cells, cells, 1, hi=(1.0, 1.0, h))
     nf = 4
     disc = pkg.NavierStokesFV1("u,v,w,p", "Inner")

@@ -108,7 +108,8 @@ int  nsb_set_params(nsb_ctx *ctx, const nsb_params *p);
 int  nsb_upload_mesh(nsb_ctx *ctx, int elem_type, int64_t n_elem, int64_t n_node,
                      const int32_t *conn, const double *coords);
 /* FVCR variant: additionally elem_sides [n_elem][nside] (global side ids; side k of an element is its
- * reference side k). dofs: side*dim+d, then n_side*dim + elem for the pressure. */
+ * reference side k). dofs: side*dim+d, then n_side*dim + elem for the pressure. Element types: NSB_TRI, NSB_TET,
+ * NSB_QUAD, NSB_HEX (fvcr/navier_stokes_fvcr.cpp:790-813; prism / pyramid CR geometries: NSB_ERR_UNSUPPORTED). */
 int  nsb_upload_mesh_fvcr(nsb_ctx *ctx, int elem_type, int64_t n_elem, int64_t n_node, int64_t n_side,
                           const int32_t *conn, const int32_t *elem_sides, const double *coords);
 

@@ -93,7 +93,7 @@ def test_fvcr_cavity_on_quadrilaterals_converges_to_the_reference_ghia_tables():
     assert res[32]["horizontal"]["max_diff"] < 0.8 * res[16]["horizontal"]["max_diff"]
 
 
-@pytest.mark.parametrize("elem", ["hex", "tet"])
+@pytest.mark.parametrize("elem", ["hex", "tet", "prism"])
 def test_extruded_cavity_pins_the_3d_element_types_to_the_ghia_tables(elem):
     """FV1 on hexahedra / tetrahedra solving the 2-D problem (the square extruded by one cell in z, w = 0, zero flux through the
     z faces): converges to the reference's Ghia table like the quadrilateral run (profiles/r2_cavity_ghia.txt: hex 0.046 / 0.027,
@@ -106,6 +106,7 @@ def test_extruded_cavity_pins_the_3d_element_types_to_the_ghia_tables(elem):
         assert hist[-1] < 1e-7 * hist[0]
         res[cells] = tools.DrivenCavityLinesEval(u2, c2, q2, 100)["Ghia"]
         disc.close()
+    print("extruded", elem, {c: (res[c]["vertical"]["max_diff"], res[c]["horizontal"]["max_diff"]) for c in res})
     assert res[32]["vertical"]["max_diff"] < 0.032 and res[32]["horizontal"]["max_diff"] < 0.030
     assert res[32]["vertical"]["max_diff"] < 0.7 * res[16]["vertical"]["max_diff"]
     assert res[32]["horizontal"]["max_diff"] < 0.7 * res[16]["horizontal"]["max_diff"]
