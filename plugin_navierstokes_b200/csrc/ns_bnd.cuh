@@ -25,21 +25,21 @@ template <int E>
 NSB_DEV void bf_corner_set(const double (*x)[ET<E>::DIM], int side, int j, double (*c)[ET<E>::DIM], int& nc)
 {
     constexpr int DIM = ET<E>::DIM;
-    const int ns = tab::SIDE_N[E][side], co = tab::SIDE[E][side][j];
+    const int ns = t_side_n<E>(side), co = t_side<E>(side, j);
 #pragma unroll
     for (int d = 0; d < DIM; d++) c[0][d] = x[co][d];
     if constexpr (DIM == 2) {
-        const int other = tab::SIDE[E][side][1 - j];
+        const int other = t_side<E>(side, 1 - j);
 #pragma unroll
         for (int d = 0; d < DIM; d++) c[1][d] = 0.5 * (x[co][d] + x[other][d]);
         nc = 2;
     } else {
-        const int nx = tab::SIDE[E][side][(j + 1) % ns], pv = tab::SIDE[E][side][(j + ns - 1) % ns];
+        const int nx = t_side<E>(side, (j + 1) % ns), pv = t_side<E>(side, (j + ns - 1) % ns);
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
             c[1][d] = 0.5 * (x[co][d] + x[nx][d]); c[3][d] = 0.5 * (x[co][d] + x[pv][d]);
             double s = 0.0;
-            for (int k = 0; k < ns; k++) s += x[tab::SIDE[E][side][k]][d];
+            for (int k = 0; k < ns; k++) s += x[t_side<E>(side, k)][d];
             c[2][d] = s / ns;
         }
         nc = 4;
@@ -55,7 +55,7 @@ NSB_DEV void bf_normal_lip(const double (*x)[ET<E>::DIM], int side, int j, doubl
 #pragma unroll
     for (int k = 0; k < NSH; k++)
 #pragma unroll
-        for (int d = 0; d < DIM; d++) xr[k][d] = tab::CORNER[E][k][d];
+        for (int d = 0; d < DIM; d++) xr[k][d] = t_corner<E>(k, d);
     int nc;
     bf_corner_set<E>(x, side, j, c, nc);
     bf_corner_set<E>(xr, side, j, lc, nc);
@@ -71,13 +71,13 @@ NSB_DEV void bf_normal_lip(const double (*x)[ET<E>::DIM], int side, int j, doubl
         for (int d = 0; d < 3; d++) n[d] *= 0.5;
     }
     // outward: away from the element barycentre
-    const int ns = tab::SIDE_N[E][side];
+    const int ns = t_side_n<E>(side);
     double o = 0.0;
 #pragma unroll
     for (int d = 0; d < DIM; d++) {
         double bary = 0.0, sc = 0.0;
         for (int k = 0; k < NSH; k++) bary += x[k][d];
-        for (int k = 0; k < ns; k++) sc += x[tab::SIDE[E][side][k]][d];
+        for (int k = 0; k < ns; k++) sc += x[t_side<E>(side, k)][d];
         o += n[d] * (sc / ns - bary / NSH);
     }
     if (o < 0) {
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(64) fv1_boundary_kernel(KParams p, MeshDev m, 
         const double svn = dotv<DIM>(sv, n);
         double flux = svn * p.rho;                                     // no inflow through the outflow boundary (:299, :329)
         if (flux < 0) flux = 0.0;
-        const int co = tab::SIDE[E][f.side][f.j];
+        const int co = t_side<E>(f.side, f.j);
         if (want_jac) {
             const uint8_t* em = m.emap + ((int64_t)f.elem * NSH + co) * NSH;
             for (int sh = 0; sh < NSH; sh++) {

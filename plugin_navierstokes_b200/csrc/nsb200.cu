@@ -1232,7 +1232,8 @@ extern "C" int nsb_set_boundary_faces(nsb_ctx* c, int kind, int64_t n_side, cons
 {
     if (!c || kind < 0 || kind > 2) return NSB_ERR_INVALID;
     if (!c->mesh_ready) return set_err(c, NSB_ERR_INVALID, "nsb_set_boundary_faces: no grid uploaded");
-    if (c->disc != NSB_DISC_FV1 || c->elem == NSB_PRISM) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_boundary_faces: FV1 on tri / quad / tet / hex only");
+    if (c->disc != NSB_DISC_FV1) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_boundary_faces: FV1 only");
+    if (c->elem == NSB_PRISM && kind == NSB_BND_TURB_ZERO) return set_err(c, NSB_ERR_UNSUPPORTED, "nsb_set_boundary_faces: the turbulence-zero boundary belongs to the Smagorinsky provider, which is not provided for prisms");
     if (n_side < 0 || (n_side > 0 && (!elem || !side))) return NSB_ERR_INVALID;
     if (kind == NSB_BND_INFLOW && n_side > 0 && !data) return set_err(c, NSB_ERR_INVALID, "nsb_set_boundary_faces: the inflow condition needs its vector data at the boundary-face ips");
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -1242,18 +1243,17 @@ extern "C" int nsb_set_boundary_faces(nsb_ctx* c, int kind, int64_t n_side, cons
     if (kind == NSB_BND_TURB_ZERO) { cudaFree(c->d_bidx); cudaFree(c->d_dbf); c->d_bidx = nullptr; c->d_dbf = nullptr; }
     if (n_side == 0) return NSB_OK;
     const int nsh = kNSH[c->elem], dim = kDIM[c->elem], nside = kNSIDE[c->elem];
-    static const int side_n[4] = {2, 2, 3, 4};
-    static const int8_t sides[4][6][4] = {{{0, 1, -1, -1}, {1, 2, -1, -1}, {2, 0, -1, -1}}, {{0, 1, -1, -1}, {1, 2, -1, -1}, {2, 3, -1, -1}, {3, 0, -1, -1}},
+    static const int8_t sides[5][6][4] = {{{0, 1, -1, -1}, {1, 2, -1, -1}, {2, 0, -1, -1}}, {{0, 1, -1, -1}, {1, 2, -1, -1}, {2, 3, -1, -1}, {3, 0, -1, -1}},
                                           {{0, 2, 1, -1}, {1, 2, 3, -1}, {0, 3, 2, -1}, {0, 1, 3, -1}},
-                                          {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}}};
+                                          {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}},
+                                          {{0, 2, 1, -1}, {0, 1, 4, 3}, {1, 2, 5, 4}, {2, 0, 3, 5}, {3, 4, 5, -1}}};   // prism: triangles and quadrilaterals
     std::vector<int32_t> conn((size_t)c->n_elem * nsh);
     CUDA_TRY(c, cudaMemcpy(conn.data(), c->d_conn, conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    const int sn = side_n[c->elem];
     struct Key { int32_t node; int64_t b; int j; };
-    std::vector<Key> keys; keys.reserve((size_t)n_side * sn);
+    std::vector<Key> keys; keys.reserve((size_t)n_side * 4);
     for (int64_t q = 0; q < n_side; q++) {
         if (elem[q] < 0 || elem[q] >= c->n_elem || side[q] < 0 || side[q] >= nside) return set_err(c, NSB_ERR_INVALID, "nsb_set_boundary_faces: bad (element, side) pair %lld", (long long)q);
-        for (int j = 0; j < sn; j++) keys.push_back({conn[(size_t)elem[q] * nsh + sides[c->elem][side[q]][j]], q, j});
+        for (int j = 0; j < 4 && sides[c->elem][side[q]][j] >= 0; j++) keys.push_back({conn[(size_t)elem[q] * nsh + sides[c->elem][side[q]][j]], q, j});
     }
     std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) { return x.node != y.node ? x.node < y.node : (x.b != y.b ? x.b < y.b : x.j < y.j); });
     std::vector<int32_t> bnode; std::vector<int64_t> bptr; std::vector<nsb::BndFace> bf(keys.size());
@@ -1308,7 +1308,7 @@ extern "C" int nsb_assemble_boundary(nsb_ctx* c, int what, const double* u, doub
         if (kind == NSB_BND_INFLOW && !dfc) continue;
         const unsigned nblk = (unsigned)((b.n_bnode + 63) / 64);
 #define NSB_BND(EE) fv1_boundary_kernel<EE><<<nblk, 64, 0, c->stream>>>(k, m, kind, b.n_bnode, b.d_bnode, b.d_bptr, b.d_bf, b.d_data, du, dv, dfc ? dd : nullptr, c->d_err)
-        switch (c->elem) { case NSB_TRI: NSB_BND(E_TRI); break; case NSB_QUAD: NSB_BND(E_QUAD); break; case NSB_TET: NSB_BND(E_TET); break; default: NSB_BND(E_HEX); }
+        switch (c->elem) { case NSB_TRI: NSB_BND(E_TRI); break; case NSB_QUAD: NSB_BND(E_QUAD); break; case NSB_TET: NSB_BND(E_TET); break; case NSB_PRISM: NSB_BND(E_PRISM); break; default: NSB_BND(E_HEX); }
 #undef NSB_BND
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());

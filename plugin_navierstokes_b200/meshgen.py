@@ -140,7 +140,8 @@ def element_sides(elem, conn):
     Returns (elem_sides [n_elem, nside] int32, n_side). Side k of an element is the reference side k."""
     sides = SIDES[elem]
     ne = conn.shape[0]
-    keys = np.stack([np.sort(conn[:, list(s)], axis=1) for s in sides], axis=1)  # [ne, nside, nco]
+    width = max(len(sd) for sd in sides)                    # prisms mix triangles and quadrilaterals: pad the keys with -1
+    keys = np.stack([np.sort(np.pad(conn[:, list(sd)], ((0, 0), (width - len(sd), 0)), constant_values=-1), axis=1) for sd in sides], axis=1)  # [ne, nside, nco]
     flat = keys.reshape(ne * len(sides), -1)
     _, inv = np.unique(flat, axis=0, return_inverse=True)
     inv = np.asarray(inv).reshape(-1)

@@ -17,9 +17,10 @@ def _inflow(*x):
     return (1.0 + 0.3 * x[1], 0.2 * x[0]) if len(x) == 2 else (1.0 + 0.3 * x[1], 0.2 * x[0], -0.1 * x[2])
 
 
-@pytest.mark.parametrize("elem,n", [("tri", 7), ("quad", 7), ("tet", 3), ("hex", 4)])
+@pytest.mark.parametrize("elem,n,axis", [("tri", 7, 0), ("quad", 7, 0), ("tet", 3, 0), ("hex", 4, 0),
+                                         ("prism", 3, 0), ("prism", 3, 2)])      # prisms: quadrilateral (x) and triangular (z) boundary sides
 @pytest.mark.parametrize("flags", [dict(), dict(laplace=True), dict(stokes=True)])
-def test_boundary_discs_match_the_oracle(ora, elem, n, flags):
+def test_boundary_discs_match_the_oracle(ora, elem, n, axis, flags):
     import torch
     coords, conn, u = parity.make_case(elem, n, seed=9)
     u = u.reshape(-1)
@@ -27,14 +28,14 @@ def test_boundary_discs_match_the_oracle(ora, elem, n, flags):
     disc = pkg.NavierStokesFV1("u,v,w,p" if dim == 3 else "u,v,p", "Inner")
     parity.configure(disc, upwind="full", stab="fields", visc=0.05, density=1.3, **flags)
     disc.set_grid(elem, conn, coords)
-    xmax, xmin = coords[:, 0].max(), coords[:, 0].min()
-    out_e, out_s = meshgen.boundary_sides(elem, conn, coords, where=lambda c: np.isclose(c[:, 0], xmax))
-    in_e, in_s = meshgen.boundary_sides(elem, conn, coords, where=lambda c: np.isclose(c[:, 0], xmin))
+    xmax, xmin = coords[:, axis].max(), coords[:, axis].min()
+    out_e, out_s = meshgen.boundary_sides(elem, conn, coords, where=lambda c: np.isclose(c[:, axis], xmax))
+    in_e, in_s = meshgen.boundary_sides(elem, conn, coords, where=lambda c: np.isclose(c[:, axis], xmin))
     outflow = pkg.NavierStokesNoNormalStressOutflow(disc)
     outflow.add(out_e, out_s)
     outflow.apply()
     inflow = pkg.NavierStokesInflowFV1(disc)
-    in_nodes = np.nonzero(np.isclose(coords[:, 0], xmin))[0]
+    in_nodes = np.nonzero(np.isclose(coords[:, axis], xmin))[0]
     inflow.add(_inflow, in_nodes, coords, sides=(in_e, in_s), conn=conn, elem=elem)
     inflow.apply()
     rowptr, colind = ora.fv1_csr(ora.ELEM[elem], conn, coords.shape[0])

@@ -8,7 +8,7 @@ import scipy.sparse as sp
 from plugin_navierstokes_b200 import meshgen
 from tests.conftest import jittered_ref_element
 
-ELEMS = ["tri", "quad", "tet", "hex"]
+ELEMS = ["tri", "quad", "tet", "hex", "prism"]
 
 
 @pytest.mark.parametrize("elem", ELEMS)
@@ -56,7 +56,7 @@ def _problem(ora, elem, n, seed=4):
     return coords, conn, u, rowptr, colind
 
 
-@pytest.mark.parametrize("elem,n", [("tri", 5), ("quad", 5), ("tet", 3), ("hex", 3)])
+@pytest.mark.parametrize("elem,n", [("tri", 5), ("quad", 5), ("tet", 3), ("hex", 3), ("prism", 3)])
 @pytest.mark.parametrize("laplace", [False, True])
 def test_outflow_picard_property_and_pattern(ora, elem, n, laplace):
     """J(u) u = d(u) for the fixed-point Jacobian of the outflow disc (diffusive and continuity parts are linear, the convective
@@ -85,7 +85,7 @@ def test_outflow_picard_property_and_pattern(ora, elem, n, laplace):
     assert np.abs(As @ (2 * u0) - 2 * ds).max() < 1e-12 * np.abs(ds).max()       # linear in u
 
 
-@pytest.mark.parametrize("elem,n", [("quad", 4), ("hex", 3), ("tri", 4), ("tet", 2)])
+@pytest.mark.parametrize("elem,n", [("quad", 4), ("hex", 3), ("tri", 4), ("tet", 2), ("prism", 2)])
 def test_mass_balance_of_a_uniform_flow(ora, elem, n):
     """uniform velocity, no stabilisation: the continuity defect of the element loop plus outflow faces on the WHOLE boundary is
     zero at every node (each control volume is closed by SCVFs and BFs); the inflow term with the same datum has the same
@@ -112,7 +112,7 @@ def test_mass_balance_of_a_uniform_flow(ora, elem, n):
 
 
 def test_bf_ips_of_meshgen_match_the_oracle(ora):
-    for elem, n in [("tri", 3), ("quad", 3), ("tet", 2), ("hex", 2)]:
+    for elem, n in [("tri", 3), ("quad", 3), ("tet", 2), ("hex", 2), ("prism", 2)]:
         coords, conn = meshgen.make_mesh(elem, n, jitter=0.2, seed=7)
         be, bs = meshgen.boundary_sides(elem, conn)
         xip = meshgen.fv1_bf_ips(elem, conn, coords, be, bs)
