@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Generates tests/golden/fv1_fvcr_golden.npz.
+"""Generates tests/golden/fv1_fvcr_golden.npz (CASES) and tests/golden/elem_types_golden.npz (CASES_ELEM_TYPES: the element types
+added at the end of round 2 -- FV1 prisms, FVCR quadrilaterals / hexahedra; a separate file so that the first one stays frozen).
 
 The reference plugin cannot be compiled or run here (ugcore is absent), and it ships no golden
 vectors, so these fixtures are FROZEN OUTPUTS OF THE CPU ORACLE (oracle/ns_oracle.c) on small seeded cases --
@@ -27,6 +28,14 @@ CASES = [
     ("tet_skewed_flow_pac", "fv1", "tet", 2, "skewed", "flow", dict(kin_visc=5e-3, pac=True, exact_jac=0.5)),
     ("cfg4_tet_fvcr_full", "fvcr", "tet", 2, "full", None, dict(kin_visc=1e-3, density=1.1)),
     ("tri_fvcr_lps_graddiv", "fvcr", "tri", 4, "lps", None, dict(kin_visc=1e-2, grad_div=0.2, laplace=True)),
+]
+
+CASES_ELEM_TYPES = [
+    ("prism_lps_fields", "fv1", "prism", 3, "lps", "fields", dict(kin_visc=1e-2)),
+    ("prism_pos_flow_td", "fv1", "prism", 2, "positive", "flow", dict(kin_visc=1 / 1600, dt=1e-2, time_dependent=True)),
+    ("prism_full_flow_exact_peclet", "fv1", "prism", 2, "full", "flow", dict(kin_visc=5e-3, exact_jac=1.0, peclet_blend=True)),
+    ("quad_fvcr_lps_graddiv", "fvcr", "quad", 4, "lps", None, dict(kin_visc=1e-2, grad_div=0.2, laplace=True)),
+    ("hex_fvcr_full", "fvcr", "hex", 2, "full", None, dict(kin_visc=1e-3, density=1.1)),
 ]
 
 
@@ -59,9 +68,13 @@ def build(case):
 
 
 if __name__ == "__main__":
-    data = {}
-    for c in CASES:
-        data.update(build(c))
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fv1_fvcr_golden.npz")
-    np.savez_compressed(path, **data)
-    print("wrote", path, os.path.getsize(path), "bytes")
+    # the first file is frozen since round 1: it is rewritten only on request (python make_golden.py --all)
+    for fname, cases in (("fv1_fvcr_golden.npz", CASES if "--all" in sys.argv else []), ("elem_types_golden.npz", CASES_ELEM_TYPES)):
+        if not cases:
+            continue
+        data = {}
+        for c in cases:
+            data.update(build(c))
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), fname)
+        np.savez_compressed(path, **data)
+        print("wrote", path, os.path.getsize(path), "bytes")

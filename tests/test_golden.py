@@ -6,10 +6,15 @@ import numpy as np
 import pytest
 
 from tests import parity
-from tests.golden.make_golden import CASES
+from tests.golden.make_golden import CASES as _CASES_R1, CASES_ELEM_TYPES
 from tests.parity import TOL
 
-GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fv1_fvcr_golden.npz"))
+CASES = _CASES_R1 + CASES_ELEM_TYPES
+_GDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD = {}
+for _f in ("fv1_fvcr_golden.npz", "elem_types_golden.npz"):
+    with np.load(os.path.join(_GDIR, _f)) as _z:
+        GOLD.update({k: _z[k] for k in _z.files})
 
 
 def _get(name, key):
