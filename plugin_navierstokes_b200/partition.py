@@ -130,8 +130,9 @@ def graph_partition(conn, n_node, n_parts, dim=None):
 
 
 def face_nodes(nsh, dim):
-    """nodes two face-neighbours share: tri / quad 2, tet 3, hex 4 (nsh = 4 is a quad in 2-D and a tet in 3-D)"""
-    return 2 if nsh == 3 or (nsh == 4 and dim == 2) else (3 if nsh == 4 else 4)
+    """nodes two face-neighbours share: tri / quad 2, tet 3, hex 4, prism 3 (its triangular sides; the quadrilateral ones share 4).
+    nsh = 4 is a quad in 2-D and a tet in 3-D"""
+    return 2 if nsh == 3 or (nsh == 4 and dim == 2) else (3 if nsh in (4, 6) else 4)
 
 
 def best_partition(conn, coords, n_parts):
