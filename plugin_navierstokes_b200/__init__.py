@@ -5,6 +5,7 @@ csrc/      CUDA kernels + the C ABI (include/nsb200.h) -> libnsb200.so (built in
 disc.py    host-side mirror of NavierStokesFV1 / NavierStokesFVCR (names, setters, errors of the reference)
 meshgen.py synthetic grids / states of the BASELINE.json configurations
 partition.py  element partition + interface lists for the multi-GPU path
+cr_reorder.py host mirror of OrderCRCuthillMcKee (FVCR dof ordering, solver-side preprocessing)
 """
 from . import _capi as capi                                   # noqa: F401
 from .disc import (NavierStokes, NavierStokesFV1, NavierStokesFVCR, UGError,            # noqa: F401
@@ -14,3 +15,4 @@ from .disc import (NavierStokes, NavierStokesFV1, NavierStokesFVCR, UGError,    
                    NavierStokesFIELDSStabilization, NavierStokesFLOWStabilization,
                    NavierStokesFV1WithoutStabilization, NavierStokesWall, NavierStokesInflowFV1, NavierStokesNoNormalStressOutflowFV1,
                    NavierStokesNoNormalStressOutflow, FV1SmagorinskyTurbViscData, DiscConstraintFVCR, ThetaTimeStep)
+from .cr_reorder import OrderCRCuthillMcKee                    # noqa: F401,E402
