@@ -64,6 +64,7 @@ class ClockSampler:
             pynvml.nvmlInit()
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)      # priming query (discarded)
             self.nvml = pynvml
         except Exception:
             self.nvml = None
@@ -279,6 +280,7 @@ def main():
             disc.assemble(what, ud, values=vals, defect=dfc, scatter_mode=mode)
             exch.sum_to_owner(vals, dfc)
 
+    sampler = ClockSampler(local)           # NVML initialised and primed before the warm-up: the first query of a process is slow
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -286,7 +288,6 @@ def main():
     l0 = disc.launch_count + (exch.launches if exch else 0)
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     torch.cuda.synchronize()
