@@ -120,16 +120,18 @@ def evaluate_global_cr(u, coords, conn, elem_sides, fct, points, dim=2):
 
 def interpolateCRToLagrange(u_cr, coords, conn, elem_sides, n_side):
     """mirror of interpolateCRToLagrange (navier_stokes_tools.h:53-229, registered as "CRToLagrange"): nodal (Lagrange P1) velocities
-    from a Crouzeix-Raviart function on simplices. Per element and corner i the CR function is evaluated at the local ip of the FV1
+    from a Crouzeix-Raviart function on triangles / tetrahedra (and, through `_cr_to_lagrange_tensor`, quadrilaterals / hexahedra). Per element and corner i the CR function is evaluated at the local ip of the FV1
     sub-control volume of the corner (:196-201), weighted with the SCV volume (:195, :205) and divided by the summed nodal volume at
     the end (:216-228). u_cr: FVCR layout side * dim + d (pressures behind the velocities are ignored). Returns [n_node][dim]."""
     from . import meshgen
     coords = np.asarray(coords, dtype=np.float64)
     dim = coords.shape[1]
     nco = dim + 1
+    if conn.shape[1] == 2 ** dim:
+        return _cr_to_lagrange_tensor(u_cr, coords, conn, elem_sides, n_side)
     elem = "tri" if dim == 2 else "tet"
     if conn.shape[1] != nco:
-        raise ValueError("interpolateCRToLagrange: simplices only")
+        raise ValueError("interpolateCRToLagrange: triangles / quadrilaterals / tetrahedra / hexahedra")
     sides = meshgen.SIDES[elem]
     opp = [[c for c in range(nco) if c not in sd][0] for sd in sides]
     # barycentric coordinates of the SCV ip of corner i = mean of the SCV corners (node, edge midpoints, (face centres,) barycentre)
@@ -147,6 +149,43 @@ def interpolateCRToLagrange(u_cr, coords, conn, elem_sides, n_side):
         shape = np.array([1.0 - dim * lam[opp[s]] for s in range(len(sides))])      # CR shapes at the SCV ip
         np.add.at(out, conn[:, i], scv[:, None] * np.einsum("s,esd->ed", shape, us))
         np.add.at(vsum, conn[:, i], scv)
+    return out / vsum[:, None]
+
+
+def _cr_shapes_tensor(dim, xi):
+    """rotated bi- / trilinear Crouzeix-Raviart shapes nodal at the side centres (span {1, x, y, (z,) x^2 - y^2 (, y^2 - z^2)})"""
+    if dim == 2:
+        x, y = xi
+        q = x * x - y * y
+        return np.array([0.75 + x - 2 * y - q, -0.25 + y + q, -0.25 + x - q, 0.75 - 2 * x + y + q])
+    x, y, z = xi
+    b = np.array([1.0, x, y, z, x * x - y * y, y * y - z * z])
+    C = np.array([[2, 2, 2, -7, -2, -4], [2, 2, -7, 2, -2, 2], [-1, -1, 2, 2, 4, 2], [-1, 2, -1, 2, -2, 2], [2, -7, 2, 2, 4, 2], [-1, 2, 2, -1, -2, -4]]) / 3.0
+    return C @ b
+
+
+def _cr_to_lagrange_tensor(u_cr, coords, conn, elem_sides, n_side):
+    """interpolateCRToLagrange on quadrilaterals / hexahedra: the SCV of corner i is the image of the reference quadrant / octant at
+    that corner (local ip = its centre), its volume the integral of det J over it (2-point Gauss per direction, exact)"""
+    dim = coords.shape[1]
+    elem = "quad" if dim == 2 else "hex"
+    rc = _REF_CORNERS[elem]
+    x = coords[conn]                                       # [ne][nco][dim]
+    vel = np.asarray(u_cr, dtype=np.float64)[:n_side * dim].reshape(n_side, dim)
+    us = vel[elem_sides]                                   # [ne][nside][dim]
+    out = np.zeros((coords.shape[0], dim)); vsum = np.zeros(coords.shape[0])
+    g = 0.25 / np.sqrt(3.0)
+    import itertools
+    for i in range(rc.shape[0]):
+        centre = 0.25 + 0.5 * rc[i]                       # centre of the quadrant / octant adjacent to corner i
+        vol = np.zeros(conn.shape[0])
+        for sg in itertools.product((-g, g), repeat=dim):
+            _, dN = _lagrange(elem, centre + np.array(sg))
+            J = np.einsum("kd,ekj->edj", dN, x)           # [ne][dim][dim]
+            vol += np.abs(np.linalg.det(J)) * 0.25 ** dim
+        shape = _cr_shapes_tensor(dim, centre)
+        np.add.at(out, conn[:, i], vol[:, None] * np.einsum("s,esd->ed", shape, us))
+        np.add.at(vsum, conn[:, i], vol)
     return out / vsum[:, None]
 
 

@@ -143,3 +143,50 @@ def test_drag_lift_on_analytic_fields(elem):
     be, bs = meshgen.boundary_sides(elem, conn, coords, where=lambda x: np.isclose(x[:, last], 0.0))
     drag, lift = tools.DragLift(u.reshape(-1), coords, conn, elem, be, bs, nu, rho, quad_order=2)
     assert abs(drag - nu * rho * c) < 1e-12 and abs(lift + 0.3) < 1e-12
+
+
+@pytest.mark.parametrize("elem,n", [("quad", 5), ("hex", 3)])
+def test_interpolate_cr_to_lagrange_on_quadrilaterals_and_hexahedra(ora, elem, n):
+    """rotated bi- / trilinear CR shapes at the SCV ips: (1) on a parallelepiped grid an affine field given at the side centres is
+    returned exactly at the interior nodes (their SCV ips lie symmetrically around the node), a constant everywhere;
+    (2) the weights are the FV1 SCV volumes of the oracle's geometry (jittered grid)"""
+    coords0, conn = meshgen.make_mesh(elem, n)
+    dim = coords0.shape[1]
+    A = np.array([[1.0, 0.3, 0.1], [0.2, 0.9, -0.2], [0.0, 0.1, 1.1]])[:dim, :dim]
+    coords = coords0 @ A.T
+    es, n_side = meshgen.element_sides(elem, conn)
+
+    def side_centres(c):
+        mid = np.zeros((n_side, dim)); cnt = np.zeros(n_side)
+        for k, sd in enumerate(meshgen.SIDES[elem]):
+            np.add.at(mid, es[:, k], c[conn[:, list(sd)]].mean(axis=1)); np.add.at(cnt, es[:, k], 1)
+        return mid / cnt[:, None]
+
+    def f(X):
+        return np.stack([1 + 0.5 * X[:, 0] - 2 * X[:, 1], -0.25 * X[:, 0] + X[:, dim - 1]] + ([0.7 * X[:, 1] - X[:, 2]] if dim == 3 else []), axis=1)
+    u = np.concatenate([f(side_centres(coords)).ravel(), np.zeros(conn.shape[0])])
+    got = tools.interpolateCRToLagrange(u, coords, conn, es, n_side)
+    interior = np.all((coords0 > 1e-9) & (coords0 < 1 - 1e-9), axis=1)
+    assert interior.sum() > 0 and np.abs(got - f(coords))[interior].max() < 1e-13
+    one = np.concatenate([np.ones(n_side * dim), np.zeros(conn.shape[0])])
+    assert np.abs(tools.interpolateCRToLagrange(one, coords, conn, es, n_side) - 1.0).max() < 1e-14
+    # (2) brute force with the oracle's SCV volumes on a jittered grid
+    coords, conn = meshgen.make_mesh(elem, n, jitter=0.2, seed=4)
+    es, n_side = meshgen.element_sides(elem, conn)
+    rng = np.random.default_rng(1)
+    u = np.concatenate([rng.uniform(-1, 1, n_side * dim), np.zeros(conn.shape[0])])
+    got = tools.interpolateCRToLagrange(u, coords, conn, es, n_side)
+    ref = np.zeros((coords.shape[0], dim)); vs = np.zeros(coords.shape[0])
+    rc = np.array(meshgen_ref_corners(elem), float)
+    for e in range(conn.shape[0]):
+        g = ora.fv1_geometry(ora.ELEM[elem], coords[conn[e]])
+        for i in range(conn.shape[1]):
+            N = tools._cr_shapes_tensor(dim, 0.25 + 0.5 * rc[i])
+            val = sum(N[s] * u[es[e, s] * dim:(es[e, s] + 1) * dim] for s in range(es.shape[1]))
+            ref[conn[e, i]] += g["vol"][i] * val; vs[conn[e, i]] += g["vol"][i]
+    assert np.allclose(got, ref / vs[:, None], atol=1e-13)
+
+
+def meshgen_ref_corners(elem):
+    return {"quad": [(0, 0), (1, 0), (1, 1), (0, 1)],
+            "hex": [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]}[elem]
