@@ -194,6 +194,7 @@ _REF_CORNERS = {
     "quad": np.array([(0, 0), (1, 0), (1, 1), (0, 1)], dtype=np.float64),
     "tet": np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], dtype=np.float64),
     "hex": np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)], dtype=np.float64),
+    "prism": np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (0, 1, 1)], dtype=np.float64),
 }
 
 
@@ -203,6 +204,11 @@ def _lagrange(elem, xi):
     if elem in ("tri", "tet"):
         N = np.concatenate([[1.0 - xi.sum()], xi])
         dN = np.vstack([-np.ones(len(xi)), np.eye(len(xi))])
+        return N, dN
+    if elem == "prism":                                    # P1 on the triangle x P1 along the axis
+        lam, dl, z = np.array([1.0 - xi[0] - xi[1], xi[0], xi[1]]), np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]]), xi[2]
+        N = np.concatenate([lam * (1 - z), lam * z])
+        dN = np.vstack([np.hstack([dl * (1 - z), -lam[:, None]]), np.hstack([dl * z, lam[:, None]])])
         return N, dN
     f = np.where(rc > 0.5, xi, 1.0 - xi)                   # [nsh][dim] factors
     sg = np.where(rc > 0.5, 1.0, -1.0)

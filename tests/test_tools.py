@@ -119,7 +119,7 @@ def test_interpolate_cr_to_lagrange(elem):
     assert np.allclose(tools.interpolateCRToLagrange(uc, coords, conn, es, n_side), [0.7, -0.2, 0.4][:dim], atol=1e-13)
 
 
-@pytest.mark.parametrize("elem", ["tri", "quad", "tet", "hex"])
+@pytest.mark.parametrize("elem", ["tri", "quad", "tet", "hex", "prism"])
 def test_drag_lift_on_analytic_fields(elem):
     """DragLift mirror (navier_stokes_tools.h:981-1228) on fields the P1 / Q1 space holds exactly: linear pressure over the whole
     outer boundary of the unit box, Couette shear on the bottom wall"""
