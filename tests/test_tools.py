@@ -190,3 +190,27 @@ def test_interpolate_cr_to_lagrange_on_quadrilaterals_and_hexahedra(ora, elem, n
 def meshgen_ref_corners(elem):
     return {"quad": [(0, 0), (1, 0), (1, 1), (0, 1)],
             "hex": [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]}[elem]
+
+
+@pytest.mark.parametrize("elem", ["quad", "hex"])
+def test_rotated_cr_shapes_are_nodal_at_the_side_centres(ora, elem):
+    """the coefficient table of the rotated bi- / trilinear Crouzeix-Raviart shapes (the same rationals as in csrc/ns_fvcr_q.cuh):
+    N_s(centre of side t) = delta_st, partition of unity, span {1, x, y, (z,) x^2 - y^2 (, y^2 - z^2)} -- and the oracle, which obtains
+    its coefficients by inverting the Vandermonde matrix numerically, evaluates the same functions at its SCVF ips"""
+    rc = np.array(meshgen_ref_corners(elem), float)
+    dim = rc.shape[1]
+    sides = meshgen.SIDES[elem]
+    for t, sd in enumerate(sides):
+        N = tools._cr_shapes_tensor(dim, rc[list(sd)].mean(axis=0))
+        assert np.allclose(N, np.eye(len(sides))[t], atol=1e-15)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        assert abs(tools._cr_shapes_tensor(dim, rng.uniform(0, 1, dim)).sum() - 1.0) < 1e-14
+    # x^2 + y^2 (+ z^2) is NOT in the span, x^2 - y^2 is: interpolate it from the side centres and compare at a point
+    f = lambda p: p[0] ** 2 - p[1] ** 2
+    p = rng.uniform(0, 1, dim)
+    vals = np.array([f(rc[list(sd)].mean(axis=0)) for sd in sides])
+    assert abs(tools._cr_shapes_tensor(dim, p) @ vals - f(p)) < 1e-14
+    g = ora.cr_geometry(ora.ELEM[elem], rc)
+    for ip in range(g["nip"]):
+        assert np.allclose(g["shape"][ip], tools._cr_shapes_tensor(dim, g["lip"][ip]), atol=1e-14)
