@@ -68,6 +68,23 @@ def test_unit_cube_fixture(ora):
     assert np.allclose(np.linalg.norm(g["normal"], axis=1), 0.25)
 
 
+def test_unit_prism_fixture(ora):
+    """hand-derived: reference prism (volume 1/2). SCVF of edge (0, 1) = rectangle [edge midpoint (1/2, 0, 0), bottom-triangle centre
+    (1/3, 1/3, 0), barycentre (1/3, 1/3, 1/2), centre of the quadrilateral y = 0 (1/2, 0, 1/2)]: ip = (5/12, 1/6, 1/4), area vector
+    (1/6, 1/12, 0) pointing from corner 0 to corner 1; every SCV holds 1/12; the vertical edge (0, 3) has the SCVF [edge midpoint,
+    centres of the quadrilaterals y = 0 and x = 0, barycentre] with normal (0, 0, 1/6)"""
+    g = ora.fv1_geometry(ora.PRISM, jittered_ref_element("prism", amp=0.0))
+    assert g["nsh"] == 6 and g["nip"] == 9
+    assert list(g["frm"]) == [0, 1, 2, 0, 1, 2, 3, 4, 5] and list(g["to"]) == [1, 2, 0, 3, 4, 5, 4, 5, 3]
+    assert np.allclose(g["xip"][0], [5 / 12, 1 / 6, 1 / 4]) and np.allclose(g["normal"][0], [1 / 6, 1 / 12, 0])
+    assert np.allclose(g["vol"], 1 / 12)
+    lam = np.array([5 / 12, 5 / 12, 1 / 6])
+    assert np.allclose(g["shape"][0], np.concatenate([0.75 * lam, 0.25 * lam]))
+    # edge (0, 3): corners (0, 0, 1/2), (1/2, 0, 1/2), (1/3, 1/3, 1/2), (0, 1/2, 1/2) -> planar, area 1/2 |(1/3, 1/3) x (-1/2, 1/2)| = 1/6
+    assert np.allclose(g["xip"][3], [5 / 24, 5 / 24, 1 / 2]) and np.allclose(g["normal"][3], [0, 0, 1 / 6])
+    assert np.isclose(g["c0c2sq"][3], 2 / 9)
+
+
 @pytest.mark.parametrize("elem", ELEMS)
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_fv1_geometry_invariants(ora, elem, seed):
