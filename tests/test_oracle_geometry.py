@@ -265,3 +265,20 @@ def test_cr_geometry(ora, elem):
             if g["to"][ip] == s:
                 tot -= g["normal"][ip]
         assert np.allclose(tot, 0, atol=1e-14)
+
+
+def test_cr_geometry_unit_square_and_cube_fixtures(ora):
+    """hand-derived CRFVGeometry values on the non-simplex reference elements: SCV = triangle / pyramid between a side and the
+    barycentre (1/4 of the square, 1/6 of the cube), outward unit side normals; SCVF of corner 0 of the square: segment (0, 0) ->
+    (1/2, 1/2) between side 0 (bottom) and side 3 (left), normal (-1/2, 1/2); SCVF of edge (0, 1) of the cube: triangle
+    (0,0,0), (1,0,0), (1/2,1/2,1/2) between side 0 (bottom) and side 1 (y = 0), area vector (0, -1/4, 1/4), ip (1/2, 1/6, 1/6)"""
+    q = ora.cr_geometry(ora.QUAD, jittered_ref_element("quad", amp=0.0))
+    assert q["nsh"] == 4 and q["nip"] == 4 and np.allclose(q["vol"], 0.25)
+    assert np.allclose(q["scv_normal"], [[0, -1], [1, 0], [0, 1], [-1, 0]])
+    assert (q["frm"][0], q["to"][0]) == (0, 3) and np.allclose(q["normal"][0], [-0.5, 0.5]) and np.allclose(q["xip"][0], [0.25, 0.25])
+    h = ora.cr_geometry(ora.HEX, jittered_ref_element("hex", amp=0.0))
+    assert h["nsh"] == 6 and h["nip"] == 12 and np.allclose(h["vol"], 1 / 6)
+    assert np.allclose(h["scv_normal"], [[0, 0, -1], [0, -1, 0], [1, 0, 0], [0, 1, 0], [-1, 0, 0], [0, 0, 1]])
+    assert (h["frm"][0], h["to"][0]) == (0, 1) and np.allclose(h["normal"][0], [0, -0.25, 0.25]) and np.allclose(h["xip"][0], [0.5, 1 / 6, 1 / 6])
+    # the rotated shapes at that ip: N_0 (bottom) = N_1 (y = 0) by symmetry, gradients sum to zero
+    assert np.isclose(h["shape"][0][0], h["shape"][0][1]) and np.abs(h["ggrad"][0].sum(axis=0)).max() < 1e-14
