@@ -2,7 +2,8 @@
 configuration with elements/s, algorithmic GB/s and the fraction of the measured HBM roofline. Not the contract bench
 (bench.py measures config 3 at the contract size); sizes here are the single-GPU points of §8d that fit comfortably.
 
-  python tools/config_bench.py [scale]     # scale 1.0 = sizes below"""
+  python tools/config_bench.py [scale]     # scale 1.0 = sizes below
+  NSB_CONFIGS=6,7,8,9 python tools/config_bench.py   # the element types added at the end of round 2 (FV1 prisms, FVCR quad / hex)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -93,6 +94,49 @@ def main():
       u = meshgen.state_taylor_green(coords, t=0.0)
       uo = meshgen.state_taylor_green(coords, t=-1e-2)
       fv1("config5 hex %d^3 FLOW+POSITIVE instationary (A + M defect)" % n, "hex", coords, conn, u, "positive", "flow", JD | capi.DEF_M, td=(uo, 1e-2), visc=1.0 / 1600)
+    extra(sc)
+
+
+def fvcr_generic(name, elem, coords, conn):
+    """FVCR on the given grid, FullUpwind, A + M defect (the measured operations of config 4)"""
+    JD = capi.JAC_A | capi.DEF_A
+    dim = coords.shape[1]
+    es, n_side = meshgen.element_sides(elem, conn)
+    rng = np.random.default_rng(4)
+    mean = [0.3, 0.0, 0.0][:dim]
+    u = np.concatenate([0.3 * rng.uniform(-1, 1, n_side * dim) + np.tile(mean, n_side), rng.uniform(-1, 1, conn.shape[0])])
+    disc = pkg.NavierStokesFVCR("u,v,w,p" if dim == 3 else "u,v,p", "Inner")
+    disc.set_kinematic_viscosity(1e-3); disc.set_upwind("full"); disc.set_defect_upwind(True)
+    disc.set_grid(elem, conn, coords, es, n_side)
+    disc.use_stream(torch.cuda.current_stream().cuda_stream)
+    ud = torch.from_numpy(u).cuda()
+    l0 = disc.launch_count
+    ms = timeit(disc, JD | capi.DEF_M, ud, None)
+    report(name, conn.shape[0], conn.shape[1], dim, coords.shape[0], disc.num_dofs, disc.nnz, 1, ms, (disc.launch_count - l0) // 8)
+    disc.close()
+
+
+def extra(sc):
+    """the element types added at the end of round 2 (NSB_CONFIGS=6,7,8,9): not BASELINE configurations, untuned kernels"""
+    JD = capi.JAC_A | capi.DEF_A
+    sel = set(int(x) for x in os.environ.get("NSB_CONFIGS", "").split(",") if x)
+    if 6 in sel:
+        n = int(96 * sc)
+        coords, conn = meshgen.prism_grid(n, n, n)
+        fv1("extra6 prism %d^3 x2 LPS+FIELDS (element kernel, coloured)" % n, "prism", coords, conn, meshgen.state_vortex3d(coords, seed=3), "lps", "fields", JD)
+    if 7 in sel:
+        n = int(96 * sc)
+        coords, conn = meshgen.prism_grid(n, n, n, lo=(0, 0, 0), hi=(2 * np.pi,) * 3)
+        u, uo = meshgen.state_taylor_green(coords, t=0.0), meshgen.state_taylor_green(coords, t=-1e-2)
+        fv1("extra7 prism %d^3 x2 FLOW+POSITIVE instationary (A + M defect)" % n, "prism", coords, conn, u, "positive", "flow", JD | capi.DEF_M, td=(uo, 1e-2), visc=1.0 / 1600)
+    if 8 in sel:
+        n = int(2048 * sc)
+        coords, conn = meshgen.quad_grid(n, n, jitter=0.2, seed=4)
+        fvcr_generic("extra8 quad %d^2 FVCR FULL (A + M defect)" % n, "quad", coords, conn)
+    if 9 in sel:
+        n = int(128 * sc)
+        coords, conn = meshgen.hex_grid(n, n, n, jitter=0.2, seed=4)
+        fvcr_generic("extra9 hex %d^3 FVCR FULL (A + M defect)" % n, "hex", coords, conn)
 
 
 def fvcr4(n):
