@@ -6,6 +6,7 @@ disc.py    host-side mirror of NavierStokesFV1 / NavierStokesFVCR (names, setter
 meshgen.py synthetic grids / states of the BASELINE.json configurations
 partition.py  element partition + interface lists for the multi-GPU path
 cr_reorder.py host mirror of OrderCRCuthillMcKee (FVCR dof ordering, solver-side preprocessing)
+cr_ilut.py    host mirror of the CRILUT preconditioner (reference algorithm on the host, not a device solver)
 """
 from . import _capi as capi                                   # noqa: F401
 from .disc import (NavierStokes, NavierStokesFV1, NavierStokesFVCR, UGError,            # noqa: F401
@@ -16,3 +17,4 @@ from .disc import (NavierStokes, NavierStokesFV1, NavierStokesFVCR, UGError,    
                    NavierStokesFV1WithoutStabilization, NavierStokesWall, NavierStokesInflowFV1, NavierStokesNoNormalStressOutflowFV1,
                    NavierStokesNoNormalStressOutflow, FV1SmagorinskyTurbViscData, DiscConstraintFVCR, ThetaTimeStep)
 from .cr_reorder import OrderCRCuthillMcKee                    # noqa: F401,E402
+from .cr_ilut import CRILUTPreconditioner as CRILUT             # noqa: F401,E402
